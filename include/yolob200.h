@@ -1,0 +1,157 @@
+/*
+ * yolob200.h - C ABI of the B200-native YOLO forward / NMS engine.
+ *
+ * This is the drop-in boundary for the hot path of IntptrMax/YoloSharp (reference
+ * @16dc3cd, paths below relative to /root/reference/YoloSharp).  The reference has no
+ * FFI of its own; these entry points are what a C# `[DllImport("yolob200")]` shim (see
+ * INTEGRATION.md) binds in place of the TorchSharp calls at the seams listed per function.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 (YB_OK) or a negative yb_status and never
+ *     throws; the message for the last failure on the calling thread is yb_last_error().
+ *   - "dev" pointers are CUDA device pointers on the engine's device; the caller (TorchSharp /
+ *     PyTorch tensors) owns all input/output buffers, the engine owns weights + workspace.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - one engine = one device, not re-entrant (the reference runs the model on the caller's
+ *     thread only, Models/YoloBaseTaskModel.cs:19).
+ */
+#ifndef YOLOB200_H
+#define YOLOB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YB_ABI_VERSION 1
+
+typedef enum {
+  YB_OK = 0,
+  YB_ERR_INVALID_ARG = -1,   /* reference: ArgumentException (e.g. Utils/Ops.cs:248-255) */
+  YB_ERR_NOT_IMPLEMENTED = -2, /* reference: NotImplementedException */
+  YB_ERR_CUDA = -3,
+  YB_ERR_STATE = -4,         /* call order violated (e.g. forward before finalize) */
+  YB_ERR_MISSING_WEIGHT = -5,
+  YB_ERR_SHAPE = -6,
+  YB_ERR_NO_DEVICE = -7
+} yb_status;
+
+/* Types/YoloTypes.cs: YoloType / YoloSize / TaskType */
+typedef enum { YB_ARCH_V8 = 8, YB_ARCH_V11 = 11 } yb_arch;
+typedef enum { YB_SIZE_N = 0, YB_SIZE_S = 1, YB_SIZE_M = 2, YB_SIZE_L = 3, YB_SIZE_X = 4 } yb_size;
+typedef enum { YB_TASK_DETECT = 0, YB_TASK_SEGMENT = 1 } yb_task;
+
+/* arithmetic mode of the network body */
+typedef enum {
+  YB_PREC_F32 = 0, /* parity mode: fp32 storage + fp32 FMA (matches the fp32 oracle to ~1e-5) */
+  YB_PREC_F16 = 1  /* throughput mode: fp16 NHWC storage, tcgen05 tensor-core MMA, fp32 accumulate */
+} yb_precision;
+
+/* element types of caller buffers; values are torch ScalarType codes as stored in the
+ * reference's .bin checkpoints (Utils/Lib.cs:38) */
+typedef enum { YB_U8 = 0, YB_F16 = 5, YB_F32 = 6, YB_BF16 = 15 } yb_dtype;
+
+typedef struct {
+  int32_t arch;       /* yb_arch   - Data/Config.cs YoloType */
+  int32_t size;       /* yb_size   - Data/Config.cs YoloSize (Models/Yolo.cs:45-49, 213-217) */
+  int32_t task;       /* yb_task */
+  int32_t nc;         /* number of classes (Config.NumberClass, default 80) */
+  int32_t reg_max;    /* DFL bins, 16 */
+  int32_t precision;  /* yb_precision */
+  int32_t device;     /* CUDA device ordinal */
+  int32_t max_batch;  /* workspace is planned for this many images */
+  int32_t height;     /* input H, multiple of 32 (Models/Detector.cs:35-41 pads to it) */
+  int32_t width;      /* input W, multiple of 32 */
+  int32_t flags;      /* YB_FLAG_* */
+} yb_config;
+
+#define YB_FLAG_NO_TCGEN05 1  /* F16 mode: use the CUDA-core fp16 kernels instead of tcgen05 (debug) */
+#define YB_FLAG_NO_GRAPH   2  /* do not capture the forward into a CUDA graph */
+
+typedef struct yb_engine yb_engine;
+
+/* ABI / build info. */
+int32_t yb_abi_version(void);
+const char* yb_build_info(void);
+const char* yb_last_error(void);
+
+/* Replaces: `new Yolo.Yolov8(nc, yoloSize:..)` / `Yolov11` / `Yolov8Segment` construction
+ * (Models/Yolo.cs:27-39, 204-207, 339-342; Models/Detector.cs:12-25). */
+int32_t yb_create(const yb_config* cfg, yb_engine** out);
+void yb_destroy(yb_engine* e);
+
+/* Number of anchors A and channels of the prediction tensor for the configured input size:
+ * pred is (B, 4+nc[+32], A) as produced by Detect._inference (Modules/Head.cs:204-208). */
+int32_t yb_num_anchors(const yb_engine* e);
+int32_t yb_pred_channels(const yb_engine* e);
+
+/* Replaces: `yolo.load_state_dict(state_dict)` (Models/YoloBaseTaskModel.cs:100).  `name` is a
+ * reference state_dict key (e.g. "model.0.conv.weight", "model.22.cv2.0.2.bias"); `data` is a
+ * HOST pointer to `ndim`-shaped row-major data of `dtype` (YB_F16 / YB_F32 / YB_BF16).
+ * Unknown names (num_batches_tracked, anchors, strides, dfl.conv.weight) are accepted and ignored. */
+int32_t yb_load_tensor(yb_engine* e, const char* name, int32_t dtype, int32_t ndim,
+                       const int64_t* shape, const void* data);
+
+/* Fold eval-mode BatchNorm (eps 1e-3, Modules/Convs.cs:41) into the conv weights, pack to the
+ * device layouts, build TMA descriptors.  Fails with YB_ERR_MISSING_WEIGHT naming the first
+ * absent tensor (the reference silently keeps random weights, YoloBaseTaskModel.cs:32-35; we do not). */
+int32_t yb_finalize_weights(yb_engine* e);
+
+/* Number of parameter/buffer tensors the engine expects, and their names (for host-side checks). */
+int32_t yb_num_expected_tensors(const yb_engine* e);
+const char* yb_expected_tensor_name(const yb_engine* e, int32_t i);
+
+/* Replaces: `yolo.forward(input).inference["boxes"]` [+ `["proto"]`] in eval mode
+ * (Models/Yolo.cs:92-134 -> Modules/Head.cs:89-115, 283-306).
+ *   in       dev, NCHW (B,3,H,W): YB_F32/YB_F16 already scaled to [0,1] (Detector.cs:41),
+ *            or YB_U8 raw pixels (the /255 is fused into the stem)
+ *   out_pred dev, float32 (B, 4+nc[+32], A): xywh in input pixels, class probabilities, mask coeffs
+ *   out_proto dev, float32 (B,32,H/4,W/4) for segment engines, else NULL */
+int32_t yb_forward(yb_engine* e, const void* in, int32_t in_dtype, int32_t batch,
+                   float* out_pred, float* out_proto, void* stream);
+
+/* Replaces: `Ops.non_max_suppression(prediction, conf_thres, iou_thres, .., max_det, nc, ..,
+ * max_nms, max_wh)` (Utils/Ops.cs:239-371), non-rotated, non-end2end path, incl. the
+ * torchvision.ops.nms call at :357.
+ *   pred     dev, float32 (B, C, A) with C = 4 + nc + extra (not modified: the reference's
+ *            in-place xywh->xyxy conversion is done on the fly)
+ *   dets     dev, float32 (B, max_det, 6+extra): x1,y1,x2,y2,conf,cls,extra.. score-descending;
+ *            rows >= counts[b] are zero
+ *   counts   dev, int32 (B)
+ *   keep_idx dev, int32 (B, max_det) original anchor index of each kept row (`keepi`), or NULL
+ * Errors: conf/iou outside [0,1] -> YB_ERR_INVALID_ARG (reference throws ArgumentException). */
+int32_t yb_nms(const float* pred, int32_t batch, int32_t channels, int32_t anchors, int32_t nc,
+               float conf_thres, float iou_thres, int32_t max_det, int32_t max_nms, int32_t max_wh,
+               float* dets, int32_t* counts, int32_t* keep_idx, void* stream);
+
+/* Replaces: `Ops.process_mask(proto[i], rows[:,6:], rows[:,:4], shape, upsample:true)`
+ * (Utils/Ops.cs:462-489, CUDA branch of crop_mask :437-447) for a whole batch.
+ *   proto  dev float32 (B,32,mh,mw);  dets/counts as written by yb_nms with extra == 32
+ *   masks  dev uint8 (B, max_det, H, W), 1 where mask > 0; rows >= counts[b] untouched */
+int32_t yb_masks(const float* proto, const float* dets, const int32_t* counts, int32_t batch,
+                 int32_t max_det, int32_t nm, int32_t mh, int32_t mw, int32_t height, int32_t width,
+                 uint8_t* masks, void* stream);
+
+/* Replaces: the body of `Detector.ImagePredict` (Models/Detector.cs:27-72) for a batch of
+ * equally sized images: HOST uint8 (B,3,H,W) RGB in, HOST detections out; H2D copy, /255,
+ * forward, NMS and D2H copy run on `stream` and the call returns after the results landed.
+ *   dets_host   float32 (B, max_det, 6[+32]);  counts_host int32 (B) */
+int32_t yb_predict_u8(yb_engine* e, const uint8_t* images_host, int32_t batch, float conf_thres,
+                      float iou_thres, int32_t max_det, float* dets_host, int32_t* counts_host,
+                      void* stream);
+
+/* Debug / profiling helpers (not part of the reference surface). */
+int32_t yb_num_ops(const yb_engine* e);
+/* copy the activation written by op `op_index` (NHWC -> NCHW float32 host buffer); returns
+ * channels*H*W per image through *chw (C,H,W) */
+int32_t yb_debug_read_activation(yb_engine* e, int32_t op_index, int32_t batch, float* host_out,
+                                 int64_t host_capacity, int32_t chw[3]);
+const char* yb_op_name(const yb_engine* e, int32_t op_index);
+/* number of kernel launches one yb_forward issues (for bench.py's gpu_launches) */
+int32_t yb_launches_per_forward(const yb_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLOB200_H */

@@ -151,12 +151,13 @@ def build(arch="v8", task="detect", size="n", nc=80):
     return cls(nc=nc, size=size)
 
 
-def synth_weights(model, seed=0, cls_bias=None):
+def synth_weights(model, seed=0, cls_bias=None, head_gain=1.0):
     """Seeded synthetic weights for sizes with no shipped checkpoint:
     conv ~ N(0, 2/fan_in) scaled down slightly so activations stay O(1) through ~60 layers,
     BN gamma U(0.5,1.5), beta N(0,0.1), running_mean N(0,0.1), running_var U(0.5,1.5);
     values are rounded through fp16 so an fp16-storage engine holds identical weights.
-    cls_bias: bias of the final class conv (controls how many anchors pass the conf filter)."""
+    cls_bias / head_gain: bias and weight gain of the final 1x1 convs (control how many anchors
+    pass the conf filter and how peaked the DFL distributions are)."""
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for name, mod in model.named_modules():
@@ -174,8 +175,12 @@ def synth_weights(model, seed=0, cls_bias=None):
                 mod.bias.copy_((torch.randn(c, generator=g) * 0.1).half().float())
                 mod.running_mean.copy_((torch.randn(c, generator=g) * 0.1).half().float())
                 mod.running_var.copy_((torch.rand(c, generator=g) + 0.5).half().float())
+        head = model.model[-1]
+        if head_gain != 1.0:  # spread the final logits so that NMS sees a realistic candidate set
+            for branch in (head.cv2, head.cv3):
+                for seq in branch:
+                    seq[-1].weight.copy_((seq[-1].weight * head_gain).half().float())
         if cls_bias is not None:
-            head = model.model[-1]
             for seq in head.cv3:
                 seq[-1].bias.fill_(float(torch.tensor(cls_bias).half()))
     return model

@@ -1,0 +1,94 @@
+// Shared declarations for the yolob200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+
+#include "yolob200.h"
+
+namespace yb {
+
+// A channel-slice view of an NHWC activation buffer: element (n,h,w,c) lives at
+// base[((n*H + h)*W + w) * pitch + coff + c].  Concat/chunk of the reference graph
+// (Modules/Block.cs:391-396) become views of one wider buffer - no copies.
+struct View {
+  void* base = nullptr;  // device pointer to the buffer start (element type = engine storage type)
+  int H = 0, W = 0;
+  int pitch = 0;  // channels of the whole buffer
+  int coff = 0;   // first channel of this view
+  int C = 0;      // channels of this view
+};
+
+enum Act { ACT_NONE = 0, ACT_SILU = 1 };
+
+struct ConvParams {
+  View in, out, res;  // res.base == nullptr -> no residual
+  View out2;          // optional second destination: nearest-2x upsampled copy (out2.base != nullptr)
+  const void* w;      // packed weights, layout depends on kernel
+  const float* bias;  // [Cout] fp32 (folded BN beta - mean*scale, or conv bias)
+  int B;
+  int Cin, Cout;
+  int k, stride, pad;
+  int Ho, Wo;
+  int act;
+};
+
+void set_error(const std::string& msg);
+
+#define YB_CUDA_CHECK(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::yb::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +   \
+                      __FILE__ + ":" + std::to_string(__LINE__));                            \
+      return YB_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+// ---- kernels_generic.cu : CUDA-core kernels, templated on storage type (float | __half) ----
+template <typename T>
+int launch_conv_generic(const ConvParams& p, cudaStream_t s);
+template <typename T>
+int launch_dwconv3x3(const ConvParams& p, cudaStream_t s);  // depthwise 3x3 s1 p1, w [9][C] fp32
+template <typename T>
+int launch_sppf_pool(const View& in, const View& out5, const View& out9, const View& out13, int B,
+                     cudaStream_t s);
+template <typename T>
+int launch_upsample2x(const View& in, const View& out, int B, cudaStream_t s);
+// network input (B,3,H,W) NCHW of dtype u8/f16/f32 -> NHWC T with pitch/coff from `out`
+template <typename T>
+int launch_input_to_nhwc(const void* in, int in_dtype, const View& out, int B, cudaStream_t s);
+// read back a view as NCHW fp32 (debug)
+template <typename T>
+int launch_view_to_nchw_f32(const View& in, float* out, int B, cudaStream_t s);
+
+// Head decode (Modules/Head.cs:204-223 + Block.cs:15-45 + Tal.cs:313-356):
+// box logits (64 ch) + class logits (nc ch) [+ mask coeffs] of one level, NHWC ->
+// rows [0,4) xywh*stride, [4,4+nc) sigmoid, [4+nc,..) coeffs of pred (B, Ctot, A), anchors
+// [a0, a0 + H*W) of this level.
+template <typename T>
+int launch_decode_level(const View& box, const View& cls, const View* coef, int B, int nc, int nm,
+                        int reg_max, float stride, int a0, int A, int Ctot, float* pred,
+                        cudaStream_t s);
+// proto (B,h,w,32) NHWC T -> (B,32,h,w) fp32
+template <typename T>
+int launch_proto_out(const View& in, float* out, int B, cudaStream_t s);
+
+// ---- conv_tc.cu : tcgen05 implicit-GEMM conv (fp16 storage, fp32 accumulate in TMEM) ----
+struct TcConvPlan;  // opaque: tensor maps + tiling for one conv layer
+TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err);
+void tc_conv_plan_destroy(TcConvPlan* plan);
+int tc_conv_launch(const TcConvPlan* plan, int B, cudaStream_t s);
+bool tc_conv_supported(const ConvParams& p);
+// stem: NCHW u8/f16/f32 input -> 3x3 s2 conv (Cin=3) + bias + SiLU -> NHWC fp16
+int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const float* w /*[27][Cout]*/,
+                    const float* bias, const View& out, cudaStream_t s);
+
+// ---- nms.cu ----
+int nms_launch(const float* pred, int B, int C, int A, int nc, float conf, float iou, int max_det,
+               int max_nms, int max_wh, float* dets, int* counts, int* keep_idx, cudaStream_t s);
+int masks_launch(const float* proto, const float* dets, const int* counts, int B, int max_det, int nm,
+                 int mh, int mw, int H, int W, uint8_t* masks, cudaStream_t s);
+
+}  // namespace yb

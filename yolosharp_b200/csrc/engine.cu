@@ -1,0 +1,805 @@
+// yolob200 engine: graph construction, weight ingest, workspace planning, forward, C ABI.
+//
+// The layer list and wiring follow the reference graph definitions
+// (Models/Yolo.cs:41-134 Yolov8, :209-257 Yolov11, :337-352 Yolov8Segment) and module
+// constructors (Modules/Block.cs, Modules/Head.cs); they are re-expressed as a flat list of
+// fused device ops over channel-slice views of NHWC buffers:
+//   Conv+BN+SiLU        -> one conv op (BN folded at load, SiLU in the epilogue)
+//   chunk / cat         -> producers write channel slices of one wider buffer
+//   Bottleneck shortcut -> residual read in the conv epilogue
+//   Upsample + Concat   -> copy into the consumer's concat slice
+//   SPPF 3x MaxPool     -> one shared-memory kernel writing three slices
+//   Detect tail         -> DFL + dist2bbox + sigmoid decode kernel per level
+#include <map>
+#include <memory>
+#include <vector>
+#include <cmath>
+#include <cstring>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace yb {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+struct VRef {  // view reference: buffer id + channel slice
+  int buf = -1, coff = 0, C = 0;
+};
+
+struct BufDesc {
+  int H, W, C;
+  size_t offset = 0;  // bytes into the arena
+};
+
+enum OpType { OP_CONV, OP_DWCONV, OP_POOL, OP_UPSAMPLE, OP_DECODE, OP_PROTO_OUT, OP_CONVT, OP_ATTN };
+
+struct OpDesc {
+  OpType type;
+  std::string name;  // reference module path ("model.2.m.0.cv1") or a descriptive tag
+  VRef in, out, res, out2, out3;
+  int k = 1, s = 1, act = ACT_SILU, cin = 0, cout = 0, groups = 1;
+  bool bn = true;        // Conv (conv+bn) vs plain Conv2d(bias)
+  // decode
+  int level = 0, a0 = 0;
+  float stride = 0;
+  VRef cls, coef;
+  // device weights
+  float* w_f32 = nullptr;   // generic layout [tap][Cin][Cout] (or [9][C] depthwise)
+  __half* w_f16 = nullptr;  // tensor-core layout [Cout][tap*Cin]
+  float* bias = nullptr;
+  TcConvPlan* plan = nullptr;
+  bool use_tc = false;
+};
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+}  // namespace yb
+
+using namespace yb;
+
+struct yb_engine {
+  yb_config cfg;
+  std::vector<BufDesc> bufs;
+  std::vector<OpDesc> ops;
+  std::map<std::string, HostTensor> host;
+  std::vector<std::string> expected;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  bool finalized = false;
+  int esize = 4;  // bytes per activation element
+  int A = 0, pred_c = 0;
+  int widths[5];
+  int ch[3];
+  VRef input_nhwc;  // generic path: converted network input (3 channels)
+  VRef proto_view;
+  bool has_stem_tc = false;
+  // staging for yb_predict_u8
+  uint8_t* stage_in = nullptr;
+  float* stage_pred = nullptr;
+  float* stage_dets = nullptr;
+  int* stage_counts = nullptr;
+  int stage_max_det = 0;
+  // CUDA graph cache
+  struct GraphKey {
+    const void* in; int dtype; int B; float* pred; float* proto;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(in, dtype, B, pred, proto) < std::tie(o.in, o.dtype, o.B, o.pred, o.proto);
+    }
+  };
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::map<GraphKey, int> seen;
+  cudaStream_t capture_stream = nullptr;
+  std::vector<void*> dev_allocs;
+};
+
+namespace yb {
+
+// ------------------------------------------------------------------------------------------
+// Graph builder
+// ------------------------------------------------------------------------------------------
+struct Builder {
+  yb_engine* e;
+  VRef new_buf(int H, int W, int C) {
+    e->bufs.push_back({H, W, C, 0});
+    return VRef{(int)e->bufs.size() - 1, 0, C};
+  }
+  static VRef slice(VRef v, int coff, int C) { return VRef{v.buf, v.coff + coff, C}; }
+  int H(VRef v) const { return e->bufs[v.buf].H; }
+  int W(VRef v) const { return e->bufs[v.buf].W; }
+
+  // Convs.Conv (Modules/Convs.cs:36-56) or plain Conv2d(bias) when bn == false
+  void conv(const std::string& name, VRef in, VRef out, int k, int s, int act = ACT_SILU, bool bn = true,
+            VRef res = VRef(), int groups = 1) {
+    OpDesc op;
+    op.type = groups == 1 ? OP_CONV : OP_DWCONV;
+    op.name = name;
+    op.in = in; op.out = out; op.res = res;
+    op.k = k; op.s = s; op.act = act; op.cin = in.C; op.cout = out.C; op.bn = bn; op.groups = groups;
+    e->ops.push_back(op);
+    if (bn) {
+      for (const char* sfx : {".conv.weight", ".bn.weight", ".bn.bias", ".bn.running_mean", ".bn.running_var"})
+        e->expected.push_back(name + sfx);
+    } else {
+      e->expected.push_back(name + ".weight");
+      e->expected.push_back(name + ".bias");
+    }
+  }
+
+  // Block.Bottleneck (Block.cs:572-607)
+  void bottleneck(const std::string& name, VRef in, VRef out, bool shortcut, int k0, int k1, double ex) {
+    const int c_ = (int)(out.C * ex);
+    VRef t = new_buf(H(in), W(in), c_);
+    conv(name + ".cv1", in, t, k0, 1);
+    conv(name + ".cv2", t, out, k1, 1, ACT_SILU, true, (shortcut && in.C == out.C) ? in : VRef());
+  }
+
+  // Block.C2f (Block.cs:371-398): cv1 -> 2 chunks; each Bottleneck(c,c,e=1.0) appends a slice; cv2 on the cat
+  void c2f(const std::string& name, VRef in, VRef out, int n, bool shortcut) {
+    const int c = (int)(out.C * 0.5);
+    VRef cat = new_buf(H(in), W(in), (2 + n) * c);
+    conv(name + ".cv1", in, slice(cat, 0, 2 * c), 1, 1);
+    for (int i = 0; i < n; i++)
+      bottleneck(name + ".m." + std::to_string(i), slice(cat, (1 + i) * c, c), slice(cat, (2 + i) * c, c), shortcut,
+                 3, 3, 1.0);
+    conv(name + ".cv2", cat, out, 1, 1);
+  }
+
+  // Block.C3k (Block.cs:611-620 over C3 :404-441): cv3(cat(m(cv1 x), cv2 x)), m = n x Bottleneck(k 3,3 e 1.0)
+  void c3k(const std::string& name, VRef in, VRef out, int n, bool shortcut) {
+    const int c_ = (int)(out.C * 0.5);
+    VRef cat = new_buf(H(in), W(in), 2 * c_);
+    VRef cur = new_buf(H(in), W(in), c_);
+    conv(name + ".cv1", in, cur, 1, 1);
+    for (int i = 0; i < n; i++) {
+      VRef nxt = (i == n - 1) ? slice(cat, 0, c_) : new_buf(H(in), W(in), c_);
+      bottleneck(name + ".m." + std::to_string(i), cur, nxt, shortcut, 3, 3, 1.0);
+      cur = nxt;
+    }
+    conv(name + ".cv2", in, slice(cat, c_, c_), 1, 1);
+    conv(name + ".cv3", cat, out, 1, 1);
+  }
+
+  // Block.C3k2 (Block.cs:623-661)
+  void c3k2(const std::string& name, VRef in, VRef out, int n, bool use_c3k, double ex, bool shortcut = true) {
+    const int c = (int)(out.C * ex);
+    VRef cat = new_buf(H(in), W(in), (2 + n) * c);
+    conv(name + ".cv1", in, slice(cat, 0, 2 * c), 1, 1);
+    for (int i = 0; i < n; i++) {
+      VRef bi = slice(cat, (1 + i) * c, c), bo = slice(cat, (2 + i) * c, c);
+      if (use_c3k) c3k(name + ".m." + std::to_string(i), bi, bo, 2, shortcut);
+      else bottleneck(name + ".m." + std::to_string(i), bi, bo, shortcut, 3, 3, 0.5);
+    }
+    conv(name + ".cv2", cat, out, 1, 1);
+  }
+
+  // Block.SPPF (Block.cs:236-282): cv1 has no activation (reference quirk, :257)
+  void sppf(const std::string& name, VRef in, VRef out) {
+    const int c_ = in.C / 2;
+    VRef cat = new_buf(H(in), W(in), 4 * c_);
+    conv(name + ".cv1", in, slice(cat, 0, c_), 1, 1, ACT_NONE);
+    OpDesc op;
+    op.type = OP_POOL;
+    op.name = name + ".m";
+    op.in = slice(cat, 0, c_);
+    op.out = slice(cat, c_, c_);
+    op.out2 = slice(cat, 2 * c_, c_);
+    op.out3 = slice(cat, 3 * c_, c_);
+    e->ops.push_back(op);
+    conv(name + ".cv2", cat, out, 1, 1);
+  }
+
+  void upsample(const std::string& name, VRef in, VRef out) {
+    OpDesc op;
+    op.type = OP_UPSAMPLE;
+    op.name = name;
+    op.in = in; op.out = out;
+    e->ops.push_back(op);
+  }
+};
+
+static int build_graph(yb_engine* e) {
+  const yb_config& c = e->cfg;
+  Builder b{e};
+  const int H = c.height, W = c.width;
+  int w[5];
+  int n3[3];  // C2f depths
+  bool v11 = c.arch == YB_ARCH_V11;
+  bool use_c3k = false;
+  int n11 = 1;
+  if (!v11) {
+    // Yolo.cs:45-49
+    static const float dm[5] = {0.34f, 0.34f, 0.67f, 1.0f, 1.0f};
+    static const float wm[5] = {0.25f, 0.5f, 0.75f, 1.0f, 1.25f};
+    static const int mc[5] = {1024, 1024, 576, 512, 640};
+    const int base[5] = {64, 128, 256, 512, 1024};
+    for (int i = 0; i < 5; i++) w[i] = std::min((int)(base[i] * wm[c.size]), mc[c.size]);
+    const int d[3] = {3, 6, 9};
+    for (int i = 0; i < 3; i++) n3[i] = (int)(d[i] * dm[c.size]);
+  } else {
+    // Yolo.cs:213-217
+    static const float dm[5] = {0.5f, 0.5f, 0.5f, 1.0f, 1.0f};
+    static const float wm[5] = {0.25f, 0.5f, 1.0f, 1.0f, 1.5f};
+    static const int mc[5] = {1024, 1024, 512, 512, 768};
+    static const bool ck[5] = {false, false, true, true, true};
+    const int base[5] = {64, 128, 256, 512, 1024};
+    for (int i = 0; i < 5; i++) w[i] = std::min((int)(base[i] * wm[c.size]), mc[c.size]);
+    n11 = (int)(2 * dm[c.size]);
+    use_c3k = ck[c.size];
+  }
+  for (int i = 0; i < 5; i++) e->widths[i] = w[i];
+  e->ch[0] = w[2]; e->ch[1] = w[3]; e->ch[2] = w[4];
+
+  // generic path reads the network input through an NHWC copy (3 channels)
+  e->input_nhwc = b.new_buf(H, W, 3);
+  auto M = [](int i) { return "model." + std::to_string(i); };
+
+  VRef p3, p4, p5;  // Detect inputs
+  if (!v11) {
+    // concat buffers (Yolo.cs:70-84; Concat order = [x, saved])
+    VRef cat11 = b.new_buf(H / 16, W / 16, w[4] + w[3]);  // [up(L9), L6]
+    VRef cat14 = b.new_buf(H / 8, W / 8, w[3] + w[2]);    // [up(L12), L4]
+    VRef cat17 = b.new_buf(H / 16, W / 16, w[2] + w[3]);  // [L16, L12]
+    VRef cat20 = b.new_buf(H / 32, W / 32, w[3] + w[4]);  // [L19, L9]
+    VRef l0 = b.new_buf(H / 2, W / 2, w[0]);
+    b.conv(M(0), e->input_nhwc, l0, 3, 2);
+    VRef l1 = b.new_buf(H / 4, W / 4, w[1]);
+    b.conv(M(1), l0, l1, 3, 2);
+    VRef l2 = b.new_buf(H / 4, W / 4, w[1]);
+    b.c2f(M(2), l1, l2, n3[0], true);
+    VRef l3 = b.new_buf(H / 8, W / 8, w[2]);
+    b.conv(M(3), l2, l3, 3, 2);
+    VRef l4 = Builder::slice(cat14, w[3], w[2]);
+    b.c2f(M(4), l3, l4, n3[1], true);
+    VRef l5 = b.new_buf(H / 16, W / 16, w[3]);
+    b.conv(M(5), l4, l5, 3, 2);
+    VRef l6 = Builder::slice(cat11, w[4], w[3]);
+    b.c2f(M(6), l5, l6, n3[1], true);
+    VRef l7 = b.new_buf(H / 32, W / 32, w[4]);
+    b.conv(M(7), l6, l7, 3, 2);
+    VRef l8 = b.new_buf(H / 32, W / 32, w[4]);
+    b.c2f(M(8), l7, l8, n3[0], true);
+    VRef l9 = Builder::slice(cat20, w[3], w[4]);
+    b.sppf(M(9), l8, l9);
+    b.upsample(M(10), l9, Builder::slice(cat11, 0, w[4]));
+    VRef l12 = Builder::slice(cat17, w[2], w[3]);
+    b.c2f(M(12), cat11, l12, n3[0], false);
+    b.upsample(M(13), l12, Builder::slice(cat14, 0, w[3]));
+    VRef l15 = b.new_buf(H / 8, W / 8, w[2]);
+    b.c2f(M(15), cat14, l15, n3[0], false);
+    b.conv(M(16), l15, Builder::slice(cat17, 0, w[2]), 3, 2);
+    VRef l18 = b.new_buf(H / 16, W / 16, w[3]);
+    b.c2f(M(18), cat17, l18, n3[0], false);
+    b.conv(M(19), l18, Builder::slice(cat20, 0, w[3]), 3, 2);
+    VRef l21 = b.new_buf(H / 32, W / 32, w[4]);
+    b.c2f(M(21), cat20, l21, n3[0], false);
+    p3 = l15; p4 = l18; p5 = l21;
+  } else {
+    set_error("YOLOv11 graph is not implemented in this build");
+    return YB_ERR_NOT_IMPLEMENTED;
+  }
+
+  // ---- Detect / Segment head (Head.cs:35-53, 247-259) ----
+  const int head = v11 ? 23 : 22;
+  const std::string hn = M(head);
+  const int nc = c.nc, rm = c.reg_max;
+  const int c2 = std::max(16, std::max(e->ch[0] / 4, rm * 4));
+  const int c3 = std::max(e->ch[0], std::min(nc, 100));
+  const bool seg = c.task == YB_TASK_SEGMENT;
+  const int nm = 32;
+  const int c4 = std::max(e->ch[0] / 4, nm);
+  VRef feats[3] = {p3, p4, p5};
+  const int strides[3] = {8, 16, 32};
+  e->A = 0;
+  for (int l = 0; l < 3; l++) e->A += (H / strides[l]) * (W / strides[l]);
+  e->pred_c = 4 + nc + (seg ? nm : 0);
+  int a0 = 0;
+  for (int l = 0; l < 3; l++) {
+    const int hl = H / strides[l], wl = W / strides[l];
+    const std::string L = std::to_string(l);
+    VRef t1 = b.new_buf(hl, wl, c2), t2 = b.new_buf(hl, wl, c2), box = b.new_buf(hl, wl, 4 * rm);
+    b.conv(hn + ".cv2." + L + ".0", feats[l], t1, 3, 1);
+    b.conv(hn + ".cv2." + L + ".1", t1, t2, 3, 1);
+    b.conv(hn + ".cv2." + L + ".2", t2, box, 1, 1, ACT_NONE, false);
+    VRef u1 = b.new_buf(hl, wl, c3), u2 = b.new_buf(hl, wl, c3), cls = b.new_buf(hl, wl, nc);
+    b.conv(hn + ".cv3." + L + ".0", feats[l], u1, 3, 1);
+    b.conv(hn + ".cv3." + L + ".1", u1, u2, 3, 1);
+    b.conv(hn + ".cv3." + L + ".2", u2, cls, 1, 1, ACT_NONE, false);
+    VRef coef;
+    if (seg) {
+      VRef m1 = b.new_buf(hl, wl, c4), m2 = b.new_buf(hl, wl, c4);
+      coef = b.new_buf(hl, wl, nm);
+      b.conv(hn + ".cv4." + L + ".0", feats[l], m1, 3, 1);
+      b.conv(hn + ".cv4." + L + ".1", m1, m2, 3, 1);
+      b.conv(hn + ".cv4." + L + ".2", m2, coef, 1, 1, ACT_NONE, false);
+    }
+    OpDesc op;
+    op.type = OP_DECODE;
+    op.name = hn + ".decode." + L;
+    op.in = box; op.cls = cls; op.coef = coef;
+    op.level = l; op.a0 = a0; op.stride = (float)strides[l];
+    e->ops.push_back(op);
+    a0 += hl * wl;
+  }
+  if (seg) {
+    set_error("segment head (Proto) is not implemented in this build");
+    return YB_ERR_NOT_IMPLEMENTED;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Weights
+// ------------------------------------------------------------------------------------------
+static const HostTensor* find_tensor(yb_engine* e, const std::string& name) {
+  auto it = e->host.find(name);
+  if (it == e->host.end()) {
+    set_error("missing weight tensor: " + name);
+    return nullptr;
+  }
+  return &it->second;
+}
+
+static float round_f16(float v) { return __half2float(__float2half_rn(v)); }
+
+template <typename T>
+static int upload(yb_engine* e, const std::vector<T>& h, T** dptr) {
+  YB_CUDA_CHECK(cudaMalloc((void**)dptr, h.size() * sizeof(T)));
+  e->dev_allocs.push_back(*dptr);
+  YB_CUDA_CHECK(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int finalize_conv(yb_engine* e, OpDesc& op) {
+  const bool f16 = e->cfg.precision == YB_PREC_F16;
+  const int taps = op.k * op.k;
+  const int cing = op.cin / op.groups;  // input channels per group
+  const HostTensor* W = find_tensor(e, op.name + (op.bn ? ".conv.weight" : ".weight"));
+  if (!W) return YB_ERR_MISSING_WEIGHT;
+  if ((int64_t)W->data.size() != (int64_t)op.cout * cing * taps) {
+    set_error("shape mismatch for " + op.name + " weight");
+    return YB_ERR_SHAPE;
+  }
+  std::vector<double> scale(op.cout, 1.0);
+  std::vector<float> bias(op.cout, 0.f);
+  if (op.bn) {
+    const HostTensor *g = find_tensor(e, op.name + ".bn.weight"), *bt = find_tensor(e, op.name + ".bn.bias"),
+                     *mu = find_tensor(e, op.name + ".bn.running_mean"),
+                     *var = find_tensor(e, op.name + ".bn.running_var");
+    if (!g || !bt || !mu || !var) return YB_ERR_MISSING_WEIGHT;
+    if ((int)g->data.size() != op.cout || (int)bt->data.size() != op.cout || (int)mu->data.size() != op.cout ||
+        (int)var->data.size() != op.cout) {
+      set_error("shape mismatch for " + op.name + " bn");
+      return YB_ERR_SHAPE;
+    }
+    for (int o = 0; o < op.cout; o++) {
+      // eval-mode BatchNorm2d, eps = 1e-3 (Modules/Convs.cs:41)
+      scale[o] = (double)g->data[o] / std::sqrt((double)var->data[o] + 1e-3);
+      bias[o] = (float)((double)bt->data[o] - (double)mu->data[o] * scale[o]);
+    }
+  } else {
+    const HostTensor* bb = find_tensor(e, op.name + ".bias");
+    if (!bb) return YB_ERR_MISSING_WEIGHT;
+    if ((int)bb->data.size() != op.cout) {
+      set_error("shape mismatch for " + op.name + " bias");
+      return YB_ERR_SHAPE;
+    }
+    for (int o = 0; o < op.cout; o++) bias[o] = bb->data[o];
+  }
+  // folded weight (o, ci, kh, kw) -> fp32; in F16 mode rounded through fp16 so that the CUDA-core
+  // twin and the tensor-core kernel see identical operand values
+  std::vector<float> wf((size_t)op.cout * cing * taps);
+  for (int o = 0; o < op.cout; o++)
+    for (int ci = 0; ci < cing; ci++)
+      for (int t = 0; t < taps; t++) {
+        float v = (float)((double)W->data[((size_t)o * cing + ci) * taps + t] * scale[o]);
+        if (f16) v = round_f16(v);
+        wf[((size_t)o * cing + ci) * taps + t] = v;
+      }
+  if (upload(e, bias, &op.bias)) return YB_ERR_CUDA;
+  if (op.type == OP_DWCONV) {
+    if (op.groups != op.cin || op.cin != op.cout || op.k != 3 || op.s != 1) {
+      set_error("only depthwise 3x3 s1 grouped convs are supported: " + op.name);
+      return YB_ERR_NOT_IMPLEMENTED;
+    }
+    std::vector<float> g9((size_t)9 * op.cout);
+    for (int o = 0; o < op.cout; o++)
+      for (int t = 0; t < 9; t++) g9[(size_t)t * op.cout + o] = wf[(size_t)o * 9 + t];
+    return upload(e, g9, &op.w_f32);
+  }
+  // generic layout [tap][Cin][Cout]
+  std::vector<float> wg((size_t)taps * op.cin * op.cout);
+  for (int o = 0; o < op.cout; o++)
+    for (int ci = 0; ci < op.cin; ci++)
+      for (int t = 0; t < taps; t++)
+        wg[((size_t)t * op.cin + ci) * op.cout + o] = wf[((size_t)o * op.cin + ci) * taps + t];
+  if (upload(e, wg, &op.w_f32)) return YB_ERR_CUDA;
+  if (f16) {
+    // tensor-core layout [Cout][tap][Cin] (K-major rows for the UMMA B operand)
+    std::vector<__half> wh((size_t)op.cout * taps * op.cin);
+    for (int o = 0; o < op.cout; o++)
+      for (int t = 0; t < taps; t++)
+        for (int ci = 0; ci < op.cin; ci++)
+          wh[((size_t)o * taps + t) * op.cin + ci] = __float2half_rn(wf[((size_t)o * op.cin + ci) * taps + t]);
+    if (upload(e, wh, &op.w_f16)) return YB_ERR_CUDA;
+  }
+  return 0;
+}
+
+static View make_view(const yb_engine* e, VRef r) {
+  View v;
+  if (r.buf < 0) return v;
+  const BufDesc& b = e->bufs[r.buf];
+  v.base = e->arena + b.offset;
+  v.H = b.H; v.W = b.W; v.pitch = b.C; v.coff = r.coff; v.C = r.C;
+  return v;
+}
+
+static ConvParams conv_params(const yb_engine* e, const OpDesc& op, int B) {
+  ConvParams p;
+  p.in = make_view(e, op.in);
+  p.out = make_view(e, op.out);
+  p.res = make_view(e, op.res);
+  p.w = op.w_f32;
+  p.bias = op.bias;
+  p.B = B;
+  p.Cin = op.cin; p.Cout = op.cout;
+  p.k = op.k; p.stride = op.s; p.pad = op.k / 2;
+  p.Ho = p.out.H; p.Wo = p.out.W;
+  p.act = op.act;
+  return p;
+}
+
+template <typename T>
+static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out_pred, float* out_proto,
+                   cudaStream_t s) {
+  int rc;
+  bool input_converted = false;
+  for (size_t i = 0; i < e->ops.size(); i++) {
+    OpDesc& op = e->ops[i];
+    switch (op.type) {
+      case OP_CONV: {
+        if (i == 0 && e->has_stem_tc) {
+          rc = launch_stem_f16(in, in_dtype, B, e->cfg.height, e->cfg.width, op.w_f32, op.bias,
+                               make_view(e, op.out), s);
+          if (rc) return rc;
+          break;
+        }
+        if (!input_converted) {
+          rc = launch_input_to_nhwc<T>(in, in_dtype, make_view(e, e->input_nhwc), B, s);
+          if (rc) return rc;
+          input_converted = true;
+        }
+        if (op.use_tc) {
+          rc = tc_conv_launch(op.plan, B, s);
+        } else {
+          rc = launch_conv_generic<T>(conv_params(e, op, B), s);
+        }
+        if (rc) return rc;
+        break;
+      }
+      case OP_DWCONV:
+        rc = launch_dwconv3x3<T>(conv_params(e, op, B), s);
+        if (rc) return rc;
+        break;
+      case OP_POOL:
+        rc = launch_sppf_pool<T>(make_view(e, op.in), make_view(e, op.out), make_view(e, op.out2),
+                                 make_view(e, op.out3), B, s);
+        if (rc) return rc;
+        break;
+      case OP_UPSAMPLE:
+        rc = launch_upsample2x<T>(make_view(e, op.in), make_view(e, op.out), B, s);
+        if (rc) return rc;
+        break;
+      case OP_DECODE: {
+        View coef = make_view(e, op.coef);
+        rc = launch_decode_level<T>(make_view(e, op.in), make_view(e, op.cls), op.coef.buf >= 0 ? &coef : nullptr, B,
+                                    e->cfg.nc, 32, e->cfg.reg_max, op.stride, op.a0, e->A, e->pred_c, out_pred, s);
+        if (rc) return rc;
+        break;
+      }
+      case OP_PROTO_OUT:
+        if (out_proto) {
+          rc = launch_proto_out<T>(make_view(e, op.in), out_proto, B, s);
+          if (rc) return rc;
+        }
+        break;
+      default:
+        set_error("op type not implemented: " + op.name);
+        return YB_ERR_NOT_IMPLEMENTED;
+    }
+  }
+  return 0;
+}
+
+}  // namespace yb
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t yb_abi_version(void) { return YB_ABI_VERSION; }
+
+const char* yb_build_info(void) {
+  return "yolob200 (sm_100a; tcgen05+TMA conv, CUDA-core fp32 parity path) built " __DATE__ " " __TIME__;
+}
+
+const char* yb_last_error(void) { return g_last_error.c_str(); }
+
+int32_t yb_create(const yb_config* cfg, yb_engine** out) {
+  if (!cfg || !out) { set_error("yb_create: null argument"); return YB_ERR_INVALID_ARG; }
+  *out = nullptr;
+  if (cfg->arch != YB_ARCH_V8 && cfg->arch != YB_ARCH_V11) { set_error("yb_create: arch must be 8 or 11"); return YB_ERR_INVALID_ARG; }
+  if (cfg->size < 0 || cfg->size > 4) { set_error("yb_create: size must be 0..4 (n,s,m,l,x)"); return YB_ERR_INVALID_ARG; }
+  if (cfg->task != YB_TASK_DETECT && cfg->task != YB_TASK_SEGMENT) { set_error("yb_create: unsupported task"); return YB_ERR_NOT_IMPLEMENTED; }
+  if (cfg->nc <= 0 || cfg->nc >= 4096 || cfg->reg_max != 16) { set_error("yb_create: need 0 < nc < 4096 and reg_max == 16"); return YB_ERR_INVALID_ARG; }
+  if (cfg->height <= 0 || cfg->width <= 0 || cfg->height % 32 || cfg->width % 32) { set_error("yb_create: height/width must be positive multiples of 32"); return YB_ERR_INVALID_ARG; }
+  if (cfg->max_batch <= 0) { set_error("yb_create: max_batch must be positive"); return YB_ERR_INVALID_ARG; }
+  if (cfg->precision != YB_PREC_F32 && cfg->precision != YB_PREC_F16) { set_error("yb_create: bad precision"); return YB_ERR_INVALID_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("yb_create: no CUDA device available (this engine has no CPU fallback)");
+    return YB_ERR_NO_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { set_error("yb_create: bad device ordinal"); return YB_ERR_INVALID_ARG; }
+  YB_CUDA_CHECK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  YB_CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_error(std::string("yb_create: device '") + prop.name + "' is not sm_100 (Blackwell B200); this library only contains sm_100a code");
+    return YB_ERR_NO_DEVICE;
+  }
+  std::unique_ptr<yb_engine> e(new yb_engine());
+  e->cfg = *cfg;
+  e->esize = cfg->precision == YB_PREC_F16 ? 2 : 4;
+  int rc = build_graph(e.get());
+  if (rc) return rc;
+  // workspace: one arena, every buffer sized for max_batch, 1 KiB aligned (TMA/UMMA friendly)
+  size_t off = 0;
+  for (auto& b : e->bufs) {
+    b.offset = off;
+    size_t bytes = (size_t)cfg->max_batch * b.H * b.W * b.C * e->esize;
+    off += (bytes + 1023) / 1024 * 1024;
+  }
+  e->arena_bytes = off;
+  YB_CUDA_CHECK(cudaMalloc((void**)&e->arena, off));
+  YB_CUDA_CHECK(cudaMemset(e->arena, 0, off));
+  YB_CUDA_CHECK(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
+  *out = e.release();
+  return YB_OK;
+}
+
+void yb_destroy(yb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& op : e->ops) if (op.plan) tc_conv_plan_destroy(op.plan);
+  for (void* p : e->dev_allocs) cudaFree(p);
+  if (e->arena) cudaFree(e->arena);
+  if (e->stage_in) cudaFree(e->stage_in);
+  if (e->stage_pred) cudaFree(e->stage_pred);
+  if (e->stage_dets) cudaFree(e->stage_dets);
+  if (e->stage_counts) cudaFree(e->stage_counts);
+  if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
+  delete e;
+}
+
+int32_t yb_num_anchors(const yb_engine* e) { return e ? e->A : 0; }
+int32_t yb_pred_channels(const yb_engine* e) { return e ? e->pred_c : 0; }
+int32_t yb_num_expected_tensors(const yb_engine* e) { return e ? (int32_t)e->expected.size() : 0; }
+const char* yb_expected_tensor_name(const yb_engine* e, int32_t i) {
+  if (!e || i < 0 || i >= (int32_t)e->expected.size()) return nullptr;
+  return e->expected[i].c_str();
+}
+
+int32_t yb_load_tensor(yb_engine* e, const char* name, int32_t dtype, int32_t ndim, const int64_t* shape,
+                       const void* data) {
+  if (!e || !name || (ndim > 0 && !shape) || ndim < 0 || ndim > 8) { set_error("yb_load_tensor: bad argument"); return YB_ERR_INVALID_ARG; }
+  if (e->finalized) { set_error("yb_load_tensor: weights already finalized"); return YB_ERR_STATE; }
+  int64_t n = 1;
+  for (int i = 0; i < ndim; i++) {
+    if (shape[i] < 0) { set_error("yb_load_tensor: negative dimension"); return YB_ERR_INVALID_ARG; }
+    n *= shape[i];
+  }
+  if (n > 0 && !data) { set_error("yb_load_tensor: null data"); return YB_ERR_INVALID_ARG; }
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  t.data.resize((size_t)n);
+  switch (dtype) {
+    case YB_F32:
+      std::memcpy(t.data.data(), data, (size_t)n * 4);
+      break;
+    case YB_F16: {
+      const __half* h = reinterpret_cast<const __half*>(data);
+      for (int64_t i = 0; i < n; i++) t.data[i] = __half2float(h[i]);
+      break;
+    }
+    case YB_BF16: {
+      const uint16_t* h = reinterpret_cast<const uint16_t*>(data);
+      for (int64_t i = 0; i < n; i++) {
+        uint32_t u = (uint32_t)h[i] << 16;
+        std::memcpy(&t.data[i], &u, 4);
+      }
+      break;
+    }
+    default:
+      set_error("yb_load_tensor: unsupported dtype " + std::to_string(dtype) + " (5=f16, 6=f32, 15=bf16)");
+      return YB_ERR_INVALID_ARG;
+  }
+  e->host[name] = std::move(t);
+  return YB_OK;
+}
+
+int32_t yb_finalize_weights(yb_engine* e) {
+  if (!e) { set_error("yb_finalize_weights: null engine"); return YB_ERR_INVALID_ARG; }
+  if (e->finalized) { set_error("yb_finalize_weights: already finalized"); return YB_ERR_STATE; }
+  YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  const bool f16 = e->cfg.precision == YB_PREC_F16;
+  const bool allow_tc = f16 && !(e->cfg.flags & YB_FLAG_NO_TCGEN05);
+  for (size_t i = 0; i < e->ops.size(); i++) {
+    OpDesc& op = e->ops[i];
+    if (op.type != OP_CONV && op.type != OP_DWCONV) continue;
+    int rc = finalize_conv(e, op);
+    if (rc) return rc;
+    if (op.type == OP_CONV && allow_tc) {
+      if (i == 0) {
+        e->has_stem_tc = true;  // Cin = 3: dedicated stem kernel reading NCHW directly
+        continue;
+      }
+      ConvParams p = conv_params(e, op, e->cfg.max_batch);
+      p.w = op.w_f16;
+      if (tc_conv_supported(p)) {
+        std::string err;
+        op.plan = tc_conv_plan_create(p, &err);
+        if (!op.plan) { set_error("tcgen05 plan failed for " + op.name + ": " + err); return YB_ERR_CUDA; }
+        op.use_tc = true;
+      }
+    }
+  }
+  e->host.clear();
+  e->finalized = true;
+  return YB_OK;
+}
+
+int32_t yb_forward(yb_engine* e, const void* in, int32_t in_dtype, int32_t batch, float* out_pred,
+                   float* out_proto, void* stream) {
+  if (!e || !in || !out_pred) { set_error("yb_forward: null argument"); return YB_ERR_INVALID_ARG; }
+  if (!e->finalized) { set_error("yb_forward: call yb_finalize_weights first"); return YB_ERR_STATE; }
+  if (batch <= 0 || batch > e->cfg.max_batch) { set_error("yb_forward: batch outside [1, max_batch]"); return YB_ERR_INVALID_ARG; }
+  if (in_dtype != YB_U8 && in_dtype != YB_F16 && in_dtype != YB_F32) { set_error("yb_forward: in_dtype must be u8/f16/f32"); return YB_ERR_INVALID_ARG; }
+  if (e->cfg.task == YB_TASK_SEGMENT && !out_proto) { set_error("yb_forward: segment engine needs out_proto"); return YB_ERR_INVALID_ARG; }
+  YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool f16 = e->cfg.precision == YB_PREC_F16;
+  auto run = [&](cudaStream_t st) {
+    return f16 ? run_ops<__half>(e, in, in_dtype, batch, out_pred, out_proto, st)
+               : run_ops<float>(e, in, in_dtype, batch, out_pred, out_proto, st);
+  };
+  if (e->cfg.flags & YB_FLAG_NO_GRAPH) return run(s);
+  yb_engine::GraphKey key{in, in_dtype, batch, out_pred, out_proto};
+  auto it = e->graphs.find(key);
+  if (it != e->graphs.end()) {
+    YB_CUDA_CHECK(cudaGraphLaunch(it->second, s));
+    return YB_OK;
+  }
+  // first call with these buffers runs eagerly (also performs one-time attribute setup); the
+  // second call captures the launch sequence on a private stream and replays it from then on
+  if (e->seen[key]++ == 0) return run(s);
+  cudaGraph_t graph = nullptr;
+  YB_CUDA_CHECK(cudaStreamBeginCapture(e->capture_stream, cudaStreamCaptureModeThreadLocal));
+  int rc = run(e->capture_stream);
+  cudaError_t ce = cudaStreamEndCapture(e->capture_stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) { set_error(std::string("graph capture failed: ") + cudaGetErrorString(ce)); return YB_ERR_CUDA; }
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) { set_error(std::string("graph instantiate failed: ") + cudaGetErrorString(ce)); return YB_ERR_CUDA; }
+  if (e->graphs.size() > 64) {  // bound the cache
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+    e->graphs.clear();
+  }
+  e->graphs[key] = exec;
+  YB_CUDA_CHECK(cudaGraphLaunch(exec, s));
+  return YB_OK;
+}
+
+int32_t yb_nms(const float* pred, int32_t batch, int32_t channels, int32_t anchors, int32_t nc, float conf_thres,
+               float iou_thres, int32_t max_det, int32_t max_nms, int32_t max_wh, float* dets, int32_t* counts,
+               int32_t* keep_idx, void* stream) {
+  if (!pred || !dets || !counts) { set_error("yb_nms: null argument"); return YB_ERR_INVALID_ARG; }
+  return nms_launch(pred, batch, channels, anchors, nc, conf_thres, iou_thres, max_det, max_nms, max_wh, dets, counts,
+                    keep_idx, (cudaStream_t)stream);
+}
+
+int32_t yb_masks(const float* proto, const float* dets, const int32_t* counts, int32_t batch, int32_t max_det,
+                 int32_t nm, int32_t mh, int32_t mw, int32_t height, int32_t width, uint8_t* masks, void* stream) {
+  if (!proto || !dets || !counts || !masks) { set_error("yb_masks: null argument"); return YB_ERR_INVALID_ARG; }
+  if (batch <= 0 || max_det <= 0 || nm <= 0 || mh <= 0 || mw <= 0 || height <= 0 || width <= 0) { set_error("yb_masks: bad shape"); return YB_ERR_INVALID_ARG; }
+  return masks_launch(proto, dets, counts, batch, max_det, nm, mh, mw, height, width, masks, (cudaStream_t)stream);
+}
+
+int32_t yb_predict_u8(yb_engine* e, const uint8_t* images_host, int32_t batch, float conf_thres, float iou_thres,
+                      int32_t max_det, float* dets_host, int32_t* counts_host, void* stream) {
+  if (!e || !images_host || !dets_host || !counts_host) { set_error("yb_predict_u8: null argument"); return YB_ERR_INVALID_ARG; }
+  if (!e->finalized) { set_error("yb_predict_u8: call yb_finalize_weights first"); return YB_ERR_STATE; }
+  if (batch <= 0 || batch > e->cfg.max_batch) { set_error("yb_predict_u8: batch outside [1, max_batch]"); return YB_ERR_INVALID_ARG; }
+  if (e->cfg.task != YB_TASK_DETECT) { set_error("yb_predict_u8: detect engines only"); return YB_ERR_NOT_IMPLEMENTED; }
+  if (max_det <= 0 || max_det > 1024) { set_error("yb_predict_u8: max_det outside [1,1024]"); return YB_ERR_INVALID_ARG; }
+  YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t img_bytes = (size_t)3 * e->cfg.height * e->cfg.width;
+  const int row_w = 6 + (e->pred_c - 4 - e->cfg.nc);
+  if (!e->stage_in) {
+    YB_CUDA_CHECK(cudaMalloc((void**)&e->stage_in, img_bytes * e->cfg.max_batch));
+    YB_CUDA_CHECK(cudaMalloc((void**)&e->stage_pred, (size_t)e->cfg.max_batch * e->pred_c * e->A * sizeof(float)));
+    YB_CUDA_CHECK(cudaMalloc((void**)&e->stage_counts, (size_t)e->cfg.max_batch * sizeof(int)));
+  }
+  if (e->stage_max_det < max_det) {
+    if (e->stage_dets) cudaFree(e->stage_dets);
+    e->stage_dets = nullptr;
+    YB_CUDA_CHECK(cudaMalloc((void**)&e->stage_dets, (size_t)e->cfg.max_batch * max_det * row_w * sizeof(float)));
+    e->stage_max_det = max_det;
+  }
+  YB_CUDA_CHECK(cudaMemcpyAsync(e->stage_in, images_host, img_bytes * batch, cudaMemcpyHostToDevice, s));
+  int rc = yb_forward(e, e->stage_in, YB_U8, batch, e->stage_pred, nullptr, stream);
+  if (rc) return rc;
+  rc = nms_launch(e->stage_pred, batch, e->pred_c, e->A, e->cfg.nc, conf_thres, iou_thres, max_det, 30000, 7680,
+                  e->stage_dets, e->stage_counts, nullptr, s);
+  if (rc) return rc;
+  YB_CUDA_CHECK(cudaMemcpyAsync(dets_host, e->stage_dets, (size_t)batch * max_det * row_w * sizeof(float),
+                                cudaMemcpyDeviceToHost, s));
+  YB_CUDA_CHECK(cudaMemcpyAsync(counts_host, e->stage_counts, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, s));
+  YB_CUDA_CHECK(cudaStreamSynchronize(s));
+  return YB_OK;
+}
+
+int32_t yb_num_ops(const yb_engine* e) { return e ? (int32_t)e->ops.size() : 0; }
+const char* yb_op_name(const yb_engine* e, int32_t i) {
+  if (!e || i < 0 || i >= (int32_t)e->ops.size()) return nullptr;
+  return e->ops[i].name.c_str();
+}
+
+int32_t yb_debug_read_activation(yb_engine* e, int32_t op_index, int32_t batch, float* host_out, int64_t host_capacity,
+                                 int32_t chw[3]) {
+  if (!e || !host_out || !chw || op_index < 0 || op_index >= (int32_t)e->ops.size()) { set_error("yb_debug_read_activation: bad argument"); return YB_ERR_INVALID_ARG; }
+  YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  const OpDesc& op = e->ops[op_index];
+  View v = make_view(e, op.out);
+  chw[0] = v.C; chw[1] = v.H; chw[2] = v.W;
+  const int64_t n = (int64_t)batch * v.C * v.H * v.W;
+  if (n > host_capacity) { set_error("yb_debug_read_activation: host buffer too small"); return YB_ERR_INVALID_ARG; }
+  float* d = nullptr;
+  YB_CUDA_CHECK(cudaMalloc((void**)&d, n * sizeof(float)));
+  int rc = e->cfg.precision == YB_PREC_F16 ? launch_view_to_nchw_f32<__half>(v, d, batch, 0)
+                                           : launch_view_to_nchw_f32<float>(v, d, batch, 0);
+  if (!rc && cudaMemcpy(host_out, d, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("yb_debug_read_activation: copy failed");
+    rc = YB_ERR_CUDA;
+  }
+  cudaFree(d);
+  return rc;
+}
+
+int32_t yb_launches_per_forward(const yb_engine* e) {
+  if (!e) return 0;
+  int n = 0;
+  bool conv_seen = false;
+  for (size_t i = 0; i < e->ops.size(); i++) {
+    const OpDesc& op = e->ops[i];
+    if (op.type == OP_CONV && !conv_seen) {
+      conv_seen = true;
+      if (!(i == 0 && e->has_stem_tc)) n++;  // input layout conversion
+    }
+    n++;
+  }
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+// GPU non-max suppression + mask post-processing.
+//
+// Restates Utils/Ops.cs:239-371 (`non_max_suppression`, non-rotated / non-end2end path) of the
+// reference, including the torchvision.ops.nms core it calls at :357, with bit-identical
+// arithmetic: every fp32 op below is an explicit round-to-nearest intrinsic so nvcc cannot
+// contract mul+add into FMA (the CPU kernel is compiled without FMA contraction).
+//
+//  per image (one CTA, 1024 threads):
+//   1. candidate scan  : conf = max_c prob[c][a], j = first argmax; keep conf > conf_thres
+//                        (Ops.cs:272, 325-328).  64-bit key = (~bits(conf) << 32) | anchor << 12 | j
+//   2. bitonic sort    : ascending key == score descending, anchor index ascending on ties
+//                        (torchvision sorts scores with a stable descending sort); truncate to
+//                        max_nms (Ops.cs:338-342)
+//   3. greedy suppress : boxes offset by cls*max_wh in fp32 (Ops.cs:345,356); candidates are
+//                        consumed in chunks of 32: a 32x32 IoU bit-matrix inside the chunk plus a
+//                        check against the kept list, then a 32-step serial resolve.  Stops at
+//                        max_det kept boxes (Ops.cs:360 - later boxes cannot change earlier ones).
+#include "common.cuh"
+
+namespace yb {
+
+constexpr int NMS_THREADS = 1024;
+constexpr int NMS_SMEM_KEYS = 16384;  // candidates sortable in shared memory (128 KB of keys)
+constexpr int NMS_MAX_DET_CAP = 1024;
+
+struct Box5 {
+  float x1, y1, x2, y2, area;
+};
+
+// IoU > thr test with the exact op order of torchvision's CPU kernel (nms_kernel_impl):
+//   w = max(0, xx2-xx1); h = max(0, yy2-yy1); inter = w*h; ovr = inter / (iarea + area_j - inter)
+__device__ __forceinline__ bool iou_gt(const Box5& a, const Box5& b, float thr) {
+  const float xx1 = fmaxf(a.x1, b.x1), yy1 = fmaxf(a.y1, b.y1);
+  const float xx2 = fminf(a.x2, b.x2), yy2 = fminf(a.y2, b.y2);
+  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
+  const float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter));
+  return ovr > thr;  // NaN (0/0) compares false, as on the CPU
+}
+
+__global__ void __launch_bounds__(NMS_THREADS, 1)
+nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thres, float iou_thres,
+           int max_det, int max_nms, float max_wh, float* __restrict__ dets, int* __restrict__ counts,
+           int* __restrict__ keep_idx, unsigned long long* __restrict__ gkeys, int key_cap) {
+  extern __shared__ __align__(16) unsigned char nms_smem[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* P = pred + (size_t)b * C * A;
+  const int extra = C - 4 - nc;
+  const int row_w = 6 + extra;
+
+  // shared carve-up
+  Box5* kept = reinterpret_cast<Box5*>(nms_smem);                       // [max_det]
+  Box5* cbox = kept + NMS_MAX_DET_CAP;                                   // [32] chunk boxes (offset)
+  float* craw = reinterpret_cast<float*>(cbox + 32);                     // [32][6] raw row
+  int* canchor = reinterpret_cast<int*>(craw + 32 * 6);                  // [32]
+  unsigned* rowmask = reinterpret_cast<unsigned*>(canchor + 32);         // [32]
+  unsigned* misc = rowmask + 32;                                         // [4]: n_cand, supp, keepmask, kept_n
+  unsigned long long* keys =
+      gkeys ? gkeys + (size_t)b * key_cap
+            : reinterpret_cast<unsigned long long*>(nms_smem + ((NMS_MAX_DET_CAP + 32) * sizeof(Box5) +
+                                                                32 * 6 * 4 + 32 * 4 + 32 * 4 + 16));
+  if (tid < 4) misc[tid] = 0;
+  __syncthreads();
+
+  // ---- 1. candidate scan ----
+  for (int a = tid; a < A; a += NMS_THREADS) {
+    float best = P[(size_t)4 * A + a];
+    int bj = 0;
+    for (int c = 1; c < nc; c++) {
+      const float v = P[(size_t)(4 + c) * A + a];
+      if (v > best) { best = v; bj = c; }
+    }
+    if (best > conf_thres) {
+      const unsigned slot = atomicAdd(&misc[0], 1u);
+      if (slot < (unsigned)key_cap)
+        keys[slot] = ((unsigned long long)(~__float_as_uint(best)) << 32) |
+                     ((unsigned long long)(unsigned)a << 12) | (unsigned)bj;
+    }
+  }
+  __syncthreads();
+  int n = min((int)misc[0], key_cap);
+  if (n == 0) {
+    if (tid == 0) counts[b] = 0;
+    return;
+  }
+
+  // ---- 2. bitonic sort (ascending) over the next power of two ----
+  int P2 = 1;
+  while (P2 < n) P2 <<= 1;
+  for (int i = n + tid; i < P2; i += NMS_THREADS) keys[i] = ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= P2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P2; i += NMS_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = keys[i], y = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { keys[i] = y; keys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  n = min(n, max_nms);
+
+  // ---- 3. greedy suppression in chunks of 32 ----
+  int kept_n = 0;
+  for (int s0 = 0; s0 < n && kept_n < max_det; s0 += 32) {
+    const int cnt = min(32, n - s0);
+    if (tid < 32) {
+      Box5 bx = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (lane < cnt) {
+        const unsigned long long key = keys[s0 + lane];
+        const int a = (int)((key >> 12) & 0xFFFFF);
+        const int j = (int)(key & 0xFFF);
+        const float conf = __uint_as_float(~(unsigned)(key >> 32));
+        const float cx = P[a], cy = P[(size_t)A + a], w = P[(size_t)2 * A + a], h = P[(size_t)3 * A + a];
+        // xywh2xyxy (Ops.cs:76-79): x - w/2, x + w/2 (w/2 is exact)
+        const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+        const float x1 = __fsub_rn(cx, hw), y1 = __fsub_rn(cy, hh);
+        const float x2 = __fadd_rn(cx, hw), y2 = __fadd_rn(cy, hh);
+        const float off = __fmul_rn((float)j, max_wh);  // Ops.cs:345
+        bx.x1 = __fadd_rn(x1, off); bx.y1 = __fadd_rn(y1, off);
+        bx.x2 = __fadd_rn(x2, off); bx.y2 = __fadd_rn(y2, off);
+        bx.area = __fmul_rn(__fsub_rn(bx.x2, bx.x1), __fsub_rn(bx.y2, bx.y1));
+        float* r = craw + lane * 6;
+        r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2; r[4] = conf; r[5] = (float)j;
+        canchor[lane] = a;
+      }
+      cbox[lane] = bx;
+      if (lane == 0) misc[1] = 0;
+    }
+    __syncthreads();
+    // phase A: warp g = row g of the intra-chunk matrix, then kept entries g, g+32, ...
+    {
+      const Box5 mine = cbox[lane];
+      const Box5 rowb = cbox[warp];
+      const bool hit = (warp < cnt) && (lane < cnt) && (lane > warp) && iou_gt(rowb, mine, iou_thres);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) rowmask[warp] = m;
+      bool sup = false;
+      if (lane < cnt)
+        for (int k = warp; k < kept_n; k += 32) sup = sup || iou_gt(kept[k], mine, iou_thres);
+      const unsigned sm = __ballot_sync(0xffffffffu, sup);
+      if (lane == 0 && sm) atomicOr(&misc[1], sm);
+    }
+    __syncthreads();
+    // phase B: serial resolve inside the chunk (warp 0, every lane runs the same bit loop)
+    if (warp == 0) {
+      unsigned supp = misc[1];
+      unsigned keepmask = 0;
+      int kn = kept_n;
+      for (int i = 0; i < cnt && kn < max_det; i++) {
+        if (!((supp >> i) & 1u)) {
+          keepmask |= 1u << i;
+          supp |= rowmask[i];
+          kn++;
+        }
+      }
+      if ((keepmask >> lane) & 1u) {
+        const int pos = kept_n + __popc(keepmask & ((1u << lane) - 1u));
+        kept[pos] = cbox[lane];
+        float* o = dets + ((size_t)b * max_det + pos) * row_w;
+        const float* r = craw + lane * 6;
+#pragma unroll
+        for (int q = 0; q < 6; q++) o[q] = r[q];
+        const int a = canchor[lane];
+        for (int q = 0; q < extra; q++) o[6 + q] = P[(size_t)(4 + nc + q) * A + a];
+        if (keep_idx) keep_idx[(size_t)b * max_det + pos] = a;
+      }
+      if (lane == 0) misc[3] = (unsigned)kn;
+    }
+    __syncthreads();
+    kept_n = (int)misc[3];
+  }
+  if (tid == 0) counts[b] = kept_n;
+}
+
+int nms_launch(const float* pred, int B, int C, int A, int nc, float conf, float iou, int max_det,
+               int max_nms, int max_wh, float* dets, int* counts, int* keep_idx, cudaStream_t s) {
+  if (!(conf >= 0.f && conf <= 1.f)) {
+    set_error("Invalid Confidence threshold " + std::to_string(conf) + ", valid values are between 0.0 and 1.0");
+    return YB_ERR_INVALID_ARG;
+  }
+  if (!(iou >= 0.f && iou <= 1.f)) {
+    set_error("Invalid IoU " + std::to_string(iou) + ", valid values are between 0.0 and 1.0");
+    return YB_ERR_INVALID_ARG;
+  }
+  if (nc <= 0) nc = C - 4;
+  if (B <= 0 || A <= 0 || C < 4 + nc || nc >= 4096 || A >= (1 << 20) || max_det <= 0 ||
+      max_det > NMS_MAX_DET_CAP || max_nms <= 0) {
+    set_error("yb_nms: unsupported shape (need nc < 4096, anchors < 2^20, 0 < max_det <= 1024)");
+    return YB_ERR_SHAPE;
+  }
+  const int extra = C - 4 - nc;
+  YB_CUDA_CHECK(cudaMemsetAsync(dets, 0, (size_t)B * max_det * (6 + extra) * sizeof(float), s));
+  if (keep_idx) YB_CUDA_CHECK(cudaMemsetAsync(keep_idx, 0xFF, (size_t)B * max_det * sizeof(int), s));
+  const size_t fixed = (NMS_MAX_DET_CAP + 32) * sizeof(Box5) + 32 * 6 * 4 + 32 * 4 + 32 * 4 + 16;
+  unsigned long long* gkeys = nullptr;
+  int key_cap = A;  // every anchor may be a candidate
+  size_t smem = fixed;
+  int P2 = 1;
+  while (P2 < A) P2 <<= 1;
+  if (P2 <= NMS_SMEM_KEYS) {
+    smem += (size_t)P2 * 8;
+    key_cap = P2;
+  } else {
+    key_cap = P2;
+    YB_CUDA_CHECK(cudaMallocAsync(&gkeys, (size_t)B * P2 * 8, s));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    YB_CUDA_CHECK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(fixed + NMS_SMEM_KEYS * 8)));
+    attr_set = true;
+  }
+  nms_kernel<<<B, NMS_THREADS, smem, s>>>(pred, C, A, nc, conf, iou, max_det, max_nms, (float)max_wh, dets, counts,
+                                          keep_idx, gkeys, key_cap);
+  YB_CUDA_CHECK(cudaGetLastError());
+  if (gkeys) YB_CUDA_CHECK(cudaFreeAsync(gkeys, s));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Masks: Utils/Ops.cs:462-489 process_mask(upsample: true) with the CUDA branch of crop_mask
+// (:437-447).  For every kept detection: m = coeff . proto (mh x mw), zero outside the box scaled
+// to proto resolution (r >= x1 && r < x2 && c >= y1 && c < y2 in float), bilinear x(H/mh)
+// upsample with align_corners=false (ATen upsample_bilinear2d), then > 0.
+// One block per (detection, output row tile): the needed low-res rows are produced on the fly.
+// ------------------------------------------------------------------------------------------
+__global__ void masks_kernel(const float* __restrict__ proto, const float* __restrict__ dets,
+                             const int* __restrict__ counts, int max_det, int nm, int mh, int mw, int H, int W,
+                             uint8_t* __restrict__ masks) {
+  extern __shared__ float mk_smem[];  // [mh*mw] cropped low-res mask of this detection
+  const int det = blockIdx.x, b = blockIdx.y;
+  if (det >= counts[b]) return;
+  const int row_w = 6 + nm;
+  const float* d = dets + ((size_t)b * max_det + det) * row_w;
+  const float* pr = proto + (size_t)b * nm * mh * mw;
+  // width_ratio = (float)mw / iw etc. (Ops.cs:472-479)
+  const float wr = __fdiv_rn((float)mw, (float)W), hr = __fdiv_rn((float)mh, (float)H);
+  const float x1 = __fmul_rn(d[0], wr), x2 = __fmul_rn(d[2], wr);
+  const float y1 = __fmul_rn(d[1], hr), y2 = __fmul_rn(d[3], hr);
+  for (int i = threadIdx.x; i < mh * mw; i += blockDim.x) {
+    const int r = i / mw, c = i - r * mw;
+    float acc = 0.f;
+    for (int k = 0; k < nm; k++) acc = fmaf(d[6 + k], pr[(size_t)k * mh * mw + i], acc);
+    const bool inside = ((float)c >= x1) && ((float)c < x2) && ((float)r >= y1) && ((float)r < y2);
+    mk_smem[i] = inside ? acc : 0.f;
+  }
+  __syncthreads();
+  // ATen upsample_bilinear2d, align_corners=false: src = max(0, (dst + 0.5) * scale - 0.5),
+  // scale = in/out
+  const float sh = (float)mh / (float)H, sw = (float)mw / (float)W;
+  uint8_t* out = masks + ((size_t)b * max_det + det) * H * W;
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+    const int oy = i / W, ox = i - oy * W;
+    float fy = fmaxf(0.f, ((float)oy + 0.5f) * sh - 0.5f);
+    float fx = fmaxf(0.f, ((float)ox + 0.5f) * sw - 0.5f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1i = y0 + (y0 < mh - 1 ? 1 : 0), x1i = x0 + (x0 < mw - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float v = hy * (hx * mk_smem[y0 * mw + x0] + lx * mk_smem[y0 * mw + x1i]) +
+                    ly * (hx * mk_smem[y1i * mw + x0] + lx * mk_smem[y1i * mw + x1i]);
+    out[i] = v > 0.f ? 1 : 0;
+  }
+}
+
+int masks_launch(const float* proto, const float* dets, const int* counts, int B, int max_det, int nm,
+                 int mh, int mw, int H, int W, uint8_t* masks, cudaStream_t s) {
+  const size_t smem = (size_t)mh * mw * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("yb_masks: proto map too large");
+    return YB_ERR_SHAPE;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    YB_CUDA_CHECK(cudaFuncSetAttribute(masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  masks_kernel<<<dim3(max_det, B), 512, smem, s>>>(proto, dets, counts, max_det, nm, mh, mw, H, W, masks);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace yb

@@ -1,0 +1,148 @@
+"""Thin object wrapper over the C ABI (include/yolob200.h).  PyTorch is used only for device
+memory and streams; every computation is a kernel of libyolob200.so."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+class Engine:
+    def __init__(self, arch="v8", size="n", task="detect", nc=80, precision="f16", device=0, max_batch=1,
+                 height=640, width=640, flags=0):
+        self._h = C.c_void_p()
+        lib = L.lib()
+        cfg = L.yb_config(arch={"v8": L.YB_ARCH_V8, "v11": L.YB_ARCH_V11}[arch], size=L.SIZES[size],
+                          task={"detect": L.YB_TASK_DETECT, "segment": L.YB_TASK_SEGMENT}[task], nc=nc, reg_max=16,
+                          precision={"f32": L.YB_PREC_F32, "f16": L.YB_PREC_F16}[precision], device=device,
+                          max_batch=max_batch, height=height, width=width, flags=flags)
+        L.check(lib.yb_create(C.byref(cfg), C.byref(self._h)))
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        self.nc, self.height, self.width, self.max_batch = nc, height, width, max_batch
+        self.task = task
+        self.anchors = lib.yb_num_anchors(self._h)
+        self.pred_channels = lib.yb_pred_channels(self._h)
+        self.finalized = False
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            L.lib().yb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    # ---- weights ----
+    def expected_tensors(self):
+        lib = L.lib()
+        return [lib.yb_expected_tensor_name(self._h, i).decode() for i in range(lib.yb_num_expected_tensors(self._h))]
+
+    def load_tensor_raw(self, name, dtype_code, shape, data_bytes):
+        shp = (C.c_int64 * len(shape))(*shape)
+        buf = C.create_string_buffer(data_bytes, len(data_bytes)) if data_bytes else None
+        L.check(L.lib().yb_load_tensor(self._h, name.encode(), dtype_code, len(shape), shp,
+                                       C.cast(buf, C.c_void_p) if buf else None))
+
+    def load_state_dict(self, state_dict):
+        """state_dict: reference names -> torch tensors / numpy arrays (fp16 / fp32 / bf16)."""
+        want = set(self.expected_tensors())
+        for name, t in state_dict.items():
+            if name not in want:
+                continue
+            if isinstance(t, np.ndarray):
+                t = torch.from_numpy(t)
+            t = t.detach().cpu().contiguous()
+            code = {torch.float16: L.YB_F16, torch.float32: L.YB_F32, torch.bfloat16: L.YB_BF16}.get(t.dtype)
+            if code is None:
+                t, code = t.float(), L.YB_F32
+            shp = (C.c_int64 * t.dim())(*t.shape)
+            L.check(L.lib().yb_load_tensor(self._h, name.encode(), code, t.dim(), shp, C.c_void_p(t.data_ptr())))
+
+    def finalize(self):
+        L.check(L.lib().yb_finalize_weights(self._h))
+        self.finalized = True
+
+    # ---- compute ----
+    def forward(self, x, out_pred=None, out_proto=None, stream=None):
+        """x: CUDA (B,3,H,W) uint8 / float16 / float32 -> pred float32 (B, C, A) [, proto]."""
+        assert x.is_cuda and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3
+        assert x.shape[2] == self.height and x.shape[3] == self.width, "engine was planned for another input size"
+        code = {torch.uint8: L.YB_U8, torch.float16: L.YB_F16, torch.float32: L.YB_F32}[x.dtype]
+        B = x.shape[0]
+        if out_pred is None:
+            out_pred = torch.empty((B, self.pred_channels, self.anchors), dtype=torch.float32, device=x.device)
+        proto_ptr = None
+        if self.task == "segment":
+            if out_proto is None:
+                out_proto = torch.empty((B, 32, self.height // 4, self.width // 4), dtype=torch.float32, device=x.device)
+            proto_ptr = C.c_void_p(out_proto.data_ptr())
+        L.check(L.lib().yb_forward(self._h, C.c_void_p(x.data_ptr()), code, B, C.c_void_p(out_pred.data_ptr()),
+                                   proto_ptr, _stream_ptr(stream)))
+        return (out_pred, out_proto) if self.task == "segment" else out_pred
+
+    def predict_u8(self, images_host, conf_thres=0.25, iou_thres=0.45, max_det=300, dets_host=None, counts_host=None,
+                   stream=None):
+        """HOST uint8 (B,3,H,W) -> HOST (dets (B,max_det,6), counts (B,)); H2D + forward + NMS + D2H."""
+        assert not images_host.is_cuda and images_host.dtype == torch.uint8 and images_host.is_contiguous()
+        B = images_host.shape[0]
+        row_w = 6 + self.pred_channels - 4 - self.nc
+        if dets_host is None:
+            dets_host = torch.empty((B, max_det, row_w), dtype=torch.float32).pin_memory()
+            counts_host = torch.empty((B,), dtype=torch.int32).pin_memory()
+        L.check(L.lib().yb_predict_u8(self._h, C.c_void_p(images_host.data_ptr()), B, conf_thres, iou_thres, max_det,
+                                      C.c_void_p(dets_host.data_ptr()), C.c_void_p(counts_host.data_ptr()),
+                                      _stream_ptr(stream)))
+        return dets_host, counts_host
+
+    # ---- debug ----
+    def op_names(self):
+        lib = L.lib()
+        return [lib.yb_op_name(self._h, i).decode() for i in range(lib.yb_num_ops(self._h))]
+
+    def read_activation(self, op_index, batch):
+        """NCHW float32 copy of what op `op_index` wrote during the last forward."""
+        chw = (C.c_int32 * 3)()
+        cap = batch * 1024 * 640 * 640 // 16
+        buf = np.empty(cap, dtype=np.float32)
+        L.check(L.lib().yb_debug_read_activation(self._h, op_index, batch, buf.ctypes.data_as(C.c_void_p), cap,
+                                                 C.byref(chw)))
+        c, h, w = chw
+        return torch.from_numpy(buf[:batch * c * h * w].reshape(batch, c, h, w).copy())
+
+    def launches_per_forward(self):
+        return L.lib().yb_launches_per_forward(self._h)
+
+
+def nms(pred, conf_thres=0.25, iou_thres=0.45, max_det=300, nc=0, max_nms=30000, max_wh=7680, stream=None,
+        out=None):
+    """Raw batched call of yb_nms.  pred: CUDA float32 (B,C,A).  -> dets (B,max_det,6+extra), counts, keep_idx."""
+    assert pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3
+    B, Cc, A = pred.shape
+    ncc = nc or Cc - 4
+    extra = Cc - 4 - ncc
+    if out is None:
+        dets = torch.empty((B, max_det, 6 + extra), dtype=torch.float32, device=pred.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=pred.device)
+        keep = torch.empty((B, max_det), dtype=torch.int32, device=pred.device)
+    else:
+        dets, counts, keep = out
+    L.check(L.lib().yb_nms(C.c_void_p(pred.data_ptr()), B, Cc, A, ncc, conf_thres, iou_thres, max_det, max_nms, max_wh,
+                           C.c_void_p(dets.data_ptr()), C.c_void_p(counts.data_ptr()), C.c_void_p(keep.data_ptr()),
+                           _stream_ptr(stream)))
+    return dets, counts, keep
+
+
+def masks(proto, dets, counts, height, width, stream=None):
+    """yb_masks: proto (B,32,mh,mw) f32, dets (B,max_det,38), counts -> uint8 (B,max_det,H,W)."""
+    B, nm, mh, mw = proto.shape
+    max_det = dets.shape[1]
+    out = torch.zeros((B, max_det, height, width), dtype=torch.uint8, device=proto.device)
+    L.check(L.lib().yb_masks(C.c_void_p(proto.data_ptr()), C.c_void_p(dets.data_ptr()), C.c_void_p(counts.data_ptr()), B,
+                             max_det, nm, mh, mw, height, width, C.c_void_p(out.data_ptr()), _stream_ptr(stream)))
+    return out
