@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py - images/sec of the YOLO hot path (forward + decode + NMS) on synthetic 3x640x640 batches.
+
+    python bench.py --gpus N --steps K --warmup W [--model v8n|v8s|v8x] [--batch B]
+    torchrun --nproc-per-node N bench.py --gpus N ...           (one rank per GPU, NCCL)
+    python bench.py --impl reference ...                         (the reference's CPU path, see below)
+
+One "step" = one pass of the hot path over one batch per GPU: yb_forward (tcgen05 fp16 network +
+DFL/box decode) -> yb_nms (GPU NMS) [-> NCCL all-gather of the fixed-capacity detection buffers when
+N > 1].  Workload at N=1 = BASELINE.json configs[1]: YOLOv8n detect, batch 32 x 3x640x640, fp16.
+Weights are seeded-synthetic (no network for checkpoints; shape/arch identical), inputs synthetic.
+
+Printed JSON (one line, rank 0):
+  value      images/s, device-timed (CUDA events, max over ranks), inputs resident in HBM
+  e2e        same metric through the host-buffer C-ABI call yb_predict_u8 (pinned uint8 images in,
+             detections out; H2D + D2H inside the timed region)
+  roofline   the dominant kernel (conv_tc_kernel, the tcgen05 implicit-GEMM conv): algorithmic FLOPs
+             and bytes of all its launches in one step / their summed device time, measured with CUDA
+             events around every launch in a separate eager pass of the same step
+  cpu_baseline  the oracle (PyTorch-CPU restatement of the reference's TorchSharp op sequence, the
+             reference itself is C# and cannot run here) timed on this box's host cores
+--impl reference times that same CPU path as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODELS = {"v8n": ("v8", "n", 8.743), "v8s": ("v8", "s", 28.602), "v8x": ("v8", "x", 257.803)}  # GFLOP/img @640^2
+CONF, IOU, MAX_DET = 0.25, 0.45, 300
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(model_key, batch, steps, warmup):
+    """The reference's CPU path: un-fused conv->BN->SiLU graph + torchvision NMS via the oracle
+    (PyTorch CPU = same libtorch operator family as TorchSharp), all host threads."""
+    import torch
+    from oracle import ops as oops
+    from tests.util import oracle_model, synth_image
+    arch, size, _ = MODELS[model_key]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = oracle_model(arch, "detect", size)
+    x = synth_image(batch, 640, 640)
+    def step():
+        with torch.no_grad():
+            pred = m(x)[0]["boxes"]
+        oops.non_max_suppression(pred, CONF, IOU)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="v8n", choices=sorted(MODELS))
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    arch, size, gflop_img = MODELS[args.model]
+    workload = f"YOLO{args.model} detect inference (forward+decode+NMS), batch {args.batch}x3x640x640 per GPU, fp16"
+    config = {"workload": workload, "model": args.model, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+              "imgsz": 640, "conf": CONF, "iou": IOU, "max_det": MAX_DET,
+              "parallelism": f"batch-sharded x{world}" + (" + NCCL all-gather of detections" if world > 1 else ""),
+              "l2": "4 rotating input batches (>L2) and ~1 GB of activations rewritten per step"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample_b = 8
+        val, ms, cores = cpu_reference_run(args.model, sample_b, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": f"images/sec YOLO{args.model} 3x640x640", "value": round(val, 2),
+                "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": round(val, 2), "unit": "images/s", "cores": cores, "kind": "port",
+                                 "sample": f"{sample_b} of {args.batch} images per step, {args.steps} steps; PyTorch-CPU "
+                                           "restatement of the TorchSharp op sequence (the C# reference cannot run: no .NET)"},
+                "e2e": {"value": round(val, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import yolosharp_b200 as y
+    from tests.util import oracle_model, synth_image
+    assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback in the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    m = oracle_model(arch, "detect", size)  # seeded synthetic weights (weights only; the oracle net is not run here)
+    eng = y.Engine(arch, size, "detect", 80, "f16", local_rank, B, 640, 640)
+    eng.load_state_dict(m.state_dict())
+    eng.finalize()
+    del m
+    A, Cp = eng.anchors, eng.pred_channels
+    xs = [synth_image(B, 640, 640, seed=100 + rank * 8 + i, dtype=torch.float16).to(dev) for i in range(4)]
+    pred = torch.empty((B, Cp, A), dtype=torch.float32, device=dev)
+    dets = torch.empty((B, MAX_DET, 6), dtype=torch.float32, device=dev)
+    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    keep = torch.empty((B, MAX_DET), dtype=torch.int32, device=dev)
+    if world > 1:
+        all_dets = torch.empty((world * B, MAX_DET, 6), dtype=torch.float32, device=dev)
+        all_counts = torch.empty((world * B,), dtype=torch.int32, device=dev)
+
+    def step(i):
+        eng.forward(xs[i % 4], pred)
+        y.nms(pred, CONF, IOU, MAX_DET, 80, out=(dets, counts, keep))
+        if world > 1:
+            dist.all_gather_into_tensor(all_dets, dets)
+            dist.all_gather_into_tensor(all_counts, counts)
+
+    for i in range(max(args.warmup, 8)):  # >= 8 so every rotating input has its CUDA graph captured
+        step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total / 1e3)
+    mean_dets = float(counts.float().mean().item())
+
+    # ---- e2e: host uint8 images -> host detections through yb_predict_u8 ----
+    u8 = [synth_image(B, 640, 640, seed=200 + rank * 8 + i, dtype=torch.uint8).pin_memory() for i in range(2)]
+    dh = torch.empty((B, MAX_DET, 6), dtype=torch.float32).pin_memory()
+    ch = torch.empty((B,), dtype=torch.int32).pin_memory()
+    e2e_steps = max(5, args.steps // 2)
+    for i in range(4):
+        eng.predict_u8(u8[i % 2], CONF, IOU, MAX_DET, dh, ch)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng.predict_u8(u8[i % 2], CONF, IOU, MAX_DET, dh, ch)  # returns after the D2H copy completed
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * e2e_steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events in an eager pass of the same step ----
+    peaks = load_peaks()
+    prof = None
+    for _ in range(3):
+        prof = eng.profile(xs[0], pred)
+    tc = [r for r in prof if r["kind"] == 0]
+    tc_ms = sum(r["ms"] for r in tc)
+    tc_flops = sum(r["flops"] for r in tc)
+    tc_bytes = sum(r["bytes"] for r in tc)
+    all_ms = sum(r["ms"] for r in prof)
+    t_tc = tc_flops / (peaks["tc"] * 1e12)
+    t_hbm = tc_bytes / (peaks["hbm"] * 1e9)
+    if t_hbm >= t_tc:
+        ach = tc_bytes / (tc_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": round(ach / peaks["hbm"], 4)}
+    else:
+        ach = tc_flops / (tc_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tc"], "unit": "TFLOP/s",
+                "frac": round(ach / peaks["tc"], 4)}
+    roof.update({"traffic": None, "kernel": "conv_tc_kernel", "launches_per_step": len(tc),
+                 "kernel_ms_per_step": round(tc_ms, 4), "share_of_step": round(tc_ms / all_ms, 3),
+                 "algorithmic_gflop_per_step": round(tc_flops / 1e9, 2), "algorithmic_mb_per_step": round(tc_bytes / 1e6, 1),
+                 "tensor_tflops": round(tc_flops / (tc_ms / 1e3) / 1e12, 2),
+                 "hbm_gbs": round(tc_bytes / (tc_ms / 1e3) / 1e9, 1), "peak_source": peaks["src"] + ", sustained TC",
+                 "whole_net_tflops": round(gflop_img * 1e9 * value / world / 1e12, 2)})
+    top = sorted(prof, key=lambda r: -r["ms"])[:6]
+    roof["top_ops"] = [{"name": r["name"], "ms": round(r["ms"], 4)} for r in top]
+
+    line = {"metric": f"images/sec YOLO{args.model} 3x640x640", "value": round(value, 1), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": config, "clocks": clocks,
+            "e2e": {"value": round(e2e_val, 1), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 640 * 640,
+                    "d2h_bytes_per_step": B * MAX_DET * 6 * 4 + B * 4, "steps": e2e_steps,
+                    "api": "yb_predict_u8 (pinned host uint8 in, host detections out)"},
+            "gpu_launches": (eng.launches_per_forward() + 1) * args.steps,
+            "launches_per_step": eng.launches_per_forward() + 1, "mean_detections_per_image": round(mean_dets, 1),
+            "roofline": roof}
+    if world == 1 and not args.no_cpu_baseline:
+        cb_b, cb_steps = 8, 10
+        val, ms, cores = cpu_reference_run(args.model, cb_b, cb_steps, 3)
+        line["cpu_baseline"] = {"value": round(val, 2), "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"batch {cb_b} x {cb_steps} steps of the same workload (fp32, PyTorch-CPU oracle "
+                                          "= restated TorchSharp op sequence; C# reference not runnable here)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

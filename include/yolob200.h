@@ -150,6 +150,15 @@ int32_t yb_debug_read_activation(yb_engine* e, int32_t op_index, int32_t batch, 
 const char* yb_op_name(const yb_engine* e, int32_t op_index);
 /* number of kernel launches one yb_forward issues (for bench.py's gpu_launches) */
 int32_t yb_launches_per_forward(const yb_engine* e);
+/* Per-op timing: runs the forward eagerly (no graph) with a CUDA event pair around every op on
+ * `stream`; ms_per_op[i] (i < yb_num_ops) receives the device time of op i. */
+int32_t yb_profile_forward(yb_engine* e, const void* in, int32_t in_dtype, int32_t batch, float* out_pred,
+                           float* out_proto, float* ms_per_op, int32_t n_ops, void* stream);
+/* Algorithmic work of op i for `batch` images: flops = 2*MACs (convs only), bytes = input view +
+ * output view (+ residual) + weights, each counted once (SURVEY.md section 8(d) definitions). */
+int32_t yb_op_cost(const yb_engine* e, int32_t op_index, int32_t batch, double* flops, double* bytes);
+/* 0 = tcgen05 conv, 1 = CUDA-core conv, 2 = stem, 3 = depthwise, 4 = pool, 5 = upsample, 6 = decode, 7 = other */
+int32_t yb_op_kind(const yb_engine* e, int32_t op_index);
 
 #ifdef __cplusplus
 }

@@ -65,7 +65,10 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, agnostic=Fa
         c = x[:, 5:6] * max_wh
         scores = x[:, 4]
         boxes = x[:, :4] + c
-        i = torchvision.ops.nms(boxes, scores, iou_thres)
+        # The reference passes a C# `float` (Ops.cs:241) that is widened to the kernel's double
+        # threshold; a Python float would compare against 0.3 instead of (double)0.3f, which
+        # differs exactly when an IoU equals the fp32 threshold.
+        i = torchvision.ops.nms(boxes, scores, float(np.float32(iou_thres)))
         i = i[:max_det]
         output[xi], keepi[xi] = x[i], xk[i].reshape(-1)
     return output, keepi

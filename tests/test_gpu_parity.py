@@ -221,8 +221,30 @@ def test_fp16_tcgen05_matches_cuda_core_twin(y):
         b.close()
 
 
+def test_fp16_detections_real_weights(y):
+    """Shipped Yolov8n weights + bus.jpg in fp16 tcgen05 mode: same detections as the fp32 oracle
+    (classes equal, boxes within 2 px, scores within 0.02)."""
+    m, sd = oracle_real_v8n()
+    img = torch.from_numpy(np.load(os.path.join(GOLDEN, "bus_u8.npy")))
+    z = np.load(os.path.join(GOLDEN, "v8n_bus.npz"))
+    det = y.Detector(y.Config(YoloType="Yolov8", YoloSize="n", ScalarType="Float16"))
+    det.yolo.load_state_dict(sd)
+    res = det.ImagePredict(img, 0.3, 0.7)
+    rows = z["rows"]
+    strong = rows[rows[:, 4] > 0.5]
+    assert len(strong) == 4
+    for r, ex in zip(res[:4], oops.to_yolo_results(torch.from_numpy(strong))):
+        assert r.ClassID == ex["ClassID"]
+        assert abs(r.Score - ex["Score"]) < 0.02
+        for k in ("CenterX", "CenterY", "Width", "Height"):
+            assert abs(getattr(r, k) - ex[k]) <= 2, (k, r, ex)
+
+
 def test_fp16_detections_640(y):
-    """configs[1] shape (batch of 640x640, fp16 tcgen05): detections agree with the fp32 oracle."""
+    """configs[1] shape (batch of 640x640, fp16 tcgen05), synthetic weights: the prediction tensor stays
+    within fp16 tolerance of the fp32 oracle and the strong detections survive.  (Random weights give
+    heavily overlapping boxes whose near-threshold NMS decisions flip under fp16 noise, hence the
+    loose survival bound; exact NMS behaviour is covered by the bit-exact NMS tests.)"""
     m = oracle_model("v8", "detect", "n")
     x = synth_image(4, 640, 640)
     with torch.no_grad():
@@ -230,11 +252,16 @@ def test_fp16_detections_640(y):
     net = y.Yolov8(80, yoloSize="n", dtype=torch.float16, max_batch=4)
     net.load_state_dict(m.state_dict())
     pred = net.forward(x.half().cuda())[0]["boxes"]
-    out, _ = y.Ops.non_max_suppression(pred, 0.25, 0.45)
-    oout, _ = oops.non_max_suppression(ref, 0.25, 0.45)
+    err = (pred.cpu() - ref).abs()
+    assert float(err[:, :4].max()) < 4.0 and float(err[:, 4:].max()) < 0.05
+    out, keep = y.Ops.non_max_suppression(pred, 0.25, 0.45)
+    oout, okeep = oops.non_max_suppression(pred.cpu(), 0.25, 0.45)  # same input -> must be identical
     for i in range(4):
-        strong = oout[i][oout[i][:, 4] > 0.35]
-        assert match_detections(strong, out[i].cpu()) > 0.95
+        assert torch.equal(keep[i].cpu(), okeep[i]) and torch.equal(out[i].cpu(), oout[i])
+    oref, _ = oops.non_max_suppression(ref, 0.25, 0.45)
+    for i in range(4):
+        strong = oref[i][oref[i][:, 4] > 0.35]
+        assert match_detections(strong, out[i].cpu(), iou_thr=0.85) > 0.8
 
 
 def test_batch_independence_full_size(y):

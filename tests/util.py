@@ -87,11 +87,11 @@ def oracle_activations(model, x):
 def expected_for_op(model, acts, op_name):
     """Oracle tensor that the engine op `op_name` should reproduce (or None if not comparable).
     A Bottleneck's cv2 op includes the shortcut add, so it maps to the Bottleneck output."""
+    if op_name.endswith(".m") and op_name[:-2] in acts:
+        sppf = model.get_submodule(op_name[:-2])
+        if isinstance(sppf, om.SPPF):  # SPPF pool op: the engine view is the first pooled map
+            return sppf.m(acts[op_name[:-2] + ".cv1"])
     if op_name not in acts:
-        if op_name.endswith(".m") and op_name[:-2] in acts:  # SPPF pool op: first pooled map
-            sppf = model.get_submodule(op_name[:-2])
-            if isinstance(sppf, om.SPPF):
-                return sppf.m(acts[op_name[:-2] + ".cv1"])
         return None
     t = acts[op_name]
     if not torch.is_tensor(t):

@@ -44,6 +44,9 @@ SIGNATURES = {
     "yb_debug_read_activation": (c_i32, [c_vp, c_i32, c_i32, c_vp, C.c_int64, C.POINTER(c_i32 * 3)]),
     "yb_op_name": (c_cp, [c_vp, c_i32]),
     "yb_launches_per_forward": (c_i32, [c_vp]),
+    "yb_profile_forward": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),
+    "yb_op_cost": (c_i32, [c_vp, c_i32, c_i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "yb_op_kind": (c_i32, [c_vp, c_i32]),
 }
 
 _lib = None

@@ -447,7 +447,14 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    // dynamic limit = ring budget + alignment slack (static smem of the kernel counts against the 227 KiB cap)
+    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
+    if (ce != cudaSuccess) {
+      if (err) *err = std::string("cudaFuncSetAttribute(conv_tc_kernel) failed: ") + cudaGetErrorString(ce);
+      num_sms = 0;
+      delete plan;
+      return nullptr;
+    }
   }
   plan->grid = num_sms;
   return plan;

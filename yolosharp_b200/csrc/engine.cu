@@ -456,11 +456,12 @@ static ConvParams conv_params(const yb_engine* e, const OpDesc& op, int B) {
 
 template <typename T>
 static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out_pred, float* out_proto,
-                   cudaStream_t s) {
+                   cudaStream_t s, cudaEvent_t* events = nullptr) {
   int rc;
   bool input_converted = false;
   for (size_t i = 0; i < e->ops.size(); i++) {
     OpDesc& op = e->ops[i];
+    if (events) YB_CUDA_CHECK(cudaEventRecord(events[i], s));
     switch (op.type) {
       case OP_CONV: {
         if (i == 0 && e->has_stem_tc) {
@@ -513,6 +514,7 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
         return YB_ERR_NOT_IMPLEMENTED;
     }
   }
+  if (events) YB_CUDA_CHECK(cudaEventRecord(events[e->ops.size()], s));
   return 0;
 }
 
@@ -785,6 +787,63 @@ int32_t yb_debug_read_activation(yb_engine* e, int32_t op_index, int32_t batch, 
   }
   cudaFree(d);
   return rc;
+}
+
+int32_t yb_profile_forward(yb_engine* e, const void* in, int32_t in_dtype, int32_t batch, float* out_pred,
+                           float* out_proto, float* ms_per_op, int32_t n_ops, void* stream) {
+  if (!e || !in || !out_pred || !ms_per_op) { set_error("yb_profile_forward: null argument"); return YB_ERR_INVALID_ARG; }
+  if (!e->finalized) { set_error("yb_profile_forward: call yb_finalize_weights first"); return YB_ERR_STATE; }
+  if (batch <= 0 || batch > e->cfg.max_batch || n_ops < (int32_t)e->ops.size()) { set_error("yb_profile_forward: bad batch / n_ops"); return YB_ERR_INVALID_ARG; }
+  YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev(e->ops.size() + 1);
+  for (auto& x : ev) YB_CUDA_CHECK(cudaEventCreate(&x));
+  int rc = e->cfg.precision == YB_PREC_F16 ? run_ops<__half>(e, in, in_dtype, batch, out_pred, out_proto, s, ev.data())
+                                           : run_ops<float>(e, in, in_dtype, batch, out_pred, out_proto, s, ev.data());
+  if (!rc && cudaStreamSynchronize(s) != cudaSuccess) { set_error("yb_profile_forward: sync failed"); rc = YB_ERR_CUDA; }
+  if (!rc)
+    for (size_t i = 0; i < e->ops.size(); i++) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
+  for (auto& x : ev) cudaEventDestroy(x);
+  return rc;
+}
+
+int32_t yb_op_cost(const yb_engine* e, int32_t i, int32_t batch, double* flops, double* bytes) {
+  if (!e || i < 0 || i >= (int32_t)e->ops.size() || !flops || !bytes) { set_error("yb_op_cost: bad argument"); return YB_ERR_INVALID_ARG; }
+  const OpDesc& op = e->ops[i];
+  auto vbytes = [&](VRef r) -> double {
+    if (r.buf < 0) return 0.0;
+    const BufDesc& b = e->bufs[r.buf];
+    return (double)batch * b.H * b.W * r.C * e->esize;
+  };
+  *flops = 0;
+  *bytes = vbytes(op.in) + vbytes(op.out) + vbytes(op.res) + vbytes(op.out2) + vbytes(op.out3);
+  if (op.type == OP_CONV || op.type == OP_DWCONV) {
+    const BufDesc& ob = e->bufs[op.out.buf];
+    const double macs = (double)batch * ob.H * ob.W * op.cout * (op.cin / op.groups) * op.k * op.k;
+    *flops = 2.0 * macs;
+    *bytes += (double)op.cout * (op.cin / op.groups) * op.k * op.k * e->esize;
+    if (i == 0) {  // stem reads the caller's NCHW tensor, not an engine buffer
+      *bytes -= vbytes(op.in);
+      *bytes += (double)batch * 3 * e->cfg.height * e->cfg.width * e->esize;
+    }
+  } else if (op.type == OP_DECODE) {
+    *bytes = vbytes(op.in) + vbytes(op.cls) + vbytes(op.coef) +
+             (double)batch * e->pred_c * e->bufs[op.in.buf].H * e->bufs[op.in.buf].W * 4.0;
+  }
+  return YB_OK;
+}
+
+int32_t yb_op_kind(const yb_engine* e, int32_t i) {
+  if (!e || i < 0 || i >= (int32_t)e->ops.size()) return -1;
+  const OpDesc& op = e->ops[i];
+  switch (op.type) {
+    case OP_CONV: return (i == 0 && e->has_stem_tc) ? 2 : (op.use_tc ? 0 : 1);
+    case OP_DWCONV: return 3;
+    case OP_POOL: return 4;
+    case OP_UPSAMPLE: return 5;
+    case OP_DECODE: return 6;
+    default: return 7;
+  }
 }
 
 int32_t yb_launches_per_forward(const yb_engine* e) {

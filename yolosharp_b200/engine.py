@@ -115,6 +115,28 @@ class Engine:
         c, h, w = chw
         return torch.from_numpy(buf[:batch * c * h * w].reshape(batch, c, h, w).copy())
 
+    def profile(self, x, out_pred=None, stream=None):
+        """Per-op device times (ms) of one eager forward + per-op algorithmic flops/bytes/kind."""
+        lib = L.lib()
+        n = lib.yb_num_ops(self._h)
+        B = x.shape[0]
+        code = {torch.uint8: L.YB_U8, torch.float16: L.YB_F16, torch.float32: L.YB_F32}[x.dtype]
+        if out_pred is None:
+            out_pred = torch.empty((B, self.pred_channels, self.anchors), dtype=torch.float32, device=x.device)
+        proto = torch.empty((B, 32, self.height // 4, self.width // 4), dtype=torch.float32, device=x.device) \
+            if self.task == "segment" else None
+        ms = (C.c_float * n)()
+        L.check(lib.yb_profile_forward(self._h, C.c_void_p(x.data_ptr()), code, B, C.c_void_p(out_pred.data_ptr()),
+                                       C.c_void_p(proto.data_ptr()) if proto is not None else None, ms, n,
+                                       _stream_ptr(stream)))
+        rows = []
+        for i in range(n):
+            fl, by = C.c_double(), C.c_double()
+            L.check(lib.yb_op_cost(self._h, i, B, C.byref(fl), C.byref(by)))
+            rows.append(dict(index=i, name=lib.yb_op_name(self._h, i).decode(), kind=lib.yb_op_kind(self._h, i),
+                             ms=float(ms[i]), flops=fl.value, bytes=by.value))
+        return rows
+
     def launches_per_forward(self):
         return L.lib().yb_launches_per_forward(self._h)
 
