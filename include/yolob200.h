@@ -68,6 +68,8 @@ typedef struct {
 
 #define YB_FLAG_NO_TCGEN05 1  /* F16 mode: use the CUDA-core fp16 kernels instead of tcgen05 (debug) */
 #define YB_FLAG_NO_GRAPH   2  /* do not capture the forward into a CUDA graph */
+#define YB_FLAG_DRY_RUN    4  /* build the op graph / expected-tensor list only (no CUDA calls; for host-side checks).
+                                 Every compute entry point fails with YB_ERR_STATE on such an engine. */
 
 typedef struct yb_engine yb_engine;
 

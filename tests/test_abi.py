@@ -89,3 +89,22 @@ def test_bin_roundtrip(tmp_path):
         assert len(r) == 357
         binfmt.write_bin(p, r)
         assert open(p, "rb").read() == open(ref, "rb").read()
+
+
+@pytest.mark.parametrize("arch,task,size", [("v8", "detect", "n"), ("v8", "detect", "s"), ("v8", "detect", "m"),
+                                           ("v8", "detect", "l"), ("v8", "detect", "x"), ("v11", "detect", "n"),
+                                           ("v11", "detect", "s"), ("v11", "detect", "m"), ("v11", "detect", "x"),
+                                           ("v8", "segment", "n"), ("v8", "segment", "s"), ("v11", "segment", "n")])
+def test_graph_tensor_names_match_reference_state_dict(built_lib, arch, task, size):
+    """The engine's op graph (dry run, no GPU) asks for exactly the reference's state_dict entries:
+    every oracle key is expected except the bookkeeping ones the reference never reads on this path."""
+    import yolosharp_b200 as y
+    from yolosharp_b200 import _lib as L
+    from oracle import yolo as oyolo
+    e = y.Engine(arch, size, task, 80, "f32", 0, 1, 64, 64, flags=L.YB_FLAG_DRY_RUN)
+    want = e.expected_tensors()
+    e.close()
+    assert len(want) == len(set(want))
+    keys = [k for k in oyolo.build(arch, task, size).state_dict()
+            if not k.endswith(("num_batches_tracked", ".anchors", ".strides", "dfl.conv.weight"))]
+    assert sorted(want) == sorted(keys)

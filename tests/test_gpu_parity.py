@@ -30,8 +30,8 @@ def y():
     return yolosharp_b200
 
 
-def make_engine(y, model, prec, B, H, W, size="n", flags=0):
-    e = y.Engine("v8", size, "detect", 80, prec, 0, B, H, W, flags=flags)
+def make_engine(y, model, prec, B, H, W, size="n", flags=0, arch="v8", task="detect"):
+    e = y.Engine(arch, size, task, 80, prec, 0, B, H, W, flags=flags)
     e.load_state_dict(model.state_dict())
     e.finalize()
     return e
@@ -92,9 +92,11 @@ def test_nms_errors(y):
 
 
 # ------------------------------------------------------------------ forward, fp32 parity mode
-def check_layers(e, model, x, tol, B):
+def check_layers(e, model, x, tol, B, min_ops=55):
     (inf, _), acts = oracle_activations(model, x)
     pred = e.forward(x.cuda())
+    if isinstance(pred, tuple):
+        pred = pred[0]
     torch.cuda.synchronize()
     worst = ("", 0.0)
     n = 0
@@ -102,13 +104,17 @@ def check_layers(e, model, x, tol, B):
         exp = expected_for_op(model, acts, name)
         if exp is None:
             continue
-        got = e.read_activation(i, B)
+        try:
+            got = e.read_activation(i, B)
+        except Exception as ex:  # head convs whose epilogue writes pred directly have no NHWC output
+            assert "fused head decode" in str(ex), ex
+            continue
         assert tuple(got.shape) == tuple(exp.shape), name
         err = rel_err(got, exp)
         assert err < tol, f"op {i} {name}: rel err {err:.3e}"
         worst = max(worst, (name, err), key=lambda t: t[1])
         n += 1
-    assert n >= 60
+    assert n >= min_ops
     return pred.cpu(), inf["boxes"], worst
 
 
@@ -209,13 +215,18 @@ def test_fp16_tcgen05_matches_cuda_core_twin(y):
         x = synth_image(2, *hw).cuda()
         a = make_engine(y, m, "f16", 2, hw[0], hw[1], size, flags=0)
         b = make_engine(y, m, "f16", 2, hw[0], hw[1], size, flags=1)
-        a.forward(x)
-        b.forward(x)
+        pa = a.forward(x).clone()
+        pb = b.forward(x).clone()
         torch.cuda.synchronize()
+        assert float((pa - pb).abs()[:, :4].max()) < 1.0 and float((pa - pb).abs()[:, 4:].max()) < 0.02
         for i, name in enumerate(a.op_names()):
             if "decode" in name:
                 continue
-            ga, gb = a.read_activation(i, 2), b.read_activation(i, 2)
+            try:
+                ga, gb = a.read_activation(i, 2), b.read_activation(i, 2)
+            except Exception as ex:
+                assert "fused head decode" in str(ex), ex
+                continue
             assert rel_err(ga, gb) < 1e-2, f"v8{size} op {i} {name}: {rel_err(ga, gb):.3e}"
         a.close()
         b.close()
@@ -305,3 +316,59 @@ def test_missing_weight_is_an_error(y):
     with pytest.raises(y.YbError) as ei:
         e.finalize()
     assert "model.4.cv2.bn.running_var" in str(ei.value)
+
+
+# ------------------------------------------------------------------ YOLOv11 (C3k2 / C2PSA / DW head)
+@pytest.mark.parametrize("prec,flags,tol,ptol", [("f32", 0, 1e-4, (1e-3, 1e-3)), ("f16", 0, 3e-2, (4.0, 0.05))])
+def test_v11n_layers_and_pred(y, prec, flags, tol, ptol):
+    m = oracle_model("v11", "detect", "n")
+    x = synth_image(2, 256, 320)
+    e = make_engine(y, m, prec, 2, 256, 320, flags=flags, arch="v11")
+    pred, ref, worst = check_layers(e, m, x, tol, 2, min_ops=80)
+    if prec == "f32":
+        np.testing.assert_allclose(pred.numpy(), ref.numpy(), rtol=ptol[0], atol=ptol[1])
+    else:
+        err = (pred - ref).abs()
+        assert float(err[:, :4].max()) < ptol[0] and float(err[:, 4:].max()) < ptol[1]
+
+
+def test_v11s_fp32_pred(y):
+    """configs[3] architecture (YOLOv11s; forward only - the train step is not built yet)."""
+    m = oracle_model("v11", "detect", "s")
+    x = synth_image(1, 128, 160)
+    e = make_engine(y, m, "f32", 1, 128, 160, size="s", arch="v11")
+    with torch.no_grad():
+        ref = m(x)[0]["boxes"]
+    np.testing.assert_allclose(e.forward(x.cuda()).cpu().numpy(), ref.numpy(), rtol=1e-3, atol=1e-3)
+
+
+# ------------------------------------------------------------------ segmentation (Segment head, Proto, masks)
+@pytest.mark.parametrize("prec,size", [("f32", "n"), ("f16", "n"), ("f32", "s")])
+def test_v8_seg_pred_proto_masks(y, prec, size):
+    m = oracle_model("v8", "segment", size)
+    B, H, W = 2, 160, 192
+    x = synth_image(B, H, W)
+    e = make_engine(y, m, prec, B, H, W, size=size, task="segment")
+    with torch.no_grad():
+        inf, _ = m(x)
+    pred, proto = e.forward(x.cuda())
+    assert tuple(pred.shape) == tuple(inf["boxes"].shape) and tuple(proto.shape) == tuple(inf["proto"].shape)
+    if prec == "f32":
+        np.testing.assert_allclose(pred.cpu().numpy(), inf["boxes"].numpy(), rtol=1e-3, atol=1e-3)
+        np.testing.assert_allclose(proto.cpu().numpy(), inf["proto"].numpy(), rtol=1e-3, atol=1e-3)
+    else:
+        assert rel_err(proto.cpu(), inf["proto"]) < 3e-2
+        assert float((pred.cpu() - inf["boxes"]).abs()[:, 4:84].max()) < 0.05
+    # NMS with 32 extra columns + masks, both computed from the ENGINE's pred/proto on each side
+    dets, counts, keep = y.nms(pred, 0.25, 0.45, 300, 80)
+    out, keepi = oops.non_max_suppression(pred.cpu(), 0.25, 0.45, nc=80)
+    masks = y.masks(proto, dets, counts, H, W).cpu()
+    for i in range(B):
+        n = counts[i].item()
+        assert n == out[i].shape[0] and torch.equal(keep[i, :n].cpu().long(), keepi[i])
+        assert torch.equal(dets[i, :n].cpu(), out[i])
+        if n == 0:
+            continue
+        ref_masks = oops.process_mask(proto[i].cpu(), out[i][:, 6:], out[i][:, :4], (H, W), upsample=True)
+        agree = (masks[i, :n].bool() == ref_masks.bool()).float().mean().item()
+        assert agree > 0.999, agree

@@ -91,6 +91,12 @@ def expected_for_op(model, acts, op_name):
         sppf = model.get_submodule(op_name[:-2])
         if isinstance(sppf, om.SPPF):  # SPPF pool op: the engine view is the first pooled map
             return sppf.m(acts[op_name[:-2] + ".cv1"])
+    if op_name.endswith((".attn.pe", ".attn.proj", ".proto.upsample")):
+        return None  # engine op = module output + fused residual / pre-shuffle layout: no oracle twin
+    if op_name.endswith(".ffn.1"):  # PSABlock output: b1 + ffn(b1)
+        return acts.get(op_name[:-len(".ffn.1")])
+    if op_name.endswith(".upsample.shuffle"):
+        return acts.get(op_name[:-len(".shuffle")])
     if op_name not in acts:
         return None
     t = acts[op_name]

@@ -21,7 +21,7 @@ SIZES = {"n": 0, "s": 1, "m": 2, "l": 3, "x": 4}
 YB_TASK_DETECT, YB_TASK_SEGMENT = 0, 1
 YB_PREC_F32, YB_PREC_F16 = 0, 1
 YB_U8, YB_F16, YB_F32, YB_BF16 = 0, 5, 6, 15
-YB_FLAG_NO_TCGEN05, YB_FLAG_NO_GRAPH = 1, 2
+YB_FLAG_NO_TCGEN05, YB_FLAG_NO_GRAPH, YB_FLAG_DRY_RUN = 1, 2, 4
 
 # name -> (restype, argtypes); must list every function declared in include/yolob200.h
 SIGNATURES = {

@@ -93,10 +93,9 @@ class _YoloModule:
         for e in self._engines.values():
             e.close()
         self._engines = {}
-        probe = self._engine(64, 64, 1, finalize=False)
+        probe = Engine(self.arch, self.yoloSize, self.task, self.nc, "f32", 0, 1, 64, 64, flags=L.YB_FLAG_DRY_RUN)
         want = probe.expected_tensors()
         probe.close()
-        self._engines = {}
         missing = [k for k in want if k not in self._state]
         ws = set(want)
         unexpected = [k for k in self._state if k not in ws]

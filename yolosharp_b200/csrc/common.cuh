@@ -22,9 +22,22 @@ struct View {
 
 enum Act { ACT_NONE = 0, ACT_SILU = 1 };
 
+// Head-tail fusion (tcgen05 path): the final 1x1 convs of the Detect branches write straight into the
+// prediction tensor (B, Ctot, A) instead of an NHWC buffer (Modules/Head.cs:204-223 decode).
+enum EpiMode { EPI_STORE = 0, EPI_DFL_BOX = 1, EPI_SIGMOID = 2, EPI_RAW = 3 };
+struct EpiDecode {
+  int mode = EPI_STORE;
+  int A = 0, Ctot = 0;  // anchors per image, channels of pred
+  int a0 = 0;           // first anchor of this pyramid level
+  int ch0 = 0;          // first pred channel written (4 for class probs, 4+nc for mask coeffs)
+  int Wl = 0, HW = 0;   // level width, pixels per image
+  float stride = 0.f;
+};
+
 struct ConvParams {
   View in, out, res;  // res.base == nullptr -> no residual
   View out2;          // optional second destination: nearest-2x upsampled copy (out2.base != nullptr)
+  EpiDecode dec;
   const void* w;      // packed weights, layout depends on kernel
   const float* bias;  // [Cout] fp32 (folded BN beta - mean*scale, or conv bias)
   int B;
@@ -71,6 +84,12 @@ template <typename T>
 int launch_decode_level(const View& box, const View& cls, const View* coef, int B, int nc, int nm,
                         int reg_max, float stride, int a0, int A, int Ctot, float* pred,
                         cudaStream_t s);
+template <typename T>
+int launch_pixel_shuffle2(const View& in, const View& out, int B, cudaStream_t s);
+// C2PSA attention core: qkv (B,N,nh*(2kd+hd)) -> out (B,N,nh*hd) and the dense v copy for the pe conv
+template <typename T>
+int launch_attention(const View& qkv, const View& out, const View& vout, int B, int nh, int kd, int hd, float scale,
+                     cudaStream_t s);
 // proto (B,h,w,32) NHWC T -> (B,32,h,w) fp32
 template <typename T>
 int launch_proto_out(const View& in, float* out, int B, cudaStream_t s);
@@ -79,7 +98,7 @@ int launch_proto_out(const View& in, float* out, int B, cudaStream_t s);
 struct TcConvPlan;  // opaque: tensor maps + tiling for one conv layer
 TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err);
 void tc_conv_plan_destroy(TcConvPlan* plan);
-int tc_conv_launch(const TcConvPlan* plan, int B, cudaStream_t s);
+int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s);
 bool tc_conv_supported(const ConvParams& p);
 // stem: NCHW u8/f16/f32 input -> 3x3 s2 conv (Cin=3) + bias + SiLU -> NHWC fp16
 int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const float* w /*[27][Cout]*/,

@@ -25,8 +25,11 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace yb {
+
+enum TcMode { TC_TAP = 0, TC_HALO = 1 };
 
 struct TcArgs {
   CUtensorMap tmA;
@@ -43,13 +46,21 @@ struct TcArgs {
   int ksz, stride, pad;
   int Cin, BK, chunks;   // chunks = Cin / BK
   int act;
-  int stages;
-  uint32_t a_bytes, b_bytes;      // TMA transaction bytes per slab
+  int mode;                       // TcMode
+  int stages_a, stages_b;
+  uint32_t a_bytes, b_bytes;      // TMA transaction bytes per A slab / B slab
   uint32_t a_stride, b_stride;    // smem bytes reserved per slab (1 KiB aligned)
-  uint32_t sbo;                   // UMMA stride-byte-offset (8 rows), >> 4
+  uint32_t sbo_a, sbo_b;          // UMMA stride-byte-offset between 8-row groups, >> 4
+  uint32_t row_bytes;             // BK * 2
   uint32_t layout_type;           // UMMA LayoutType: 2 = SW128, 4 = SW64, 6 = SW32
   uint32_t tmem_cols;
   int total_tiles;
+  int b_resident;                 // all weight slabs stay in smem for the CTA's lifetime
+  int ksteps;
+  // fused head decode (EpiDecode)
+  int epi_mode, dA, dCtot, da0, dch0, dWl, dHW;
+  float dstride;
+  float* pred;
 };
 
 struct TcConvPlan {
@@ -60,109 +71,60 @@ struct TcConvPlan {
   int grid;
 };
 
-// ------------------------------------------------------------------------------------------
-// PTX helpers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P1;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major operand, swizzled rows (cute::UMMA::SmemDescriptor):
-//  [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 |
-//  [46,48) version=1 | [61,64) layout type
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo, uint32_t layout_type) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)sbo << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)layout_type << 61);
-}
-
 __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 constexpr int TC_THREADS = 192;
-constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_STAGES = 12;
+constexpr int HALO_BW = 8, HALO_BH = 16;  // output rectangle of a halo tile (128 rows)
 
+// ------------------------------------------------------------------------------------------
+// Two operand rings feed the single MMA-issuing thread:
+//   A ring  : TC_TAP  - one 128-row slab per (tap, channel slab)
+//             TC_HALO - one (BH+2)x(BW+2)-pixel halo tile per channel slab; the 9 taps of a 3x3
+//                       stride-1 conv are issued from the SAME bytes with the descriptor start
+//                       shifted by (kh*(BW+2)+kw) rows and SBO = (BW+2) rows.  tcgen05 applies the
+//                       128B/64B/32B swizzle on absolute smem address bits, so a row-shifted start
+//                       needs no base-offset (verified on B200 by tools/exp_umma_shift.cu).
+//                       -> 180 TMA rows per slab instead of 9 x 128: the kernel is bound by L2
+//                       request rate (~30 requests/clk chip-wide), not by bytes.
+//   B ring  : one [n_tile x BK] weight slab per (tap, channel slab), or all slabs resident.
+// ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
-  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[4 * TC_MAX_STAGES + 5];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // dynamic smem base rounded up to 1 KiB (SWIZZLE_128B atoms need it)
   const uint32_t smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
   const uint32_t smemA = smem0;
-  const uint32_t smemB = smem0 + a.stages * a.a_stride;
-  const uint32_t full0 = smem_u32(&bars[0]);
-  const uint32_t empty0 = smem_u32(&bars[TC_MAX_STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * TC_MAX_STAGES]);
-  const uint32_t tempty0 = smem_u32(&bars[2 * TC_MAX_STAGES + 2]);
+  const uint32_t smemB = smem0 + a.stages_a * a.a_stride;
+  const uint32_t fullA = smem_u32(&bars[0]);
+  const uint32_t emptyA = smem_u32(&bars[TC_MAX_STAGES]);
+  const uint32_t fullB = smem_u32(&bars[2 * TC_MAX_STAGES]);
+  const uint32_t emptyB = smem_u32(&bars[3 * TC_MAX_STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[4 * TC_MAX_STAGES]);
+  const uint32_t tempty0 = smem_u32(&bars[4 * TC_MAX_STAGES + 2]);
+  const uint32_t bfull = smem_u32(&bars[4 * TC_MAX_STAGES + 4]);
+
+  // PDL: let the next kernel of the stream/graph start its prologue while this grid runs; it blocks in
+  // its own griddepcontrol.wait until this grid has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < a.stages; s++) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
+    for (int s = 0; s < a.stages_a; s++) {
+      mbar_init(fullA + 8 * s, 1);
+      mbar_init(emptyA + 8 * s, 1);
+    }
+    for (int s = 0; s < a.stages_b; s++) {
+      mbar_init(fullB + 8 * s, 1);
+      mbar_init(emptyB + 8 * s, 1);
     }
     for (int s = 0; s < 2; s++) {
       mbar_init(tfull0 + 8 * s, 1);
       mbar_init(tempty0 + 8 * s, 4);  // one arrive per epilogue warp
     }
+    mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -177,16 +139,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  const int ksteps = a.ksz * a.ksz * a.chunks;
+  const int taps = a.ksz * a.ksz;
   const int tiles_per_img = a.tiles_w * a.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmB) : "memory");
+    if (a.b_resident) {
+      // weights do not depend on the previous kernel: fetch them before the grid dependency resolves
+      mbar_arrive_expect_tx(bfull, a.b_bytes * a.ksteps);
+      for (int t = 0; t < taps; t++)
+        for (int ch = 0; ch < a.chunks; ch++)
+          tma_load_2d(smemB + (t * a.chunks + ch) * a.b_stride, &a.tmB, bfull, t * a.Cin + ch * a.BK, 0);
+    }
+  }
+  // activations written by the previous kernel are visible only after this point
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmB) : "memory");
-      int stage = 0;
-      uint32_t phase = 0;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int nt = tile % a.n_tiles;
         const int mt = tile / a.n_tiles;
@@ -195,14 +169,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int th = r / a.tiles_w, tw = r - th * a.tiles_w;
         const int wbase = tw * a.BW * a.stride - a.pad;
         const int hbase = th * a.BH * a.stride - a.pad;
-        for (int t = 0; t < a.ksz * a.ksz; t++) {
-          const int kh = t / a.ksz, kw = t - kh * a.ksz;
+        if (a.mode == TC_HALO) {
           for (int ch = 0; ch < a.chunks; ch++) {
-            mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            mbar_arrive_expect_tx(full0 + 8 * stage, a.a_bytes + a.b_bytes);
-            tma_load_4d(smemA + stage * a.a_stride, &a.tmA, full0 + 8 * stage, ch * a.BK, wbase + kw, hbase + kh, img);
-            tma_load_2d(smemB + stage * a.b_stride, &a.tmB, full0 + 8 * stage, t * a.Cin + ch * a.BK, nt * a.n_tile);
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            mbar_wait(emptyA + 8 * sa, pa ^ 1);
+            mbar_arrive_expect_tx(fullA + 8 * sa, a.a_bytes);
+            tma_load_4d(smemA + sa * a.a_stride, &a.tmA, fullA + 8 * sa, ch * a.BK, wbase, hbase, img);
+            if (++sa == a.stages_a) { sa = 0; pa ^= 1; }
+            if (!a.b_resident)
+              for (int t = 0; t < taps; t++) {
+                mbar_wait(emptyB + 8 * sb, pb ^ 1);
+                mbar_arrive_expect_tx(fullB + 8 * sb, a.b_bytes);
+                tma_load_2d(smemB + sb * a.b_stride, &a.tmB, fullB + 8 * sb, t * a.Cin + ch * a.BK, nt * a.n_tile);
+                if (++sb == a.stages_b) { sb = 0; pb ^= 1; }
+              }
+          }
+        } else {
+          for (int t = 0; t < taps; t++) {
+            const int kh = t / a.ksz, kw = t - kh * a.ksz;
+            for (int ch = 0; ch < a.chunks; ch++) {
+              mbar_wait(emptyA + 8 * sa, pa ^ 1);
+              mbar_arrive_expect_tx(fullA + 8 * sa, a.a_bytes);
+              tma_load_4d(smemA + sa * a.a_stride, &a.tmA, fullA + 8 * sa, ch * a.BK, wbase + kw, hbase + kh, img);
+              if (++sa == a.stages_a) { sa = 0; pa ^= 1; }
+              if (!a.b_resident) {
+                mbar_wait(emptyB + 8 * sb, pb ^ 1);
+                mbar_arrive_expect_tx(fullB + 8 * sb, a.b_bytes);
+                tma_load_2d(smemB + sb * a.b_stride, &a.tmB, fullB + 8 * sb, t * a.Cin + ch * a.BK, nt * a.n_tile);
+                if (++sb == a.stages_b) { sb = 0; pb ^= 1; }
+              }
+            }
           }
         }
       }
@@ -213,24 +208,70 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b F16, K-major both,
       // n_dim = N>>3 at bit 17, m_dim = 128>>4 at bit 24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(a.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
+      const int kk = a.BK >> 4;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       int acc = 0;
       uint32_t aphase = 0;
+      if (a.b_resident) mbar_wait(bfull, 0);
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         mbar_wait(tempty0 + 8 * acc, aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * a.n_tile;
-        for (int ks = 0; ks < ksteps; ks++) {
-          mbar_wait(full0 + 8 * stage, phase);
-          tc_fence_after();
-          const uint64_t ad = umma_desc(smemA + stage * a.a_stride, a.sbo, a.layout_type);
-          const uint64_t bd = umma_desc(smemB + stage * a.b_stride, a.sbo, a.layout_type);
-          const int kk = a.BK >> 4;
-          for (int k = 0; k < kk; k++)  // +32 B per K=16 step inside the swizzled row
-            umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (ks | k) != 0);
-          umma_commit(empty0 + 8 * stage);  // slab free once these MMAs retire
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        uint32_t first = 1;
+        if (a.mode == TC_HALO) {
+          for (int ch = 0; ch < a.chunks; ch++) {
+            mbar_wait(fullA + 8 * sa, pa);
+            tc_fence_after();
+            const uint32_t abase = smemA + sa * a.a_stride;
+            for (int t = 0; t < taps; t++) {
+              const int kh = t / 3, kw = t - kh * 3;
+              uint32_t bslab;
+              if (a.b_resident) {
+                bslab = smemB + (t * a.chunks + ch) * a.b_stride;
+              } else {
+                mbar_wait(fullB + 8 * sb, pb);
+                tc_fence_after();
+                bslab = smemB + sb * a.b_stride;
+              }
+              const uint64_t ad = umma_desc(abase + (kh * (a.BW + 2) + kw) * a.row_bytes, a.sbo_a, a.layout_type);
+              const uint64_t bd = umma_desc(bslab, a.sbo_b, a.layout_type);
+              for (int k = 0; k < kk; k++) {  // +32 B per K=16 step inside the swizzled row
+                umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, first ^ 1u);
+                first = 0;
+              }
+              if (!a.b_resident) {
+                umma_commit(emptyB + 8 * sb);
+                if (++sb == a.stages_b) { sb = 0; pb ^= 1; }
+              }
+            }
+            umma_commit(emptyA + 8 * sa);  // halo tile free once its 9 taps retired
+            if (++sa == a.stages_a) { sa = 0; pa ^= 1; }
+          }
+        } else {
+          for (int ks = 0; ks < a.ksteps; ks++) {
+            mbar_wait(fullA + 8 * sa, pa);
+            uint32_t bslab;
+            if (a.b_resident) {
+              bslab = smemB + ks * a.b_stride;
+            } else {
+              mbar_wait(fullB + 8 * sb, pb);
+              bslab = smemB + sb * a.b_stride;
+            }
+            tc_fence_after();
+            const uint64_t ad = umma_desc(smemA + sa * a.a_stride, a.sbo_a, a.layout_type);
+            const uint64_t bd = umma_desc(bslab, a.sbo_b, a.layout_type);
+            for (int k = 0; k < kk; k++) {
+              umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, first ^ 1u);
+              first = 0;
+            }
+            umma_commit(emptyA + 8 * sa);  // slab free once these MMAs retire
+            if (++sa == a.stages_a) { sa = 0; pa ^= 1; }
+            if (!a.b_resident) {
+              umma_commit(emptyB + 8 * sb);
+              if (++sb == a.stages_b) { sb = 0; pb ^= 1; }
+            }
+          }
         }
         umma_commit(tfull0 + 8 * acc);  // accumulator complete
         acc ^= 1;
@@ -260,6 +301,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_wait(tfull0 + 8 * acc, aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * a.n_tile;
+      if (a.epi_mode != EPI_STORE) {
+        // fused Detect tail (flattened 1x1 conv): this thread's row is pixel `wo` of the whole batch
+        const int n = valid ? wo / a.dHW : 0;
+        const int i = wo - n * a.dHW;
+        float* po = a.pred + (size_t)n * a.dCtot * a.dA + a.da0 + i;
+        if (a.epi_mode == EPI_DFL_BOX) {
+          // DFL (Block.cs:44): softmax over the 16 bins of each side, expectation with weights 0..15;
+          // then dist2bbox(xywh) * stride (Tal.cs:338-356, Head.cs:221)
+          float d[4];
+#pragma unroll
+          for (int sd = 0; sd < 4; sd++) {
+            uint32_t v[16];
+            tmem_ld16(taddr + sd * 16, v);
+            tmem_ld_wait();
+            float f[16], mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 16; j++) { f[j] = __uint_as_float(v[j]) + __ldg(a.bias + sd * 16 + j); mx = fmaxf(mx, f[j]); }
+            float sum = 0.f, ex = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; j++) { const float e = __expf(f[j] - mx); sum += e; ex = fmaf(e, (float)j, ex); }
+            d[sd] = __fdividef(ex, sum);
+          }
+          if (valid) {
+            const int y = i / a.dWl, x = i - y * a.dWl;
+            const float ax = (float)x + 0.5f, ay = (float)y + 0.5f;
+            const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+            po[0] = (x1 + x2) * 0.5f * a.dstride;
+            po[(size_t)a.dA] = (y1 + y2) * 0.5f * a.dstride;
+            po[(size_t)2 * a.dA] = (x2 - x1) * a.dstride;
+            po[(size_t)3 * a.dA] = (y2 - y1) * a.dstride;
+          }
+        } else {
+          for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) {
+                float f = __uint_as_float(v[j]) + __ldg(a.bias + c0 + j);
+                if (a.epi_mode == EPI_SIGMOID) f = __fdividef(1.0f, 1.0f + __expf(-f));
+                po[(size_t)(a.dch0 + c0 + j) * a.dA] = f;  // lanes = consecutive anchors: coalesced
+              }
+            }
+          }
+        }
+      } else
       for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
@@ -372,7 +460,9 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   const CUtensorMapSwizzle swz = a.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                             : (a.BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   a.layout_type = a.BK == 64 ? 2 : (a.BK == 32 ? 4 : 6);
-  a.sbo = (8 * a.BK * 2) >> 4;
+  a.row_bytes = a.BK * 2;
+  a.sbo_a = a.sbo_b = (8 * a.row_bytes) >> 4;
+  a.mode = (p.k == 3 && p.stride == 1) ? TC_HALO : TC_TAP;
 
   plan->flat = (p.k == 1 && p.stride == 1);
   const size_t esz = 2;
@@ -392,17 +482,25 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     gstr[0] = (cuuint64_t)p.in.pitch * esz;
     gstr[1] = gstr[0] * p.in.W;
     gstr[2] = gstr[1] * p.in.H;
-    // choose the output rectangle BW x BH (<= 128 rows) with the least padding waste
-    double best = -1;
-    for (int bw = 1; bw <= std::min(p.Wo, 128); bw++) {
-      const int bh = std::min(p.Ho, 128 / bw);
-      if (bw * p.stride > 256 || bh * p.stride > 256) continue;
-      const double tiles = (double)((p.Wo + bw - 1) / bw) * ((p.Ho + bh - 1) / bh);
-      const double eff = (double)p.Wo * p.Ho / (tiles * 128.0);
-      if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > a.BW)) { best = eff; a.BW = bw; a.BH = bh; }
+    if (a.mode == TC_HALO) {
+      // 8 x 16 output pixels; one TMA box carries the 10 x 18 input halo of a channel slab
+      a.BW = HALO_BW; a.BH = HALO_BH;
+      a.sbo_a = ((a.BW + 2) * a.row_bytes) >> 4;
+      box[0] = a.BK; box[1] = a.BW + 2; box[2] = a.BH + 2; box[3] = 1;
+      estr[0] = estr[1] = estr[2] = estr[3] = 1;
+    } else {
+      // choose the output rectangle BW x BH (<= 128 rows) with the least padding waste
+      double best = -1;
+      for (int bw = 1; bw <= std::min(p.Wo, 128); bw++) {
+        const int bh = std::min(p.Ho, 128 / bw);
+        if (bw * p.stride > 256 || bh * p.stride > 256) continue;
+        const double tiles = (double)((p.Wo + bw - 1) / bw) * ((p.Ho + bh - 1) / bh);
+        const double eff = (double)p.Wo * p.Ho / (tiles * 128.0);
+        if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > a.BW)) { best = eff; a.BW = bw; a.BH = bh; }
+      }
+      box[0] = a.BK; box[1] = a.BW * p.stride; box[2] = a.BH * p.stride; box[3] = 1;
+      estr[0] = 1; estr[1] = p.stride; estr[2] = p.stride; estr[3] = 1;
     }
-    box[0] = a.BK; box[1] = a.BW * p.stride; box[2] = a.BH * p.stride; box[3] = 1;
-    estr[0] = 1; estr[1] = p.stride; estr[2] = p.stride; estr[3] = 1;
   }
   CUresult cr = encode(&a.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, gdim, gstr, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -427,18 +525,43 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
       return nullptr;
     }
   }
-  a.a_bytes = (uint32_t)(a.BW * a.BH * a.BK * 2);
-  a.b_bytes = (uint32_t)(a.n_tile * a.BK * 2);
-  a.a_stride = (uint32_t)((128 * a.BK * 2 + 1023) / 1024 * 1024);
-  a.b_stride = (uint32_t)((a.n_tile * a.BK * 2 + 1023) / 1024 * 1024);
+  const int a_rows = a.mode == TC_HALO ? (a.BW + 2) * (a.BH + 2) : a.BW * a.BH;
+  a.a_bytes = (uint32_t)(a_rows * a.row_bytes);
+  a.b_bytes = (uint32_t)(a.n_tile * a.row_bytes);
+  a.a_stride = (uint32_t)((std::max(a_rows, 128) * a.row_bytes + 1023) / 1024 * 1024);
+  a.b_stride = (uint32_t)((a.n_tile * a.row_bytes + 1023) / 1024 * 1024);
+  a.ksteps = p.k * p.k * a.chunks;
   const size_t budget = 200 * 1024;
-  a.stages = (int)std::min<size_t>(TC_MAX_STAGES, budget / (a.a_stride + a.b_stride));
-  if (a.stages < 2) {
+  // keep the whole weight matrix in smem when it leaves room for >= 3 activation slabs: removes the
+  // weight re-fetch per tile (the kernel is L2-request-bound, not byte-bound)
+  const size_t b_all = (size_t)a.ksteps * a.b_stride;
+  a.b_resident = (a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= budget) ? 1 : 0;
+  if (a.b_resident) {
+    a.stages_a = (int)std::min<size_t>(a.mode == TC_HALO ? 6 : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
+    a.stages_b = 0;
+    plan->smem = (size_t)a.stages_a * a.a_stride + b_all + 1024;
+  } else if (a.mode == TC_HALO) {
+    // A slab serves 9 B slabs: a short A ring and as many weight slabs as fit
+    a.stages_a = (int)std::min<size_t>(3, std::max<size_t>(2, (budget / 3) / a.a_stride));
+    a.stages_b = (int)std::min<size_t>(TC_MAX_STAGES, (budget - (size_t)a.stages_a * a.a_stride) / a.b_stride);
+    plan->smem = (size_t)a.stages_a * a.a_stride + (size_t)a.stages_b * a.b_stride + 1024;
+  } else {
+    a.stages_a = a.stages_b = (int)std::min<size_t>(8, budget / (a.a_stride + a.b_stride));
+    plan->smem = (size_t)a.stages_a * (a.a_stride + a.b_stride) + 1024;
+  }
+  if (a.stages_a < 2 || (!a.b_resident && a.stages_b < 2)) {
     if (err) *err = "tile does not fit in shared memory";
     delete plan;
     return nullptr;
   }
-  plan->smem = (size_t)a.stages * (a.a_stride + a.b_stride) + 1024;
+  a.epi_mode = p.dec.mode;
+  a.dA = p.dec.A; a.dCtot = p.dec.Ctot; a.da0 = p.dec.a0; a.dch0 = p.dec.ch0; a.dWl = p.dec.Wl; a.dHW = p.dec.HW;
+  a.dstride = p.dec.stride;
+  if (a.epi_mode != EPI_STORE && !(plan->flat && a.n_tiles == 1 && (a.epi_mode != EPI_DFL_BOX || a.n_tile == 64))) {
+    if (err) *err = "fused decode epilogue needs a flattened 1x1 conv with a single N tile";
+    delete plan;
+    return nullptr;
+  }
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * a.n_tile)) cols <<= 1;
   a.tmem_cols = cols;
@@ -462,8 +585,9 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
 
 void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
 
-int tc_conv_launch(const TcConvPlan* plan, int B, cudaStream_t s) {
+int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s) {
   TcArgs a = plan->args;
+  a.pred = pred;
   const ConvParams& p = plan->p;
   if (plan->flat) {
     a.imgs = 1;
@@ -479,8 +603,17 @@ int tc_conv_launch(const TcConvPlan* plan, int B, cudaStream_t s) {
   }
   a.total_tiles = a.imgs * a.tiles_w * a.tiles_h * a.n_tiles;
   const int grid = std::min(plan->grid, a.total_tiles);
-  conv_tc_kernel<<<grid, TC_THREADS, plan->smem, s>>>(a);
-  YB_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = plan->smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL (see griddepcontrol in the kernel)
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  YB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel, a));
   return 0;
 }
 
@@ -495,42 +628,55 @@ __device__ __forceinline__ float stem_load(const void* in, int dtype, size_t i) 
   return reinterpret_cast<const float*>(in)[i];
 }
 
+constexpr int ST_TW = 64, ST_TH = 4;  // output tile per block (256 threads = one output pixel each)
+
 __global__ void __launch_bounds__(256) stem_kernel(const void* __restrict__ in, int dtype, int B, int H, int W, int Cout,
                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                    View out) {
-  extern __shared__ float st_smem[];  // [27][Cout] weights + [Cout] bias
-  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) st_smem[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) st_smem[27 * Cout + i] = bias[i];
-  __syncthreads();
+  extern __shared__ __align__(16) float st_smem[];  // [27][Cout] weights | [Cout] bias | [3][2*TH+1][2*TW+1] input patch
+  float* sw = st_smem;
+  float* sb = sw + 27 * Cout;
+  float* sx = sb + Cout;
+  constexpr int PW = 2 * ST_TW + 1, PH = 2 * ST_TH + 1;
   const int Ho = H / 2, Wo = W / 2;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * Ho * Wo) return;
-  const int wo = idx % Wo;
-  const int ho = (idx / Wo) % Ho;
-  const int n = idx / ((size_t)Wo * Ho);
+  const int tiles_w = (Wo + ST_TW - 1) / ST_TW, tiles_h = (Ho + ST_TH - 1) / ST_TH;
+  const int n = blockIdx.x / (tiles_w * tiles_h);
+  const int tr = blockIdx.x - n * tiles_w * tiles_h;
+  const int ho0 = (tr / tiles_w) * ST_TH, wo0 = (tr % tiles_w) * ST_TW;
+  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
+  // coalesced patch load: rows of 2*TW+1 consecutive input pixels per channel (zero = conv padding)
+  const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
+  for (int i = threadIdx.x; i < 3 * PH * PW; i += blockDim.x) {
+    const int c = i / (PH * PW), r = (i / PW) % PH, x = i % PW;
+    const int hi = hi0 + r, wi = wi0 + x;
+    sx[i] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? stem_load(in, dtype, ((size_t)(n * 3 + c) * H + hi) * W + wi) : 0.f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % ST_TW, ty = threadIdx.x / ST_TW;
+  const int ho = ho0 + ty, wo = wo0 + tx;
+  if (ho >= Ho || wo >= Wo) return;
   float x[27];
 #pragma unroll
-  for (int kh = 0; kh < 3; kh++) {
-    const int hi = ho * 2 + kh - 1;
+  for (int kh = 0; kh < 3; kh++)
 #pragma unroll
-    for (int kw = 0; kw < 3; kw++) {
-      const int wi = wo * 2 + kw - 1;
-      const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+    for (int kw = 0; kw < 3; kw++)
 #pragma unroll
-      for (int c = 0; c < 3; c++)
-        x[(kh * 3 + kw) * 3 + c] = ok ? stem_load(in, dtype, ((size_t)(n * 3 + c) * H + hi) * W + wi) : 0.f;
-    }
-  }
-  __half* o = reinterpret_cast<__half*>(out.base) + idx * out.pitch + out.coff;
+      for (int c = 0; c < 3; c++) x[(kh * 3 + kw) * 3 + c] = sx[(c * PH + 2 * ty + kh) * PW + 2 * tx + kw];
+  __half* o = reinterpret_cast<__half*>(out.base) + ((size_t)(n * Ho + ho) * Wo + wo) * out.pitch + out.coff;
   for (int c0 = 0; c0 < Cout; c0 += 8) {
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = st_smem[27 * Cout + c0 + j];
+    for (int j = 0; j < 8; j++) acc[j] = sb[c0 + j];
 #pragma unroll
     for (int k = 0; k < 27; k++) {
-      const float* wr = st_smem + k * Cout + c0;
-#pragma unroll
-      for (int j = 0; j < 8; j++) acc[j] = fmaf(x[k], wr[j], acc[j]);
+      // two 16-byte broadcast loads per 8 FMAs (scalar LDS made the kernel LSU-bound)
+      const float4 w0 = *reinterpret_cast<const float4*>(sw + k * Cout + c0);
+      const float4 w1 = *reinterpret_cast<const float4*>(sw + k * Cout + c0 + 4);
+      acc[0] = fmaf(x[k], w0.x, acc[0]); acc[1] = fmaf(x[k], w0.y, acc[1]);
+      acc[2] = fmaf(x[k], w0.z, acc[2]); acc[3] = fmaf(x[k], w0.w, acc[3]);
+      acc[4] = fmaf(x[k], w1.x, acc[4]); acc[5] = fmaf(x[k], w1.y, acc[5]);
+      acc[6] = fmaf(x[k], w1.z, acc[6]); acc[7] = fmaf(x[k], w1.w, acc[7]);
     }
     int4 ov;
     __half2* oh = reinterpret_cast<__half2*>(&ov);
@@ -546,9 +692,10 @@ int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const flo
     set_error("stem: output channels must be a multiple of 8");
     return YB_ERR_SHAPE;
   }
-  const size_t total = (size_t)B * (H / 2) * (W / 2);
-  const size_t smem = (size_t)28 * out.C * sizeof(float);
-  stem_kernel<<<(unsigned)((total + 255) / 256), 256, smem, s>>>(in, in_dtype, B, H, W, out.C, w, bias, out);
+  const int Ho = H / 2, Wo = W / 2;
+  const int tiles = ((Wo + ST_TW - 1) / ST_TW) * ((Ho + ST_TH - 1) / ST_TH);
+  const size_t smem = ((size_t)28 * out.C + 3 * (2 * ST_TH + 1) * (2 * ST_TW + 1)) * sizeof(float);
+  stem_kernel<<<(unsigned)(B * tiles), 256, smem, s>>>(in, in_dtype, B, H, W, out.C, w, bias, out);
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -33,7 +33,7 @@ struct BufDesc {
   size_t offset = 0;  // bytes into the arena
 };
 
-enum OpType { OP_CONV, OP_DWCONV, OP_POOL, OP_UPSAMPLE, OP_DECODE, OP_PROTO_OUT, OP_CONVT, OP_ATTN };
+enum OpType { OP_CONV, OP_DWCONV, OP_POOL, OP_UPSAMPLE, OP_DECODE, OP_PROTO_OUT, OP_PIXSHUF, OP_ATTN };
 
 struct OpDesc {
   OpType type;
@@ -41,6 +41,9 @@ struct OpDesc {
   VRef in, out, res, out2, out3;
   int k = 1, s = 1, act = ACT_SILU, cin = 0, cout = 0, groups = 1;
   bool bn = true;        // Conv (conv+bn) vs plain Conv2d(bias)
+  bool convt = false;    // weights come from a ConvTranspose2d(c,c,2,2) [Cin][Cout][2][2]: run as 1x1 conv to 4*c
+  int nh = 0, kd = 0, hd = 0;  // attention
+  float scale = 0.f;
   // decode
   int level = 0, a0 = 0;
   float stride = 0;
@@ -51,6 +54,8 @@ struct OpDesc {
   float* bias = nullptr;
   TcConvPlan* plan = nullptr;
   bool use_tc = false;
+  EpiDecode dec;       // conv: fused Detect-tail epilogue (tcgen05 path)
+  bool fused = false;  // decode op: its work is done by the producing convs' epilogues
 };
 
 struct HostTensor {
@@ -193,6 +198,66 @@ struct Builder {
     conv(name + ".cv2", cat, out, 1, 1);
   }
 
+  // Convs.DWConv (Convs.cs:108-114): groups = gcd(c1,c2) = c for the square cases used by v11
+  void dwconv(const std::string& name, VRef in, VRef out, VRef res = VRef()) {
+    conv(name, in, out, 3, 1, ACT_SILU, true, res, in.C);
+  }
+
+  // Block.Attention + PSABlock + C2PSA (Block.cs:664-810).  All convs keep SiLU (reference quirk).
+  void c2psa(const std::string& name, VRef in, VRef out, int n) {
+    const int c = (int)(in.C * 0.5);
+    const int h = H(in), w = W(in);
+    VRef cat = new_buf(h, w, 2 * c);
+    conv(name + ".cv1", in, cat, 1, 1);
+    VRef b = slice(cat, c, c);
+    const int nh = c / 64, hd = c / nh, kd = (int)(hd * 0.5);
+    for (int i = 0; i < n; i++) {
+      const std::string bn = name + ".m." + std::to_string(i);
+      VRef qkv = new_buf(h, w, c + 2 * nh * kd);
+      conv(bn + ".attn.qkv", b, qkv, 1, 1);
+      VRef ao = new_buf(h, w, c), vd = new_buf(h, w, c), xs = new_buf(h, w, c), b1 = new_buf(h, w, c);
+      OpDesc op;
+      op.type = OP_ATTN;
+      op.name = bn + ".attn.core";
+      op.in = qkv; op.out = ao; op.out2 = vd;
+      op.nh = nh; op.kd = kd; op.hd = hd;
+      op.scale = (float)std::pow((double)kd, -0.5);
+      e->ops.push_back(op);
+      dwconv(bn + ".attn.pe", vd, xs, ao);           // attn_out + pe(v)
+      conv(bn + ".attn.proj", xs, b1, 1, 1, ACT_SILU, true, b);  // b + attn(b)
+      VRef f = new_buf(h, w, 2 * c);
+      conv(bn + ".ffn.0", b1, f, 1, 1);
+      conv(bn + ".ffn.1", f, b, 1, 1, ACT_SILU, true, b1);      // b1 + ffn(b1), back into the cat slice
+    }
+    conv(name + ".cv2", cat, out, 1, 1);
+  }
+
+  // Block.Proto (Block.cs:51-84): Conv3x3 -> ConvTranspose2d(2,2) -> Conv3x3 -> Conv1x1
+  VRef proto(const std::string& name, VRef in, int npr, int nm) {
+    const int h = H(in), w = W(in);
+    VRef p1 = new_buf(h, w, npr);
+    conv(name + ".cv1", in, p1, 3, 1);
+    VRef up4 = new_buf(h, w, 4 * npr);
+    conv(name + ".upsample", p1, up4, 1, 1, ACT_NONE, false);
+    e->ops.back().convt = true;
+    VRef up = new_buf(2 * h, 2 * w, npr);
+    OpDesc op;
+    op.type = OP_PIXSHUF;
+    op.name = name + ".upsample.shuffle";
+    op.in = up4; op.out = up;
+    e->ops.push_back(op);
+    VRef p2 = new_buf(2 * h, 2 * w, npr);
+    conv(name + ".cv2", up, p2, 3, 1);
+    VRef p3 = new_buf(2 * h, 2 * w, nm);
+    conv(name + ".cv3", p2, p3, 1, 1);
+    OpDesc po;
+    po.type = OP_PROTO_OUT;
+    po.name = name + ".out";
+    po.in = p3; po.out = p3;
+    e->ops.push_back(po);
+    return p3;
+  }
+
   void upsample(const std::string& name, VRef in, VRef out) {
     OpDesc op;
     op.type = OP_UPSAMPLE;
@@ -279,8 +344,46 @@ static int build_graph(yb_engine* e) {
     b.c2f(M(21), cat20, l21, n3[0], false);
     p3 = l15; p4 = l18; p5 = l21;
   } else {
-    set_error("YOLOv11 graph is not implemented in this build");
-    return YB_ERR_NOT_IMPLEMENTED;
+    // Yolo.cs:209-257; saved outputs {4,6,10,13,16,19,22}, concat partners {6,4,13,10}
+    VRef cat12 = b.new_buf(H / 16, W / 16, w[4] + w[3]);  // [up(L10), L6]
+    VRef cat15 = b.new_buf(H / 8, W / 8, w[3] + w[3]);    // [up(L13), L4]
+    VRef cat18 = b.new_buf(H / 16, W / 16, w[2] + w[3]);  // [L17, L13]
+    VRef cat21 = b.new_buf(H / 32, W / 32, w[3] + w[4]);  // [L20, L10]
+    VRef l0 = b.new_buf(H / 2, W / 2, w[0]);
+    b.conv(M(0), e->input_nhwc, l0, 3, 2);
+    VRef l1 = b.new_buf(H / 4, W / 4, w[1]);
+    b.conv(M(1), l0, l1, 3, 2);
+    VRef l2 = b.new_buf(H / 4, W / 4, w[2]);
+    b.c3k2(M(2), l1, l2, n11, use_c3k, 0.25);
+    VRef l3 = b.new_buf(H / 8, W / 8, w[2]);
+    b.conv(M(3), l2, l3, 3, 2);
+    VRef l4 = Builder::slice(cat15, w[3], w[3]);
+    b.c3k2(M(4), l3, l4, n11, use_c3k, 0.25);
+    VRef l5 = b.new_buf(H / 16, W / 16, w[3]);
+    b.conv(M(5), l4, l5, 3, 2);
+    VRef l6 = Builder::slice(cat12, w[4], w[3]);
+    b.c3k2(M(6), l5, l6, n11, true, 0.5);
+    VRef l7 = b.new_buf(H / 32, W / 32, w[4]);
+    b.conv(M(7), l6, l7, 3, 2);
+    VRef l8 = b.new_buf(H / 32, W / 32, w[4]);
+    b.c3k2(M(8), l7, l8, n11, true, 0.5);
+    VRef l9 = b.new_buf(H / 32, W / 32, w[4]);
+    b.sppf(M(9), l8, l9);
+    VRef l10 = Builder::slice(cat21, w[3], w[4]);
+    b.c2psa(M(10), l9, l10, n11);
+    b.upsample(M(11), l10, Builder::slice(cat12, 0, w[4]));
+    VRef l13 = Builder::slice(cat18, w[2], w[3]);
+    b.c3k2(M(13), cat12, l13, n11, use_c3k, 0.5);
+    b.upsample(M(14), l13, Builder::slice(cat15, 0, w[3]));
+    VRef l16 = b.new_buf(H / 8, W / 8, w[2]);
+    b.c3k2(M(16), cat15, l16, n11, use_c3k, 0.5);
+    b.conv(M(17), l16, Builder::slice(cat18, 0, w[2]), 3, 2);
+    VRef l19 = b.new_buf(H / 16, W / 16, w[3]);
+    b.c3k2(M(19), cat18, l19, n11, use_c3k, 0.5);
+    b.conv(M(20), l19, Builder::slice(cat21, 0, w[3]), 3, 2);
+    VRef l22 = b.new_buf(H / 32, W / 32, w[4]);
+    b.c3k2(M(22), cat21, l22, n11, true, 0.5);
+    p3 = l16; p4 = l19; p5 = l22;
   }
 
   // ---- Detect / Segment head (Head.cs:35-53, 247-259) ----
@@ -306,8 +409,16 @@ static int build_graph(yb_engine* e) {
     b.conv(hn + ".cv2." + L + ".1", t1, t2, 3, 1);
     b.conv(hn + ".cv2." + L + ".2", t2, box, 1, 1, ACT_NONE, false);
     VRef u1 = b.new_buf(hl, wl, c3), u2 = b.new_buf(hl, wl, c3), cls = b.new_buf(hl, wl, nc);
-    b.conv(hn + ".cv3." + L + ".0", feats[l], u1, 3, 1);
-    b.conv(hn + ".cv3." + L + ".1", u1, u2, 3, 1);
+    if (!v11) {  // legacy cls branch: two 3x3 Convs (Head.cs:49)
+      b.conv(hn + ".cv3." + L + ".0", feats[l], u1, 3, 1);
+      b.conv(hn + ".cv3." + L + ".1", u1, u2, 3, 1);
+    } else {     // Head.cs:50: [DW3x3(x) + Conv1x1(x->c3)] . [DW3x3(c3) + Conv1x1(c3->c3)]
+      VRef d1 = b.new_buf(hl, wl, feats[l].C), d2 = b.new_buf(hl, wl, c3);
+      b.dwconv(hn + ".cv3." + L + ".0.0", feats[l], d1);
+      b.conv(hn + ".cv3." + L + ".0.1", d1, u1, 1, 1);
+      b.dwconv(hn + ".cv3." + L + ".1.0", u1, d2);
+      b.conv(hn + ".cv3." + L + ".1.1", d2, u2, 1, 1);
+    }
     b.conv(hn + ".cv3." + L + ".2", u2, cls, 1, 1, ACT_NONE, false);
     VRef coef;
     if (seg) {
@@ -325,10 +436,7 @@ static int build_graph(yb_engine* e) {
     e->ops.push_back(op);
     a0 += hl * wl;
   }
-  if (seg) {
-    set_error("segment head (Proto) is not implemented in this build");
-    return YB_ERR_NOT_IMPLEMENTED;
-  }
+  if (seg) e->proto_view = b.proto(hn + ".proto", feats[0], e->ch[0], nm);  // Head.cs:247: npr = ch[0]
   return 0;
 }
 
@@ -364,6 +472,15 @@ static int finalize_conv(yb_engine* e, OpDesc& op) {
     set_error("shape mismatch for " + op.name + " weight");
     return YB_ERR_SHAPE;
   }
+  HostTensor Wt;  // ConvTranspose2d [Cin][Cout][2][2] -> 1x1 conv weight [(i*2+j)*Cout + co][Cin]
+  if (op.convt) {
+    const int cr = op.cout / 4;
+    Wt.data.resize(W->data.size());
+    for (int ci = 0; ci < op.cin; ci++)
+      for (int co = 0; co < cr; co++)
+        for (int ph = 0; ph < 4; ph++) Wt.data[((size_t)ph * cr + co) * op.cin + ci] = W->data[((size_t)ci * cr + co) * 4 + ph];
+    W = &Wt;
+  }
   std::vector<double> scale(op.cout, 1.0);
   std::vector<float> bias(op.cout, 0.f);
   if (op.bn) {
@@ -384,11 +501,12 @@ static int finalize_conv(yb_engine* e, OpDesc& op) {
   } else {
     const HostTensor* bb = find_tensor(e, op.name + ".bias");
     if (!bb) return YB_ERR_MISSING_WEIGHT;
-    if ((int)bb->data.size() != op.cout) {
+    const int breal = op.convt ? op.cout / 4 : op.cout;
+    if ((int)bb->data.size() != breal) {
       set_error("shape mismatch for " + op.name + " bias");
       return YB_ERR_SHAPE;
     }
-    for (int o = 0; o < op.cout; o++) bias[o] = bb->data[o];
+    for (int o = 0; o < op.cout; o++) bias[o] = bb->data[o % breal];
   }
   // folded weight (o, ci, kh, kw) -> fp32; in F16 mode rounded through fp16 so that the CUDA-core
   // twin and the tensor-core kernel see identical operand values
@@ -468,6 +586,7 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
           rc = launch_stem_f16(in, in_dtype, B, e->cfg.height, e->cfg.width, op.w_f32, op.bias,
                                make_view(e, op.out), s);
           if (rc) return rc;
+          input_converted = true;  // the stem reads the caller's NCHW tensor directly
           break;
         }
         if (!input_converted) {
@@ -476,7 +595,7 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
           input_converted = true;
         }
         if (op.use_tc) {
-          rc = tc_conv_launch(op.plan, B, s);
+          rc = tc_conv_launch(op.plan, B, out_pred, s);
         } else {
           rc = launch_conv_generic<T>(conv_params(e, op, B), s);
         }
@@ -497,12 +616,22 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
         if (rc) return rc;
         break;
       case OP_DECODE: {
+        if (op.fused) break;
         View coef = make_view(e, op.coef);
         rc = launch_decode_level<T>(make_view(e, op.in), make_view(e, op.cls), op.coef.buf >= 0 ? &coef : nullptr, B,
                                     e->cfg.nc, 32, e->cfg.reg_max, op.stride, op.a0, e->A, e->pred_c, out_pred, s);
         if (rc) return rc;
         break;
       }
+      case OP_PIXSHUF:
+        rc = launch_pixel_shuffle2<T>(make_view(e, op.in), make_view(e, op.out), B, s);
+        if (rc) return rc;
+        break;
+      case OP_ATTN:
+        rc = launch_attention<T>(make_view(e, op.in), make_view(e, op.out), make_view(e, op.out2), B, op.nh, op.kd,
+                                 op.hd, op.scale, s);
+        if (rc) return rc;
+        break;
       case OP_PROTO_OUT:
         if (out_proto) {
           rc = launch_proto_out<T>(make_view(e, op.in), out_proto, B, s);
@@ -543,6 +672,15 @@ int32_t yb_create(const yb_config* cfg, yb_engine** out) {
   if (cfg->height <= 0 || cfg->width <= 0 || cfg->height % 32 || cfg->width % 32) { set_error("yb_create: height/width must be positive multiples of 32"); return YB_ERR_INVALID_ARG; }
   if (cfg->max_batch <= 0) { set_error("yb_create: max_batch must be positive"); return YB_ERR_INVALID_ARG; }
   if (cfg->precision != YB_PREC_F32 && cfg->precision != YB_PREC_F16) { set_error("yb_create: bad precision"); return YB_ERR_INVALID_ARG; }
+  if (cfg->flags & YB_FLAG_DRY_RUN) {
+    std::unique_ptr<yb_engine> d(new yb_engine());
+    d->cfg = *cfg;
+    d->esize = cfg->precision == YB_PREC_F16 ? 2 : 4;
+    int rc = build_graph(d.get());
+    if (rc) return rc;
+    *out = d.release();
+    return YB_OK;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -579,6 +717,7 @@ int32_t yb_create(const yb_config* cfg, yb_engine** out) {
 
 void yb_destroy(yb_engine* e) {
   if (!e) return;
+  if (e->cfg.flags & YB_FLAG_DRY_RUN) { delete e; return; }
   cudaSetDevice(e->cfg.device);
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   for (auto& op : e->ops) if (op.plan) tc_conv_plan_destroy(op.plan);
@@ -641,9 +780,37 @@ int32_t yb_load_tensor(yb_engine* e, const char* name, int32_t dtype, int32_t nd
 int32_t yb_finalize_weights(yb_engine* e) {
   if (!e) { set_error("yb_finalize_weights: null engine"); return YB_ERR_INVALID_ARG; }
   if (e->finalized) { set_error("yb_finalize_weights: already finalized"); return YB_ERR_STATE; }
+  if (e->cfg.flags & YB_FLAG_DRY_RUN) { set_error("yb_finalize_weights: dry-run engine has no device"); return YB_ERR_STATE; }
   YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
   const bool f16 = e->cfg.precision == YB_PREC_F16;
   const bool allow_tc = f16 && !(e->cfg.flags & YB_FLAG_NO_TCGEN05);
+  if (allow_tc) {
+    // Detect tail fusion: when every final 1x1 conv of a level can run on the tcgen05 kernel, their
+    // epilogues write the prediction tensor directly and the decode kernel is dropped.
+    for (auto& d : e->ops) {
+      if (d.type != OP_DECODE) continue;
+      std::vector<OpDesc*> prod;
+      bool ok = true;
+      for (int bufid : {d.in.buf, d.cls.buf, d.coef.buf}) {
+        if (bufid < 0) continue;
+        OpDesc* pr = nullptr;
+        for (auto& c : e->ops)
+          if (c.type == OP_CONV && c.out.buf == bufid) pr = &c;
+        if (!pr || pr->k != 1 || pr->s != 1 || pr->cin % 16 || pr->cout % 16 || pr->cout > 256) ok = false;
+        prod.push_back(pr);
+      }
+      if (!ok || e->cfg.reg_max != 16) continue;
+      const BufDesc& lb = e->bufs[d.in.buf];
+      for (OpDesc* pr : prod) {
+        EpiDecode& dc = pr->dec;
+        dc.A = e->A; dc.Ctot = e->pred_c; dc.a0 = d.a0; dc.Wl = lb.W; dc.HW = lb.H * lb.W; dc.stride = d.stride;
+        if (pr->out.buf == d.in.buf) { dc.mode = EPI_DFL_BOX; dc.ch0 = 0; }
+        else if (pr->out.buf == d.cls.buf) { dc.mode = EPI_SIGMOID; dc.ch0 = 4; }
+        else { dc.mode = EPI_RAW; dc.ch0 = 4 + e->cfg.nc; }
+      }
+      d.fused = true;
+    }
+  }
   for (size_t i = 0; i < e->ops.size(); i++) {
     OpDesc& op = e->ops[i];
     if (op.type != OP_CONV && op.type != OP_DWCONV) continue;
@@ -656,6 +823,7 @@ int32_t yb_finalize_weights(yb_engine* e) {
       }
       ConvParams p = conv_params(e, op, e->cfg.max_batch);
       p.w = op.w_f16;
+      p.dec = op.dec;
       if (tc_conv_supported(p)) {
         std::string err;
         op.plan = tc_conv_plan_create(p, &err);
@@ -663,6 +831,14 @@ int32_t yb_finalize_weights(yb_engine* e) {
         op.use_tc = true;
       }
     }
+  }
+  for (auto& d : e->ops) {
+    if (d.type != OP_DECODE || !d.fused) continue;
+    for (auto& c : e->ops)
+      if (c.type == OP_CONV && c.dec.mode != EPI_STORE && c.dec.a0 == d.a0 && !c.use_tc) {
+        set_error("internal: fused decode producer " + c.name + " did not get a tcgen05 plan");
+        return YB_ERR_STATE;
+      }
   }
   e->host.clear();
   e->finalized = true;
@@ -773,6 +949,10 @@ int32_t yb_debug_read_activation(yb_engine* e, int32_t op_index, int32_t batch, 
   if (!e || !host_out || !chw || op_index < 0 || op_index >= (int32_t)e->ops.size()) { set_error("yb_debug_read_activation: bad argument"); return YB_ERR_INVALID_ARG; }
   YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
   const OpDesc& op = e->ops[op_index];
+  if (op.type == OP_DECODE || (op.use_tc && op.dec.mode != EPI_STORE)) {
+    set_error("yb_debug_read_activation: op '" + op.name + "' writes the prediction tensor directly (fused head decode)");
+    return YB_ERR_STATE;
+  }
   View v = make_view(e, op.out);
   chw[0] = v.C; chw[1] = v.H; chw[2] = v.W;
   const int64_t n = (int64_t)batch * v.C * v.H * v.W;
@@ -822,6 +1002,8 @@ int32_t yb_op_cost(const yb_engine* e, int32_t i, int32_t batch, double* flops, 
     const double macs = (double)batch * ob.H * ob.W * op.cout * (op.cin / op.groups) * op.k * op.k;
     *flops = 2.0 * macs;
     *bytes += (double)op.cout * (op.cin / op.groups) * op.k * op.k * e->esize;
+    if (op.use_tc && op.dec.mode != EPI_STORE)  // fused head tail writes fp32 straight into pred
+      *bytes += vbytes(op.out) / e->esize * 4.0 - vbytes(op.out);
     if (i == 0) {  // stem reads the caller's NCHW tensor, not an engine buffer
       *bytes -= vbytes(op.in);
       *bytes += (double)batch * 3 * e->cfg.height * e->cfg.width * e->esize;
@@ -848,16 +1030,9 @@ int32_t yb_op_kind(const yb_engine* e, int32_t i) {
 
 int32_t yb_launches_per_forward(const yb_engine* e) {
   if (!e) return 0;
-  int n = 0;
-  bool conv_seen = false;
-  for (size_t i = 0; i < e->ops.size(); i++) {
-    const OpDesc& op = e->ops[i];
-    if (op.type == OP_CONV && !conv_seen) {
-      conv_seen = true;
-      if (!(i == 0 && e->has_stem_tc)) n++;  // input layout conversion
-    }
-    n++;
-  }
+  int n = e->has_stem_tc ? 0 : 1;  // generic path converts the input layout first
+  for (const OpDesc& op : e->ops)
+    if (!(op.type == OP_DECODE && op.fused)) n++;
   return n;
 }
 

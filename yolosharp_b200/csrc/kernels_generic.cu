@@ -433,3 +433,170 @@ template int launch_proto_out<float>(const View&, float*, int, cudaStream_t);
 template int launch_proto_out<__half>(const View&, float*, int, cudaStream_t);
 
 }  // namespace yb
+
+namespace yb {
+
+// ------------------------------------------------------------------------------------------
+// ConvTranspose2d(c, c, 2, 2, 0) of Proto (Block.cs:69,82) = one 1x1 conv to 4*c channels
+// (phase-major: oc = (i*2+j)*c + co) followed by this pixel shuffle:
+//   out[n, 2h+i, 2w+j, co] = in[n, h, w, (i*2+j)*c + co]
+// ------------------------------------------------------------------------------------------
+template <typename T, typename V>
+__global__ void pixel_shuffle2_kernel(View in, View out, size_t total, int vec) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = out.C / vec;
+  const int c = (idx % cv) * vec;
+  size_t pix = idx / cv;
+  const int w = pix % out.W;
+  const int h = (pix / out.W) % out.H;
+  const int n = pix / ((size_t)out.W * out.H);
+  const int ph = ((h & 1) * 2 + (w & 1)) * out.C;
+  const T* src = reinterpret_cast<const T*>(in.base) +
+                 ((size_t)(n * in.H + (h >> 1)) * in.W + (w >> 1)) * in.pitch + in.coff + ph + c;
+  T* dst = reinterpret_cast<T*>(out.base) + pix * out.pitch + out.coff + c;
+  *reinterpret_cast<V*>(dst) = *reinterpret_cast<const V*>(src);
+}
+
+template <typename T>
+int launch_pixel_shuffle2(const View& in, const View& out, int B, cudaStream_t s) {
+  int vec = 16 / (int)sizeof(T);
+  while (vec > 1 && (out.C % vec || in.coff % vec || in.pitch % vec || out.coff % vec || out.pitch % vec)) vec >>= 1;
+  const size_t total = (size_t)B * out.H * out.W * (out.C / vec);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  const int bytes = vec * (int)sizeof(T);
+  if (bytes == 16) pixel_shuffle2_kernel<T, int4><<<blocks, 256, 0, s>>>(in, out, total, vec);
+  else if (bytes == 8) pixel_shuffle2_kernel<T, int2><<<blocks, 256, 0, s>>>(in, out, total, vec);
+  else if (bytes == 4) pixel_shuffle2_kernel<T, int><<<blocks, 256, 0, s>>>(in, out, total, vec);
+  else pixel_shuffle2_kernel<T, T><<<blocks, 256, 0, s>>>(in, out, total, vec);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+template int launch_pixel_shuffle2<float>(const View&, const View&, int, cudaStream_t);
+template int launch_pixel_shuffle2<__half>(const View&, const View&, int, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------
+// C2PSA attention core (Block.cs:784-791): per (image, head)
+//   attn = softmax_j(q_i . k_j * scale);  out_i = sum_j attn_ij v_j
+// qkv is the NHWC output of the qkv conv: token t = pixel, channel = head*(2kd+hd) + [q | k | v].
+// Writes out (B,N,C) with channel head*hd + d, and the dense copy of v the positional-encoding
+// depthwise conv needs (`pe(v.reshape(B,C,H,W))`).  N = 400 tokens at 640x640: one warp per query
+// row, keys streamed through shared memory in blocks of 32.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) attention_kernel(View qkv, View out, View vout, int nh, int kd, int hd, float scale) {
+  extern __shared__ float at_smem[];  // per warp: scores[N]; shared: K block [32][kd+1], V block [32][hd]
+  const int N = qkv.H * qkv.W;
+  const int b = blockIdx.z, head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int per = 2 * kd + hd;
+  const T* base = reinterpret_cast<const T*>(qkv.base) + (size_t)b * N * qkv.pitch + qkv.coff + head * per;
+  float* sc = at_smem + (size_t)warp * N;
+  float* kblk = at_smem + (size_t)nwarps * N;
+  float* vblk = kblk + 32 * (kd + 1);
+  const int i = blockIdx.x * nwarps + warp;  // query row of this warp
+  const bool active = i < N;
+  // q_i in registers (kd <= 64: up to 2 per lane)
+  float q0 = 0.f, q1 = 0.f;
+  if (active) {
+    if (lane < kd) q0 = to_f<T>(base[(size_t)i * qkv.pitch + lane]);
+    if (lane + 32 < kd) q1 = to_f<T>(base[(size_t)i * qkv.pitch + lane + 32]);
+  }
+  // pass 1: scores
+  for (int j0 = 0; j0 < N; j0 += 32) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 32 * kd; t += blockDim.x) {
+      const int jj = t / kd, d = t - jj * kd;
+      kblk[jj * (kd + 1) + d] = (j0 + jj < N) ? to_f<T>(base[(size_t)(j0 + jj) * qkv.pitch + kd + d]) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      // lane = key j0+lane: dot(q_i, k_j) with q broadcast by shuffles
+      float acc = 0.f;
+      for (int d = 0; d < kd; d++) {
+        const float qd = __shfl_sync(0xffffffffu, d < 32 ? q0 : q1, d & 31);
+        acc = fmaf(qd, kblk[lane * (kd + 1) + d], acc);
+      }
+      if (j0 + lane < N) sc[j0 + lane] = acc * scale;
+    }
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  if (active)
+    for (int j = lane; j < N; j += 32) mx = fmaxf(mx, sc[j]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  if (active)
+    for (int j = lane; j < N; j += 32) {
+      const float e = expf(sc[j] - mx);
+      sc[j] = e;
+      sum += e;
+    }
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  __syncwarp();
+  // pass 2: out_i[d] = sum_j p_j v_j[d]; lane owns d = lane, lane+32, ...
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+  for (int j0 = 0; j0 < N; j0 += 32) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 32 * hd; t += blockDim.x) {
+      const int jj = t / hd, d = t - jj * hd;
+      vblk[jj * hd + d] = (j0 + jj < N) ? to_f<T>(base[(size_t)(j0 + jj) * qkv.pitch + 2 * kd + d]) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      const int jn = min(32, N - j0);
+      for (int jj = 0; jj < jn; jj++) {
+        const float pj = sc[j0 + jj];
+        if (lane < hd) o0 = fmaf(pj, vblk[jj * hd + lane], o0);
+        if (lane + 32 < hd) o1 = fmaf(pj, vblk[jj * hd + lane + 32], o1);
+        if (lane + 64 < hd) o2 = fmaf(pj, vblk[jj * hd + lane + 64], o2);
+        if (lane + 96 < hd) o3 = fmaf(pj, vblk[jj * hd + lane + 96], o3);
+      }
+    }
+  }
+  if (!active) return;
+  T* op = reinterpret_cast<T*>(out.base) + ((size_t)b * N + i) * out.pitch + out.coff + head * hd;
+  T* vp = reinterpret_cast<T*>(vout.base) + ((size_t)b * N + i) * vout.pitch + vout.coff + head * hd;
+  const T* vsrc = base + (size_t)i * qkv.pitch + 2 * kd;
+  const float ov[4] = {o0, o1, o2, o3};
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int d = lane + 32 * r;
+    if (d < hd) {
+      op[d] = from_f<T>(ov[r] * inv);
+      vp[d] = vsrc[d];
+    }
+  }
+}
+
+template <typename T>
+int launch_attention(const View& qkv, const View& out, const View& vout, int B, int nh, int kd, int hd, float scale,
+                     cudaStream_t s) {
+  const int N = qkv.H * qkv.W;
+  if (kd > 64 || hd > 128) {
+    set_error("attention: key_dim <= 64 and head_dim <= 128 supported");
+    return YB_ERR_SHAPE;
+  }
+  const int nwarps = 8;
+  const size_t smem = ((size_t)nwarps * N + 32 * (kd + 1) + 32 * hd) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("attention: too many tokens for the shared-memory kernel");
+    return YB_ERR_SHAPE;
+  }
+  static bool attr_set[2] = {false, false};
+  const int ti = sizeof(T) == 4 ? 0 : 1;
+  if (!attr_set[ti]) {
+    YB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set[ti] = true;
+  }
+  dim3 grid((N + nwarps - 1) / nwarps, nh, B);
+  attention_kernel<T><<<grid, nwarps * 32, smem, s>>>(qkv, out, vout, nh, kd, hd, scale);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+template int launch_attention<float>(const View&, const View&, const View&, int, int, int, int, float, cudaStream_t);
+template int launch_attention<__half>(const View&, const View&, const View&, int, int, int, int, float, cudaStream_t);
+
+}  // namespace yb

@@ -24,7 +24,7 @@ class Engine:
                           max_batch=max_batch, height=height, width=width, flags=flags)
         L.check(lib.yb_create(C.byref(cfg), C.byref(self._h)))
         self.cfg = cfg
-        self.device = torch.device("cuda", device)
+        self.device = torch.device("cuda", device) if not flags & L.YB_FLAG_DRY_RUN else None
         self.nc, self.height, self.width, self.max_batch = nc, height, width, max_batch
         self.task = task
         self.anchors = lib.yb_num_anchors(self._h)
@@ -32,8 +32,9 @@ class Engine:
         self.finalized = False
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            L.lib().yb_destroy(self._h)
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and L is not None and getattr(L, "_lib", None) is not None:
+            L._lib.yb_destroy(h)
             self._h = C.c_void_p()
 
     __del__ = close
