@@ -1,0 +1,78 @@
+"""world_size-2/3 gloo tests (CPU) of the multi-GPU host logic: block sharding, padding, and the
+all-gather of the fixed-capacity detection buffers restore the global image order."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from yolosharp_b200 import dist as ydist
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_images, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        images = torch.rand(n_images, 3, 4, 4, generator=g)  # every rank builds the same global batch
+        local, real = ydist.pad_shard(images, rank, world)
+        # stand-in for forward+NMS: detections that encode the image content
+        max_det = 5
+        dets = torch.zeros(local.shape[0], max_det, 6)
+        counts = torch.zeros(local.shape[0], dtype=torch.int32)
+        for i in range(real):
+            k = 1 + int(local[i].sum().item() * 7) % max_det
+            counts[i] = k
+            dets[i, :k, 4] = local[i].mean()
+            dets[i, :k, 0] = torch.arange(k)
+        all_dets, all_counts = ydist.gather_detections(dets, counts)
+        d, c = ydist.unpad_gathered(all_dets, all_counts, n_images, world)
+        ok = d.shape[0] == n_images
+        for i in range(n_images):
+            k = 1 + int(images[i].sum().item() * 7) % max_det
+            ok &= int(c[i]) == k and bool(torch.allclose(d[i, :k, 4], images[i].mean().expand(k)))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, n_images):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_images, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(r, True) for r in range(world)]
+
+
+def test_shard_range_partitions():
+    for n in (1, 7, 8, 32, 64):
+        for w in (1, 2, 3, 8):
+            spans = [ydist.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_gather_world2_even():
+    _run(2, 8)
+
+
+def test_gather_world3_ragged():
+    _run(3, 7)

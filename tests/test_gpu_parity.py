@@ -110,6 +110,9 @@ def check_layers(e, model, x, tol, B, min_ops=55):
             assert "fused head decode" in str(ex), ex
             continue
         assert tuple(got.shape) == tuple(exp.shape), name
+        if name.endswith(".cv1") and type(model.get_submodule(name.rsplit(".", 1)[0])).__name__ == "C2PSA":
+            # the second half of this buffer is later overwritten in place by the PSA block output
+            got, exp = got[:, :got.shape[1] // 2], exp[:, :exp.shape[1] // 2]
         err = rel_err(got, exp)
         assert err < tol, f"op {i} {name}: rel err {err:.3e}"
         worst = max(worst, (name, err), key=lambda t: t[1])

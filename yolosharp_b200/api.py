@@ -243,14 +243,62 @@ class Detector:
         return _to_results(out[0].cpu())
 
 
+class Segmenter(Detector):
+    """Models/Segmenter.cs:12-84 (predict side): Detector + Segment head, Proto and instance masks."""
+
+    def __init__(self, config: Config):
+        self.config = config
+        dtype = torch.float16 if config.ScalarType == "Float16" else torch.float32
+        if config.YoloType != "Yolov8":
+            raise NotImplementedError("segmentation is built for Yolov8 graphs")
+        self.yolo = Yolov8Segment(config.NumberClass, yoloSize=config.YoloSize, end2end=config.End2End,
+                                  device=config.DeviceIndex, dtype=dtype, max_batch=config.MaxBatch)
+
+    def ImagePredict(self, orgImage, predictThreshold=None, iouThreshold=None) -> List[YoloResult]:
+        """Segmenter.cs:28-84: as Detector.ImagePredict plus process_mask(upsample: true); boxes are
+        clipped to the original image (Ops.clip_boxes, Ops.cs:150-158); masks cover the padded input and
+        are resized (not cropped) to the original size when padding occurred - the reference's behaviour."""
+        conf = self.config.PredictThreshold if predictThreshold is None else predictThreshold
+        iou = self.config.IouThreshold if iouThreshold is None else iouThreshold
+        img = orgImage.to(torch.device("cuda", self.config.DeviceIndex))
+        if img.dtype != torch.uint8:
+            raise ValueError("ImagePredict expects a uint8 (3,H,W) image tensor")
+        x = img.unsqueeze(0)
+        h, w = x.shape[2], x.shape[3]
+        ph, pw = (32 - h % 32) % 32, (32 - w % 32) % 32
+        if ph or pw:
+            x = torch.nn.functional.pad(x, (0, pw, 0, ph), mode="constant", value=114)
+        inference, _ = self.yolo.eval().forward(x)
+        pred, proto = inference["boxes"], inference["proto"]
+        dets, counts, _ = _nms(pred, conf, iou, 300, self.config.NumberClass)
+        n = int(counts[0].item())
+        if n == 0:
+            return []
+        masks = _masks(proto, dets, counts, x.shape[2], x.shape[3])[0, :n]
+        rows = dets[0, :n].clone()
+        rows[:, [0, 2]] = rows[:, [0, 2]].clamp(0, w)   # clip_boxes: x to [0, width], y to [0, height]
+        rows[:, [1, 3]] = rows[:, [1, 3]].clamp(0, h)
+        if ph or pw:
+            masks = torch.nn.functional.interpolate(masks[None].float(), size=(h, w), mode="bilinear",
+                                                    align_corners=False)[0].to(torch.uint8)
+        res = _to_results(rows.cpu())
+        mcpu = masks.cpu().numpy()
+        for r, mk in zip(res, mcpu):
+            r.Mask = mk.T.copy()  # reference stores byte[width, height] (Segmenter.cs:61-62)
+        return res
+
+
 class YoloTask:
     """Models/YoloTask.cs:10-107 (LoadModel / ImagePredict; Train is not built yet)."""
 
     def __init__(self, config: Config):
-        if config.TaskType != "Detection":
+        if config.TaskType == "Detection":
+            self.yolo = Detector(config)
+        elif config.TaskType == "Segmentation":
+            self.yolo = Segmenter(config)
+        else:
             raise NotImplementedError("Task type not support now.")
         self.config = config
-        self.yolo = Detector(config)
 
     def LoadModel(self, path, skipNcNotEqualLayers=False):
         self.yolo.LoadModel(path, skipNcNotEqualLayers)

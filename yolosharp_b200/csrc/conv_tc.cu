@@ -55,6 +55,7 @@ struct TcArgs {
   uint32_t layout_type;           // UMMA LayoutType: 2 = SW128, 4 = SW64, 6 = SW32
   uint32_t tmem_cols;
   int total_tiles;
+  uint32_t stage_off;             // byte offset of the epilogue staging tiles (4 warps x 8 KiB)
   int b_resident;                 // all weight slabs stay in smem for the CTA's lifetime
   int ksteps;
   // fused head decode (EpiDecode)
@@ -72,10 +73,118 @@ struct TcConvPlan {
 };
 
 __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op instead of two (ex2 + rcp)
+__device__ __forceinline__ float silu_tanh(float v) {
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int TC_MAX_COUT = 1024;
 constexpr int TC_MAX_STAGES = 12;
 constexpr int HALO_BW = 8, HALO_BH = 16;  // output rectangle of a halo tile (128 rows)
+
+// ------------------------------------------------------------------------------------------
+// MMA issue loop.  One thread issues every tcgen05.mma of the CTA, so its per-instruction overhead is
+// the kernel's pace for small N (a 128x64x16 MMA occupies the tensor pipe for ~34 cycles; the measured
+// single-thread issue floor is ~55 cycles, tools/exp_mma_issue.cu).  Everything that can be hoisted is
+// hoisted: descriptor high words are loop constants, low words advance by compile-time amounts
+// (KK = BK/16 MMAs per slab, tap shifts of the halo tile), kernel parameters live in registers.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+template <int KK>
+__device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32_t smemB, uint32_t tmem_base,
+                                         uint32_t fullA, uint32_t emptyA, uint32_t fullB, uint32_t emptyB,
+                                         uint32_t tfull0, uint32_t tempty0, uint32_t bfull) {
+  const uint32_t n_tile = a.n_tile;
+  const uint32_t idesc = (1u << 4) | ((n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  // descriptor = lo | hi << 32 :  lo = start>>4 | LBO(1)<<16 ;  hi = SBO | version(1)<<14 | layout<<29
+  const uint32_t a_hi = a.sbo_a | (1u << 14) | (a.layout_type << 29);
+  const uint32_t b_hi = a.sbo_b | (1u << 14) | (a.layout_type << 29);
+  const uint32_t lo_flags = 1u << 16;
+  const uint32_t a_stride16 = a.a_stride >> 4, b_stride16 = a.b_stride >> 4;
+  const uint32_t a_lo0 = ((smemA & 0x3FFFF) >> 4) | lo_flags, b_lo0 = ((smemB & 0x3FFFF) >> 4) | lo_flags;
+  const int stages_a = a.stages_a, stages_b = a.stages_b, chunks = a.chunks, ksteps = a.ksteps;
+  const bool resident = a.b_resident != 0, halo = a.mode == TC_HALO;
+  const int total_tiles = a.total_tiles, gstride = gridDim.x;
+  constexpr uint32_t ROW16 = KK * 2;  // bytes per operand row / 16
+  int sa = 0, sb = 0;
+  uint32_t pa = 0, pb = 0;
+  int acc = 0;
+  uint32_t aphase = 0;
+  if (resident) mbar_wait(bfull, 0);
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gstride) {
+    mbar_wait(tempty0 + 8 * acc, aphase ^ 1);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + acc * n_tile;
+    uint32_t accf = 0;
+    if (halo) {
+      for (int ch = 0; ch < chunks; ch++) {
+        mbar_wait(fullA + 8 * sa, pa);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + sa * a_stride16;
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+          constexpr int W2 = HALO_BW + 2;
+          const uint32_t tap16 = (uint32_t)((t / 3) * W2 + (t % 3)) * ROW16;  // compile-time after unrolling
+          uint32_t b_lo;
+          if (resident) {
+            b_lo = b_lo0 + (t * chunks + ch) * b_stride16;
+          } else {
+            mbar_wait(fullB + 8 * sb, pb);
+            tc_fence_after();
+            b_lo = b_lo0 + sb * b_stride16;
+          }
+#pragma unroll
+          for (int k = 0; k < KK; k++) {  // +32 B per K=16 step inside the swizzled row
+            umma_f16(d_tmem, desc64(a_lo + tap16 + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc, accf);
+            accf = 1;
+          }
+          if (!resident) {
+            umma_commit(emptyB + 8 * sb);
+            if (++sb == stages_b) { sb = 0; pb ^= 1; }
+          }
+        }
+        umma_commit(emptyA + 8 * sa);  // halo tile free once its 9 taps retired
+        if (++sa == stages_a) { sa = 0; pa ^= 1; }
+      }
+    } else {
+      for (int ks = 0; ks < ksteps; ks++) {
+        mbar_wait(fullA + 8 * sa, pa);
+        uint32_t b_lo;
+        if (resident) {
+          b_lo = b_lo0 + ks * b_stride16;
+        } else {
+          mbar_wait(fullB + 8 * sb, pb);
+          b_lo = b_lo0 + sb * b_stride16;
+        }
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + sa * a_stride16;
+#pragma unroll
+        for (int k = 0; k < KK; k++) {
+          umma_f16(d_tmem, desc64(a_lo + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc, accf);
+          accf = 1;
+        }
+        umma_commit(emptyA + 8 * sa);  // slab free once these MMAs retire
+        if (++sa == stages_a) { sa = 0; pa ^= 1; }
+        if (!resident) {
+          umma_commit(emptyB + 8 * sb);
+          if (++sb == stages_b) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+    umma_commit(tfull0 + 8 * acc);  // accumulator complete
+    acc ^= 1;
+    if (acc == 0) aphase ^= 1;
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // Two operand rings feed the single MMA-issuing thread:
@@ -93,8 +202,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   __shared__ __align__(8) uint64_t bars[4 * TC_MAX_STAGES + 5];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[TC_MAX_COUT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < a.n_tile * a.n_tiles; i += TC_THREADS) s_bias[i] = a.bias[i];  // constant data
   // dynamic smem base rounded up to 1 KiB (SWIZZLE_128B atoms need it)
   const uint32_t smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
   const uint32_t smemA = smem0;
@@ -122,7 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     for (int s = 0; s < 2; s++) {
       mbar_init(tfull0 + 8 * s, 1);
-      mbar_init(tempty0 + 8 * s, 4);  // one arrive per epilogue warp
+      mbar_init(tempty0 + 8 * s, 8);  // one arrive per epilogue warp
     }
     mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -205,83 +316,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b F16, K-major both,
-      // n_dim = N>>3 at bit 17, m_dim = 128>>4 at bit 24
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(a.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const int kk = a.BK >> 4;
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      int acc = 0;
-      uint32_t aphase = 0;
-      if (a.b_resident) mbar_wait(bfull, 0);
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty0 + 8 * acc, aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * a.n_tile;
-        uint32_t first = 1;
-        if (a.mode == TC_HALO) {
-          for (int ch = 0; ch < a.chunks; ch++) {
-            mbar_wait(fullA + 8 * sa, pa);
-            tc_fence_after();
-            const uint32_t abase = smemA + sa * a.a_stride;
-            for (int t = 0; t < taps; t++) {
-              const int kh = t / 3, kw = t - kh * 3;
-              uint32_t bslab;
-              if (a.b_resident) {
-                bslab = smemB + (t * a.chunks + ch) * a.b_stride;
-              } else {
-                mbar_wait(fullB + 8 * sb, pb);
-                tc_fence_after();
-                bslab = smemB + sb * a.b_stride;
-              }
-              const uint64_t ad = umma_desc(abase + (kh * (a.BW + 2) + kw) * a.row_bytes, a.sbo_a, a.layout_type);
-              const uint64_t bd = umma_desc(bslab, a.sbo_b, a.layout_type);
-              for (int k = 0; k < kk; k++) {  // +32 B per K=16 step inside the swizzled row
-                umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, first ^ 1u);
-                first = 0;
-              }
-              if (!a.b_resident) {
-                umma_commit(emptyB + 8 * sb);
-                if (++sb == a.stages_b) { sb = 0; pb ^= 1; }
-              }
-            }
-            umma_commit(emptyA + 8 * sa);  // halo tile free once its 9 taps retired
-            if (++sa == a.stages_a) { sa = 0; pa ^= 1; }
-          }
-        } else {
-          for (int ks = 0; ks < a.ksteps; ks++) {
-            mbar_wait(fullA + 8 * sa, pa);
-            uint32_t bslab;
-            if (a.b_resident) {
-              bslab = smemB + ks * a.b_stride;
-            } else {
-              mbar_wait(fullB + 8 * sb, pb);
-              bslab = smemB + sb * a.b_stride;
-            }
-            tc_fence_after();
-            const uint64_t ad = umma_desc(smemA + sa * a.a_stride, a.sbo_a, a.layout_type);
-            const uint64_t bd = umma_desc(bslab, a.sbo_b, a.layout_type);
-            for (int k = 0; k < kk; k++) {
-              umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, first ^ 1u);
-              first = 0;
-            }
-            umma_commit(emptyA + 8 * sa);  // slab free once these MMAs retire
-            if (++sa == a.stages_a) { sa = 0; pa ^= 1; }
-            if (!a.b_resident) {
-              umma_commit(emptyB + 8 * sb);
-              if (++sb == a.stages_b) { sb = 0; pb ^= 1; }
-            }
-          }
-        }
-        umma_commit(tfull0 + 8 * acc);  // accumulator complete
-        acc ^= 1;
-        if (acc == 0) aphase ^= 1;
+      switch (a.BK) {
+        case 64: mma_role<4>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull); break;
+        case 32: mma_role<2>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull); break;
+        default: mma_role<1>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull); break;
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quarter (hardware rule: a warp reads lanes 32*(warp%4)..+31) split the
+    // N columns between them, so every SM sub-partition has two epilogue warps to overlap the
+    // tcgen05.ld / MUFU / store latencies (ncu: with one warp per sub-partition the epilogue ran at
+    // ~0.2 IPC and paced the whole kernel).
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
     const int row = q * 32 + lane;
+    const uint32_t stg_out = smem0 + a.stage_off + ew * 4096;  // per-warp 32 x 64 B transpose tiles
+    const uint32_t stg_res = stg_out + 2048;
     int acc = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
@@ -295,8 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const bool valid = hl < a.BH && ho < a.Ho && wo < a.Wo;
       const size_t pix = ((size_t)img * a.Ho + ho) * a.Wo + wo;
       const int n0 = nt * a.n_tile;
-      __half* orow = a.out + pix * a.out_pitch + a.out_coff + n0;
-      const __half* rrow = a.res ? a.res + pix * a.res_pitch + a.res_coff + n0 : nullptr;
+      const float* bias = s_bias + n0;
 
       mbar_wait(tfull0 + 8 * acc, aphase);
       tc_fence_after();
@@ -308,80 +359,121 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         float* po = a.pred + (size_t)n * a.dCtot * a.dA + a.da0 + i;
         if (a.epi_mode == EPI_DFL_BOX) {
           // DFL (Block.cs:44): softmax over the 16 bins of each side, expectation with weights 0..15;
-          // then dist2bbox(xywh) * stride (Tal.cs:338-356, Head.cs:221)
-          float d[4];
+          // then dist2bbox(xywh) * stride (Tal.cs:338-356, Head.cs:221).  half 0 owns the x sides
+          // (left/right -> cx, w), half 1 the y sides (top/bottom -> cy, h).
+          float d[2];
 #pragma unroll
-          for (int sd = 0; sd < 4; sd++) {
+          for (int s2 = 0; s2 < 2; s2++) {
+            const int sd = half + 2 * s2;
             uint32_t v[16];
             tmem_ld16(taddr + sd * 16, v);
             tmem_ld_wait();
             float f[16], mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 16; j++) { f[j] = __uint_as_float(v[j]) + __ldg(a.bias + sd * 16 + j); mx = fmaxf(mx, f[j]); }
+            for (int j = 0; j < 16; j++) { f[j] = __uint_as_float(v[j]) + bias[sd * 16 + j]; mx = fmaxf(mx, f[j]); }
             float sum = 0.f, ex = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; j++) { const float e = __expf(f[j] - mx); sum += e; ex = fmaf(e, (float)j, ex); }
-            d[sd] = __fdividef(ex, sum);
+            d[s2] = __fdividef(ex, sum);
           }
           if (valid) {
             const int y = i / a.dWl, x = i - y * a.dWl;
-            const float ax = (float)x + 0.5f, ay = (float)y + 0.5f;
-            const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
-            po[0] = (x1 + x2) * 0.5f * a.dstride;
-            po[(size_t)a.dA] = (y1 + y2) * 0.5f * a.dstride;
-            po[(size_t)2 * a.dA] = (x2 - x1) * a.dstride;
-            po[(size_t)3 * a.dA] = (y2 - y1) * a.dstride;
+            const float ac = (half == 0 ? (float)x : (float)y) + 0.5f;
+            const float lo = ac - d[0], hi = ac + d[1];
+            po[(size_t)half * a.dA] = (lo + hi) * 0.5f * a.dstride;
+            po[(size_t)(2 + half) * a.dA] = (hi - lo) * a.dstride;
           }
         } else {
-          for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+          for (int c0 = half * 16; c0 < a.n_tile; c0 += 32) {
             uint32_t v[16];
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
             if (valid) {
 #pragma unroll
               for (int j = 0; j < 16; j++) {
-                float f = __uint_as_float(v[j]) + __ldg(a.bias + c0 + j);
+                float f = __uint_as_float(v[j]) + bias[c0 + j];
                 if (a.epi_mode == EPI_SIGMOID) f = __fdividef(1.0f, 1.0f + __expf(-f));
                 po[(size_t)(a.dch0 + c0 + j) * a.dA] = f;  // lanes = consecutive anchors: coalesced
               }
             }
           }
         }
-      } else
-      for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        if (valid) {
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; j++) f[j] = __uint_as_float(v[j]) + __ldg(a.bias + n0 + c0 + j);
-          if (a.act == ACT_SILU) {
-#pragma unroll
-            for (int j = 0; j < 16; j++) f[j] = silu_fast(f[j]);
+      } else {
+        // Store path: 32-column blocks alternate between the two warps of a pair.  A lane owns one
+        // output pixel (TMEM lane); rows are transposed through a per-warp smem tile so that a warp
+        // store instruction writes 8 rows x 64 contiguous bytes instead of 32 scattered 16-byte pieces.
+        const uint32_t pix_lo = (uint32_t)pix, pix_hi = (uint32_t)((uint64_t)pix >> 32);
+        for (int cb0 = half * 32; cb0 < a.n_tile; cb0 += 64) {
+          const int wb = min(32, a.n_tile - cb0);  // 32 or 16 channels
+          const int pieces = wb >> 3;              // 16-byte pieces per row (4 or 2)
+          const int rpi = 32 / pieces;             // rows per warp instruction
+          const int pmask = pieces - 1;
+          const int my_r = lane / pieces, my_pc = lane - my_r * pieces;
+          if (a.res) {
+            for (int it = 0; it < pieces; it++) {
+              const int rr = it * rpi + my_r;
+              const uint32_t lo = __shfl_sync(0xffffffffu, pix_lo, rr), hi = __shfl_sync(0xffffffffu, pix_hi, rr);
+              const int vr = __shfl_sync(0xffffffffu, (int)valid, rr);
+              int4 v = make_int4(0, 0, 0, 0);
+              if (vr) {
+                const size_t px = ((size_t)hi << 32) | lo;
+                v = *reinterpret_cast<const int4*>(a.res + px * a.res_pitch + a.res_coff + n0 + cb0 + my_pc * 8);
+              }
+              st_shared_v4(stg_res + (rr * pieces + (my_pc ^ (rr & pmask))) * 16, v);
+            }
+            __syncwarp();
           }
-          if (rrow) {
-            const int4 r0 = *reinterpret_cast<const int4*>(rrow + c0);
-            const int4 r1 = *reinterpret_cast<const int4*>(rrow + c0 + 8);
-            const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-            const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+          for (int c0 = cb0; c0 < cb0 + wb; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias + c0 + j);
+              f[j] = __uint_as_float(v[j]) + bv.x; f[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + bv.z; f[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
+            }
+            if (a.act == ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) f[j] = silu_tanh(f[j]);
+            }
+            const int pc0 = (c0 - cb0) >> 3;
+            if (a.res) {
+              const int4 r0 = ld_shared_v4(stg_res + (lane * pieces + (pc0 ^ (lane & pmask))) * 16);
+              const int4 r1 = ld_shared_v4(stg_res + (lane * pieces + ((pc0 + 1) ^ (lane & pmask))) * 16);
+              const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+              const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const float2 x = __half22float2(h0[j]), y = __half22float2(h1[j]);
+                f[2 * j] += x.x; f[2 * j + 1] += x.y;
+                f[8 + 2 * j] += y.x; f[8 + 2 * j + 1] += y.y;
+              }
+            }
+            int4 o0, o1;
+            __half2* p0 = reinterpret_cast<__half2*>(&o0);
+            __half2* p1 = reinterpret_cast<__half2*>(&o1);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-              const float2 x = __half22float2(h0[j]), y = __half22float2(h1[j]);
-              f[2 * j] += x.x; f[2 * j + 1] += x.y;
-              f[8 + 2 * j] += y.x; f[8 + 2 * j + 1] += y.y;
+              p0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+              p1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+            }
+            st_shared_v4(stg_out + (lane * pieces + (pc0 ^ (lane & pmask))) * 16, o0);
+            st_shared_v4(stg_out + (lane * pieces + ((pc0 + 1) ^ (lane & pmask))) * 16, o1);
+          }
+          __syncwarp();
+          for (int it = 0; it < pieces; it++) {
+            const int rr = it * rpi + my_r;
+            const uint32_t lo = __shfl_sync(0xffffffffu, pix_lo, rr), hi = __shfl_sync(0xffffffffu, pix_hi, rr);
+            const int vr = __shfl_sync(0xffffffffu, (int)valid, rr);
+            const int4 v = ld_shared_v4(stg_out + (rr * pieces + (my_pc ^ (rr & pmask))) * 16);
+            if (vr) {
+              const size_t px = ((size_t)hi << 32) | lo;
+              *reinterpret_cast<int4*>(a.out + px * a.out_pitch + a.out_coff + n0 + cb0 + my_pc * 8) = v;
             }
           }
-          int4 o0, o1;
-          __half2* p0 = reinterpret_cast<__half2*>(&o0);
-          __half2* p1 = reinterpret_cast<__half2*>(&o1);
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            p0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-            p1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
-          }
-          *reinterpret_cast<int4*>(orow + c0) = o0;
-          *reinterpret_cast<int4*>(orow + c0 + 8) = o1;
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -423,7 +515,7 @@ static EncodeTiledFn get_encode_fn(std::string* err) {
 }
 
 bool tc_conv_supported(const ConvParams& p) {
-  if (p.Cin % 16 || p.Cout % 16) return false;
+  if (p.Cin % 16 || p.Cout % 16 || p.Cout > TC_MAX_COUT) return false;
   if (!((p.k == 1 && p.stride == 1) || (p.k == 3 && (p.stride == 1 || p.stride == 2)))) return false;
   if (p.in.coff % 8 || p.in.pitch % 8 || p.out.coff % 8 || p.out.pitch % 8) return false;
   if (p.res.base && (p.res.coff % 8 || p.res.pitch % 8)) return false;
@@ -531,7 +623,7 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   a.a_stride = (uint32_t)((std::max(a_rows, 128) * a.row_bytes + 1023) / 1024 * 1024);
   a.b_stride = (uint32_t)((a.n_tile * a.row_bytes + 1023) / 1024 * 1024);
   a.ksteps = p.k * p.k * a.chunks;
-  const size_t budget = 200 * 1024;
+  const size_t budget = 200 * 1024 - 32 * 1024;  // 32 KiB go to the epilogue transpose tiles
   // keep the whole weight matrix in smem when it leaves room for >= 3 activation slabs: removes the
   // weight re-fetch per tile (the kernel is L2-request-bound, not byte-bound)
   const size_t b_all = (size_t)a.ksteps * a.b_stride;
@@ -549,6 +641,8 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     a.stages_a = a.stages_b = (int)std::min<size_t>(8, budget / (a.a_stride + a.b_stride));
     plan->smem = (size_t)a.stages_a * (a.a_stride + a.b_stride) + 1024;
   }
+  a.stage_off = (uint32_t)(plan->smem - 1024);
+  plan->smem += 32 * 1024;
   if (a.stages_a < 2 || (!a.b_resident && a.stages_b < 2)) {
     if (err) *err = "tile does not fit in shared memory";
     delete plan;

@@ -22,10 +22,14 @@ namespace yb {
 constexpr int NMS_THREADS = 1024;
 constexpr int NMS_SMEM_KEYS = 16384;  // candidates sortable in shared memory (128 KB of keys)
 constexpr int NMS_MAX_DET_CAP = 1024;
+constexpr int NMS_SC = 1024;  // sorted candidates gathered into shared memory per super-chunk
 
 struct Box5 {
   float x1, y1, x2, y2, area;
 };
+// kept[1024] + super-chunk boxes/rows/anchors + rowmask + misc, padded to 8 bytes for the 64-bit keys
+constexpr size_t NMS_FIXED_SMEM =
+    ((NMS_MAX_DET_CAP + NMS_SC) * sizeof(Box5) + NMS_SC * 6 * 4 + NMS_SC * 4 + 32 * 4 + 16 + 7) / 8 * 8;
 
 // IoU > thr test with the exact op order of torchvision's CPU kernel (nms_kernel_impl):
 //   w = max(0, xx2-xx1); h = max(0, yy2-yy1); inter = w*h; ovr = inter / (iarea + area_j - inter)
@@ -39,10 +43,39 @@ __device__ __forceinline__ bool iou_gt(const Box5& a, const Box5& b, float thr) 
   return ovr > thr;  // NaN (0/0) compares false, as on the CPU
 }
 
+// Stage 1 (all SMs): per anchor best class + confidence (Ops.cs:272, 325-328).  conf = -1 marks
+// "not a candidate"; strict '>' keeps the FIRST maximal class like torch.max.
+__global__ void __launch_bounds__(256) nms_scan_kernel(const float* __restrict__ pred, int C, int A, int nc,
+                                                       float conf_thres, float* __restrict__ sconf,
+                                                       int* __restrict__ scls) {
+  const int b = blockIdx.y;
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  if (a >= A) return;
+  const float* P = pred + (size_t)b * C * A + (size_t)4 * A + a;
+  float best = P[0];
+  int bj = 0;
+  int c = 1;
+  for (; c + 8 <= nc; c += 8) {  // 8 independent loads in flight per thread
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = P[(size_t)(c + u) * A];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (v[u] > best) { best = v[u]; bj = c + u; }
+  }
+  for (; c < nc; c++) {
+    const float v = P[(size_t)c * A];
+    if (v > best) { best = v; bj = c; }
+  }
+  sconf[(size_t)b * A + a] = best > conf_thres ? best : -1.0f;
+  scls[(size_t)b * A + a] = bj;
+}
+
 __global__ void __launch_bounds__(NMS_THREADS, 1)
 nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thres, float iou_thres,
            int max_det, int max_nms, float max_wh, float* __restrict__ dets, int* __restrict__ counts,
-           int* __restrict__ keep_idx, unsigned long long* __restrict__ gkeys, int key_cap) {
+           int* __restrict__ keep_idx, unsigned long long* __restrict__ gkeys, int key_cap,
+           const float* __restrict__ sconf, const int* __restrict__ scls) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -51,28 +84,22 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
   const int row_w = 6 + extra;
 
   // shared carve-up
-  Box5* kept = reinterpret_cast<Box5*>(nms_smem);                       // [max_det]
-  Box5* cbox = kept + NMS_MAX_DET_CAP;                                   // [32] chunk boxes (offset)
-  float* craw = reinterpret_cast<float*>(cbox + 32);                     // [32][6] raw row
-  int* canchor = reinterpret_cast<int*>(craw + 32 * 6);                  // [32]
-  unsigned* rowmask = reinterpret_cast<unsigned*>(canchor + 32);         // [32]
-  unsigned* misc = rowmask + 32;                                         // [4]: n_cand, supp, keepmask, kept_n
+  Box5* kept = reinterpret_cast<Box5*>(nms_smem);                       // [NMS_MAX_DET_CAP]
+  Box5* cbox = kept + NMS_MAX_DET_CAP;                                   // [NMS_SC] super-chunk boxes (class-offset)
+  float* craw = reinterpret_cast<float*>(cbox + NMS_SC);                 // [NMS_SC][6] raw rows
+  int* canchor = reinterpret_cast<int*>(craw + NMS_SC * 6);              // [NMS_SC]
+  unsigned* rowmask = reinterpret_cast<unsigned*>(canchor + NMS_SC);     // [32]
+  unsigned* misc = rowmask + 32;                                         // [4]: n_cand, supp, -, kept_n
   unsigned long long* keys =
-      gkeys ? gkeys + (size_t)b * key_cap
-            : reinterpret_cast<unsigned long long*>(nms_smem + ((NMS_MAX_DET_CAP + 32) * sizeof(Box5) +
-                                                                32 * 6 * 4 + 32 * 4 + 32 * 4 + 16));
+      gkeys ? gkeys + (size_t)b * key_cap : reinterpret_cast<unsigned long long*>(nms_smem + NMS_FIXED_SMEM);
   if (tid < 4) misc[tid] = 0;
   __syncthreads();
 
-  // ---- 1. candidate scan ----
+  // ---- 1. candidate compaction (per-anchor conf/class come from nms_scan_kernel) ----
   for (int a = tid; a < A; a += NMS_THREADS) {
-    float best = P[(size_t)4 * A + a];
-    int bj = 0;
-    for (int c = 1; c < nc; c++) {
-      const float v = P[(size_t)(4 + c) * A + a];
-      if (v > best) { best = v; bj = c; }
-    }
-    if (best > conf_thres) {
+    const float best = sconf[(size_t)b * A + a];
+    if (best >= 0.0f) {
+      const int bj = scls[(size_t)b * A + a];
       const unsigned slot = atomicAdd(&misc[0], 1u);
       if (slot < (unsigned)key_cap)
         keys[slot] = ((unsigned long long)(~__float_as_uint(best)) << 32) |
@@ -106,75 +133,79 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
   }
   n = min(n, max_nms);
 
-  // ---- 3. greedy suppression in chunks of 32 ----
+  // ---- 3. greedy suppression: super-chunks of 1024 sorted candidates are gathered into shared
+  //         memory by all threads (one global-latency exposure), then consumed 32 at a time ----
   int kept_n = 0;
-  for (int s0 = 0; s0 < n && kept_n < max_det; s0 += 32) {
-    const int cnt = min(32, n - s0);
-    if (tid < 32) {
-      Box5 bx = {0.f, 0.f, 0.f, 0.f, 0.f};
-      if (lane < cnt) {
-        const unsigned long long key = keys[s0 + lane];
-        const int a = (int)((key >> 12) & 0xFFFFF);
-        const int j = (int)(key & 0xFFF);
-        const float conf = __uint_as_float(~(unsigned)(key >> 32));
-        const float cx = P[a], cy = P[(size_t)A + a], w = P[(size_t)2 * A + a], h = P[(size_t)3 * A + a];
-        // xywh2xyxy (Ops.cs:76-79): x - w/2, x + w/2 (w/2 is exact)
-        const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
-        const float x1 = __fsub_rn(cx, hw), y1 = __fsub_rn(cy, hh);
-        const float x2 = __fadd_rn(cx, hw), y2 = __fadd_rn(cy, hh);
-        const float off = __fmul_rn((float)j, max_wh);  // Ops.cs:345
-        bx.x1 = __fadd_rn(x1, off); bx.y1 = __fadd_rn(y1, off);
-        bx.x2 = __fadd_rn(x2, off); bx.y2 = __fadd_rn(y2, off);
-        bx.area = __fmul_rn(__fsub_rn(bx.x2, bx.x1), __fsub_rn(bx.y2, bx.y1));
-        float* r = craw + lane * 6;
-        r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2; r[4] = conf; r[5] = (float)j;
-        canchor[lane] = a;
+  for (int sc0 = 0; sc0 < n && kept_n < max_det; sc0 += NMS_SC) {
+    const int scn = min(NMS_SC, n - sc0);
+    if (tid < scn) {
+      const unsigned long long key = keys[sc0 + tid];
+      const int a = (int)((key >> 12) & 0xFFFFF);
+      const int j = (int)(key & 0xFFF);
+      const float conf = __uint_as_float(~(unsigned)(key >> 32));
+      const float cx = P[a], cy = P[(size_t)A + a], w = P[(size_t)2 * A + a], h = P[(size_t)3 * A + a];
+      // xywh2xyxy (Ops.cs:76-79): x - w/2, x + w/2 (w/2 is exact)
+      const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+      const float x1 = __fsub_rn(cx, hw), y1 = __fsub_rn(cy, hh);
+      const float x2 = __fadd_rn(cx, hw), y2 = __fadd_rn(cy, hh);
+      const float off = __fmul_rn((float)j, max_wh);  // Ops.cs:345
+      Box5 bx;
+      bx.x1 = __fadd_rn(x1, off); bx.y1 = __fadd_rn(y1, off);
+      bx.x2 = __fadd_rn(x2, off); bx.y2 = __fadd_rn(y2, off);
+      bx.area = __fmul_rn(__fsub_rn(bx.x2, bx.x1), __fsub_rn(bx.y2, bx.y1));
+      cbox[tid] = bx;
+      float* r = craw + tid * 6;
+      r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2; r[4] = conf; r[5] = (float)j;
+      canchor[tid] = a;
+    }
+    if (tid == 0) misc[1] = 0;
+    __syncthreads();
+    for (int s0 = 0; s0 < scn && kept_n < max_det; s0 += 32) {
+      const int cnt = min(32, scn - s0);
+      // phase A: warp g = row g of the intra-chunk IoU bit-matrix, then kept entries g, g+32, ...
+      {
+        const Box5 mine = cbox[s0 + min(lane, cnt - 1)];
+        const Box5 rowb = cbox[s0 + min(warp, cnt - 1)];
+        const bool hit = (warp < cnt) && (lane < cnt) && (lane > warp) && iou_gt(rowb, mine, iou_thres);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) rowmask[warp] = m;
+        bool sup = false;
+        if (lane < cnt)
+          for (int k = warp; k < kept_n; k += 32) sup = sup || iou_gt(kept[k], mine, iou_thres);
+        const unsigned sm = __ballot_sync(0xffffffffu, sup);
+        if (lane == 0 && sm) atomicOr(&misc[1], sm);
       }
-      cbox[lane] = bx;
-      if (lane == 0) misc[1] = 0;
-    }
-    __syncthreads();
-    // phase A: warp g = row g of the intra-chunk matrix, then kept entries g, g+32, ...
-    {
-      const Box5 mine = cbox[lane];
-      const Box5 rowb = cbox[warp];
-      const bool hit = (warp < cnt) && (lane < cnt) && (lane > warp) && iou_gt(rowb, mine, iou_thres);
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (lane == 0) rowmask[warp] = m;
-      bool sup = false;
-      if (lane < cnt)
-        for (int k = warp; k < kept_n; k += 32) sup = sup || iou_gt(kept[k], mine, iou_thres);
-      const unsigned sm = __ballot_sync(0xffffffffu, sup);
-      if (lane == 0 && sm) atomicOr(&misc[1], sm);
-    }
-    __syncthreads();
-    // phase B: serial resolve inside the chunk (warp 0, every lane runs the same bit loop)
-    if (warp == 0) {
-      unsigned supp = misc[1];
-      unsigned keepmask = 0;
-      int kn = kept_n;
-      for (int i = 0; i < cnt && kn < max_det; i++) {
-        if (!((supp >> i) & 1u)) {
-          keepmask |= 1u << i;
-          supp |= rowmask[i];
-          kn++;
+      __syncthreads();
+      // phase B: serial resolve inside the chunk (warp 0, every lane runs the same bit loop)
+      if (warp == 0) {
+        unsigned supp = misc[1];
+        unsigned keepmask = 0;
+        int kn = kept_n;
+        for (int i = 0; i < cnt && kn < max_det; i++) {
+          if (!((supp >> i) & 1u)) {
+            keepmask |= 1u << i;
+            supp |= rowmask[i];
+            kn++;
+          }
         }
-      }
-      if ((keepmask >> lane) & 1u) {
-        const int pos = kept_n + __popc(keepmask & ((1u << lane) - 1u));
-        kept[pos] = cbox[lane];
-        float* o = dets + ((size_t)b * max_det + pos) * row_w;
-        const float* r = craw + lane * 6;
+        if ((keepmask >> lane) & 1u) {
+          const int pos = kept_n + __popc(keepmask & ((1u << lane) - 1u));
+          kept[pos] = cbox[s0 + lane];
+          float* o = dets + ((size_t)b * max_det + pos) * row_w;
+          const float* r = craw + (s0 + lane) * 6;
 #pragma unroll
-        for (int q = 0; q < 6; q++) o[q] = r[q];
-        const int a = canchor[lane];
-        for (int q = 0; q < extra; q++) o[6 + q] = P[(size_t)(4 + nc + q) * A + a];
-        if (keep_idx) keep_idx[(size_t)b * max_det + pos] = a;
+          for (int q = 0; q < 6; q++) o[q] = r[q];
+          const int a = canchor[s0 + lane];
+          for (int q = 0; q < extra; q++) o[6 + q] = P[(size_t)(4 + nc + q) * A + a];
+          if (keep_idx) keep_idx[(size_t)b * max_det + pos] = a;
+        }
+        __syncwarp();
+        if (lane == 0) { misc[3] = (unsigned)kn; misc[1] = 0; }
       }
-      if (lane == 0) misc[3] = (unsigned)kn;
+      __syncthreads();
+      kept_n = (int)misc[3];
     }
-    __syncthreads();
-    kept_n = (int)misc[3];
+    __syncthreads();  // the next super-chunk overwrites cbox/craw
   }
   if (tid == 0) counts[b] = kept_n;
 }
@@ -198,7 +229,7 @@ int nms_launch(const float* pred, int B, int C, int A, int nc, float conf, float
   const int extra = C - 4 - nc;
   YB_CUDA_CHECK(cudaMemsetAsync(dets, 0, (size_t)B * max_det * (6 + extra) * sizeof(float), s));
   if (keep_idx) YB_CUDA_CHECK(cudaMemsetAsync(keep_idx, 0xFF, (size_t)B * max_det * sizeof(int), s));
-  const size_t fixed = (NMS_MAX_DET_CAP + 32) * sizeof(Box5) + 32 * 6 * 4 + 32 * 4 + 32 * 4 + 16;
+  const size_t fixed = NMS_FIXED_SMEM;
   unsigned long long* gkeys = nullptr;
   int key_cap = A;  // every anchor may be a candidate
   size_t smem = fixed;
@@ -217,9 +248,15 @@ int nms_launch(const float* pred, int B, int C, int A, int nc, float conf, float
                                        (int)(fixed + NMS_SMEM_KEYS * 8)));
     attr_set = true;
   }
-  nms_kernel<<<B, NMS_THREADS, smem, s>>>(pred, C, A, nc, conf, iou, max_det, max_nms, (float)max_wh, dets, counts,
-                                          keep_idx, gkeys, key_cap);
+  float* sconf = nullptr;
+  YB_CUDA_CHECK(cudaMallocAsync(&sconf, (size_t)B * A * 8, s));  // conf[B][A] then cls[B][A]
+  int* scls = reinterpret_cast<int*>(sconf + (size_t)B * A);
+  nms_scan_kernel<<<dim3((A + 255) / 256, B), 256, 0, s>>>(pred, C, A, nc, conf, sconf, scls);
   YB_CUDA_CHECK(cudaGetLastError());
+  nms_kernel<<<B, NMS_THREADS, smem, s>>>(pred, C, A, nc, conf, iou, max_det, max_nms, (float)max_wh, dets, counts,
+                                          keep_idx, gkeys, key_cap, sconf, scls);
+  YB_CUDA_CHECK(cudaGetLastError());
+  YB_CUDA_CHECK(cudaFreeAsync(sconf, s));
   if (gkeys) YB_CUDA_CHECK(cudaFreeAsync(gkeys, s));
   return 0;
 }
