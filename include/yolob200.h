@@ -68,6 +68,7 @@ typedef struct {
 
 #define YB_FLAG_NO_TCGEN05 1  /* F16 mode: use the CUDA-core fp16 kernels instead of tcgen05 (debug) */
 #define YB_FLAG_NO_GRAPH   2  /* do not capture the forward into a CUDA graph */
+#define YB_FLAG_NO_CONCURRENCY 8  /* run the independent head branches serially on one stream */
 #define YB_FLAG_DRY_RUN    4  /* build the op graph / expected-tensor list only (no CUDA calls; for host-side checks).
                                  Every compute entry point fails with YB_ERR_STATE on such an engine. */
 
@@ -142,6 +143,15 @@ int32_t yb_masks(const float* proto, const float* dets, const int32_t* counts, i
 int32_t yb_predict_u8(yb_engine* e, const uint8_t* images_host, int32_t batch, float conf_thres,
                       float iou_thres, int32_t max_det, float* dets_host, int32_t* counts_host,
                       void* stream);
+
+/* Pipelined form of yb_predict_u8 for serving loops: `slot` (0 or 1) selects one of two engine-owned
+ * stream + staging-buffer sets, so the H2D copy / forward / NMS / D2H of one batch overlap those of the
+ * other.  submit returns immediately; the host buffers must stay valid (and should be pinned) until
+ * yb_predict_u8_wait(slot) returned. */
+int32_t yb_predict_u8_submit(yb_engine* e, int32_t slot, const uint8_t* images_host, int32_t batch,
+                             float conf_thres, float iou_thres, int32_t max_det, float* dets_host,
+                             int32_t* counts_host);
+int32_t yb_predict_u8_wait(yb_engine* e, int32_t slot);
 
 /* Debug / profiling helpers (not part of the reference surface). */
 int32_t yb_num_ops(const yb_engine* e);

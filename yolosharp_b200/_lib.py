@@ -21,7 +21,7 @@ SIZES = {"n": 0, "s": 1, "m": 2, "l": 3, "x": 4}
 YB_TASK_DETECT, YB_TASK_SEGMENT = 0, 1
 YB_PREC_F32, YB_PREC_F16 = 0, 1
 YB_U8, YB_F16, YB_F32, YB_BF16 = 0, 5, 6, 15
-YB_FLAG_NO_TCGEN05, YB_FLAG_NO_GRAPH, YB_FLAG_DRY_RUN = 1, 2, 4
+YB_FLAG_NO_TCGEN05, YB_FLAG_NO_GRAPH, YB_FLAG_DRY_RUN, YB_FLAG_NO_CONCURRENCY = 1, 2, 4, 8
 
 # name -> (restype, argtypes); must list every function declared in include/yolob200.h
 SIGNATURES = {
@@ -40,6 +40,8 @@ SIGNATURES = {
     "yb_nms": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "yb_masks": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "yb_predict_u8": (c_i32, [c_vp, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp]),
+    "yb_predict_u8_submit": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp]),
+    "yb_predict_u8_wait": (c_i32, [c_vp, c_i32]),
     "yb_num_ops": (c_i32, [c_vp]),
     "yb_debug_read_activation": (c_i32, [c_vp, c_i32, c_i32, c_vp, C.c_int64, C.POINTER(c_i32 * 3)]),
     "yb_op_name": (c_cp, [c_vp, c_i32]),

@@ -38,6 +38,7 @@ struct ConvParams {
   View in, out, res;  // res.base == nullptr -> no residual
   View out2;          // optional second destination: nearest-2x upsampled copy (out2.base != nullptr)
   EpiDecode dec;
+  int share_sms = 0;  // 1: op runs concurrently with sibling branches - size its grid to half the SMs
   const void* w;      // packed weights, layout depends on kernel
   const float* bias;  // [Cout] fp32 (folded BN beta - mean*scale, or conv bias)
   int B;

@@ -68,6 +68,7 @@ struct TcConvPlan {
   TcArgs args;
   ConvParams p;
   bool flat;   // 1x1 stride-1 conv on the flattened pixel dimension
+  int occ;     // CTAs per SM this plan is sized for
   size_t smem;
   int grid;
 };
@@ -97,6 +98,29 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
   uint64_t d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
+}
+
+// Residual (Bottleneck shortcut) rows of one 32/16-column block, fetched with whole-row coalescing:
+// lane -> (row it*rpi + lane/pieces, 16-byte piece lane%pieces).  Issued BEFORE the accumulator is
+// awaited so the global-load latency overlaps the MMAs.
+__device__ __forceinline__ void res_prefetch(const TcArgs& a, int n0, int cb0, int lane, uint32_t pix_lo,
+                                             uint32_t pix_hi, bool valid, int4 (&rv)[4]) {
+  const int wb = min(32, a.n_tile - cb0);
+  const int pieces = wb >> 3, rpi = 32 / pieces;
+  const int my_r = lane / pieces, my_pc = lane - my_r * pieces;
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    rv[it] = make_int4(0, 0, 0, 0);
+    if (it < pieces) {
+      const int rr = it * rpi + my_r;
+      const uint32_t lo = __shfl_sync(0xffffffffu, pix_lo, rr), hi = __shfl_sync(0xffffffffu, pix_hi, rr);
+      const int vr = __shfl_sync(0xffffffffu, (int)valid, rr);
+      if (vr) {
+        const size_t px = ((size_t)hi << 32) | lo;
+        rv[it] = *reinterpret_cast<const int4*>(a.res + px * a.res_pitch + a.res_coff + n0 + cb0 + my_pc * 8);
+      }
+    }
+  }
 }
 
 template <int KK>
@@ -198,7 +222,7 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
 //                       request rate (~30 requests/clk chip-wide), not by bytes.
 //   B ring  : one [n_tile x BK] weight slab per (tap, channel slab), or all slabs resident.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   __shared__ __align__(8) uint64_t bars[4 * TC_MAX_STAGES + 5];
   __shared__ uint32_t tmem_base_slot;
@@ -348,6 +372,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const size_t pix = ((size_t)img * a.Ho + ho) * a.Wo + wo;
       const int n0 = nt * a.n_tile;
       const float* bias = s_bias + n0;
+      const uint32_t pix_lo = (uint32_t)pix, pix_hi = (uint32_t)((uint64_t)pix >> 32);
+      int4 rv[4];
+      const bool use_res = a.epi_mode == EPI_STORE && a.res != nullptr;
+      if (use_res && half * 32 < a.n_tile) res_prefetch(a, n0, half * 32, lane, pix_lo, pix_hi, valid, rv);
 
       mbar_wait(tfull0 + 8 * acc, aphase);
       tc_fence_after();
@@ -402,26 +430,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // Store path: 32-column blocks alternate between the two warps of a pair.  A lane owns one
         // output pixel (TMEM lane); rows are transposed through a per-warp smem tile so that a warp
         // store instruction writes 8 rows x 64 contiguous bytes instead of 32 scattered 16-byte pieces.
-        const uint32_t pix_lo = (uint32_t)pix, pix_hi = (uint32_t)((uint64_t)pix >> 32);
         for (int cb0 = half * 32; cb0 < a.n_tile; cb0 += 64) {
           const int wb = min(32, a.n_tile - cb0);  // 32 or 16 channels
           const int pieces = wb >> 3;              // 16-byte pieces per row (4 or 2)
           const int rpi = 32 / pieces;             // rows per warp instruction
           const int pmask = pieces - 1;
           const int my_r = lane / pieces, my_pc = lane - my_r * pieces;
-          if (a.res) {
-            for (int it = 0; it < pieces; it++) {
-              const int rr = it * rpi + my_r;
-              const uint32_t lo = __shfl_sync(0xffffffffu, pix_lo, rr), hi = __shfl_sync(0xffffffffu, pix_hi, rr);
-              const int vr = __shfl_sync(0xffffffffu, (int)valid, rr);
-              int4 v = make_int4(0, 0, 0, 0);
-              if (vr) {
-                const size_t px = ((size_t)hi << 32) | lo;
-                v = *reinterpret_cast<const int4*>(a.res + px * a.res_pitch + a.res_coff + n0 + cb0 + my_pc * 8);
+          if (use_res) {
+#pragma unroll
+            for (int it = 0; it < 4; it++)
+              if (it < pieces) {
+                const int rr = it * rpi + my_r;
+                st_shared_v4(stg_res + (rr * pieces + (my_pc ^ (rr & pmask))) * 16, rv[it]);
               }
-              st_shared_v4(stg_res + (rr * pieces + (my_pc ^ (rr & pmask))) * 16, v);
-            }
             __syncwarp();
+            if (cb0 + 64 < a.n_tile) res_prefetch(a, n0, cb0 + 64, lane, pix_lo, pix_hi, valid, rv);  // next block
           }
           for (int c0 = cb0; c0 < cb0 + wb; c0 += 16) {
             uint32_t v[16];
@@ -439,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               for (int j = 0; j < 16; j++) f[j] = silu_tanh(f[j]);
             }
             const int pc0 = (c0 - cb0) >> 3;
-            if (a.res) {
+            if (use_res) {
               const int4 r0 = ld_shared_v4(stg_res + (lane * pieces + (pc0 ^ (lane & pmask))) * 16);
               const int4 r1 = ld_shared_v4(stg_res + (lane * pieces + ((pc0 + 1) ^ (lane & pmask))) * 16);
               const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
@@ -623,23 +646,42 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   a.a_stride = (uint32_t)((std::max(a_rows, 128) * a.row_bytes + 1023) / 1024 * 1024);
   a.b_stride = (uint32_t)((a.n_tile * a.row_bytes + 1023) / 1024 * 1024);
   a.ksteps = p.k * p.k * a.chunks;
-  const size_t budget = 200 * 1024 - 32 * 1024;  // 32 KiB go to the epilogue transpose tiles
-  // keep the whole weight matrix in smem when it leaves room for >= 3 activation slabs: removes the
-  // weight re-fetch per tile (the kernel is L2-request-bound, not byte-bound)
+  // Two CTAs per SM (each <= ~100 KiB smem, <= 256 TMEM columns) double the tiles in flight per SM and
+  // hide the producer -> MMA -> epilogue hand-off latencies of the HBM-bound high-resolution layers;
+  // layers whose resident weights or wide N tiles do not fit run one CTA per SM with the full budget.
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * a.n_tile)) cols <<= 1;
+  a.tmem_cols = cols;
   const size_t b_all = (size_t)a.ksteps * a.b_stride;
-  a.b_resident = (a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= budget) ? 1 : 0;
-  if (a.b_resident) {
-    a.stages_a = (int)std::min<size_t>(a.mode == TC_HALO ? 6 : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
-    a.stages_b = 0;
-    plan->smem = (size_t)a.stages_a * a.a_stride + b_all + 1024;
-  } else if (a.mode == TC_HALO) {
-    // A slab serves 9 B slabs: a short A ring and as many weight slabs as fit
-    a.stages_a = (int)std::min<size_t>(3, std::max<size_t>(2, (budget / 3) / a.a_stride));
-    a.stages_b = (int)std::min<size_t>(TC_MAX_STAGES, (budget - (size_t)a.stages_a * a.a_stride) / a.b_stride);
-    plan->smem = (size_t)a.stages_a * a.a_stride + (size_t)a.stages_b * a.b_stride + 1024;
-  } else {
-    a.stages_a = a.stages_b = (int)std::min<size_t>(8, budget / (a.a_stride + a.b_stride));
-    plan->smem = (size_t)a.stages_a * (a.a_stride + a.b_stride) + 1024;
+  const int m_tiles = plan->flat ? (p.B * p.Ho * p.Wo + 127) / 128
+                                 : p.B * ((p.Wo + a.BW - 1) / a.BW) * ((p.Ho + a.BH - 1) / a.BH);
+  plan->occ = 1;
+  for (int occ = 2; occ >= 1; occ--) {
+    const size_t budget = occ == 2 ? 62 * 1024 : 200 * 1024 - 32 * 1024;  // rings only (32 KiB epilogue tiles extra)
+    if (occ == 2 && (cols > 256 || m_tiles * a.n_tiles < 2 * 148)) continue;
+    // keep the whole weight matrix in smem when it leaves room for >= 3 activation slabs: removes the
+    // weight re-fetch per tile
+    a.b_resident = (a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= budget) ? 1 : 0;
+    // resident weights at one CTA/SM beat re-fetched weights at two CTAs/SM
+    if (occ == 2 && !a.b_resident && a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= 168 * 1024) continue;
+    if (a.b_resident) {
+      a.stages_a = (int)std::min<size_t>(a.mode == TC_HALO ? 6 : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
+      a.stages_b = 0;
+      plan->smem = (size_t)a.stages_a * a.a_stride + b_all + 1024;
+    } else if (a.mode == TC_HALO) {
+      // A slab serves 9 B slabs: a short A ring and as many weight slabs as fit
+      a.stages_a = (int)std::min<size_t>(3, std::max<size_t>(2, (budget / 3) / a.a_stride));
+      const size_t rest = budget > (size_t)a.stages_a * a.a_stride ? budget - (size_t)a.stages_a * a.a_stride : 0;
+      a.stages_b = (int)std::min<size_t>(TC_MAX_STAGES, rest / a.b_stride);
+      plan->smem = (size_t)a.stages_a * a.a_stride + (size_t)a.stages_b * a.b_stride + 1024;
+    } else {
+      a.stages_a = a.stages_b = (int)std::min<size_t>(8, budget / (a.a_stride + a.b_stride));
+      plan->smem = (size_t)a.stages_a * (a.a_stride + a.b_stride) + 1024;
+    }
+    const bool fits = a.stages_a >= 2 && (a.b_resident || a.stages_b >= ((occ == 2 && a.mode == TC_HALO) ? 4 : 2)) &&
+                      (size_t)a.stages_a * a.a_stride + (a.b_resident ? b_all : (size_t)a.stages_b * a.b_stride) <= budget;
+    if (fits && (occ == 1 || a.stages_a >= 3)) { plan->occ = occ; break; }
+    if (occ == 1) a.stages_a = 0;  // reported below
   }
   a.stage_off = (uint32_t)(plan->smem - 1024);
   plan->smem += 32 * 1024;
@@ -656,15 +698,13 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     delete plan;
     return nullptr;
   }
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * a.n_tile)) cols <<= 1;
-  a.tmem_cols = cols;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     // dynamic limit = ring budget + alignment slack (static smem of the kernel counts against the 227 KiB cap)
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 202 * 1024);
     if (ce != cudaSuccess) {
       if (err) *err = std::string("cudaFuncSetAttribute(conv_tc_kernel) failed: ") + cudaGetErrorString(ce);
@@ -673,7 +713,7 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
       return nullptr;
     }
   }
-  plan->grid = num_sms;
+  plan->grid = num_sms * plan->occ;
   return plan;
 }
 
@@ -696,7 +736,10 @@ int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s) {
     a.tiles_h = (p.Ho + a.BH - 1) / a.BH;
   }
   a.total_tiles = a.imgs * a.tiles_w * a.tiles_h * a.n_tiles;
-  const int grid = std::min(plan->grid, a.total_tiles);
+  int grid = std::min(plan->grid, a.total_tiles);
+  // concurrent head branches: a latency-bound layer with ~1 tile per CTA gives up half of its CTAs (each
+  // then pipelines 2-3 tiles) so that a sibling branch can occupy the other SMs at the same time
+  if (plan->p.share_sms && a.total_tiles <= 4 * plan->grid) grid = std::max(1, std::min(grid, (a.total_tiles + 2) / 3));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(TC_THREADS);

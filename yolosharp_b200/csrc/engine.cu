@@ -54,6 +54,9 @@ struct OpDesc {
   float* bias = nullptr;
   TcConvPlan* plan = nullptr;
   bool use_tc = false;
+  int lane = 0;        // 0 = main stream; >0 = independent head branch that may run concurrently
+  int lane_level = -1; // pyramid level whose feature map a side lane waits for
+  int feat_level = -1; // this op completes feats[feat_level] (fork point for the head lanes)
   EpiDecode dec;       // conv: fused Detect-tail epilogue (tcgen05 path)
   bool fused = false;  // decode op: its work is done by the producing convs' epilogues
 };
@@ -83,12 +86,16 @@ struct yb_engine {
   VRef input_nhwc;  // generic path: converted network input (3 channels)
   VRef proto_view;
   bool has_stem_tc = false;
-  // staging for yb_predict_u8
-  uint8_t* stage_in = nullptr;
-  float* stage_pred = nullptr;
-  float* stage_dets = nullptr;
-  int* stage_counts = nullptr;
-  int stage_max_det = 0;
+  // staging for yb_predict_u8 (index 0) and the two pipelined slots of yb_predict_u8_submit (1, 2)
+  struct Stage {
+    uint8_t* in = nullptr;
+    float* pred = nullptr;
+    float* dets = nullptr;
+    int* counts = nullptr;
+    int max_det = 0;
+    cudaStream_t stream = nullptr;
+  };
+  Stage stage[3];
   // CUDA graph cache
   struct GraphKey {
     const void* in; int dtype; int B; float* pred; float* proto;
@@ -100,6 +107,11 @@ struct yb_engine {
   std::map<GraphKey, int> seen;
   cudaStream_t capture_stream = nullptr;
   std::vector<void*> dev_allocs;
+  // concurrent head branches (box / cls / mask-coefficient chains of the three levels + Proto)
+  static const int kLanes = 13;
+  cudaStream_t side[kLanes] = {};
+  cudaEvent_t ev_feat[3] = {}, ev_done[kLanes] = {};
+  bool lanes_ok = false;
 };
 
 namespace yb {
@@ -401,13 +413,22 @@ static int build_graph(yb_engine* e) {
   for (int l = 0; l < 3; l++) e->A += (H / strides[l]) * (W / strides[l]);
   e->pred_c = 4 + nc + (seg ? nm : 0);
   int a0 = 0;
+  for (int l = 0; l < 3; l++)  // fork points: the last op that writes each Detect input
+    for (int i = (int)e->ops.size() - 1; i >= 0; i--)
+      if (e->ops[i].out.buf == feats[l].buf) { e->ops[i].feat_level = l; break; }
+  auto tag_lane = [&](size_t from, int lane, int level) {
+    for (size_t i = from; i < e->ops.size(); i++) { e->ops[i].lane = lane; e->ops[i].lane_level = level; }
+  };
   for (int l = 0; l < 3; l++) {
     const int hl = H / strides[l], wl = W / strides[l];
     const std::string L = std::to_string(l);
+    size_t mark = e->ops.size();
     VRef t1 = b.new_buf(hl, wl, c2), t2 = b.new_buf(hl, wl, c2), box = b.new_buf(hl, wl, 4 * rm);
     b.conv(hn + ".cv2." + L + ".0", feats[l], t1, 3, 1);
     b.conv(hn + ".cv2." + L + ".1", t1, t2, 3, 1);
     b.conv(hn + ".cv2." + L + ".2", t2, box, 1, 1, ACT_NONE, false);
+    tag_lane(mark, 1 + 3 * l, l);
+    mark = e->ops.size();
     VRef u1 = b.new_buf(hl, wl, c3), u2 = b.new_buf(hl, wl, c3), cls = b.new_buf(hl, wl, nc);
     if (!v11) {  // legacy cls branch: two 3x3 Convs (Head.cs:49)
       b.conv(hn + ".cv3." + L + ".0", feats[l], u1, 3, 1);
@@ -420,6 +441,8 @@ static int build_graph(yb_engine* e) {
       b.conv(hn + ".cv3." + L + ".1.1", d2, u2, 1, 1);
     }
     b.conv(hn + ".cv3." + L + ".2", u2, cls, 1, 1, ACT_NONE, false);
+    tag_lane(mark, 2 + 3 * l, l);
+    mark = e->ops.size();
     VRef coef;
     if (seg) {
       VRef m1 = b.new_buf(hl, wl, c4), m2 = b.new_buf(hl, wl, c4);
@@ -427,6 +450,7 @@ static int build_graph(yb_engine* e) {
       b.conv(hn + ".cv4." + L + ".0", feats[l], m1, 3, 1);
       b.conv(hn + ".cv4." + L + ".1", m1, m2, 3, 1);
       b.conv(hn + ".cv4." + L + ".2", m2, coef, 1, 1, ACT_NONE, false);
+      tag_lane(mark, 3 + 3 * l, l);
     }
     OpDesc op;
     op.type = OP_DECODE;
@@ -436,7 +460,11 @@ static int build_graph(yb_engine* e) {
     e->ops.push_back(op);
     a0 += hl * wl;
   }
-  if (seg) e->proto_view = b.proto(hn + ".proto", feats[0], e->ch[0], nm);  // Head.cs:247: npr = ch[0]
+  if (seg) {
+    const size_t mark = e->ops.size();
+    e->proto_view = b.proto(hn + ".proto", feats[0], e->ch[0], nm);  // Head.cs:247: npr = ch[0]
+    tag_lane(mark, 10, 0);
+  }
   return 0;
 }
 
@@ -577,8 +605,22 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
                    cudaStream_t s, cudaEvent_t* events = nullptr) {
   int rc;
   bool input_converted = false;
+  // Head branches are independent chains of small, latency-bound kernels: with every Detect tail fused
+  // (tcgen05 path) they run on side streams forked at the op that completes their feature map and are
+  // joined at the end; inside a captured CUDA graph this becomes real branch parallelism.
+  const bool lanes = e->lanes_ok && !events;
+  bool lane_started[yb_engine::kLanes] = {};
+  cudaStream_t main_s = s;
   for (size_t i = 0; i < e->ops.size(); i++) {
     OpDesc& op = e->ops[i];
+    s = main_s;
+    if (lanes && op.lane > 0) {
+      s = e->side[op.lane];
+      if (!lane_started[op.lane]) {
+        YB_CUDA_CHECK(cudaStreamWaitEvent(s, e->ev_feat[op.lane_level], 0));
+        lane_started[op.lane] = true;
+      }
+    }
     if (events) YB_CUDA_CHECK(cudaEventRecord(events[i], s));
     switch (op.type) {
       case OP_CONV: {
@@ -642,7 +684,15 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
         set_error("op type not implemented: " + op.name);
         return YB_ERR_NOT_IMPLEMENTED;
     }
+    if (lanes && op.feat_level >= 0) YB_CUDA_CHECK(cudaEventRecord(e->ev_feat[op.feat_level], main_s));
   }
+  s = main_s;
+  if (lanes)
+    for (int l = 1; l < yb_engine::kLanes; l++)
+      if (lane_started[l]) {
+        YB_CUDA_CHECK(cudaEventRecord(e->ev_done[l], e->side[l]));
+        YB_CUDA_CHECK(cudaStreamWaitEvent(main_s, e->ev_done[l], 0));
+      }
   if (events) YB_CUDA_CHECK(cudaEventRecord(events[e->ops.size()], s));
   return 0;
 }
@@ -711,6 +761,11 @@ int32_t yb_create(const yb_config* cfg, yb_engine** out) {
   YB_CUDA_CHECK(cudaMalloc((void**)&e->arena, off));
   YB_CUDA_CHECK(cudaMemset(e->arena, 0, off));
   YB_CUDA_CHECK(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
+  for (int l = 1; l < yb_engine::kLanes; l++) {
+    YB_CUDA_CHECK(cudaStreamCreateWithFlags(&e->side[l], cudaStreamNonBlocking));
+    YB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done[l], cudaEventDisableTiming));
+  }
+  for (int l = 0; l < 3; l++) YB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_feat[l], cudaEventDisableTiming));
   *out = e.release();
   return YB_OK;
 }
@@ -723,11 +778,20 @@ void yb_destroy(yb_engine* e) {
   for (auto& op : e->ops) if (op.plan) tc_conv_plan_destroy(op.plan);
   for (void* p : e->dev_allocs) cudaFree(p);
   if (e->arena) cudaFree(e->arena);
-  if (e->stage_in) cudaFree(e->stage_in);
-  if (e->stage_pred) cudaFree(e->stage_pred);
-  if (e->stage_dets) cudaFree(e->stage_dets);
-  if (e->stage_counts) cudaFree(e->stage_counts);
+  for (auto& st : e->stage) {
+    if (st.in) cudaFree(st.in);
+    if (st.pred) cudaFree(st.pred);
+    if (st.dets) cudaFree(st.dets);
+    if (st.counts) cudaFree(st.counts);
+    if (st.stream) cudaStreamDestroy(st.stream);
+  }
   if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
+  for (int l = 1; l < yb_engine::kLanes; l++) {
+    if (e->side[l]) cudaStreamDestroy(e->side[l]);
+    if (e->ev_done[l]) cudaEventDestroy(e->ev_done[l]);
+  }
+  for (int l = 0; l < 3; l++)
+    if (e->ev_feat[l]) cudaEventDestroy(e->ev_feat[l]);
   delete e;
 }
 
@@ -824,6 +888,7 @@ int32_t yb_finalize_weights(yb_engine* e) {
       ConvParams p = conv_params(e, op, e->cfg.max_batch);
       p.w = op.w_f16;
       p.dec = op.dec;
+      p.share_sms = (op.lane > 0 && !(e->cfg.flags & YB_FLAG_NO_CONCURRENCY)) ? 1 : 0;
       if (tc_conv_supported(p)) {
         std::string err;
         op.plan = tc_conv_plan_create(p, &err);
@@ -840,6 +905,11 @@ int32_t yb_finalize_weights(yb_engine* e) {
         return YB_ERR_STATE;
       }
   }
+  e->lanes_ok = allow_tc && !(e->cfg.flags & YB_FLAG_NO_CONCURRENCY);
+  for (auto& d : e->ops)
+    if (d.type == OP_DECODE && !d.fused) e->lanes_ok = false;  // the generic decode kernel joins box+cls lanes
+  for (auto& c : e->ops)
+    if (c.lane > 0 && (c.type == OP_CONV || c.type == OP_DWCONV) && c.type == OP_CONV && !c.use_tc) {}
   e->host.clear();
   e->finalized = true;
   return YB_OK;
@@ -903,38 +973,68 @@ int32_t yb_masks(const float* proto, const float* dets, const int32_t* counts, i
   return masks_launch(proto, dets, counts, batch, max_det, nm, mh, mw, height, width, masks, (cudaStream_t)stream);
 }
 
-int32_t yb_predict_u8(yb_engine* e, const uint8_t* images_host, int32_t batch, float conf_thres, float iou_thres,
-                      int32_t max_det, float* dets_host, int32_t* counts_host, void* stream) {
-  if (!e || !images_host || !dets_host || !counts_host) { set_error("yb_predict_u8: null argument"); return YB_ERR_INVALID_ARG; }
-  if (!e->finalized) { set_error("yb_predict_u8: call yb_finalize_weights first"); return YB_ERR_STATE; }
-  if (batch <= 0 || batch > e->cfg.max_batch) { set_error("yb_predict_u8: batch outside [1, max_batch]"); return YB_ERR_INVALID_ARG; }
-  if (e->cfg.task != YB_TASK_DETECT) { set_error("yb_predict_u8: detect engines only"); return YB_ERR_NOT_IMPLEMENTED; }
-  if (max_det <= 0 || max_det > 1024) { set_error("yb_predict_u8: max_det outside [1,1024]"); return YB_ERR_INVALID_ARG; }
+static int32_t predict_enqueue(yb_engine* e, yb_engine::Stage& st, const uint8_t* images_host, int32_t batch,
+                               float conf_thres, float iou_thres, int32_t max_det, float* dets_host,
+                               int32_t* counts_host, cudaStream_t s, const char* who) {
+  if (!e || !images_host || !dets_host || !counts_host) { set_error(std::string(who) + ": null argument"); return YB_ERR_INVALID_ARG; }
+  if (!e->finalized) { set_error(std::string(who) + ": call yb_finalize_weights first"); return YB_ERR_STATE; }
+  if (batch <= 0 || batch > e->cfg.max_batch) { set_error(std::string(who) + ": batch outside [1, max_batch]"); return YB_ERR_INVALID_ARG; }
+  if (e->cfg.task != YB_TASK_DETECT) { set_error(std::string(who) + ": detect engines only"); return YB_ERR_NOT_IMPLEMENTED; }
+  if (max_det <= 0 || max_det > 1024) { set_error(std::string(who) + ": max_det outside [1,1024]"); return YB_ERR_INVALID_ARG; }
   YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
-  cudaStream_t s = (cudaStream_t)stream;
   const size_t img_bytes = (size_t)3 * e->cfg.height * e->cfg.width;
   const int row_w = 6 + (e->pred_c - 4 - e->cfg.nc);
-  if (!e->stage_in) {
-    YB_CUDA_CHECK(cudaMalloc((void**)&e->stage_in, img_bytes * e->cfg.max_batch));
-    YB_CUDA_CHECK(cudaMalloc((void**)&e->stage_pred, (size_t)e->cfg.max_batch * e->pred_c * e->A * sizeof(float)));
-    YB_CUDA_CHECK(cudaMalloc((void**)&e->stage_counts, (size_t)e->cfg.max_batch * sizeof(int)));
+  if (!st.in) {
+    YB_CUDA_CHECK(cudaMalloc((void**)&st.in, img_bytes * e->cfg.max_batch));
+    YB_CUDA_CHECK(cudaMalloc((void**)&st.pred, (size_t)e->cfg.max_batch * e->pred_c * e->A * sizeof(float)));
+    YB_CUDA_CHECK(cudaMalloc((void**)&st.counts, (size_t)e->cfg.max_batch * sizeof(int)));
   }
-  if (e->stage_max_det < max_det) {
-    if (e->stage_dets) cudaFree(e->stage_dets);
-    e->stage_dets = nullptr;
-    YB_CUDA_CHECK(cudaMalloc((void**)&e->stage_dets, (size_t)e->cfg.max_batch * max_det * row_w * sizeof(float)));
-    e->stage_max_det = max_det;
+  if (st.max_det < max_det) {
+    if (st.dets) cudaFree(st.dets);
+    st.dets = nullptr;
+    YB_CUDA_CHECK(cudaMalloc((void**)&st.dets, (size_t)e->cfg.max_batch * max_det * row_w * sizeof(float)));
+    st.max_det = max_det;
   }
-  YB_CUDA_CHECK(cudaMemcpyAsync(e->stage_in, images_host, img_bytes * batch, cudaMemcpyHostToDevice, s));
-  int rc = yb_forward(e, e->stage_in, YB_U8, batch, e->stage_pred, nullptr, stream);
+  YB_CUDA_CHECK(cudaMemcpyAsync(st.in, images_host, img_bytes * batch, cudaMemcpyHostToDevice, s));
+  int rc = yb_forward(e, st.in, YB_U8, batch, st.pred, nullptr, (void*)s);
   if (rc) return rc;
-  rc = nms_launch(e->stage_pred, batch, e->pred_c, e->A, e->cfg.nc, conf_thres, iou_thres, max_det, 30000, 7680,
-                  e->stage_dets, e->stage_counts, nullptr, s);
+  rc = nms_launch(st.pred, batch, e->pred_c, e->A, e->cfg.nc, conf_thres, iou_thres, max_det, 30000, 7680, st.dets,
+                  st.counts, nullptr, s);
   if (rc) return rc;
-  YB_CUDA_CHECK(cudaMemcpyAsync(dets_host, e->stage_dets, (size_t)batch * max_det * row_w * sizeof(float),
+  YB_CUDA_CHECK(cudaMemcpyAsync(dets_host, st.dets, (size_t)batch * max_det * row_w * sizeof(float),
                                 cudaMemcpyDeviceToHost, s));
-  YB_CUDA_CHECK(cudaMemcpyAsync(counts_host, e->stage_counts, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, s));
-  YB_CUDA_CHECK(cudaStreamSynchronize(s));
+  YB_CUDA_CHECK(cudaMemcpyAsync(counts_host, st.counts, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, s));
+  return YB_OK;
+}
+
+int32_t yb_predict_u8(yb_engine* e, const uint8_t* images_host, int32_t batch, float conf_thres, float iou_thres,
+                      int32_t max_det, float* dets_host, int32_t* counts_host, void* stream) {
+  if (!e) { set_error("yb_predict_u8: null argument"); return YB_ERR_INVALID_ARG; }
+  int rc = predict_enqueue(e, e->stage[0], images_host, batch, conf_thres, iou_thres, max_det, dets_host, counts_host,
+                           (cudaStream_t)stream, "yb_predict_u8");
+  if (rc) return rc;
+  YB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return YB_OK;
+}
+
+int32_t yb_predict_u8_submit(yb_engine* e, int32_t slot, const uint8_t* images_host, int32_t batch, float conf_thres,
+                             float iou_thres, int32_t max_det, float* dets_host, int32_t* counts_host) {
+  if (!e || slot < 0 || slot > 1) { set_error("yb_predict_u8_submit: bad engine / slot (0 or 1)"); return YB_ERR_INVALID_ARG; }
+  yb_engine::Stage& st = e->stage[1 + slot];
+  if (!st.stream) {
+    YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    YB_CUDA_CHECK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  }
+  return predict_enqueue(e, st, images_host, batch, conf_thres, iou_thres, max_det, dets_host, counts_host, st.stream,
+                         "yb_predict_u8_submit");
+}
+
+int32_t yb_predict_u8_wait(yb_engine* e, int32_t slot) {
+  if (!e || slot < 0 || slot > 1) { set_error("yb_predict_u8_wait: bad engine / slot (0 or 1)"); return YB_ERR_INVALID_ARG; }
+  yb_engine::Stage& st = e->stage[1 + slot];
+  if (!st.stream) { set_error("yb_predict_u8_wait: nothing was submitted on this slot"); return YB_ERR_STATE; }
+  YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  YB_CUDA_CHECK(cudaStreamSynchronize(st.stream));
   return YB_OK;
 }
 

@@ -101,6 +101,16 @@ class Engine:
                                       _stream_ptr(stream)))
         return dets_host, counts_host
 
+    def predict_u8_submit(self, slot, images_host, dets_host, counts_host, conf_thres=0.25, iou_thres=0.45, max_det=300):
+        """Pipelined predict: enqueue H2D + forward + NMS + D2H on the engine's slot stream (slot 0/1)."""
+        assert not images_host.is_cuda and images_host.dtype == torch.uint8 and images_host.is_contiguous()
+        L.check(L.lib().yb_predict_u8_submit(self._h, slot, C.c_void_p(images_host.data_ptr()), images_host.shape[0],
+                                             conf_thres, iou_thres, max_det, C.c_void_p(dets_host.data_ptr()),
+                                             C.c_void_p(counts_host.data_ptr())))
+
+    def predict_u8_wait(self, slot):
+        L.check(L.lib().yb_predict_u8_wait(self._h, slot))
+
     # ---- debug ----
     def op_names(self):
         lib = L.lib()
