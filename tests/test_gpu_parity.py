@@ -310,6 +310,29 @@ def test_predict_u8_end_to_end(y):
         assert torch.equal(dets[i, :counts[i], 5], oout[i][:, 5])
 
 
+def test_predict_u8_submit_wait_pipelined(y):
+    """Two-slot pipelined predict (yb_predict_u8_submit / _wait) returns the same detections as the
+    synchronous call, for interleaved submissions of different batches."""
+    m = oracle_model("v8", "detect", "n")
+    e = make_engine(y, m, "f16", 4, 320, 320)
+    imgs = [synth_image(4, 320, 320, seed=40 + i, dtype=torch.uint8).pin_memory() for i in range(3)]
+    ref = [tuple(t.clone() for t in e.predict_u8(im, 0.25, 0.45, 300)) for im in imgs]
+    dh = [torch.empty((4, 300, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+    ch = [torch.empty((4,), dtype=torch.int32).pin_memory() for _ in range(2)]
+    for rep in range(3):
+        e.predict_u8_submit(0, imgs[0], dh[0], ch[0], 0.25, 0.45, 300)
+        e.predict_u8_submit(1, imgs[1], dh[1], ch[1], 0.25, 0.45, 300)
+        e.predict_u8_wait(0)
+        assert torch.equal(ch[0], ref[0][1]) and torch.equal(dh[0], ref[0][0])
+        e.predict_u8_submit(0, imgs[2], dh[0], ch[0], 0.25, 0.45, 300)
+        e.predict_u8_wait(1)
+        assert torch.equal(ch[1], ref[1][1]) and torch.equal(dh[1], ref[1][0])
+        e.predict_u8_wait(0)
+        assert torch.equal(ch[0], ref[2][1]) and torch.equal(dh[0], ref[2][0])
+    with pytest.raises(y.YbError):
+        e.predict_u8_wait(5)
+
+
 def test_missing_weight_is_an_error(y):
     m = oracle_model("v8", "detect", "n")
     sd = dict(m.state_dict())

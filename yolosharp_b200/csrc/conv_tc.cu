@@ -29,6 +29,11 @@
 
 namespace yb {
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn(std::string* err);
+
 enum TcMode { TC_TAP = 0, TC_HALO = 1 };
 
 struct TcArgs {
@@ -69,6 +74,7 @@ struct TcConvPlan {
   ConvParams p;
   bool flat;   // 1x1 stride-1 conv on the flattened pixel dimension
   int occ;     // CTAs per SM this plan is sized for
+  bool small;  // <= 2 tiles per CTA
   size_t smem;
   int grid;
 };
@@ -518,10 +524,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------
 // Host side: tiling choice + tensor maps
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static EncodeTiledFn get_encode_fn(std::string* err) {
   static EncodeTiledFn fn = nullptr;
   if (fn) return fn;
@@ -657,13 +659,16 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
                                  : p.B * ((p.Wo + a.BW - 1) / a.BW) * ((p.Ho + a.BH - 1) / a.BH);
   plan->occ = 1;
   for (int occ = 2; occ >= 1; occ--) {
-    const size_t budget = occ == 2 ? 62 * 1024 : 200 * 1024 - 32 * 1024;  // rings only (32 KiB epilogue tiles extra)
-    if (occ == 2 && (cols > 256 || m_tiles * a.n_tiles < 2 * 148)) continue;
+    const size_t budget = occ == 2 ? 72 * 1024 : 200 * 1024 - 32 * 1024;  // rings only (32 KiB epilogue tiles extra)
+    // layers with <= 2 tiles per CTA gain nothing from deep rings or resident weights; a small footprint
+    // lets the NEXT kernel's CTAs (PDL / sibling branches) become resident while this one drains
+    const bool small = m_tiles * a.n_tiles <= 2 * 148;
+    if (occ == 2 && cols > 256) continue;
     // keep the whole weight matrix in smem when it leaves room for >= 3 activation slabs: removes the
     // weight re-fetch per tile
     a.b_resident = (a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= budget) ? 1 : 0;
     // resident weights at one CTA/SM beat re-fetched weights at two CTAs/SM
-    if (occ == 2 && !a.b_resident && a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= 168 * 1024) continue;
+    if (occ == 2 && !small && !a.b_resident && a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= 168 * 1024) continue;
     if (a.b_resident) {
       a.stages_a = (int)std::min<size_t>(a.mode == TC_HALO ? 6 : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
       a.stages_b = 0;
@@ -678,9 +683,9 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
       a.stages_a = a.stages_b = (int)std::min<size_t>(8, budget / (a.a_stride + a.b_stride));
       plan->smem = (size_t)a.stages_a * (a.a_stride + a.b_stride) + 1024;
     }
-    const bool fits = a.stages_a >= 2 && (a.b_resident || a.stages_b >= ((occ == 2 && a.mode == TC_HALO) ? 4 : 2)) &&
+    const bool fits = a.stages_a >= 2 && (a.b_resident || a.stages_b >= ((occ == 2 && a.mode == TC_HALO) ? 3 : 2)) &&
                       (size_t)a.stages_a * a.a_stride + (a.b_resident ? b_all : (size_t)a.stages_b * a.b_stride) <= budget;
-    if (fits && (occ == 1 || a.stages_a >= 3)) { plan->occ = occ; break; }
+    if (fits && (occ == 1 || small || a.stages_a >= 3)) { plan->occ = occ; break; }
     if (occ == 1) a.stages_a = 0;  // reported below
   }
   a.stage_off = (uint32_t)(plan->smem - 1024);
@@ -714,6 +719,7 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     }
   }
   plan->grid = num_sms * plan->occ;
+  plan->small = m_tiles * a.n_tiles <= 2 * 148;
   return plan;
 }
 
@@ -739,7 +745,8 @@ int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s) {
   int grid = std::min(plan->grid, a.total_tiles);
   // concurrent head branches: a latency-bound layer with ~1 tile per CTA gives up half of its CTAs (each
   // then pipelines 2-3 tiles) so that a sibling branch can occupy the other SMs at the same time
-  if (plan->p.share_sms && a.total_tiles <= 4 * plan->grid) grid = std::max(1, std::min(grid, (a.total_tiles + 2) / 3));
+  if (plan->p.share_sms && a.total_tiles <= 4 * plan->grid && a.ksteps * (a.BK >> 4) <= 40)
+    grid = std::max(1, std::min(grid, (a.total_tiles + 2) / 3));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(TC_THREADS);
@@ -756,83 +763,191 @@ int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------
 // Stem: model.0 = Conv(3, C, k3, s2) straight from the NCHW network input (u8 / f16 / f32).
-// K = 27 is too thin for the tensor cores and the layer is HBM-bound (reads the image once, writes
-// C x H/2 x W/2 fp16); one thread per output pixel, weights broadcast from shared memory.
+// K = 27 (padded to 32) on the tensor cores: per tile of 16 x 8 output pixels
+//   im2col   128 threads, one output pixel each: 27 taps read from global (neighbours share lines in
+//            L1) -> fp16 -> one 64-byte A row (SWIZZLE_64B layout written by hand)
+//   MMA      2 x tcgen05.mma (M=128, N=Cout, K=16), weights [Cout][32] fp16 resident in smem
+//   epilogue same 128 threads: tcgen05.ld -> +bias -> SiLU -> fp16 NHWC store (Cout*2 contiguous bytes)
+// Four CTAs per SM overlap each other's load / MMA / store latencies; the layer is HBM-bound
+// (reads the image once, writes Cout x H/2 x W/2 fp16).
+// (A TMA box load of the NCHW patch faulted with "illegal instruction" on B200 for rank-3 f32 maps;
+//  plain loads are used instead.)
 // ------------------------------------------------------------------------------------------
+constexpr int ST_TW = 16, ST_TH = 8;
+constexpr int ST_THREADS = 160;  // warps 0-3: im2col + epilogue, warp 4: MMA issue
+
+struct StemArgs {
+  const void* in;
+  const __half* w16;   // [Cout][32] fp16, k = (kh*3+kw)*3 + c, k >= 27 zero
+  const float* bias;
+  __half* out;
+  int out_pitch, out_coff;
+  int B, H, W, Ho, Wo, Cout;
+  int dtype;
+  int tiles_w, tiles_h, total_tiles;
+  uint32_t tmem_cols;
+};
+
 __device__ __forceinline__ float stem_load(const void* in, int dtype, size_t i) {
   if (dtype == YB_U8) return (float)reinterpret_cast<const uint8_t*>(in)[i] * (1.0f / 255.0f);
   if (dtype == YB_F16) return __half2float(reinterpret_cast<const __half*>(in)[i]);
   return reinterpret_cast<const float*>(in)[i];
 }
 
-constexpr int ST_TW = 64, ST_TH = 4;  // output tile per block (256 threads = one output pixel each)
-
-__global__ void __launch_bounds__(256) stem_kernel(const void* __restrict__ in, int dtype, int B, int H, int W, int Cout,
-                                                   const float* __restrict__ w, const float* __restrict__ bias,
-                                                   View out) {
-  extern __shared__ __align__(16) float st_smem[];  // [27][Cout] weights | [Cout] bias | [3][2*TH+1][2*TW+1] input patch
-  float* sw = st_smem;
-  float* sb = sw + 27 * Cout;
-  float* sx = sb + Cout;
-  constexpr int PW = 2 * ST_TW + 1, PH = 2 * ST_TH + 1;
-  const int Ho = H / 2, Wo = W / 2;
-  const int tiles_w = (Wo + ST_TW - 1) / ST_TW, tiles_h = (Ho + ST_TH - 1) / ST_TH;
-  const int n = blockIdx.x / (tiles_w * tiles_h);
-  const int tr = blockIdx.x - n * tiles_w * tiles_h;
-  const int ho0 = (tr / tiles_w) * ST_TH, wo0 = (tr % tiles_w) * ST_TW;
-  for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias[i];
-  // coalesced patch load: rows of 2*TW+1 consecutive input pixels per channel (zero = conv padding)
-  const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
-  for (int i = threadIdx.x; i < 3 * PH * PW; i += blockDim.x) {
-    const int c = i / (PH * PW), r = (i / PW) % PH, x = i % PW;
-    const int hi = hi0 + r, wi = wi0 + x;
-    sx[i] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? stem_load(in, dtype, ((size_t)(n * 3 + c) * H + hi) * W + wi) : 0.f;
+__global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_constant__ StemArgs a) {
+  extern __shared__ __align__(1024) uint8_t st_smem[];
+  __shared__ __align__(8) uint64_t bars[2];  // a_ready, mma_done
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const uint32_t base = (smem_u32(st_smem) + 1023u) & ~1023u;
+  const uint32_t smA = base;         // 128 rows x 64 B
+  const uint32_t smB = base + 8192;  // Cout rows x 64 B (<= 16 KiB)
+  const uint32_t a_ready = smem_u32(&bars[0]), mma_done = smem_u32(&bars[1]);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid == 0) {
+    mbar_init(a_ready, 128);
+    mbar_init(mma_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // weights -> smem with the SWIZZLE_64B pattern (16-byte piece p of row n lands at p ^ ((n >> 1) & 3))
+  for (int i = tid; i < a.Cout * 4; i += ST_THREADS) {
+    const int n = i >> 2, pc = i & 3;
+    const int4 v = *reinterpret_cast<const int4*>(a.w16 + n * 32 + pc * 8);
+    st_shared_v4(smB + n * 64 + ((pc ^ ((n >> 1) & 3)) << 4), v);
+  }
+  for (int i = tid; i < a.Cout; i += ST_THREADS) s_bias[i] = a.bias[i];
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
   __syncthreads();
-  const int tx = threadIdx.x % ST_TW, ty = threadIdx.x / ST_TW;
-  const int ho = ho0 + ty, wo = wo0 + tx;
-  if (ho >= Ho || wo >= Wo) return;
-  float x[27];
-#pragma unroll
-  for (int kh = 0; kh < 3; kh++)
-#pragma unroll
-    for (int kw = 0; kw < 3; kw++)
-#pragma unroll
-      for (int c = 0; c < 3; c++) x[(kh * 3 + kw) * 3 + c] = sx[(c * PH + 2 * ty + kh) * PW + 2 * tx + kw];
-  __half* o = reinterpret_cast<__half*>(out.base) + ((size_t)(n * Ho + ho) * Wo + wo) * out.pitch + out.coff;
-  for (int c0 = 0; c0 < Cout; c0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = sb[c0 + j];
-#pragma unroll
-    for (int k = 0; k < 27; k++) {
-      // two 16-byte broadcast loads per 8 FMAs (scalar LDS made the kernel LSU-bound)
-      const float4 w0 = *reinterpret_cast<const float4*>(sw + k * Cout + c0);
-      const float4 w1 = *reinterpret_cast<const float4*>(sw + k * Cout + c0 + 4);
-      acc[0] = fmaf(x[k], w0.x, acc[0]); acc[1] = fmaf(x[k], w0.y, acc[1]);
-      acc[2] = fmaf(x[k], w0.z, acc[2]); acc[3] = fmaf(x[k], w0.w, acc[3]);
-      acc[4] = fmaf(x[k], w1.x, acc[4]); acc[5] = fmaf(x[k], w1.y, acc[5]);
-      acc[6] = fmaf(x[k], w1.z, acc[6]); acc[7] = fmaf(x[k], w1.w, acc[7]);
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const int tiles_per_img = a.tiles_w * a.tiles_h;
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(a.Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t hi = 32u | (1u << 14) | (4u << 29);  // SBO = 8 rows x 64 B, version 1, SWIZZLE_64B
+      const uint32_t a_lo = ((smA & 0x3FFFF) >> 4) | (1u << 16), b_lo = ((smB & 0x3FFFF) >> 4) | (1u << 16);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, it++) {
+        mbar_wait(a_ready, it & 1);
+        tc_fence_after();
+        umma_f16(tmem, desc64(a_lo, hi), desc64(b_lo, hi), idesc, 0);
+        umma_f16(tmem, desc64(a_lo + 2, hi), desc64(b_lo + 2, hi), idesc, 1);
+        umma_commit(mma_done);
+      }
     }
-    int4 ov;
-    __half2* oh = reinterpret_cast<__half2*>(&ov);
+  } else {
+    const int tx = tid & (ST_TW - 1), ty = tid / ST_TW;  // output pixel inside the tile
+    // 27 taps of one output pixel -> fp16, k = (kh*3 + kw)*3 + c ; zero outside the image = conv padding
+    auto gather = [&](int tile, __half (&hv)[32]) {
+      const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+      const int ho = (r / a.tiles_w) * ST_TH + ty, wo = (r % a.tiles_w) * ST_TW + tx;
 #pragma unroll
-    for (int j = 0; j < 4; j++) oh[j] = __floats2half2_rn(silu_fast(acc[2 * j]), silu_fast(acc[2 * j + 1]));
-    *reinterpret_cast<int4*>(o + c0) = ov;
+      for (int kh = 0; kh < 3; kh++) {
+        const int hi_ = ho * 2 + kh - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; kw++) {
+          const int wi = wo * 2 + kw - 1;
+          const bool ok = hi_ >= 0 && hi_ < a.H && wi >= 0 && wi < a.W;
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+            hv[(kh * 3 + kw) * 3 + c] =
+                __float2half_rn(ok ? stem_load(a.in, a.dtype, ((size_t)(n * 3 + c) * a.H + hi_) * a.W + wi) : 0.f);
+        }
+      }
+#pragma unroll
+      for (int k = 27; k < 32; k++) hv[k] = __float2half_rn(0.f);
+    };
+    __half hv[32];
+    if (blockIdx.x < a.total_tiles) gather(blockIdx.x, hv);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, it++) {
+      const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
+      const int ho = (r / a.tiles_w) * ST_TH + ty, wo = (r % a.tiles_w) * ST_TW + tx;
+#pragma unroll
+      for (int pc = 0; pc < 4; pc++) {
+        int4 v;
+        __half2* h2 = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; j++) h2[j] = __halves2half2(hv[pc * 8 + 2 * j], hv[pc * 8 + 2 * j + 1]);
+        st_shared_v4(smA + tid * 64 + ((pc ^ ((tid >> 1) & 3)) << 4), v);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+      mbar_arrive(a_ready);
+      if (tile + (int)gridDim.x < a.total_tiles) gather(tile + gridDim.x, hv);  // next tile's loads fly during the MMA
+      mbar_wait(mma_done, it & 1);
+      tc_fence_after();
+      const bool valid = ho < a.Ho && wo < a.Wo;
+      __half* o = a.out + ((size_t)(n * a.Ho + ho) * a.Wo + wo) * a.out_pitch + a.out_coff;
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+      for (int c0 = 0; c0 < a.Cout; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          int4 o0, o1;
+          __half2* p0 = reinterpret_cast<__half2*>(&o0);
+          __half2* p1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            p0[j] = __floats2half2_rn(silu_tanh(__uint_as_float(v[2 * j]) + s_bias[c0 + 2 * j]),
+                                      silu_tanh(__uint_as_float(v[2 * j + 1]) + s_bias[c0 + 2 * j + 1]));
+            p1[j] = __floats2half2_rn(silu_tanh(__uint_as_float(v[8 + 2 * j]) + s_bias[c0 + 8 + 2 * j]),
+                                      silu_tanh(__uint_as_float(v[8 + 2 * j + 1]) + s_bias[c0 + 8 + 2 * j + 1]));
+          }
+          *reinterpret_cast<int4*>(o + c0) = o0;
+          *reinterpret_cast<int4*>(o + c0 + 8) = o1;
+        }
+      }
+      tc_fence_before();  // TMEM reads done before the next tile's MMA overwrites the accumulator
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(a.tmem_cols) : "memory");
   }
 }
 
-int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const float* w, const float* bias,
+int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const __half* w16, const float* bias,
                     const View& out, cudaStream_t s) {
-  if (out.C % 8 || out.coff % 8 || out.pitch % 8) {
-    set_error("stem: output channels must be a multiple of 8");
+  if (out.C % 16 || out.C > 256 || out.coff % 8 || out.pitch % 8) {
+    set_error("stem: output channels must be a multiple of 16 and <= 256");
     return YB_ERR_SHAPE;
   }
-  const int Ho = H / 2, Wo = W / 2;
-  const int tiles = ((Wo + ST_TW - 1) / ST_TW) * ((Ho + ST_TH - 1) / ST_TH);
-  const size_t smem = ((size_t)28 * out.C + 3 * (2 * ST_TH + 1) * (2 * ST_TW + 1)) * sizeof(float);
-  stem_kernel<<<(unsigned)(B * tiles), 256, smem, s>>>(in, in_dtype, B, H, W, out.C, w, bias, out);
+  StemArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = in; a.w16 = w16; a.bias = bias;
+  a.out = reinterpret_cast<__half*>(out.base);
+  a.out_pitch = out.pitch; a.out_coff = out.coff;
+  a.B = B; a.H = H; a.W = W; a.Ho = H / 2; a.Wo = W / 2; a.Cout = out.C;
+  a.dtype = in_dtype;
+  a.tiles_w = (a.Wo + ST_TW - 1) / ST_TW;
+  a.tiles_h = (a.Ho + ST_TH - 1) / ST_TH;
+  a.total_tiles = B * a.tiles_w * a.tiles_h;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)a.Cout) cols <<= 1;
+  a.tmem_cols = cols;
+  static int num_sms = 0;
+  const size_t smem = 1024 + 8192 + 16384;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int per_sm = std::max(1, std::min(4, (int)(512 / cols)));
+  const int grid = std::min(a.total_tiles, num_sms * per_sm);
+  stem_tc_kernel<<<grid, ST_THREADS, smem, s>>>(a);
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -571,6 +571,14 @@ static int finalize_conv(yb_engine* e, OpDesc& op) {
       for (int t = 0; t < taps; t++)
         for (int ci = 0; ci < op.cin; ci++)
           wh[((size_t)o * taps + t) * op.cin + ci] = __float2half_rn(wf[((size_t)o * op.cin + ci) * taps + t]);
+    if (op.cin == 3 && op.k == 3) {
+      // stem: K = 27 padded to 32, k = (kh*3 + kw)*3 + c  (tensor-core stem kernel)
+      wh.assign((size_t)op.cout * 32, __float2half_rn(0.f));
+      for (int o = 0; o < op.cout; o++)
+        for (int t = 0; t < 9; t++)
+          for (int ci = 0; ci < 3; ci++)
+            wh[(size_t)o * 32 + t * 3 + ci] = __float2half_rn(wf[((size_t)o * 3 + ci) * 9 + t]);
+    }
     if (upload(e, wh, &op.w_f16)) return YB_ERR_CUDA;
   }
   return 0;
@@ -625,7 +633,7 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
     switch (op.type) {
       case OP_CONV: {
         if (i == 0 && e->has_stem_tc) {
-          rc = launch_stem_f16(in, in_dtype, B, e->cfg.height, e->cfg.width, op.w_f32, op.bias,
+          rc = launch_stem_f16(in, in_dtype, B, e->cfg.height, e->cfg.width, op.w_f16, op.bias,
                                make_view(e, op.out), s);
           if (rc) return rc;
           input_converted = true;  // the stem reads the caller's NCHW tensor directly
