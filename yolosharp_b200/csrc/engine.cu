@@ -96,6 +96,8 @@ struct yb_engine {
     cudaStream_t stream = nullptr;
   };
   Stage stage[3];
+  cudaEvent_t arena_free = nullptr;  // recorded after each staged forward: the activation arena is shared
+  bool arena_used = false;
   // CUDA graph cache
   struct GraphKey {
     const void* in; int dtype; int B; float* pred; float* proto;
@@ -793,6 +795,7 @@ void yb_destroy(yb_engine* e) {
     if (st.counts) cudaFree(st.counts);
     if (st.stream) cudaStreamDestroy(st.stream);
   }
+  if (e->arena_free) cudaEventDestroy(e->arena_free);
   if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
   for (int l = 1; l < yb_engine::kLanes; l++) {
     if (e->side[l]) cudaStreamDestroy(e->side[l]);
@@ -1004,8 +1007,14 @@ static int32_t predict_enqueue(yb_engine* e, yb_engine::Stage& st, const uint8_t
     st.max_det = max_det;
   }
   YB_CUDA_CHECK(cudaMemcpyAsync(st.in, images_host, img_bytes * batch, cudaMemcpyHostToDevice, s));
+  // one activation arena per engine: forwards of different slots are serialised on the device (their H2D
+  // copies, NMS and D2H copies still overlap the other slot's forward)
+  if (!e->arena_free) YB_CUDA_CHECK(cudaEventCreateWithFlags(&e->arena_free, cudaEventDisableTiming));
+  if (e->arena_used) YB_CUDA_CHECK(cudaStreamWaitEvent(s, e->arena_free, 0));
   int rc = yb_forward(e, st.in, YB_U8, batch, st.pred, nullptr, (void*)s);
   if (rc) return rc;
+  YB_CUDA_CHECK(cudaEventRecord(e->arena_free, s));
+  e->arena_used = true;
   rc = nms_launch(st.pred, batch, e->pred_c, e->A, e->cfg.nc, conf_thres, iou_thres, max_det, 30000, 7680, st.dets,
                   st.counts, nullptr, s);
   if (rc) return rc;
