@@ -171,6 +171,8 @@ int32_t yb_profile_forward(yb_engine* e, const void* in, int32_t in_dtype, int32
 int32_t yb_op_cost(const yb_engine* e, int32_t op_index, int32_t batch, double* flops, double* bytes);
 /* 0 = tcgen05 conv, 1 = CUDA-core conv, 2 = stem, 3 = depthwise, 4 = pool, 5 = upsample, 6 = decode, 7 = other */
 int32_t yb_op_kind(const yb_engine* e, int32_t op_index);
+/* debug: the `skip`-th tcgen05 conv launch from now records a clock64 timeline of CTA 0 into dev_buf (128 x int64) */
+int32_t yb_debug_timeline(long long* dev_buf, int32_t skip);
 
 #ifdef __cplusplus
 }

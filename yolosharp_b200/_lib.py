@@ -49,6 +49,7 @@ SIGNATURES = {
     "yb_profile_forward": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),
     "yb_op_cost": (c_i32, [c_vp, c_i32, c_i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "yb_op_kind": (c_i32, [c_vp, c_i32]),
+    "yb_debug_timeline": (c_i32, [c_vp, c_i32]),
 }
 
 _lib = None

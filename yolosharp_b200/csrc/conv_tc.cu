@@ -59,14 +59,18 @@ struct TcArgs {
   uint32_t row_bytes;             // BK * 2
   uint32_t layout_type;           // UMMA LayoutType: 2 = SW128, 4 = SW64, 6 = SW32
   uint32_t tmem_cols;
+  int n_issuers;                  // 1 or 2 MMA-issuing warps (each with its own half of the rings)
+  int n_acc;                      // TMEM accumulator buffers (2 or 4)
   int total_tiles;
-  uint32_t stage_off;             // byte offset of the epilogue staging tiles (4 warps x 8 KiB)
   int b_resident;                 // all weight slabs stay in smem for the CTA's lifetime
   int ksteps;
   // fused head decode (EpiDecode)
   int epi_mode, dA, dCtot, da0, dch0, dWl, dHW;
   float dstride;
   float* pred;
+  // exact x / d for x*d < 2^40 as (x * ceil(2^40/d)) >> 40 (runtime integer division costs ~100+ cycles)
+  uint64_t m_ntiles, m_tpi, m_tw, m_bw;
+  long long* dbg;  // optional timeline buffer (tools/exp_timeline.py); nullptr in production
 };
 
 struct TcConvPlan {
@@ -79,6 +83,8 @@ struct TcConvPlan {
   int grid;
 };
 
+__device__ __forceinline__ int fdiv(int x, uint64_t magic) { return (int)(((uint64_t)(uint32_t)x * magic) >> 40); }
+
 __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 // x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op instead of two (ex2 + rcp)
 __device__ __forceinline__ float silu_tanh(float v) {
@@ -88,7 +94,9 @@ __device__ __forceinline__ float silu_tanh(float v) {
   return fmaf(h, t, h);
 }
 
-constexpr int TC_THREADS = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int TC_THREADS = 352;  // warp 0 TMA producer, warps 1 and 10 MMA issuers, warps 2..9 epilogue
+constexpr int TC_ISSUERS = 2;
+constexpr int TC_MAX_ACC = 4;
 constexpr int TC_MAX_COUT = 1024;
 constexpr int TC_MAX_STAGES = 12;
 constexpr int HALO_BW = 8, HALO_BH = 16;  // output rectangle of a halo tile (128 rows)
@@ -106,33 +114,22 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
   return d;
 }
 
-// Residual (Bottleneck shortcut) rows of one 32/16-column block, fetched with whole-row coalescing:
-// lane -> (row it*rpi + lane/pieces, 16-byte piece lane%pieces).  Issued BEFORE the accumulator is
-// awaited so the global-load latency overlaps the MMAs.
-__device__ __forceinline__ void res_prefetch(const TcArgs& a, int n0, int cb0, int lane, uint32_t pix_lo,
-                                             uint32_t pix_hi, bool valid, int4 (&rv)[4]) {
+// Residual (Bottleneck shortcut) values of this lane's own row for one 32/16-column block, issued BEFORE
+// the accumulator is awaited so the global-load latency overlaps the MMAs.
+__device__ __forceinline__ void res_prefetch(const TcArgs& a, int n0, int cb0, size_t pix, bool valid, int4 (&rv)[4]) {
   const int wb = min(32, a.n_tile - cb0);
-  const int pieces = wb >> 3, rpi = 32 / pieces;
-  const int my_r = lane / pieces, my_pc = lane - my_r * pieces;
+  const __half* rrow = a.res + pix * a.res_pitch + a.res_coff + n0 + cb0;
 #pragma unroll
-  for (int it = 0; it < 4; it++) {
-    rv[it] = make_int4(0, 0, 0, 0);
-    if (it < pieces) {
-      const int rr = it * rpi + my_r;
-      const uint32_t lo = __shfl_sync(0xffffffffu, pix_lo, rr), hi = __shfl_sync(0xffffffffu, pix_hi, rr);
-      const int vr = __shfl_sync(0xffffffffu, (int)valid, rr);
-      if (vr) {
-        const size_t px = ((size_t)hi << 32) | lo;
-        rv[it] = *reinterpret_cast<const int4*>(a.res + px * a.res_pitch + a.res_coff + n0 + cb0 + my_pc * 8);
-      }
-    }
+  for (int g = 0; g < 4; g++) {
+    rv[g] = make_int4(0, 0, 0, 0);
+    if (valid && g * 8 < wb) rv[g] = *reinterpret_cast<const int4*>(rrow + g * 8);
   }
 }
 
 template <int KK>
 __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32_t smemB, uint32_t tmem_base,
                                          uint32_t fullA, uint32_t emptyA, uint32_t fullB, uint32_t emptyB,
-                                         uint32_t tfull0, uint32_t tempty0, uint32_t bfull) {
+                                         uint32_t tfull0, uint32_t tempty0, uint32_t bfull, int issuer) {
   const uint32_t n_tile = a.n_tile;
   const uint32_t idesc = (1u << 4) | ((n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   // descriptor = lo | hi << 32 :  lo = start>>4 | LBO(1)<<16 ;  hi = SBO | version(1)<<14 | layout<<29
@@ -145,21 +142,37 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
   const bool resident = a.b_resident != 0, halo = a.mode == TC_HALO;
   const int total_tiles = a.total_tiles, gstride = gridDim.x;
   constexpr uint32_t ROW16 = KK * 2;  // bytes per operand row / 16
+  // Two issuer warps take alternate tiles (local tile index li = issuer, issuer+2, ...): one thread tops
+  // out at ~55-80 cycles per tcgen05.mma, two keep the tensor pipe fed for N <= 64.  Each issuer owns its
+  // own half of the A (and B) ring - the producer fills ring (li % n_issuers) for tile li - so every
+  // mbarrier is waited on strictly in phase order by exactly one thread (a parity wait cannot tell
+  // "two phases behind" from "done").
+  const int nb = a.n_acc;                      // TMEM accumulator buffers
+  const int ni = a.n_issuers;
+  if (issuer >= ni) return;
+  const int ra = stages_a / ni, rb = resident ? 0 : stages_b / ni;  // ring depth per issuer
+  const int a_base = issuer * ra, b_base = issuer * rb;
   int sa = 0, sb = 0;
   uint32_t pa = 0, pb = 0;
-  int acc = 0;
-  uint32_t aphase = 0;
   if (resident) mbar_wait(bfull, 0);
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gstride) {
+  for (int li = issuer;; li += ni) {
+    const int tile = blockIdx.x + li * gstride;
+    if (tile >= total_tiles) break;
+    const int dbg_i = li;
+    const int acc = li & (nb - 1);  // nb is 2 or 4
+    const uint32_t aphase = (uint32_t)(li >> (nb == 4 ? 2 : 1)) & 1u;
+    if (a.dbg && blockIdx.x == 0 && dbg_i < 16) a.dbg[dbg_i * 8 + 0] = clock64();
     mbar_wait(tempty0 + 8 * acc, aphase ^ 1);
     tc_fence_after();
+    if (a.dbg && blockIdx.x == 0 && dbg_i < 16) a.dbg[dbg_i * 8 + 1] = clock64();
     const uint32_t d_tmem = tmem_base + acc * n_tile;
     uint32_t accf = 0;
     if (halo) {
       for (int ch = 0; ch < chunks; ch++) {
-        mbar_wait(fullA + 8 * sa, pa);
+        mbar_wait(fullA + 8 * (a_base + sa), pa);
         tc_fence_after();
-        const uint32_t a_lo = a_lo0 + sa * a_stride16;
+        if (a.dbg && blockIdx.x == 0 && dbg_i < 16 && ch == 0) a.dbg[dbg_i * 8 + 2] = clock64();
+        const uint32_t a_lo = a_lo0 + (a_base + sa) * a_stride16;
 #pragma unroll
         for (int t = 0; t < 9; t++) {
           constexpr int W2 = HALO_BW + 2;
@@ -168,9 +181,9 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
           if (resident) {
             b_lo = b_lo0 + (t * chunks + ch) * b_stride16;
           } else {
-            mbar_wait(fullB + 8 * sb, pb);
+            mbar_wait(fullB + 8 * (b_base + sb), pb);
             tc_fence_after();
-            b_lo = b_lo0 + sb * b_stride16;
+            b_lo = b_lo0 + (b_base + sb) * b_stride16;
           }
 #pragma unroll
           for (int k = 0; k < KK; k++) {  // +32 B per K=16 step inside the swizzled row
@@ -178,41 +191,40 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
             accf = 1;
           }
           if (!resident) {
-            umma_commit(emptyB + 8 * sb);
-            if (++sb == stages_b) { sb = 0; pb ^= 1; }
+            umma_commit(emptyB + 8 * (b_base + sb));
+            if (++sb == rb) { sb = 0; pb ^= 1; }
           }
         }
-        umma_commit(emptyA + 8 * sa);  // halo tile free once its 9 taps retired
-        if (++sa == stages_a) { sa = 0; pa ^= 1; }
+        umma_commit(emptyA + 8 * (a_base + sa));  // halo tile free once its 9 taps retired
+        if (++sa == ra) { sa = 0; pa ^= 1; }
       }
     } else {
       for (int ks = 0; ks < ksteps; ks++) {
-        mbar_wait(fullA + 8 * sa, pa);
+        mbar_wait(fullA + 8 * (a_base + sa), pa);
         uint32_t b_lo;
         if (resident) {
           b_lo = b_lo0 + ks * b_stride16;
         } else {
-          mbar_wait(fullB + 8 * sb, pb);
-          b_lo = b_lo0 + sb * b_stride16;
+          mbar_wait(fullB + 8 * (b_base + sb), pb);
+          b_lo = b_lo0 + (b_base + sb) * b_stride16;
         }
         tc_fence_after();
-        const uint32_t a_lo = a_lo0 + sa * a_stride16;
+        const uint32_t a_lo = a_lo0 + (a_base + sa) * a_stride16;
 #pragma unroll
         for (int k = 0; k < KK; k++) {
           umma_f16(d_tmem, desc64(a_lo + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc, accf);
           accf = 1;
         }
-        umma_commit(emptyA + 8 * sa);  // slab free once these MMAs retire
-        if (++sa == stages_a) { sa = 0; pa ^= 1; }
+        umma_commit(emptyA + 8 * (a_base + sa));  // slab free once these MMAs retire
+        if (++sa == ra) { sa = 0; pa ^= 1; }
         if (!resident) {
-          umma_commit(emptyB + 8 * sb);
-          if (++sb == stages_b) { sb = 0; pb ^= 1; }
+          umma_commit(emptyB + 8 * (b_base + sb));
+          if (++sb == rb) { sb = 0; pb ^= 1; }
         }
       }
     }
     umma_commit(tfull0 + 8 * acc);  // accumulator complete
-    acc ^= 1;
-    if (acc == 0) aphase ^= 1;
+    if (a.dbg && blockIdx.x == 0 && dbg_i < 16) a.dbg[dbg_i * 8 + 3] = clock64();
   }
 }
 
@@ -230,7 +242,7 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
-  __shared__ __align__(8) uint64_t bars[4 * TC_MAX_STAGES + 5];
+  __shared__ __align__(8) uint64_t bars[4 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[TC_MAX_COUT];
 
@@ -245,8 +257,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
   const uint32_t fullB = smem_u32(&bars[2 * TC_MAX_STAGES]);
   const uint32_t emptyB = smem_u32(&bars[3 * TC_MAX_STAGES]);
   const uint32_t tfull0 = smem_u32(&bars[4 * TC_MAX_STAGES]);
-  const uint32_t tempty0 = smem_u32(&bars[4 * TC_MAX_STAGES + 2]);
-  const uint32_t bfull = smem_u32(&bars[4 * TC_MAX_STAGES + 4]);
+  const uint32_t tempty0 = smem_u32(&bars[4 * TC_MAX_STAGES + TC_MAX_ACC]);
+  const uint32_t bfull = smem_u32(&bars[4 * TC_MAX_STAGES + 2 * TC_MAX_ACC]);
 
   // PDL: let the next kernel of the stream/graph start its prologue while this grid runs; it blocks in
   // its own griddepcontrol.wait until this grid has completed and flushed.
@@ -261,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
       mbar_init(fullB + 8 * s, 1);
       mbar_init(emptyB + 8 * s, 1);
     }
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < a.n_acc; s++) {
       mbar_init(tfull0 + 8 * s, 1);
       mbar_init(tempty0 + 8 * s, 8);  // one arrive per epilogue warp
     }
@@ -300,59 +312,70 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const int nt = tile % a.n_tiles;
-        const int mt = tile / a.n_tiles;
-        const int img = mt / tiles_per_img;
+      const int ni = a.n_issuers;
+      const int ra = a.stages_a / ni, rb = a.b_resident ? 0 : a.stages_b / ni;
+      int sa_[2] = {0, 0}, sb_[2] = {0, 0};
+      uint32_t pa_[2] = {0, 0}, pb_[2] = {0, 0};
+      int li = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, li++) {
+        const int rg = ni == 2 ? (li & 1) : 0;  // ring (= issuer) of this tile
+        int& sa = sa_[rg]; int& sb = sb_[rg];
+        uint32_t& pa = pa_[rg]; uint32_t& pb = pb_[rg];
+        const int a_base = rg * ra, b_base = rg * rb;
+        const int mt = fdiv(tile, a.m_ntiles);
+        const int nt = tile - mt * a.n_tiles;
+        const int img = fdiv(mt, a.m_tpi);
         const int r = mt - img * tiles_per_img;
-        const int th = r / a.tiles_w, tw = r - th * a.tiles_w;
+        const int th = fdiv(r, a.m_tw), tw = r - th * a.tiles_w;
         const int wbase = tw * a.BW * a.stride - a.pad;
         const int hbase = th * a.BH * a.stride - a.pad;
         if (a.mode == TC_HALO) {
           for (int ch = 0; ch < a.chunks; ch++) {
-            mbar_wait(emptyA + 8 * sa, pa ^ 1);
-            mbar_arrive_expect_tx(fullA + 8 * sa, a.a_bytes);
-            tma_load_4d(smemA + sa * a.a_stride, &a.tmA, fullA + 8 * sa, ch * a.BK, wbase, hbase, img);
-            if (++sa == a.stages_a) { sa = 0; pa ^= 1; }
+            mbar_wait(emptyA + 8 * (a_base + sa), pa ^ 1);
+            mbar_arrive_expect_tx(fullA + 8 * (a_base + sa), a.a_bytes);
+            tma_load_4d(smemA + (a_base + sa) * a.a_stride, &a.tmA, fullA + 8 * (a_base + sa), ch * a.BK, wbase, hbase, img);
+            if (++sa == ra) { sa = 0; pa ^= 1; }
             if (!a.b_resident)
               for (int t = 0; t < taps; t++) {
-                mbar_wait(emptyB + 8 * sb, pb ^ 1);
-                mbar_arrive_expect_tx(fullB + 8 * sb, a.b_bytes);
-                tma_load_2d(smemB + sb * a.b_stride, &a.tmB, fullB + 8 * sb, t * a.Cin + ch * a.BK, nt * a.n_tile);
-                if (++sb == a.stages_b) { sb = 0; pb ^= 1; }
+                mbar_wait(emptyB + 8 * (b_base + sb), pb ^ 1);
+                mbar_arrive_expect_tx(fullB + 8 * (b_base + sb), a.b_bytes);
+                tma_load_2d(smemB + (b_base + sb) * a.b_stride, &a.tmB, fullB + 8 * (b_base + sb), t * a.Cin + ch * a.BK,
+                            nt * a.n_tile);
+                if (++sb == rb) { sb = 0; pb ^= 1; }
               }
           }
         } else {
           for (int t = 0; t < taps; t++) {
-            const int kh = t / a.ksz, kw = t - kh * a.ksz;
+            const int kh = a.ksz == 3 ? (t >= 6 ? 2 : (t >= 3 ? 1 : 0)) : 0, kw = t - kh * a.ksz;
             for (int ch = 0; ch < a.chunks; ch++) {
-              mbar_wait(emptyA + 8 * sa, pa ^ 1);
-              mbar_arrive_expect_tx(fullA + 8 * sa, a.a_bytes);
-              tma_load_4d(smemA + sa * a.a_stride, &a.tmA, fullA + 8 * sa, ch * a.BK, wbase + kw, hbase + kh, img);
-              if (++sa == a.stages_a) { sa = 0; pa ^= 1; }
+              mbar_wait(emptyA + 8 * (a_base + sa), pa ^ 1);
+              mbar_arrive_expect_tx(fullA + 8 * (a_base + sa), a.a_bytes);
+              tma_load_4d(smemA + (a_base + sa) * a.a_stride, &a.tmA, fullA + 8 * (a_base + sa), ch * a.BK, wbase + kw,
+                          hbase + kh, img);
+              if (++sa == ra) { sa = 0; pa ^= 1; }
               if (!a.b_resident) {
-                mbar_wait(emptyB + 8 * sb, pb ^ 1);
-                mbar_arrive_expect_tx(fullB + 8 * sb, a.b_bytes);
-                tma_load_2d(smemB + sb * a.b_stride, &a.tmB, fullB + 8 * sb, t * a.Cin + ch * a.BK, nt * a.n_tile);
-                if (++sb == a.stages_b) { sb = 0; pb ^= 1; }
+                mbar_wait(emptyB + 8 * (b_base + sb), pb ^ 1);
+                mbar_arrive_expect_tx(fullB + 8 * (b_base + sb), a.b_bytes);
+                tma_load_2d(smemB + (b_base + sb) * a.b_stride, &a.tmB, fullB + 8 * (b_base + sb), t * a.Cin + ch * a.BK,
+                            nt * a.n_tile);
+                if (++sb == rb) { sb = 0; pb ^= 1; }
               }
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 10) {
+    // ===================== MMA issuers =====================
     if (lane == 0) {
+      const int issuer = warp == 1 ? 0 : 1;
       switch (a.BK) {
-        case 64: mma_role<4>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull); break;
-        case 32: mma_role<2>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull); break;
-        default: mma_role<1>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull); break;
+        case 64: mma_role<4>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer); break;
+        case 32: mma_role<2>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer); break;
+        default: mma_role<1>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer); break;
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 9) {
     // ===================== epilogue (warps 2..9) =====================
     // Two warps per TMEM lane quarter (hardware rule: a warp reads lanes 32*(warp%4)..+31) split the
     // N columns between them, so every SM sub-partition has two epilogue warps to overlap the
@@ -362,29 +385,31 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     const int q = warp & 3;
     const int half = ew >> 2;
     const int row = q * 32 + lane;
-    const uint32_t stg_out = smem0 + a.stage_off + ew * 4096;  // per-warp 32 x 64 B transpose tiles
-    const uint32_t stg_res = stg_out + 2048;
-    int acc = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-      const int nt = tile % a.n_tiles;
-      const int mt = tile / a.n_tiles;
-      const int img = mt / tiles_per_img;
+    int li = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, li++) {
+      const int acc = li & (a.n_acc - 1);  // n_acc is 2 or 4
+      const uint32_t aphase = (uint32_t)(li >> (a.n_acc == 4 ? 2 : 1)) & 1u;
+      const int mt = fdiv(tile, a.m_ntiles);
+      const int nt = tile - mt * a.n_tiles;
+      const int img = fdiv(mt, a.m_tpi);
       const int r = mt - img * tiles_per_img;
-      const int th = r / a.tiles_w, tw = r - th * a.tiles_w;
-      const int hl = row / a.BW, wl = row - hl * a.BW;
+      const int th = fdiv(r, a.m_tw), tw = r - th * a.tiles_w;
+      const int hl = fdiv(row, a.m_bw), wl = row - hl * a.BW;
       const int ho = th * a.BH + hl, wo = tw * a.BW + wl;
       const bool valid = hl < a.BH && ho < a.Ho && wo < a.Wo;
       const size_t pix = ((size_t)img * a.Ho + ho) * a.Wo + wo;
       const int n0 = nt * a.n_tile;
       const float* bias = s_bias + n0;
-      const uint32_t pix_lo = (uint32_t)pix, pix_hi = (uint32_t)((uint64_t)pix >> 32);
       int4 rv[4];
       const bool use_res = a.epi_mode == EPI_STORE && a.res != nullptr;
-      if (use_res && half * 32 < a.n_tile) res_prefetch(a, n0, half * 32, lane, pix_lo, pix_hi, valid, rv);
+      if (use_res && half * 32 < a.n_tile) res_prefetch(a, n0, half * 32, pix, valid, rv);
 
+      const int dbg_t = li;
+      const bool dbg_on = a.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && dbg_t < 16;
+      if (dbg_on) a.dbg[dbg_t * 8 + 4] = clock64();
       mbar_wait(tfull0 + 8 * acc, aphase);
       tc_fence_after();
+      if (dbg_on) a.dbg[dbg_t * 8 + 5] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * a.n_tile;
       if (a.epi_mode != EPI_STORE) {
         // fused Detect tail (flattened 1x1 conv): this thread's row is pixel `wo` of the whole batch
@@ -433,83 +458,53 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
           }
         }
       } else {
-        // Store path: 32-column blocks alternate between the two warps of a pair.  A lane owns one
-        // output pixel (TMEM lane); rows are transposed through a per-warp smem tile so that a warp
-        // store instruction writes 8 rows x 64 contiguous bytes instead of 32 scattered 16-byte pieces.
+        // Store path: 32-column blocks alternate between the two warps of a pair.  A lane owns one output
+        // pixel (TMEM lane) and writes its own 64 contiguous bytes per block with four 16-byte stores.
+        // (A smem-transposed variant that made every warp store cover whole rows cut L2 requests 8x but
+        // cost ~1000 cycles of shuffles / smem round trips per tile; ncu shows L2 far from saturated,
+        // so the short instruction path wins.)
+        __half* orow = a.out + pix * a.out_pitch + a.out_coff + n0;
         for (int cb0 = half * 32; cb0 < a.n_tile; cb0 += 64) {
           const int wb = min(32, a.n_tile - cb0);  // 32 or 16 channels
-          const int pieces = wb >> 3;              // 16-byte pieces per row (4 or 2)
-          const int rpi = 32 / pieces;             // rows per warp instruction
-          const int pmask = pieces - 1;
-          const int my_r = lane / pieces, my_pc = lane - my_r * pieces;
-          if (use_res) {
+          uint32_t v[32];
+          if (wb == 32) tmem_ld32(taddr + cb0, v); else tmem_ld16(taddr + cb0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_ld_wait();
 #pragma unroll
-            for (int it = 0; it < 4; it++)
-              if (it < pieces) {
-                const int rr = it * rpi + my_r;
-                st_shared_v4(stg_res + (rr * pieces + (my_pc ^ (rr & pmask))) * 16, rv[it]);
+          for (int g = 0; g < 4; g++) {  // 8 channels -> one 16-byte store
+            if (g * 8 < wb) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias + cb0 + g * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias + cb0 + g * 8 + 4);
+              float f[8];
+              f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+              f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+              f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+              f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+              if (a.act == ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) f[j] = silu_tanh(f[j]);
               }
-            __syncwarp();
-            if (cb0 + 64 < a.n_tile) res_prefetch(a, n0, cb0 + 64, lane, pix_lo, pix_hi, valid, rv);  // next block
-          }
-          for (int c0 = cb0; c0 < cb0 + wb; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + c0, v);
-            tmem_ld_wait();
-            float f[16];
+              if (use_res) {
+                const __half2* h = reinterpret_cast<const __half2*>(&rv[g]);
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(bias + c0 + j);
-              f[j] = __uint_as_float(v[j]) + bv.x; f[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
-              f[j + 2] = __uint_as_float(v[j + 2]) + bv.z; f[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
-            }
-            if (a.act == ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 16; j++) f[j] = silu_tanh(f[j]);
-            }
-            const int pc0 = (c0 - cb0) >> 3;
-            if (use_res) {
-              const int4 r0 = ld_shared_v4(stg_res + (lane * pieces + (pc0 ^ (lane & pmask))) * 16);
-              const int4 r1 = ld_shared_v4(stg_res + (lane * pieces + ((pc0 + 1) ^ (lane & pmask))) * 16);
-              const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-              const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                const float2 x = __half22float2(h0[j]), y = __half22float2(h1[j]);
-                f[2 * j] += x.x; f[2 * j + 1] += x.y;
-                f[8 + 2 * j] += y.x; f[8 + 2 * j + 1] += y.y;
+                for (int j = 0; j < 4; j++) {
+                  const float2 x = __half22float2(h[j]);
+                  f[2 * j] += x.x; f[2 * j + 1] += x.y;
+                }
               }
-            }
-            int4 o0, o1;
-            __half2* p0 = reinterpret_cast<__half2*>(&o0);
-            __half2* p1 = reinterpret_cast<__half2*>(&o1);
+              int4 o;
+              __half2* ph = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              p0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-              p1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
-            }
-            st_shared_v4(stg_out + (lane * pieces + (pc0 ^ (lane & pmask))) * 16, o0);
-            st_shared_v4(stg_out + (lane * pieces + ((pc0 + 1) ^ (lane & pmask))) * 16, o1);
-          }
-          __syncwarp();
-          for (int it = 0; it < pieces; it++) {
-            const int rr = it * rpi + my_r;
-            const uint32_t lo = __shfl_sync(0xffffffffu, pix_lo, rr), hi = __shfl_sync(0xffffffffu, pix_hi, rr);
-            const int vr = __shfl_sync(0xffffffffu, (int)valid, rr);
-            const int4 v = ld_shared_v4(stg_out + (rr * pieces + (my_pc ^ (rr & pmask))) * 16);
-            if (vr) {
-              const size_t px = ((size_t)hi << 32) | lo;
-              *reinterpret_cast<int4*>(a.out + px * a.out_pitch + a.out_coff + n0 + cb0 + my_pc * 8) = v;
+              for (int j = 0; j < 4; j++) ph[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+              if (valid) *reinterpret_cast<int4*>(orow + cb0 + g * 8) = o;
             }
           }
-          __syncwarp();
+          if (use_res && cb0 + 64 < a.n_tile) res_prefetch(a, n0, cb0 + 64, pix, valid, rv);  // next block of this warp
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-      acc ^= 1;
-      if (acc == 0) aphase ^= 1;
+      if (dbg_on) a.dbg[dbg_t * 8 + 6] = clock64();
     }
   }
 
@@ -651,15 +646,17 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   // Two CTAs per SM (each <= ~100 KiB smem, <= 256 TMEM columns) double the tiles in flight per SM and
   // hide the producer -> MMA -> epilogue hand-off latencies of the HBM-bound high-resolution layers;
   // layers whose resident weights or wide N tiles do not fit run one CTA per SM with the full budget.
+  // 4 accumulator buffers when they fit in 256 TMEM columns (keeps two CTAs per SM possible), else 2
+  a.n_acc = 4 * a.n_tile <= 256 ? 4 : 2;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * a.n_tile)) cols <<= 1;
+  while (cols < (uint32_t)(a.n_acc * a.n_tile)) cols <<= 1;
   a.tmem_cols = cols;
   const size_t b_all = (size_t)a.ksteps * a.b_stride;
   const int m_tiles = plan->flat ? (p.B * p.Ho * p.Wo + 127) / 128
                                  : p.B * ((p.Wo + a.BW - 1) / a.BW) * ((p.Ho + a.BH - 1) / a.BH);
   plan->occ = 1;
   for (int occ = 2; occ >= 1; occ--) {
-    const size_t budget = occ == 2 ? 72 * 1024 : 200 * 1024 - 32 * 1024;  // rings only (32 KiB epilogue tiles extra)
+    const size_t budget = occ == 2 ? 104 * 1024 : 200 * 1024;  // operand rings
     // layers with <= 2 tiles per CTA gain nothing from deep rings or resident weights; a small footprint
     // lets the NEXT kernel's CTAs (PDL / sibling branches) become resident while this one drains
     const bool small = m_tiles * a.n_tiles <= 2 * 148;
@@ -668,7 +665,7 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     // weight re-fetch per tile
     a.b_resident = (a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= budget) ? 1 : 0;
     // resident weights at one CTA/SM beat re-fetched weights at two CTAs/SM
-    if (occ == 2 && !small && !a.b_resident && a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= 168 * 1024) continue;
+    if (occ == 2 && !small && !a.b_resident && a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= 200 * 1024) continue;
     if (a.b_resident) {
       a.stages_a = (int)std::min<size_t>(a.mode == TC_HALO ? 6 : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
       a.stages_b = 0;
@@ -688,8 +685,13 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     if (fits && (occ == 1 || small || a.stages_a >= 3)) { plan->occ = occ; break; }
     if (occ == 1) a.stages_a = 0;  // reported below
   }
-  a.stage_off = (uint32_t)(plan->smem - 1024);
-  plan->smem += 32 * 1024;
+  // two issuers need >= 2 slabs per half ring
+  a.n_issuers = (a.stages_a >= 4 && (a.b_resident || a.stages_b >= 4)) ? 2 : 1;
+  if (a.n_issuers == 2) {
+    a.stages_a &= ~1;  // even split
+    if (!a.b_resident) a.stages_b &= ~1;
+  }
+  if (a.n_issuers == 1 && a.n_acc > 2) { /* one issuer: two accumulators are enough */ }
   if (a.stages_a < 2 || (!a.b_resident && a.stages_b < 2)) {
     if (err) *err = "tile does not fit in shared memory";
     delete plan;
@@ -725,9 +727,14 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
 
 void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
 
+long long* g_tc_dbg = nullptr;  // set by yb_debug_timeline: next tcgen05 conv launches write their timeline here
+int g_tc_dbg_countdown = -1;
+
 int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s) {
   TcArgs a = plan->args;
   a.pred = pred;
+  a.dbg = nullptr;
+  if (g_tc_dbg && g_tc_dbg_countdown >= 0 && g_tc_dbg_countdown-- == 0) a.dbg = g_tc_dbg;
   const ConvParams& p = plan->p;
   if (plan->flat) {
     a.imgs = 1;
@@ -742,6 +749,8 @@ int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s) {
     a.tiles_h = (p.Ho + a.BH - 1) / a.BH;
   }
   a.total_tiles = a.imgs * a.tiles_w * a.tiles_h * a.n_tiles;
+  auto magic = [](int d) { return (uint64_t)(((((unsigned __int128)1) << 40) + d - 1) / (unsigned)d); };
+  a.m_ntiles = magic(a.n_tiles); a.m_tpi = magic(a.tiles_w * a.tiles_h); a.m_tw = magic(a.tiles_w); a.m_bw = magic(a.BW);
   int grid = std::min(plan->grid, a.total_tiles);
   // concurrent head branches: a latency-bound layer with ~1 tile per CTA gives up half of its CTAs (each
   // then pipelines 2-3 tiles) so that a sibling branch can occupy the other SMs at the same time

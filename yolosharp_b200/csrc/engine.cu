@@ -21,6 +21,9 @@
 
 namespace yb {
 
+extern long long* g_tc_dbg;     // conv_tc.cu (debug timeline)
+extern int g_tc_dbg_countdown;
+
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -1129,6 +1132,14 @@ int32_t yb_op_cost(const yb_engine* e, int32_t i, int32_t batch, double* flops, 
     *bytes = vbytes(op.in) + vbytes(op.cls) + vbytes(op.coef) +
              (double)batch * e->pred_c * e->bufs[op.in.buf].H * e->bufs[op.in.buf].W * 4.0;
   }
+  return YB_OK;
+}
+
+/* debug: the `skip`-th tcgen05 conv launch from now on records a timeline (CTA 0: MMA-issuer and first
+ * epilogue warp clock64 stamps for its first 16 tiles) into dev_buf (128 x int64). */
+int32_t yb_debug_timeline(long long* dev_buf, int32_t skip) {
+  yb::g_tc_dbg = dev_buf;
+  yb::g_tc_dbg_countdown = skip;
   return YB_OK;
 }
 
