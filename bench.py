@@ -33,7 +33,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-MODELS = {"v8n": ("v8", "n", 8.743), "v8s": ("v8", "s", 28.602), "v8x": ("v8", "x", 257.803)}  # GFLOP/img @640^2
+# name -> (arch, size, task, GFLOP per image @640^2: 2*MACs of all convs)
+MODELS = {"v8n": ("v8", "n", "detect", 8.743), "v8s": ("v8", "s", "detect", 28.602), "v8x": ("v8", "x", "detect", 257.803),
+          "v11n": ("v11", "n", "detect", 6.5), "v11s": ("v11", "s", "detect", 21.589),
+          "v8n-seg": ("v8", "n", "segment", 12.6), "v8s-seg": ("v8", "s", "segment", 40.085)}
 CONF, IOU, MAX_DET = 0.25, 0.45, 300
 
 
@@ -101,15 +104,19 @@ def cpu_reference_run(model_key, batch, steps, warmup):
     import torch
     from oracle import ops as oops
     from tests.util import oracle_model, synth_image
-    arch, size, _ = MODELS[model_key]
+    arch, size, task, _ = MODELS[model_key]
     ncpu = os.cpu_count() or 1
-    m = oracle_model(arch, "detect", size)
+    m = oracle_model(arch, task, size)
     x = synth_image(batch, 640, 640)
 
     def step(inp):
         with torch.no_grad():
-            pred = m(inp)[0]["boxes"]
-        oops.non_max_suppression(pred, CONF, IOU)
+            inf = m(inp)[0]
+        out, _ = oops.non_max_suppression(inf["boxes"], CONF, IOU, nc=80)
+        if task == "segment":  # Segmenter.cs:54: masks of the kept detections
+            for i, o in enumerate(out):
+                if o.shape[0]:
+                    oops.process_mask(inf["proto"][i], o[:, 6:], o[:, :4], (640, 640), upsample=True)
 
     best_t, best_n = None, ncpu
     for n in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
@@ -144,8 +151,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    arch, size, gflop_img = MODELS[args.model]
-    workload = f"YOLO{args.model} detect inference (forward+decode+NMS), batch {args.batch}x3x640x640 per GPU, fp16"
+    arch, size, task, gflop_img = MODELS[args.model]
+    workload = (f"YOLO{args.model} {task} inference (forward+decode+NMS" + ("+masks" if task == "segment" else "") +
+                f"), batch {args.batch}x3x640x640 per GPU, fp16")
     config = {"workload": workload, "model": args.model, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
               "imgsz": 640, "conf": CONF, "iou": IOU, "max_det": MAX_DET,
               "parallelism": f"batch-sharded x{world}" + (" + NCCL all-gather of detections" if world > 1 else ""),
@@ -179,8 +187,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    m = oracle_model(arch, "detect", size)  # seeded synthetic weights (weights only; the oracle net is not run here)
-    eng = y.Engine(arch, size, "detect", 80, "f16", local_rank, B, 640, 640)
+    m = oracle_model(arch, task, size)  # seeded synthetic weights (weights only; the oracle net is not run here)
+    eng = y.Engine(arch, size, task, 80, "f16", local_rank, B, 640, 640)
     eng.load_state_dict(m.state_dict())
     eng.finalize()
     del m
@@ -191,22 +199,28 @@ def main():
     # inside the timed region.
     s_f, s_n = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     preds = [torch.empty((B, Cp, A), dtype=torch.float32, device=dev) for _ in range(2)]
-    detb = [(torch.empty((B, MAX_DET, 6), dtype=torch.float32, device=dev),
+    seg = task == "segment"
+    ROW = 6 + (32 if seg else 0)
+    protos = [torch.empty((B, 32, 160, 160), dtype=torch.float32, device=dev) for _ in range(2)] if seg else None
+    mask_buf = [torch.empty((B, MAX_DET, 640, 640), dtype=torch.uint8, device=dev) for _ in range(2)] if seg else None
+    detb = [(torch.empty((B, MAX_DET, ROW), dtype=torch.float32, device=dev),
              torch.empty((B,), dtype=torch.int32, device=dev),
              torch.empty((B, MAX_DET), dtype=torch.int32, device=dev)) for _ in range(2)]
     ev_f = [torch.cuda.Event() for _ in range(2)]
     ev_n = [torch.cuda.Event() for _ in range(2)]
     if world > 1:
-        gath = [(torch.empty((world * B, MAX_DET, 6), dtype=torch.float32, device=dev),
+        gath = [(torch.empty((world * B, MAX_DET, ROW), dtype=torch.float32, device=dev),
                  torch.empty((world * B,), dtype=torch.int32, device=dev)) for _ in range(2)]
 
     def step(i):
         b = i & 1
         s_f.wait_event(ev_n[b])  # pred buffer b is free once NMS of step i-2 has consumed it
-        eng.forward(xs[i % 4], preds[b], stream=s_f)
+        eng.forward(xs[i % 4], preds[b], protos[b] if seg else None, stream=s_f)
         ev_f[b].record(s_f)
         s_n.wait_event(ev_f[b])
         y.nms(preds[b], CONF, IOU, MAX_DET, 80, out=detb[b], stream=s_n)
+        if seg:  # instance masks of the kept detections (Ops.process_mask, upsample=true)
+            y.masks(protos[b], detb[b][0], detb[b][1], 640, 640, stream=s_n, out=mask_buf[b])
         if world > 1:
             with torch.cuda.stream(s_n):
                 ydist.gather_detections(detb[b][0], detb[b][1], gath[b][0], gath[b][1])
@@ -242,28 +256,30 @@ def main():
 
     # ---- e2e: host uint8 images -> host detections through the pipelined C-ABI call pair
     #      yb_predict_u8_submit / yb_predict_u8_wait (two slots: H2D+forward+NMS+D2H of step i+1 overlap step i) ----
-    u8 = [synth_image(B, 640, 640, seed=200 + rank * 8 + i, dtype=torch.uint8).pin_memory() for i in range(2)]
-    dh = [torch.empty((B, MAX_DET, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
-    ch = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
-    e2e_steps = max(6, args.steps // 2)
-    for i in range(6):
-        eng.predict_u8_submit(i & 1, u8[i & 1], dh[i & 1], ch[i & 1], CONF, IOU, MAX_DET)
-        eng.predict_u8_wait(i & 1)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        if i >= 2:
-            eng.predict_u8_wait(i & 1)  # results of step i-2 are in host memory
-        eng.predict_u8_submit(i & 1, u8[i & 1], dh[i & 1], ch[i & 1], CONF, IOU, MAX_DET)
-    eng.predict_u8_wait(0)
-    eng.predict_u8_wait(1)
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * e2e_steps / float(t.item())
+    e2e_val, e2e_steps = None, 0
+    if not seg:  # yb_predict_u8 is the Detector.ImagePredict path (detect engines)
+        u8 = [synth_image(B, 640, 640, seed=200 + rank * 8 + i, dtype=torch.uint8).pin_memory() for i in range(2)]
+        dh = [torch.empty((B, MAX_DET, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+        ch = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        e2e_steps = max(6, args.steps // 2)
+        for i in range(6):
+            eng.predict_u8_submit(i & 1, u8[i & 1], dh[i & 1], ch[i & 1], CONF, IOU, MAX_DET)
+            eng.predict_u8_wait(i & 1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            if i >= 2:
+                eng.predict_u8_wait(i & 1)  # results of step i-2 are in host memory
+            eng.predict_u8_submit(i & 1, u8[i & 1], dh[i & 1], ch[i & 1], CONF, IOU, MAX_DET)
+        eng.predict_u8_wait(0)
+        eng.predict_u8_wait(1)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_val = world * B * e2e_steps / float(t.item())
 
     if rank != 0:
         if world > 1:
@@ -275,6 +291,12 @@ def main():
     prof = None
     for _ in range(3):
         prof = eng.profile(xs[0], pred)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+    if os.path.exists(tpath):  # dram bytes of the same launches from an ncu capture (tools/ncu_traffic.py)
+        tj = json.load(open(tpath))
+        if tj.get("model") == args.model and tj.get("batch") == B:
+            traffic = tj["dram_bytes_per_step"]
     tc = [r for r in prof if r["kind"] == 0]
     tc_ms = sum(r["ms"] for r in tc)
     tc_flops = sum(r["flops"] for r in tc)
@@ -290,7 +312,7 @@ def main():
         ach = tc_flops / (tc_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "achieved": round(ach, 2), "peak": peaks["tc"], "unit": "TFLOP/s",
                 "frac": round(ach / peaks["tc"], 4)}
-    roof.update({"traffic": None, "kernel": "conv_tc_kernel", "launches_per_step": len(tc),
+    roof.update({"traffic": traffic, "kernel": "conv_tc_kernel", "launches_per_step": len(tc),
                  "kernel_ms_per_step": round(tc_ms, 4), "share_of_step": round(tc_ms / all_ms, 3),
                  "algorithmic_gflop_per_step": round(tc_flops / 1e9, 2), "algorithmic_mb_per_step": round(tc_bytes / 1e6, 1),
                  "tensor_tflops": round(tc_flops / (tc_ms / 1e3) / 1e12, 2),
@@ -303,11 +325,11 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": config, "clocks": clocks,
-            "e2e": {"value": round(e2e_val, 1), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 640 * 640,
+            "e2e": {"value": round(e2e_val, 1) if e2e_val else None, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 640 * 640,
                     "d2h_bytes_per_step": B * MAX_DET * 6 * 4 + B * 4, "steps": e2e_steps,
                     "api": "yb_predict_u8_submit/_wait, 2 slots (pinned host uint8 in, host detections out)"},
-            "gpu_launches": (eng.launches_per_forward() + 1) * args.steps,
-            "launches_per_step": eng.launches_per_forward() + 1, "mean_detections_per_image": round(mean_dets, 1),
+            "gpu_launches": (eng.launches_per_forward() + 2 + (1 if seg else 0)) * args.steps,
+            "launches_per_step": eng.launches_per_forward() + 2 + (1 if seg else 0), "mean_detections_per_image": round(mean_dets, 1),
             "roofline": roof}
     if world == 1 and not args.no_cpu_baseline:
         cb_b, cb_steps = 8, 10

@@ -13,9 +13,9 @@ from tests.util import oracle_model, synth_image  # noqa: E402
 
 model = sys.argv[1] if len(sys.argv) > 1 else "v8n"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-arch, size, _ = MODELS[model]
-m = oracle_model(arch, "detect", size)
-e = y.Engine(arch, size, "detect", 80, "f16", 0, B, 640, 640, flags=2)
+arch, size, task, _ = MODELS[model]
+m = oracle_model(arch, task, size)
+e = y.Engine(arch, size, task, 80, "f16", 0, B, 640, 640, flags=2)
 e.load_state_dict(m.state_dict())
 e.finalize()
 x = synth_image(B, 640, 640, dtype=torch.float16).cuda()

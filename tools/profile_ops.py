@@ -15,10 +15,10 @@ from tests.util import oracle_model, synth_image  # noqa: E402
 
 model = sys.argv[1] if len(sys.argv) > 1 else "v8n"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-arch, size, gflop = MODELS[model]
+arch, size, task, gflop = MODELS[model]
 peaks = load_peaks()
-m = oracle_model(arch, "detect", size)
-e = y.Engine(arch, size, "detect", 80, "f16", 0, B, 640, 640)
+m = oracle_model(arch, task, size)
+e = y.Engine(arch, size, task, 80, "f16", 0, B, 640, 640)
 e.load_state_dict(m.state_dict())
 e.finalize()
 x = synth_image(B, 640, 640, dtype=torch.float16).cuda()

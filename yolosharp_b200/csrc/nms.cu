@@ -281,8 +281,16 @@ __global__ void masks_kernel(const float* __restrict__ proto, const float* __res
   const float wr = __fdiv_rn((float)mw, (float)W), hr = __fdiv_rn((float)mh, (float)H);
   const float x1 = __fmul_rn(d[0], wr), x2 = __fmul_rn(d[2], wr);
   const float y1 = __fmul_rn(d[1], hr), y2 = __fmul_rn(d[3], hr);
-  for (int i = threadIdx.x; i < mh * mw; i += blockDim.x) {
-    const int r = i / mw, c = i - r * mw;
+  // crop_mask (Ops.cs:439-447) zeroes everything outside [x1,x2) x [y1,y2): only the box region needs
+  // the coeff . proto dot products (typically a few % of the 160x160 map)
+  for (int i = threadIdx.x; i < mh * mw; i += blockDim.x) mk_smem[i] = 0.f;
+  const int cx0 = max(0, (int)ceilf(x1)), cx1 = min(mw, (int)ceilf(x2));  // c >= x1 && c < x2
+  const int cy0 = max(0, (int)ceilf(y1)), cy1 = min(mh, (int)ceilf(y2));
+  const int bw = max(0, cx1 - cx0), bh = max(0, cy1 - cy0);
+  __syncthreads();
+  for (int j = threadIdx.x; j < bw * bh; j += blockDim.x) {
+    const int r = cy0 + j / bw, c = cx0 + j % bw;
+    const int i = r * mw + c;
     float acc = 0.f;
     for (int k = 0; k < nm; k++) acc = fmaf(d[6 + k], pr[(size_t)k * mh * mw + i], acc);
     const bool inside = ((float)c >= x1) && ((float)c < x2) && ((float)r >= y1) && ((float)r < y2);
@@ -293,17 +301,36 @@ __global__ void masks_kernel(const float* __restrict__ proto, const float* __res
   // scale = in/out
   const float sh = (float)mh / (float)H, sw = (float)mw / (float)W;
   uint8_t* out = masks + ((size_t)b * max_det + det) * H * W;
-  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
-    const int oy = i / W, ox = i - oy * W;
-    float fy = fmaxf(0.f, ((float)oy + 0.5f) * sh - 0.5f);
-    float fx = fmaxf(0.f, ((float)ox + 0.5f) * sw - 0.5f);
+  // 4 consecutive pixels per thread -> one 32-bit store (the output, n x H x W bytes, is the HBM traffic)
+  const int W4 = W >> 2;
+  for (int i = threadIdx.x; i < H * W4; i += blockDim.x) {
+    const int oy = i / W4, ox0 = (i - oy * W4) * 4;
+    const float fy = fmaxf(0.f, ((float)oy + 0.5f) * sh - 0.5f);
+    const int y0 = (int)fy;
+    const int y1i = y0 + (y0 < mh - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, hy = 1.f - ly;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float fx = fmaxf(0.f, ((float)(ox0 + j) + 0.5f) * sw - 0.5f);
+      const int x0 = (int)fx;
+      const int x1i = x0 + (x0 < mw - 1 ? 1 : 0);
+      const float lx = fx - (float)x0, hx = 1.f - lx;
+      const float v = hy * (hx * mk_smem[y0 * mw + x0] + lx * mk_smem[y0 * mw + x1i]) +
+                      ly * (hx * mk_smem[y1i * mw + x0] + lx * mk_smem[y1i * mw + x1i]);
+      packed |= (v > 0.f ? 1u : 0u) << (8 * j);
+    }
+    *reinterpret_cast<uint32_t*>(out + (size_t)oy * W + ox0) = packed;
+  }
+  for (int i = threadIdx.x; i < H * (W & 3); i += blockDim.x) {  // ragged right edge (W % 4 != 0)
+    const int oy = i / (W & 3), ox = (W & ~3) + i % (W & 3);
+    const float fy = fmaxf(0.f, ((float)oy + 0.5f) * sh - 0.5f), fx = fmaxf(0.f, ((float)ox + 0.5f) * sw - 0.5f);
     const int y0 = (int)fy, x0 = (int)fx;
     const int y1i = y0 + (y0 < mh - 1 ? 1 : 0), x1i = x0 + (x0 < mw - 1 ? 1 : 0);
-    const float ly = fy - (float)y0, lx = fx - (float)x0;
-    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
     const float v = hy * (hx * mk_smem[y0 * mw + x0] + lx * mk_smem[y0 * mw + x1i]) +
                     ly * (hx * mk_smem[y1i * mw + x0] + lx * mk_smem[y1i * mw + x1i]);
-    out[i] = v > 0.f ? 1 : 0;
+    out[(size_t)oy * W + ox] = v > 0.f ? 1 : 0;
   }
 }
 

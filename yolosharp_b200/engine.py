@@ -171,11 +171,12 @@ def nms(pred, conf_thres=0.25, iou_thres=0.45, max_det=300, nc=0, max_nms=30000,
     return dets, counts, keep
 
 
-def masks(proto, dets, counts, height, width, stream=None):
+def masks(proto, dets, counts, height, width, stream=None, out=None):
     """yb_masks: proto (B,32,mh,mw) f32, dets (B,max_det,38), counts -> uint8 (B,max_det,H,W)."""
     B, nm, mh, mw = proto.shape
     max_det = dets.shape[1]
-    out = torch.zeros((B, max_det, height, width), dtype=torch.uint8, device=proto.device)
+    if out is None:
+        out = torch.zeros((B, max_det, height, width), dtype=torch.uint8, device=proto.device)
     L.check(L.lib().yb_masks(C.c_void_p(proto.data_ptr()), C.c_void_p(dets.data_ptr()), C.c_void_p(counts.data_ptr()), B,
                              max_det, nm, mh, mw, height, width, C.c_void_p(out.data_ptr()), _stream_ptr(stream)))
     return out
