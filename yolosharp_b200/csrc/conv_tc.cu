@@ -60,6 +60,7 @@ struct TcArgs {
   uint32_t layout_type;           // UMMA LayoutType: 2 = SW128, 4 = SW64, 6 = SW32
   uint32_t tmem_cols;
   int n_issuers;                  // 1 or 2 MMA-issuing warps (each with its own half of the rings)
+  int n_groups;                   // epilogue groups of 4 warps (2 or 4)
   int n_acc;                      // TMEM accumulator buffers (2 or 4)
   int total_tiles;
   int b_resident;                 // all weight slabs stay in smem for the CTA's lifetime
@@ -78,6 +79,7 @@ struct TcConvPlan {
   ConvParams p;
   bool flat;   // 1x1 stride-1 conv on the flattened pixel dimension
   int occ;     // CTAs per SM this plan is sized for
+  int threads; // 3 role warps + 4 warps per epilogue group
   bool small;  // <= 2 tiles per CTA
   size_t smem;
   int grid;
@@ -94,7 +96,8 @@ __device__ __forceinline__ float silu_tanh(float v) {
   return fmaf(h, t, h);
 }
 
-constexpr int TC_THREADS = 352;  // warp 0 TMA producer, warps 1 and 10 MMA issuers, warps 2..9 epilogue
+constexpr int TC_MAX_THREADS = 608;  // warp 0 TMA producer, warps 1-2 MMA issuers, warps 3.. epilogue groups of 4 warps
+constexpr int TC_MAX_GROUPS = 4;
 constexpr int TC_ISSUERS = 2;
 constexpr int TC_MAX_ACC = 4;
 constexpr int TC_MAX_COUT = 1024;
@@ -240,14 +243,15 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
 //                       request rate (~30 requests/clk chip-wide), not by bytes.
 //   B ring  : one [n_tile x BK] weight slab per (tap, channel slab), or all slabs resident.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__(704, 1) conv_tc_kernel(  // 704 = 2 x 352: caps registers at 93 so two 352-thread CTAs fit an SM
+const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   __shared__ __align__(8) uint64_t bars[4 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[TC_MAX_COUT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < a.n_tile * a.n_tiles; i += TC_THREADS) s_bias[i] = a.bias[i];  // constant data
+  for (int i = threadIdx.x; i < a.n_tile * a.n_tiles; i += blockDim.x) s_bias[i] = a.bias[i];  // constant data
   // dynamic smem base rounded up to 1 KiB (SWIZZLE_128B atoms need it)
   const uint32_t smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
   const uint32_t smemA = smem0;
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     }
     for (int s = 0; s < a.n_acc; s++) {
       mbar_init(tfull0 + 8 * s, 1);
-      mbar_init(tempty0 + 8 * s, 8);  // one arrive per epilogue warp
+      mbar_init(tempty0 + 8 * s, 4);  // one arrive per warp of the draining epilogue group
     }
     mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -365,28 +369,31 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1 || warp == 10) {
+  } else if (warp == 1 || warp == 2) {
     // ===================== MMA issuers =====================
     if (lane == 0) {
-      const int issuer = warp == 1 ? 0 : 1;
+      const int issuer = warp - 1;
       switch (a.BK) {
         case 64: mma_role<4>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer); break;
         case 32: mma_role<2>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer); break;
         default: mma_role<1>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer); break;
       }
     }
-  } else if (warp >= 2 && warp <= 9) {
-    // ===================== epilogue (warps 2..9) =====================
-    // Two warps per TMEM lane quarter (hardware rule: a warp reads lanes 32*(warp%4)..+31) split the
-    // N columns between them, so every SM sub-partition has two epilogue warps to overlap the
-    // tcgen05.ld / MUFU / store latencies (ncu: with one warp per sub-partition the epilogue ran at
-    // ~0.2 IPC and paced the whole kernel).
-    const int ew = warp - 2;
+  } else {
+    // ===================== epilogue (warps 3 ..) =====================
+    // G groups of four warps (one warp per TMEM lane quarter: a warp may only read lanes
+    // 32*(warp%4)..+31; any four consecutive warps cover all quarters) drain different tiles: group g
+    // takes local tiles g, g+G, ...  The per-tile epilogue is a latency-bound ~2000-4000 cycle chain
+    // (tcgen05.ld -> bias -> SiLU -> pack -> store), so its THROUGHPUT comes from having several tiles in
+    // their epilogue at once (timeline: one tile at a time paced the whole kernel for N <= 64).
+    const int ew = warp - 3;
     const int q = warp & 3;
-    const int half = ew >> 2;
+    const int grp = ew >> 2;
+    const int G = a.n_groups;
     const int row = q * 32 + lane;
-    int li = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, li++) {
+    for (int li = grp;; li += G) {
+      const int tile = blockIdx.x + li * gridDim.x;
+      if (tile >= a.total_tiles) break;
       const int acc = li & (a.n_acc - 1);  // n_acc is 2 or 4
       const uint32_t aphase = (uint32_t)(li >> (a.n_acc == 4 ? 2 : 1)) & 1u;
       const int mt = fdiv(tile, a.m_ntiles);
@@ -402,10 +409,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
       const float* bias = s_bias + n0;
       int4 rv[4];
       const bool use_res = a.epi_mode == EPI_STORE && a.res != nullptr;
-      if (use_res && half * 32 < a.n_tile) res_prefetch(a, n0, half * 32, pix, valid, rv);
+      if (use_res) res_prefetch(a, n0, 0, pix, valid, rv);
 
       const int dbg_t = li;
-      const bool dbg_on = a.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && dbg_t < 16;
+      const bool dbg_on = a.dbg && blockIdx.x == 0 && (warp & 3) == 3 && lane == 0 && dbg_t < 16;
       if (dbg_on) a.dbg[dbg_t * 8 + 4] = clock64();
       mbar_wait(tfull0 + 8 * acc, aphase);
       tc_fence_after();
@@ -418,12 +425,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
         float* po = a.pred + (size_t)n * a.dCtot * a.dA + a.da0 + i;
         if (a.epi_mode == EPI_DFL_BOX) {
           // DFL (Block.cs:44): softmax over the 16 bins of each side, expectation with weights 0..15;
-          // then dist2bbox(xywh) * stride (Tal.cs:338-356, Head.cs:221).  half 0 owns the x sides
-          // (left/right -> cx, w), half 1 the y sides (top/bottom -> cy, h).
-          float d[2];
+          // then dist2bbox(xywh) * stride (Tal.cs:338-356, Head.cs:221)
+          float d[4];
 #pragma unroll
-          for (int s2 = 0; s2 < 2; s2++) {
-            const int sd = half + 2 * s2;
+          for (int sd = 0; sd < 4; sd++) {
             uint32_t v[16];
             tmem_ld16(taddr + sd * 16, v);
             tmem_ld_wait();
@@ -433,17 +438,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
             float sum = 0.f, ex = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; j++) { const float e = __expf(f[j] - mx); sum += e; ex = fmaf(e, (float)j, ex); }
-            d[s2] = __fdividef(ex, sum);
+            d[sd] = __fdividef(ex, sum);
           }
           if (valid) {
             const int y = i / a.dWl, x = i - y * a.dWl;
-            const float ac = (half == 0 ? (float)x : (float)y) + 0.5f;
-            const float lo = ac - d[0], hi = ac + d[1];
-            po[(size_t)half * a.dA] = (lo + hi) * 0.5f * a.dstride;
-            po[(size_t)(2 + half) * a.dA] = (hi - lo) * a.dstride;
+            const float ax = (float)x + 0.5f, ay = (float)y + 0.5f;
+            const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+            po[0] = (x1 + x2) * 0.5f * a.dstride;
+            po[(size_t)a.dA] = (y1 + y2) * 0.5f * a.dstride;
+            po[(size_t)2 * a.dA] = (x2 - x1) * a.dstride;
+            po[(size_t)3 * a.dA] = (y2 - y1) * a.dstride;
           }
         } else {
-          for (int c0 = half * 16; c0 < a.n_tile; c0 += 32) {
+          for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
@@ -458,13 +465,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
           }
         }
       } else {
-        // Store path: 32-column blocks alternate between the two warps of a pair.  A lane owns one output
-        // pixel (TMEM lane) and writes its own 64 contiguous bytes per block with four 16-byte stores.
+        // Store path, 32 columns at a time.  A lane owns one output pixel (TMEM lane) and writes its own
+        // 64 contiguous bytes per block with four 16-byte stores.
         // (A smem-transposed variant that made every warp store cover whole rows cut L2 requests 8x but
         // cost ~1000 cycles of shuffles / smem round trips per tile; ncu shows L2 far from saturated,
         // so the short instruction path wins.)
         __half* orow = a.out + pix * a.out_pitch + a.out_coff + n0;
-        for (int cb0 = half * 32; cb0 < a.n_tile; cb0 += 64) {
+        for (int cb0 = 0; cb0 < a.n_tile; cb0 += 32) {
           const int wb = min(32, a.n_tile - cb0);  // 32 or 16 channels
           uint32_t v[32];
           if (wb == 32) tmem_ld32(taddr + cb0, v); else tmem_ld16(taddr + cb0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
@@ -498,7 +505,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
               if (valid) *reinterpret_cast<int4*>(orow + cb0 + g * 8) = o;
             }
           }
-          if (use_res && cb0 + 64 < a.n_tile) res_prefetch(a, n0, cb0 + 64, pix, valid, rv);  // next block of this warp
+          if (use_res && cb0 + 32 < a.n_tile) res_prefetch(a, n0, cb0 + 32, pix, valid, rv);  // next block
         }
       }
       tc_fence_before();
@@ -685,6 +692,9 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     if (fits && (occ == 1 || small || a.stages_a >= 3)) { plan->occ = occ; break; }
     if (occ == 1) a.stages_a = 0;  // reported below
   }
+  // epilogue groups: one per accumulator buffer at one CTA/SM (608 threads); two when two CTAs share the SM
+  a.n_groups = (plan->occ == 1 && a.n_acc == 4) ? 4 : 2;
+  plan->threads = 96 + 128 * a.n_groups;
   // two issuers need >= 2 slabs per half ring
   a.n_issuers = (a.stages_a >= 4 && (a.b_resident || a.stages_b >= 4)) ? 2 : 1;
   if (a.n_issuers == 2) {
@@ -758,7 +768,7 @@ int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s) {
     grid = std::max(1, std::min(grid, (a.total_tiles + 2) / 3));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(plan->threads);
   cfg.dynamicSmemBytes = plan->smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
