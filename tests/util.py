@@ -97,6 +97,13 @@ def expected_for_op(model, acts, op_name):
         return acts.get(op_name[:-len(".ffn.1")])
     if op_name.endswith(".upsample.shuffle"):
         return acts.get(op_name[:-len(".shuffle")])
+    if "+" in op_name:  # merged first convs of the Detect branches: outputs concatenated along channels
+        first = op_name.split("+")[0]
+        prefix = first[:first.rfind(".cv")]
+        names = [first] + [prefix + "." + p for p in op_name.split("+")[1:]]
+        if all(n in acts for n in names):
+            return torch.cat([acts[n] for n in names], 1)
+        return None
     if op_name not in acts:
         return None
     t = acts[op_name]

@@ -57,6 +57,10 @@ struct OpDesc {
   float* bias = nullptr;
   TcConvPlan* plan = nullptr;
   bool use_tc = false;
+  std::vector<std::string> parts;  // merged conv: reference names whose output channels are concatenated
+  std::vector<int> part_cout;
+  int fork_id = -1;    // after this op: record ev_fork[fork_id] (sibling lanes wait for it)
+  int wait_fork = -1;  // lane start waits for ev_fork[wait_fork] instead of the level's feature event
   int lane = 0;        // 0 = main stream; >0 = independent head branch that may run concurrently
   int lane_level = -1; // pyramid level whose feature map a side lane waits for
   int feat_level = -1; // this op completes feats[feat_level] (fork point for the head lanes)
@@ -115,7 +119,7 @@ struct yb_engine {
   // concurrent head branches (box / cls / mask-coefficient chains of the three levels + Proto)
   static const int kLanes = 13;
   cudaStream_t side[kLanes] = {};
-  cudaEvent_t ev_feat[3] = {}, ev_done[kLanes] = {};
+  cudaEvent_t ev_feat[3] = {}, ev_done[kLanes] = {}, ev_fork[3] = {};
   bool lanes_ok = false;
 };
 
@@ -150,6 +154,23 @@ struct Builder {
       e->expected.push_back(name + ".weight");
       e->expected.push_back(name + ".bias");
     }
+  }
+
+  // Several Conv modules that read the SAME input (the first convs of the Detect branches, Head.cs:47-49)
+  // as one conv whose output channels are the concatenation of theirs: one pass over the input and a
+  // wider N per tcgen05.mma (N = 144 instead of 64 and 80).
+  void conv_merged(const std::vector<std::string>& names, const std::vector<int>& couts, VRef in, VRef out, int k, int s) {
+    OpDesc op;
+    op.type = OP_CONV;
+    op.name = names[0];
+    for (size_t i = 1; i < names.size(); i++) op.name += "+" + names[i].substr(names[i].rfind(".cv") + 1);
+    op.in = in; op.out = out;
+    op.k = k; op.s = s; op.act = ACT_SILU; op.cin = in.C; op.cout = out.C; op.bn = true;
+    op.parts = names; op.part_cout = couts;
+    e->ops.push_back(op);
+    for (const auto& n : names)
+      for (const char* sfx : {".conv.weight", ".bn.weight", ".bn.bias", ".bn.running_mean", ".bn.running_var"})
+        e->expected.push_back(n + sfx);
   }
 
   // Block.Bottleneck (Block.cs:572-607)
@@ -428,17 +449,32 @@ static int build_graph(yb_engine* e) {
     const int hl = H / strides[l], wl = W / strides[l];
     const std::string L = std::to_string(l);
     size_t mark = e->ops.size();
-    VRef t1 = b.new_buf(hl, wl, c2), t2 = b.new_buf(hl, wl, c2), box = b.new_buf(hl, wl, 4 * rm);
-    b.conv(hn + ".cv2." + L + ".0", feats[l], t1, 3, 1);
+    const bool merge = !v11;  // legacy head: cv2[l][0], cv3[l][0] (and cv4[l][0]) are 3x3 Convs of the same input
+    VRef t1, u1, m1;
+    if (merge) {
+      std::vector<std::string> names = {hn + ".cv2." + L + ".0", hn + ".cv3." + L + ".0"};
+      std::vector<int> couts = {c2, c3};
+      if (seg) { names.push_back(hn + ".cv4." + L + ".0"); couts.push_back(c4); }
+      VRef first = b.new_buf(hl, wl, c2 + c3 + (seg ? c4 : 0));
+      b.conv_merged(names, couts, feats[l], first, 3, 1);
+      e->ops.back().fork_id = l;
+      t1 = Builder::slice(first, 0, c2);
+      u1 = Builder::slice(first, c2, c3);
+      if (seg) m1 = Builder::slice(first, c2 + c3, c4);
+    } else {
+      t1 = b.new_buf(hl, wl, c2);
+      b.conv(hn + ".cv2." + L + ".0", feats[l], t1, 3, 1);
+    }
+    VRef t2 = b.new_buf(hl, wl, c2), box = b.new_buf(hl, wl, 4 * rm);
     b.conv(hn + ".cv2." + L + ".1", t1, t2, 3, 1);
     b.conv(hn + ".cv2." + L + ".2", t2, box, 1, 1, ACT_NONE, false);
     tag_lane(mark, 1 + 3 * l, l);
     mark = e->ops.size();
-    VRef u1 = b.new_buf(hl, wl, c3), u2 = b.new_buf(hl, wl, c3), cls = b.new_buf(hl, wl, nc);
-    if (!v11) {  // legacy cls branch: two 3x3 Convs (Head.cs:49)
-      b.conv(hn + ".cv3." + L + ".0", feats[l], u1, 3, 1);
+    VRef u2 = b.new_buf(hl, wl, c3), cls = b.new_buf(hl, wl, nc);
+    if (!v11) {  // legacy cls branch: two 3x3 Convs (Head.cs:49); the first one is part of the merged conv
       b.conv(hn + ".cv3." + L + ".1", u1, u2, 3, 1);
     } else {     // Head.cs:50: [DW3x3(x) + Conv1x1(x->c3)] . [DW3x3(c3) + Conv1x1(c3->c3)]
+      u1 = b.new_buf(hl, wl, c3);
       VRef d1 = b.new_buf(hl, wl, feats[l].C), d2 = b.new_buf(hl, wl, c3);
       b.dwconv(hn + ".cv3." + L + ".0.0", feats[l], d1);
       b.conv(hn + ".cv3." + L + ".0.1", d1, u1, 1, 1);
@@ -447,15 +483,20 @@ static int build_graph(yb_engine* e) {
     }
     b.conv(hn + ".cv3." + L + ".2", u2, cls, 1, 1, ACT_NONE, false);
     tag_lane(mark, 2 + 3 * l, l);
+    if (merge) for (size_t i = mark; i < e->ops.size(); i++) e->ops[i].wait_fork = l;
     mark = e->ops.size();
     VRef coef;
     if (seg) {
-      VRef m1 = b.new_buf(hl, wl, c4), m2 = b.new_buf(hl, wl, c4);
+      VRef m2 = b.new_buf(hl, wl, c4);
       coef = b.new_buf(hl, wl, nm);
-      b.conv(hn + ".cv4." + L + ".0", feats[l], m1, 3, 1);
+      if (!merge) {
+        m1 = b.new_buf(hl, wl, c4);
+        b.conv(hn + ".cv4." + L + ".0", feats[l], m1, 3, 1);
+      }
       b.conv(hn + ".cv4." + L + ".1", m1, m2, 3, 1);
       b.conv(hn + ".cv4." + L + ".2", m2, coef, 1, 1, ACT_NONE, false);
       tag_lane(mark, 3 + 3 * l, l);
+      if (merge) for (size_t i = mark; i < e->ops.size(); i++) e->ops[i].wait_fork = l;
     }
     OpDesc op;
     op.type = OP_DECODE;
@@ -496,6 +537,26 @@ static int upload(yb_engine* e, const std::vector<T>& h, T** dptr) {
 }
 
 static int finalize_conv(yb_engine* e, OpDesc& op) {
+  if (!op.parts.empty() && e->host.find(op.name + ".conv.weight") == e->host.end()) {
+    // merged conv: synthesise concatenated tensors under the merged name, then fold as usual
+    HostTensor W, g, bt, mu, var;
+    for (const auto& n : op.parts) {
+      const HostTensor *w1 = find_tensor(e, n + ".conv.weight"), *g1 = find_tensor(e, n + ".bn.weight"),
+                       *b1 = find_tensor(e, n + ".bn.bias"), *m1 = find_tensor(e, n + ".bn.running_mean"),
+                       *v1 = find_tensor(e, n + ".bn.running_var");
+      if (!w1 || !g1 || !b1 || !m1 || !v1) return YB_ERR_MISSING_WEIGHT;
+      W.data.insert(W.data.end(), w1->data.begin(), w1->data.end());
+      g.data.insert(g.data.end(), g1->data.begin(), g1->data.end());
+      bt.data.insert(bt.data.end(), b1->data.begin(), b1->data.end());
+      mu.data.insert(mu.data.end(), m1->data.begin(), m1->data.end());
+      var.data.insert(var.data.end(), v1->data.begin(), v1->data.end());
+    }
+    e->host[op.name + ".conv.weight"] = W;
+    e->host[op.name + ".bn.weight"] = g;
+    e->host[op.name + ".bn.bias"] = bt;
+    e->host[op.name + ".bn.running_mean"] = mu;
+    e->host[op.name + ".bn.running_var"] = var;
+  }
   const bool f16 = e->cfg.precision == YB_PREC_F16;
   const int taps = op.k * op.k;
   const int cing = op.cin / op.groups;  // input channels per group
@@ -630,7 +691,7 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
     if (lanes && op.lane > 0) {
       s = e->side[op.lane];
       if (!lane_started[op.lane]) {
-        YB_CUDA_CHECK(cudaStreamWaitEvent(s, e->ev_feat[op.lane_level], 0));
+        YB_CUDA_CHECK(cudaStreamWaitEvent(s, op.wait_fork >= 0 ? e->ev_fork[op.wait_fork] : e->ev_feat[op.lane_level], 0));
         lane_started[op.lane] = true;
       }
     }
@@ -698,6 +759,7 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
         return YB_ERR_NOT_IMPLEMENTED;
     }
     if (lanes && op.feat_level >= 0) YB_CUDA_CHECK(cudaEventRecord(e->ev_feat[op.feat_level], main_s));
+    if (lanes && op.fork_id >= 0) YB_CUDA_CHECK(cudaEventRecord(e->ev_fork[op.fork_id], s));
   }
   s = main_s;
   if (lanes)
@@ -778,7 +840,10 @@ int32_t yb_create(const yb_config* cfg, yb_engine** out) {
     YB_CUDA_CHECK(cudaStreamCreateWithFlags(&e->side[l], cudaStreamNonBlocking));
     YB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done[l], cudaEventDisableTiming));
   }
-  for (int l = 0; l < 3; l++) YB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_feat[l], cudaEventDisableTiming));
+  for (int l = 0; l < 3; l++) {
+    YB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_feat[l], cudaEventDisableTiming));
+    YB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork[l], cudaEventDisableTiming));
+  }
   *out = e.release();
   return YB_OK;
 }
@@ -804,8 +869,10 @@ void yb_destroy(yb_engine* e) {
     if (e->side[l]) cudaStreamDestroy(e->side[l]);
     if (e->ev_done[l]) cudaEventDestroy(e->ev_done[l]);
   }
-  for (int l = 0; l < 3; l++)
+  for (int l = 0; l < 3; l++) {
     if (e->ev_feat[l]) cudaEventDestroy(e->ev_feat[l]);
+    if (e->ev_fork[l]) cudaEventDestroy(e->ev_fork[l]);
+  }
   delete e;
 }
 
