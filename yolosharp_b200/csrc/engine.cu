@@ -638,12 +638,13 @@ static int finalize_conv(yb_engine* e, OpDesc& op) {
         for (int ci = 0; ci < op.cin; ci++)
           wh[((size_t)o * taps + t) * op.cin + ci] = __float2half_rn(wf[((size_t)o * op.cin + ci) * taps + t]);
     if (op.cin == 3 && op.k == 3) {
-      // stem: K = 27 padded to 32, k = (kh*3 + kw)*3 + c  (tensor-core stem kernel)
-      wh.assign((size_t)op.cout * 32, __float2half_rn(0.f));
+      // stem: k = (kh*3 + c)*4 + kw + 1, K = 36 padded to 64 (see stem_tc_kernel)
+      wh.assign((size_t)op.cout * 64, __float2half_rn(0.f));
       for (int o = 0; o < op.cout; o++)
-        for (int t = 0; t < 9; t++)
+        for (int kh = 0; kh < 3; kh++)
           for (int ci = 0; ci < 3; ci++)
-            wh[(size_t)o * 32 + t * 3 + ci] = __float2half_rn(wf[((size_t)o * 3 + ci) * 9 + t]);
+            for (int kw = 0; kw < 3; kw++)
+              wh[(size_t)o * 64 + (kh * 3 + ci) * 4 + kw + 1] = __float2half_rn(wf[((size_t)o * 3 + ci) * 9 + kh * 3 + kw]);
     }
     if (upload(e, wh, &op.w_f16)) return YB_ERR_CUDA;
   }

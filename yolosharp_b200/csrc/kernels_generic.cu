@@ -4,6 +4,8 @@
 // plus the HBM-bound glue ops used by both modes (SPPF pool, upsample, decode, layout).
 // Reference ops restated: Modules/Convs.cs:36-56 (Conv), Block.cs:236-282 (SPPF),
 // Head.cs:204-223 + Block.cs:15-45 + Utils/Tal.cs:313-356 (decode).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace yb {
@@ -232,9 +234,75 @@ __global__ void __launch_bounds__(256) sppf_pool_kernel(View in, View o5, View o
   }
 }
 
+// fp16 fast path: one CTA per (image, 8-channel chunk); a thread owns whole pixels as one 16-byte vector
+// (4 x half2), separable 5x5 max = row pass + column pass through two smem planes, three cascaded pools.
+__device__ __forceinline__ int4 hmax8(const int4& x, const int4& y) {
+  int4 r;
+  const __half2* a = reinterpret_cast<const __half2*>(&x);
+  const __half2* b = reinterpret_cast<const __half2*>(&y);
+  __half2* o = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; j++) o[j] = __hmax2(a[j], b[j]);
+  return r;
+}
+
+__global__ void __launch_bounds__(512) sppf_pool_h8_kernel(View in, View o5, View o9, View o13) {
+  extern __shared__ __align__(16) int4 sp8[];
+  const int H = in.H, W = in.W, HW = H * W;
+  int4* cur = sp8;
+  int4* tmp = sp8 + HW;
+  const int n = blockIdx.y, c0 = blockIdx.x * 8;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const __half* src = reinterpret_cast<const __half*>(in.base) + (size_t)n * HW * in.pitch + in.coff + c0;
+  for (int p = threadIdx.x; p < HW; p += blockDim.x) cur[p] = *reinterpret_cast<const int4*>(src + (size_t)p * in.pitch);
+  __syncthreads();
+#pragma unroll
+  for (int pass = 0; pass < 3; pass++) {
+    const View& ov = pass == 0 ? o5 : (pass == 1 ? o9 : o13);
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+      const int h = p / W, w = p - h * W;
+      int4 m = cur[p];
+#pragma unroll
+      for (int d = -2; d <= 2; d++)
+        if (d != 0 && w + d >= 0 && w + d < W) m = hmax8(m, cur[p + d]);
+      tmp[p] = m;
+    }
+    __syncthreads();
+    __half* dst = reinterpret_cast<__half*>(ov.base) + (size_t)n * HW * ov.pitch + ov.coff + c0;
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+      const int h = p / W;
+      int4 m = tmp[p];
+#pragma unroll
+      for (int d = -2; d <= 2; d++)
+        if (d != 0 && h + d >= 0 && h + d < H) m = hmax8(m, tmp[p + d * W]);
+      cur[p] = m;  // safe: the column pass reads tmp only
+      *reinterpret_cast<int4*>(dst + (size_t)p * ov.pitch) = m;
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T>
 int launch_sppf_pool(const View& in, const View& o5, const View& o9, const View& o13, int B,
                      cudaStream_t s) {
+  if (sizeof(T) == 2 && in.C % 8 == 0 && in.coff % 8 == 0 && in.pitch % 8 == 0 && o5.coff % 8 == 0 && o5.pitch % 8 == 0 &&
+      o9.coff % 8 == 0 && o13.coff % 8 == 0 && (size_t)2 * in.H * in.W * 16 <= 48 * 1024) {
+    const int HW = in.H * in.W;
+    const int threads = std::min(512, (HW + 31) / 32 * 32);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(in.C / 8, B);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = (size_t)2 * HW * 16;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    YB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sppf_pool_h8_kernel, in, o5, o9, o13));
+    return 0;
+  }
   const size_t smem = (size_t)3 * in.H * in.W * SP_CC * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("sppf_pool: feature map too large for the shared-memory kernel");

@@ -11,25 +11,41 @@
 //   2. bitonic sort    : ascending key == score descending, anchor index ascending on ties
 //                        (torchvision sorts scores with a stable descending sort); truncate to
 //                        max_nms (Ops.cs:338-342)
-//   3. greedy suppress : boxes offset by cls*max_wh in fp32 (Ops.cs:345,356); candidates are
-//                        consumed in chunks of 32: a 32x32 IoU bit-matrix inside the chunk plus a
-//                        check against the kept list, then a 32-step serial resolve.  Stops at
-//                        max_det kept boxes (Ops.cs:360 - later boxes cannot change earlier ones).
+//   3. greedy suppress : boxes offset by cls*max_wh in fp32 (Ops.cs:345,356).
+//        fast path (<= 4096 candidates, every box inside (-0.49, 0.49) * max_wh): the class offsets then
+//          make boxes of different classes disjoint, so IoU across classes is exactly 0 and the greedy
+//          pass decomposes into independent per-class passes.  Candidates are re-sorted class-major
+//          (score order inside a class), each warp runs whole class segments 32 candidates at a time
+//          (kept list of the class, then a ballot-driven resolve inside the chunk), and the kept flags are
+//          compacted in score order - the same set in the same order as the sequential pass.
+//        general path: candidates are consumed in chunks of 32 by the whole CTA: a 32x32 IoU bit-matrix
+//          inside the chunk plus a check against the kept list, then a 32-step serial resolve.  Stops at
+//          max_det kept boxes (Ops.cs:360 - later boxes cannot change earlier ones).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace yb {
 
 constexpr int NMS_THREADS = 1024;
 constexpr int NMS_SMEM_KEYS = 16384;  // candidates sortable in shared memory (128 KB of keys)
+constexpr int NMS_FAST_N = 4096;      // candidates the class-wise fast path handles
+constexpr int NMS_LONG_SEG = 128;     // longer class segments are processed by the whole CTA
 constexpr int NMS_MAX_DET_CAP = 1024;
 constexpr int NMS_SC = 1024;  // sorted candidates gathered into shared memory per super-chunk
 
 struct Box5 {
   float x1, y1, x2, y2, area;
 };
-// kept[1024] + super-chunk boxes/rows/anchors + rowmask + misc, padded to 8 bytes for the 64-bit keys
-constexpr size_t NMS_FIXED_SMEM =
-    ((NMS_MAX_DET_CAP + NMS_SC) * sizeof(Box5) + NMS_SC * 6 * 4 + NMS_SC * 4 + 32 * 4 + 16 + 7) / 8 * 8;
+// shared memory: [64-bit keys of NMS_SMEM_KEYS candidates][union of the two greedy paths]
+//   general path: kept[1024] + super-chunk boxes/rows/anchors + rowmask
+//   fast path   : float4 boxes + 32-bit class-major keys + keep flags + segment starts, NMS_FAST_N each
+constexpr size_t NMS_KEYS_SMEM = (size_t)NMS_SMEM_KEYS * 8;
+constexpr size_t NMS_GENERAL_SMEM = (NMS_MAX_DET_CAP + NMS_SC) * sizeof(Box5) + NMS_SC * 6 * 4 + NMS_SC * 4 + 32 * 4;
+constexpr size_t NMS_FAST_SMEM = (size_t)NMS_FAST_N * (16 + 4 + 1 + 2) + 64 * 4;
+constexpr size_t NMS_TOTAL_SMEM =
+    NMS_KEYS_SMEM + (NMS_GENERAL_SMEM > NMS_FAST_SMEM ? NMS_GENERAL_SMEM : NMS_FAST_SMEM) + 64;
+
 
 // IoU > thr test with the exact op order of torchvision's CPU kernel (nms_kernel_impl):
 //   w = max(0, xx2-xx1); h = max(0, yy2-yy1); inter = w*h; ovr = inter / (iarea + area_j - inter)
@@ -41,6 +57,15 @@ __device__ __forceinline__ bool iou_gt(const Box5& a, const Box5& b, float thr) 
   const float inter = __fmul_rn(w, h);
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter));
   return ovr > thr;  // NaN (0/0) compares false, as on the CPU
+}
+
+__device__ __forceinline__ bool iou_gt4(const float4& a, const float4& b, float thr) {
+  Box5 x, y;
+  x.x1 = a.x; x.y1 = a.y; x.x2 = a.z; x.y2 = a.w;
+  x.area = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  y.x1 = b.x; y.y1 = b.y; y.x2 = b.z; y.y2 = b.w;
+  y.area = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  return iou_gt(x, y, thr);
 }
 
 // Stage 1 (all SMs): per anchor best class + confidence (Ops.cs:272, 325-328).  conf = -1 marks
@@ -75,7 +100,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1)
 nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thres, float iou_thres,
            int max_det, int max_nms, float max_wh, float* __restrict__ dets, int* __restrict__ counts,
            int* __restrict__ keep_idx, unsigned long long* __restrict__ gkeys, int key_cap,
-           const float* __restrict__ sconf, const int* __restrict__ scls) {
+           const float* __restrict__ sconf, const int* __restrict__ scls, int fast_n) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -84,15 +109,23 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
   const int row_w = 6 + extra;
 
   // shared carve-up
-  Box5* kept = reinterpret_cast<Box5*>(nms_smem);                       // [NMS_MAX_DET_CAP]
+  unsigned* misc = reinterpret_cast<unsigned*>(nms_smem);                // [8]: n_cand, supp, n_seg, kept_n, ...
+  unsigned long long* skeys = reinterpret_cast<unsigned long long*>(nms_smem + 64);
+  unsigned char* un = nms_smem + 64 + NMS_KEYS_SMEM;
+  // general path
+  Box5* kept = reinterpret_cast<Box5*>(un);                              // [NMS_MAX_DET_CAP]
   Box5* cbox = kept + NMS_MAX_DET_CAP;                                   // [NMS_SC] super-chunk boxes (class-offset)
   float* craw = reinterpret_cast<float*>(cbox + NMS_SC);                 // [NMS_SC][6] raw rows
   int* canchor = reinterpret_cast<int*>(craw + NMS_SC * 6);              // [NMS_SC]
   unsigned* rowmask = reinterpret_cast<unsigned*>(canchor + NMS_SC);     // [32]
-  unsigned* misc = rowmask + 32;                                         // [4]: n_cand, supp, -, kept_n
-  unsigned long long* keys =
-      gkeys ? gkeys + (size_t)b * key_cap : reinterpret_cast<unsigned long long*>(nms_smem + NMS_FIXED_SMEM);
-  if (tid < 4) misc[tid] = 0;
+  // fast path
+  float4* fbox = reinterpret_cast<float4*>(un);                          // [NMS_FAST_N] class-offset boxes by rank
+  unsigned* ckey = reinterpret_cast<unsigned*>(fbox + NMS_FAST_N);       // [NMS_FAST_N] class << 12 | rank
+  unsigned* frow = ckey + NMS_FAST_N;                                    // [32] chunk bit-matrix rows, [32..63] long segments
+  unsigned short* segs = reinterpret_cast<unsigned short*>(frow + 64);   // [NMS_FAST_N] segment starts
+  unsigned char* keepf = reinterpret_cast<unsigned char*>(segs + NMS_FAST_N);      // [NMS_FAST_N]
+  unsigned long long* keys = gkeys + (size_t)b * key_cap;
+  if (tid < 8) misc[tid] = 0;
   __syncthreads();
 
   // ---- 1. candidate compaction (per-anchor conf/class come from nms_scan_kernel) ----
@@ -111,6 +144,12 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
   if (n == 0) {
     if (tid == 0) counts[b] = 0;
     return;
+  }
+  const bool in_smem = n <= NMS_SMEM_KEYS;
+  if (in_smem) {  // sort in shared memory
+    for (int i = tid; i < n; i += NMS_THREADS) skeys[i] = keys[i];
+    keys = skeys;
+    __syncthreads();
   }
 
   // ---- 2. bitonic sort (ascending) over the next power of two ----
@@ -133,7 +172,200 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
   }
   n = min(n, max_nms);
 
-  // ---- 3. greedy suppression: super-chunks of 1024 sorted candidates are gathered into shared
+  // ---- 3a. class-wise fast path ----
+  if (n <= fast_n) {
+    const float lim = __fmul_rn(0.49f, max_wh);
+    int bad = 0;
+    for (int r = tid; r < n; r += NMS_THREADS) {
+      const unsigned long long key = keys[r];
+      const int a = (int)((key >> 12) & 0xFFFFF);
+      const int j = (int)(key & 0xFFF);
+      const float cx = P[a], cy = P[(size_t)A + a], w = P[(size_t)2 * A + a], h = P[(size_t)3 * A + a];
+      const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+      const float x1 = __fsub_rn(cx, hw), y1 = __fsub_rn(cy, hh);
+      const float x2 = __fadd_rn(cx, hw), y2 = __fadd_rn(cy, hh);
+      const float off = __fmul_rn((float)j, max_wh);  // Ops.cs:345
+      fbox[r] = make_float4(__fadd_rn(x1, off), __fadd_rn(y1, off), __fadd_rn(x2, off), __fadd_rn(y2, off));
+      ckey[r] = ((unsigned)j << 12) | (unsigned)r;
+      keepf[r] = 0;
+      // x extents strictly inside (-0.49, 0.49) * max_wh => boxes of different classes cannot intersect
+      if (!(fabsf(x1) < lim && fabsf(x2) < lim)) bad = 1;
+    }
+    bad = __syncthreads_or(bad);
+    if (!bad) {
+      int P2c = 1;
+      while (P2c < n) P2c <<= 1;
+      for (int i = n + tid; i < P2c; i += NMS_THREADS) ckey[i] = 0xFFFFFFFFu;
+      __syncthreads();
+      for (int k = 2; k <= P2c; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < P2c; i += NMS_THREADS) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const unsigned x = ckey[i], y = ckey[ixj];
+              const bool up = (i & k) == 0;
+              if ((x > y) == up) { ckey[i] = y; ckey[ixj] = x; }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      // segment (= class) starts, in any order
+      for (int i = tid; i < n; i += NMS_THREADS)
+        if (i == 0 || (ckey[i] >> 12) != (ckey[i - 1] >> 12)) segs[atomicAdd(&misc[2], 1u)] = (unsigned short)i;
+      __syncthreads();
+      const int nseg = (int)misc[2];
+      // short segments: one warp each
+      for (int sg = warp; sg < nseg; sg += NMS_THREADS / 32) {
+        const int s_begin = segs[sg];
+        const unsigned cls = ckey[s_begin] >> 12;
+        if (s_begin + NMS_LONG_SEG < n && (ckey[s_begin + NMS_LONG_SEG] >> 12) == cls) {  // long: whole CTA, below
+          if (lane == 0) frow[32 + atomicAdd(&misc[4], 1u)] = (unsigned)s_begin;
+          continue;
+        }
+        int kcount = 0;  // kept of this class so far; their keys are stored in place at ckey[s_begin ..]
+        for (int s0 = s_begin; s0 < n && kcount < max_det; s0 += 32) {
+          const unsigned ck = (s0 + lane < n) ? ckey[s0 + lane] : 0xFFFFFFFFu;
+          const bool valid = (ck >> 12) == cls;
+          const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+          if (!vmask) break;
+          const int rank = (int)(ck & 0xFFF);
+          const float4 mine = valid ? fbox[rank] : make_float4(0.f, 0.f, 0.f, 0.f);
+          bool sup = false;
+          for (int t = 0; t < kcount; t++) {
+            const float4 kb = fbox[ckey[s_begin + t] & 0xFFFu];
+            sup = sup || iou_gt4(kb, mine, iou_thres);
+          }
+          unsigned alive = __ballot_sync(0xffffffffu, valid && !sup);
+          unsigned keptmask = 0;
+          while (alive) {
+            const int i = __ffs(alive) - 1;
+            keptmask |= 1u << i;
+            float4 bi;
+            bi.x = __shfl_sync(0xffffffffu, mine.x, i); bi.y = __shfl_sync(0xffffffffu, mine.y, i);
+            bi.z = __shfl_sync(0xffffffffu, mine.z, i); bi.w = __shfl_sync(0xffffffffu, mine.w, i);
+            const bool s2 = lane > i && iou_gt4(bi, mine, iou_thres);
+            alive &= ~__ballot_sync(0xffffffffu, s2);
+            alive &= ~(1u << i);
+          }
+          __syncwarp();
+          if ((keptmask >> lane) & 1u) {
+            // class bits stay in place: a neighbouring warp scanning past its own segment must never see a
+            // foreign class here
+            ckey[s_begin + kcount + __popc(keptmask & ((1u << lane) - 1u))] = (cls << 12) | (unsigned)rank;
+            keepf[rank] = 1;
+          }
+          __syncwarp();
+          kcount += __popc(keptmask);
+          if (vmask != 0xffffffffu) break;  // the segment ended inside this chunk
+        }
+      }
+      __syncthreads();
+      // long segments (> NMS_LONG_SEG candidates of one class; at most 31 of them): the whole CTA works on one
+      // chunk of 32 at a time - warp g builds row g of the chunk's IoU bit-matrix and tests the chunk against
+      // kept entries g, g+32, ...; warp 0 then resolves the chunk serially.  All operands are already in smem.
+      const int nlong = (int)misc[4];
+      for (int lg = 0; lg < nlong; lg++) {
+        const int s_begin = (int)frow[32 + lg];
+        const unsigned cls = ckey[s_begin] >> 12;
+        int kcount = 0;
+        for (int s0 = s_begin; s0 < n && kcount < max_det; s0 += 32) {
+          const unsigned ck = (s0 + lane < n) ? ckey[s0 + lane] : 0xFFFFFFFFu;
+          const bool valid = (ck >> 12) == cls;
+          const unsigned vmask = __ballot_sync(0xffffffffu, valid);  // identical in every warp
+          if (!vmask) break;
+          const int rank = (int)(ck & 0xFFF);
+          const float4 mine = valid ? fbox[rank] : make_float4(0.f, 0.f, 0.f, 0.f);
+          {
+            const unsigned ckr = (s0 + warp < n) ? ckey[s0 + warp] : 0xFFFFFFFFu;
+            const bool rvalid = (ckr >> 12) == cls;
+            const float4 rowb = rvalid ? fbox[ckr & 0xFFFu] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool hit = rvalid && valid && lane > warp && iou_gt4(rowb, mine, iou_thres);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) frow[warp] = m;
+            bool sup = false;
+            if (valid)
+              for (int k = warp; k < kcount; k += 32) sup = sup || iou_gt4(fbox[ckey[s_begin + k] & 0xFFFu], mine, iou_thres);
+            const unsigned sm = __ballot_sync(0xffffffffu, sup);
+            if (lane == 0 && sm) atomicOr(&misc[1], sm);
+          }
+          __syncthreads();
+          if (warp == 0) {
+            unsigned supp = misc[1] | ~vmask;
+            unsigned keptmask = 0;
+            int kn = kcount;
+            for (int i = 0; i < 32 && kn < max_det; i++) {
+              if (!((supp >> i) & 1u)) {
+                keptmask |= 1u << i;
+                supp |= frow[i];
+                kn++;
+              }
+            }
+            if ((keptmask >> lane) & 1u) {
+              ckey[s_begin + kcount + __popc(keptmask & ((1u << lane) - 1u))] = (cls << 12) | (unsigned)rank;
+              keepf[rank] = 1;
+            }
+            __syncwarp();
+            if (lane == 0) { misc[5] = (unsigned)kn; misc[1] = 0; }
+          }
+          __syncthreads();
+          kcount = (int)misc[5];
+          if (vmask != 0xffffffffu) break;
+        }
+        __syncthreads();
+      }
+      // ordered compaction of the kept flags (score order), 4 consecutive ranks per thread
+      __shared__ unsigned s_wsum[32];
+      const int r0 = tid * 4;
+      int f[4], local = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) { f[q] = (r0 + q < n) ? keepf[r0 + q] : 0; local += f[q]; }
+      int incl = local;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      if (lane == 31) s_wsum[warp] = (unsigned)incl;
+      __syncthreads();
+      if (warp == 0) {
+        int v = (int)s_wsum[lane], inc2 = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, inc2, d);
+          if (lane >= d) inc2 += u;
+        }
+        s_wsum[lane] = (unsigned)(inc2 - v);  // exclusive warp offsets
+        if (lane == 31) misc[3] = (unsigned)inc2;
+      }
+      __syncthreads();
+      int pos = (int)s_wsum[warp] + incl - local;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (f[q]) {
+          if (pos < max_det) {
+            const unsigned long long key = keys[r0 + q];
+            const int a = (int)((key >> 12) & 0xFFFFF);
+            const int j = (int)(key & 0xFFF);
+            const float conf = __uint_as_float(~(unsigned)(key >> 32));
+            const float cx = P[a], cy = P[(size_t)A + a], w = P[(size_t)2 * A + a], h = P[(size_t)3 * A + a];
+            const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+            float* o = dets + ((size_t)b * max_det + pos) * row_w;
+            o[0] = __fsub_rn(cx, hw); o[1] = __fsub_rn(cy, hh); o[2] = __fadd_rn(cx, hw); o[3] = __fadd_rn(cy, hh);
+            o[4] = conf; o[5] = (float)j;
+            for (int e = 0; e < extra; e++) o[6 + e] = P[(size_t)(4 + nc + e) * A + a];
+            if (keep_idx) keep_idx[(size_t)b * max_det + pos] = a;
+          }
+          pos++;
+        }
+      }
+      if (tid == 0) counts[b] = min((int)misc[3], max_det);
+      return;
+    }
+    __syncthreads();  // fall through to the general path (its buffers overlay the fast-path arrays)
+  }
+
+  // ---- 3b. general greedy suppression: super-chunks of 1024 sorted candidates are gathered into shared
   //         memory by all threads (one global-latency exposure), then consumed 32 at a time ----
   int kept_n = 0;
   for (int sc0 = 0; sc0 < n && kept_n < max_det; sc0 += NMS_SC) {
@@ -229,32 +461,40 @@ int nms_launch(const float* pred, int B, int C, int A, int nc, float conf, float
   const int extra = C - 4 - nc;
   YB_CUDA_CHECK(cudaMemsetAsync(dets, 0, (size_t)B * max_det * (6 + extra) * sizeof(float), s));
   if (keep_idx) YB_CUDA_CHECK(cudaMemsetAsync(keep_idx, 0xFF, (size_t)B * max_det * sizeof(int), s));
-  const size_t fixed = NMS_FIXED_SMEM;
+  // candidate keys are compacted into global memory (every anchor may be a candidate); up to NMS_SMEM_KEYS of
+  // them are then sorted in shared memory
   unsigned long long* gkeys = nullptr;
-  int key_cap = A;  // every anchor may be a candidate
-  size_t smem = fixed;
   int P2 = 1;
   while (P2 < A) P2 <<= 1;
-  if (P2 <= NMS_SMEM_KEYS) {
-    smem += (size_t)P2 * 8;
-    key_cap = P2;
-  } else {
-    key_cap = P2;
-    YB_CUDA_CHECK(cudaMallocAsync(&gkeys, (size_t)B * P2 * 8, s));
+  const int key_cap = P2;
+  const size_t smem = NMS_TOTAL_SMEM;
+  static bool pool_set = false;
+  if (!pool_set) {
+    // scratch comes from the stream-ordered pool on every call: keep freed blocks cached across host
+    // synchronisation points (the default threshold 0 hands them back to the OS, and the next call pays for
+    // mapping them again)
+    int dev = 0;
+    cudaMemPool_t pool = nullptr;
+    unsigned long long keep_all = ~0ull;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all);
+    cudaGetLastError();
+    pool_set = true;
   }
+  YB_CUDA_CHECK(cudaMallocAsync(&gkeys, (size_t)B * P2 * 8, s));
   static bool attr_set = false;
   if (!attr_set) {
-    YB_CUDA_CHECK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(fixed + NMS_SMEM_KEYS * 8)));
+    YB_CUDA_CHECK(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NMS_TOTAL_SMEM));
     attr_set = true;
   }
   float* sconf = nullptr;
   YB_CUDA_CHECK(cudaMallocAsync(&sconf, (size_t)B * A * 8, s));  // conf[B][A] then cls[B][A]
   int* scls = reinterpret_cast<int*>(sconf + (size_t)B * A);
+  static const int fast_n = getenv("YB_DEBUG_NMS_GENERAL") ? 0 : NMS_FAST_N;  // experiments only
   nms_scan_kernel<<<dim3((A + 255) / 256, B), 256, 0, s>>>(pred, C, A, nc, conf, sconf, scls);
   YB_CUDA_CHECK(cudaGetLastError());
   nms_kernel<<<B, NMS_THREADS, smem, s>>>(pred, C, A, nc, conf, iou, max_det, max_nms, (float)max_wh, dets, counts,
-                                          keep_idx, gkeys, key_cap, sconf, scls);
+                                          keep_idx, gkeys, key_cap, sconf, scls, fast_n);
   YB_CUDA_CHECK(cudaGetLastError());
   YB_CUDA_CHECK(cudaFreeAsync(sconf, s));
   if (gkeys) YB_CUDA_CHECK(cudaFreeAsync(gkeys, s));
