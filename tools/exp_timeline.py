@@ -7,9 +7,10 @@ import torch
 import yolosharp_b200 as y
 from yolosharp_b200 import _lib as L
 from tests.util import oracle_model, synth_image
-m = oracle_model("v8", "detect", "n")
-B = 32
-e = y.Engine("v8", "n", "detect", 80, "f16", 0, B, 640, 640, flags=2 | 8)
+size = os.environ.get("YB_TL_SIZE", "n")
+m = oracle_model("v8", "detect", size)
+B = int(os.environ.get("YB_TL_BATCH", "32"))
+e = y.Engine("v8", size, "detect", 80, "f16", 0, B, 640, 640, flags=2 | 8)
 e.load_state_dict(m.state_dict()); e.finalize()
 x = synth_image(B, 640, 640, dtype=torch.float16).cuda()
 e.forward(x); torch.cuda.synchronize()

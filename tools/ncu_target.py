@@ -18,7 +18,8 @@ m = oracle_model(arch, task, size)
 e = y.Engine(arch, size, task, 80, "f16", 0, B, 640, 640, flags=2)
 e.load_state_dict(m.state_dict())
 e.finalize()
-x = synth_image(B, 640, 640, dtype=torch.float16).cuda()
+in_dt = {"f16": torch.float16, "u8": torch.uint8, "f32": torch.float32}[os.environ.get("YB_IN_DTYPE", "f16")]
+x = synth_image(B, 640, 640, dtype=in_dt).cuda()
 names = e.op_names()
 tc = [n for n in names if "decode" not in n and n != "model.0" and not n.endswith(".m") and n not in ("model.10", "model.13")]
 if len(sys.argv) > 3:

@@ -39,7 +39,7 @@ enum TcMode { TC_TAP = 0, TC_HALO = 1, TC_S2P = 2 };
 
 struct TcArgs {
   CUtensorMap tmA;
-  CUtensorMap tmB;
+  const uint8_t* wpk;  // weights pre-packed as shared-memory slab images [n tile][tap][chunk][b_stride bytes]
   __half* out;
   const __half* res;
   const float* bias;
@@ -84,6 +84,7 @@ struct TcConvPlan {
   bool small;  // <= 2 tiles per CTA
   size_t smem;
   int grid;
+  uint8_t* wpk = nullptr;  // device, owned: packed weight slabs
 };
 
 __device__ __forceinline__ int fdiv(int x, uint64_t magic) { return (int)(((uint64_t)(uint32_t)x * magic) >> 40); }
@@ -308,13 +309,11 @@ const __grid_constant__ TcArgs a) {
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmB) : "memory");
     if (a.b_resident) {
       // weights do not depend on the previous kernel: fetch them before the grid dependency resolves
       mbar_arrive_expect_tx(bfull, a.b_bytes * a.ksteps);
-      for (int t = 0; t < taps; t++)
-        for (int ch = 0; ch < a.chunks; ch++)
-          tma_load_2d(smemB + (t * a.chunks + ch) * a.b_stride, &a.tmB, bfull, t * a.Cin + ch * a.BK, 0);
+      for (int ks = 0; ks < a.ksteps; ks++)
+        bulk_load_1d(smemB + ks * a.b_stride, a.wpk + (size_t)ks * a.b_stride, a.b_bytes, bfull);
     }
   }
   // activations written by the previous kernel are visible only after this point
@@ -351,8 +350,9 @@ const __grid_constant__ TcArgs a) {
               for (int t = 0; t < taps; t++) {
                 mbar_wait(emptyB + 8 * (b_base + sb), pb ^ 1);
                 mbar_arrive_expect_tx(fullB + 8 * (b_base + sb), a.b_bytes);
-                tma_load_2d(smemB + (b_base + sb) * a.b_stride, &a.tmB, fullB + 8 * (b_base + sb), t * a.Cin + ch * a.BK,
-                            nt * a.n_tile);
+                bulk_load_1d(smemB + (b_base + sb) * a.b_stride,
+                             a.wpk + (size_t)((nt * taps + t) * a.chunks + ch) * a.b_stride, a.b_bytes,
+                             fullB + 8 * (b_base + sb));
                 if (++sb == rb) { sb = 0; pb ^= 1; }
               }
           }
@@ -368,8 +368,9 @@ const __grid_constant__ TcArgs a) {
               if (!a.b_resident) {
                 mbar_wait(emptyB + 8 * (b_base + sb), pb ^ 1);
                 mbar_arrive_expect_tx(fullB + 8 * (b_base + sb), a.b_bytes);
-                tma_load_2d(smemB + (b_base + sb) * a.b_stride, &a.tmB, fullB + 8 * (b_base + sb), t * a.Cin + ch * a.BK,
-                            nt * a.n_tile);
+                bulk_load_1d(smemB + (b_base + sb) * a.b_stride,
+                             a.wpk + (size_t)((nt * taps + t) * a.chunks + ch) * a.b_stride, a.b_bytes,
+                             fullB + 8 * (b_base + sb));
                 if (++sb == rb) { sb = 0; pb ^= 1; }
               }
             }
@@ -531,6 +532,27 @@ const __grid_constant__ TcArgs a) {
   }
 }
 
+// One-time weight packing: w [Cout][tap][Cin] fp16 -> slab images [n tile][tap][chunk][b_stride bytes]; inside a
+// slab row r (output channel) holds BK channels, its 16-byte piece c sits at the K-major swizzled position the
+// UMMA descriptor expects: c ^ (r & 7) for 128-byte rows, c ^ ((r >> 1) & 3) for 64-byte, c ^ ((r >> 2) & 1) for 32-byte.
+__global__ void pack_weights_kernel(const __half* __restrict__ w, uint8_t* __restrict__ out, int n_tile, int n_tiles,
+                                    int taps, int chunks, int BK, int Cin, uint32_t b_stride, long long pieces) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pieces) return;
+  const int c16 = BK / 8;
+  const int c = (int)(i % c16);
+  long long q = i / c16;
+  const int r = (int)(q % n_tile); q /= n_tile;
+  const int ch = (int)(q % chunks); q /= chunks;
+  const int t = (int)(q % taps);
+  const int nt = (int)(q / taps);
+  const size_t K = (size_t)taps * Cin;
+  const int4 v = *reinterpret_cast<const int4*>(w + (size_t)(nt * n_tile + r) * K + (size_t)t * Cin + ch * BK + c * 8);
+  const int sw = BK == 64 ? (r & 7) : (BK == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
+  uint8_t* slab = out + (size_t)((nt * taps + t) * chunks + ch) * b_stride;
+  *reinterpret_cast<int4*>(slab + (size_t)r * BK * 2 + ((c ^ sw) << 4)) = v;
+}
+
 // ------------------------------------------------------------------------------------------
 // Host side: tiling choice + tensor maps
 // ------------------------------------------------------------------------------------------
@@ -659,21 +681,6 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     delete plan;
     return nullptr;
   }
-  {
-    const int K = p.k * p.k * p.Cin;
-    cuuint64_t bdim[2] = {(cuuint64_t)K, (cuuint64_t)p.Cout};
-    cuuint64_t bstr[1] = {(cuuint64_t)K * esz};
-    cuuint32_t bbox[2] = {(cuuint32_t)a.BK, (cuuint32_t)a.n_tile};
-    cuuint32_t bes[2] = {1, 1};
-    cr = encode(&a.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p.w), bdim, bstr, bbox, bes,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-      if (err) *err = "cuTensorMapEncodeTiled(B) failed with code " + std::to_string((int)cr);
-      delete plan;
-      return nullptr;
-    }
-  }
   const int a_rows = a.mode == TC_HALO ? (a.BW + 2) * (a.BH + 2)
                                        : (a.mode == TC_S2P ? 2 * (a.BW + 1) * (2 * a.BH + 1) : a.BW * a.BH);
   a.a_bytes = (uint32_t)(a_rows * a.row_bytes);
@@ -681,6 +688,32 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   a.a_stride = (uint32_t)((std::max(a_rows, 128) * a.row_bytes + 1023) / 1024 * 1024);
   a.b_stride = (uint32_t)((a.n_tile * a.row_bytes + 1023) / 1024 * 1024);
   a.ksteps = p.k * p.k * a.chunks;
+  {
+    // Weights are constant: store every [n_tile x BK] slab in global memory exactly as it must look in shared
+    // memory (swizzled rows, padded to b_stride), so the kernel fetches a slab with ONE contiguous bulk copy.
+    // (As 2-D TMA boxes the slabs cost ~3 cycles per row in the TMA unit - 7200 rows per tile for a 3x3 160->160
+    //  layer, more than its MMAs - and bounded the wide layers of v8s / v8x at ~30 % of the tensor peak.)
+    const size_t total = (size_t)a.n_tiles * a.ksteps * a.b_stride;
+    if (cudaMalloc(&plan->wpk, total) != cudaSuccess) {
+      if (err) *err = "cudaMalloc(packed weights) failed";
+      cudaGetLastError();
+      delete plan;
+      return nullptr;
+    }
+    cudaMemset(plan->wpk, 0, total);
+    const int chunks16 = a.BK / 8;  // 16-byte pieces per row
+    const long long pieces = (long long)a.n_tiles * a.ksteps * a.n_tile * chunks16;
+    pack_weights_kernel<<<(unsigned)((pieces + 255) / 256), 256>>>(reinterpret_cast<const __half*>(p.w), plan->wpk, a.n_tile,
+                                                                    a.n_tiles, p.k * p.k, a.chunks, a.BK, p.Cin,
+                                                                    a.b_stride, pieces);
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      if (err) *err = std::string("pack_weights_kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+      cudaFree(plan->wpk);
+      delete plan;
+      return nullptr;
+    }
+    a.wpk = plan->wpk;
+  }
   // Two CTAs per SM (each <= ~100 KiB smem, <= 256 TMEM columns) double the tiles in flight per SM and
   // hide the producer -> MMA -> epilogue hand-off latencies of the HBM-bound high-resolution layers;
   // layers whose resident weights or wide N tiles do not fit run one CTA per SM with the full budget.
@@ -766,7 +799,10 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   return plan;
 }
 
-void tc_conv_plan_destroy(TcConvPlan* plan) { delete plan; }
+void tc_conv_plan_destroy(TcConvPlan* plan) {
+  if (plan && plan->wpk) cudaFree(plan->wpk);
+  delete plan;
+}
 
 long long* g_tc_dbg = nullptr;  // set by yb_debug_timeline: next tcgen05 conv launches write their timeline here
 int g_tc_dbg_countdown = -1;
