@@ -65,6 +65,7 @@ struct TcArgs {
   int n_acc;                      // TMEM accumulator buffers (2 or 4)
   int total_tiles;
   int b_resident;                 // all weight slabs stay in smem for the CTA's lifetime
+  int dual;                       // streamed weights: tiles are processed in pairs that share every weight slab
   int ksteps;
   // fused head decode (EpiDecode)
   int epi_mode, dA, dCtot, da0, dch0, dWl, dHW;
@@ -239,6 +240,102 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
   }
 }
 
+// Streamed-weight layers (weights too large to stay resident): two tiles are accumulated side by side so that
+// every weight slab fetched from L2 feeds the MMAs of BOTH.  The timeline of a 3x3 160->160 layer (v8x) showed the
+// issuer waiting for weight slabs ~250 cycles per MMA: 148 SMs re-streaming the same 460 KB per 128-pixel tile run
+// into the L2 -> SM delivery limit, not into the tensor pipe.  One issuer (wide N: the tensor pipe is the pace).
+template <int KK>
+__device__ __forceinline__ void mma_role_dual(const TcArgs& a, uint32_t smemA, uint32_t smemB, uint32_t tmem_base,
+                                              uint32_t fullA, uint32_t emptyA, uint32_t fullB, uint32_t emptyB,
+                                              uint32_t tfull0, uint32_t tempty0) {
+  const uint32_t n_tile = a.n_tile;
+  const uint32_t idesc = (1u << 4) | ((n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t a_hi = a.sbo_a | (1u << 14) | (a.layout_a << 29);
+  const uint32_t b_hi = a.sbo_b | (1u << 14) | (a.layout_b << 29);
+  const uint32_t a_stride16 = a.a_stride >> 4, b_stride16 = a.b_stride >> 4;
+  const uint32_t a_lo0 = ((smemA & 0x3FFFF) >> 4) | (1u << 16), b_lo0 = ((smemB & 0x3FFFF) >> 4) | (1u << 16);
+  const int ra = a.stages_a, rb = a.stages_b, chunks = a.chunks, ksteps = a.ksteps, nb = a.n_acc;
+  const bool halo = a.mode != TC_TAP, s2p = a.mode == TC_S2P;
+  const int total_tiles = a.total_tiles, gstride = gridDim.x;
+  constexpr uint32_t ROW16 = KK * 2;
+  int sa = 0, sb = 0;
+  uint32_t pa = 0, pb = 0;
+  int li = 0;
+  for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += 2 * gstride, li += 2) {
+    const int nT = (tile0 + gstride < total_tiles) ? 2 : 1;
+    uint32_t d_tmem[2] = {0, 0};
+    int acc[2] = {0, 0};
+    for (int q = 0; q < nT; q++) {
+      acc[q] = (li + q) & (nb - 1);
+      const uint32_t aphase = (uint32_t)((li + q) >> (nb == 4 ? 2 : 1)) & 1u;
+      mbar_wait(tempty0 + 8 * acc[q], aphase ^ 1);
+      d_tmem[q] = tmem_base + acc[q] * n_tile;
+    }
+    tc_fence_after();
+    uint32_t alo[2] = {0, 0};
+    int stq[2] = {0, 0};
+    if (halo) {
+      for (int ch = 0; ch < chunks; ch++) {
+        for (int q = 0; q < nT; q++) {
+          mbar_wait(fullA + 8 * sa, pa);
+          alo[q] = a_lo0 + sa * a_stride16;
+          stq[q] = sa;
+          if (++sa == ra) { sa = 0; pa ^= 1; }
+        }
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+          const uint32_t TAP_HALO = (uint32_t)((t / 3) * (HALO_BW + 2) + (t % 3)) * ROW16;
+          const uint32_t TAP_S2P = (uint32_t)((t / 3) * (HALO_BW + 1) + (t % 3 != 0 ? 1 : 0)) * 2 * ROW16 +
+                                   (t % 3 != 1 ? ROW16 : 0);
+          const uint32_t tap16 = s2p ? TAP_S2P : TAP_HALO;
+          mbar_wait(fullB + 8 * sb, pb);
+          tc_fence_after();
+          const uint32_t b_lo = b_lo0 + sb * b_stride16;
+          const uint32_t first = (ch == 0 && t == 0) ? 1u : 0u;
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            if (q < nT) {
+#pragma unroll
+              for (int k = 0; k < KK; k++)
+                umma_f16(d_tmem[q], desc64(alo[q] + tap16 + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc,
+                         (first && k == 0) ? 0u : 1u);
+            }
+          }
+          umma_commit(emptyB + 8 * sb);
+          if (++sb == rb) { sb = 0; pb ^= 1; }
+        }
+        for (int q = 0; q < nT; q++) umma_commit(emptyA + 8 * stq[q]);
+      }
+    } else {
+      for (int ks = 0; ks < ksteps; ks++) {
+        for (int q = 0; q < nT; q++) {
+          mbar_wait(fullA + 8 * sa, pa);
+          alo[q] = a_lo0 + sa * a_stride16;
+          stq[q] = sa;
+          if (++sa == ra) { sa = 0; pa ^= 1; }
+        }
+        mbar_wait(fullB + 8 * sb, pb);
+        tc_fence_after();
+        const uint32_t b_lo = b_lo0 + sb * b_stride16;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          if (q < nT) {
+#pragma unroll
+            for (int k = 0; k < KK; k++)
+              umma_f16(d_tmem[q], desc64(alo[q] + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc,
+                       (ks == 0 && k == 0) ? 0u : 1u);
+          }
+        }
+        for (int q = 0; q < nT; q++) umma_commit(emptyA + 8 * stq[q]);
+        umma_commit(emptyB + 8 * sb);
+        if (++sb == rb) { sb = 0; pb ^= 1; }
+      }
+    }
+    for (int q = 0; q < nT; q++) umma_commit(tfull0 + 8 * acc[q]);  // both accumulators complete
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Two operand rings feed the single MMA-issuing thread:
 //   A ring  : TC_TAP  - one 128-row slab per (tap, channel slab)
@@ -322,12 +419,59 @@ const __grid_constant__ TcArgs a) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (a.dual) {
+        // pairs of tiles (same N tile: the grid is a multiple of n_tiles) share every weight slab
+        const int ra = a.stages_a, rb = a.stages_b;
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        for (int tile0 = blockIdx.x; tile0 < a.total_tiles; tile0 += 2 * gridDim.x) {
+          const int nT = (tile0 + (int)gridDim.x < a.total_tiles) ? 2 : 1;
+          int img_[2], wc_[2], hb_[2], nt = 0;
+          for (int q = 0; q < nT; q++) {
+            const int tile = tile0 + q * gridDim.x;
+            const int mt = fdiv(tile, a.m_ntiles);
+            nt = tile - mt * a.n_tiles;
+            img_[q] = fdiv(mt, a.m_tpi);
+            const int r = mt - img_[q] * tiles_per_img;
+            const int th = fdiv(r, a.m_tw), tw = r - th * a.tiles_w;
+            wc_[q] = a.mode == TC_S2P ? tw * a.BW - 1 : tw * a.BW * a.stride - a.pad;
+            hb_[q] = th * a.BH * a.stride - a.pad;
+          }
+          auto load_a = [&](int q, int c0, int dw, int dh) {
+            mbar_wait(emptyA + 8 * sa, pa ^ 1);
+            mbar_arrive_expect_tx(fullA + 8 * sa, a.a_bytes);
+            tma_load_4d(smemA + sa * a.a_stride, &a.tmA, fullA + 8 * sa, c0, wc_[q] + dw, hb_[q] + dh, img_[q]);
+            if (++sa == ra) { sa = 0; pa ^= 1; }
+          };
+          auto load_b = [&](int t, int ch) {
+            mbar_wait(emptyB + 8 * sb, pb ^ 1);
+            mbar_arrive_expect_tx(fullB + 8 * sb, a.b_bytes);
+            bulk_load_1d(smemB + sb * a.b_stride, a.wpk + (size_t)((nt * taps + t) * a.chunks + ch) * a.b_stride, a.b_bytes,
+                         fullB + 8 * sb);
+            if (++sb == rb) { sb = 0; pb ^= 1; }
+          };
+          if (a.mode != TC_TAP) {
+            for (int ch = 0; ch < a.chunks; ch++) {
+              for (int q = 0; q < nT; q++) load_a(q, ch * a.BK, 0, 0);
+              for (int t = 0; t < taps; t++) load_b(t, ch);
+            }
+          } else {
+            for (int t = 0; t < taps; t++) {
+              const int kh = a.ksz == 3 ? (t >= 6 ? 2 : (t >= 3 ? 1 : 0)) : 0, kw = t - kh * a.ksz;
+              for (int ch = 0; ch < a.chunks; ch++) {
+                for (int q = 0; q < nT; q++) load_a(q, ch * a.BK, kw, kh);
+                load_b(t, ch);
+              }
+            }
+          }
+        }
+      }
       const int ni = a.n_issuers;
       const int ra = a.stages_a / ni, rb = a.b_resident ? 0 : a.stages_b / ni;
       int sa_[2] = {0, 0}, sb_[2] = {0, 0};
       uint32_t pa_[2] = {0, 0}, pb_[2] = {0, 0};
       int li = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, li++) {
+      for (int tile = a.dual ? a.total_tiles : (int)blockIdx.x; tile < a.total_tiles; tile += gridDim.x, li++) {
         const int rg = ni == 2 ? (li & 1) : 0;  // ring (= issuer) of this tile
         int& sa = sa_[rg]; int& sb = sb_[rg];
         uint32_t& pa = pa_[rg]; uint32_t& pb = pb_[rg];
@@ -382,6 +526,15 @@ const __grid_constant__ TcArgs a) {
     // ===================== MMA issuers =====================
     if (lane == 0) {
       const int issuer = warp - 1;
+      if (a.dual) {
+        if (issuer == 0) {
+          switch (a.BK) {
+            case 64: mma_role_dual<4>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0); break;
+            case 32: mma_role_dual<2>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0); break;
+            default: mma_role_dual<1>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0); break;
+          }
+        }
+      } else
       switch (a.BK) {
         case 64: mma_role<4>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer); break;
         case 32: mma_role<2>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer); break;
@@ -547,6 +700,7 @@ __global__ void pack_weights_kernel(const __half* __restrict__ w, uint8_t* __res
   const int t = (int)(q % taps);
   const int nt = (int)(q / taps);
   const size_t K = (size_t)taps * Cin;
+  if (ch * BK + c * 8 >= Cin) return;  // ragged last slab: stays zero
   const int4 v = *reinterpret_cast<const int4*>(w + (size_t)(nt * n_tile + r) * K + (size_t)t * Cin + ch * BK + c * 8);
   const int sw = BK == 64 ? (r & 7) : (BK == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1));
   uint8_t* slab = out + (size_t)((nt * taps + t) * chunks + ch) * b_stride;
@@ -604,8 +758,14 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   // stride-2 3x3 convs over a whole-buffer view with <= 32 channels use pair rows (below)
   const bool s2p_ok = p.k == 3 && p.stride == 2 && p.in.coff == 0 && p.in.pitch == p.Cin && p.Cin <= 32 && p.in.W % 2 == 0;
   a.mode = (p.k == 3 && p.stride == 1) ? TC_HALO : (s2p_ok ? TC_S2P : TC_TAP);
-  a.BK = (p.Cin % 64 == 0) ? 64 : (p.Cin % 32 == 0 ? 32 : 16);
-  a.chunks = p.Cin / a.BK;
+  // channel slab: the widest of 64 / 32 / 16 channels (128 / 64 / 32-byte operand rows) that pads K by at most
+  // 35 %; a ragged last slab
+  // is zero-filled by TMA (activations, dim 0 bound = Cin) and by the weight packing.  (80 / 160 / 400-channel
+  // layers of v8x ran with 16 / 32-channel slabs = 32 / 64-byte rows and stayed at ~30 % of the tensor peak while
+  // the 320 / 640-channel layers reached 45-75 %.)
+  auto padded = [&](int bk) { return (p.Cin + bk - 1) / bk * bk; };
+  a.BK = padded(64) * 100 <= p.Cin * 135 ? 64 : (padded(32) * 100 <= p.Cin * 135 ? 32 : 16);  // <= 35 % zero K
+  a.chunks = (p.Cin + a.BK - 1) / a.BK;
   a.act = p.act;
   a.n_tile = pick_n_tile(p.Cout);
   a.n_tiles = p.Cout / a.n_tile;
@@ -765,7 +925,26 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     a.stages_a &= ~1;  // even split
     if (!a.b_resident) a.stages_b &= ~1;
   }
-  if (a.n_issuers == 1 && a.n_acc > 2) { /* one issuer: two accumulators are enough */ }
+  if (!a.b_resident) {
+    // streamed weights: tile pairs share the weight slabs (mma_role_dual); two activation slabs per step
+    const size_t budget = plan->occ == 2 ? 104 * 1024 : 200 * 1024;
+    int sa2, sb2;
+    if (a.mode != TC_TAP) {
+      sa2 = (size_t)4 * a.a_stride + 3 * (size_t)a.b_stride <= budget ? 4 : 2;
+      sb2 = budget > (size_t)sa2 * a.a_stride ? (int)std::min<size_t>(TC_MAX_STAGES, (budget - (size_t)sa2 * a.a_stride) / a.b_stride) : 0;
+    } else {
+      const int S = (int)std::min<size_t>(6, budget / (2 * (size_t)a.a_stride + a.b_stride));
+      sa2 = 2 * S;
+      sb2 = S;
+    }
+    if (sa2 >= 2 && sb2 >= 2) {
+      a.dual = 1;
+      a.n_issuers = 1;
+      a.stages_a = sa2;
+      a.stages_b = sb2;
+      plan->smem = (size_t)a.stages_a * a.a_stride + (size_t)a.stages_b * a.b_stride + 1024;
+    }
+  }
   if (a.stages_a < 2 || (!a.b_resident && a.stages_b < 2)) {
     if (err) *err = "tile does not fit in shared memory";
     delete plan;
@@ -833,6 +1012,7 @@ int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s) {
   // then pipelines 2-3 tiles) so that a sibling branch can occupy the other SMs at the same time
   if (plan->p.share_sms && a.total_tiles <= 4 * plan->grid && a.ksteps * (a.BK >> 4) <= 40)
     grid = std::max(1, std::min(grid, (a.total_tiles + 2) / 3));
+  if (a.dual && grid >= a.n_tiles) grid -= grid % a.n_tiles;  // tile t and t + grid must share their N tile
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(plan->threads);
