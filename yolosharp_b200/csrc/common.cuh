@@ -99,7 +99,7 @@ int launch_proto_out(const View& in, float* out, int B, cudaStream_t s);
 struct TcConvPlan;  // opaque: tensor maps + tiling for one conv layer
 TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err);
 void tc_conv_plan_destroy(TcConvPlan* plan);
-int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s);
+int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, int* tile_ctr, cudaStream_t s);
 bool tc_conv_supported(const ConvParams& p);
 // stem: NCHW u8/f16/f32 input -> 3x3 s2 conv (Cin=3) + bias + SiLU -> NHWC fp16
 int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const __half* w16 /*[Cout][32]*/,

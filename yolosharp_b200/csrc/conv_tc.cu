@@ -73,6 +73,7 @@ struct TcArgs {
   float* pred;
   // exact x / d for x*d < 2^40 as (x * ceil(2^40/d)) >> 40 (runtime integer division costs ~100+ cycles)
   uint64_t m_ntiles, m_tpi, m_tw, m_bw;
+  int* tile_ctr;   // dynamic tile scheduler: global counter of this launch (nullptr = static round-robin)
   long long* dbg;  // optional timeline buffer (tools/exp_timeline.py); nullptr in production
 };
 
@@ -114,6 +115,28 @@ constexpr int HALO_BW = 8, HALO_BH = 16;  // output rectangle of a halo tile (12
 // hoisted: descriptor high words are loop constants, low words advance by compile-time amounts
 // (KK = BK/16 MMAs per slab, tap shifts of the halo tile), kernel parameters live in registers.
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// Dynamic tile scheduler.  The producer thread draws tile indices from a global counter (first tile =
+// blockIdx.x, then gridDim.x + atomicAdd) and publishes them in a small shared-memory queue that the MMA
+// issuers and epilogue groups follow.  CTAs that start late - SMs held by a concurrent kernel (NMS of the
+// previous batch, a sibling head branch) - simply take fewer tiles instead of delaying the whole grid with a
+// fixed share.  The queue cannot wrap onto unread entries: the producer is at most stages_a + n_acc + groups
+// (< 32) tiles ahead of the slowest reader.
+// ------------------------------------------------------------------------------------------
+constexpr int TQ = 32;
+__device__ __forceinline__ void tq_publish(int* s_tile, volatile int* s_head, int li, int tile) {
+  s_tile[li & (TQ - 1)] = tile;
+  __threadfence_block();
+  *s_head = li + 1;
+}
+__device__ __forceinline__ int tq_get(const int* s_tile, const volatile int* s_head, int li) {
+  const long long t0 = clock64();
+  while (*s_head <= li)
+    if (clock64() - t0 > 4000000000ll) __trap();
+  __threadfence_block();
+  return reinterpret_cast<const volatile int*>(s_tile)[li & (TQ - 1)];
+}
+
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
   uint64_t d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
@@ -135,7 +158,8 @@ __device__ __forceinline__ void res_prefetch(const TcArgs& a, int n0, int cb0, s
 template <int KK>
 __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32_t smemB, uint32_t tmem_base,
                                          uint32_t fullA, uint32_t emptyA, uint32_t fullB, uint32_t emptyB,
-                                         uint32_t tfull0, uint32_t tempty0, uint32_t bfull, int issuer) {
+                                         uint32_t tfull0, uint32_t tempty0, uint32_t bfull, int issuer,
+                                         const int* s_tile, const volatile int* s_head) {
   const uint32_t n_tile = a.n_tile;
   const uint32_t idesc = (1u << 4) | ((n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   // descriptor = lo | hi << 32 :  lo = start>>4 | LBO(1)<<16 ;  hi = SBO | version(1)<<14 | layout<<29
@@ -161,9 +185,10 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
   int sa = 0, sb = 0;
   uint32_t pa = 0, pb = 0;
   if (resident) mbar_wait(bfull, 0);
+  const bool dyn = a.tile_ctr != nullptr;
   for (int li = issuer;; li += ni) {
-    const int tile = blockIdx.x + li * gstride;
-    if (tile >= total_tiles) break;
+    const int tile = dyn ? tq_get(s_tile, s_head, li) : (int)blockIdx.x + li * gstride;
+    if (tile < 0 || tile >= total_tiles) break;
     const int dbg_i = li;
     const int acc = li & (nb - 1);  // nb is 2 or 4
     const uint32_t aphase = (uint32_t)(li >> (nb == 4 ? 2 : 1)) & 1u;
@@ -353,6 +378,8 @@ const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   __shared__ __align__(8) uint64_t bars[4 * TC_MAX_STAGES + 2 * TC_MAX_ACC + 1];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ int s_tile[TQ];
+  __shared__ volatile int s_head;
   __shared__ __align__(16) float s_bias[TC_MAX_COUT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -374,6 +401,7 @@ const __grid_constant__ TcArgs a) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0 && lane == 0) {
+    s_head = 0;
     for (int s = 0; s < a.stages_a; s++) {
       mbar_init(fullA + 8 * s, 1);
       mbar_init(emptyA + 8 * s, 1);
@@ -471,7 +499,12 @@ const __grid_constant__ TcArgs a) {
       int sa_[2] = {0, 0}, sb_[2] = {0, 0};
       uint32_t pa_[2] = {0, 0}, pb_[2] = {0, 0};
       int li = 0;
-      for (int tile = a.dual ? a.total_tiles : (int)blockIdx.x; tile < a.total_tiles; tile += gridDim.x, li++) {
+      const bool dyn = a.tile_ctr != nullptr;
+      int tile = a.dual ? a.total_tiles : (int)blockIdx.x;
+      int nxt = a.total_tiles;
+      if (dyn && tile < a.total_tiles) nxt = (int)gridDim.x + atomicAdd(a.tile_ctr, 1);  // next tile, needed one tile later
+      for (; tile < a.total_tiles; li++) {
+        if (dyn) tq_publish(s_tile, &s_head, li, tile);
         const int rg = ni == 2 ? (li & 1) : 0;  // ring (= issuer) of this tile
         int& sa = sa_[rg]; int& sb = sb_[rg];
         uint32_t& pa = pa_[rg]; uint32_t& pb = pb_[rg];
@@ -520,6 +553,16 @@ const __grid_constant__ TcArgs a) {
             }
           }
         }
+        if (dyn) {
+          tile = nxt;
+          if (tile < a.total_tiles) nxt = (int)gridDim.x + atomicAdd(a.tile_ctr, 1);
+        } else {
+          tile += gridDim.x;
+        }
+      }
+      if (dyn && !a.dual) {  // end marks for every reader (2 issuers, up to 4 epilogue groups)
+        for (int k = 0; k < 3; k++) s_tile[(li + k) & (TQ - 1)] = -1;
+        tq_publish(s_tile, &s_head, li + 3, -1);
       }
     }
   } else if (warp == 1 || warp == 2) {
@@ -536,9 +579,9 @@ const __grid_constant__ TcArgs a) {
         }
       } else
       switch (a.BK) {
-        case 64: mma_role<4>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer); break;
-        case 32: mma_role<2>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer); break;
-        default: mma_role<1>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer); break;
+        case 64: mma_role<4>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer, s_tile, &s_head); break;
+        case 32: mma_role<2>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer, s_tile, &s_head); break;
+        default: mma_role<1>(a, smemA, smemB, tmem_base, fullA, emptyA, fullB, emptyB, tfull0, tempty0, bfull, issuer, s_tile, &s_head); break;
       }
     }
   } else {
@@ -553,9 +596,10 @@ const __grid_constant__ TcArgs a) {
     const int grp = ew >> 2;
     const int G = a.n_groups;
     const int row = q * 32 + lane;
+    const bool dyn = a.tile_ctr != nullptr;
     for (int li = grp;; li += G) {
-      const int tile = blockIdx.x + li * gridDim.x;
-      if (tile >= a.total_tiles) break;
+      const int tile = dyn ? tq_get(s_tile, &s_head, li) : (int)blockIdx.x + li * (int)gridDim.x;
+      if (tile < 0 || tile >= a.total_tiles) break;
       const int acc = li & (a.n_acc - 1);  // n_acc is 2 or 4
       const uint32_t aphase = (uint32_t)(li >> (a.n_acc == 4 ? 2 : 1)) & 1u;
       const int mt = fdiv(tile, a.m_ntiles);
@@ -986,9 +1030,10 @@ void tc_conv_plan_destroy(TcConvPlan* plan) {
 long long* g_tc_dbg = nullptr;  // set by yb_debug_timeline: next tcgen05 conv launches write their timeline here
 int g_tc_dbg_countdown = -1;
 
-int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, cudaStream_t s) {
+int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, int* tile_ctr, cudaStream_t s) {
   TcArgs a = plan->args;
   a.pred = pred;
+  a.tile_ctr = a.dual ? nullptr : tile_ctr;  // tile pairs keep the static order (both tiles need the same N tile)
   a.dbg = nullptr;
   if (g_tc_dbg && g_tc_dbg_countdown >= 0 && g_tc_dbg_countdown-- == 0) a.dbg = g_tc_dbg;
   const ConvParams& p = plan->p;

@@ -85,6 +85,7 @@ struct yb_engine {
   std::vector<std::string> expected;
   char* arena = nullptr;
   size_t arena_bytes = 0;
+  int* tile_ctr = nullptr;  // one dynamic-scheduler counter per op, zeroed at the start of every forward
   bool finalized = false;
   int esize = 4;  // bytes per activation element
   int A = 0, pred_c = 0;
@@ -686,6 +687,7 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
   const bool lanes = e->lanes_ok && !events;
   bool lane_started[yb_engine::kLanes] = {};
   cudaStream_t main_s = s;
+  if (e->tile_ctr) YB_CUDA_CHECK(cudaMemsetAsync(e->tile_ctr, 0, e->ops.size() * sizeof(int), s));
   for (size_t i = 0; i < e->ops.size(); i++) {
     OpDesc& op = e->ops[i];
     s = main_s;
@@ -712,7 +714,7 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
           input_converted = true;
         }
         if (op.use_tc) {
-          rc = tc_conv_launch(op.plan, B, out_pred, s);
+          rc = tc_conv_launch(op.plan, B, out_pred, e->tile_ctr ? e->tile_ctr + i : nullptr, s);
         } else {
           rc = launch_conv_generic<T>(conv_params(e, op, B), s);
         }
@@ -836,6 +838,7 @@ int32_t yb_create(const yb_config* cfg, yb_engine** out) {
   e->arena_bytes = off;
   YB_CUDA_CHECK(cudaMalloc((void**)&e->arena, off));
   YB_CUDA_CHECK(cudaMemset(e->arena, 0, off));
+  YB_CUDA_CHECK(cudaMalloc((void**)&e->tile_ctr, e->ops.size() * sizeof(int)));
   YB_CUDA_CHECK(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
   for (int l = 1; l < yb_engine::kLanes; l++) {
     YB_CUDA_CHECK(cudaStreamCreateWithFlags(&e->side[l], cudaStreamNonBlocking));
@@ -857,6 +860,7 @@ void yb_destroy(yb_engine* e) {
   for (auto& op : e->ops) if (op.plan) tc_conv_plan_destroy(op.plan);
   for (void* p : e->dev_allocs) cudaFree(p);
   if (e->arena) cudaFree(e->arena);
+  if (e->tile_ctr) cudaFree(e->tile_ctr);
   for (auto& st : e->stage) {
     if (st.in) cudaFree(st.in);
     if (st.pred) cudaFree(st.pred);
