@@ -13,6 +13,23 @@ using namespace yb;
 
 // mode 0: descriptors recomputed per MMA like conv_tc_kernel (runtime k loop)
 // mode 1: fully unrolled, descriptor low words precomputed, 4 MMAs per iteration
+// mode 2: the WHOLE warp runs the loop (warp-uniform descriptors -> uniform datapath), elect.sync picks the issuing lane
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(160, 1) issue_kernel(int N, int iters, int n_issuers, int mode, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[4];
@@ -33,7 +50,23 @@ __global__ void __launch_bounds__(160, 1) issue_kernel(int N, int iters, int n_i
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (warp < n_issuers && lane == 0) {
+  if (mode == 2 && warp < n_issuers) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t smA = base, smB = base + 16 * 1024;
+    const uint32_t d = tmem + warp * 128;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+      const uint64_t ad = umma_desc(smA + (it & 3) * 128, 64, 2);
+      const uint64_t bd = umma_desc(smB, 64, 2);
+#pragma unroll
+      for (int k = 0; k < 4; k++) umma_f16_elect(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (it | k) != 0);
+    }
+    const long long t1 = clock64();
+    umma_commit_elect(smem_u32(&bars[warp]));
+    mbar_wait(smem_u32(&bars[warp]), 0);
+    const long long t2 = clock64();
+    if (lane == 0) { out[warp * 2] = t1 - t0; out[warp * 2 + 1] = t2 - t0; }
+  } else if (warp < n_issuers && lane == 0) {
     const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t smA = base, smB = base + 16 * 1024;
     const uint32_t d = tmem + warp * 128;  // own accumulator columns (N <= 128)
@@ -72,7 +105,7 @@ int main() {
   cudaMalloc(&dout, 64);
   cudaFuncSetAttribute(issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int iters = 2000;
-  for (int mode : {0, 1})
+  for (int mode : {0, 1, 2})
     for (int N : {16, 64, 128})
       for (int ni : {1, 2, 4}) {
         issue_kernel<<<1, 160, 50 * 1024>>>(N, iters, ni, mode, dout);

@@ -155,6 +155,12 @@ __device__ __forceinline__ void res_prefetch(const TcArgs& a, int n0, int cb0, s
   }
 }
 
+// every lane of the issuing warp waits; the warp is converged again before the next elect.sync
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  mbar_wait(bar, parity);
+  __syncwarp();
+}
+
 template <int KK>
 __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32_t smemB, uint32_t tmem_base,
                                          uint32_t fullA, uint32_t emptyA, uint32_t fullB, uint32_t emptyB,
@@ -184,25 +190,26 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
   const int a_base = issuer * ra, b_base = issuer * rb;
   int sa = 0, sb = 0;
   uint32_t pa = 0, pb = 0;
-  if (resident) mbar_wait(bfull, 0);
+  if (resident) mbar_wait_warp(bfull, 0);
   const bool dyn = a.tile_ctr != nullptr;
   for (int li = issuer;; li += ni) {
     const int tile = dyn ? tq_get(s_tile, s_head, li) : (int)blockIdx.x + li * gstride;
+    __syncwarp();
     if (tile < 0 || tile >= total_tiles) break;
     const int dbg_i = li;
     const int acc = li & (nb - 1);  // nb is 2 or 4
     const uint32_t aphase = (uint32_t)(li >> (nb == 4 ? 2 : 1)) & 1u;
-    if (a.dbg && blockIdx.x == 0 && dbg_i < 16) a.dbg[dbg_i * 8 + 0] = clock64();
-    mbar_wait(tempty0 + 8 * acc, aphase ^ 1);
+    if (a.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && dbg_i < 16) a.dbg[dbg_i * 8 + 0] = clock64();
+    mbar_wait_warp(tempty0 + 8 * acc, aphase ^ 1);
     tc_fence_after();
-    if (a.dbg && blockIdx.x == 0 && dbg_i < 16) a.dbg[dbg_i * 8 + 1] = clock64();
+    if (a.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && dbg_i < 16) a.dbg[dbg_i * 8 + 1] = clock64();
     const uint32_t d_tmem = tmem_base + acc * n_tile;
     uint32_t accf = 0;
     if (halo) {
       for (int ch = 0; ch < chunks; ch++) {
-        mbar_wait(fullA + 8 * (a_base + sa), pa);
+        mbar_wait_warp(fullA + 8 * (a_base + sa), pa);
         tc_fence_after();
-        if (a.dbg && blockIdx.x == 0 && dbg_i < 16 && ch == 0) a.dbg[dbg_i * 8 + 2] = clock64();
+        if (a.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && dbg_i < 16 && ch == 0) a.dbg[dbg_i * 8 + 2] = clock64();
         const uint32_t a_lo = a_lo0 + (a_base + sa) * a_stride16;
 #pragma unroll
         for (int t = 0; t < 9; t++) {
@@ -218,50 +225,50 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
           if (resident) {
             b_lo = b_lo0 + (t * chunks + ch) * b_stride16;
           } else {
-            mbar_wait(fullB + 8 * (b_base + sb), pb);
+            mbar_wait_warp(fullB + 8 * (b_base + sb), pb);
             tc_fence_after();
             b_lo = b_lo0 + (b_base + sb) * b_stride16;
           }
 #pragma unroll
           for (int k = 0; k < KK; k++) {  // +32 B per K=16 step inside the swizzled row
-            umma_f16(d_tmem, desc64(a_lo + tap16 + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc, accf);
+            umma_f16_elect(d_tmem, desc64(a_lo + tap16 + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc, accf);
             accf = 1;
           }
           if (!resident) {
-            umma_commit(emptyB + 8 * (b_base + sb));
+            umma_commit_elect(emptyB + 8 * (b_base + sb));
             if (++sb == rb) { sb = 0; pb ^= 1; }
           }
         }
-        umma_commit(emptyA + 8 * (a_base + sa));  // halo tile free once its 9 taps retired
+        umma_commit_elect(emptyA + 8 * (a_base + sa));  // halo tile free once its 9 taps retired
         if (++sa == ra) { sa = 0; pa ^= 1; }
       }
     } else {
       for (int ks = 0; ks < ksteps; ks++) {
-        mbar_wait(fullA + 8 * (a_base + sa), pa);
+        mbar_wait_warp(fullA + 8 * (a_base + sa), pa);
         uint32_t b_lo;
         if (resident) {
           b_lo = b_lo0 + ks * b_stride16;
         } else {
-          mbar_wait(fullB + 8 * (b_base + sb), pb);
+          mbar_wait_warp(fullB + 8 * (b_base + sb), pb);
           b_lo = b_lo0 + (b_base + sb) * b_stride16;
         }
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + (a_base + sa) * a_stride16;
 #pragma unroll
         for (int k = 0; k < KK; k++) {
-          umma_f16(d_tmem, desc64(a_lo + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc, accf);
+          umma_f16_elect(d_tmem, desc64(a_lo + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc, accf);
           accf = 1;
         }
-        umma_commit(emptyA + 8 * (a_base + sa));  // slab free once these MMAs retire
+        umma_commit_elect(emptyA + 8 * (a_base + sa));  // slab free once these MMAs retire
         if (++sa == ra) { sa = 0; pa ^= 1; }
         if (!resident) {
-          umma_commit(emptyB + 8 * (b_base + sb));
+          umma_commit_elect(emptyB + 8 * (b_base + sb));
           if (++sb == rb) { sb = 0; pb ^= 1; }
         }
       }
     }
-    umma_commit(tfull0 + 8 * acc);  // accumulator complete
-    if (a.dbg && blockIdx.x == 0 && dbg_i < 16) a.dbg[dbg_i * 8 + 3] = clock64();
+    umma_commit_elect(tfull0 + 8 * acc);  // accumulator complete
+    if (a.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && dbg_i < 16) a.dbg[dbg_i * 8 + 3] = clock64();
   }
 }
 
@@ -293,7 +300,7 @@ __device__ __forceinline__ void mma_role_dual(const TcArgs& a, uint32_t smemA, u
     for (int q = 0; q < nT; q++) {
       acc[q] = (li + q) & (nb - 1);
       const uint32_t aphase = (uint32_t)((li + q) >> (nb == 4 ? 2 : 1)) & 1u;
-      mbar_wait(tempty0 + 8 * acc[q], aphase ^ 1);
+      mbar_wait_warp(tempty0 + 8 * acc[q], aphase ^ 1);
       d_tmem[q] = tmem_base + acc[q] * n_tile;
     }
     tc_fence_after();
@@ -302,7 +309,7 @@ __device__ __forceinline__ void mma_role_dual(const TcArgs& a, uint32_t smemA, u
     if (halo) {
       for (int ch = 0; ch < chunks; ch++) {
         for (int q = 0; q < nT; q++) {
-          mbar_wait(fullA + 8 * sa, pa);
+          mbar_wait_warp(fullA + 8 * sa, pa);
           alo[q] = a_lo0 + sa * a_stride16;
           stq[q] = sa;
           if (++sa == ra) { sa = 0; pa ^= 1; }
@@ -314,7 +321,7 @@ __device__ __forceinline__ void mma_role_dual(const TcArgs& a, uint32_t smemA, u
           const uint32_t TAP_S2P = (uint32_t)((t / 3) * (HALO_BW + 1) + (t % 3 != 0 ? 1 : 0)) * 2 * ROW16 +
                                    (t % 3 != 1 ? ROW16 : 0);
           const uint32_t tap16 = s2p ? TAP_S2P : TAP_HALO;
-          mbar_wait(fullB + 8 * sb, pb);
+          mbar_wait_warp(fullB + 8 * sb, pb);
           tc_fence_after();
           const uint32_t b_lo = b_lo0 + sb * b_stride16;
           const uint32_t first = (ch == 0 && t == 0) ? 1u : 0u;
@@ -323,24 +330,24 @@ __device__ __forceinline__ void mma_role_dual(const TcArgs& a, uint32_t smemA, u
             if (q < nT) {
 #pragma unroll
               for (int k = 0; k < KK; k++)
-                umma_f16(d_tmem[q], desc64(alo[q] + tap16 + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc,
+                umma_f16_elect(d_tmem[q], desc64(alo[q] + tap16 + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc,
                          (first && k == 0) ? 0u : 1u);
             }
           }
-          umma_commit(emptyB + 8 * sb);
+          umma_commit_elect(emptyB + 8 * sb);
           if (++sb == rb) { sb = 0; pb ^= 1; }
         }
-        for (int q = 0; q < nT; q++) umma_commit(emptyA + 8 * stq[q]);
+        for (int q = 0; q < nT; q++) umma_commit_elect(emptyA + 8 * stq[q]);
       }
     } else {
       for (int ks = 0; ks < ksteps; ks++) {
         for (int q = 0; q < nT; q++) {
-          mbar_wait(fullA + 8 * sa, pa);
+          mbar_wait_warp(fullA + 8 * sa, pa);
           alo[q] = a_lo0 + sa * a_stride16;
           stq[q] = sa;
           if (++sa == ra) { sa = 0; pa ^= 1; }
         }
-        mbar_wait(fullB + 8 * sb, pb);
+        mbar_wait_warp(fullB + 8 * sb, pb);
         tc_fence_after();
         const uint32_t b_lo = b_lo0 + sb * b_stride16;
 #pragma unroll
@@ -348,16 +355,16 @@ __device__ __forceinline__ void mma_role_dual(const TcArgs& a, uint32_t smemA, u
           if (q < nT) {
 #pragma unroll
             for (int k = 0; k < KK; k++)
-              umma_f16(d_tmem[q], desc64(alo[q] + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc,
+              umma_f16_elect(d_tmem[q], desc64(alo[q] + 2 * k, a_hi), desc64(b_lo + 2 * k, b_hi), idesc,
                        (ks == 0 && k == 0) ? 0u : 1u);
           }
         }
-        for (int q = 0; q < nT; q++) umma_commit(emptyA + 8 * stq[q]);
-        umma_commit(emptyB + 8 * sb);
+        for (int q = 0; q < nT; q++) umma_commit_elect(emptyA + 8 * stq[q]);
+        umma_commit_elect(emptyB + 8 * sb);
         if (++sb == rb) { sb = 0; pb ^= 1; }
       }
     }
-    for (int q = 0; q < nT; q++) umma_commit(tfull0 + 8 * acc[q]);  // both accumulators complete
+    for (int q = 0; q < nT; q++) umma_commit_elect(tfull0 + 8 * acc[q]);  // both accumulators complete
   }
 }
 
@@ -566,8 +573,8 @@ const __grid_constant__ TcArgs a) {
       }
     }
   } else if (warp == 1 || warp == 2) {
-    // ===================== MMA issuers =====================
-    if (lane == 0) {
+    // ===================== MMA issuers (whole warp, elect.sync issues) =====================
+    {
       const int issuer = warp - 1;
       if (a.dual) {
         if (issuer == 0) {

@@ -291,15 +291,15 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
           }
           __syncthreads();
           if (warp == 0) {
-            unsigned supp = misc[1] | ~vmask;
+            // serial resolve, one step per KEPT candidate: the lowest surviving index is kept and removes its row
+            unsigned alive = ~(misc[1] | ~vmask);
             unsigned keptmask = 0;
             int kn = kcount;
-            for (int i = 0; i < 32 && kn < max_det; i++) {
-              if (!((supp >> i) & 1u)) {
-                keptmask |= 1u << i;
-                supp |= frow[i];
-                kn++;
-              }
+            while (alive && kn < max_det) {
+              const int i = __ffs(alive) - 1;
+              keptmask |= 1u << i;
+              alive &= ~(frow[i] | (1u << i));
+              kn++;
             }
             if ((keptmask >> lane) & 1u) {
               ckey[s_begin + kcount + __popc(keptmask & ((1u << lane) - 1u))] = (cls << 12) | (unsigned)rank;
@@ -410,15 +410,14 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
       __syncthreads();
       // phase B: serial resolve inside the chunk (warp 0, every lane runs the same bit loop)
       if (warp == 0) {
-        unsigned supp = misc[1];
+        unsigned alive = ~misc[1] & (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));
         unsigned keepmask = 0;
         int kn = kept_n;
-        for (int i = 0; i < cnt && kn < max_det; i++) {
-          if (!((supp >> i) & 1u)) {
-            keepmask |= 1u << i;
-            supp |= rowmask[i];
-            kn++;
-          }
+        while (alive && kn < max_det) {  // one step per kept candidate
+          const int i = __ffs(alive) - 1;
+          keepmask |= 1u << i;
+          alive &= ~(rowmask[i] | (1u << i));
+          kn++;
         }
         if ((keepmask >> lane) & 1u) {
           const int pos = kept_n + __popc(keepmask & ((1u << lane) - 1u));
