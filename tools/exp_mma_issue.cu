@@ -14,23 +14,7 @@ using namespace yb;
 // mode 0: descriptors recomputed per MMA like conv_tc_kernel (runtime k loop)
 // mode 1: fully unrolled, descriptor low words precomputed, 4 MMAs per iteration
 // mode 2: the WHOLE warp runs the loop (warp-uniform descriptors -> uniform datapath), elect.sync picks the issuing lane
-__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
-}
-
-__global__ void __launch_bounds__(160, 1) issue_kernel(int N, int iters, int n_issuers, int mode, long long* out) {
+__global__ void __launch_bounds__(160, 1) issue_kernel(int N, int iters, int n_issuers, int mode, long long* out, int lay = 2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[4];
   __shared__ uint32_t tmem_slot;
@@ -56,8 +40,10 @@ __global__ void __launch_bounds__(160, 1) issue_kernel(int N, int iters, int n_i
     const uint32_t d = tmem + warp * 128;
     const long long t0 = clock64();
     for (int it = 0; it < iters; it++) {
-      const uint64_t ad = umma_desc(smA + (it & 3) * 128, 64, 2);
-      const uint64_t bd = umma_desc(smB, 64, 2);
+      // lay 2 = SWIZZLE_128B rows of 128 B (SBO 1024 B), 4 = 64B rows (SBO 512 B), 6 = 32B rows (SBO 256 B)
+      const uint32_t sbo = lay == 2 ? 64 : (lay == 4 ? 32 : 16);
+      const uint64_t ad = umma_desc(smA + (it & 3) * 128, sbo, lay);
+      const uint64_t bd = umma_desc(smB, sbo, lay);
 #pragma unroll
       for (int k = 0; k < 4; k++) umma_f16_elect(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (it | k) != 0);
     }
@@ -117,5 +103,15 @@ int main() {
         printf("mode=%d N=%3d issuers=%d : issue %.1f cyc/MMA, issue+drain %.1f cyc/MMA per issuer; aggregate %.1f cyc/MMA (ideal tensor %.1f)\n",
                mode, N, ni, h[0] / n_mma, h[1] / n_mma, h[1] / (n_mma * ni), 128.0 * N * 16 / 3868.0);
       }
+  for (int lay : {2, 4, 6})
+    for (int N : {16, 80, 160}) {
+      issue_kernel<<<1, 160, 50 * 1024>>>(N, iters, 1, 2, dout, lay);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+      long long h[8];
+      cudaMemcpy(h, dout, 64, cudaMemcpyDeviceToHost);
+      printf("layout=%d (rows of %d B) N=%3d one warp, elect: %.1f cyc/MMA (K-slices of one row per MMA: k*32 B offsets)\n", lay,
+             lay == 2 ? 128 : (lay == 4 ? 64 : 32), N, h[1] / (4.0 * iters));
+    }
   return 0;
 }

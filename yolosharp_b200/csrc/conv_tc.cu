@@ -74,6 +74,7 @@ struct TcArgs {
   // exact x / d for x*d < 2^40 as (x * ceil(2^40/d)) >> 40 (runtime integer division costs ~100+ cycles)
   uint64_t m_ntiles, m_tpi, m_tw, m_bw;
   int* tile_ctr;   // dynamic tile scheduler: global counter of this launch (nullptr = static round-robin)
+  int tile_batch;  // consecutive tiles drawn per atomicAdd (one counter address serves the whole grid)
   long long* dbg;  // optional timeline buffer (tools/exp_timeline.py); nullptr in production
 };
 
@@ -508,8 +509,10 @@ const __grid_constant__ TcArgs a) {
       int li = 0;
       const bool dyn = a.tile_ctr != nullptr;
       int tile = a.dual ? a.total_tiles : (int)blockIdx.x;
-      int nxt = a.total_tiles;
-      if (dyn && tile < a.total_tiles) nxt = (int)gridDim.x + atomicAdd(a.tile_ctr, 1);  // next tile, needed one tile later
+      int nxt = a.total_tiles, left = 1;
+      const int batch = a.tile_batch;
+      // the next batch of tiles is drawn one batch ahead, so the atomic's latency never sits on the load path
+      if (dyn && tile < a.total_tiles) nxt = (int)gridDim.x + atomicAdd(a.tile_ctr, batch);
       for (; tile < a.total_tiles; li++) {
         if (dyn) tq_publish(s_tile, &s_head, li, tile);
         const int rg = ni == 2 ? (li & 1) : 0;  // ring (= issuer) of this tile
@@ -561,8 +564,13 @@ const __grid_constant__ TcArgs a) {
           }
         }
         if (dyn) {
-          tile = nxt;
-          if (tile < a.total_tiles) nxt = (int)gridDim.x + atomicAdd(a.tile_ctr, 1);
+          if (--left > 0) {
+            tile++;
+          } else {
+            tile = nxt;
+            left = batch;
+            if (tile < a.total_tiles) nxt = (int)gridDim.x + atomicAdd(a.tile_ctr, batch);
+          }
         } else {
           tile += gridDim.x;
         }
@@ -949,7 +957,7 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     // resident weights at one CTA/SM beat re-fetched weights at two CTAs/SM
     if (occ == 2 && !small && !a.b_resident && a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= 200 * 1024) continue;
     if (a.b_resident) {
-      a.stages_a = (int)std::min<size_t>(a.mode != TC_TAP ? 6 : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
+      a.stages_a = (int)std::min<size_t>(a.mode != TC_TAP ? (a.chunks > 1 ? 8 : 6) : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
       a.stages_b = 0;
       plan->smem = (size_t)a.stages_a * a.a_stride + b_all + 1024;
     } else if (a.mode != TC_TAP) {
@@ -972,6 +980,14 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   plan->threads = 96 + 128 * a.n_groups;
   // two issuers need >= 2 slabs per half ring
   a.n_issuers = (a.stages_a >= 4 && (a.b_resident || a.stages_b >= 4)) ? 2 : 1;
+  {
+    // Each issuer owns half of the ring and the single producer fills tiles in order: when a half ring cannot hold
+    // one tile's activation slabs plus one of the next tile, the producer blocks inside a tile and the other
+    // issuer starves (timeline of the 3-slab 80->80 layers of v8x: the two issuers alternated instead of
+    // overlapping).  Such layers run one issuer on the whole ring.
+    const int slabs_per_tile = a.mode != TC_TAP ? a.chunks : a.ksteps;
+    if (a.n_issuers == 2 && a.stages_a / 2 < slabs_per_tile + 1) a.n_issuers = 1;
+  }
   if (a.n_issuers == 2) {
     a.stages_a &= ~1;  // even split
     if (!a.b_resident) a.stages_b &= ~1;
@@ -1065,6 +1081,9 @@ int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, int* tile_ctr, cu
   if (plan->p.share_sms && a.total_tiles <= 4 * plan->grid && a.ksteps * (a.BK >> 4) <= 40)
     grid = std::max(1, std::min(grid, (a.total_tiles + 2) / 3));
   if (a.dual && grid >= a.n_tiles) grid -= grid % a.n_tiles;  // tile t and t + grid must share their N tile
+  // one atomic per ~quarter of a CTA's share (every atomic of the grid hits the same L2 address: per-tile draws
+  // cost the 6400-tile layers 6-8 us)
+  a.tile_batch = std::max(1, std::min(8, a.total_tiles / (4 * grid)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(plan->threads);
