@@ -230,6 +230,20 @@ def test_fp16_layers_v8n(y, flags, label):
     assert float(err[:, 4:].max()) < 0.05, "class probabilities"
 
 
+@pytest.mark.parametrize("size", ["s", "x"])
+def test_fp16_layers_wide_models(y, size):
+    """v8s / v8x in tcgen05 mode, layer by layer: streamed weights with tile pairs (odd tile counts, several N tiles
+    per layer), ragged channel slabs (80 / 160 / 400 channels), dynamic tile queue."""
+    m = oracle_model("v8", "detect", size)
+    x = synth_image(3, 256, 320)
+    e = make_engine(y, m, "f16", 3, 256, 320, size)
+    pred, ref, worst = check_layers(e, m, x, 5e-2, 3, min_ops=55)
+    err = (pred - ref).abs()
+    assert float(err[:, :4].max()) < 6.0, ("boxes (pixels)", worst)
+    assert float(err[:, 4:].max()) < 0.08, ("class probabilities", worst)
+    e.close()
+
+
 def test_fp16_tcgen05_matches_cuda_core_twin(y):
     """Same fp16 operands, fp32 accumulation: the tensor-core kernel and its CUDA-core twin may only
     differ by summation order / fp16 rounding of near-ties."""
