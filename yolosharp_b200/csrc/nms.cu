@@ -54,6 +54,8 @@ __device__ __forceinline__ bool iou_gt(const Box5& a, const Box5& b, float thr) 
   const float xx2 = fminf(a.x2, b.x2), yy2 = fminf(a.y2, b.y2);
   const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
   const float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  // disjoint boxes (the common case): inter = 0 -> ovr = 0 or NaN, never > thr (thr >= 0); skip the IEEE division
+  if (!(w > 0.0f && h > 0.0f)) return false;
   const float inter = __fmul_rn(w, h);
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter));
   return ovr > thr;  // NaN (0/0) compares false, as on the CPU
@@ -232,9 +234,12 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
           const int rank = (int)(ck & 0xFFF);
           const float4 mine = valid ? fbox[rank] : make_float4(0.f, 0.f, 0.f, 0.f);
           bool sup = false;
-          for (int t = 0; t < kcount; t++) {
-            const float4 kb = fbox[ckey[s_begin + t] & 0xFFFu];
-            sup = sup || iou_gt4(kb, mine, iou_thres);
+          for (int t = 0; t < kcount; t += 2) {  // two kept boxes per step (independent chains)
+            const bool has1 = t + 1 < kcount;
+            const float4 k0 = fbox[ckey[s_begin + t] & 0xFFFu];
+            const float4 k1 = fbox[ckey[s_begin + (has1 ? t + 1 : t)] & 0xFFFu];
+            const bool s0 = iou_gt4(k0, mine, iou_thres), s1 = iou_gt4(k1, mine, iou_thres);
+            sup = sup || s0 || (has1 && s1);
           }
           unsigned alive = __ballot_sync(0xffffffffu, valid && !sup);
           unsigned keptmask = 0;
@@ -284,8 +289,16 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (lane == 0) frow[warp] = m;
             bool sup = false;
-            if (valid)
-              for (int k = warp; k < kcount; k += 32) sup = sup || iou_gt4(fbox[ckey[s_begin + k] & 0xFFFu], mine, iou_thres);
+            if (valid) {
+              // two kept boxes per step: independent smem chains and IoU arithmetic in flight
+              for (int k = warp; k < kcount; k += 64) {
+                const float4 k0 = fbox[ckey[s_begin + k] & 0xFFFu];
+                const bool has1 = k + 32 < kcount;
+                const float4 k1 = fbox[ckey[s_begin + (has1 ? k + 32 : k)] & 0xFFFu];
+                const bool s0 = iou_gt4(k0, mine, iou_thres), s1 = iou_gt4(k1, mine, iou_thres);
+                sup = sup || s0 || (has1 && s1);
+              }
+            }
             const unsigned sm = __ballot_sync(0xffffffffu, sup);
             if (lane == 0 && sm) atomicOr(&misc[1], sm);
           }
@@ -403,7 +416,11 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
         if (lane == 0) rowmask[warp] = m;
         bool sup = false;
         if (lane < cnt)
-          for (int k = warp; k < kept_n; k += 32) sup = sup || iou_gt(kept[k], mine, iou_thres);
+          for (int k = warp; k < kept_n; k += 64) {  // two kept boxes per step (independent chains)
+            const bool has1 = k + 32 < kept_n;
+            const bool s0 = iou_gt(kept[k], mine, iou_thres), s1 = iou_gt(kept[has1 ? k + 32 : k], mine, iou_thres);
+            sup = sup || s0 || (has1 && s1);
+          }
         const unsigned sm = __ballot_sync(0xffffffffu, sup);
         if (lane == 0 && sm) atomicOr(&misc[1], sm);
       }
