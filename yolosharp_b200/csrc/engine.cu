@@ -14,6 +14,7 @@
 #include <memory>
 #include <vector>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <tuple>
 
@@ -839,9 +840,14 @@ int32_t yb_create(const yb_config* cfg, yb_engine** out) {
   YB_CUDA_CHECK(cudaMalloc((void**)&e->arena, off));
   YB_CUDA_CHECK(cudaMemset(e->arena, 0, off));
   YB_CUDA_CHECK(cudaMalloc((void**)&e->tile_ctr, e->ops.size() * sizeof(int)));
-  YB_CUDA_CHECK(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
+  // forward kernels are captured at the highest stream priority: when the caller overlaps post-processing of the
+  // previous batch (NMS on another stream) with this forward, freed SMs go to the forward's CTAs first
+  int prio_least = 0, prio_greatest = 0;
+  YB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  if (getenv("YB_DEBUG_NO_PRIORITY")) prio_greatest = prio_least;  // experiments only
+  YB_CUDA_CHECK(cudaStreamCreateWithPriority(&e->capture_stream, cudaStreamNonBlocking, prio_greatest));
   for (int l = 1; l < yb_engine::kLanes; l++) {
-    YB_CUDA_CHECK(cudaStreamCreateWithFlags(&e->side[l], cudaStreamNonBlocking));
+    YB_CUDA_CHECK(cudaStreamCreateWithPriority(&e->side[l], cudaStreamNonBlocking, prio_greatest));
     YB_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done[l], cudaEventDisableTiming));
   }
   for (int l = 0; l < 3; l++) {
