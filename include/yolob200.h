@@ -128,6 +128,24 @@ int32_t yb_nms(const float* pred, int32_t batch, int32_t channels, int32_t ancho
                float conf_thres, float iou_thres, int32_t max_det, int32_t max_nms, int32_t max_wh,
                float* dets, int32_t* counts, int32_t* keep_idx, void* stream);
 
+/* Replaces (training path, first step): `v8DetectionLoss.forward` (Utils/Loss.cs:328-485) incl. the
+ * TaskAlignedAssigner (Utils/Tal.cs:13-311, topk = 10, alpha 0.5, beta 6), BboxLoss/DFLoss (Loss.cs:94-167) and the
+ * CIoU of Utils/Metrics.cs:36-111, on the raw outputs of the train-mode head (Head.cs:71-87):
+ *   boxes   dev float32 (B, 4*reg_max, A) distribution logits;  scores dev float32 (B, nc, A) class logits
+ *   height/width  network input size (anchor grid = strides 8/16/32, Tal.cs:313-335)
+ *   targets HOST float32 (n_targets, 6) rows [image index, class, x, y, w, h] with xywh normalised to [0,1]
+ *           (= cat(batch_idx, cls, bboxes), Loss.cs:424)
+ *   loss_items  dev float32 (3): box, cls, dfl after the gains = the reference's `loss.detach()` (Loss.cs:473)
+ *   grad_boxes / grad_scores  dev, same shapes as boxes / scores, or NULL: gradient of sum(loss_items) * B, i.e. of
+ *           the tensor the reference calls backward on (Loss.cs:473 returns loss * batch_size)
+ *   fg / gt_idx / target_score  optional dev outputs (B, A): uint8 foreground flag, int32 assigned target row inside
+ *           the image, float32 normalised alignment score - for tests and for the mask / pose losses later
+ * The assignment is computed from detached values, as in the reference. */
+int32_t yb_detection_loss(const float* boxes, const float* scores, int32_t batch, int32_t nc, int32_t reg_max,
+                          int32_t height, int32_t width, const float* targets_host, int32_t n_targets, int32_t topk,
+                          float hyp_box, float hyp_cls, float hyp_dfl, float* loss_items, float* grad_boxes,
+                          float* grad_scores, uint8_t* fg, int32_t* gt_idx, float* target_score, void* stream);
+
 /* Replaces: `Ops.process_mask(proto[i], rows[:,6:], rows[:,:4], shape, upsample:true)`
  * (Utils/Ops.cs:462-489, CUDA branch of crop_mask :437-447) for a whole batch.
  *   proto  dev float32 (B,32,mh,mw);  dets/counts as written by yb_nms with extra == 32

@@ -434,3 +434,65 @@ def test_v8_seg_pred_proto_masks(y, prec, size):
         ref_masks = oops.process_mask(proto[i].cpu(), out[i][:, 6:], out[i][:, :4], (H, W), upsample=True)
         agree = (masks[i, :n].bool() == ref_masks.bool()).float().mean().item()
         assert agree > 0.999, agree
+
+
+# ------------------------------------------------------------------ training path: detection loss + gradients
+def _loss_case(B=3, H=160, W=192, seed=0):
+    from oracle import loss as oloss
+    m = oracle_model("v8", "detect", "n").train()
+    x = synth_image(B, H, W, seed=seed)
+    with torch.no_grad():
+        _, preds = m(x)
+    g = torch.Generator().manual_seed(seed + 7)
+    n = 11
+    bidx = torch.randint(0, B, (n,), generator=g).sort().values  # the reference's collate keeps targets grouped by image
+    bidx[0] = 0
+    cls = torch.randint(0, 80, (n,), generator=g)
+    xy = torch.rand(n, 2, generator=g) * 0.6 + 0.2
+    wh = torch.rand(n, 2, generator=g) * 0.45 + 0.02
+    wh[1] = torch.tensor([0.03, 0.025])  # smaller than the smallest stride: widened by select_candidates_in_gts
+    batch = {"batch_idx": bidx.float(), "cls": cls.float(), "bboxes": torch.cat((xy, wh), 1)}
+    return oloss, preds, batch, H, W
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_detection_loss_and_gradients_vs_oracle(y, seed):
+    """yb_detection_loss vs autograd through the oracle restatement of v8DetectionLoss: loss items, assignment
+    (target scores), d(loss * batch)/d(boxes, scores).  fp32 on both sides; tolerance 1e-3 relative."""
+    oloss, preds, batch, H, W = _loss_case(seed=seed)
+    crit = oloss.V8DetectionLoss(80)
+    boxes = preds["boxes"].clone().requires_grad_(True)
+    scores = preds["scores"].clone().requires_grad_(True)
+    p = {"boxes": boxes, "scores": scores, "feats": preds["feats"]}
+    loss, items = crit(p, batch)
+    gb, gs = torch.autograd.grad(loss.sum(), (boxes, scores))
+    fg, gt_idx, tbox, tscore = crit.assign(p, batch)
+    tgt = torch.cat((batch["batch_idx"].view(-1, 1), batch["cls"].view(-1, 1), batch["bboxes"]), 1)
+    out = y.detection_loss(preds["boxes"].cuda().contiguous(), preds["scores"].cuda().contiguous(), tgt, H, W)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out["items"].cpu().numpy(), items.numpy(), rtol=1e-3, atol=1e-5)
+    ts_ref = tscore.sum(-1)
+    np.testing.assert_allclose(out["target_score"].cpu().numpy(), ts_ref.numpy(), rtol=1e-3, atol=1e-6)
+    pos = ts_ref > 0
+    assert int(pos.sum()) >= 20
+    assert torch.equal(out["fg"].cpu().bool()[pos], fg[pos])
+    assert torch.equal(out["gt_idx"].cpu().long()[pos], gt_idx[pos])
+    for got, ref, name in ((out["grad_scores"], gs, "scores"), (out["grad_boxes"], gb, "boxes")):
+        got = got.cpu()
+        scale = float(ref.abs().max())
+        assert scale > 0
+        err = float((got - ref).abs().max())
+        assert err < 2e-3 * scale, (name, err, scale)
+
+
+def test_detection_loss_without_targets(y):
+    oloss, preds, batch, H, W = _loss_case(B=2, H=96, W=96)
+    crit = oloss.V8DetectionLoss(80)
+    empty = {"batch_idx": torch.zeros(0), "cls": torch.zeros(0), "bboxes": torch.zeros(0, 4)}
+    _, items = crit(preds, empty)
+    out = y.detection_loss(preds["boxes"].cuda().contiguous(), preds["scores"].cuda().contiguous(), torch.zeros(0, 6), H, W)
+    np.testing.assert_allclose(out["items"].cpu().numpy(), items.numpy(), rtol=1e-3, atol=1e-6)
+    assert float(out["grad_boxes"].abs().max()) == 0.0 and int(out["fg"].sum()) == 0
+    with pytest.raises(y.YbError):
+        y.detection_loss(preds["boxes"].cuda().contiguous(), preds["scores"].cuda().contiguous(),
+                         torch.tensor([[5.0, 1, 0.5, 0.5, 0.1, 0.1]]), H, W)

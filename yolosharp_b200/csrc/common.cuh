@@ -108,6 +108,10 @@ int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const __h
 // ---- nms.cu ----
 int nms_launch(const float* pred, int B, int C, int A, int nc, float conf, float iou, int max_det,
                int max_nms, int max_wh, float* dets, int* counts, int* keep_idx, cudaStream_t s);
+int detection_loss_launch(const float* boxes, const float* scores, int B, int nc, int reg_max, int H, int W,
+                          const float* targets_host, int n_targets, int topk, float hyp_box, float hyp_cls, float hyp_dfl,
+                          float* loss_items, float* grad_boxes, float* grad_scores, unsigned char* fg_out, int* gt_idx_out,
+                          float* tscore_out, cudaStream_t s);
 int masks_launch(const float* proto, const float* dets, const int* counts, int B, int max_det, int nm,
                  int mh, int mw, int H, int W, uint8_t* masks, cudaStream_t s);
 

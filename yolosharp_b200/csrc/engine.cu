@@ -1065,6 +1065,25 @@ int32_t yb_masks(const float* proto, const float* dets, const int32_t* counts, i
   return masks_launch(proto, dets, counts, batch, max_det, nm, mh, mw, height, width, masks, (cudaStream_t)stream);
 }
 
+int32_t yb_detection_loss(const float* boxes, const float* scores, int32_t batch, int32_t nc, int32_t reg_max,
+                          int32_t height, int32_t width, const float* targets_host, int32_t n_targets, int32_t topk,
+                          float hyp_box, float hyp_cls, float hyp_dfl, float* loss_items, float* grad_boxes,
+                          float* grad_scores, uint8_t* fg, int32_t* gt_idx, float* target_score, void* stream) {
+  if (!boxes || !scores || !loss_items || (n_targets > 0 && !targets_host)) {
+    set_error("yb_detection_loss: null argument");
+    return YB_ERR_INVALID_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("yb_detection_loss: no CUDA device");
+    return YB_ERR_NO_DEVICE;
+  }
+  return detection_loss_launch(boxes, scores, batch, nc, reg_max, height, width, targets_host, n_targets, topk, hyp_box,
+                               hyp_cls, hyp_dfl, loss_items, grad_boxes, grad_scores, fg, gt_idx, target_score,
+                               (cudaStream_t)stream);
+}
+
 static int32_t predict_enqueue(yb_engine* e, yb_engine::Stage& st, const uint8_t* images_host, int32_t batch,
                                float conf_thres, float iou_thres, int32_t max_det, float* dets_host,
                                int32_t* counts_host, cudaStream_t s, const char* who) {

@@ -180,3 +180,30 @@ def masks(proto, dets, counts, height, width, stream=None, out=None):
     L.check(L.lib().yb_masks(C.c_void_p(proto.data_ptr()), C.c_void_p(dets.data_ptr()), C.c_void_p(counts.data_ptr()), B,
                              max_det, nm, mh, mw, height, width, C.c_void_p(out.data_ptr()), _stream_ptr(stream)))
     return out
+
+
+def detection_loss(boxes, scores, targets, height, width, reg_max=16, topk=10, hyp_box=7.5, hyp_cls=0.5, hyp_dfl=1.5,
+                   want_grad=True, stream=None):
+    """yb_detection_loss: v8DetectionLoss (Utils/Loss.cs:328-485) on the raw train-mode head outputs.
+    boxes (B, 4*reg_max, A), scores (B, nc, A): CUDA float32;  targets: (n, 6) rows [image, cls, x, y, w, h]
+    (normalised xywh), any device / dtype (copied to host float32).
+    -> dict(items (3,), grad_boxes, grad_scores, fg (B, A) uint8, gt_idx (B, A) int32, target_score (B, A))."""
+    assert boxes.is_cuda and scores.is_cuda and boxes.dtype == torch.float32 and scores.dtype == torch.float32
+    assert boxes.is_contiguous() and scores.is_contiguous()
+    B, c4, A = boxes.shape
+    nc = scores.shape[1]
+    assert c4 == 4 * reg_max and scores.shape[0] == B and scores.shape[2] == A
+    t = torch.as_tensor(targets, dtype=torch.float32).reshape(-1, 6).cpu().contiguous()
+    items = torch.empty(3, dtype=torch.float32, device=boxes.device)
+    gb = torch.empty_like(boxes) if want_grad else None
+    gs = torch.empty_like(scores) if want_grad else None
+    fg = torch.empty((B, A), dtype=torch.uint8, device=boxes.device)
+    gi = torch.empty((B, A), dtype=torch.int32, device=boxes.device)
+    ts = torch.empty((B, A), dtype=torch.float32, device=boxes.device)
+    L.check(L.lib().yb_detection_loss(
+        C.c_void_p(boxes.data_ptr()), C.c_void_p(scores.data_ptr()), B, nc, reg_max, height, width,
+        C.c_void_p(t.data_ptr()) if t.numel() else None, t.shape[0], topk, hyp_box, hyp_cls, hyp_dfl,
+        C.c_void_p(items.data_ptr()), C.c_void_p(gb.data_ptr()) if want_grad else None,
+        C.c_void_p(gs.data_ptr()) if want_grad else None, C.c_void_p(fg.data_ptr()), C.c_void_p(gi.data_ptr()),
+        C.c_void_p(ts.data_ptr()), _stream_ptr(stream)))
+    return {"items": items, "grad_boxes": gb, "grad_scores": gs, "fg": fg, "gt_idx": gi, "target_score": ts}
