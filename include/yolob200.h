@@ -146,6 +146,27 @@ int32_t yb_detection_loss(const float* boxes, const float* scores, int32_t batch
                           float hyp_box, float hyp_cls, float hyp_dfl, float* loss_items, float* grad_boxes,
                           float* grad_scores, uint8_t* fg, int32_t* gt_idx, float* target_score, void* stream);
 
+/* Replaces (training path): BatchNorm2d in TRAIN mode followed by SiLU inside every `Conv` block
+ * (Modules/Convs.cs:36-56 under `yolo.train()`, YoloBaseTaskModel.cs:299,325; BatchNorm2d(eps 1e-3, momentum 0.03)).
+ *   z       dev float32, M = B*H*W rows x C channels, row pitch `pitch` elements (NHWC conv output)
+ *   y       dev float32 (M, C) with row pitch `ypitch`: act ? SiLU(bn(z)) : bn(z)
+ *   running_mean / running_var  dev (C), updated in place with `momentum` and the UNBIASED batch variance, or NULL
+ *   save_mean / save_invstd     dev (C) outputs the backward pass needs */
+int32_t yb_bn_silu_train_forward(const float* z, int64_t rows, int32_t channels, int32_t pitch, const float* gamma,
+                                 const float* beta, float eps, float momentum, int32_t act, float* running_mean,
+                                 float* running_var, float* y, int32_t ypitch, float* save_mean, float* save_invstd,
+                                 void* stream);
+/* Backward of the above: dy (M, C) -> dz (M, C), dgamma (C), dbeta (C). */
+int32_t yb_bn_silu_backward(const float* z, const float* dy, int64_t rows, int32_t channels, int32_t pitch,
+                            int32_t dpitch, const float* gamma, const float* beta, const float* save_mean,
+                            const float* save_invstd, int32_t act, float* dz, int32_t zpitch, float* dgamma,
+                            float* dbeta, void* stream);
+/* Replaces: one `AdamW.step()` over a flat parameter group (YoloBaseTaskModel.cs:142-160 builds
+ * AdamW(lr = round(0.01/(4+nc), 6), weight_decay 5e-4, default betas 0.9 / 0.999, eps 1e-8); Utils/Amp.cs:260-286
+ * calls it).  p, g, m, v: dev float32 (n); step counts from 1. */
+int32_t yb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, void* stream);
+
 /* Replaces: `Ops.process_mask(proto[i], rows[:,6:], rows[:,:4], shape, upsample:true)`
  * (Utils/Ops.cs:462-489, CUDA branch of crop_mask :437-447) for a whole batch.
  *   proto  dev float32 (B,32,mh,mw);  dets/counts as written by yb_nms with extra == 32

@@ -496,3 +496,45 @@ def test_detection_loss_without_targets(y):
     with pytest.raises(y.YbError):
         y.detection_loss(preds["boxes"].cuda().contiguous(), preds["scores"].cuda().contiguous(),
                          torch.tensor([[5.0, 1, 0.5, 0.5, 0.1, 0.1]]), H, W)
+
+
+# ------------------------------------------------------------------ training path: BatchNorm(train)+SiLU, AdamW
+@pytest.mark.parametrize("shape,act", [((4, 40, 52, 32), True), ((2, 20, 20, 256), True), ((3, 7, 9, 80), False)])
+def test_bn_silu_train_forward_backward_vs_torch(y, shape, act):
+    """Train-mode BatchNorm2d(eps 1e-3, momentum 0.03) + SiLU of the Conv block (Convs.cs:36-56) against
+    torch.nn.functional.batch_norm(training=True) + autograd, NHWC storage."""
+    g = torch.Generator().manual_seed(sum(shape))
+    Cc = shape[-1]
+    z = (torch.randn(shape, generator=g) * 1.7 + torch.randn(Cc, generator=g) * 3).contiguous()
+    gamma, beta = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g) * 0.3
+    rm, rv = torch.randn(Cc, generator=g) * 0.1, torch.rand(Cc, generator=g) + 0.5
+    dy = torch.randn(shape, generator=g)
+    zt = z.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    gt, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    u = torch.nn.functional.batch_norm(zt, rm_ref, rv_ref, gt, bt, training=True, momentum=0.03, eps=1e-3)
+    yt = torch.nn.functional.silu(u) if act else u
+    yt.backward(dy.permute(0, 3, 1, 2))
+    rm_d, rv_d = rm.cuda(), rv.cuda()
+    out, mean, invstd = y.bn_silu_train_forward(z.cuda(), gamma.cuda(), beta.cuda(), rm_d, rv_d, act=act)
+    np.testing.assert_allclose(out.cpu().numpy(), yt.detach().permute(0, 2, 3, 1).numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(rm_d.cpu().numpy(), rm_ref.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rv_d.cpu().numpy(), rv_ref.numpy(), rtol=1e-4, atol=1e-6)
+    dz, dg, db = y.bn_silu_backward(z.cuda(), dy.cuda().contiguous(), gamma.cuda(), beta.cuda(), mean, invstd, act=act)
+    np.testing.assert_allclose(dz.cpu().numpy(), zt.grad.permute(0, 2, 3, 1).numpy(), rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(dg.cpu().numpy(), gt.grad.numpy(), rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(db.cpu().numpy(), bt.grad.numpy(), rtol=1e-3, atol=1e-3)
+
+
+def test_adamw_step_vs_torch(y):
+    g = torch.Generator().manual_seed(5)
+    p0 = torch.randn(10007, generator=g)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([p_ref], lr=1.19e-4, weight_decay=5e-4)
+    p, m, v = p0.cuda(), torch.zeros(10007, device="cuda"), torch.zeros(10007, device="cuda")
+    for step in range(1, 4):
+        grad = torch.randn(10007, generator=g) * 0.1
+        p_ref.grad = grad.clone()
+        opt.step()
+        y.adamw_step(p, grad.cuda(), m, v, step, 1.19e-4)
+        np.testing.assert_allclose(p.cpu().numpy(), p_ref.detach().numpy(), rtol=1e-5, atol=1e-6)

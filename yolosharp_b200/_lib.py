@@ -41,6 +41,11 @@ SIGNATURES = {
     "yb_masks": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "yb_detection_loss": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_f32, c_f32, c_f32,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "yb_bn_silu_train_forward": (c_i32, [c_vp, C.c_int64, c_i32, c_i32, c_vp, c_vp, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp, c_i32,
+                                         c_vp, c_vp, c_vp]),
+    "yb_bn_silu_backward": (c_i32, [c_vp, c_vp, C.c_int64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp,
+                                    c_vp, c_vp]),
+    "yb_adamw_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, C.c_int64, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp]),
     "yb_predict_u8": (c_i32, [c_vp, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp]),
     "yb_predict_u8_submit": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp]),
     "yb_predict_u8_wait": (c_i32, [c_vp, c_i32]),

@@ -1,0 +1,203 @@
+// Train-mode BatchNorm2d + SiLU of the reference's Conv block (Modules/Convs.cs:36-56 with `yolo.train()`,
+// YoloBaseTaskModel.cs:299,325): forward with batch statistics + running-statistics update, and backward.
+//
+//   forward   z (M = B*H*W rows, C channels, NHWC fp32) -> mean_c, var_c over the M rows (biased, two-pass),
+//             y = SiLU(gamma * (z - mean) * invstd + beta), invstd = 1/sqrt(var + eps);
+//             running_mean = (1-m) running_mean + m mean, running_var = (1-m) running_var + m var * M/(M-1)
+//             (PyTorch BatchNorm2d semantics; the reference builds BatchNorm2d(eps 1e-3, momentum 0.03))
+//   backward  u = gamma * xhat + beta, g = dy * SiLU'(u);  dbeta = sum g, dgamma = sum g*xhat,
+//             dz = gamma * invstd * (g - dbeta/M - xhat * dgamma/M)
+//
+// All three passes are column reductions over a tall NHWC matrix: every block owns 32 channels x a slab of rows
+// (32 x 8 threads, 128-byte coalesced rows), writes one partial per (slab, channel), and a second tiny kernel folds
+// the partials in a fixed order - deterministic, no atomics.  HBM-bound: forward reads z twice (+1 in the
+// elementwise pass) and writes y once; backward reads z, dy twice and writes dz.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace yb {
+
+namespace {
+
+constexpr int BN_TX = 32, BN_TY = 8, BN_ROWS_PER_BLOCK = 256;
+
+__device__ __forceinline__ float silu_f(float u) { return u / (1.f + expf(-u)); }
+__device__ __forceinline__ float silu_grad(float u) {
+  const float s = 1.f / (1.f + expf(-u));
+  return s * (1.f + u * (1.f - s));
+}
+
+// mode 0: sum z                      -> p0
+// mode 1: sum (z - mean)^2           -> p0
+// mode 2: sum g, sum g * xhat        -> p0, p1   (g = dy * SiLU'(gamma*xhat+beta))
+__global__ void __launch_bounds__(BN_TX* BN_TY) bn_partial_kernel(int mode, int act, const float* __restrict__ z, const float* __restrict__ dy,
+                                                                long long M, int C, int pitch, int dpitch,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float* __restrict__ p0, float* __restrict__ p1) {
+  const int c = blockIdx.x * BN_TX + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * BN_ROWS_PER_BLOCK;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    const float mu = mode ? mean[c] : 0.f;
+    const float is = mode == 2 ? invstd[c] : 0.f, ga = mode == 2 ? gamma[c] : 0.f, be = mode == 2 ? beta[c] : 0.f;
+    for (long long r = r0 + threadIdx.y; r < min(M, r0 + BN_ROWS_PER_BLOCK); r += BN_TY) {
+      const float v = z[r * pitch + c];
+      if (mode == 0) {
+        a0 += v;
+      } else if (mode == 1) {
+        const float d = v - mu;
+        a0 += d * d;
+      } else {
+        const float xh = (v - mu) * is;
+        const float g = dy[r * dpitch + c] * (act ? silu_grad(ga * xh + be) : 1.f);
+        a0 += g;
+        a1 += g * xh;
+      }
+    }
+  }
+  __shared__ float s0[BN_TY][BN_TX], s1[BN_TY][BN_TX];
+  s0[threadIdx.y][threadIdx.x] = a0;
+  s1[threadIdx.y][threadIdx.x] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int k = 0; k < BN_TY; k++) { t0 += s0[k][threadIdx.x]; t1 += s1[k][threadIdx.x]; }
+    p0[(size_t)blockIdx.y * C + c] = t0;
+    if (mode == 2) p1[(size_t)blockIdx.y * C + c] = t1;
+  }
+}
+
+// fold the per-slab partials in slab order; step 0 -> mean, step 1 -> var / invstd / running stats, step 2 -> dgamma, dbeta
+__global__ void bn_finish_kernel(int step, const float* __restrict__ p0, const float* __restrict__ p1, int slabs, int C,
+                                 long long M, float eps, float momentum, float* __restrict__ mean, float* __restrict__ invstd,
+                                 float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ dgamma,
+                                 float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t0 = 0.f, t1 = 0.f;
+  for (int s = 0; s < slabs; s++) {
+    t0 += p0[(size_t)s * C + c];
+    if (step == 2) t1 += p1[(size_t)s * C + c];
+  }
+  if (step == 0) {
+    mean[c] = t0 / (float)M;
+  } else if (step == 1) {
+    const float var = t0 / (float)M;  // biased: used for normalisation
+    invstd[c] = 1.f / sqrtf(var + eps);
+    if (running_mean) {
+      const float unbiased = M > 1 ? t0 / (float)(M - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean[c];
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+  } else {
+    dbeta[c] = t0;
+    dgamma[c] = t1;
+  }
+}
+
+__global__ void bn_silu_apply_kernel(const float* __restrict__ z, long long M, int C, int pitch, int opitch,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, int act, float* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C) return;
+  const long long r = i / C;
+  const int c = (int)(i - r * C);
+  const float u = gamma[c] * (z[r * pitch + c] - mean[c]) * invstd[c] + beta[c];
+  y[r * opitch + c] = act ? silu_f(u) : u;
+}
+
+__global__ void bn_silu_dz_kernel(const float* __restrict__ z, const float* __restrict__ dy, long long M, int C, int pitch, int dpitch,
+                                  int opitch, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                  const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dz) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C) return;
+  const long long r = i / C;
+  const int c = (int)(i - r * C);
+  const float xh = (z[r * pitch + c] - mean[c]) * invstd[c];
+  const float g = dy[r * dpitch + c] * (act ? silu_grad(gamma[c] * xh + beta[c]) : 1.f);
+  const float inv_m = 1.f / (float)M;
+  dz[r * opitch + c] = gamma[c] * invstd[c] * (g - dbeta[c] * inv_m - xh * dgamma[c] * inv_m);
+}
+
+}  // namespace
+
+int bn_silu_train_forward(const float* z, long long M, int C, int pitch, const float* gamma, const float* beta, float eps,
+                          float momentum, int act, float* running_mean, float* running_var, float* y, int ypitch,
+                          float* save_mean, float* save_invstd, cudaStream_t s) {
+  if (M <= 0 || C <= 0 || pitch < C || ypitch < C) {
+    set_error("yb_bn_silu_train_forward: bad shape");
+    return YB_ERR_SHAPE;
+  }
+  const int slabs = (int)((M + BN_ROWS_PER_BLOCK - 1) / BN_ROWS_PER_BLOCK);
+  float* part = nullptr;
+  YB_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)slabs * C * sizeof(float), s));
+  const dim3 grid((C + BN_TX - 1) / BN_TX, slabs), block(BN_TX, BN_TY);
+  const int fb = 128, fg = (C + fb - 1) / fb;
+  bn_partial_kernel<<<grid, block, 0, s>>>(0, act, z, nullptr, M, C, pitch, 0, nullptr, nullptr, nullptr, nullptr, part, nullptr);
+  bn_finish_kernel<<<fg, fb, 0, s>>>(0, part, nullptr, slabs, C, M, eps, momentum, save_mean, save_invstd, nullptr, nullptr, nullptr,
+                                     nullptr);
+  bn_partial_kernel<<<grid, block, 0, s>>>(1, act, z, nullptr, M, C, pitch, 0, save_mean, nullptr, nullptr, nullptr, part, nullptr);
+  bn_finish_kernel<<<fg, fb, 0, s>>>(1, part, nullptr, slabs, C, M, eps, momentum, save_mean, save_invstd, running_mean, running_var,
+                                     nullptr, nullptr);
+  const long long total = M * C;
+  bn_silu_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, M, C, pitch, ypitch, save_mean, save_invstd, gamma, beta, act, y);
+  YB_CUDA_CHECK(cudaGetLastError());
+  YB_CUDA_CHECK(cudaFreeAsync(part, s));
+  return YB_OK;
+}
+
+int bn_silu_backward(const float* z, const float* dy, long long M, int C, int pitch, int dpitch, const float* gamma,
+                     const float* beta, const float* save_mean, const float* save_invstd, int act, float* dz, int zpitch,
+                     float* dgamma, float* dbeta, cudaStream_t s) {
+  if (M <= 0 || C <= 0 || pitch < C || dpitch < C || zpitch < C) {
+    set_error("yb_bn_silu_backward: bad shape");
+    return YB_ERR_SHAPE;
+  }
+  const int slabs = (int)((M + BN_ROWS_PER_BLOCK - 1) / BN_ROWS_PER_BLOCK);
+  float* part = nullptr;
+  YB_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)2 * slabs * C * sizeof(float), s));
+  const dim3 grid((C + BN_TX - 1) / BN_TX, slabs), block(BN_TX, BN_TY);
+  bn_partial_kernel<<<grid, block, 0, s>>>(2, act, z, dy, M, C, pitch, dpitch, save_mean, save_invstd, gamma, beta, part,
+                                          part + (size_t)slabs * C);
+  bn_finish_kernel<<<(C + 127) / 128, 128, 0, s>>>(2, part, part + (size_t)slabs * C, slabs, C, M, 0.f, 0.f, nullptr, nullptr, nullptr,
+                                                   nullptr, dgamma, dbeta);
+  const long long total = M * C;
+  bn_silu_dz_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, dy, M, C, pitch, dpitch, zpitch, save_mean, save_invstd, gamma, beta,
+                                                                act, dgamma, dbeta, dz);
+  YB_CUDA_CHECK(cudaGetLastError());
+  YB_CUDA_CHECK(cudaFreeAsync(part, s));
+  return YB_OK;
+}
+
+// AdamW step (torch.optim.AdamW semantics, the optimizer the reference builds in YoloBaseTaskModel.cs:142-160):
+//   p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  float pi = p[i] * (1.f - lr * wd);
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
+int adamw_step(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2, float eps,
+               float wd, cudaStream_t s) {
+  if (n <= 0 || step < 1) {
+    set_error("yb_adamw_step: need n > 0 and step >= 1");
+    return YB_ERR_INVALID_ARG;
+  }
+  const float bc1 = 1.f - powf(b1, (float)step), bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
+  adamw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, bc2_sqrt);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return YB_OK;
+}
+
+}  // namespace yb

@@ -1084,6 +1084,52 @@ int32_t yb_detection_loss(const float* boxes, const float* scores, int32_t batch
                                (cudaStream_t)stream);
 }
 
+static bool have_device(const char* who) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error(std::string(who) + ": no CUDA device");
+    return false;
+  }
+  return true;
+}
+
+int32_t yb_bn_silu_train_forward(const float* z, int64_t rows, int32_t channels, int32_t pitch, const float* gamma,
+                                 const float* beta, float eps, float momentum, int32_t act, float* running_mean,
+                                 float* running_var, float* y, int32_t ypitch, float* save_mean, float* save_invstd,
+                                 void* stream) {
+  if (!z || !gamma || !beta || !y || !save_mean || !save_invstd || (!running_mean) != (!running_var)) {
+    set_error("yb_bn_silu_train_forward: null argument");
+    return YB_ERR_INVALID_ARG;
+  }
+  if (!have_device("yb_bn_silu_train_forward")) return YB_ERR_NO_DEVICE;
+  return bn_silu_train_forward(z, rows, channels, pitch, gamma, beta, eps, momentum, act, running_mean, running_var, y, ypitch,
+                               save_mean, save_invstd, (cudaStream_t)stream);
+}
+
+int32_t yb_bn_silu_backward(const float* z, const float* dy, int64_t rows, int32_t channels, int32_t pitch,
+                            int32_t dpitch, const float* gamma, const float* beta, const float* save_mean,
+                            const float* save_invstd, int32_t act, float* dz, int32_t zpitch, float* dgamma,
+                            float* dbeta, void* stream) {
+  if (!z || !dy || !gamma || !beta || !save_mean || !save_invstd || !dz || !dgamma || !dbeta) {
+    set_error("yb_bn_silu_backward: null argument");
+    return YB_ERR_INVALID_ARG;
+  }
+  if (!have_device("yb_bn_silu_backward")) return YB_ERR_NO_DEVICE;
+  return bn_silu_backward(z, dy, rows, channels, pitch, dpitch, gamma, beta, save_mean, save_invstd, act, dz, zpitch, dgamma,
+                          dbeta, (cudaStream_t)stream);
+}
+
+int32_t yb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, void* stream) {
+  if (!p || !g || !m || !v) {
+    set_error("yb_adamw_step: null argument");
+    return YB_ERR_INVALID_ARG;
+  }
+  if (!have_device("yb_adamw_step")) return YB_ERR_NO_DEVICE;
+  return adamw_step(p, g, m, v, n, step, lr, beta1, beta2, eps, weight_decay, (cudaStream_t)stream);
+}
+
 static int32_t predict_enqueue(yb_engine* e, yb_engine::Stage& st, const uint8_t* images_host, int32_t batch,
                                float conf_thres, float iou_thres, int32_t max_det, float* dets_host,
                                int32_t* counts_host, cudaStream_t s, const char* who) {

@@ -207,3 +207,43 @@ def detection_loss(boxes, scores, targets, height, width, reg_max=16, topk=10, h
         C.c_void_p(gs.data_ptr()) if want_grad else None, C.c_void_p(fg.data_ptr()), C.c_void_p(gi.data_ptr()),
         C.c_void_p(ts.data_ptr()), _stream_ptr(stream)))
     return {"items": items, "grad_boxes": gb, "grad_scores": gs, "fg": fg, "gt_idx": gi, "target_score": ts}
+
+
+def bn_silu_train_forward(z, gamma, beta, running_mean=None, running_var=None, eps=1e-3, momentum=0.03, act=True, stream=None):
+    """yb_bn_silu_train_forward on an NHWC tensor z (..., C) float32 (any leading dims, contiguous).
+    -> (y, save_mean, save_invstd); running stats are updated in place when given."""
+    assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous()
+    Cc = z.shape[-1]
+    M = z.numel() // Cc
+    y = torch.empty_like(z)
+    mean = torch.empty(Cc, dtype=torch.float32, device=z.device)
+    invstd = torch.empty_like(mean)
+    L.check(L.lib().yb_bn_silu_train_forward(
+        C.c_void_p(z.data_ptr()), M, Cc, Cc, C.c_void_p(gamma.data_ptr()), C.c_void_p(beta.data_ptr()), eps, momentum, int(act),
+        C.c_void_p(running_mean.data_ptr()) if running_mean is not None else None,
+        C.c_void_p(running_var.data_ptr()) if running_var is not None else None, C.c_void_p(y.data_ptr()), Cc,
+        C.c_void_p(mean.data_ptr()), C.c_void_p(invstd.data_ptr()), _stream_ptr(stream)))
+    return y, mean, invstd
+
+
+def bn_silu_backward(z, dy, gamma, beta, save_mean, save_invstd, act=True, stream=None):
+    """yb_bn_silu_backward -> (dz, dgamma, dbeta)."""
+    assert z.is_cuda and dy.is_cuda and z.is_contiguous() and dy.is_contiguous() and z.shape == dy.shape
+    Cc = z.shape[-1]
+    M = z.numel() // Cc
+    dz = torch.empty_like(z)
+    dg = torch.empty(Cc, dtype=torch.float32, device=z.device)
+    db = torch.empty_like(dg)
+    L.check(L.lib().yb_bn_silu_backward(
+        C.c_void_p(z.data_ptr()), C.c_void_p(dy.data_ptr()), M, Cc, Cc, Cc, C.c_void_p(gamma.data_ptr()), C.c_void_p(beta.data_ptr()),
+        C.c_void_p(save_mean.data_ptr()), C.c_void_p(save_invstd.data_ptr()), int(act), C.c_void_p(dz.data_ptr()), Cc,
+        C.c_void_p(dg.data_ptr()), C.c_void_p(db.data_ptr()), _stream_ptr(stream)))
+    return dz, dg, db
+
+
+def adamw_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=5e-4, stream=None):
+    """yb_adamw_step on flat float32 CUDA tensors (in place on p, m, v)."""
+    for t in (p, g, m, v):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
+    L.check(L.lib().yb_adamw_step(C.c_void_p(p.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(m.data_ptr()),
+                                  C.c_void_p(v.data_ptr()), p.numel(), step, lr, beta1, beta2, eps, weight_decay, _stream_ptr(stream)))
