@@ -167,6 +167,15 @@ int32_t yb_bn_silu_backward(const float* z, const float* dy, int64_t rows, int32
 int32_t yb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr, float beta1,
                       float beta2, float eps, float weight_decay, void* stream);
 
+/* Replaces (training path, fp32 parity kernels): the autograd backward of `Conv2d(bias: false)` inside every Conv
+ * block (Modules/Convs.cs:44; libtorch dgrad / wgrad behind `loss.backward()`, Utils/Amp.cs:260-286).
+ *   x  dev float32 NHWC (N, H, W, Cin);  dz dev float32 NHWC (N, Ho, Wo, Cout), Ho = (H + 2 pad - k)/stride + 1
+ *   w  dev float32 in the checkpoint layout (Cout, Cin, k, k);  dx like x;  dw like w */
+int32_t yb_conv_backward_data(const float* dz, const float* w, int32_t n, int32_t height, int32_t width, int32_t cin,
+                              int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dx, void* stream);
+int32_t yb_conv_backward_weight(const float* x, const float* dz, int32_t n, int32_t height, int32_t width, int32_t cin,
+                                int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dw, void* stream);
+
 /* Replaces: `Ops.process_mask(proto[i], rows[:,6:], rows[:,:4], shape, upsample:true)`
  * (Utils/Ops.cs:462-489, CUDA branch of crop_mask :437-447) for a whole batch.
  *   proto  dev float32 (B,32,mh,mw);  dets/counts as written by yb_nms with extra == 32

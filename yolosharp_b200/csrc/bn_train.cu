@@ -201,3 +201,95 @@ int adamw_step(float* p, const float* g, float* m, float* v, long long n, int st
 }
 
 }  // namespace yb
+
+// ------------------------------------------------------------------------------------------
+// Convolution backward, fp32 CUDA-core parity path (the training-side twin of conv_generic_kernel: correct and
+// deterministic first; the tcgen05 dgrad / wgrad kernels of the throughput path will be checked against it).
+//   dz (N, Ho, Wo, Cout) NHWC, weights in the reference's checkpoint layout (Cout, Cin, k, k)
+//   dgrad  dx[n,h,w,ci] = sum_{kh,kw,co} dz[n,(h+pad-kh)/s,(w+pad-kw)/s,co] * W[co,ci,kh,kw]   (only exact divisions)
+//   wgrad  dW[co,ci,kh,kw] = sum_{n,ho,wo} dz[n,ho,wo,co] * x[n,ho*s+kh-pad,wo*s+kw-pad,ci]
+// ------------------------------------------------------------------------------------------
+namespace yb {
+
+namespace {
+
+__global__ void conv_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ w, int N, int H, int W, int Cin, int Ho,
+                                  int Wo, int Cout, int k, int stride, int pad, float* __restrict__ dx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * H * W * Cin;
+  if (i >= total) return;
+  const int ci = (int)(i % Cin);
+  long long p = i / Cin;
+  const int x = (int)(p % W);
+  p /= W;
+  const int y = (int)(p % H);
+  const int n = (int)(p / H);
+  float acc = 0.f;
+  for (int kh = 0; kh < k; kh++) {
+    const int hn = y + pad - kh;
+    if (hn < 0 || hn % stride) continue;
+    const int ho = hn / stride;
+    if (ho >= Ho) continue;
+    for (int kw = 0; kw < k; kw++) {
+      const int wn = x + pad - kw;
+      if (wn < 0 || wn % stride) continue;
+      const int wo = wn / stride;
+      if (wo >= Wo) continue;
+      const float* dzp = dz + (((size_t)n * Ho + ho) * Wo + wo) * Cout;
+      const float* wp = w + ((size_t)ci * k + kh) * k + kw;  // + co * Cin*k*k
+      for (int co = 0; co < Cout; co++) acc = fmaf(dzp[co], wp[(size_t)co * Cin * k * k], acc);
+    }
+  }
+  dx[i] = acc;
+}
+
+// one block per (co, tap): threads over ci, serial over pixels (deterministic sums)
+__global__ void __launch_bounds__(128) conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, int N, int H, int W,
+                                                        int Cin, int Ho, int Wo, int Cout, int k, int stride, int pad,
+                                                        float* __restrict__ dw) {
+  const int tap = blockIdx.x, co = blockIdx.y;
+  const int kh = tap / k, kw = tap - kh * k;
+  for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
+    float acc = 0.f;
+    for (int n = 0; n < N; n++)
+      for (int ho = 0; ho < Ho; ho++) {
+        const int hi = ho * stride + kh - pad;
+        if (hi < 0 || hi >= H) continue;
+        for (int wo = 0; wo < Wo; wo++) {
+          const int wi = wo * stride + kw - pad;
+          if (wi < 0 || wi >= W) continue;
+          acc = fmaf(dz[(((size_t)n * Ho + ho) * Wo + wo) * Cout + co], x[(((size_t)n * H + hi) * W + wi) * Cin + ci], acc);
+        }
+      }
+    dw[(((size_t)co * Cin + ci) * k + kh) * k + kw] = acc;
+  }
+}
+
+}  // namespace
+
+int conv_backward_data(const float* dz, const float* w, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                       float* dx, cudaStream_t s) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || k <= 0 || stride <= 0 || pad < 0) {
+    set_error("yb_conv_backward_data: bad shape");
+    return YB_ERR_SHAPE;
+  }
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const long long total = (long long)N * H * W * Cin;
+  conv_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dz, w, N, H, W, Cin, Ho, Wo, Cout, k, stride, pad, dx);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return YB_OK;
+}
+
+int conv_backward_weight(const float* x, const float* dz, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                         float* dw, cudaStream_t s) {
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || k <= 0 || stride <= 0 || pad < 0) {
+    set_error("yb_conv_backward_weight: bad shape");
+    return YB_ERR_SHAPE;
+  }
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  conv_wgrad_kernel<<<dim3(k * k, Cout), 128, 0, s>>>(x, dz, N, H, W, Cin, Ho, Wo, Cout, k, stride, pad, dw);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return YB_OK;
+}
+
+}  // namespace yb

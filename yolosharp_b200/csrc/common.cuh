@@ -120,6 +120,10 @@ int bn_silu_backward(const float* z, const float* dy, long long M, int C, int pi
                      float* dgamma, float* dbeta, cudaStream_t s);
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2, float eps,
                float wd, cudaStream_t s);
+int conv_backward_data(const float* dz, const float* w, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                       float* dx, cudaStream_t s);
+int conv_backward_weight(const float* x, const float* dz, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                         float* dw, cudaStream_t s);
 int masks_launch(const float* proto, const float* dets, const int* counts, int B, int max_det, int nm,
                  int mh, int mw, int H, int W, uint8_t* masks, cudaStream_t s);
 

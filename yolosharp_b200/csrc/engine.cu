@@ -1130,6 +1130,20 @@ int32_t yb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, i
   return adamw_step(p, g, m, v, n, step, lr, beta1, beta2, eps, weight_decay, (cudaStream_t)stream);
 }
 
+int32_t yb_conv_backward_data(const float* dz, const float* w, int32_t n, int32_t height, int32_t width, int32_t cin,
+                              int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dx, void* stream) {
+  if (!dz || !w || !dx) { set_error("yb_conv_backward_data: null argument"); return YB_ERR_INVALID_ARG; }
+  if (!have_device("yb_conv_backward_data")) return YB_ERR_NO_DEVICE;
+  return conv_backward_data(dz, w, n, height, width, cin, cout, k, stride, pad, dx, (cudaStream_t)stream);
+}
+
+int32_t yb_conv_backward_weight(const float* x, const float* dz, int32_t n, int32_t height, int32_t width, int32_t cin,
+                                int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dw, void* stream) {
+  if (!x || !dz || !dw) { set_error("yb_conv_backward_weight: null argument"); return YB_ERR_INVALID_ARG; }
+  if (!have_device("yb_conv_backward_weight")) return YB_ERR_NO_DEVICE;
+  return conv_backward_weight(x, dz, n, height, width, cin, cout, k, stride, pad, dw, (cudaStream_t)stream);
+}
+
 static int32_t predict_enqueue(yb_engine* e, yb_engine::Stage& st, const uint8_t* images_host, int32_t batch,
                                float conf_thres, float iou_thres, int32_t max_det, float* dets_host,
                                int32_t* counts_host, cudaStream_t s, const char* who) {

@@ -247,3 +247,18 @@ def adamw_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_de
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
     L.check(L.lib().yb_adamw_step(C.c_void_p(p.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(m.data_ptr()),
                                   C.c_void_p(v.data_ptr()), p.numel(), step, lr, beta1, beta2, eps, weight_decay, _stream_ptr(stream)))
+
+
+def conv_backward(x, dz, w, stride=1, pad=None, stream=None):
+    """yb_conv_backward_data / _weight: x (N,H,W,Cin), dz (N,Ho,Wo,Cout) NHWC float32, w (Cout,Cin,k,k) -> (dx, dw)."""
+    for t in (x, dz, w):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    N, H, W, Cin = x.shape
+    Cout, _, k, _ = w.shape
+    pad = k // 2 if pad is None else pad
+    dx, dw = torch.empty_like(x), torch.empty_like(w)
+    L.check(L.lib().yb_conv_backward_data(C.c_void_p(dz.data_ptr()), C.c_void_p(w.data_ptr()), N, H, W, Cin, Cout, k, stride, pad,
+                                          C.c_void_p(dx.data_ptr()), _stream_ptr(stream)))
+    L.check(L.lib().yb_conv_backward_weight(C.c_void_p(x.data_ptr()), C.c_void_p(dz.data_ptr()), N, H, W, Cin, Cout, k, stride, pad,
+                                            C.c_void_p(dw.data_ptr()), _stream_ptr(stream)))
+    return dx, dw
