@@ -76,3 +76,46 @@ def test_gather_world2_even():
 
 def test_gather_world3_ragged():
     _run(3, 7)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # a tiny conv + BN "model": every rank computes gradients on its shard of one global batch; after the flat
+        # all-reduce every rank must hold the gradient of the whole batch (sum of per-sample losses, as Loss.cs:473)
+        torch.manual_seed(0)
+        w = torch.randn(8, 3, 3, 3)
+        b = torch.randn(8)
+        x = torch.randn(6, 3, 10, 10)
+        bucket = ydist.GradBucket([w.shape, b.shape])
+
+        def grads(xs):
+            ww, bb = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+            loss = (torch.nn.functional.conv2d(xs, ww, bb, padding=1) ** 2).sum()
+            return torch.autograd.grad(loss, (ww, bb))
+        s, e = ydist.shard_range(6, rank, world)
+        gw, gb = grads(x[s:e])
+        bucket.view(0).copy_(gw)
+        bucket.view(1).copy_(gb)
+        bucket.all_reduce()
+        rw, rb = grads(x)
+        ok = torch.allclose(bucket.view(0), rw, rtol=1e-4, atol=1e-4) and torch.allclose(bucket.view(1), rb, rtol=1e-4, atol=1e-4)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_bucket_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]

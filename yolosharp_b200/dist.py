@@ -1,6 +1,8 @@
-"""Multi-GPU plumbing for the inference path: one process per GPU (torchrun), images sharded per
-rank in contiguous blocks, detections exchanged with ONE all-gather of the fixed-capacity buffers
-(SURVEY.md §8(e)).  The reference is single-device (Data/Config.cs:301); this layer is net-new.
+"""Multi-GPU plumbing: one process per GPU (torchrun).
+Inference: images sharded per rank in contiguous blocks, detections exchanged with ONE all-gather of the
+fixed-capacity buffers.  Training: data-parallel gradient averaging over ONE flat buffer
+(`GradBucket`) - the reference's `loss.sum().backward(); step()` (Utils/Amp.cs:260-286) is single-device
+(Data/Config.cs:301), so this layer is net-new.
 Works with the NCCL backend on GPUs and with gloo on CPU tensors (used by the CPU tests)."""
 import torch
 import torch.distributed as dist
@@ -50,3 +52,32 @@ def unpad_gathered(all_dets, all_counts, n_images, world):
         idx.extend(range(r * per, r * per + (e - s)))
     idx = torch.tensor(idx, dtype=torch.long, device=all_dets.device)
     return all_dets.index_select(0, idx), all_counts.index_select(0, idx)
+
+
+class GradBucket:
+    """All gradients of the model live in ONE flat float32 buffer (views per parameter), so data-parallel training
+    needs a single all-reduce per step (NVSwitch: the cost is launch latency, not link count) and the optimizer
+    (`yb_adamw_step`) runs over the same flat buffer.  The reference multiplies the loss by the LOCAL batch size
+    (Loss.cs:473) and does not average over samples, so ranks' gradients are SUMMED (= one big batch), not meaned."""
+
+    def __init__(self, shapes, device="cpu", dtype=torch.float32):
+        self.shapes = [tuple(s) for s in shapes]
+        self.offsets, n = [], 0
+        for s in self.shapes:
+            self.offsets.append(n)
+            n += int(torch.Size(s).numel())
+        self.flat = torch.zeros(n, dtype=dtype, device=device)
+
+    def view(self, i):
+        n = int(torch.Size(self.shapes[i]).numel())
+        return self.flat[self.offsets[i]:self.offsets[i] + n].view(self.shapes[i])
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce(self, group=None, average=False):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                self.flat.div_(dist.get_world_size(group))
+        return self.flat
