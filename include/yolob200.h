@@ -167,6 +167,13 @@ int32_t yb_bn_silu_backward(const float* z, const float* dy, int64_t rows, int32
 int32_t yb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr, float beta1,
                       float beta2, float eps, float weight_decay, void* stream);
 
+/* Replaces (training path, fp32 parity kernels): the forward of `Conv2d` without the (train-mode) BatchNorm folded in
+ * (Modules/Convs.cs:44, Head.cs:41-52 for the biased 1x1 convs).
+ *   x  dev float32 NHWC (N, H, W, Cin);  w_packed dev float32 [kh][kw][Cin][Cout] (= weight.permute(2,3,1,0));
+ *   bias dev float32 (Cout) or NULL;  z dev float32 NHWC (N, Ho, Wo, Cout) */
+int32_t yb_conv_forward_f32(const float* x, const float* w_packed, const float* bias, int32_t n, int32_t height,
+                            int32_t width, int32_t cin, int32_t cout, int32_t k, int32_t stride, int32_t pad, float* z,
+                            void* stream);
 /* Replaces (training path, fp32 parity kernels): the autograd backward of `Conv2d(bias: false)` inside every Conv
  * block (Modules/Convs.cs:44; libtorch dgrad / wgrad behind `loss.backward()`, Utils/Amp.cs:260-286).
  *   x  dev float32 NHWC (N, H, W, Cin);  dz dev float32 NHWC (N, Ho, Wo, Cout), Ho = (H + 2 pad - k)/stride + 1

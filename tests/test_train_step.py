@@ -1,0 +1,83 @@
+"""Whole training step of YOLOv8n (yolosharp_b200/train.py) against autograd through the oracle model + oracle loss
++ torch.optim.AdamW.  On CPU the step runs on a PyTorch stand-in of the kernel interface (tests/torch_train_ops.py):
+this pins the graph logic; the -m gpu test runs the same comparison with the real kernels."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss as oloss
+from tests.util import oracle_model, synth_image
+
+
+def _targets(B, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    n = 7
+    bidx = torch.randint(0, B, (n,), generator=g).sort().values.float()
+    cls = torch.randint(0, 80, (n,), generator=g).float()
+    xy = torch.rand(n, 2, generator=g) * 0.6 + 0.2
+    wh = torch.rand(n, 2, generator=g) * 0.4 + 0.05
+    return torch.cat((bidx.view(-1, 1), cls.view(-1, 1), xy, wh), 1)
+
+
+def _reference_step(m, x, targets, lr, wd):
+    """oracle: train-mode forward, v8DetectionLoss, backward, AdamW on every trained parameter."""
+    m.train()
+    params = [(k, p) for k, p in m.named_parameters() if ".dfl." not in k]
+    opt = torch.optim.AdamW([p for _, p in params], lr=lr, weight_decay=wd)
+    _, preds = m(x)
+    crit = oloss.V8DetectionLoss(80)
+    batch = {"batch_idx": targets[:, 0], "cls": targets[:, 1], "bboxes": targets[:, 2:]}
+    loss, items = crit(preds, batch)
+    opt.zero_grad()
+    loss.sum().backward()
+    grads = {k: p.grad.detach().clone() for k, p in params}
+    opt.step()
+    return items, grads
+
+
+def _compare(step_cls, ops, device, tol):
+    torch.manual_seed(0)
+    m = oracle_model("v8", "detect", "n")
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    B, H, W = 2, 64, 96
+    x = synth_image(B, H, W)
+    targets = _targets(B)
+    lr, wd = 1e-3, 5e-4
+    items_ref, grads_ref = _reference_step(m, x, targets, lr, wd)
+    ts = step_cls(sd0, "n", 80, device=device, ops=ops, lr=lr, weight_decay=wd)
+    items = ts.step(x.to(device), targets)
+    np.testing.assert_allclose(items.detach().cpu().numpy(), items_ref.numpy(), rtol=tol, atol=1e-5)
+    worst = ("", 0.0)
+    gmax = max(float(g.abs().max()) for g in grads_ref.values())
+    for k, g in grads_ref.items():
+        got = ts.P.g(k).detach().cpu()
+        # gradients that are mathematically ~0 (e.g. the BN bias of SPPF.cv1: the BatchNorm of cv2 cancels a per-channel
+        # shift of its input, only the max-pool paths leak) are rounding noise on both sides: compare them absolutely
+        scale = max(float(g.abs().max()), 1e-4 * gmax)
+        err = float((got - g).abs().max()) / scale
+        worst = max(worst, (k, err), key=lambda t: t[1])
+    assert worst[1] < tol * 20, worst
+    new = m.state_dict()
+    # Adam's first step moves every weight by lr * g / (|g| + eps'): where the gradient is rounding noise its SIGN is
+    # noise too, so a handful of weights may differ by up to 2 * lr; everything else must agree closely
+    for k in grads_ref:
+        d = (ts.P.p(k).detach().cpu() - new[k].detach()).abs()
+        bad = d > (tol + tol * 10 * new[k].detach().abs())
+        noise_only = float(grads_ref[k].abs().max()) < 1e-4 * gmax  # the whole gradient is rounding noise (see above)
+        assert float(d.max()) <= 2.1 * lr and (noise_only or float(bad.float().mean()) < 2e-3), (k, float(d.max()), int(bad.sum()))
+    for k, v in ts.P.buffers.items():  # BatchNorm running statistics after one train-mode forward
+        np.testing.assert_allclose(v.cpu().numpy(), new[k].numpy(), rtol=1e-3, atol=1e-4)
+    assert len(grads_ref) == len(ts.P.names)
+
+
+def test_train_step_graph_logic_cpu():
+    from tests.torch_train_ops import TorchOps
+    from yolosharp_b200.train import TrainStepV8
+    _compare(TrainStepV8, TorchOps(), "cpu", 2e-4)
+
+
+@pytest.mark.gpu
+def test_train_step_kernels_gpu():
+    import yolosharp_b200  # noqa: F401  (fails loudly without the CUDA library)
+    from yolosharp_b200.train import KernelOps, TrainStepV8
+    _compare(TrainStepV8, KernelOps(), "cuda", 1e-3)

@@ -45,6 +45,7 @@ SIGNATURES = {
                                          c_vp, c_vp, c_vp]),
     "yb_bn_silu_backward": (c_i32, [c_vp, c_vp, C.c_int64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp,
                                     c_vp, c_vp]),
+    "yb_conv_forward_f32": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "yb_conv_backward_data": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "yb_conv_backward_weight": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "yb_adamw_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, C.c_int64, c_i32, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp]),

@@ -1130,6 +1130,35 @@ int32_t yb_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, i
   return adamw_step(p, g, m, v, n, step, lr, beta1, beta2, eps, weight_decay, (cudaStream_t)stream);
 }
 
+int32_t yb_conv_forward_f32(const float* x, const float* w_packed, const float* bias, int32_t n, int32_t height,
+                            int32_t width, int32_t cin, int32_t cout, int32_t k, int32_t stride, int32_t pad, float* z,
+                            void* stream) {
+  if (!x || !w_packed || !z) { set_error("yb_conv_forward_f32: null argument"); return YB_ERR_INVALID_ARG; }
+  if (n <= 0 || height <= 0 || width <= 0 || cin <= 0 || cout <= 0 || k <= 0 || stride <= 0 || pad < 0) {
+    set_error("yb_conv_forward_f32: bad shape");
+    return YB_ERR_SHAPE;
+  }
+  if (!have_device("yb_conv_forward_f32")) return YB_ERR_NO_DEVICE;
+  static float* zero_bias = nullptr;  // the generic kernel always adds a bias vector
+  static int zero_cap = 0;
+  if (!bias && zero_cap < cout) {
+    if (zero_bias) cudaFree(zero_bias);
+    zero_cap = std::max(cout, 4096);
+    YB_CUDA_CHECK(cudaMalloc((void**)&zero_bias, (size_t)zero_cap * sizeof(float)));
+    YB_CUDA_CHECK(cudaMemset(zero_bias, 0, (size_t)zero_cap * sizeof(float)));
+  }
+  ConvParams p;
+  p.in.base = const_cast<float*>(x); p.in.H = height; p.in.W = width; p.in.pitch = cin; p.in.coff = 0; p.in.C = cin;
+  p.Ho = (height + 2 * pad - k) / stride + 1;
+  p.Wo = (width + 2 * pad - k) / stride + 1;
+  p.out.base = z; p.out.H = p.Ho; p.out.W = p.Wo; p.out.pitch = cout; p.out.coff = 0; p.out.C = cout;
+  p.w = w_packed;
+  p.bias = bias ? bias : zero_bias;
+  p.B = n; p.Cin = cin; p.Cout = cout; p.k = k; p.stride = stride; p.pad = pad;
+  p.act = ACT_NONE;
+  return launch_conv_generic<float>(p, (cudaStream_t)stream);
+}
+
 int32_t yb_conv_backward_data(const float* dz, const float* w, int32_t n, int32_t height, int32_t width, int32_t cin,
                               int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dx, void* stream) {
   if (!dz || !w || !dx) { set_error("yb_conv_backward_data: null argument"); return YB_ERR_INVALID_ARG; }

@@ -262,3 +262,18 @@ def conv_backward(x, dz, w, stride=1, pad=None, stream=None):
     L.check(L.lib().yb_conv_backward_weight(C.c_void_p(x.data_ptr()), C.c_void_p(dz.data_ptr()), N, H, W, Cin, Cout, k, stride, pad,
                                             C.c_void_p(dw.data_ptr()), _stream_ptr(stream)))
     return dx, dw
+
+
+def conv_forward(x, w, bias=None, stride=1, pad=None, stream=None):
+    """yb_conv_forward_f32: x (N,H,W,Cin) NHWC float32, w (Cout,Cin,k,k) -> z (N,Ho,Wo,Cout) (no BN, no activation)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and w.is_cuda and w.dtype == torch.float32
+    N, H, W, Cin = x.shape
+    Cout, _, k, _ = w.shape
+    pad = k // 2 if pad is None else pad
+    wp = w.permute(2, 3, 1, 0).contiguous()
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    z = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    L.check(L.lib().yb_conv_forward_f32(C.c_void_p(x.data_ptr()), C.c_void_p(wp.data_ptr()),
+                                        C.c_void_p(bias.data_ptr()) if bias is not None else None, N, H, W, Cin, Cout, k, stride, pad,
+                                        C.c_void_p(z.data_ptr()), _stream_ptr(stream)))
+    return z

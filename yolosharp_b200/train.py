@@ -1,0 +1,314 @@
+"""Training step of the reference's YOLOv8 detect model on the fp32 parity kernels.
+
+One `TrainStepV8.step(images, targets)` = `yolo.train()` forward (Conv2d -> BatchNorm2d with batch statistics ->
+SiLU, Modules/Convs.cs:36-56) -> `v8DetectionLoss` (Utils/Loss.cs:328-485) -> backward -> `AdamW.step()`
+(YoloBaseTaskModel.cs:142-160, Utils/Amp.cs:260-286), i.e. what `AMPWrapper.TrainStep` does in its fp32 branch.
+Every arithmetic op is a kernel of libyolob200.so reached through `ops` (conv forward / dgrad / wgrad, BN+SiLU
+forward / backward, detection loss + gradient, AdamW); PyTorch only holds the NHWC tensors and does the data movement
+of the graph (channel concat / chunk views, nearest 2x upsampling and its sum-reduction backward, the 5x5 max-pool of
+SPPF and its index backward - the last two are the remaining library calls on this path).
+
+This is the PARITY path of the training side: correct first (it matches autograd through the oracle restatement
+parameter by parameter), CUDA-core fp32 kernels; the tcgen05 dgrad / wgrad kernels and a captured train-mode graph
+replace it next.  Parameter names are the reference's state_dict keys (`model.{i}.conv.weight`, ...).
+"""
+import torch
+import torch.nn.functional as F
+
+V8_SIZES = {  # Models/Yolo.cs:45-49 (depth_multiple, width_multiple, max_channels)
+    "n": (0.34, 0.25, 1024), "s": (0.34, 0.5, 1024), "m": (0.67, 0.75, 576), "l": (1.0, 1.0, 512), "x": (1.0, 1.25, 640),
+}
+
+
+class KernelOps:
+    """The C-ABI kernels (no fallback: importing this on a machine without the CUDA library fails loudly)."""
+
+    def __init__(self):
+        from . import engine as E
+        self.E = E
+
+    def conv_forward(self, x, w, bias, stride, pad):
+        return self.E.conv_forward(x, w, bias, stride, pad)
+
+    def conv_backward(self, x, dz, w, stride, pad):
+        return self.E.conv_backward(x, dz.contiguous(), w, stride, pad)
+
+    def bn_silu_forward(self, z, gamma, beta, rm, rv, act):
+        return self.E.bn_silu_train_forward(z, gamma, beta, rm, rv, act=act)
+
+    def bn_silu_backward(self, z, dy, gamma, beta, mean, invstd, act):
+        return self.E.bn_silu_backward(z, dy.contiguous(), gamma, beta, mean, invstd, act=act)
+
+    def detection_loss(self, boxes, scores, targets, H, W):
+        o = self.E.detection_loss(boxes.contiguous(), scores.contiguous(), targets, H, W)
+        return o["items"], o["grad_boxes"], o["grad_scores"]
+
+    def adamw(self, p, g, m, v, step, lr, wd):
+        self.E.adamw_step(p, g, m, v, step, lr, weight_decay=wd)
+
+
+class _Params:
+    """Flat parameter / gradient / Adam-moment buffers with named views (one optimizer launch, one all-reduce)."""
+
+    def __init__(self, state_dict, device):
+        self.names = [k for k, v in state_dict.items() if v.dtype.is_floating_point and v.numel() > 0 and
+                      not k.endswith(("running_mean", "running_var")) and ".dfl." not in k]
+        self.shapes = {k: tuple(state_dict[k].shape) for k in self.names}
+        n = sum(int(torch.Size(self.shapes[k]).numel()) for k in self.names)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.off, o = {}, 0
+        for k in self.names:
+            c = int(torch.Size(self.shapes[k]).numel())
+            self.off[k] = (o, c)
+            self.flat[o:o + c].copy_(state_dict[k].detach().reshape(-1).to(device=device, dtype=torch.float32))
+            o += c
+        self.buffers = {k: v.detach().clone().to(device=device, dtype=torch.float32) for k, v in state_dict.items()
+                        if k.endswith(("running_mean", "running_var"))}
+
+    def p(self, k):
+        o, c = self.off[k]
+        return self.flat[o:o + c].view(self.shapes[k])
+
+    def g(self, k):
+        o, c = self.off[k]
+        return self.grad[o:o + c].view(self.shapes[k])
+
+
+class _Conv:
+    """Conv block: Conv2d(bias=False) -> BatchNorm2d(train) -> SiLU / identity (Convs.cs:36-56)."""
+
+    def __init__(self, net, name, k=1, s=1, act=True):
+        self.net, self.name, self.k, self.s, self.act = net, name, k, s, act
+
+    def forward(self, x):
+        P, ops = self.net.P, self.net.ops
+        self.x = x
+        self.z = ops.conv_forward(x, P.p(self.name + ".conv.weight"), None, self.s, self.k // 2)
+        y, self.mean, self.invstd = ops.bn_silu_forward(self.z, P.p(self.name + ".bn.weight"), P.p(self.name + ".bn.bias"),
+                                                        P.buffers[self.name + ".bn.running_mean"],
+                                                        P.buffers[self.name + ".bn.running_var"], self.act)
+        return y
+
+    def backward(self, dy):
+        P, ops = self.net.P, self.net.ops
+        dz, dg, db = ops.bn_silu_backward(self.z, dy, P.p(self.name + ".bn.weight"), P.p(self.name + ".bn.bias"), self.mean,
+                                          self.invstd, self.act)
+        dx, dw = ops.conv_backward(self.x, dz, P.p(self.name + ".conv.weight"), self.s, self.k // 2)
+        P.g(self.name + ".conv.weight").copy_(dw)
+        P.g(self.name + ".bn.weight").copy_(dg)
+        P.g(self.name + ".bn.bias").copy_(db)
+        return dx
+
+
+class _Conv2dBias:
+    """Plain Conv2d(k=1, bias=True): the last layer of every Detect branch (Head.cs:41-52)."""
+
+    def __init__(self, net, name):
+        self.net, self.name = net, name
+
+    def forward(self, x):
+        self.x = x
+        return self.net.ops.conv_forward(x, self.net.P.p(self.name + ".weight"), self.net.P.p(self.name + ".bias"), 1, 0)
+
+    def backward(self, dz):
+        dx, dw = self.net.ops.conv_backward(self.x, dz, self.net.P.p(self.name + ".weight"), 1, 0)
+        self.net.P.g(self.name + ".weight").copy_(dw)
+        self.net.P.g(self.name + ".bias").copy_(dz.sum((0, 1, 2)))
+        return dx
+
+
+class _Bottleneck:
+    """Block.cs:572-607, k = (3, 3), e = 1.0 inside C2f."""
+
+    def __init__(self, net, name, shortcut):
+        self.cv1, self.cv2, self.add = _Conv(net, name + ".cv1", 3), _Conv(net, name + ".cv2", 3), shortcut
+
+    def forward(self, x):
+        y = self.cv2.forward(self.cv1.forward(x))
+        return x + y if self.add else y
+
+    def backward(self, dy):
+        dx = self.cv1.backward(self.cv2.backward(dy))
+        return dx + dy if self.add else dx
+
+
+class _C2f:
+    """Block.cs:371-398."""
+
+    def __init__(self, net, name, c2, n, shortcut):
+        self.c = c2 // 2
+        self.cv1, self.cv2 = _Conv(net, name + ".cv1", 1), _Conv(net, name + ".cv2", 1)
+        self.m = [_Bottleneck(net, f"{name}.m.{i}", shortcut) for i in range(n)]
+
+    def forward(self, x):
+        y = self.cv1.forward(x)
+        ys = [y[..., :self.c], y[..., self.c:]]
+        for m in self.m:
+            ys.append(m.forward(ys[-1].contiguous()))
+        return self.cv2.forward(torch.cat(ys, -1))
+
+    def backward(self, dy):
+        d = list(self.cv2.backward(dy).split(self.c, -1))
+        for i in range(len(self.m) - 1, -1, -1):
+            d[i + 1] = d[i + 1] + self.m[i].backward(d[i + 2].contiguous())
+        return self.cv1.backward(torch.cat((d[0], d[1]), -1))
+
+
+def _pool(x):  # MaxPool2d(5, 1, 2) on NHWC (library call, see module docstring)
+    y, idx = F.max_pool2d(x.permute(0, 3, 1, 2), 5, 1, 2, return_indices=True)
+    return y.permute(0, 2, 3, 1).contiguous(), idx
+
+
+def _pool_backward(dy, x, idx):
+    d = torch.ops.aten.max_pool2d_with_indices_backward(dy.permute(0, 3, 1, 2).contiguous(), x.permute(0, 3, 1, 2).contiguous(),
+                                                       [5, 5], [1, 1], [2, 2], [1, 1], False, idx)
+    return d.permute(0, 2, 3, 1)
+
+
+class _SPPF:
+    """Block.cs:236-282: cv1 has NO activation in the reference (:257)."""
+
+    def __init__(self, net, name):
+        self.cv1, self.cv2 = _Conv(net, name + ".cv1", 1, act=False), _Conv(net, name + ".cv2", 1)
+
+    def forward(self, x):
+        self.t = [self.cv1.forward(x)]
+        self.idx = []
+        for _ in range(3):
+            y, i = _pool(self.t[-1])
+            self.t.append(y)
+            self.idx.append(i)
+        return self.cv2.forward(torch.cat(self.t, -1))
+
+    def backward(self, dy):
+        c = self.t[0].shape[-1]
+        d = list(self.cv2.backward(dy).split(c, -1))
+        for i in (2, 1, 0):
+            d[i] = d[i] + _pool_backward(d[i + 1], self.t[i], self.idx[i])
+        return self.cv1.backward(d[0].contiguous())
+
+
+class _Detect:
+    """Detect.forward_head (Head.cs:35-53, 71-87), legacy (v8) class branch."""
+
+    def __init__(self, net, name, nc, ch, reg_max=16):
+        self.nc, self.reg_max = nc, reg_max
+        self.cv2 = [[_Conv(net, f"{name}.cv2.{i}.0", 3), _Conv(net, f"{name}.cv2.{i}.1", 3), _Conv2dBias(net, f"{name}.cv2.{i}.2")]
+                    for i in range(len(ch))]
+        self.cv3 = [[_Conv(net, f"{name}.cv3.{i}.0", 3), _Conv(net, f"{name}.cv3.{i}.1", 3), _Conv2dBias(net, f"{name}.cv3.{i}.2")]
+                    for i in range(len(ch))]
+
+    @staticmethod
+    def _seq(layers, x):
+        for layer in layers:
+            x = layer.forward(x)
+        return x
+
+    def forward(self, feats):
+        self.shapes = [f.shape for f in feats]
+        b = [self._seq(self.cv2[i], f) for i, f in enumerate(feats)]
+        s = [self._seq(self.cv3[i], f) for i, f in enumerate(feats)]
+        B = feats[0].shape[0]
+        boxes = torch.cat([t.permute(0, 3, 1, 2).reshape(B, 4 * self.reg_max, -1) for t in b], -1)
+        scores = torch.cat([t.permute(0, 3, 1, 2).reshape(B, self.nc, -1) for t in s], -1)
+        return boxes, scores
+
+    def backward(self, gboxes, gscores):
+        out, a0 = [], 0
+        for i, shp in enumerate(self.shapes):
+            B, h, w, _ = shp
+            gb = gboxes[:, :, a0:a0 + h * w].reshape(B, 4 * self.reg_max, h, w).permute(0, 2, 3, 1).contiguous()
+            gs = gscores[:, :, a0:a0 + h * w].reshape(B, self.nc, h, w).permute(0, 2, 3, 1).contiguous()
+            a0 += h * w
+            d = None
+            for layers, g in ((self.cv2[i], gb), (self.cv3[i], gs)):
+                for layer in reversed(layers):
+                    g = layer.backward(g)
+                d = g if d is None else d + g
+            out.append(d)
+        return out
+
+
+class TrainStepV8:
+    """YOLOv8 detect training step.  `state_dict`: the reference's names -> tensors (as loaded from a .bin)."""
+
+    def __init__(self, state_dict, size="n", nc=80, device="cuda", ops=None, lr=None, weight_decay=5e-4):
+        self.ops = ops if ops is not None else KernelOps()
+        self.P = _Params(state_dict, device)
+        d, wm, mc = V8_SIZES[size]
+        w = [min(int(x * wm), mc) for x in (64, 128, 256, 512, 1024)]
+        dp = [int(x * d) for x in (3, 6, 9)]
+        self.nc, self.step_count = nc, 0
+        self.lr = lr if lr is not None else round(0.002 * 5 / (4 + nc), 6)  # YoloBaseTaskModel.cs:142
+        self.wd = weight_decay
+        N = self
+        self.layers = [  # Yolo.cs:53-89
+            _Conv(N, "model.0", 3, 2), _Conv(N, "model.1", 3, 2), _C2f(N, "model.2", w[1], dp[0], True),
+            _Conv(N, "model.3", 3, 2), _C2f(N, "model.4", w[2], dp[1], True), _Conv(N, "model.5", 3, 2),
+            _C2f(N, "model.6", w[3], dp[1], True), _Conv(N, "model.7", 3, 2), _C2f(N, "model.8", w[4], dp[0], True),
+            _SPPF(N, "model.9"), "up", "cat", _C2f(N, "model.12", w[3], dp[0], False), "up", "cat",
+            _C2f(N, "model.15", w[2], dp[0], False), _Conv(N, "model.16", 3, 2), "cat", _C2f(N, "model.18", w[3], dp[0], False),
+            _Conv(N, "model.19", 3, 2), "cat", _C2f(N, "model.21", w[4], dp[0], False),
+        ]
+        self.detect = _Detect(N, "model.22", nc, (w[2], w[3], w[4]))
+        self.output_indexs = (4, 6, 9, 12, 15, 18, 21)  # Yolo.cs:13
+        self.concat_index = (1, 0, 3, 2)                 # Yolo.cs:14
+
+    # ---- forward / backward of the graph wiring (Yolo.cs:92-134) ----
+    def forward(self, images_nchw):
+        x = images_nchw.permute(0, 2, 3, 1).contiguous()
+        outputs, cat_count, self.cat_split = [], 0, []
+        for i, m in enumerate(self.layers):
+            if m == "up":
+                x = x.repeat_interleave(2, 1).repeat_interleave(2, 2)
+            elif m == "cat":
+                other = outputs[self.concat_index[cat_count]]
+                self.cat_split.append((x.shape[-1], self.concat_index[cat_count]))
+                x = torch.cat((x, other), -1)
+                cat_count += 1
+            else:
+                x = m.forward(x.contiguous())
+            if i in self.output_indexs:
+                outputs.append(x)
+        self.n_out = len(outputs)
+        return self.detect.forward([outputs[-3], outputs[-2], outputs[-1]])
+
+    def backward(self, gboxes, gscores):
+        dfeat = self.detect.backward(gboxes, gscores)
+        dout = [None] * self.n_out  # gradient arriving at each saved output from its later consumers
+        for k, d in zip((-3, -2, -1), dfeat):
+            dout[self.n_out + k] = d
+        out_pos = {idx: j for j, idx in enumerate(self.output_indexs)}
+        cat_count = len(self.cat_split)
+        dx = None
+        for i in range(len(self.layers) - 1, -1, -1):
+            if i in out_pos and dout[out_pos[i]] is not None:
+                dx = dout[out_pos[i]] if dx is None else dx + dout[out_pos[i]]
+            m = self.layers[i]
+            if m == "up":
+                B, H, W, C = dx.shape
+                dx = dx.reshape(B, H // 2, 2, W // 2, 2, C).sum((2, 4))
+            elif m == "cat":
+                cat_count -= 1
+                cx, src = self.cat_split[cat_count]
+                d_other = dx[..., cx:]
+                dout[src] = d_other if dout[src] is None else dout[src] + d_other
+                dx = dx[..., :cx]
+            else:
+                dx = m.backward(dx.contiguous())
+        return dx
+
+    def step(self, images_nchw, targets):
+        """images (B,3,H,W) float32 in [0,1] on the device; targets (n,6) rows [image, cls, x, y, w, h].
+        -> loss items (3,) (= the reference's `loss.detach()`)."""
+        B, _, H, W = images_nchw.shape
+        boxes, scores = self.forward(images_nchw)
+        items, gb, gs = self.ops.detection_loss(boxes, scores, targets, H, W)
+        self.P.grad.zero_()
+        self.backward(gb, gs)
+        self.step_count += 1
+        self.ops.adamw(self.P.flat, self.P.grad, self.P.m, self.P.v, self.step_count, self.lr, self.wd)
+        return items
