@@ -1,5 +1,3 @@
 timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -2
-python bench.py --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('v8n', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['gpu_launches'])"
+timeout 300 python tools/exp_train_time.py 8 n 2>&1 | tail -3

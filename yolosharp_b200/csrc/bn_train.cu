@@ -243,26 +243,37 @@ __global__ void conv_dgrad_kernel(const float* __restrict__ dz, const float* __r
   dx[i] = acc;
 }
 
-// one block per (co, tap): threads over ci, serial over pixels (deterministic sums)
+// one block per (co, tap, slab of output rows): threads over ci, serial over the slab's pixels; the per-slab
+// partials are folded in slab order by conv_wgrad_reduce_kernel (deterministic sums, no atomics)
 __global__ void __launch_bounds__(128) conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, int N, int H, int W,
                                                         int Cin, int Ho, int Wo, int Cout, int k, int stride, int pad,
-                                                        float* __restrict__ dw) {
-  const int tap = blockIdx.x, co = blockIdx.y;
+                                                        int rows_per_slab, float* __restrict__ part) {
+  const int tap = blockIdx.x, co = blockIdx.y, slab = blockIdx.z;
   const int kh = tap / k, kw = tap - kh * k;
+  const int r0 = slab * rows_per_slab, r1 = min(N * Ho, r0 + rows_per_slab);  // rows of the flattened (n, ho) index
+  const size_t dw_size = (size_t)Cout * Cin * k * k;
   for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
     float acc = 0.f;
-    for (int n = 0; n < N; n++)
-      for (int ho = 0; ho < Ho; ho++) {
-        const int hi = ho * stride + kh - pad;
-        if (hi < 0 || hi >= H) continue;
-        for (int wo = 0; wo < Wo; wo++) {
-          const int wi = wo * stride + kw - pad;
-          if (wi < 0 || wi >= W) continue;
-          acc = fmaf(dz[(((size_t)n * Ho + ho) * Wo + wo) * Cout + co], x[(((size_t)n * H + hi) * W + wi) * Cin + ci], acc);
-        }
+    for (int r = r0; r < r1; r++) {
+      const int n = r / Ho, ho = r - n * Ho;
+      const int hi = ho * stride + kh - pad;
+      if (hi < 0 || hi >= H) continue;
+      for (int wo = 0; wo < Wo; wo++) {
+        const int wi = wo * stride + kw - pad;
+        if (wi < 0 || wi >= W) continue;
+        acc = fmaf(dz[(((size_t)n * Ho + ho) * Wo + wo) * Cout + co], x[(((size_t)n * H + hi) * W + wi) * Cin + ci], acc);
       }
-    dw[(((size_t)co * Cin + ci) * k + kh) * k + kw] = acc;
+    }
+    part[(size_t)slab * dw_size + (((size_t)co * Cin + ci) * k + kh) * k + kw] = acc;
   }
+}
+
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ part, int slabs, size_t dw_size, float* __restrict__ dw) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dw_size) return;
+  float t = 0.f;
+  for (int s = 0; s < slabs; s++) t += part[(size_t)s * dw_size + i];
+  dw[i] = t;
 }
 
 }  // namespace
@@ -287,8 +298,19 @@ int conv_backward_weight(const float* x, const float* dz, int N, int H, int W, i
     return YB_ERR_SHAPE;
   }
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-  conv_wgrad_kernel<<<dim3(k * k, Cout), 128, 0, s>>>(x, dz, N, H, W, Cin, Ho, Wo, Cout, k, stride, pad, dw);
+  const size_t dw_size = (size_t)Cout * Cin * k * k;
+  // enough slabs to fill the machine on the high-resolution layers, bounded partial buffer (<= 64 MB)
+  int slabs = std::max(1, std::min(64, (N * Ho * Wo) / 2048));
+  slabs = (int)std::max<size_t>(1, std::min<size_t>((size_t)slabs, ((size_t)16 << 20) / dw_size));
+  slabs = std::min(slabs, N * Ho);
+  const int rows_per_slab = (N * Ho + slabs - 1) / slabs;
+  slabs = (N * Ho + rows_per_slab - 1) / rows_per_slab;
+  float* part = nullptr;
+  YB_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)slabs * dw_size * sizeof(float), s));
+  conv_wgrad_kernel<<<dim3(k * k, Cout, slabs), 128, 0, s>>>(x, dz, N, H, W, Cin, Ho, Wo, Cout, k, stride, pad, rows_per_slab, part);
+  conv_wgrad_reduce_kernel<<<(unsigned)((dw_size + 255) / 256), 256, 0, s>>>(part, slabs, dw_size, dw);
   YB_CUDA_CHECK(cudaGetLastError());
+  YB_CUDA_CHECK(cudaFreeAsync(part, s));
   return YB_OK;
 }
 
