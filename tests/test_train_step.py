@@ -81,3 +81,54 @@ def test_train_step_kernels_gpu():
     import yolosharp_b200  # noqa: F401  (fails loudly without the CUDA library)
     from yolosharp_b200.train import KernelOps, TrainStepV8
     _compare(TrainStepV8, KernelOps(), "cuda", 1e-3)
+
+
+def test_lr_schedule_and_warmup():
+    """LrLambda / OneCycle / Interp / warm-up restated from YoloBaseTaskModel.cs:307-319, 492-536."""
+    from yolosharp_b200.train import interp, lr_lambda_linear, lr_lambda_onecycle, warmup_lrs
+    assert lr_lambda_linear(0, 0.01, 100) == 1.0 and abs(lr_lambda_linear(100, 0.01, 100) - 0.01) < 1e-12
+    assert abs(lr_lambda_linear(50, 0.01, 100) - 0.505) < 1e-12 and lr_lambda_linear(150, 0.01, 100) == 0.01
+    assert lr_lambda_onecycle(0, 0.01, 100) == 1.0 and abs(lr_lambda_onecycle(100, 0.01, 100) - 0.01) < 1e-12
+    assert abs(lr_lambda_onecycle(50, 0.01, 100) - 0.505) < 1e-12
+    assert interp(-1, [0, 10], [3, 5]) == 3 and interp(11, [0, 10], [3, 5]) == 5 and interp(5, [0, 10], [3, 5]) == 4
+    lr0 = round(0.002 * 5 / (4 + 80), 6)
+    assert lr0 == 0.000119
+    b, o = warmup_lrs(0, 300, lr0, 1.0)
+    assert b == 0.1 and o == 0.0                       # bias group starts at WarmUpBiasLr, the others at 0
+    b, o = warmup_lrs(150, 300, lr0, 1.0)
+    assert abs(b - (0.1 + lr0) / 2) < 1e-12 and abs(o - lr0 / 2) < 1e-12
+    assert warmup_lrs(301, 300, lr0, 1.0) is None
+
+
+def test_train_step_param_groups_cpu():
+    """Two steps with different learning rates for the "bias" group and the rest (warm-up) against
+    torch.optim.AdamW with the same two parameter groups."""
+    from tests.torch_train_ops import TorchOps
+    from yolosharp_b200.train import TrainStepV8
+    torch.manual_seed(0)
+    m = oracle_model("v8", "detect", "n")
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    B, H, W = 2, 64, 64
+    x, targets = synth_image(B, H, W), _targets(B, seed=3)
+    m.train()
+    named = [(k, p) for k, p in m.named_parameters() if ".dfl." not in k]
+    groups = [{"params": [p for k, p in named if "bias" in k]}, {"params": [p for k, p in named if "bias" not in k]}]
+    opt = torch.optim.AdamW(groups, lr=1e-3, weight_decay=5e-4)
+    crit = oloss.V8DetectionLoss(80)
+    batch = {"batch_idx": targets[:, 0], "cls": targets[:, 1], "bboxes": targets[:, 2:]}
+    ts = TrainStepV8(sd0, "n", 80, device="cpu", ops=TorchOps(), lr=1e-3)
+    for lrs in ((0.05, 1e-4), (0.02, 3e-4)):
+        opt.param_groups[0]["lr"], opt.param_groups[1]["lr"] = lrs
+        _, preds = m(x)
+        loss, _ = crit(preds, batch)
+        opt.zero_grad()
+        loss.sum().backward()
+        opt.step()
+        ts.step(x, targets, lrs=lrs)
+    new = m.state_dict()
+    bad = 0
+    for k, _ in named:
+        d = (ts.P.p(k).detach() - new[k].detach()).abs()
+        assert float(d.max()) <= 2.1 * 2 * 0.05, k      # sign-of-noise elements move by at most lr per step
+        bad += int((d > 1e-4 + 1e-3 * new[k].detach().abs()).sum())
+    assert bad < 0.01 * ts.P.flat.numel(), bad

@@ -12,12 +12,47 @@ This is the PARITY path of the training side: correct first (it matches autograd
 parameter by parameter), CUDA-core fp32 kernels; the tcgen05 dgrad / wgrad kernels and a captured train-mode graph
 replace it next.  Parameter names are the reference's state_dict keys (`model.{i}.conv.weight`, ...).
 """
+import math
+
 import torch
 import torch.nn.functional as F
 
 V8_SIZES = {  # Models/Yolo.cs:45-49 (depth_multiple, width_multiple, max_channels)
     "n": (0.34, 0.25, 1024), "s": (0.34, 0.5, 1024), "m": (0.67, 0.75, 576), "l": (1.0, 1.0, 512), "x": (1.0, 1.25, 640),
 }
+
+
+def lr_lambda_linear(epoch, lrf=0.01, epochs=100):
+    """LrLambda(1.0, Lrf, Epochs), YoloBaseTaskModel.cs:504-512."""
+    return max(1 - epoch / epochs, 0) * (1.0 - lrf) + lrf
+
+
+def lr_lambda_onecycle(epoch, lrf=0.01, epochs=100):
+    """OneCycle(1.0, Lrf, Epochs), YoloBaseTaskModel.cs:492-502 (UseCosLR)."""
+    return max((1 - math.cos(epoch * math.pi / epochs)) / 2, 0) * (lrf - 1.0) + 1.0
+
+
+def interp(x, xp, fp):
+    """YoloBaseTaskModel.cs:514-536 (two-point use: clamp outside, linear inside)."""
+    if x <= xp[0]:
+        return fp[0]
+    if x >= xp[-1]:
+        return fp[-1]
+    for i in range(1, len(xp)):
+        if x == xp[i]:
+            return fp[i]
+        if x < xp[i]:
+            t = (x - xp[i - 1]) / (xp[i] - xp[i - 1])
+            return fp[i - 1] + t * (fp[i] - fp[i - 1])
+
+
+def warmup_lrs(ni, nw, initial_lr, lam, warmup_bias_lr=0.1):
+    """Per-group learning rates during warm-up (YoloBaseTaskModel.cs:307-319): the FIRST parameter group (names
+    containing "bias") ramps from WarmUpBiasLr, the others from 0, to initial_lr * lambda(epoch); None after warm-up."""
+    if ni > nw:
+        return None
+    d = initial_lr * lam
+    return interp(ni, [0, nw], [warmup_bias_lr, d]), interp(ni, [0, nw], [0.0, d])
 
 
 class KernelOps:
@@ -51,8 +86,14 @@ class _Params:
     """Flat parameter / gradient / Adam-moment buffers with named views (one optimizer launch, one all-reduce)."""
 
     def __init__(self, state_dict, device):
-        self.names = [k for k, v in state_dict.items() if v.dtype.is_floating_point and v.numel() > 0 and
-                      not k.endswith(("running_mean", "running_var")) and ".dfl." not in k]
+        names = [k for k, v in state_dict.items() if v.dtype.is_floating_point and v.numel() > 0 and
+                 not k.endswith(("running_mean", "running_var")) and ".dfl." not in k]
+        # the reference's optimizer groups by name substring (YoloBaseTaskModel.cs:144-153): group 0 = "bias", then
+        # "weight"; the flat buffers keep each group contiguous so a group is one optimizer launch with its own lr.
+        # (BatchNorm parameters also match the third filter "bn"; whether TorchSharp then steps them twice cannot be
+        # verified here - they are stepped once.)
+        self.names = [k for k in names if "bias" in k] + [k for k in names if "bias" not in k]
+        self.n_bias = sum(int(state_dict[k].numel()) for k in names if "bias" in k)
         self.shapes = {k: tuple(state_dict[k].shape) for k in self.names}
         n = sum(int(torch.Size(self.shapes[k]).numel()) for k in self.names)
         self.flat = torch.zeros(n, dtype=torch.float32, device=device)
@@ -301,14 +342,19 @@ class TrainStepV8:
                 dx = m.backward(dx.contiguous())
         return dx
 
-    def step(self, images_nchw, targets):
-        """images (B,3,H,W) float32 in [0,1] on the device; targets (n,6) rows [image, cls, x, y, w, h].
-        -> loss items (3,) (= the reference's `loss.detach()`)."""
+    def step(self, images_nchw, targets, lrs=None):
+        """images (B,3,H,W) float32 in [0,1] on the device; targets (n,6) rows [image, cls, x, y, w, h];
+        lrs = (lr of the "bias" group, lr of the other parameters) for this iteration (warm-up / schedule), default
+        the constant initial lr.  -> loss items (3,) (= the reference's `loss.detach()`)."""
         B, _, H, W = images_nchw.shape
         boxes, scores = self.forward(images_nchw)
         items, gb, gs = self.ops.detection_loss(boxes, scores, targets, H, W)
         self.P.grad.zero_()
         self.backward(gb, gs)
         self.step_count += 1
-        self.ops.adamw(self.P.flat, self.P.grad, self.P.m, self.P.v, self.step_count, self.lr, self.wd)
+        lr_bias, lr_other = lrs if lrs is not None else (self.lr, self.lr)
+        nb = self.P.n_bias
+        for lo, hi, lr in ((0, nb, lr_bias), (nb, self.P.flat.numel(), lr_other)):
+            if hi > lo:
+                self.ops.adamw(self.P.flat[lo:hi], self.P.grad[lo:hi], self.P.m[lo:hi], self.P.v[lo:hi], self.step_count, lr, self.wd)
         return items
