@@ -52,3 +52,26 @@ class TorchOps:
         v.mul_(b2).addcmul_(g, g, value=1 - b2)
         denom = (v.sqrt() / (1 - b2 ** step) ** 0.5).add_(eps)
         p.addcdiv_(m, denom, value=-lr / (1 - b1 ** step))
+
+    # ---- v11 extras (no library kernels yet: tests/test_train_step.py checks the graph logic only) ----
+    def gconv_forward(self, x, w, stride, pad, groups):
+        return F.conv2d(x.permute(0, 3, 1, 2), w, None, stride, pad, 1, groups).permute(0, 2, 3, 1).contiguous()
+
+    def gconv_backward(self, x, dz, w, stride, pad, groups):
+        xn, dzn = x.permute(0, 3, 1, 2), dz.permute(0, 3, 1, 2)
+        dx = torch.nn.grad.conv2d_input(xn.shape, w, dzn, stride, pad, 1, groups)
+        dw = torch.nn.grad.conv2d_weight(xn, w.shape, dzn, stride, pad, 1, groups)
+        return dx.permute(0, 2, 3, 1).contiguous(), dw
+
+    @staticmethod
+    def _attn(q, k, v, scale):
+        # q, k (B, N, nh, kd), v (B, N, nh, hd): out[b, n, h] = sum_m softmax_m(q_n . k_m * scale) v_m
+        a = torch.einsum("bnhd,bmhd->bhnm", q, k) * scale
+        return torch.einsum("bhnm,bmhd->bnhd", a.softmax(-1), v)
+
+    def attention_forward(self, q, k, v, scale):
+        return self._attn(q, k, v, scale)
+
+    def attention_backward(self, q, k, v, scale, dout):
+        q, k, v = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+        return torch.autograd.grad(self._attn(q, k, v, scale), (q, k, v), dout)
