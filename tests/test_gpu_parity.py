@@ -60,8 +60,8 @@ def test_nms_golden_bit_exact(y):
                                                    (13, 3, 2, 2100, 0.5, 4), (14, 1, 1, 33, 1.0, None),
                                                    (15, 2, 80, 20000, 0.1, None)])
 def test_nms_random_vs_oracle(y, seed, B, nc, A, frac, quant):
-    """Ties (quantised scores/boxes), every-anchor-is-a-candidate, single class, A > 16384 (global
-    memory sort path)."""
+    """Ties (quantised scores/boxes), every-anchor-is-a-candidate (8400 > 4096: general path, shared-memory sort),
+    single class, 20000 anchors (key capacity above the shared-memory sort size; ~2000 candidates: fast path)."""
     pred = nms_case(seed, B, nc, A, 0, 1.0, quant, frac)
     for conf, iou in ((0.25, 0.45), (0.1, 0.7), (0.6, 0.3)):
         out, keepi = oops.non_max_suppression(pred, conf, iou, nc=nc)
