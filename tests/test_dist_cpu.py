@@ -119,3 +119,50 @@ def test_grad_bucket_allreduce_world2():
         p.join(60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _ddp_step_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.test_train_step import _targets
+        from tests.torch_train_ops import TorchOps
+        from tests.util import oracle_model, synth_image
+        from yolosharp_b200.train import TrainStepV8
+        torch.manual_seed(0)
+        m = oracle_model("v8", "detect", "n")
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        x = synth_image(2, 64, 64, seed=10 + rank)       # every rank has its own shard of the global batch
+        t = _targets(2, seed=20 + rank)
+        solo = TrainStepV8(sd, "n", 80, device="cpu", ops=TorchOps(), lr=1e-3)
+        solo.group = False                                 # this rank's gradient alone
+        solo.step(x, t)
+        g_local = solo.P.grad.clone()
+        ddp = TrainStepV8(sd, "n", 80, device="cpu", ops=TorchOps(), lr=1e-3)
+        ddp.step(x, t)
+        gathered = [torch.zeros_like(g_local) for _ in range(world)]
+        dist.all_gather(gathered, g_local)
+        ok = torch.allclose(ddp.P.grad, sum(gathered), rtol=1e-5, atol=1e-6)
+        weights = [torch.zeros_like(ddp.P.flat) for _ in range(world)]
+        dist.all_gather(weights, ddp.P.flat)
+        ok = ok and all(torch.equal(weights[0], w) for w in weights)   # replicas stay bit-identical
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_train_step_world2():
+    """Two ranks, each a shard of the batch: after the flat all-reduce every rank holds the SUM of the ranks' gradients
+    and the AdamW step leaves the replicas bit-identical (train.py, SURVEY.md section 8(e) for the training path)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_step_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]

@@ -283,6 +283,7 @@ class TrainStepV8:
         w = [min(int(x * wm), mc) for x in (64, 128, 256, 512, 1024)]
         dp = [int(x * d) for x in (3, 6, 9)]
         self.nc, self.step_count = nc, 0
+        self.group = None  # process group of the gradient all-reduce (None = default group, False = never reduce)
         self.lr = lr if lr is not None else round(0.002 * 5 / (4 + nc), 6)  # YoloBaseTaskModel.cs:142
         self.wd = weight_decay
         N = self
@@ -351,6 +352,12 @@ class TrainStepV8:
         items, gb, gs = self.ops.detection_loss(boxes, scores, targets, H, W)
         self.P.grad.zero_()
         self.backward(gb, gs)
+        # data-parallel: ONE all-reduce of the flat gradient buffer (NCCL on GPUs, gloo in the CPU tests); ranks are
+        # summed, not averaged - the reference scales the loss by the local batch size (Loss.cs:473).  BatchNorm
+        # statistics stay per rank, as in the reference (no SyncBN).
+        if self.group is not False and torch.distributed.is_available() and torch.distributed.is_initialized() and \
+                torch.distributed.get_world_size(self.group) > 1:
+            torch.distributed.all_reduce(self.P.grad, group=self.group)
         self.step_count += 1
         lr_bias, lr_other = lrs if lrs is not None else (self.lr, self.lr)
         nb = self.P.n_bias

@@ -249,6 +249,7 @@ class TrainStepV11(TrainStepV8):
         w = [min(int(x * wm), mc) for x in (64, 128, 256, 512, 1024)]
         n = int(2 * d)
         self.nc, self.step_count = nc, 0
+        self.group = None
         self.lr = lr if lr is not None else round(0.002 * 5 / (4 + nc), 6)
         self.wd = weight_decay
         N = self
