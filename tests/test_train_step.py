@@ -145,3 +145,30 @@ def test_train_step_v11_graph_logic_cpu():
     _compare(TrainStepV11, TorchOps(), "cpu", 2e-4, arch="v11")
     with pytest.raises(NotImplementedError):
         KernelOpsV11.gconv_forward(None, None, None, 1, 1, 1)
+
+
+def test_fit_loop_learning_rates():
+    """Epoch loop: warm-up per iteration, lambda per epoch, target-less batches skipped (YoloBaseTaskModel.cs:289-345)."""
+    from yolosharp_b200.train import fit, lr_lambda_linear
+
+    class FakeStep:
+        lr = 1e-3
+
+        def __init__(self):
+            self.calls = []
+
+        def step(self, images, targets, lrs=None):
+            self.calls.append(lrs)
+            return torch.tensor([1.0, 2.0, 3.0])
+    batches = [(None, torch.zeros(2, 6)), (None, torch.zeros(0, 6)), (None, torch.zeros(1, 6))] * 20  # nb = 60
+    st = FakeStep()
+    hist = fit(st, batches, epochs=3, lrf=0.01, warmup_epochs=1)
+    assert len(st.calls) == 3 * 40 and len(hist) == 3 and torch.equal(hist[0], torch.tensor([1.0, 2.0, 3.0]))
+    nw = 100                                            # max(1 * 60, 100)
+    b0, o0 = st.calls[0]
+    assert b0 == 0.1 and o0 == 0.0                      # ni = 0
+    # iteration i = 2 of epoch 1 -> ni = 62 (the 42nd executed call: 40 per epoch + 2 of 3 batches)
+    b, o = st.calls[41]
+    d = 1e-3 * lr_lambda_linear(1, 0.01, 3)
+    assert abs(o - 62 / nw * d) < 1e-12 and abs(b - (0.1 + 62 / nw * (d - 0.1))) < 1e-12
+    assert st.calls[-1] == (1e-3 * lr_lambda_linear(2, 0.01, 3),) * 2   # past warm-up: scheduler value of epoch 2

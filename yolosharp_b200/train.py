@@ -365,3 +365,30 @@ class TrainStepV8:
             if hi > lo:
                 self.ops.adamw(self.P.flat[lo:hi], self.P.grad[lo:hi], self.P.m[lo:hi], self.P.v[lo:hi], self.step_count, lr, self.wd)
         return items
+
+
+def fit(step, batches, epochs, lrf=0.01, warmup_epochs=3, warmup_bias_lr=0.1, cos_lr=False, on_iteration=None):
+    """The reference's epoch loop around the training step (YoloBaseTaskModel.cs:167-170, 289-345): per iteration the
+    warm-up interpolation of the per-group learning rates while ni <= nw = max(warmup_epochs * nb, 100), afterwards
+    lr = initial_lr * lambda(epoch) (LambdaLR stepped once per epoch); batches without targets are skipped (:321-324).
+    `batches` is a re-iterable of (images (B,3,H,W) float32 on the device, targets (n,6)) - data loading and
+    augmentation are outside this library.  Returns the per-epoch mean of the loss items."""
+    lam = lr_lambda_onecycle if cos_lr else lr_lambda_linear
+    nb = len(batches)
+    nw = max(warmup_epochs * nb, 100)
+    history = []
+    for epoch in range(epochs):
+        total, count = None, 0
+        lam_e = lam(epoch, lrf, epochs)
+        for i, (images, targets) in enumerate(batches):
+            ni = i + nb * epoch
+            lrs = warmup_lrs(ni, nw, step.lr, lam_e, warmup_bias_lr) or (step.lr * lam_e, step.lr * lam_e)
+            if len(targets) < 1:
+                continue
+            items = step.step(images, targets, lrs=lrs)
+            if on_iteration is not None:
+                on_iteration(epoch, i, lrs, items)
+            total = items.detach().clone() if total is None else total + items.detach()
+            count += 1
+        history.append(total / max(count, 1) if total is not None else None)
+    return history
