@@ -153,3 +153,41 @@ def to_yolo_results(rows):
         res.append(dict(ClassID=int(r[5]), Score=float(np.float32(r[4])),
                         CenterX=x + int(rw / 2), CenterY=y + int(rh / 2), Width=rw, Height=rh))
     return res
+
+
+def clip_boxes(x, shape):
+    """Ops.cs:150-158: x to [0, shape[1]], y to [0, shape[0]]."""
+    box = torch.zeros_like(x)
+    box[..., 0] = x[..., 0].clamp(0, shape[1])
+    box[..., 1] = x[..., 1].clamp(0, shape[0])
+    box[..., 2] = x[..., 2].clamp(0, shape[1])
+    box[..., 3] = x[..., 3].clamp(0, shape[0])
+    return box
+
+
+def detector_predict(model, img_u8_chw, conf, iou, pre=preprocess):
+    """Models/Detector.cs:27-72 on an oracle model: -> (rows (n,6), keep, YoloResult dicts)."""
+    with torch.no_grad():
+        pred = model(pre(img_u8_chw))[0]["boxes"]
+    out, keep = non_max_suppression(pred, conf, iou)
+    return out[0], keep[0], to_yolo_results(out[0])
+
+
+def segmenter_predict(model, img_u8_chw, conf, iou, nc=80, pre=preprocess):
+    """Models/Segmenter.cs:28-84 on an oracle segment model: -> (rows (n,38) with boxes clipped to the original
+    image, masks uint8 (n, h, w) at the ORIGINAL size, YoloResult dicts).  Masks are computed on the padded input
+    and then resized - not cropped - to the original size (reference behaviour, :56-57); the `.byte()` cast
+    truncates the bilinear values, so only exact ones survive."""
+    h, w = int(img_u8_chw.shape[1]), int(img_u8_chw.shape[2])
+    x = pre(img_u8_chw)
+    with torch.no_grad():
+        inf = model(x)[0]
+    out, _ = non_max_suppression(inf["boxes"], conf, iou, nc=nc)
+    rows = out[0].clone()
+    if rows.shape[0] == 0:
+        return rows, torch.zeros((0, h, w), dtype=torch.uint8), []
+    masks = process_mask(inf["proto"][0], rows[:, 6:], rows[:, :4], (x.shape[2], x.shape[3]), upsample=True)
+    rows[:, :4] = clip_boxes(rows[:, :4], (h, w))
+    if (x.shape[2], x.shape[3]) != (h, w):
+        masks = torch.nn.functional.interpolate(masks[None].float(), size=(h, w), mode="bilinear", align_corners=False)[0]
+    return rows, masks.to(torch.uint8), to_yolo_results(rows)

@@ -166,3 +166,47 @@ def test_data_parallel_train_step_world2():
         p.join(120)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _fit_empty_shard_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.test_train_step import _targets
+        from tests.torch_train_ops import TorchOps
+        from tests.util import oracle_model, synth_image
+        from yolosharp_b200.train import TrainStepV8, fit
+        torch.manual_seed(0)
+        m = oracle_model("v8", "detect", "n")
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        st = TrainStepV8(sd, "n", 80, device="cpu", ops=TorchOps(), lr=1e-3)
+        x = synth_image(2, 64, 64, seed=30 + rank)
+        empty = torch.zeros(0, 6)
+        # iteration 0: rank 1's shard has no targets (it must still enter the collective);
+        # iteration 1: NO rank has targets (skipped everywhere); iteration 2: both have targets
+        batches = [(x, _targets(2, seed=40) if rank == 0 else empty), (x, empty), (x, _targets(2, seed=41 + rank))]
+        calls = []
+        fit(st, batches, epochs=1, on_iteration=lambda e, i, lrs, items: calls.append((e, i)))
+        weights = [torch.zeros_like(st.P.flat) for _ in range(world)]
+        dist.all_gather(weights, st.P.flat)
+        ok = calls == [(1, 0), (1, 1)] and st.step_count == 2 and all(torch.equal(weights[0], w) for w in weights)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fit_with_an_empty_shard_world2():
+    """a rank whose shard has no targets must not skip the step alone (the gradient all-reduce would
+    mispair): a batch is skipped only when every rank is empty; replicas and step counts stay identical."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fit_empty_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]

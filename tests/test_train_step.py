@@ -165,10 +165,18 @@ def test_fit_loop_learning_rates():
     hist = fit(st, batches, epochs=3, lrf=0.01, warmup_epochs=1)
     assert len(st.calls) == 3 * 40 and len(hist) == 3 and torch.equal(hist[0], torch.tensor([1.0, 2.0, 3.0]))
     nw = 100                                            # max(1 * 60, 100)
+    # the reference's epochs are 1-based and `i` counts executed batches only: the first call has ni = 0 + 60 * 1
+    d1 = 1e-3 * lr_lambda_linear(1, 0.01, 3)
     b0, o0 = st.calls[0]
-    assert b0 == 0.1 and o0 == 0.0                      # ni = 0
-    # iteration i = 2 of epoch 1 -> ni = 62 (the 42nd executed call: 40 per epoch + 2 of 3 batches)
-    b, o = st.calls[41]
-    d = 1e-3 * lr_lambda_linear(1, 0.01, 3)
-    assert abs(o - 62 / nw * d) < 1e-12 and abs(b - (0.1 + 62 / nw * (d - 0.1))) < 1e-12
-    assert st.calls[-1] == (1e-3 * lr_lambda_linear(2, 0.01, 3),) * 2   # past warm-up: scheduler value of epoch 2
+    assert abs(o0 - 60 / nw * d1) < 1e-12 and abs(b0 - (0.1 + 60 / nw * (d1 - 0.1))) < 1e-12
+    # executed call 40 of epoch 1 has i = 39 -> ni = 99 <= nw: still warming up
+    b, o = st.calls[39]
+    assert abs(o - 99 / nw * d1) < 1e-12
+    # epoch 2 starts at ni = 120 > nw: LambdaLR was stepped once after epoch 1 -> InitialLR * lambda(1)
+    assert st.calls[40] == (d1,) * 2
+    assert st.calls[-1] == (1e-3 * lr_lambda_linear(2, 0.01, 3),) * 2   # epoch 3: lambda(2)
+    # warm-up that ends in the middle of an epoch leaves the last interpolated value in place (never reset)
+    st2 = FakeStep()
+    fit(st2, [(None, torch.zeros(1, 6))] * 70, epochs=1, lrf=0.01, warmup_epochs=1)   # nb = 70, nw = 100, ni = 70 .. 139
+    d = 1e-3 * lr_lambda_linear(1, 0.01, 1)
+    assert abs(st2.calls[30][1] - d) < 1e-15 and st2.calls[31] == st2.calls[30] == st2.calls[-1]   # ni = 100 is the last update

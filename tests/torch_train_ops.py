@@ -42,8 +42,8 @@ class TorchOps:
         t = torch.as_tensor(targets, dtype=torch.float32).reshape(-1, 6)
         batch = {"batch_idx": t[:, 0], "cls": t[:, 1], "bboxes": t[:, 2:]}
         loss, items = crit({"boxes": b, "scores": s, "feats": feats}, batch)
-        gb, gs = torch.autograd.grad(loss.sum(), (b, s))
-        return items, gb, gs
+        gb, gs = torch.autograd.grad(loss.sum(), (b, s), allow_unused=True)  # no targets: the box branch is unused
+        return items, gb if gb is not None else torch.zeros_like(b), gs if gs is not None else torch.zeros_like(s)
 
     def adamw(self, p, g, m, v, step, lr, wd):
         b1, b2, eps = 0.9, 0.999, 1e-8

@@ -367,28 +367,48 @@ class TrainStepV8:
         return items
 
 
-def fit(step, batches, epochs, lrf=0.01, warmup_epochs=3, warmup_bias_lr=0.1, cos_lr=False, on_iteration=None):
-    """The reference's epoch loop around the training step (YoloBaseTaskModel.cs:167-170, 289-345): per iteration the
-    warm-up interpolation of the per-group learning rates while ni <= nw = max(warmup_epochs * nb, 100), afterwards
-    lr = initial_lr * lambda(epoch) (LambdaLR stepped once per epoch); batches without targets are skipped (:321-324).
+def fit(step, batches, epochs, lrf=0.01, warmup_epochs=3, warmup_bias_lr=0.1, cos_lr=False, on_iteration=None, group=None):
+    """The reference's epoch loop around the training step, restated index for index
+    (YoloBaseTaskModel.cs:167-170 Train, :291-356 TrainEpoch):
+      * epochs run 1 .. Epochs; inside an epoch `i` counts the EXECUTED batches only (the `continue` of a target-less
+        batch skips the `i++`, :321-324 / :353), ni = i + nb * epoch - so warm-up starts at ni = nb, not 0;
+      * while ni <= nw = max(WarmUpEpoches * nb, 100) both parameter groups are set to
+        interp(ni, [0, nw], [WarmUpBiasLr | 0, InitialLR * lambda(epoch)]) (:307-319);
+      * LambdaLR is stepped once AFTER each epoch (:182): past warm-up the rate during epoch e is
+        InitialLR * lambda(e - 1); when warm-up ends in the middle of an epoch the groups keep the last interpolated
+        value until that step (the reference never resets them).
+    Data parallelism (net-new, the reference is single-device): `step.step` all-reduces gradients, so a rank must not
+    skip it alone - a batch is skipped only when EVERY rank of `group` has no targets (one all-reduce of a flag per
+    iteration); a rank with an empty shard calls step() with zero targets (the loss kernels handle n_targets = 0).
     `batches` is a re-iterable of (images (B,3,H,W) float32 on the device, targets (n,6)) - data loading and
     augmentation are outside this library.  Returns the per-epoch mean of the loss items."""
     lam = lr_lambda_onecycle if cos_lr else lr_lambda_linear
     nb = len(batches)
     nw = max(warmup_epochs * nb, 100)
+    dp = group is not False and torch.distributed.is_available() and torch.distributed.is_initialized() and \
+        torch.distributed.get_world_size(group) > 1
     history = []
-    for epoch in range(epochs):
-        total, count = None, 0
-        lam_e = lam(epoch, lrf, epochs)
-        for i, (images, targets) in enumerate(batches):
+    lrs = (step.lr * lam(0, lrf, epochs),) * 2  # LambdaLR construction: InitialLR * lambda(0)
+    for epoch in range(1, epochs + 1):
+        total, count, i = None, 0, 0
+        for images, targets in batches:
             ni = i + nb * epoch
-            lrs = warmup_lrs(ni, nw, step.lr, lam_e, warmup_bias_lr) or (step.lr * lam_e, step.lr * lam_e)
-            if len(targets) < 1:
+            w = warmup_lrs(ni, nw, step.lr, lam(epoch, lrf, epochs), warmup_bias_lr)
+            if w is not None:
+                lrs = w
+            has = len(targets) >= 1
+            if dp:
+                flag = torch.tensor([1.0 if has else 0.0], device=step.P.grad.device if hasattr(step, "P") else "cpu")
+                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX, group=group)
+                has = bool(flag.item() > 0)
+            if not has:
                 continue
             items = step.step(images, targets, lrs=lrs)
             if on_iteration is not None:
                 on_iteration(epoch, i, lrs, items)
             total = items.detach().clone() if total is None else total + items.detach()
             count += 1
+            i += 1
+        lrs = (step.lr * lam(epoch, lrf, epochs),) * 2  # lr_scheduler.step() after the epoch
         history.append(total / max(count, 1) if total is not None else None)
     return history
