@@ -208,6 +208,40 @@ int32_t yb_predict_u8_submit(yb_engine* e, int32_t slot, const uint8_t* images_h
                              int32_t* counts_host);
 int32_t yb_predict_u8_wait(yb_engine* e, int32_t slot);
 
+/* ---- multi-GPU: exchange of the fixed-capacity detection payloads over NVLink peer memory (csrc/comm.cu) ----
+ * Design target SURVEY.md section 8(e); the reference is single-device (Data/Config.cs:301), so this surface is
+ * net-new.  One yb_comm per process (= per GPU), all ranks on one node.  Every rank pushes its payload into a
+ * window of every peer with plain stores through cudaIpc-mapped pointers and publishes a sequence flag; consumers
+ * poll flags in their own memory - no collective kernel has to be co-resident on all ranks.
+ *   1. yb_comm_create on every rank (same world / bytes_per_rank / slots)
+ *   2. yb_comm_local_handle -> exchange the yb_comm_handle_bytes() opaque bytes by any host channel
+ *      (torch.distributed, MPI, files) -> yb_comm_connect with all ranks' handles in rank order
+ *   3. per step: producer kernels write the payload into yb_comm_send_buffer(slot); yb_comm_allgather(slot, stream);
+ *      after it (stream order) yb_comm_window(slot) holds world x bytes_per_rank, rank r at offset r * bytes_per_rank;
+ *      yb_comm_release(slot, stream) once the consumer is done (peers may then overwrite the slot). */
+typedef struct yb_comm yb_comm;
+int32_t yb_comm_handle_bytes(void);
+int32_t yb_comm_create(int32_t rank, int32_t world, int32_t device, int64_t bytes_per_rank, int32_t slots, yb_comm** out);
+int32_t yb_comm_local_handle(yb_comm* c, void* handle_out);
+int32_t yb_comm_connect(yb_comm* c, const void* handles /* world x yb_comm_handle_bytes(), rank order */);
+int32_t yb_comm_info(const yb_comm* c, int32_t* rank, int32_t* world, int64_t* bytes_per_rank, int32_t* slots);
+void* yb_comm_send_buffer(yb_comm* c, int32_t slot);
+void* yb_comm_window(yb_comm* c, int32_t slot);
+int32_t yb_comm_allgather(yb_comm* c, int32_t slot, void* stream);
+int32_t yb_comm_release(yb_comm* c, int32_t slot, void* stream);
+void yb_comm_destroy(yb_comm* c);
+/* bytes of one rank's detection payload: dets (batch, max_det, row_width) float32 followed by counts (batch) int32,
+ * each padded to 16 bytes - the layout yb_predict_u8_submit_gather and bench.py use */
+int64_t yb_comm_detection_payload_bytes(int32_t batch, int32_t max_det, int32_t row_width);
+
+/* yb_predict_u8_submit for a batch sharded over `world` GPUs (BASELINE configs[2]): as yb_predict_u8_submit, but the
+ * NMS rows of every rank are exchanged through `comm` slot `slot` before the D2H copy, so all_dets_host
+ * (world*batch, max_det, 6[+32]) / all_counts_host (world*batch) receive the detections of ALL ranks in global
+ * image order.  Every rank must call it with the same batch / max_det; wait with yb_predict_u8_wait(slot). */
+int32_t yb_predict_u8_submit_gather(yb_engine* e, yb_comm* comm, int32_t slot, const uint8_t* images_host, int32_t batch,
+                                    float conf_thres, float iou_thres, int32_t max_det, float* all_dets_host,
+                                    int32_t* all_counts_host);
+
 /* Debug / profiling helpers (not part of the reference surface). */
 int32_t yb_num_ops(const yb_engine* e);
 /* copy the activation written by op `op_index` (NHWC -> NCHW float32 host buffer); returns
@@ -221,6 +255,11 @@ int32_t yb_launches_per_forward(const yb_engine* e);
  * `stream`; ms_per_op[i] (i < yb_num_ops) receives the device time of op i. */
 int32_t yb_profile_forward(yb_engine* e, const void* in, int32_t in_dtype, int32_t batch, float* out_pred,
                            float* out_proto, float* ms_per_op, int32_t n_ops, void* stream);
+/* Back-to-back timing of ONE op: `reps` launches of op `op_index` between two CUDA events on `stream`, on the data
+ * the last forward left in the engine's buffers (launch gaps amortised; used by bench.py to take the non-conv
+ * kernels out of the graph-timed forward when it reports the dominant kernel's in-graph time). */
+int32_t yb_time_op(yb_engine* e, int32_t op_index, const void* in, int32_t in_dtype, int32_t batch, float* out_pred,
+                   float* out_proto, int32_t reps, float* ms_per_launch, void* stream);
 /* Algorithmic work of op i for `batch` images: flops = 2*MACs (convs only), bytes = input view +
  * output view (+ residual) + weights, each counted once (SURVEY.md section 8(d) definitions). */
 int32_t yb_op_cost(const yb_engine* e, int32_t op_index, int32_t batch, double* flops, double* bytes);

@@ -210,3 +210,39 @@ def test_fit_with_an_empty_shard_world2():
         p.join(120)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _gather_packed_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = ydist.DetectionGather(3, 5, 6, torch.device("cpu"), mode="nccl", slots=2)  # "nccl" = the process group's all-gather
+        ok = True
+        for step in range(4):
+            d, c = g.local_buffers(step & 1)
+            d.copy_(torch.arange(3 * 5 * 6, dtype=torch.float32).view(3, 5, 6) + 1000 * rank + step)
+            c.copy_(torch.tensor([1, 2, 3], dtype=torch.int32) + 10 * rank + step)
+            g.gather(step & 1)
+            gd, gc = g.gathered(step & 1)
+            for r in range(world):
+                ok = ok and torch.equal(gd[3 * r:3 * r + 3], torch.arange(90, dtype=torch.float32).view(3, 5, 6) + 1000 * r + step)
+                ok = ok and torch.equal(gc[3 * r:3 * r + 3], torch.tensor([1, 2, 3], dtype=torch.int32) + 10 * r + step)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_packed_detection_gather_world2():
+    """One all-gather of the packed (dets + counts) payload: the layout the peer-memory exchange uses on GPUs."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_packed_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]

@@ -52,11 +52,24 @@ SIGNATURES = {
     "yb_predict_u8": (c_i32, [c_vp, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp]),
     "yb_predict_u8_submit": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp]),
     "yb_predict_u8_wait": (c_i32, [c_vp, c_i32]),
+    "yb_predict_u8_submit_gather": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp]),
+    "yb_comm_handle_bytes": (c_i32, []),
+    "yb_comm_create": (c_i32, [c_i32, c_i32, c_i32, C.c_int64, c_i32, C.POINTER(c_vp)]),
+    "yb_comm_local_handle": (c_i32, [c_vp, c_vp]),
+    "yb_comm_connect": (c_i32, [c_vp, c_vp]),
+    "yb_comm_info": (c_i32, [c_vp, C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(C.c_int64), C.POINTER(c_i32)]),
+    "yb_comm_send_buffer": (c_vp, [c_vp, c_i32]),
+    "yb_comm_window": (c_vp, [c_vp, c_i32]),
+    "yb_comm_allgather": (c_i32, [c_vp, c_i32, c_vp]),
+    "yb_comm_release": (c_i32, [c_vp, c_i32, c_vp]),
+    "yb_comm_destroy": (None, [c_vp]),
+    "yb_comm_detection_payload_bytes": (C.c_int64, [c_i32, c_i32, c_i32]),
     "yb_num_ops": (c_i32, [c_vp]),
     "yb_debug_read_activation": (c_i32, [c_vp, c_i32, c_i32, c_vp, C.c_int64, C.POINTER(c_i32 * 3)]),
     "yb_op_name": (c_cp, [c_vp, c_i32]),
     "yb_launches_per_forward": (c_i32, [c_vp]),
     "yb_profile_forward": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp]),
+    "yb_time_op": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, C.POINTER(c_f32), c_vp]),
     "yb_op_cost": (c_i32, [c_vp, c_i32, c_i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "yb_op_kind": (c_i32, [c_vp, c_i32]),
     "yb_debug_timeline": (c_i32, [c_vp, c_i32]),

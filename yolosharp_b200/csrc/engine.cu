@@ -679,17 +679,19 @@ static ConvParams conv_params(const yb_engine* e, const OpDesc& op, int B) {
 
 template <typename T>
 static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out_pred, float* out_proto,
-                   cudaStream_t s, cudaEvent_t* events = nullptr) {
+                   cudaStream_t s, cudaEvent_t* events = nullptr, int only = -1) {
   int rc;
   bool input_converted = false;
   // Head branches are independent chains of small, latency-bound kernels: with every Detect tail fused
   // (tcgen05 path) they run on side streams forked at the op that completes their feature map and are
   // joined at the end; inside a captured CUDA graph this becomes real branch parallelism.
-  const bool lanes = e->lanes_ok && !events;
+  const bool lanes = e->lanes_ok && !events && only < 0;
   bool lane_started[yb_engine::kLanes] = {};
   cudaStream_t main_s = s;
+  if (only >= 0) input_converted = true;  // single-op timing (yb_time_op): buffers hold the last forward's data
   if (e->tile_ctr) YB_CUDA_CHECK(cudaMemsetAsync(e->tile_ctr, 0, e->ops.size() * sizeof(int), s));
   for (size_t i = 0; i < e->ops.size(); i++) {
+    if (only >= 0 && (int)i != only) continue;
     OpDesc& op = e->ops[i];
     s = main_s;
     if (lanes && op.lane > 0) {
@@ -1175,7 +1177,8 @@ int32_t yb_conv_backward_weight(const float* x, const float* dz, int32_t n, int3
 
 static int32_t predict_enqueue(yb_engine* e, yb_engine::Stage& st, const uint8_t* images_host, int32_t batch,
                                float conf_thres, float iou_thres, int32_t max_det, float* dets_host,
-                               int32_t* counts_host, cudaStream_t s, const char* who) {
+                               int32_t* counts_host, cudaStream_t s, const char* who, yb_comm* comm = nullptr,
+                               int comm_slot = 0) {
   if (!e || !images_host || !dets_host || !counts_host) { set_error(std::string(who) + ": null argument"); return YB_ERR_INVALID_ARG; }
   if (!e->finalized) { set_error(std::string(who) + ": call yb_finalize_weights first"); return YB_ERR_STATE; }
   if (batch <= 0 || batch > e->cfg.max_batch) { set_error(std::string(who) + ": batch outside [1, max_batch]"); return YB_ERR_INVALID_ARG; }
@@ -1204,6 +1207,32 @@ static int32_t predict_enqueue(yb_engine* e, yb_engine::Stage& st, const uint8_t
   if (rc) return rc;
   YB_CUDA_CHECK(cudaEventRecord(e->arena_free, s));
   e->arena_used = true;
+  if (comm) {
+    // multi-GPU: NMS writes its rows + counts straight into the exchange's send buffer; every rank's payload is
+    // pushed into every rank's window over NVLink (csrc/comm.cu), then ONE strided D2H copy per array brings the
+    // detections of ALL ranks (global image order = rank order) to the host
+    int32_t world = 1;
+    int64_t cbytes = 0;
+    yb_comm_info(comm, nullptr, &world, &cbytes, nullptr);
+    const size_t dets_bytes = ((size_t)batch * max_det * row_w * sizeof(float) + 15) / 16 * 16;
+    if ((int64_t)(dets_bytes + ((size_t)batch * 4 + 15) / 16 * 16) > cbytes) {
+      set_error(std::string(who) + ": detection payload larger than the exchange's bytes_per_rank");
+      return YB_ERR_INVALID_ARG;
+    }
+    char* send = (char*)yb_comm_send_buffer(comm, comm_slot);
+    const char* win = (const char*)yb_comm_window(comm, comm_slot);
+    if (!send || !win) { set_error(std::string(who) + ": bad exchange slot"); return YB_ERR_INVALID_ARG; }
+    rc = nms_launch(st.pred, batch, e->pred_c, e->A, e->cfg.nc, conf_thres, iou_thres, max_det, 30000, 7680,
+                    (float*)send, (int*)(send + dets_bytes), nullptr, s);
+    if (rc) return rc;
+    rc = yb_comm_allgather(comm, comm_slot, (void*)s);
+    if (rc) return rc;
+    const size_t dw = (size_t)batch * max_det * row_w * sizeof(float);
+    YB_CUDA_CHECK(cudaMemcpy2DAsync(dets_host, dw, win, (size_t)cbytes, dw, world, cudaMemcpyDeviceToHost, s));
+    YB_CUDA_CHECK(cudaMemcpy2DAsync(counts_host, (size_t)batch * 4, win + dets_bytes, (size_t)cbytes, (size_t)batch * 4, world,
+                                    cudaMemcpyDeviceToHost, s));
+    return yb_comm_release(comm, comm_slot, (void*)s);
+  }
   rc = nms_launch(st.pred, batch, e->pred_c, e->A, e->cfg.nc, conf_thres, iou_thres, max_det, 30000, 7680, st.dets,
                   st.counts, nullptr, s);
   if (rc) return rc;
@@ -1233,6 +1262,19 @@ int32_t yb_predict_u8_submit(yb_engine* e, int32_t slot, const uint8_t* images_h
   }
   return predict_enqueue(e, st, images_host, batch, conf_thres, iou_thres, max_det, dets_host, counts_host, st.stream,
                          "yb_predict_u8_submit");
+}
+
+int32_t yb_predict_u8_submit_gather(yb_engine* e, yb_comm* comm, int32_t slot, const uint8_t* images_host, int32_t batch,
+                                    float conf_thres, float iou_thres, int32_t max_det, float* all_dets_host,
+                                    int32_t* all_counts_host) {
+  if (!e || !comm || slot < 0 || slot > 1) { set_error("yb_predict_u8_submit_gather: bad engine / comm / slot (0 or 1)"); return YB_ERR_INVALID_ARG; }
+  yb_engine::Stage& st = e->stage[1 + slot];
+  if (!st.stream) {
+    YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    YB_CUDA_CHECK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  }
+  return predict_enqueue(e, st, images_host, batch, conf_thres, iou_thres, max_det, all_dets_host, all_counts_host,
+                         st.stream, "yb_predict_u8_submit_gather", comm, slot);
 }
 
 int32_t yb_predict_u8_wait(yb_engine* e, int32_t slot) {
@@ -1290,6 +1332,35 @@ int32_t yb_profile_forward(yb_engine* e, const void* in, int32_t in_dtype, int32
   if (!rc)
     for (size_t i = 0; i < e->ops.size(); i++) cudaEventElapsedTime(&ms_per_op[i], ev[i], ev[i + 1]);
   for (auto& x : ev) cudaEventDestroy(x);
+  return rc;
+}
+
+int32_t yb_time_op(yb_engine* e, int32_t op_index, const void* in, int32_t in_dtype, int32_t batch, float* out_pred,
+                   float* out_proto, int32_t reps, float* ms_per_launch, void* stream) {
+  if (!e || !in || !out_pred || !ms_per_launch || reps <= 0) { set_error("yb_time_op: bad argument"); return YB_ERR_INVALID_ARG; }
+  if (!e->finalized) { set_error("yb_time_op: call yb_finalize_weights first"); return YB_ERR_STATE; }
+  if (op_index < 0 || op_index >= (int32_t)e->ops.size() || batch <= 0 || batch > e->cfg.max_batch) { set_error("yb_time_op: bad op / batch"); return YB_ERR_INVALID_ARG; }
+  YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool f16 = e->cfg.precision == YB_PREC_F16;
+  auto once = [&]() {
+    return f16 ? run_ops<__half>(e, in, in_dtype, batch, out_pred, out_proto, s, nullptr, op_index)
+               : run_ops<float>(e, in, in_dtype, batch, out_pred, out_proto, s, nullptr, op_index);
+  };
+  cudaEvent_t a, b;
+  YB_CUDA_CHECK(cudaEventCreate(&a));
+  YB_CUDA_CHECK(cudaEventCreate(&b));
+  int rc = 0;
+  for (int i = 0; i < 2 && !rc; i++) rc = once();
+  if (!rc) cudaEventRecord(a, s);
+  for (int i = 0; i < reps && !rc; i++) rc = once();
+  if (!rc) cudaEventRecord(b, s);
+  if (!rc && cudaStreamSynchronize(s) != cudaSuccess) { set_error("yb_time_op: sync failed"); rc = YB_ERR_CUDA; }
+  float ms = 0.f;
+  if (!rc) cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  *ms_per_launch = ms / reps;
   return rc;
 }
 

@@ -108,6 +108,14 @@ class Engine:
                                              conf_thres, iou_thres, max_det, C.c_void_p(dets_host.data_ptr()),
                                              C.c_void_p(counts_host.data_ptr())))
 
+    def predict_u8_submit_gather(self, comm, slot, images_host, all_dets_host, all_counts_host, conf_thres=0.25,
+                                 iou_thres=0.45, max_det=300):
+        """yb_predict_u8_submit_gather: as predict_u8_submit, the host buffers receive the detections of ALL ranks."""
+        assert not images_host.is_cuda and images_host.dtype == torch.uint8 and images_host.is_contiguous()
+        L.check(L.lib().yb_predict_u8_submit_gather(self._h, comm._h, slot, C.c_void_p(images_host.data_ptr()),
+                                                    images_host.shape[0], conf_thres, iou_thres, max_det,
+                                                    C.c_void_p(all_dets_host.data_ptr()), C.c_void_p(all_counts_host.data_ptr())))
+
     def predict_u8_wait(self, slot):
         L.check(L.lib().yb_predict_u8_wait(self._h, slot))
 
@@ -147,6 +155,16 @@ class Engine:
             rows.append(dict(index=i, name=lib.yb_op_name(self._h, i).decode(), kind=lib.yb_op_kind(self._h, i),
                              ms=float(ms[i]), flops=fl.value, bytes=by.value))
         return rows
+
+    def time_op(self, op_index, x, out_pred, out_proto=None, reps=20, stream=None):
+        """yb_time_op: ms per launch of one op, `reps` launches back to back."""
+        code = {torch.uint8: L.YB_U8, torch.float16: L.YB_F16, torch.float32: L.YB_F32}[x.dtype]
+        ms = C.c_float()
+        L.check(L.lib().yb_time_op(self._h, op_index, C.c_void_p(x.data_ptr()), code, x.shape[0],
+                                   C.c_void_p(out_pred.data_ptr()),
+                                   C.c_void_p(out_proto.data_ptr()) if out_proto is not None else None, reps,
+                                   C.byref(ms), _stream_ptr(stream)))
+        return float(ms.value)
 
     def launches_per_forward(self):
         return L.lib().yb_launches_per_forward(self._h)
@@ -277,3 +295,67 @@ def conv_forward(x, w, bias=None, stride=1, pad=None, stream=None):
                                         C.c_void_p(bias.data_ptr()) if bias is not None else None, N, H, W, Cin, Cout, k, stride, pad,
                                         C.c_void_p(z.data_ptr()), _stream_ptr(stream)))
     return z
+
+
+class Comm:
+    """yb_comm (csrc/comm.cu): exchange of fixed-size payloads between the GPUs of one node over peer memory.
+    `exchange(handle_bytes) -> list of every rank's handle bytes` is the host channel used once at connect time
+    (torch.distributed all-gather by default)."""
+
+    def __init__(self, rank, world, device, bytes_per_rank, slots=2, exchange=None):
+        lib = L.lib()
+        self._h = C.c_void_p()
+        L.check(lib.yb_comm_create(rank, world, device, bytes_per_rank, slots, C.byref(self._h)))
+        self.rank, self.world, self.bytes, self.slots = rank, world, bytes_per_rank, slots
+        self.device = torch.device("cuda", device)
+        hb = lib.yb_comm_handle_bytes()
+        mine = C.create_string_buffer(hb)
+        L.check(lib.yb_comm_local_handle(self._h, mine))
+        if exchange is None:
+            exchange = self._exchange_torch
+        handles = exchange(bytes(mine.raw))
+        assert len(handles) == world and all(len(h) == hb for h in handles)
+        L.check(lib.yb_comm_connect(self._h, C.create_string_buffer(b"".join(handles), hb * world)))
+
+    def _exchange_torch(self, mine):
+        import torch.distributed as dist
+        cuda = dist.get_backend() == "nccl"
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8)
+        t = t.to(self.device) if cuda else t
+        out = torch.empty(self.world * t.numel(), dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        raw = out.cpu().numpy().tobytes()
+        return [raw[i * len(mine):(i + 1) * len(mine)] for i in range(self.world)]
+
+    def _view(self, ptr, nbytes):
+        """uint8 CUDA tensor over library-owned memory (no copy, not owned by torch)."""
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "version": 2,
+                                      "data": (int(ptr), False)}
+        return torch.as_tensor(a, device=self.device)
+
+    def send_buffer(self, slot):
+        return self._view(L.lib().yb_comm_send_buffer(self._h, slot), self.bytes)
+
+    def window(self, slot):
+        return self._view(L.lib().yb_comm_window(self._h, slot), self.bytes * self.world).view(self.world, self.bytes)
+
+    def allgather(self, slot, stream=None):
+        L.check(L.lib().yb_comm_allgather(self._h, slot, _stream_ptr(stream)))
+
+    def release(self, slot, stream=None):
+        L.check(L.lib().yb_comm_release(self._h, slot, _stream_ptr(stream)))
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and getattr(L, "_lib", None) is not None:
+            L._lib.yb_comm_destroy(h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+
+def detection_payload_bytes(batch, max_det, row_width):
+    return int(L.lib().yb_comm_detection_payload_bytes(batch, max_det, row_width))
