@@ -34,8 +34,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn get_encode_fn(std::string* err);
+int silu_exact_mode();
 
-enum TcMode { TC_TAP = 0, TC_HALO = 1, TC_S2P = 2 };
+// TC_HALO3: 3x3 stride-1 tile staged as THREE boxes {BK, 8, 18} (one per kw) so that every tap is a shift by whole
+// 8-row groups (kh * 8 rows) of a canonical 128-row operand: no 8-row group straddles a swizzle atom.  The single
+// 10 x 18 halo box (TC_HALO) needs 2.4x fewer TMA rows but its shifted windows cost ~2x the shared-memory operand
+// read time per MMA, which is what bounds the tensor-bound layers (Detect head, v8s / v8x).
+enum TcMode { TC_TAP = 0, TC_HALO = 1, TC_S2P = 2, TC_HALO3 = 3 };
 
 struct TcArgs {
   CUtensorMap tmA;
@@ -44,6 +49,11 @@ struct TcArgs {
   const __half* res;
   const float* bias;
   int out_pitch, out_coff, res_pitch, res_coff;
+  // fused nn.Upsample(2, nearest) + Concat (Yolo.cs:70-84): every output pixel is also written to the four pixels
+  // of the consumer's concat slice it expands to (out2 == nullptr: off)
+  __half* out2;
+  int out2_pitch, out2_coff, up_H, up_W;  // up_H x up_W = spatial size of THIS conv's output per image
+  uint64_t m_uphw, m_upw;
   int Ho, Wo;            // output extent the tiles cover (flattened for 1x1: Ho = 1, Wo = B*H*W)
   int imgs;              // images the tiles iterate over (1 for flattened 1x1)
   int tiles_w, tiles_h;  // tiles per image
@@ -52,10 +62,12 @@ struct TcArgs {
   int ksz, stride, pad;
   int Cin, BK, chunks;   // chunks = Cin / BK
   int act;
+  int silu_exact;                 // SiLU as x / (1 + 2^(-x log2 e)) (two MUFU ops) instead of h + h*tanh.approx(h)
   int mode;                       // TcMode
   int stages_a, stages_b;
   uint32_t a_bytes, b_bytes;      // TMA transaction bytes per A slab / B slab
   uint32_t a_stride, b_stride;    // smem bytes reserved per slab (1 KiB aligned)
+  uint32_t sub_stride;            // TC_HALO3: bytes between the three {BK,8,18} boxes of a slab
   uint32_t sbo_a, sbo_b;          // UMMA stride-byte-offset between 8-row groups, >> 4
   uint32_t row_bytes;             // BK * 2
   uint32_t layout_a, layout_b;    // UMMA LayoutType: 2 = SW128, 4 = SW64, 6 = SW32
@@ -176,7 +188,7 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
   const uint32_t a_stride16 = a.a_stride >> 4, b_stride16 = a.b_stride >> 4;
   const uint32_t a_lo0 = ((smemA & 0x3FFFF) >> 4) | lo_flags, b_lo0 = ((smemB & 0x3FFFF) >> 4) | lo_flags;
   const int stages_a = a.stages_a, stages_b = a.stages_b, chunks = a.chunks, ksteps = a.ksteps;
-  const bool resident = a.b_resident != 0, halo = a.mode != TC_TAP, s2p = a.mode == TC_S2P;
+  const bool resident = a.b_resident != 0, halo = a.mode != TC_TAP, s2p = a.mode == TC_S2P, h3 = a.mode == TC_HALO3;
   const int total_tiles = a.total_tiles, gstride = gridDim.x;
   constexpr uint32_t ROW16 = KK * 2;  // bytes per operand row / 16
   // Two issuer warps take alternate tiles (local tile index li = issuer, issuer+2, ...): one thread tops
@@ -221,7 +233,9 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
           const uint32_t TAP_HALO = (uint32_t)((t / 3) * (HALO_BW + 2) + (t % 3)) * ROW16;
           const uint32_t TAP_S2P = (uint32_t)((t / 3) * (HALO_BW + 1) + (t % 3 != 0 ? 1 : 0)) * 2 * ROW16 +
                                        (t % 3 != 1 ? ROW16 : 0);
-          const uint32_t tap16 = s2p ? TAP_S2P : TAP_HALO;
+          constexpr uint32_t SUB16 = (uint32_t)(((144 * KK * 32 + 1023) / 1024 * 1024) >> 4);  // one {BK,8,18} box
+          const uint32_t TAP_H3 = (uint32_t)(t % 3) * SUB16 + (uint32_t)(t / 3) * 8 * ROW16;
+          const uint32_t tap16 = h3 ? TAP_H3 : (s2p ? TAP_S2P : TAP_HALO);
           uint32_t b_lo;
           if (resident) {
             b_lo = b_lo0 + (t * chunks + ch) * b_stride16;
@@ -288,7 +302,7 @@ __device__ __forceinline__ void mma_role_dual(const TcArgs& a, uint32_t smemA, u
   const uint32_t a_stride16 = a.a_stride >> 4, b_stride16 = a.b_stride >> 4;
   const uint32_t a_lo0 = ((smemA & 0x3FFFF) >> 4) | (1u << 16), b_lo0 = ((smemB & 0x3FFFF) >> 4) | (1u << 16);
   const int ra = a.stages_a, rb = a.stages_b, chunks = a.chunks, ksteps = a.ksteps, nb = a.n_acc;
-  const bool halo = a.mode != TC_TAP, s2p = a.mode == TC_S2P;
+  const bool halo = a.mode != TC_TAP, s2p = a.mode == TC_S2P, h3 = a.mode == TC_HALO3;
   const int total_tiles = a.total_tiles, gstride = gridDim.x;
   constexpr uint32_t ROW16 = KK * 2;
   int sa = 0, sb = 0;
@@ -321,7 +335,9 @@ __device__ __forceinline__ void mma_role_dual(const TcArgs& a, uint32_t smemA, u
           const uint32_t TAP_HALO = (uint32_t)((t / 3) * (HALO_BW + 2) + (t % 3)) * ROW16;
           const uint32_t TAP_S2P = (uint32_t)((t / 3) * (HALO_BW + 1) + (t % 3 != 0 ? 1 : 0)) * 2 * ROW16 +
                                    (t % 3 != 1 ? ROW16 : 0);
-          const uint32_t tap16 = s2p ? TAP_S2P : TAP_HALO;
+          constexpr uint32_t SUB16 = (uint32_t)(((144 * KK * 32 + 1023) / 1024 * 1024) >> 4);
+          const uint32_t TAP_H3 = (uint32_t)(t % 3) * SUB16 + (uint32_t)(t / 3) * 8 * ROW16;
+          const uint32_t tap16 = h3 ? TAP_H3 : (s2p ? TAP_S2P : TAP_HALO);
           mbar_wait_warp(fullB + 8 * sb, pb);
           tc_fence_after();
           const uint32_t b_lo = b_lo0 + sb * b_stride16;
@@ -476,7 +492,12 @@ const __grid_constant__ TcArgs a) {
           auto load_a = [&](int q, int c0, int dw, int dh) {
             mbar_wait(emptyA + 8 * sa, pa ^ 1);
             mbar_arrive_expect_tx(fullA + 8 * sa, a.a_bytes);
-            tma_load_4d(smemA + sa * a.a_stride, &a.tmA, fullA + 8 * sa, c0, wc_[q] + dw, hb_[q] + dh, img_[q]);
+            if (a.mode == TC_HALO3) {
+              for (int kw = 0; kw < 3; kw++)
+                tma_load_4d(smemA + sa * a.a_stride + kw * a.sub_stride, &a.tmA, fullA + 8 * sa, c0, wc_[q] + kw, hb_[q], img_[q]);
+            } else {
+              tma_load_4d(smemA + sa * a.a_stride, &a.tmA, fullA + 8 * sa, c0, wc_[q] + dw, hb_[q] + dh, img_[q]);
+            }
             if (++sa == ra) { sa = 0; pa ^= 1; }
           };
           auto load_b = [&](int t, int ch) {
@@ -530,8 +551,14 @@ const __grid_constant__ TcArgs a) {
           for (int ch = 0; ch < a.chunks; ch++) {
             mbar_wait(emptyA + 8 * (a_base + sa), pa ^ 1);
             mbar_arrive_expect_tx(fullA + 8 * (a_base + sa), a.a_bytes);
-            tma_load_4d(smemA + (a_base + sa) * a.a_stride, &a.tmA, fullA + 8 * (a_base + sa), ch * a.BK,
-                        a.mode == TC_S2P ? tw * a.BW - 1 : wbase, hbase, img);
+            if (a.mode == TC_HALO3) {
+              for (int kw = 0; kw < 3; kw++)
+                tma_load_4d(smemA + (a_base + sa) * a.a_stride + kw * a.sub_stride, &a.tmA, fullA + 8 * (a_base + sa),
+                            ch * a.BK, wbase + kw, hbase, img);
+            } else {
+              tma_load_4d(smemA + (a_base + sa) * a.a_stride, &a.tmA, fullA + 8 * (a_base + sa), ch * a.BK,
+                          a.mode == TC_S2P ? tw * a.BW - 1 : wbase, hbase, img);
+            }
             if (++sa == ra) { sa = 0; pa ^= 1; }
             if (!a.b_resident)
               for (int t = 0; t < taps; t++) {
@@ -692,6 +719,19 @@ const __grid_constant__ TcArgs a) {
         // cost ~1000 cycles of shuffles / smem round trips per tile; ncu shows L2 far from saturated,
         // so the short instruction path wins.)
         __half* orow = a.out + pix * a.out_pitch + a.out_coff + n0;
+        __half* urow = nullptr;  // top-left of the 2x2 block this pixel expands to in the upsampled concat slice
+        if (a.out2 != nullptr && valid) {
+          int un, uy, ux;
+          if (a.imgs == 1 && a.Ho == 1) {  // flattened 1x1 conv: wo is the pixel index inside the whole batch
+            un = fdiv(wo, a.m_uphw);
+            const int rem = wo - un * a.up_H * a.up_W;
+            uy = fdiv(rem, a.m_upw);
+            ux = rem - uy * a.up_W;
+          } else {
+            un = img; uy = ho; ux = wo;
+          }
+          urow = a.out2 + (((size_t)un * 2 * a.up_H + 2 * uy) * (2 * a.up_W) + 2 * ux) * a.out2_pitch + a.out2_coff + n0;
+        }
         for (int cb0 = 0; cb0 < a.n_tile; cb0 += 32) {
           const int wb = min(32, a.n_tile - cb0);  // 32 or 16 channels
           uint32_t v[32];
@@ -708,8 +748,13 @@ const __grid_constant__ TcArgs a) {
               f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
               f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
               if (a.act == ACT_SILU) {
+                if (a.silu_exact) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) f[j] = silu_tanh(f[j]);
+                  for (int j = 0; j < 8; j++) f[j] = silu_fast(f[j]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; j++) f[j] = silu_tanh(f[j]);
+                }
               }
               if (use_res) {
                 const __half2* h = reinterpret_cast<const __half2*>(&rv[g]);
@@ -724,6 +769,14 @@ const __grid_constant__ TcArgs a) {
 #pragma unroll
               for (int j = 0; j < 4; j++) ph[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
               if (valid) *reinterpret_cast<int4*>(orow + cb0 + g * 8) = o;
+              if (urow != nullptr) {
+                const size_t rowp = (size_t)2 * a.up_W * a.out2_pitch;
+                __half* u = urow + cb0 + g * 8;
+                *reinterpret_cast<int4*>(u) = o;
+                *reinterpret_cast<int4*>(u + a.out2_pitch) = o;
+                *reinterpret_cast<int4*>(u + rowp) = o;
+                *reinterpret_cast<int4*>(u + rowp + a.out2_pitch) = o;
+              }
             }
           }
           if (use_res && cb0 + 32 < a.n_tile) res_prefetch(a, n0, cb0 + 32, pix, valid, rv);  // next block
@@ -784,11 +837,24 @@ static EncodeTiledFn get_encode_fn(std::string* err) {
   return fn;
 }
 
+// YB_SILU=tanh|exact (default set below): the one-MUFU tanh.approx form has a relative error of up to 2^-11 - the size
+// of an fp16 ulp - which doubles the rounding noise of every stored activation; the two-MUFU form is exact to fp32.
+int silu_exact_mode() {
+  static const int v = [] {
+    const char* e = getenv("YB_SILU");
+    if (e && !strcmp(e, "tanh")) return 0;
+    if (e && !strcmp(e, "exact")) return 1;
+    return 0;
+  }();
+  return v;
+}
+
 bool tc_conv_supported(const ConvParams& p) {
   if (p.Cin % 16 || p.Cout % 16 || p.Cout > TC_MAX_COUT) return false;
   if (!((p.k == 1 && p.stride == 1) || (p.k == 3 && (p.stride == 1 || p.stride == 2)))) return false;
   if (p.in.coff % 8 || p.in.pitch % 8 || p.out.coff % 8 || p.out.pitch % 8) return false;
   if (p.res.base && (p.res.coff % 8 || p.res.pitch % 8)) return false;
+  if (p.out2.base && (p.out2.coff % 8 || p.out2.pitch % 8)) return false;
   return true;
 }
 
@@ -812,11 +878,22 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   a.bias = p.bias;
   a.out_pitch = p.out.pitch; a.out_coff = p.out.coff;
   a.res_pitch = p.res.pitch; a.res_coff = p.res.coff;
+  a.out2 = reinterpret_cast<__half*>(p.out2.base);
+  a.out2_pitch = p.out2.pitch; a.out2_coff = p.out2.coff;
+  a.up_H = p.Ho; a.up_W = p.Wo;
+  {
+    auto magic0 = [](int d) { return (uint64_t)(((((unsigned __int128)1) << 40) + d - 1) / (unsigned)d); };
+    a.m_uphw = magic0(p.Ho * p.Wo); a.m_upw = magic0(p.Wo);
+  }
   a.ksz = p.k; a.stride = p.stride; a.pad = p.pad;
   a.Cin = p.Cin;
   // stride-2 3x3 convs over a whole-buffer view with <= 32 channels use pair rows (below)
   const bool s2p_ok = p.k == 3 && p.stride == 2 && p.in.coff == 0 && p.in.pitch == p.Cin && p.Cin <= 32 && p.in.W % 2 == 0;
   a.mode = (p.k == 3 && p.stride == 1) ? TC_HALO : (s2p_ok ? TC_S2P : TC_TAP);
+  // experiments / tuning: YB_H3_MIN_N = smallest Cout that uses the aligned three-box tile (0 = never)
+  static const int h3_min_n = getenv("YB_H3_MIN_N") ? atoi(getenv("YB_H3_MIN_N")) : 64;
+  static const int h3_bk = getenv("YB_H3_BK") ? atoi(getenv("YB_H3_BK")) : 0;  // force the slab width of three-box layers
+  if (a.mode == TC_HALO && h3_min_n > 0 && p.Cout >= h3_min_n) a.mode = TC_HALO3;
   // channel slab: the widest of 64 / 32 / 16 channels (128 / 64 / 32-byte operand rows) that pads K by at most
   // 35 %; a ragged last slab
   // is zero-filled by TMA (activations, dim 0 bound = Cin) and by the weight packing.  (80 / 160 / 400-channel
@@ -824,8 +901,10 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   // the 320 / 640-channel layers reached 45-75 %.)
   auto padded = [&](int bk) { return (p.Cin + bk - 1) / bk * bk; };
   a.BK = padded(64) * 100 <= p.Cin * 135 ? 64 : (padded(32) * 100 <= p.Cin * 135 ? 32 : 16);  // <= 35 % zero K
+  if (a.mode == TC_HALO3 && (h3_bk == 16 || h3_bk == 32 || h3_bk == 64) && h3_bk < a.BK) a.BK = h3_bk;
   a.chunks = (p.Cin + a.BK - 1) / a.BK;
   a.act = p.act;
+  a.silu_exact = silu_exact_mode();
   a.n_tile = pick_n_tile(p.Cout);
   a.n_tiles = p.Cout / a.n_tile;
   const CUtensorMapSwizzle swz = a.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -869,6 +948,12 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
       a.sbo_a = ((a.BW + 2) * a.row_bytes) >> 4;
       box[0] = a.BK; box[1] = a.BW + 2; box[2] = a.BH + 2; box[3] = 1;
       estr[0] = estr[1] = estr[2] = estr[3] = 1;
+    } else if (a.mode == TC_HALO3) {
+      // 8 x 16 output pixels; three boxes of 8 x 18 pixels (input columns w0-1+kw ..): row = h*8 + w, so tap (kh, kw)
+      // is box kw shifted by kh*8 rows - a canonical operand (SBO = 8 rows)
+      a.BW = HALO_BW; a.BH = HALO_BH;
+      box[0] = a.BK; box[1] = a.BW; box[2] = a.BH + 2; box[3] = 1;
+      estr[0] = estr[1] = estr[2] = estr[3] = 1;
     } else if (a.mode == TC_S2P) {
       // 8 x 16 output pixels from 9 pairs x 33 input rows; consecutive output rows are two input rows =
       // 18 pair rows apart
@@ -901,10 +986,15 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     return nullptr;
   }
   const int a_rows = a.mode == TC_HALO ? (a.BW + 2) * (a.BH + 2)
-                                       : (a.mode == TC_S2P ? 2 * (a.BW + 1) * (2 * a.BH + 1) : a.BW * a.BH);
+                                       : (a.mode == TC_S2P ? 2 * (a.BW + 1) * (2 * a.BH + 1)
+                                                           : (a.mode == TC_HALO3 ? 3 * a.BW * (a.BH + 2) : a.BW * a.BH));
   a.a_bytes = (uint32_t)(a_rows * a.row_bytes);
   a.b_bytes = (uint32_t)(a.n_tile * a.row_bytes);
   a.a_stride = (uint32_t)((std::max(a_rows, 128) * a.row_bytes + 1023) / 1024 * 1024);
+  if (a.mode == TC_HALO3) {
+    a.sub_stride = (uint32_t)((a.BW * (a.BH + 2) * a.row_bytes + 1023) / 1024 * 1024);
+    a.a_stride = 3 * a.sub_stride;
+  }
   a.b_stride = (uint32_t)((a.n_tile * a.row_bytes + 1023) / 1024 * 1024);
   a.ksteps = p.k * p.k * a.chunks;
   {
@@ -953,9 +1043,10 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     if (occ == 2 && cols > 256) continue;
     // keep the whole weight matrix in smem when it leaves room for >= 3 activation slabs: removes the
     // weight re-fetch per tile
-    a.b_resident = (a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= budget) ? 1 : 0;
+    const size_t min_a = a.mode == TC_HALO3 ? 2 : 3;  // a three-box slab is 2.4x a halo slab: double buffering is enough
+    a.b_resident = (a.n_tiles == 1 && b_all + min_a * (size_t)a.a_stride <= budget) ? 1 : 0;
     // resident weights at one CTA/SM beat re-fetched weights at two CTAs/SM
-    if (occ == 2 && !small && !a.b_resident && a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= 200 * 1024) continue;
+    if (occ == 2 && !small && !a.b_resident && a.n_tiles == 1 && b_all + min_a * (size_t)a.a_stride <= 200 * 1024) continue;
     if (a.b_resident) {
       a.stages_a = (int)std::min<size_t>(a.mode != TC_TAP ? (a.chunks > 1 ? 8 : 6) : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
       a.stages_b = 0;
@@ -1130,6 +1221,7 @@ struct StemArgs {
   int B, H, W, Ho, Wo, Cout;
   int tiles_w, tiles_h, total_tiles;
   uint32_t tmem_cols;
+  int silu_exact;
   uint64_t m_tpi, m_tw;  // magic numbers for / tiles_per_img and / tiles_w (fdiv)
 };
 
@@ -1272,10 +1364,15 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_con
           __half2* p1 = reinterpret_cast<__half2*>(&o1);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            p0[j] = __floats2half2_rn(silu_tanh(__uint_as_float(acc[2 * j]) + s_bias[c0 + 2 * j]),
-                                      silu_tanh(__uint_as_float(acc[2 * j + 1]) + s_bias[c0 + 2 * j + 1]));
-            p1[j] = __floats2half2_rn(silu_tanh(__uint_as_float(acc[8 + 2 * j]) + s_bias[c0 + 8 + 2 * j]),
-                                      silu_tanh(__uint_as_float(acc[8 + 2 * j + 1]) + s_bias[c0 + 8 + 2 * j + 1]));
+            const float v0 = __uint_as_float(acc[2 * j]) + s_bias[c0 + 2 * j], v1 = __uint_as_float(acc[2 * j + 1]) + s_bias[c0 + 2 * j + 1];
+            const float v2 = __uint_as_float(acc[8 + 2 * j]) + s_bias[c0 + 8 + 2 * j], v3 = __uint_as_float(acc[8 + 2 * j + 1]) + s_bias[c0 + 8 + 2 * j + 1];
+            if (a.silu_exact) {
+              p0[j] = __floats2half2_rn(silu_fast(v0), silu_fast(v1));
+              p1[j] = __floats2half2_rn(silu_fast(v2), silu_fast(v3));
+            } else {
+              p0[j] = __floats2half2_rn(silu_tanh(v0), silu_tanh(v1));
+              p1[j] = __floats2half2_rn(silu_tanh(v2), silu_tanh(v3));
+            }
           }
           *reinterpret_cast<int4*>(o + c0) = o0;
           *reinterpret_cast<int4*>(o + c0 + 8) = o1;
@@ -1312,6 +1409,7 @@ int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const __h
   uint32_t cols = 32;
   while (cols < (uint32_t)a.Cout) cols <<= 1;
   a.tmem_cols = cols;
+  a.silu_exact = silu_exact_mode();
   static int num_sms = 0;
   const size_t smem = 1024 + 16 * 1024 + (size_t)a.Cout * 128;
   if (!num_sms) {

@@ -66,7 +66,8 @@ struct OpDesc {
   int lane_level = -1; // pyramid level whose feature map a side lane waits for
   int feat_level = -1; // this op completes feats[feat_level] (fork point for the head lanes)
   EpiDecode dec;       // conv: fused Detect-tail epilogue (tcgen05 path)
-  bool fused = false;  // decode op: its work is done by the producing convs' epilogues
+  bool fused = false;  // decode / upsample op: its work is done by the producing convs' epilogues
+  VRef up_out;         // conv: second destination = the consumer's concat slice at 2x resolution (fused Upsample)
 };
 
 struct HostTensor {
@@ -667,6 +668,7 @@ static ConvParams conv_params(const yb_engine* e, const OpDesc& op, int B) {
   p.in = make_view(e, op.in);
   p.out = make_view(e, op.out);
   p.res = make_view(e, op.res);
+  p.out2 = make_view(e, op.up_out);
   p.w = op.w_f32;
   p.bias = op.bias;
   p.B = B;
@@ -734,6 +736,7 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
         if (rc) return rc;
         break;
       case OP_UPSAMPLE:
+        if (op.fused) break;
         rc = launch_upsample2x<T>(make_view(e, op.in), make_view(e, op.out), B, s);
         if (rc) return rc;
         break;
@@ -969,6 +972,19 @@ int32_t yb_finalize_weights(yb_engine* e) {
       d.fused = true;
     }
   }
+  if (allow_tc && !getenv("YB_DEBUG_NO_UPFUSE")) {
+    // Upsample + Concat fusion: the tcgen05 conv that produces an Upsample's input also writes the 2x2-expanded
+    // copy into the consumer's concat slice (one kernel less per FPN level, no re-read of the feature map)
+    for (auto& u : e->ops) {
+      if (u.type != OP_UPSAMPLE) continue;
+      OpDesc* pr = nullptr;
+      for (auto& c : e->ops)
+        if (c.type == OP_CONV && c.out.buf == u.in.buf && c.out.coff == u.in.coff && c.out.C == u.in.C) pr = &c;
+      if (!pr || pr->cin % 16 || pr->cout % 16 || u.out.coff % 8 || e->bufs[u.out.buf].C % 8) continue;
+      pr->up_out = u.out;
+      u.fused = true;
+    }
+  }
   for (size_t i = 0; i < e->ops.size(); i++) {
     OpDesc& op = e->ops[i];
     if (op.type != OP_CONV && op.type != OP_DWCONV) continue;
@@ -988,6 +1004,9 @@ int32_t yb_finalize_weights(yb_engine* e) {
         op.plan = tc_conv_plan_create(p, &err);
         if (!op.plan) { set_error("tcgen05 plan failed for " + op.name + ": " + err); return YB_ERR_CUDA; }
         op.use_tc = true;
+      } else if (op.up_out.buf >= 0) {
+        set_error("internal: fused upsample producer " + op.name + " did not get a tcgen05 plan");
+        return YB_ERR_STATE;
       }
     }
   }
@@ -1379,6 +1398,7 @@ int32_t yb_op_cost(const yb_engine* e, int32_t i, int32_t batch, double* flops, 
     const double macs = (double)batch * ob.H * ob.W * op.cout * (op.cin / op.groups) * op.k * op.k;
     *flops = 2.0 * macs;
     *bytes += (double)op.cout * (op.cin / op.groups) * op.k * op.k * e->esize;
+    if (op.up_out.buf >= 0) *bytes += 4.0 * vbytes(op.out);  // fused Upsample: the 2x2-expanded copy
     if (op.use_tc && op.dec.mode != EPI_STORE)  // fused head tail writes fp32 straight into pred
       *bytes += vbytes(op.out) / e->esize * 4.0 - vbytes(op.out);
     if (i == 0) {  // stem reads the caller's NCHW tensor, not an engine buffer
@@ -1417,7 +1437,7 @@ int32_t yb_launches_per_forward(const yb_engine* e) {
   if (!e) return 0;
   int n = e->has_stem_tc ? 0 : 1;  // generic path converts the input layout first
   for (const OpDesc& op : e->ops)
-    if (!(op.type == OP_DECODE && op.fused)) n++;
+    if (!((op.type == OP_DECODE || op.type == OP_UPSAMPLE) && op.fused)) n++;
   return n;
 }
 
