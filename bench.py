@@ -42,6 +42,7 @@ MODELS = {"v8n": ("v8", "n", "detect", 8.743), "v8s": ("v8", "s", "detect", 28.6
           "v11n": ("v11", "n", "detect", 6.5), "v11s": ("v11", "s", "detect", 21.589),
           "v8n-seg": ("v8", "n", "segment", 12.6), "v8s-seg": ("v8", "s", "segment", 40.085)}
 CONF, IOU, MAX_DET = 0.25, 0.45, 300
+E2E_SLOTS = 3  # batches in flight through yb_predict_u8_submit/_wait
 # compulsory bytes per image, fp16 input + fp32 prediction tensor
 COMPULSORY_MB_IMG = {"detect": 3.87, "segment": 6.0}
 
@@ -257,7 +258,7 @@ def main():
     eng = make_engine(m.state_dict())
     del m
     A, Cp = eng.anchors, eng.pred_channels
-    gatherer = ydist.DetectionGather(B, MAX_DET, ROW, dev, mode=args.gather, slots=2) if world > 1 else None
+    gatherer = ydist.DetectionGather(B, MAX_DET, ROW, dev, mode=args.gather, slots=max(2, E2E_SLOTS)) if world > 1 else None
 
     def timed_run(eng, xs, steps, warmup, with_gather):
         """Two-deep software pipeline: forward(i+1) runs on stream s_f while NMS (+ masks, + gather) of batch i runs on
@@ -347,37 +348,41 @@ def main():
     #      yb_predict_u8_submit / yb_predict_u8_wait (two slots: H2D+forward+NMS[+gather]+D2H of step i+1 overlap step i) ----
     e2e_val, e2e_steps, d2h = None, 0, 0
     if not seg:
-        u8 = [synth_image(B, 640, 640, seed=200 + rank * 8 + i, dtype=torch.uint8).pin_memory() for i in range(2)]
+        NS = E2E_SLOTS
+        torch.set_num_threads(1)  # the serving loop is ctypes calls only; idle intra-op workers cost it 15 % (profiles/r2_exp_e2e_matrix.txt)
+        host["omp_threads_e2e"] = 1
+        u8 = [synth_image(B, 640, 640, seed=200 + rank * 8 + i, dtype=torch.uint8).pin_memory() for i in range(NS)]
         GB = world * B if world > 1 else B
-        dh = [torch.empty((GB, MAX_DET, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
-        ch = [torch.empty((GB,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        dh = [torch.empty((GB, MAX_DET, 6), dtype=torch.float32).pin_memory() for _ in range(NS)]
+        ch = [torch.empty((GB,), dtype=torch.int32).pin_memory() for _ in range(NS)]
         d2h = GB * MAX_DET * 6 * 4 + GB * 4
-        e2e_steps = max(6, args.steps // 2)
+        e2e_steps = max(3 * NS, args.steps // 2)
 
         def submit(i):
+            k = i % NS
             if world > 1:
-                gatherer.predict_submit(eng, i & 1, u8[i & 1], dh[i & 1], ch[i & 1], CONF, IOU)
+                gatherer.predict_submit(eng, k, u8[k], dh[k], ch[k], CONF, IOU)
             else:
-                eng.predict_u8_submit(i & 1, u8[i & 1], dh[i & 1], ch[i & 1], CONF, IOU, MAX_DET)
+                eng.predict_u8_submit(k, u8[k], dh[k], ch[k], CONF, IOU, MAX_DET)
 
         def wait(slot):
             if world > 1:
                 gatherer.predict_wait(eng, slot)
             else:
                 eng.predict_u8_wait(slot)
-        for i in range(6):
+        for i in range(3 * NS):
             submit(i)
-            wait(i & 1)
+            wait(i % NS)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            if i >= 2:
-                wait(i & 1)  # results of step i-2 are in host memory
+            if i >= NS:
+                wait(i % NS)  # results of step i-NS are in host memory
             submit(i)
-        wait(0)
-        wait(1)
+        for k in range(NS):
+            wait(k)
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], device=dev)
         if world > 1:
@@ -449,7 +454,7 @@ def main():
                        "gather": (gatherer.describe() if gatherer else None)},
             "e2e": {"value": round(e2e_val, 1) if e2e_val else None, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 640 * 640,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "yb_predict_u8_submit/_wait, 2 slots (pinned host uint8 in, host detections out)" +
+                    "api": f"yb_predict_u8_submit/_wait, {E2E_SLOTS} slots (pinned host uint8 in, host detections out)" +
                            (", detections of all ranks gathered before the D2H copy" if world > 1 else "")},
             "gpu_launches": (eng.launches_per_forward() + 2 + (1 if seg else 0) + (3 if world > 1 else 0)) * args.steps,
             "launches_per_step": eng.launches_per_forward() + 2 + (1 if seg else 0) + (3 if world > 1 else 0),

@@ -199,9 +199,9 @@ int32_t yb_predict_u8(yb_engine* e, const uint8_t* images_host, int32_t batch, f
                       float iou_thres, int32_t max_det, float* dets_host, int32_t* counts_host,
                       void* stream);
 
-/* Pipelined form of yb_predict_u8 for serving loops: `slot` (0 or 1) selects one of two engine-owned
+/* Pipelined form of yb_predict_u8 for serving loops: `slot` (0 .. 3) selects one of four engine-owned
  * stream + staging-buffer sets, so the H2D copy / forward / NMS / D2H of one batch overlap those of the
- * other.  submit returns immediately; the host buffers must stay valid (and should be pinned) until
+ * others (the forwards themselves are serialised on the shared activation arena).  submit returns immediately; the host buffers must stay valid (and should be pinned) until
  * yb_predict_u8_wait(slot) returned. */
 int32_t yb_predict_u8_submit(yb_engine* e, int32_t slot, const uint8_t* images_host, int32_t batch,
                              float conf_thres, float iou_thres, int32_t max_det, float* dets_host,

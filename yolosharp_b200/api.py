@@ -215,7 +215,9 @@ class Detector:
             raise NotImplementedError("skipNcNotEqualLayers")
         sd = {}
         for name, dt, shape, data in binfmt.read_bin(path):
-            if dt == 5:
+            if len(data) == 0:  # empty buffers (`anchors` / `strides` of the head, Head.cs:11-12)
+                sd[name] = torch.empty(shape, dtype={5: torch.float16, 6: torch.float32, 15: torch.bfloat16}.get(dt, torch.float32))
+            elif dt == 5:
                 sd[name] = torch.frombuffer(bytearray(data), dtype=torch.float16).reshape(shape)
             elif dt == 6:
                 sd[name] = torch.frombuffer(bytearray(data), dtype=torch.float32).reshape(shape)

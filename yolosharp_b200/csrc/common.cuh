@@ -99,7 +99,18 @@ int launch_proto_out(const View& in, float* out, int B, cudaStream_t s);
 struct TcConvPlan;  // opaque: tensor maps + tiling for one conv layer
 TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err);
 void tc_conv_plan_destroy(TcConvPlan* plan);
-int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, int* tile_ctr, cudaStream_t s);
+// Cross-layer overlap (DESIGN 4.1 "layer chaining"): instead of waiting for the whole previous grid
+// (griddepcontrol.wait) a conv may start a tile as soon as the images it reads are complete in its producer.
+//   done_ctr   this launch's per-image completion counters (rows x N tiles stored), or nullptr
+//   dep_ctr    the producer launch's counters, or nullptr = wait for the previous grid as a whole
+//   dep_expect rows x N tiles the producer stores per image
+struct TcChain {
+  int* done_ctr = nullptr;
+  const int* dep_ctr = nullptr;
+  int dep_expect = 0;
+};
+int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, int* tile_ctr, cudaStream_t s, const TcChain* chain = nullptr);
+int tc_conv_rows_per_image(const TcConvPlan* plan);  // rows x N tiles one image contributes to done_ctr
 bool tc_conv_supported(const ConvParams& p);
 // stem: NCHW u8/f16/f32 input -> 3x3 s2 conv (Cin=3) + bias + SiLU -> NHWC fp16
 int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const __half* w16 /*[Cout][32]*/,

@@ -34,13 +34,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn get_encode_fn(std::string* err);
-int silu_exact_mode();
 
-// TC_HALO3: 3x3 stride-1 tile staged as THREE boxes {BK, 8, 18} (one per kw) so that every tap is a shift by whole
-// 8-row groups (kh * 8 rows) of a canonical 128-row operand: no 8-row group straddles a swizzle atom.  The single
-// 10 x 18 halo box (TC_HALO) needs 2.4x fewer TMA rows but its shifted windows cost ~2x the shared-memory operand
-// read time per MMA, which is what bounds the tensor-bound layers (Detect head, v8s / v8x).
-enum TcMode { TC_TAP = 0, TC_HALO = 1, TC_S2P = 2, TC_HALO3 = 3 };
+enum TcMode { TC_TAP = 0, TC_HALO = 1, TC_S2P = 2 };
 
 struct TcArgs {
   CUtensorMap tmA;
@@ -49,11 +44,6 @@ struct TcArgs {
   const __half* res;
   const float* bias;
   int out_pitch, out_coff, res_pitch, res_coff;
-  // fused nn.Upsample(2, nearest) + Concat (Yolo.cs:70-84): every output pixel is also written to the four pixels
-  // of the consumer's concat slice it expands to (out2 == nullptr: off)
-  __half* out2;
-  int out2_pitch, out2_coff, up_H, up_W;  // up_H x up_W = spatial size of THIS conv's output per image
-  uint64_t m_uphw, m_upw;
   int Ho, Wo;            // output extent the tiles cover (flattened for 1x1: Ho = 1, Wo = B*H*W)
   int imgs;              // images the tiles iterate over (1 for flattened 1x1)
   int tiles_w, tiles_h;  // tiles per image
@@ -62,12 +52,10 @@ struct TcArgs {
   int ksz, stride, pad;
   int Cin, BK, chunks;   // chunks = Cin / BK
   int act;
-  int silu_exact;                 // SiLU as x / (1 + 2^(-x log2 e)) (two MUFU ops) instead of h + h*tanh.approx(h)
   int mode;                       // TcMode
   int stages_a, stages_b;
   uint32_t a_bytes, b_bytes;      // TMA transaction bytes per A slab / B slab
   uint32_t a_stride, b_stride;    // smem bytes reserved per slab (1 KiB aligned)
-  uint32_t sub_stride;            // TC_HALO3: bytes between the three {BK,8,18} boxes of a slab
   uint32_t sbo_a, sbo_b;          // UMMA stride-byte-offset between 8-row groups, >> 4
   uint32_t row_bytes;             // BK * 2
   uint32_t layout_a, layout_b;    // UMMA LayoutType: 2 = SW128, 4 = SW64, 6 = SW32
@@ -85,6 +73,11 @@ struct TcArgs {
   float* pred;
   // exact x / d for x*d < 2^40 as (x * ceil(2^40/d)) >> 40 (runtime integer division costs ~100+ cycles)
   uint64_t m_ntiles, m_tpi, m_tw, m_bw;
+  // layer chaining (TcChain): per-image completion counters instead of a grid-wide dependency
+  int* done_ctr;
+  const int* dep_ctr;
+  int dep_expect;
+  uint64_t m_ohw;  // magic number for / (Ho * Wo) of this conv's output (image of a flattened pixel index)
   int* tile_ctr;   // dynamic tile scheduler: global counter of this launch (nullptr = static round-robin)
   int tile_batch;  // consecutive tiles drawn per atomicAdd (one counter address serves the whole grid)
   long long* dbg;  // optional timeline buffer (tools/exp_timeline.py); nullptr in production
@@ -150,6 +143,19 @@ __device__ __forceinline__ int tq_get(const int* s_tile, const volatile int* s_h
   return reinterpret_cast<const volatile int*>(s_tile)[li & (TQ - 1)];
 }
 
+// Producer-side dependency wait of the layer chain: poll the producer launch's counter of image `img` until all of
+// its rows are stored (acquire), bounded like every other wait of this kernel.
+__device__ __forceinline__ void dep_wait_image(const int* ctr, int img, int expect) {
+  const long long t0 = clock64();
+  while (true) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ctr + img) : "memory");
+    if (v >= expect) break;
+    __nanosleep(100);
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
   uint64_t d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
@@ -164,7 +170,9 @@ __device__ __forceinline__ void res_prefetch(const TcArgs& a, int n0, int cb0, s
 #pragma unroll
   for (int g = 0; g < 4; g++) {
     rv[g] = make_int4(0, 0, 0, 0);
-    if (valid && g * 8 < wb) rv[g] = *reinterpret_cast<const int4*>(rrow + g * 8);
+    // L2-only load: with layer chaining a neighbouring row of the same 128-byte line may still be unwritten when
+    // this one is read, and a line cached in L1 now would be stale when that row's own tile reads it later
+    if (valid && g * 8 < wb) rv[g] = __ldcg(reinterpret_cast<const int4*>(rrow + g * 8));
   }
 }
 
@@ -188,7 +196,7 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
   const uint32_t a_stride16 = a.a_stride >> 4, b_stride16 = a.b_stride >> 4;
   const uint32_t a_lo0 = ((smemA & 0x3FFFF) >> 4) | lo_flags, b_lo0 = ((smemB & 0x3FFFF) >> 4) | lo_flags;
   const int stages_a = a.stages_a, stages_b = a.stages_b, chunks = a.chunks, ksteps = a.ksteps;
-  const bool resident = a.b_resident != 0, halo = a.mode != TC_TAP, s2p = a.mode == TC_S2P, h3 = a.mode == TC_HALO3;
+  const bool resident = a.b_resident != 0, halo = a.mode != TC_TAP, s2p = a.mode == TC_S2P;
   const int total_tiles = a.total_tiles, gstride = gridDim.x;
   constexpr uint32_t ROW16 = KK * 2;  // bytes per operand row / 16
   // Two issuer warps take alternate tiles (local tile index li = issuer, issuer+2, ...): one thread tops
@@ -233,9 +241,7 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t smemA, uint32
           const uint32_t TAP_HALO = (uint32_t)((t / 3) * (HALO_BW + 2) + (t % 3)) * ROW16;
           const uint32_t TAP_S2P = (uint32_t)((t / 3) * (HALO_BW + 1) + (t % 3 != 0 ? 1 : 0)) * 2 * ROW16 +
                                        (t % 3 != 1 ? ROW16 : 0);
-          constexpr uint32_t SUB16 = (uint32_t)(((144 * KK * 32 + 1023) / 1024 * 1024) >> 4);  // one {BK,8,18} box
-          const uint32_t TAP_H3 = (uint32_t)(t % 3) * SUB16 + (uint32_t)(t / 3) * 8 * ROW16;
-          const uint32_t tap16 = h3 ? TAP_H3 : (s2p ? TAP_S2P : TAP_HALO);
+          const uint32_t tap16 = s2p ? TAP_S2P : TAP_HALO;
           uint32_t b_lo;
           if (resident) {
             b_lo = b_lo0 + (t * chunks + ch) * b_stride16;
@@ -302,7 +308,7 @@ __device__ __forceinline__ void mma_role_dual(const TcArgs& a, uint32_t smemA, u
   const uint32_t a_stride16 = a.a_stride >> 4, b_stride16 = a.b_stride >> 4;
   const uint32_t a_lo0 = ((smemA & 0x3FFFF) >> 4) | (1u << 16), b_lo0 = ((smemB & 0x3FFFF) >> 4) | (1u << 16);
   const int ra = a.stages_a, rb = a.stages_b, chunks = a.chunks, ksteps = a.ksteps, nb = a.n_acc;
-  const bool halo = a.mode != TC_TAP, s2p = a.mode == TC_S2P, h3 = a.mode == TC_HALO3;
+  const bool halo = a.mode != TC_TAP, s2p = a.mode == TC_S2P;
   const int total_tiles = a.total_tiles, gstride = gridDim.x;
   constexpr uint32_t ROW16 = KK * 2;
   int sa = 0, sb = 0;
@@ -335,9 +341,7 @@ __device__ __forceinline__ void mma_role_dual(const TcArgs& a, uint32_t smemA, u
           const uint32_t TAP_HALO = (uint32_t)((t / 3) * (HALO_BW + 2) + (t % 3)) * ROW16;
           const uint32_t TAP_S2P = (uint32_t)((t / 3) * (HALO_BW + 1) + (t % 3 != 0 ? 1 : 0)) * 2 * ROW16 +
                                    (t % 3 != 1 ? ROW16 : 0);
-          constexpr uint32_t SUB16 = (uint32_t)(((144 * KK * 32 + 1023) / 1024 * 1024) >> 4);
-          const uint32_t TAP_H3 = (uint32_t)(t % 3) * SUB16 + (uint32_t)(t / 3) * 8 * ROW16;
-          const uint32_t tap16 = h3 ? TAP_H3 : (s2p ? TAP_S2P : TAP_HALO);
+          const uint32_t tap16 = s2p ? TAP_S2P : TAP_HALO;
           mbar_wait_warp(fullB + 8 * sb, pb);
           tc_fence_after();
           const uint32_t b_lo = b_lo0 + sb * b_stride16;
@@ -465,8 +469,9 @@ const __grid_constant__ TcArgs a) {
         bulk_load_1d(smemB + ks * a.b_stride, a.wpk + (size_t)ks * a.b_stride, a.b_bytes, bfull);
     }
   }
-  // activations written by the previous kernel are visible only after this point
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // activations written by the previous kernel are visible only after this point - unless this launch is chained to
+  // its producer by per-image counters (dep_ctr): then tiles start as soon as their images are complete
+  if (a.dep_ctr == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -492,12 +497,7 @@ const __grid_constant__ TcArgs a) {
           auto load_a = [&](int q, int c0, int dw, int dh) {
             mbar_wait(emptyA + 8 * sa, pa ^ 1);
             mbar_arrive_expect_tx(fullA + 8 * sa, a.a_bytes);
-            if (a.mode == TC_HALO3) {
-              for (int kw = 0; kw < 3; kw++)
-                tma_load_4d(smemA + sa * a.a_stride + kw * a.sub_stride, &a.tmA, fullA + 8 * sa, c0, wc_[q] + kw, hb_[q], img_[q]);
-            } else {
-              tma_load_4d(smemA + sa * a.a_stride, &a.tmA, fullA + 8 * sa, c0, wc_[q] + dw, hb_[q] + dh, img_[q]);
-            }
+            tma_load_4d(smemA + sa * a.a_stride, &a.tmA, fullA + 8 * sa, c0, wc_[q] + dw, hb_[q] + dh, img_[q]);
             if (++sa == ra) { sa = 0; pa ^= 1; }
           };
           auto load_b = [&](int t, int ch) {
@@ -534,7 +534,25 @@ const __grid_constant__ TcArgs a) {
       const int batch = a.tile_batch;
       // the next batch of tiles is drawn one batch ahead, so the atomic's latency never sits on the load path
       if (dyn && tile < a.total_tiles) nxt = (int)gridDim.x + atomicAdd(a.tile_ctr, batch);
+      int dep_ready = -1;  // last image of the producer known to be complete
       for (; tile < a.total_tiles; li++) {
+        if (a.dep_ctr != nullptr) {
+          // images this tile reads: its own image, or for a flattened 1x1 tile the images of its first / last pixel
+          const int mt0 = fdiv(tile, a.m_ntiles);
+          int i0, i1;
+          if (a.imgs == 1 && a.Ho == 1) {
+            const int p0 = mt0 * 128, p1 = min(p0 + 127, a.Wo - 1);
+            i0 = fdiv(p0, a.m_ohw); i1 = fdiv(p1, a.m_ohw);
+          } else {
+            i0 = i1 = fdiv(mt0, a.m_tpi);
+          }
+          if (i1 != dep_ready || i0 != i1) {
+            for (int im = i0; im <= i1; im++)
+              if (im != dep_ready) dep_wait_image(a.dep_ctr, im, a.dep_expect);
+            dep_ready = i1;
+            asm volatile("fence.proxy.async.global;" ::: "memory");  // generic-proxy acquire -> async-proxy (TMA) reads
+          }
+        }
         if (dyn) tq_publish(s_tile, &s_head, li, tile);
         const int rg = ni == 2 ? (li & 1) : 0;  // ring (= issuer) of this tile
         int& sa = sa_[rg]; int& sb = sb_[rg];
@@ -551,14 +569,8 @@ const __grid_constant__ TcArgs a) {
           for (int ch = 0; ch < a.chunks; ch++) {
             mbar_wait(emptyA + 8 * (a_base + sa), pa ^ 1);
             mbar_arrive_expect_tx(fullA + 8 * (a_base + sa), a.a_bytes);
-            if (a.mode == TC_HALO3) {
-              for (int kw = 0; kw < 3; kw++)
-                tma_load_4d(smemA + (a_base + sa) * a.a_stride + kw * a.sub_stride, &a.tmA, fullA + 8 * (a_base + sa),
-                            ch * a.BK, wbase + kw, hbase, img);
-            } else {
-              tma_load_4d(smemA + (a_base + sa) * a.a_stride, &a.tmA, fullA + 8 * (a_base + sa), ch * a.BK,
-                          a.mode == TC_S2P ? tw * a.BW - 1 : wbase, hbase, img);
-            }
+            tma_load_4d(smemA + (a_base + sa) * a.a_stride, &a.tmA, fullA + 8 * (a_base + sa), ch * a.BK,
+                        a.mode == TC_S2P ? tw * a.BW - 1 : wbase, hbase, img);
             if (++sa == ra) { sa = 0; pa ^= 1; }
             if (!a.b_resident)
               for (int t = 0; t < taps; t++) {
@@ -719,19 +731,6 @@ const __grid_constant__ TcArgs a) {
         // cost ~1000 cycles of shuffles / smem round trips per tile; ncu shows L2 far from saturated,
         // so the short instruction path wins.)
         __half* orow = a.out + pix * a.out_pitch + a.out_coff + n0;
-        __half* urow = nullptr;  // top-left of the 2x2 block this pixel expands to in the upsampled concat slice
-        if (a.out2 != nullptr && valid) {
-          int un, uy, ux;
-          if (a.imgs == 1 && a.Ho == 1) {  // flattened 1x1 conv: wo is the pixel index inside the whole batch
-            un = fdiv(wo, a.m_uphw);
-            const int rem = wo - un * a.up_H * a.up_W;
-            uy = fdiv(rem, a.m_upw);
-            ux = rem - uy * a.up_W;
-          } else {
-            un = img; uy = ho; ux = wo;
-          }
-          urow = a.out2 + (((size_t)un * 2 * a.up_H + 2 * uy) * (2 * a.up_W) + 2 * ux) * a.out2_pitch + a.out2_coff + n0;
-        }
         for (int cb0 = 0; cb0 < a.n_tile; cb0 += 32) {
           const int wb = min(32, a.n_tile - cb0);  // 32 or 16 channels
           uint32_t v[32];
@@ -748,13 +747,8 @@ const __grid_constant__ TcArgs a) {
               f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
               f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
               if (a.act == ACT_SILU) {
-                if (a.silu_exact) {
 #pragma unroll
-                  for (int j = 0; j < 8; j++) f[j] = silu_fast(f[j]);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 8; j++) f[j] = silu_tanh(f[j]);
-                }
+                for (int j = 0; j < 8; j++) f[j] = silu_tanh(f[j]);
               }
               if (use_res) {
                 const __half2* h = reinterpret_cast<const __half2*>(&rv[g]);
@@ -769,14 +763,6 @@ const __grid_constant__ TcArgs a) {
 #pragma unroll
               for (int j = 0; j < 4; j++) ph[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
               if (valid) *reinterpret_cast<int4*>(orow + cb0 + g * 8) = o;
-              if (urow != nullptr) {
-                const size_t rowp = (size_t)2 * a.up_W * a.out2_pitch;
-                __half* u = urow + cb0 + g * 8;
-                *reinterpret_cast<int4*>(u) = o;
-                *reinterpret_cast<int4*>(u + a.out2_pitch) = o;
-                *reinterpret_cast<int4*>(u + rowp) = o;
-                *reinterpret_cast<int4*>(u + rowp + a.out2_pitch) = o;
-              }
             }
           }
           if (use_res && cb0 + 32 < a.n_tile) res_prefetch(a, n0, cb0 + 32, pix, valid, rv);  // next block
@@ -785,6 +771,19 @@ const __grid_constant__ TcArgs a) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (a.done_ctr != nullptr && a.epi_mode == EPI_STORE) {
+        // publish this warp's rows: every lane's stores are ordered before the count (fence, then warp barrier, then
+        // one atomic per image); a flattened tile may span two images
+        __threadfence();
+        const int my_img = (a.imgs == 1 && a.Ho == 1) ? fdiv(min(wo, a.Wo - 1), a.m_ohw) : img;
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        const int first = __shfl_sync(0xffffffffu, my_img, vm ? __ffs(vm) - 1 : 0);
+        const unsigned same = __ballot_sync(0xffffffffu, valid && my_img == first);
+        if (lane == 0 && vm) {
+          atomicAdd(a.done_ctr + first, __popc(same));
+          if (vm != same) atomicAdd(a.done_ctr + first + 1, __popc(vm ^ same));
+        }
+      }
       if (dbg_on) a.dbg[dbg_t * 8 + 6] = clock64();
     }
   }
@@ -837,24 +836,11 @@ static EncodeTiledFn get_encode_fn(std::string* err) {
   return fn;
 }
 
-// YB_SILU=tanh|exact (default set below): the one-MUFU tanh.approx form has a relative error of up to 2^-11 - the size
-// of an fp16 ulp - which doubles the rounding noise of every stored activation; the two-MUFU form is exact to fp32.
-int silu_exact_mode() {
-  static const int v = [] {
-    const char* e = getenv("YB_SILU");
-    if (e && !strcmp(e, "tanh")) return 0;
-    if (e && !strcmp(e, "exact")) return 1;
-    return 0;
-  }();
-  return v;
-}
-
 bool tc_conv_supported(const ConvParams& p) {
   if (p.Cin % 16 || p.Cout % 16 || p.Cout > TC_MAX_COUT) return false;
   if (!((p.k == 1 && p.stride == 1) || (p.k == 3 && (p.stride == 1 || p.stride == 2)))) return false;
   if (p.in.coff % 8 || p.in.pitch % 8 || p.out.coff % 8 || p.out.pitch % 8) return false;
   if (p.res.base && (p.res.coff % 8 || p.res.pitch % 8)) return false;
-  if (p.out2.base && (p.out2.coff % 8 || p.out2.pitch % 8)) return false;
   return true;
 }
 
@@ -878,22 +864,11 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   a.bias = p.bias;
   a.out_pitch = p.out.pitch; a.out_coff = p.out.coff;
   a.res_pitch = p.res.pitch; a.res_coff = p.res.coff;
-  a.out2 = reinterpret_cast<__half*>(p.out2.base);
-  a.out2_pitch = p.out2.pitch; a.out2_coff = p.out2.coff;
-  a.up_H = p.Ho; a.up_W = p.Wo;
-  {
-    auto magic0 = [](int d) { return (uint64_t)(((((unsigned __int128)1) << 40) + d - 1) / (unsigned)d); };
-    a.m_uphw = magic0(p.Ho * p.Wo); a.m_upw = magic0(p.Wo);
-  }
   a.ksz = p.k; a.stride = p.stride; a.pad = p.pad;
   a.Cin = p.Cin;
   // stride-2 3x3 convs over a whole-buffer view with <= 32 channels use pair rows (below)
   const bool s2p_ok = p.k == 3 && p.stride == 2 && p.in.coff == 0 && p.in.pitch == p.Cin && p.Cin <= 32 && p.in.W % 2 == 0;
   a.mode = (p.k == 3 && p.stride == 1) ? TC_HALO : (s2p_ok ? TC_S2P : TC_TAP);
-  // experiments / tuning: YB_H3_MIN_N = smallest Cout that uses the aligned three-box tile (0 = never)
-  static const int h3_min_n = getenv("YB_H3_MIN_N") ? atoi(getenv("YB_H3_MIN_N")) : 64;
-  static const int h3_bk = getenv("YB_H3_BK") ? atoi(getenv("YB_H3_BK")) : 0;  // force the slab width of three-box layers
-  if (a.mode == TC_HALO && h3_min_n > 0 && p.Cout >= h3_min_n) a.mode = TC_HALO3;
   // channel slab: the widest of 64 / 32 / 16 channels (128 / 64 / 32-byte operand rows) that pads K by at most
   // 35 %; a ragged last slab
   // is zero-filled by TMA (activations, dim 0 bound = Cin) and by the weight packing.  (80 / 160 / 400-channel
@@ -901,10 +876,8 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   // the 320 / 640-channel layers reached 45-75 %.)
   auto padded = [&](int bk) { return (p.Cin + bk - 1) / bk * bk; };
   a.BK = padded(64) * 100 <= p.Cin * 135 ? 64 : (padded(32) * 100 <= p.Cin * 135 ? 32 : 16);  // <= 35 % zero K
-  if (a.mode == TC_HALO3 && (h3_bk == 16 || h3_bk == 32 || h3_bk == 64) && h3_bk < a.BK) a.BK = h3_bk;
   a.chunks = (p.Cin + a.BK - 1) / a.BK;
   a.act = p.act;
-  a.silu_exact = silu_exact_mode();
   a.n_tile = pick_n_tile(p.Cout);
   a.n_tiles = p.Cout / a.n_tile;
   const CUtensorMapSwizzle swz = a.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -948,12 +921,6 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
       a.sbo_a = ((a.BW + 2) * a.row_bytes) >> 4;
       box[0] = a.BK; box[1] = a.BW + 2; box[2] = a.BH + 2; box[3] = 1;
       estr[0] = estr[1] = estr[2] = estr[3] = 1;
-    } else if (a.mode == TC_HALO3) {
-      // 8 x 16 output pixels; three boxes of 8 x 18 pixels (input columns w0-1+kw ..): row = h*8 + w, so tap (kh, kw)
-      // is box kw shifted by kh*8 rows - a canonical operand (SBO = 8 rows)
-      a.BW = HALO_BW; a.BH = HALO_BH;
-      box[0] = a.BK; box[1] = a.BW; box[2] = a.BH + 2; box[3] = 1;
-      estr[0] = estr[1] = estr[2] = estr[3] = 1;
     } else if (a.mode == TC_S2P) {
       // 8 x 16 output pixels from 9 pairs x 33 input rows; consecutive output rows are two input rows =
       // 18 pair rows apart
@@ -986,15 +953,10 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     return nullptr;
   }
   const int a_rows = a.mode == TC_HALO ? (a.BW + 2) * (a.BH + 2)
-                                       : (a.mode == TC_S2P ? 2 * (a.BW + 1) * (2 * a.BH + 1)
-                                                           : (a.mode == TC_HALO3 ? 3 * a.BW * (a.BH + 2) : a.BW * a.BH));
+                                       : (a.mode == TC_S2P ? 2 * (a.BW + 1) * (2 * a.BH + 1) : a.BW * a.BH);
   a.a_bytes = (uint32_t)(a_rows * a.row_bytes);
   a.b_bytes = (uint32_t)(a.n_tile * a.row_bytes);
   a.a_stride = (uint32_t)((std::max(a_rows, 128) * a.row_bytes + 1023) / 1024 * 1024);
-  if (a.mode == TC_HALO3) {
-    a.sub_stride = (uint32_t)((a.BW * (a.BH + 2) * a.row_bytes + 1023) / 1024 * 1024);
-    a.a_stride = 3 * a.sub_stride;
-  }
   a.b_stride = (uint32_t)((a.n_tile * a.row_bytes + 1023) / 1024 * 1024);
   a.ksteps = p.k * p.k * a.chunks;
   {
@@ -1043,10 +1005,9 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     if (occ == 2 && cols > 256) continue;
     // keep the whole weight matrix in smem when it leaves room for >= 3 activation slabs: removes the
     // weight re-fetch per tile
-    const size_t min_a = a.mode == TC_HALO3 ? 2 : 3;  // a three-box slab is 2.4x a halo slab: double buffering is enough
-    a.b_resident = (a.n_tiles == 1 && b_all + min_a * (size_t)a.a_stride <= budget) ? 1 : 0;
+    a.b_resident = (a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= budget) ? 1 : 0;
     // resident weights at one CTA/SM beat re-fetched weights at two CTAs/SM
-    if (occ == 2 && !small && !a.b_resident && a.n_tiles == 1 && b_all + min_a * (size_t)a.a_stride <= 200 * 1024) continue;
+    if (occ == 2 && !small && !a.b_resident && a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= 200 * 1024) continue;
     if (a.b_resident) {
       a.stages_a = (int)std::min<size_t>(a.mode != TC_TAP ? (a.chunks > 1 ? 8 : 6) : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
       a.stages_b = 0;
@@ -1144,9 +1105,18 @@ void tc_conv_plan_destroy(TcConvPlan* plan) {
 long long* g_tc_dbg = nullptr;  // set by yb_debug_timeline: next tcgen05 conv launches write their timeline here
 int g_tc_dbg_countdown = -1;
 
-int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, int* tile_ctr, cudaStream_t s) {
+int tc_conv_rows_per_image(const TcConvPlan* plan) { return plan->p.Ho * plan->p.Wo * plan->args.n_tiles; }
+
+int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, int* tile_ctr, cudaStream_t s, const TcChain* chain) {
   TcArgs a = plan->args;
   a.pred = pred;
+  if (chain) {
+    a.done_ctr = chain->done_ctr;
+    if (!plan->args.dual) {  // tile pairs (streamed weights, static order) keep the grid-wide dependency
+      a.dep_ctr = chain->dep_ctr;
+      a.dep_expect = chain->dep_expect;
+    }
+  }
   // Tile pairs keep the static order (both tiles need the same N tile).  (Restricting the queue to long-tile layers
   // made the isolated short-tile layers of v8n ~10 % faster but the overlapped step no faster, and cost v8s 4 %.)
   a.tile_ctr = a.dual ? nullptr : tile_ctr;
@@ -1168,7 +1138,12 @@ int tc_conv_launch(const TcConvPlan* plan, int B, float* pred, int* tile_ctr, cu
   a.total_tiles = a.imgs * a.tiles_w * a.tiles_h * a.n_tiles;
   auto magic = [](int d) { return (uint64_t)(((((unsigned __int128)1) << 40) + d - 1) / (unsigned)d); };
   a.m_ntiles = magic(a.n_tiles); a.m_tpi = magic(a.tiles_w * a.tiles_h); a.m_tw = magic(a.tiles_w); a.m_bw = magic(a.BW);
+  a.m_ohw = magic(p.Ho * p.Wo);
   int grid = std::min(plan->grid, a.total_tiles);
+  // chained layers: one CTA per SM for the two-CTA plans, so that the other slot of every SM is free for the NEXT
+  // layer's CTA - consecutive layers then run side by side, the later one on the images the earlier one has finished
+  static const int chain_grid1 = getenv("YB_CHAIN_GRID1") ? atoi(getenv("YB_CHAIN_GRID1")) : 1;
+  if (chain && chain_grid1 && plan->occ == 2 && !a.dual) grid = std::min(grid, std::max(1, plan->grid / 2));
   // concurrent head branches: a latency-bound layer with ~1 tile per CTA gives up half of its CTAs (each
   // then pipelines 2-3 tiles) so that a sibling branch can occupy the other SMs at the same time
   if (plan->p.share_sms && a.total_tiles <= 4 * plan->grid && a.ksteps * (a.BK >> 4) <= 40)
@@ -1221,7 +1196,6 @@ struct StemArgs {
   int B, H, W, Ho, Wo, Cout;
   int tiles_w, tiles_h, total_tiles;
   uint32_t tmem_cols;
-  int silu_exact;
   uint64_t m_tpi, m_tw;  // magic numbers for / tiles_per_img and / tiles_w (fdiv)
 };
 
@@ -1364,15 +1338,10 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_con
           __half2* p1 = reinterpret_cast<__half2*>(&o1);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            const float v0 = __uint_as_float(acc[2 * j]) + s_bias[c0 + 2 * j], v1 = __uint_as_float(acc[2 * j + 1]) + s_bias[c0 + 2 * j + 1];
-            const float v2 = __uint_as_float(acc[8 + 2 * j]) + s_bias[c0 + 8 + 2 * j], v3 = __uint_as_float(acc[8 + 2 * j + 1]) + s_bias[c0 + 8 + 2 * j + 1];
-            if (a.silu_exact) {
-              p0[j] = __floats2half2_rn(silu_fast(v0), silu_fast(v1));
-              p1[j] = __floats2half2_rn(silu_fast(v2), silu_fast(v3));
-            } else {
-              p0[j] = __floats2half2_rn(silu_tanh(v0), silu_tanh(v1));
-              p1[j] = __floats2half2_rn(silu_tanh(v2), silu_tanh(v3));
-            }
+            p0[j] = __floats2half2_rn(silu_tanh(__uint_as_float(acc[2 * j]) + s_bias[c0 + 2 * j]),
+                                      silu_tanh(__uint_as_float(acc[2 * j + 1]) + s_bias[c0 + 2 * j + 1]));
+            p1[j] = __floats2half2_rn(silu_tanh(__uint_as_float(acc[8 + 2 * j]) + s_bias[c0 + 8 + 2 * j]),
+                                      silu_tanh(__uint_as_float(acc[8 + 2 * j + 1]) + s_bias[c0 + 8 + 2 * j + 1]));
           }
           *reinterpret_cast<int4*>(o + c0) = o0;
           *reinterpret_cast<int4*>(o + c0 + 8) = o1;
@@ -1409,7 +1378,6 @@ int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const __h
   uint32_t cols = 32;
   while (cols < (uint32_t)a.Cout) cols <<= 1;
   a.tmem_cols = cols;
-  a.silu_exact = silu_exact_mode();
   static int num_sms = 0;
   const size_t smem = 1024 + 16 * 1024 + (size_t)a.Cout * 128;
   if (!num_sms) {

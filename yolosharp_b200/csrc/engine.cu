@@ -65,9 +65,9 @@ struct OpDesc {
   int lane = 0;        // 0 = main stream; >0 = independent head branch that may run concurrently
   int lane_level = -1; // pyramid level whose feature map a side lane waits for
   int feat_level = -1; // this op completes feats[feat_level] (fork point for the head lanes)
+  int dep_op = -1;     // layer chaining: the op whose per-image completion gates this op's tiles (-1: whole previous grid)
   EpiDecode dec;       // conv: fused Detect-tail epilogue (tcgen05 path)
-  bool fused = false;  // decode / upsample op: its work is done by the producing convs' epilogues
-  VRef up_out;         // conv: second destination = the consumer's concat slice at 2x resolution (fused Upsample)
+  bool fused = false;  // decode op: its work is done by the producing convs' epilogues
 };
 
 struct HostTensor {
@@ -88,6 +88,8 @@ struct yb_engine {
   char* arena = nullptr;
   size_t arena_bytes = 0;
   int* tile_ctr = nullptr;  // one dynamic-scheduler counter per op, zeroed at the start of every forward
+  int* done_ctr = nullptr;  // layer chaining: [op][image] rows stored (same allocation as tile_ctr, zeroed with it)
+  bool chain = false;
   bool finalized = false;
   int esize = 4;  // bytes per activation element
   int A = 0, pred_c = 0;
@@ -96,7 +98,7 @@ struct yb_engine {
   VRef input_nhwc;  // generic path: converted network input (3 channels)
   VRef proto_view;
   bool has_stem_tc = false;
-  // staging for yb_predict_u8 (index 0) and the two pipelined slots of yb_predict_u8_submit (1, 2)
+  // staging for yb_predict_u8 (index 0) and the pipelined slots of yb_predict_u8_submit (1 .. kSlots)
   struct Stage {
     uint8_t* in = nullptr;
     float* pred = nullptr;
@@ -105,7 +107,8 @@ struct yb_engine {
     int max_det = 0;
     cudaStream_t stream = nullptr;
   };
-  Stage stage[3];
+  static const int kSlots = 4;
+  Stage stage[1 + kSlots];
   cudaEvent_t arena_free = nullptr;  // recorded after each staged forward: the activation arena is shared
   bool arena_used = false;
   // CUDA graph cache
@@ -668,7 +671,6 @@ static ConvParams conv_params(const yb_engine* e, const OpDesc& op, int B) {
   p.in = make_view(e, op.in);
   p.out = make_view(e, op.out);
   p.res = make_view(e, op.res);
-  p.out2 = make_view(e, op.up_out);
   p.w = op.w_f32;
   p.bias = op.bias;
   p.B = B;
@@ -691,7 +693,8 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
   bool lane_started[yb_engine::kLanes] = {};
   cudaStream_t main_s = s;
   if (only >= 0) input_converted = true;  // single-op timing (yb_time_op): buffers hold the last forward's data
-  if (e->tile_ctr) YB_CUDA_CHECK(cudaMemsetAsync(e->tile_ctr, 0, e->ops.size() * sizeof(int), s));
+  if (e->tile_ctr)
+    YB_CUDA_CHECK(cudaMemsetAsync(e->tile_ctr, 0, e->ops.size() * (size_t)(1 + e->cfg.max_batch) * sizeof(int), s));
   for (size_t i = 0; i < e->ops.size(); i++) {
     if (only >= 0 && (int)i != only) continue;
     OpDesc& op = e->ops[i];
@@ -719,7 +722,16 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
           input_converted = true;
         }
         if (op.use_tc) {
-          rc = tc_conv_launch(op.plan, B, out_pred, e->tile_ctr ? e->tile_ctr + i : nullptr, s);
+          TcChain ch;
+          const bool chained = e->chain && only < 0;
+          if (chained) {
+            ch.done_ctr = e->done_ctr + i * (size_t)e->cfg.max_batch;
+            if (op.dep_op >= 0) {
+              ch.dep_ctr = e->done_ctr + op.dep_op * (size_t)e->cfg.max_batch;
+              ch.dep_expect = tc_conv_rows_per_image(e->ops[op.dep_op].plan);
+            }
+          }
+          rc = tc_conv_launch(op.plan, B, out_pred, e->tile_ctr ? e->tile_ctr + i : nullptr, s, chained ? &ch : nullptr);
         } else {
           rc = launch_conv_generic<T>(conv_params(e, op, B), s);
         }
@@ -736,7 +748,6 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
         if (rc) return rc;
         break;
       case OP_UPSAMPLE:
-        if (op.fused) break;
         rc = launch_upsample2x<T>(make_view(e, op.in), make_view(e, op.out), B, s);
         if (rc) return rc;
         break;
@@ -844,7 +855,8 @@ int32_t yb_create(const yb_config* cfg, yb_engine** out) {
   e->arena_bytes = off;
   YB_CUDA_CHECK(cudaMalloc((void**)&e->arena, off));
   YB_CUDA_CHECK(cudaMemset(e->arena, 0, off));
-  YB_CUDA_CHECK(cudaMalloc((void**)&e->tile_ctr, e->ops.size() * sizeof(int)));
+  YB_CUDA_CHECK(cudaMalloc((void**)&e->tile_ctr, e->ops.size() * (size_t)(1 + cfg->max_batch) * sizeof(int)));
+  e->done_ctr = e->tile_ctr + e->ops.size();
   // forward kernels are captured at the highest stream priority: when the caller overlaps post-processing of the
   // previous batch (NMS on another stream) with this forward, freed SMs go to the forward's CTAs first
   int prio_least = 0, prio_greatest = 0;
@@ -972,19 +984,6 @@ int32_t yb_finalize_weights(yb_engine* e) {
       d.fused = true;
     }
   }
-  if (allow_tc && !getenv("YB_DEBUG_NO_UPFUSE")) {
-    // Upsample + Concat fusion: the tcgen05 conv that produces an Upsample's input also writes the 2x2-expanded
-    // copy into the consumer's concat slice (one kernel less per FPN level, no re-read of the feature map)
-    for (auto& u : e->ops) {
-      if (u.type != OP_UPSAMPLE) continue;
-      OpDesc* pr = nullptr;
-      for (auto& c : e->ops)
-        if (c.type == OP_CONV && c.out.buf == u.in.buf && c.out.coff == u.in.coff && c.out.C == u.in.C) pr = &c;
-      if (!pr || pr->cin % 16 || pr->cout % 16 || u.out.coff % 8 || e->bufs[u.out.buf].C % 8) continue;
-      pr->up_out = u.out;
-      u.fused = true;
-    }
-  }
   for (size_t i = 0; i < e->ops.size(); i++) {
     OpDesc& op = e->ops[i];
     if (op.type != OP_CONV && op.type != OP_DWCONV) continue;
@@ -1004,9 +1003,6 @@ int32_t yb_finalize_weights(yb_engine* e) {
         op.plan = tc_conv_plan_create(p, &err);
         if (!op.plan) { set_error("tcgen05 plan failed for " + op.name + ": " + err); return YB_ERR_CUDA; }
         op.use_tc = true;
-      } else if (op.up_out.buf >= 0) {
-        set_error("internal: fused upsample producer " + op.name + " did not get a tcgen05 plan");
-        return YB_ERR_STATE;
       }
     }
   }
@@ -1017,6 +1013,28 @@ int32_t yb_finalize_weights(yb_engine* e) {
         set_error("internal: fused decode producer " + c.name + " did not get a tcgen05 plan");
         return YB_ERR_STATE;
       }
+  }
+  // Layer chaining: inside a lane, a tcgen05 conv whose stream predecessor is a tcgen05 conv that stores an NHWC
+  // tensor starts its tiles per image, as soon as the predecessor has stored that image (per-image counters), instead
+  // of waiting for the predecessor's whole grid.  Completion per image is monotone along the lane (every op waits for
+  // its predecessor's image before it stores its own), so the predecessor's counter also covers older producers of the
+  // same image (concat slices, shortcut inputs).  Ops after anything else (stem, pool, attention, depthwise convs,
+  // lane forks) keep the grid-wide dependency.
+  e->chain = allow_tc && getenv("YB_CHAIN") && atoi(getenv("YB_CHAIN")) != 0;
+  if (e->chain) {
+    int prev_in_lane[yb_engine::kLanes];
+    for (int l = 0; l < yb_engine::kLanes; l++) prev_in_lane[l] = -1;
+    for (size_t i = 0; i < e->ops.size(); i++) {
+      OpDesc& op = e->ops[i];
+      if (op.type == OP_DECODE && op.fused) continue;  // launches nothing
+      const int lane = (e->cfg.flags & YB_FLAG_NO_CONCURRENCY) ? 0 : op.lane;
+      const int pv = prev_in_lane[lane];
+      if (op.type == OP_CONV && op.use_tc && pv >= 0) {
+        const OpDesc& pr = e->ops[pv];
+        if (pr.type == OP_CONV && pr.use_tc && pr.dec.mode == EPI_STORE) op.dep_op = pv;
+      }
+      prev_in_lane[lane] = (int)i;
+    }
   }
   e->lanes_ok = allow_tc && !(e->cfg.flags & YB_FLAG_NO_CONCURRENCY);
   for (auto& d : e->ops)
@@ -1273,7 +1291,7 @@ int32_t yb_predict_u8(yb_engine* e, const uint8_t* images_host, int32_t batch, f
 
 int32_t yb_predict_u8_submit(yb_engine* e, int32_t slot, const uint8_t* images_host, int32_t batch, float conf_thres,
                              float iou_thres, int32_t max_det, float* dets_host, int32_t* counts_host) {
-  if (!e || slot < 0 || slot > 1) { set_error("yb_predict_u8_submit: bad engine / slot (0 or 1)"); return YB_ERR_INVALID_ARG; }
+  if (!e || slot < 0 || slot >= yb_engine::kSlots) { set_error("yb_predict_u8_submit: bad engine / slot (0..3)"); return YB_ERR_INVALID_ARG; }
   yb_engine::Stage& st = e->stage[1 + slot];
   if (!st.stream) {
     YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
@@ -1286,7 +1304,7 @@ int32_t yb_predict_u8_submit(yb_engine* e, int32_t slot, const uint8_t* images_h
 int32_t yb_predict_u8_submit_gather(yb_engine* e, yb_comm* comm, int32_t slot, const uint8_t* images_host, int32_t batch,
                                     float conf_thres, float iou_thres, int32_t max_det, float* all_dets_host,
                                     int32_t* all_counts_host) {
-  if (!e || !comm || slot < 0 || slot > 1) { set_error("yb_predict_u8_submit_gather: bad engine / comm / slot (0 or 1)"); return YB_ERR_INVALID_ARG; }
+  if (!e || !comm || slot < 0 || slot >= yb_engine::kSlots) { set_error("yb_predict_u8_submit_gather: bad engine / comm / slot (0..3)"); return YB_ERR_INVALID_ARG; }
   yb_engine::Stage& st = e->stage[1 + slot];
   if (!st.stream) {
     YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
@@ -1297,7 +1315,7 @@ int32_t yb_predict_u8_submit_gather(yb_engine* e, yb_comm* comm, int32_t slot, c
 }
 
 int32_t yb_predict_u8_wait(yb_engine* e, int32_t slot) {
-  if (!e || slot < 0 || slot > 1) { set_error("yb_predict_u8_wait: bad engine / slot (0 or 1)"); return YB_ERR_INVALID_ARG; }
+  if (!e || slot < 0 || slot >= yb_engine::kSlots) { set_error("yb_predict_u8_wait: bad engine / slot (0..3)"); return YB_ERR_INVALID_ARG; }
   yb_engine::Stage& st = e->stage[1 + slot];
   if (!st.stream) { set_error("yb_predict_u8_wait: nothing was submitted on this slot"); return YB_ERR_STATE; }
   YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
@@ -1398,7 +1416,6 @@ int32_t yb_op_cost(const yb_engine* e, int32_t i, int32_t batch, double* flops, 
     const double macs = (double)batch * ob.H * ob.W * op.cout * (op.cin / op.groups) * op.k * op.k;
     *flops = 2.0 * macs;
     *bytes += (double)op.cout * (op.cin / op.groups) * op.k * op.k * e->esize;
-    if (op.up_out.buf >= 0) *bytes += 4.0 * vbytes(op.out);  // fused Upsample: the 2x2-expanded copy
     if (op.use_tc && op.dec.mode != EPI_STORE)  // fused head tail writes fp32 straight into pred
       *bytes += vbytes(op.out) / e->esize * 4.0 - vbytes(op.out);
     if (i == 0) {  // stem reads the caller's NCHW tensor, not an engine buffer
@@ -1437,7 +1454,7 @@ int32_t yb_launches_per_forward(const yb_engine* e) {
   if (!e) return 0;
   int n = e->has_stem_tc ? 0 : 1;  // generic path converts the input layout first
   for (const OpDesc& op : e->ops)
-    if (!((op.type == OP_DECODE || op.type == OP_UPSAMPLE) && op.fused)) n++;
+    if (!(op.type == OP_DECODE && op.fused)) n++;
   return n;
 }
 

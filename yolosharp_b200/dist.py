@@ -94,8 +94,8 @@ class DetectionGather:
         # NCCL variant: local predict into this rank's rows of the host buffers is not enough - gather on the device
         if not hasattr(self, "_h"):
             self._h = [(torch.empty((self.B, self.max_det, self.row_w), dtype=torch.float32).pin_memory(),
-                        torch.empty((self.B,), dtype=torch.int32).pin_memory()) for _ in range(2)]
-            self._s = [torch.cuda.Stream(self.device, priority=-1) for _ in range(2)]
+                        torch.empty((self.B,), dtype=torch.int32).pin_memory()) for _ in range(len(self.send))]
+            self._s = [torch.cuda.Stream(self.device, priority=-1) for _ in range(len(self.send))]
         eng.predict_u8_submit(slot, images_host, self._h[slot][0], self._h[slot][1], conf, iou, self.max_det)
         self._pending = getattr(self, "_pending", {})
         self._pending[slot] = (all_dets_host, all_counts_host)
