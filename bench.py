@@ -192,6 +192,137 @@ def bind_to_gpu_numa(device_index):
         return f"not bound ({type(e).__name__}: {e})"
 
 
+def synth_targets(B, seed):
+    """per image G in U{1..20} boxes, cls U{0..79}, cx,cy in U(0.1,0.9), w,h in U(0.05,0.5)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    rows = []
+    for b in range(B):
+        n = int(torch.randint(1, 21, (1,), generator=g))
+        t = torch.empty(n, 6)
+        t[:, 0] = b
+        t[:, 1] = torch.randint(0, 80, (n,), generator=g).float()
+        t[:, 2:4] = torch.rand(n, 2, generator=g) * 0.8 + 0.1
+        t[:, 4:6] = torch.rand(n, 2, generator=g) * 0.45 + 0.05
+        rows.append(t)
+    return torch.cat(rows)
+
+
+def train_main(args, rank, world, local_rank):
+    """BASELINE configs[3]: YOLOv11s training step (train-mode forward with batch-statistics BatchNorm, v8DetectionLoss
+    incl. the task-aligned assigner, backward through the whole graph, ONE NCCL all-reduce of the flat gradient buffer
+    when N > 1, AdamW), batch 16 per GPU, fp32 parity kernels (CUDA cores) - the tensor-core backward is not built, so
+    this number is the correctness path's, reported as such."""
+    model = args.model if args.model.startswith("v11") else "v11s"
+    arch, size, task, gflop_img = MODELS[model]
+    B = args.batch if args.batch != 32 else 16
+    config = {"workload": f"YOLO{model} detect training step (fwd + DFL/CIoU/BCE loss + bwd + AdamW), batch {B}x3x640x640 per GPU",
+              "model": model, "batch_per_gpu": B, "global_batch": B * world, "imgsz": 640, "weights": "seeded synthetic",
+              "parallelism": f"data-parallel x{world}" + (" + NCCL all-reduce of the flat gradient buffer" if world > 1 else "")}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import torch
+        from oracle import loss as oloss
+        from tests.util import oracle_model, synth_image
+        sb = 2  # bounded sample: the CPU step is ~2 s per image
+        m = oracle_model(arch, task, size).train()
+        opt = torch.optim.AdamW([p for k, p in m.named_parameters() if ".dfl." not in k], lr=1.19e-4, weight_decay=5e-4)
+        crit = oloss.V8DetectionLoss(80)
+        x, t = synth_image(sb, 640, 640), synth_targets(sb, 1)
+        batch = {"batch_idx": t[:, 0], "cls": t[:, 1], "bboxes": t[:, 2:]}
+
+        def step():
+            _, preds = m(x)
+            loss, _ = crit(preds, batch)
+            opt.zero_grad()
+            loss.sum().backward()
+            opt.step()
+        for _ in range(min(args.warmup, 1)):
+            step()
+        n = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step()
+        dt = (time.perf_counter() - t0) / n
+        val = sb / dt
+        print(json.dumps({"impl": "reference", "metric": f"train images/sec YOLO{model} 3x640x640", "value": round(val, 3),
+                          "unit": "images/s", "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3, 1),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": config,
+                          "cpu_baseline": {"value": round(val, 3), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                                           "sample": f"{sb} of {B} images per step, {n} steps (oracle autograd step on the host cores)"},
+                          "e2e": {"value": round(val, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    import torch.distributed as dist
+    from tests.util import oracle_model, synth_image
+    from yolosharp_b200.train_v11 import KernelOpsV11, TrainStepV11
+    assert torch.cuda.is_available(), "bench.py needs a B200"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    m = oracle_model(arch, task, size)
+    st = TrainStepV11({k: v.detach().clone() for k, v in m.state_dict().items()}, size, 80, device=dev, ops=KernelOpsV11())
+    del m
+    xs = [synth_image(B, 640, 640, seed=300 + rank * 4 + i).to(dev) for i in range(2)]
+    ts = [synth_targets(B, 400 + rank * 4 + i) for i in range(2)]
+    u8 = [synth_image(B, 640, 640, seed=300 + rank * 4 + i, dtype=torch.uint8).pin_memory() for i in range(2)]
+    for i in range(args.warmup):
+        st.step(xs[i & 1], ts[i & 1])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        items = st.step(xs[i & 1], ts[i & 1])
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    # e2e: pinned uint8 images -> device (/255 there), step, loss items back on the host
+    n2 = max(2, args.steps // 2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n2):
+        x = u8[i & 1].to(dev, non_blocking=True).float().div_(255.0)
+        host_items = st.step(x, ts[i & 1]).cpu()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peaks = load_peaks()
+        value = world * B * args.steps / (ms_total / 1e3)
+        tflops = 3 * gflop_img * 1e9 * value / world / 1e12  # fwd + dgrad + wgrad ~ 3x the forward MACs
+        print(json.dumps({"metric": f"train images/sec YOLO{model} 3x640x640", "value": round(value, 2), "unit": "images/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 2),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": config, "clocks": clocks,
+                          "e2e": {"value": round(world * B * n2 / float(t.item()), 2), "unit": "images/s",
+                                  "h2d_bytes_per_step": B * 3 * 640 * 640, "d2h_bytes_per_step": 12, "steps": n2,
+                                  "api": "TrainStepV11.step over the C-ABI training kernels (pinned uint8 images in, loss items out)"},
+                          "loss_items": [round(float(v), 4) for v in host_items],
+                          "roofline": {"bound": "tensor", "achieved": round(tflops, 2), "peak": peaks["tc"], "unit": "TFLOP/s",
+                                       "frac": round(tflops / peaks["tc"], 5), "traffic": None,
+                                       "kernel": "conv_generic / conv_backward_data / conv_backward_weight (fp32 CUDA cores)",
+                                       "note": "fp32 parity kernels: the fraction is against the tensor peak the missing tcgen05 "
+                                               "dgrad / wgrad would be judged by"}}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,6 +332,8 @@ def main():
     ap.add_argument("--model", default="v8n", choices=sorted(MODELS))
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--gather", default="comm", choices=["comm", "nccl"], help="N > 1: detection exchange")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train: one YOLOv11s training step (fwd + v8DetectionLoss + bwd + all-reduce + AdamW), BASELINE configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-real-weights", action="store_true")
     args = ap.parse_args()
@@ -208,6 +341,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.mode == "train":
+        return train_main(args, rank, world, local_rank)
     arch, size, task, gflop_img = MODELS[args.model]
     workload = (f"YOLO{args.model} {task} inference (forward+decode+NMS" + ("+masks" if task == "segment" else "") +
                 f"), batch {args.batch}x3x640x640 per GPU")

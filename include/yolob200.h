@@ -183,6 +183,23 @@ int32_t yb_conv_backward_data(const float* dz, const float* w, int32_t n, int32_
 int32_t yb_conv_backward_weight(const float* x, const float* dz, int32_t n, int32_t height, int32_t width, int32_t cin,
                                 int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dw, void* stream);
 
+/* Replaces (training path of YOLOv11, fp32 parity kernels): the forward and the autograd backward of the depthwise 3x3
+ * convolutions - `Convs.DWConv` (Modules/Convs.cs:108-114; groups = gcd(c1, c2) = c for every use in Yolov11: the
+ * class branch of the head, Head.cs:50, and `Attention.pe`, Block.cs:746), stride 1, padding 1.
+ *   x, z, dz, dx  dev float32 NHWC (N, H, W, C);  w, dw  dev float32 (C, 1, 3, 3) checkpoint layout */
+int32_t yb_dwconv3x3_forward_f32(const float* x, const float* w, int32_t n, int32_t height, int32_t width, int32_t channels,
+                                 float* z, void* stream);
+int32_t yb_dwconv3x3_backward_f32(const float* x, const float* dz, const float* w, int32_t n, int32_t height, int32_t width,
+                                  int32_t channels, float* dx, float* dw, void* stream);
+/* Replaces (training path of YOLOv11): the attention core of `Block.Attention.forward` (Modules/Block.cs:785-809):
+ * out[b, i, h, :] = sum_j softmax_j(scale * q[b, i, h, :] . k[b, j, h, :]) v[b, j, h, :], and its backward.
+ *   q, k, dq, dk  dev float32 (B, N, heads, key_dim);  v, out, dout, dv  dev float32 (B, N, heads, head_dim) */
+int32_t yb_attention_forward_f32(const float* q, const float* k, const float* v, int32_t batch, int32_t tokens, int32_t heads,
+                                 int32_t key_dim, int32_t head_dim, float scale, float* out, void* stream);
+int32_t yb_attention_backward_f32(const float* q, const float* k, const float* v, const float* dout, int32_t batch, int32_t tokens,
+                                  int32_t heads, int32_t key_dim, int32_t head_dim, float scale, float* dq, float* dk, float* dv,
+                                  void* stream);
+
 /* Replaces: `Ops.process_mask(proto[i], rows[:,6:], rows[:,:4], shape, upsample:true)`
  * (Utils/Ops.cs:462-489, CUDA branch of crop_mask :437-447) for a whole batch.
  *   proto  dev float32 (B,32,mh,mw);  dets/counts as written by yb_nms with extra == 32

@@ -138,13 +138,13 @@ def test_train_step_param_groups_cpu():
 
 def test_train_step_v11_graph_logic_cpu():
     """YOLOv11 (C3k2 / C3k / C2PSA attention / depthwise convs / non-legacy head): graph logic of train_v11.py against
-    autograd through the oracle.  The GPU kernels for grouped convs and attention do not exist yet (KernelOpsV11
-    raises), so there is no -m gpu twin of this test."""
+    autograd through the oracle, with the PyTorch stand-in of the kernel interface."""
     from tests.torch_train_ops import TorchOps
-    from yolosharp_b200.train_v11 import KernelOpsV11, TrainStepV11
+    from yolosharp_b200.train_v11 import TrainStepV11
     _compare(TrainStepV11, TorchOps(), "cpu", 2e-4, arch="v11")
-    with pytest.raises(NotImplementedError):
-        KernelOpsV11.gconv_forward(None, None, None, 1, 1, 1)
+    from yolosharp_b200.train_v11 import KernelOpsV11
+    with pytest.raises(NotImplementedError):  # only depthwise 3x3 stride-1 grouped convs have kernels: refused, not emulated
+        KernelOpsV11._check_dw(torch.zeros(1, 4, 4, 8), torch.zeros(8, 2, 3, 3), 1, 1, 4)
 
 
 def test_fit_loop_learning_rates():
@@ -180,3 +180,48 @@ def test_fit_loop_learning_rates():
     fit(st2, [(None, torch.zeros(1, 6))] * 70, epochs=1, lrf=0.01, warmup_epochs=1)   # nb = 70, nw = 100, ni = 70 .. 139
     d = 1e-3 * lr_lambda_linear(1, 0.01, 1)
     assert abs(st2.calls[30][1] - d) < 1e-15 and st2.calls[31] == st2.calls[30] == st2.calls[-1]   # ni = 100 is the last update
+
+
+@pytest.mark.gpu
+def test_train_step_v11_kernels_gpu():
+    """The same comparison with the library's kernels (csrc/train_v11.cu: depthwise conv + attention forward / backward,
+    plus the fp32 parity kernels of the v8 step): BASELINE configs[3] architecture (n size), one full step."""
+    import yolosharp_b200  # noqa: F401
+    from yolosharp_b200.train_v11 import KernelOpsV11, TrainStepV11
+    _compare(TrainStepV11, KernelOpsV11(), "cuda", 1e-3, arch="v11")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 20, 20, 256), (3, 9, 7, 48), (1, 40, 40, 128)])
+def test_dwconv3x3_forward_backward_vs_autograd(shape):
+    import yolosharp_b200 as y
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g)
+    w = (torch.randn(shape[-1], 1, 3, 3, generator=g) * 0.3)
+    dz = torch.randn(shape, generator=g)
+    xt, wt = x.permute(0, 3, 1, 2).clone().requires_grad_(True), w.clone().requires_grad_(True)
+    zt = torch.nn.functional.conv2d(xt, wt, None, 1, 1, 1, shape[-1])
+    zt.backward(dz.permute(0, 3, 1, 2))
+    z = y.engine.dwconv3x3_forward(x.cuda(), w.cuda())
+    np.testing.assert_allclose(z.cpu().permute(0, 3, 1, 2).numpy(), zt.detach().numpy(), rtol=1e-5, atol=1e-5)
+    dx, dw = y.engine.dwconv3x3_backward(x.cuda(), dz.cuda(), w.cuda())
+    np.testing.assert_allclose(dx.cpu().permute(0, 3, 1, 2).numpy(), xt.grad.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dw.cpu().numpy(), wt.grad.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N,nh,kd,hd", [(2, 400, 2, 32, 64), (3, 49, 4, 16, 32), (1, 130, 1, 32, 64)])
+def test_attention_forward_backward_vs_autograd(B, N, nh, kd, hd):
+    import yolosharp_b200 as y
+    from tests.torch_train_ops import TorchOps
+    g = torch.Generator().manual_seed(N + nh)
+    q, k = torch.randn(B, N, nh, kd, generator=g), torch.randn(B, N, nh, kd, generator=g)
+    v, do = torch.randn(B, N, nh, hd, generator=g), torch.randn(B, N, nh, hd, generator=g)
+    scale = kd ** -0.5
+    ref = TorchOps._attn(q, k, v, scale)
+    rq, rk, rv = TorchOps().attention_backward(q, k, v, scale, do)
+    out = y.engine.attention_forward(q.cuda(), k.cuda(), v.cuda(), scale)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
+    dq, dk, dv = y.engine.attention_backward(q.cuda(), k.cuda(), v.cuda(), scale, do.cuda())
+    for got, exp in ((dq, rq), (dk, rk), (dv, rv)):
+        np.testing.assert_allclose(got.cpu().numpy(), exp.numpy(), rtol=1e-3, atol=2e-5)

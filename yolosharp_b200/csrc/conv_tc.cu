@@ -651,6 +651,7 @@ const __grid_constant__ TcArgs a) {
     const int G = a.n_groups;
     const int row = q * 32 + lane;
     const bool dyn = a.tile_ctr != nullptr;
+    int pend_img = -1, pend_cnt = 0;  // layer chaining: rows stored but not yet published
     for (int li = grp;; li += G) {
       const int tile = dyn ? tq_get(s_tile, &s_head, li) : (int)blockIdx.x + li * (int)gridDim.x;
       if (tile < 0 || tile >= a.total_tiles) break;
@@ -772,19 +773,38 @@ const __grid_constant__ TcArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
       if (a.done_ctr != nullptr && a.epi_mode == EPI_STORE) {
-        // publish this warp's rows: every lane's stores are ordered before the count (fence, then warp barrier, then
-        // one atomic per image); a flattened tile may span two images
-        __threadfence();
+        // Publish this warp's rows per image.  A publish is fence (every lane's stores before the count) + warp barrier
+        // + one atomic; the fence costs several hundred cycles on the epilogue's latency chain, so rows are counted in
+        // registers and published only when the warp moves on to another image (tiles arrive in image order) or runs
+        // out of tiles.  A flattened tile may span two images.
         const int my_img = (a.imgs == 1 && a.Ho == 1) ? fdiv(min(wo, a.Wo - 1), a.m_ohw) : img;
         const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        const int first = __shfl_sync(0xffffffffu, my_img, vm ? __ffs(vm) - 1 : 0);
-        const unsigned same = __ballot_sync(0xffffffffu, valid && my_img == first);
-        if (lane == 0 && vm) {
-          atomicAdd(a.done_ctr + first, __popc(same));
-          if (vm != same) atomicAdd(a.done_ctr + first + 1, __popc(vm ^ same));
+        if (vm) {
+          const int first = __shfl_sync(0xffffffffu, my_img, __ffs(vm) - 1);
+          const unsigned same = __ballot_sync(0xffffffffu, valid && my_img == first);
+          if (pend_img >= 0 && pend_img != first) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(a.done_ctr + pend_img, pend_cnt);
+            pend_cnt = 0;
+          }
+          pend_img = first;
+          pend_cnt += __popc(same);
+          if (vm != same) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(a.done_ctr + first, pend_cnt);
+            pend_img = first + 1;
+            pend_cnt = __popc(vm ^ same);
+          }
         }
       }
       if (dbg_on) a.dbg[dbg_t * 8 + 6] = clock64();
+    }
+    if (pend_img >= 0) {
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(a.done_ctr + pend_img, pend_cnt);
     }
   }
 

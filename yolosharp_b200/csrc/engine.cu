@@ -89,7 +89,7 @@ struct yb_engine {
   size_t arena_bytes = 0;
   int* tile_ctr = nullptr;  // one dynamic-scheduler counter per op, zeroed at the start of every forward
   int* done_ctr = nullptr;  // layer chaining: [op][image] rows stored (same allocation as tile_ctr, zeroed with it)
-  bool chain = false;
+  int chain = 0;  // 0 off, 1 chained, 2 publish counters only (experiments)
   bool finalized = false;
   int esize = 4;  // bytes per activation element
   int A = 0, pred_c = 0;
@@ -723,7 +723,7 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
         }
         if (op.use_tc) {
           TcChain ch;
-          const bool chained = e->chain && only < 0;
+          const bool chained = e->chain != 0 && only < 0;
           if (chained) {
             ch.done_ctr = e->done_ctr + i * (size_t)e->cfg.max_batch;
             if (op.dep_op >= 0) {
@@ -1020,8 +1020,8 @@ int32_t yb_finalize_weights(yb_engine* e) {
   // its predecessor's image before it stores its own), so the predecessor's counter also covers older producers of the
   // same image (concat slices, shortcut inputs).  Ops after anything else (stem, pool, attention, depthwise convs,
   // lane forks) keep the grid-wide dependency.
-  e->chain = allow_tc && getenv("YB_CHAIN") && atoi(getenv("YB_CHAIN")) != 0;
-  if (e->chain) {
+  e->chain = (allow_tc && getenv("YB_CHAIN")) ? atoi(getenv("YB_CHAIN")) : 0;
+  if (e->chain == 1) {
     int prev_in_lane[yb_engine::kLanes];
     for (int l = 0; l < yb_engine::kLanes; l++) prev_in_lane[l] = -1;
     for (size_t i = 0; i < e->ops.size(); i++) {

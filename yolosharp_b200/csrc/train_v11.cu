@@ -1,0 +1,362 @@
+// fp32 parity kernels of the YOLOv11 training step (BASELINE configs[3]) that the YOLOv8 step does not need:
+//   * depthwise 3x3 convolution, forward / dgrad / wgrad  - Convs.DWConv (Modules/Convs.cs:108-114, groups =
+//     gcd(c1, c2) = c for every use in Yolov11: Head.cs:50 class branch, Block.cs:746 Attention.pe)
+//   * attention core softmax(q^T k * scale) v, forward / backward  - Block.Attention.forward (Block.cs:785-809)
+// They replace the libtorch autograd kernels behind `loss.backward()` (Utils/Amp.cs:260-286) for these modules.
+// Everything is deterministic: reductions run in a fixed order (per-slab partials folded sequentially, per-row
+// sequential sums), no floating-point atomics.  Layouts are the training path's NHWC fp32 (train.py).
+#include <cmath>
+
+#include "common.cuh"
+
+namespace yb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// depthwise 3x3, stride 1, pad 1.  x, z, dz, dx: (N, H, W, C);  w: (C, 1, 3, 3) checkpoint layout
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void dw3x3_forward_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ z,
+                                     int N, int H, int W, int C, int transpose_taps) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)N * H * W * C;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  size_t p = idx / C;
+  const int wx = (int)(p % W);
+  p /= W;
+  const int hy = (int)(p % H);
+  const int n = (int)(p / H);
+  float acc = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; kh++) {
+    const int yy = hy + kh - 1;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; kw++) {
+      const int xx = wx + kw - 1;
+      if (xx < 0 || xx >= W) continue;
+      // dgrad = the same stencil with the taps rotated by 180 degrees
+      const int t = transpose_taps ? (2 - kh) * 3 + (2 - kw) : kh * 3 + kw;
+      acc = fmaf(x[(((size_t)n * H + yy) * W + xx) * C + c], w[c * 9 + t], acc);
+    }
+  }
+  z[idx] = acc;
+}
+
+// dw[c][t] = sum over pixels dz[p][c] * x[p + tap t][c]: slabs of 256 pixel rows -> partial[slab][t][c]
+constexpr int DW_SLAB = 256;
+__global__ void __launch_bounds__(256) dw3x3_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                                 float* __restrict__ partial, int N, int H, int W, int C) {
+  __shared__ float red[8][9][32];
+  const int cl = threadIdx.x & 31, r = threadIdx.x >> 5;  // 32 channels x 8 row stripes
+  const int c = blockIdx.x * 32 + cl;
+  const long long rows = (long long)N * H * W;
+  const long long r0 = (long long)blockIdx.y * DW_SLAB;
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; t++) acc[t] = 0.f;
+  if (c < C) {
+    for (long long p = r0 + r; p < r0 + DW_SLAB && p < rows; p += 8) {
+      const int wx = (int)(p % W);
+      const long long q = p / W;
+      const int hy = (int)(q % H);
+      const long long n = q / H;
+      const float g = dz[p * C + c];
+#pragma unroll
+      for (int kh = 0; kh < 3; kh++) {
+        const int yy = hy + kh - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; kw++) {
+          const int xx = wx + kw - 1;
+          if (xx < 0 || xx >= W) continue;
+          acc[kh * 3 + kw] = fmaf(g, x[((n * H + yy) * W + xx) * C + c], acc[kh * 3 + kw]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; t++) red[r][t][cl] = acc[t];
+  __syncthreads();
+  if (r == 0 && c < C) {
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      float s = 0.f;
+      for (int k = 0; k < 8; k++) s += red[k][t][cl];  // fixed order
+      partial[((size_t)blockIdx.y * 9 + t) * C + c] = s;
+    }
+  }
+}
+
+__global__ void dw3x3_wgrad_fold_kernel(const float* __restrict__ partial, float* __restrict__ dw, int slabs, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (t, c)
+  if (i >= 9 * C) return;
+  const int t = i / C, c = i - t * C;
+  float s = 0.f;
+  for (int k = 0; k < slabs; k++) s += partial[((size_t)k * 9 + t) * C + c];
+  dw[c * 9 + t] = s;
+}
+
+int dwconv3x3_forward_f32(const float* x, const float* w, int N, int H, int W, int C, float* z, cudaStream_t s) {
+  const size_t total = (size_t)N * H * W * C;
+  dw3x3_forward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, w, z, N, H, W, C, 0);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dwconv3x3_backward_f32(const float* x, const float* dz, const float* w, int N, int H, int W, int C, float* dx, float* dw,
+                           cudaStream_t s) {
+  const size_t total = (size_t)N * H * W * C;
+  dw3x3_forward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dz, w, dx, N, H, W, C, 1);
+  YB_CUDA_CHECK(cudaGetLastError());
+  const long long rows = (long long)N * H * W;
+  const int slabs = (int)((rows + DW_SLAB - 1) / DW_SLAB);
+  float* partial = nullptr;
+  YB_CUDA_CHECK(cudaMallocAsync((void**)&partial, (size_t)slabs * 9 * C * sizeof(float), s));
+  dw3x3_wgrad_partial_kernel<<<dim3((C + 31) / 32, slabs), 256, 0, s>>>(x, dz, partial, N, H, W, C);
+  dw3x3_wgrad_fold_kernel<<<(9 * C + 255) / 256, 256, 0, s>>>(partial, dw, slabs, C);
+  cudaError_t ce = cudaGetLastError();
+  cudaFreeAsync(partial, s);
+  YB_CUDA_CHECK(ce);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// attention core.  q, k: (B, N, nh, kd); v, out, dout: (B, N, nh, hd); one block per (row, head, image)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int AT_THREADS = 128;
+
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int i = 1; i < AT_THREADS / 32; i++) r = fmaxf(r, sh[i]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int i = 1; i < AT_THREADS / 32; i++) r += sh[i];  // fixed order
+  __syncthreads();
+  return r;
+}
+
+// forward: out_i = sum_j softmax_j(scale q_i.k_j) v_j; also the row statistics (max, sum) for the backward pass
+__global__ void __launch_bounds__(AT_THREADS) attn_forward_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                                  const float* __restrict__ v, float* __restrict__ out,
+                                                                  float* __restrict__ row_max, float* __restrict__ row_sum,
+                                                                  int N, int nh, int kd, int hd, float scale) {
+  extern __shared__ float sm[];  // p[N] | qrow[kd]
+  float* p = sm;
+  float* qrow = sm + N;
+  __shared__ float red[AT_THREADS / 32];
+  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const size_t qk_stride = (size_t)nh * kd, v_stride = (size_t)nh * hd;
+  const float* qi = q + ((size_t)b * N + i) * qk_stride + (size_t)h * kd;
+  for (int d = threadIdx.x; d < kd; d += AT_THREADS) qrow[d] = qi[d];
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < N; j += AT_THREADS) {
+    const float* kj = k + ((size_t)b * N + j) * qk_stride + (size_t)h * kd;
+    float s = 0.f;
+    for (int d = 0; d < kd; d++) s = fmaf(qrow[d], kj[d], s);
+    s *= scale;
+    p[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < N; j += AT_THREADS) {
+    const float e = expf(p[j] - mx);
+    p[j] = e;
+    sum += e;
+  }
+  sum = block_sum(sum, red);
+  const float inv = 1.0f / sum;
+  for (int d = threadIdx.x; d < hd; d += AT_THREADS) {
+    const float* vd = v + (size_t)b * N * v_stride + (size_t)h * hd + d;
+    float o = 0.f;
+    for (int j = 0; j < N; j++) o = fmaf(p[j], vd[(size_t)j * v_stride], o);
+    out[((size_t)b * N + i) * v_stride + (size_t)h * hd + d] = o * inv;
+  }
+  if (threadIdx.x == 0 && row_max) {
+    row_max[((size_t)b * nh + h) * N + i] = mx;
+    row_sum[((size_t)b * nh + h) * N + i] = sum;
+  }
+}
+
+// backward pass A, per query row i: D_i = sum_j p_ij dP_ij, dS_ij = p_ij (dP_ij - D_i), dQ_i = scale sum_j dS_ij k_j
+__global__ void __launch_bounds__(AT_THREADS) attn_backward_q_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                                     const float* __restrict__ v, const float* __restrict__ dout,
+                                                                     const float* __restrict__ row_max, const float* __restrict__ row_sum,
+                                                                     float* __restrict__ row_d, float* __restrict__ dq, int N, int nh,
+                                                                     int kd, int hd, float scale) {
+  extern __shared__ float sm[];  // ds[N] | qrow[kd] | dorow[hd]
+  float* ds = sm;
+  float* qrow = sm + N;
+  float* dorow = qrow + kd;
+  __shared__ float red[AT_THREADS / 32];
+  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const size_t qk_stride = (size_t)nh * kd, v_stride = (size_t)nh * hd;
+  const size_t st = ((size_t)b * nh + h) * N + i;
+  const float mx = row_max[st], inv = 1.0f / row_sum[st];
+  for (int d = threadIdx.x; d < kd; d += AT_THREADS) qrow[d] = q[((size_t)b * N + i) * qk_stride + (size_t)h * kd + d];
+  for (int d = threadIdx.x; d < hd; d += AT_THREADS) dorow[d] = dout[((size_t)b * N + i) * v_stride + (size_t)h * hd + d];
+  __syncthreads();
+  float dsum = 0.f;
+  for (int j = threadIdx.x; j < N; j += AT_THREADS) {
+    const float* kj = k + ((size_t)b * N + j) * qk_stride + (size_t)h * kd;
+    const float* vj = v + ((size_t)b * N + j) * v_stride + (size_t)h * hd;
+    float s = 0.f, dp = 0.f;
+    for (int d = 0; d < kd; d++) s = fmaf(qrow[d], kj[d], s);
+    for (int d = 0; d < hd; d++) dp = fmaf(dorow[d], vj[d], dp);
+    const float pj = expf(s * scale - mx) * inv;
+    ds[j] = pj;  // p for now; dP is recomputed below (the score row holds N floats only)
+    dsum = fmaf(pj, dp, dsum);
+  }
+  const float D = block_sum(dsum, red);
+  for (int j = threadIdx.x; j < N; j += AT_THREADS) {
+    const float* vj = v + ((size_t)b * N + j) * v_stride + (size_t)h * hd;
+    float dp = 0.f;
+    for (int d = 0; d < hd; d++) dp = fmaf(dorow[d], vj[d], dp);
+    ds[j] = ds[j] * (dp - D);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < kd; d += AT_THREADS) {
+    const float* kd_ = k + (size_t)b * N * qk_stride + (size_t)h * kd + d;
+    float a = 0.f;
+    for (int j = 0; j < N; j++) a = fmaf(ds[j], kd_[(size_t)j * qk_stride], a);
+    dq[((size_t)b * N + i) * qk_stride + (size_t)h * kd + d] = a * scale;
+  }
+  if (threadIdx.x == 0) row_d[st] = D;
+}
+
+// backward pass B, per key row j: dV_j = sum_i p_ij dO_i, dK_j = scale sum_i dS_ij q_i
+__global__ void __launch_bounds__(AT_THREADS) attn_backward_kv_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                                      const float* __restrict__ v, const float* __restrict__ dout,
+                                                                      const float* __restrict__ row_max, const float* __restrict__ row_sum,
+                                                                      const float* __restrict__ row_d, float* __restrict__ dk,
+                                                                      float* __restrict__ dv, int N, int nh, int kd, int hd, float scale) {
+  extern __shared__ float sm[];  // p[N] | ds[N] | krow[kd] | vrow[hd]
+  float* p = sm;
+  float* ds = sm + N;
+  float* krow = ds + N;
+  float* vrow = krow + kd;
+  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const size_t qk_stride = (size_t)nh * kd, v_stride = (size_t)nh * hd;
+  for (int d = threadIdx.x; d < kd; d += AT_THREADS) krow[d] = k[((size_t)b * N + j) * qk_stride + (size_t)h * kd + d];
+  for (int d = threadIdx.x; d < hd; d += AT_THREADS) vrow[d] = v[((size_t)b * N + j) * v_stride + (size_t)h * hd + d];
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += AT_THREADS) {
+    const float* qi = q + ((size_t)b * N + i) * qk_stride + (size_t)h * kd;
+    const float* doi = dout + ((size_t)b * N + i) * v_stride + (size_t)h * hd;
+    const size_t st = ((size_t)b * nh + h) * N + i;
+    float s = 0.f, dp = 0.f;
+    for (int d = 0; d < kd; d++) s = fmaf(qi[d], krow[d], s);
+    for (int d = 0; d < hd; d++) dp = fmaf(doi[d], vrow[d], dp);
+    const float pij = expf(s * scale - row_max[st]) / row_sum[st];
+    p[i] = pij;
+    ds[i] = pij * (dp - row_d[st]);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < hd; d += AT_THREADS) {
+    const float* dod = dout + (size_t)b * N * v_stride + (size_t)h * hd + d;
+    float a = 0.f;
+    for (int i = 0; i < N; i++) a = fmaf(p[i], dod[(size_t)i * v_stride], a);
+    dv[((size_t)b * N + j) * v_stride + (size_t)h * hd + d] = a;
+  }
+  for (int d = threadIdx.x; d < kd; d += AT_THREADS) {
+    const float* qd = q + (size_t)b * N * qk_stride + (size_t)h * kd + d;
+    float a = 0.f;
+    for (int i = 0; i < N; i++) a = fmaf(ds[i], qd[(size_t)i * qk_stride], a);
+    dk[((size_t)b * N + j) * qk_stride + (size_t)h * kd + d] = a * scale;
+  }
+}
+
+static int attn_check(int B, int N, int nh, int kd, int hd, size_t smem_floats) {
+  if (B <= 0 || N <= 0 || nh <= 0 || kd <= 0 || hd <= 0) { set_error("attention: bad shape"); return YB_ERR_SHAPE; }
+  if (smem_floats * sizeof(float) > 200 * 1024) { set_error("attention: N too large for the shared-memory score rows"); return YB_ERR_NOT_IMPLEMENTED; }
+  return 0;
+}
+
+int attention_forward_f32(const float* q, const float* k, const float* v, int B, int N, int nh, int kd, int hd, float scale,
+                          float* out, float* row_max, float* row_sum, cudaStream_t s) {
+  const size_t smem = (size_t)N + kd;
+  if (int rc = attn_check(B, N, nh, kd, hd, smem)) return rc;
+  YB_CUDA_CHECK(cudaFuncSetAttribute(attn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  attn_forward_kernel<<<dim3(N, nh, B), AT_THREADS, smem * sizeof(float), s>>>(q, k, v, out, row_max, row_sum, N, nh, kd, hd, scale);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int attention_backward_f32(const float* q, const float* k, const float* v, const float* dout, int B, int N, int nh, int kd,
+                           int hd, float scale, float* dq, float* dk, float* dv, cudaStream_t s) {
+  const size_t smem_q = (size_t)N + kd + hd, smem_kv = (size_t)2 * N + kd + hd;
+  if (int rc = attn_check(B, N, nh, kd, hd, smem_kv)) return rc;
+  float* stats = nullptr;  // row max | row sum | row D, each (B, nh, N)
+  const size_t n = (size_t)B * nh * N;
+  YB_CUDA_CHECK(cudaMallocAsync((void**)&stats, (3 * n + (size_t)B * N * nh * hd) * sizeof(float), s));
+  float* tmp_out = stats + 3 * n;  // the forward output is recomputed only for its row statistics
+  int rc = attention_forward_f32(q, k, v, B, N, nh, kd, hd, scale, tmp_out, stats, stats + n, s);
+  if (!rc) {
+    cudaFuncSetAttribute(attn_backward_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(attn_backward_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attn_backward_q_kernel<<<dim3(N, nh, B), AT_THREADS, smem_q * sizeof(float), s>>>(q, k, v, dout, stats, stats + n, stats + 2 * n,
+                                                                                      dq, N, nh, kd, hd, scale);
+    attn_backward_kv_kernel<<<dim3(N, nh, B), AT_THREADS, smem_kv * sizeof(float), s>>>(q, k, v, dout, stats, stats + n, stats + 2 * n,
+                                                                                        dk, dv, N, nh, kd, hd, scale);
+    if (cudaGetLastError() != cudaSuccess) { set_error("attention backward launch failed"); rc = YB_ERR_CUDA; }
+  }
+  cudaFreeAsync(stats, s);
+  return rc;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+static bool have_dev(const char* who) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error(std::string(who) + ": no CUDA device");
+    return false;
+  }
+  return true;
+}
+
+extern "C" {
+
+int32_t yb_dwconv3x3_forward_f32(const float* x, const float* w, int32_t n, int32_t height, int32_t width, int32_t channels,
+                                 float* z, void* stream) {
+  if (!x || !w || !z || n <= 0 || height <= 0 || width <= 0 || channels <= 0) { set_error("yb_dwconv3x3_forward_f32: bad argument"); return YB_ERR_INVALID_ARG; }
+  if (!have_dev("yb_dwconv3x3_forward_f32")) return YB_ERR_NO_DEVICE;
+  return dwconv3x3_forward_f32(x, w, n, height, width, channels, z, (cudaStream_t)stream);
+}
+
+int32_t yb_dwconv3x3_backward_f32(const float* x, const float* dz, const float* w, int32_t n, int32_t height, int32_t width,
+                                  int32_t channels, float* dx, float* dw, void* stream) {
+  if (!x || !dz || !w || !dx || !dw || n <= 0 || height <= 0 || width <= 0 || channels <= 0) { set_error("yb_dwconv3x3_backward_f32: bad argument"); return YB_ERR_INVALID_ARG; }
+  if (!have_dev("yb_dwconv3x3_backward_f32")) return YB_ERR_NO_DEVICE;
+  return dwconv3x3_backward_f32(x, dz, w, n, height, width, channels, dx, dw, (cudaStream_t)stream);
+}
+
+int32_t yb_attention_forward_f32(const float* q, const float* k, const float* v, int32_t batch, int32_t tokens, int32_t heads,
+                                 int32_t key_dim, int32_t head_dim, float scale, float* out, void* stream) {
+  if (!q || !k || !v || !out) { set_error("yb_attention_forward_f32: null argument"); return YB_ERR_INVALID_ARG; }
+  if (!have_dev("yb_attention_forward_f32")) return YB_ERR_NO_DEVICE;
+  return attention_forward_f32(q, k, v, batch, tokens, heads, key_dim, head_dim, scale, out, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int32_t yb_attention_backward_f32(const float* q, const float* k, const float* v, const float* dout, int32_t batch, int32_t tokens,
+                                  int32_t heads, int32_t key_dim, int32_t head_dim, float scale, float* dq, float* dk, float* dv,
+                                  void* stream) {
+  if (!q || !k || !v || !dout || !dq || !dk || !dv) { set_error("yb_attention_backward_f32: null argument"); return YB_ERR_INVALID_ARG; }
+  if (!have_dev("yb_attention_backward_f32")) return YB_ERR_NO_DEVICE;
+  return attention_backward_f32(q, k, v, dout, batch, tokens, heads, key_dim, head_dim, scale, dq, dk, dv, (cudaStream_t)stream);
+}
+
+}  // extern "C"

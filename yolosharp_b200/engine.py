@@ -282,6 +282,54 @@ def conv_backward(x, dz, w, stride=1, pad=None, stream=None):
     return dx, dw
 
 
+def dwconv3x3_forward(x, w, stream=None):
+    """yb_dwconv3x3_forward_f32: x (N,H,W,C) NHWC float32, w (C,1,3,3) -> z (N,H,W,C) (stride 1, pad 1)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and w.is_cuda and w.is_contiguous()
+    N, H, W, Cc = x.shape
+    assert tuple(w.shape) == (Cc, 1, 3, 3), "depthwise 3x3 only (groups == channels)"
+    z = torch.empty_like(x)
+    L.check(L.lib().yb_dwconv3x3_forward_f32(C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), N, H, W, Cc,
+                                             C.c_void_p(z.data_ptr()), _stream_ptr(stream)))
+    return z
+
+
+def dwconv3x3_backward(x, dz, w, stream=None):
+    """yb_dwconv3x3_backward_f32 -> (dx like x, dw like w)."""
+    for t in (x, dz, w):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    N, H, W, Cc = x.shape
+    assert tuple(w.shape) == (Cc, 1, 3, 3) and dz.shape == x.shape
+    dx, dw = torch.empty_like(x), torch.empty_like(w)
+    L.check(L.lib().yb_dwconv3x3_backward_f32(C.c_void_p(x.data_ptr()), C.c_void_p(dz.data_ptr()), C.c_void_p(w.data_ptr()), N, H, W,
+                                              Cc, C.c_void_p(dx.data_ptr()), C.c_void_p(dw.data_ptr()), _stream_ptr(stream)))
+    return dx, dw
+
+
+def attention_forward(q, k, v, scale, stream=None):
+    """yb_attention_forward_f32: q, k (B,N,nh,kd), v (B,N,nh,hd) float32 contiguous -> out (B,N,nh,hd)."""
+    for t in (q, k, v):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    B, N, nh, kd = q.shape
+    hd = v.shape[-1]
+    out = torch.empty_like(v)
+    L.check(L.lib().yb_attention_forward_f32(C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()), B, N, nh, kd,
+                                             hd, float(scale), C.c_void_p(out.data_ptr()), _stream_ptr(stream)))
+    return out
+
+
+def attention_backward(q, k, v, scale, dout, stream=None):
+    """yb_attention_backward_f32 -> (dq, dk, dv)."""
+    for t in (q, k, v, dout):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    B, N, nh, kd = q.shape
+    hd = v.shape[-1]
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    L.check(L.lib().yb_attention_backward_f32(C.c_void_p(q.data_ptr()), C.c_void_p(k.data_ptr()), C.c_void_p(v.data_ptr()),
+                                              C.c_void_p(dout.data_ptr()), B, N, nh, kd, hd, float(scale), C.c_void_p(dq.data_ptr()),
+                                              C.c_void_p(dk.data_ptr()), C.c_void_p(dv.data_ptr()), _stream_ptr(stream)))
+    return dq, dk, dv
+
+
 def conv_forward(x, w, bias=None, stride=1, pad=None, stream=None):
     """yb_conv_forward_f32: x (N,H,W,Cin) NHWC float32, w (Cout,Cin,k,k) -> z (N,Ho,Wo,Cout) (no BN, no activation)."""
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and w.is_cuda and w.dtype == torch.float32

@@ -1,9 +1,8 @@
 """Graph logic of the YOLOv11 detect training step (BASELINE configs[3]: YOLOv11s), on the same `ops` interface as
-`train.py`.  STATUS: the wiring, the forward/backward of C3k2 / C3k / C2PSA / PSABlock / Attention and the v11 Detect
-head are written and pinned on the CPU against autograd through the oracle (tests/test_train_step.py, PyTorch stand-in
-of the kernel interface).  Two kernels of the library are still missing for the GPU path - the depthwise / grouped
-convolution (forward, dgrad, wgrad) and the attention core (softmax(q^T k) v with its backward) - so
-`KernelOpsV11` raises NotImplementedError for them instead of falling back to anything.
+`train.py`: the wiring, the forward/backward of C3k2 / C3k / C2PSA / PSABlock / Attention and the v11 Detect head,
+pinned against autograd through the oracle on the CPU (PyTorch stand-in of the kernel interface) and on the GPU with
+the library's kernels (tests/test_train_step.py): csrc/train_v11.cu adds the depthwise 3x3 convolution (forward,
+dgrad, wgrad) and the attention core softmax(q^T k) v with its backward to the fp32 parity kernels of the v8 step.
 
 Reference: Models/Yolo.cs:200-258 (Yolov11 wiring, outputIndexs {4,6,10,13,16,19,22}), Modules/Block.cs:404-441 (C3),
 :611-661 (C3k, C3k2), :664-810 (C2PSA, PSABlock, Attention), Modules/Convs.cs:108-114 (DWConv), Modules/Head.cs:35-53
@@ -23,17 +22,27 @@ V11_SIZES = {  # Models/Yolo.cs:213-217 (depth, width, max_channels, c3k)
 
 
 class KernelOpsV11(KernelOps):
+    """+ the depthwise 3x3 and attention kernels of csrc/train_v11.cu.  Every grouped conv of Yolov11 is depthwise
+    3x3 stride 1 (DWConv(c, c, 3) in the head, Attention.pe); anything else is refused, not emulated."""
+
+    @staticmethod
+    def _check_dw(x, w, stride, pad, groups):
+        if not (groups == x.shape[-1] == w.shape[0] and w.shape[1] == 1 and tuple(w.shape[2:]) == (3, 3) and stride == 1 and pad == 1):
+            raise NotImplementedError("only depthwise 3x3 stride-1 grouped convolutions have training kernels")
+
     def gconv_forward(self, x, w, stride, pad, groups):
-        raise NotImplementedError("grouped / depthwise convolution training kernels are not built yet")
+        self._check_dw(x, w, stride, pad, groups)
+        return self.E.dwconv3x3_forward(x.contiguous(), w.contiguous())
 
     def gconv_backward(self, x, dz, w, stride, pad, groups):
-        raise NotImplementedError("grouped / depthwise convolution training kernels are not built yet")
+        self._check_dw(x, w, stride, pad, groups)
+        return self.E.dwconv3x3_backward(x.contiguous(), dz.contiguous(), w.contiguous())
 
     def attention_forward(self, q, k, v, scale):
-        raise NotImplementedError("attention training kernels are not built yet")
+        return self.E.attention_forward(q.contiguous(), k.contiguous(), v.contiguous(), scale)
 
     def attention_backward(self, q, k, v, scale, dout):
-        raise NotImplementedError("attention training kernels are not built yet")
+        return self.E.attention_backward(q.contiguous(), k.contiguous(), v.contiguous(), scale, dout.contiguous())
 
 
 class _GConv(_Conv):
