@@ -96,6 +96,25 @@ int32_t yb_pred_channels(const yb_engine* e);
 int32_t yb_load_tensor(yb_engine* e, const char* name, int32_t dtype, int32_t ndim,
                        const int64_t* shape, const void* data);
 
+/* Native checkpoint ingest (csrc/ckpt.cu; host code, no TorchSharp / PyTorch needed).
+ * Replaces: `Lib.LoadModel` for the TorchSharp `.bin` format (Utils/Lib.cs:9-54), `SafetensorsLoader`
+ * (ModelLoader/SafetensorsLoader.cs:7-109) and `SaveWeight` (Models/YoloBaseTaskModel.cs:470-490).  The format is chosen
+ * by the file extension (`.safetensors`, anything else = `.bin`); Ultralytics `.pt` pickles return
+ * YB_ERR_NOT_IMPLEMENTED.  dtype codes are torch ScalarType values (yb_dtype; also 1 i8, 2 i16, 3 i32, 4 i64, 7 f64).
+ *   yb_load_checkpoint  = open + yb_load_tensor for every f16 / f32 / bf16 tensor (+ counts of loaded tensors and of
+ *                         expected tensors the file lacks; unlike YoloBaseTaskModel.cs:32-35 nothing falls back to
+ *                         random weights: yb_finalize_weights fails on the first missing tensor)
+ *   yb_ckpt_*           iterate a file without an engine; pointers stay valid until yb_ckpt_close */
+typedef struct yb_ckpt yb_ckpt;
+int32_t yb_ckpt_open(const char* path, yb_ckpt** out);
+int32_t yb_ckpt_count(const yb_ckpt* c);
+int32_t yb_ckpt_tensor(const yb_ckpt* c, int32_t i, const char** name, int32_t* dtype, int32_t* ndim, const int64_t** shape,
+                       const void** data, int64_t* nbytes);
+void yb_ckpt_close(yb_ckpt* c);
+int32_t yb_load_checkpoint(yb_engine* e, const char* path, int32_t* n_loaded, int32_t* n_missing);
+int32_t yb_ckpt_write_bin(const char* path, int32_t count, const char* const* names, const int32_t* dtypes, const int32_t* ndims,
+                          const int64_t* const* shapes, const void* const* datas);
+
 /* Fold eval-mode BatchNorm (eps 1e-3, Modules/Convs.cs:41) into the conv weights, pack to the
  * device layouts, build TMA descriptors.  Fails with YB_ERR_MISSING_WEIGHT naming the first
  * absent tensor (the reference silently keeps random weights, YoloBaseTaskModel.cs:32-35; we do not). */

@@ -34,6 +34,14 @@ SIGNATURES = {
     "yb_pred_channels": (c_i32, [c_vp]),
     "yb_load_tensor": (c_i32, [c_vp, c_cp, c_i32, c_i32, C.POINTER(C.c_int64), c_vp]),
     "yb_finalize_weights": (c_i32, [c_vp]),
+    "yb_ckpt_open": (c_i32, [c_cp, C.POINTER(c_vp)]),
+    "yb_ckpt_count": (c_i32, [c_vp]),
+    "yb_ckpt_tensor": (c_i32, [c_vp, c_i32, C.POINTER(c_cp), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(C.POINTER(C.c_int64)),
+                               C.POINTER(c_vp), C.POINTER(C.c_int64)]),
+    "yb_ckpt_close": (None, [c_vp]),
+    "yb_load_checkpoint": (c_i32, [c_vp, c_cp, C.POINTER(c_i32), C.POINTER(c_i32)]),
+    "yb_ckpt_write_bin": (c_i32, [c_cp, c_i32, C.POINTER(c_cp), C.POINTER(c_i32), C.POINTER(c_i32), C.POINTER(C.POINTER(C.c_int64)),
+                                  C.POINTER(c_vp)]),
     "yb_num_expected_tensors": (c_i32, [c_vp]),
     "yb_expected_tensor_name": (c_cp, [c_vp, c_i32]),
     "yb_forward": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),

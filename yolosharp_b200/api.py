@@ -213,16 +213,8 @@ class Detector:
         error, not a silent fall-back to random weights."""
         if skipNcNotEqualLayers:
             raise NotImplementedError("skipNcNotEqualLayers")
-        sd = {}
-        for name, dt, shape, data in binfmt.read_bin(path):
-            if len(data) == 0:  # empty buffers (`anchors` / `strides` of the head, Head.cs:11-12)
-                sd[name] = torch.empty(shape, dtype={5: torch.float16, 6: torch.float32, 15: torch.bfloat16}.get(dt, torch.float32))
-            elif dt == 5:
-                sd[name] = torch.frombuffer(bytearray(data), dtype=torch.float16).reshape(shape)
-            elif dt == 6:
-                sd[name] = torch.frombuffer(bytearray(data), dtype=torch.float32).reshape(shape)
-            elif dt == 15:
-                sd[name] = torch.frombuffer(bytearray(data), dtype=torch.bfloat16).reshape(shape)
+        from .engine import read_checkpoint
+        sd = {k: v for k, v in read_checkpoint(path).items() if v.dtype.is_floating_point}  # native .bin / .safetensors reader
         missing, _ = self.yolo.load_state_dict(sd)
         if missing:
             raise KeyError(f"{path}: {len(missing)} tensors missing, e.g. {missing[:3]}")

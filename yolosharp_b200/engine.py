@@ -65,6 +65,12 @@ class Engine:
             shp = (C.c_int64 * t.dim())(*t.shape)
             L.check(L.lib().yb_load_tensor(self._h, name.encode(), code, t.dim(), shp, C.c_void_p(t.data_ptr())))
 
+    def load_checkpoint(self, path):
+        """yb_load_checkpoint: native .bin / .safetensors reader -> (tensors loaded, expected tensors missing)."""
+        n, miss = C.c_int32(), C.c_int32()
+        L.check(L.lib().yb_load_checkpoint(self._h, str(path).encode(), C.byref(n), C.byref(miss)))
+        return n.value, miss.value
+
     def finalize(self):
         L.check(L.lib().yb_finalize_weights(self._h))
         self.finalized = True
@@ -407,3 +413,43 @@ class Comm:
 
 def detection_payload_bytes(batch, max_det, row_width):
     return int(L.lib().yb_comm_detection_payload_bytes(batch, max_det, row_width))
+
+
+_TORCH_OF_CODE = {0: torch.uint8, 1: torch.int8, 2: torch.int16, 3: torch.int32, 4: torch.int64, 5: torch.float16, 6: torch.float32,
+                  7: torch.float64, 15: torch.bfloat16}
+_CODE_OF_TORCH = {v: k for k, v in _TORCH_OF_CODE.items()}
+
+
+def read_checkpoint(path):
+    """yb_ckpt_*: native reader of TorchSharp .bin / .safetensors files -> ordered dict name -> torch tensor (file dtype)."""
+    lib = L.lib()
+    h = C.c_void_p()
+    L.check(lib.yb_ckpt_open(str(path).encode(), C.byref(h)))
+    out = {}
+    try:
+        for i in range(lib.yb_ckpt_count(h)):
+            name, dt, nd, shp, data, nb = C.c_char_p(), C.c_int32(), C.c_int32(), C.POINTER(C.c_int64)(), C.c_void_p(), C.c_int64()
+            L.check(lib.yb_ckpt_tensor(h, i, C.byref(name), C.byref(dt), C.byref(nd), C.byref(shp), C.byref(data), C.byref(nb)))
+            shape = [shp[k] for k in range(nd.value)]
+            td = _TORCH_OF_CODE[dt.value]
+            if nb.value:
+                t = torch.frombuffer(bytearray(C.string_at(data.value, nb.value)), dtype=td).reshape(shape)
+            else:
+                t = torch.empty(shape, dtype=td)
+            out[name.value.decode()] = t
+    finally:
+        lib.yb_ckpt_close(h)
+    return out
+
+
+def write_checkpoint_bin(path, state_dict):
+    """yb_ckpt_write_bin: the reference's SaveWeight format (YoloBaseTaskModel.cs:470-490)."""
+    items = [(k, v.detach().cpu().contiguous()) for k, v in state_dict.items()]
+    n = len(items)
+    names = (C.c_char_p * n)(*[k.encode() for k, _ in items])
+    dts = (C.c_int32 * n)(*[_CODE_OF_TORCH[v.dtype] for _, v in items])
+    nds = (C.c_int32 * n)(*[v.dim() for _, v in items])
+    shape_arrs = [(C.c_int64 * max(v.dim(), 1))(*v.shape) for _, v in items]
+    shapes = (C.POINTER(C.c_int64) * n)(*[C.cast(a, C.POINTER(C.c_int64)) for a in shape_arrs])
+    datas = (C.c_void_p * n)(*[v.data_ptr() if v.numel() else None for _, v in items])
+    L.check(L.lib().yb_ckpt_write_bin(str(path).encode(), n, names, dts, nds, shapes, datas))

@@ -343,6 +343,29 @@ class TrainStepV8:
                 dx = m.backward(dx.contiguous())
         return dx
 
+    def state_dict(self, dtype=torch.float32):
+        """Reference-named tensors of the trained model (what `yolo.state_dict()` holds, YoloBaseTaskModel.cs:470-490):
+        parameters, BatchNorm running statistics, `num_batches_tracked` (= steps taken, int64), the fp32 DFL weight
+        arange(16) (Block.cs:29-30; it never receives a gradient) and the head's empty `anchors` / `strides` buffers."""
+        out = {}
+        bn = sorted({k[:-len(".running_mean")] for k in self.P.buffers if k.endswith(".running_mean")})
+        for k in self.P.names:
+            out[k] = self.P.p(k).detach().to(dtype).cpu()
+        for b in bn:
+            out[b + ".running_mean"] = self.P.buffers[b + ".running_mean"].detach().to(dtype).cpu()
+            out[b + ".running_var"] = self.P.buffers[b + ".running_var"].detach().to(dtype).cpu()
+            out[b + ".num_batches_tracked"] = torch.tensor(self.step_count, dtype=torch.int64)
+        head = next(k for k in self.P.names if ".cv2.0.0." in k).split(".cv2.")[0]
+        out[head + ".dfl.conv.weight"] = torch.arange(16, dtype=torch.float32).view(1, 16, 1, 1)
+        out[head + ".anchors"] = torch.empty(0, dtype=dtype)
+        out[head + ".strides"] = torch.empty(0, dtype=dtype)
+        return out
+
+    def save(self, path, dtype=torch.float32):
+        """SaveWeight (YoloBaseTaskModel.cs:470-490): the reference's `.bin` through the library's native writer."""
+        from .engine import write_checkpoint_bin
+        write_checkpoint_bin(path, self.state_dict(dtype))
+
     def step(self, images_nchw, targets, lrs=None):
         """images (B,3,H,W) float32 in [0,1] on the device; targets (n,6) rows [image, cls, x, y, w, h];
         lrs = (lr of the "bias" group, lr of the other parameters) for this iteration (warm-up / schedule), default
