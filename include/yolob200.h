@@ -244,6 +244,19 @@ int32_t yb_predict_u8_submit(yb_engine* e, int32_t slot, const uint8_t* images_h
                              int32_t* counts_host);
 int32_t yb_predict_u8_wait(yb_engine* e, int32_t slot);
 
+/* Validation-side post-processing (csrc/val.cu), batched over the images of a step.
+ * yb_box_iou  replaces `Metrics.box_iou(box1, box2)` (Utils/Metrics.cs:16-34): out (n, m) float32, xyxy boxes.
+ * yb_match_predictions  replaces the per-image `match_predictions(pred_classes, true_classes, iou)` loop of
+ * `Detector.Val` (Models/YoloBaseTaskModel.cs:377-446, Models/Detector.cs:103-120):
+ *   dets / counts  as written by yb_nms (B, max_det, row_width) / (B)
+ *   labels  dev float32 (n_labels, 6) rows [image, class, x1, y1, x2, y2] in input pixels (batch_idx, cls, xywh2xyxy(bboxes * scale))
+ *   iou_thresholds_host  the reference's linspace(0.5, 0.95, 10) as float32 (HOST pointer)
+ *   correct  dev uint8 (B, max_det, n_thresholds): 1 where detection d is a true positive at threshold i */
+int32_t yb_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, float eps, float* out, void* stream);
+int32_t yb_match_predictions(const float* dets, const int32_t* counts, int32_t batch, int32_t max_det, int32_t row_width,
+                             const float* labels, int32_t n_labels, const float* iou_thresholds_host, int32_t n_thresholds,
+                             uint8_t* correct, void* stream);
+
 /* ---- multi-GPU: exchange of the fixed-capacity detection payloads over NVLink peer memory (csrc/comm.cu) ----
  * Design target SURVEY.md section 8(e); the reference is single-device (Data/Config.cs:301), so this surface is
  * net-new.  One yb_comm per process (= per GPU), all ranks on one node.  Every rank pushes its payload into a

@@ -311,3 +311,40 @@ def test_yolotask_loadmodel_bin_and_image_path(y, tmp_path):
     binfmt.write_bin(bad, [(k, code[v.dtype], list(v.shape), v.numpy().tobytes()) for k, v in list(sd.items())[:10]])
     with pytest.raises(KeyError):
         task.LoadModel(bad)
+
+
+# ------------------------------------------------------------------ validation matching (f3)
+def test_box_iou_and_match_predictions_vs_oracle(y):
+    """yb_box_iou bit-exact; yb_match_predictions == the reference's per-image match_predictions on the engine's own
+    NMS rows, labels = jittered copies of detections (so that several detections compete for one label and vice versa)."""
+    from oracle import val as oval
+    from tests.util import nms_case
+    g = torch.Generator().manual_seed(5)
+    b1, b2 = torch.rand(37, 4, generator=g) * 300, torch.rand(53, 4, generator=g) * 300
+    b1[:, 2:] += b1[:, :2]
+    b2[:, 2:] += b2[:, :2]
+    assert torch.equal(y.engine.box_iou(b1.cuda(), b2.cuda()).cpu(), oval.box_iou(b1, b2))
+    pred = nms_case(91, 4, 6, 2500, 0, 1.0, None, 0.5)
+    dets, counts, _ = y.nms(pred.cuda(), 0.1, 0.7, 300, 6)
+    labels = []
+    for b in range(4):
+        n = int(counts[b])
+        rows = dets[b, :n].cpu()
+        pick = rows[torch.randperm(n, generator=g)[:40]]
+        boxes = pick[:, :4] + torch.randn(pick.shape[0], 4, generator=g) * 6.0
+        cls = pick[:, 5].clone()
+        cls[::7] = (cls[::7] + 1) % 6  # some labels of another class
+        labels.append(torch.cat((torch.full((pick.shape[0], 1), float(b)), cls[:, None], boxes), 1))
+        labels.append(labels[-1][:5] + torch.tensor([0, 0, 3.0, -2.0, 4.0, 1.0]))  # near-duplicate labels
+    labels = torch.cat(labels)
+    correct = y.engine.match_predictions(dets, counts, labels).cpu().bool()
+    total = 0
+    for b in range(4):
+        n = int(counts[b])
+        lb = labels[labels[:, 0] == b]
+        rows = dets[b, :n].cpu()
+        exp = oval.match_predictions(rows[:, 5], lb[:, 1], oval.box_iou(lb[:, 2:], rows[:, :4]))
+        assert torch.equal(correct[b, :n], exp), b
+        assert not correct[b, n:].any()
+        total += int(exp.sum())
+    assert total > 100

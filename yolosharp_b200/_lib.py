@@ -46,6 +46,8 @@ SIGNATURES = {
     "yb_expected_tensor_name": (c_cp, [c_vp, c_i32]),
     "yb_forward": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "yb_nms": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "yb_box_iou": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp]),
+    "yb_match_predictions": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
     "yb_masks": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "yb_detection_loss": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_f32, c_f32, c_f32,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

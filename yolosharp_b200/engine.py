@@ -206,6 +206,32 @@ def masks(proto, dets, counts, height, width, stream=None, out=None):
     return out
 
 
+def box_iou(box1, box2, eps=1e-7, stream=None):
+    """yb_box_iou: (n,4), (m,4) xyxy CUDA float32 -> (n,m)."""
+    assert box1.is_cuda and box2.is_cuda and box1.dtype == torch.float32 and box2.dtype == torch.float32
+    box1, box2 = box1.contiguous(), box2.contiguous()
+    out = torch.empty((box1.shape[0], box2.shape[0]), dtype=torch.float32, device=box1.device)
+    L.check(L.lib().yb_box_iou(C.c_void_p(box1.data_ptr()), box1.shape[0], C.c_void_p(box2.data_ptr()), box2.shape[0], eps,
+                               C.c_void_p(out.data_ptr()), _stream_ptr(stream)))
+    return out
+
+
+def match_predictions(dets, counts, labels, iouv=None, stream=None):
+    """yb_match_predictions: dets (B,max_det,W) / counts (B) from nms(), labels (M,6) [image, cls, x1,y1,x2,y2]
+    -> uint8 (B, max_det, 10) true-positive matrix (rows >= counts[b] are 0)."""
+    assert dets.is_cuda and dets.dtype == torch.float32 and dets.is_contiguous() and counts.dtype == torch.int32
+    B, max_det, W = dets.shape
+    if iouv is None:
+        iouv = torch.linspace(0.5, 0.95, 10, dtype=torch.float32)
+    iouv = iouv.float().cpu().contiguous()
+    labels = torch.as_tensor(labels, dtype=torch.float32).reshape(-1, 6).to(dets.device).contiguous()
+    correct = torch.empty((B, max_det, iouv.numel()), dtype=torch.uint8, device=dets.device)
+    L.check(L.lib().yb_match_predictions(C.c_void_p(dets.data_ptr()), C.c_void_p(counts.data_ptr()), B, max_det, W,
+                                         C.c_void_p(labels.data_ptr()) if labels.numel() else None, labels.shape[0],
+                                         C.c_void_p(iouv.data_ptr()), iouv.numel(), C.c_void_p(correct.data_ptr()), _stream_ptr(stream)))
+    return correct
+
+
 def detection_loss(boxes, scores, targets, height, width, reg_max=16, topk=10, hyp_box=7.5, hyp_cls=0.5, hyp_dfl=1.5,
                    want_grad=True, stream=None):
     """yb_detection_loss: v8DetectionLoss (Utils/Loss.cs:328-485) on the raw train-mode head outputs.
