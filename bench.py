@@ -43,6 +43,7 @@ MODELS = {"v8n": ("v8", "n", "detect", 8.743), "v8s": ("v8", "s", "detect", 28.6
           "v8n-seg": ("v8", "n", "segment", 12.6), "v8s-seg": ("v8", "s", "segment", 40.085)}
 CONF, IOU, MAX_DET = 0.25, 0.45, 300
 E2E_SLOTS = 3  # batches in flight through yb_predict_u8_submit/_wait
+MASK_CAP = 32  # segment e2e: instance masks returned per image (byte planes of 640x640)
 # compulsory bytes per image, fp16 input + fp32 prediction tensor
 COMPULSORY_MB_IMG = {"detect": 3.87, "segment": 6.0}
 
@@ -482,21 +483,26 @@ def main():
     # ---- e2e: host uint8 images -> host detections through the pipelined C-ABI call pair
     #      yb_predict_u8_submit / yb_predict_u8_wait (two slots: H2D+forward+NMS[+gather]+D2H of step i+1 overlap step i) ----
     e2e_val, e2e_steps, d2h = None, 0, 0
-    if not seg:
+    if not (seg and world > 1):
         NS = E2E_SLOTS
         torch.set_num_threads(1)  # the serving loop is ctypes calls only; idle intra-op workers cost it 15 % (profiles/r2_exp_e2e_matrix.txt)
         host["omp_threads_e2e"] = 1
         u8 = [synth_image(B, 640, 640, seed=200 + rank * 8 + i, dtype=torch.uint8).pin_memory() for i in range(NS)]
         GB = world * B if world > 1 else B
-        dh = [torch.empty((GB, MAX_DET, 6), dtype=torch.float32).pin_memory() for _ in range(NS)]
+        dh = [torch.empty((GB, MAX_DET, ROW), dtype=torch.float32).pin_memory() for _ in range(NS)]
         ch = [torch.empty((GB,), dtype=torch.int32).pin_memory() for _ in range(NS)]
-        d2h = GB * MAX_DET * 6 * 4 + GB * 4
+        d2h = GB * MAX_DET * ROW * 4 + GB * 4
+        if seg:  # Segmenter.ImagePredict path: masks of the first MASK_CAP detections of every image come back as bytes
+            mhost = [torch.empty((B, MASK_CAP, 640, 640), dtype=torch.uint8).pin_memory() for _ in range(NS)]
+            d2h += B * MASK_CAP * 640 * 640
         e2e_steps = max(3 * NS, args.steps // 2)
 
         def submit(i):
             k = i % NS
             if world > 1:
                 gatherer.predict_submit(eng, k, u8[k], dh[k], ch[k], CONF, IOU)
+            elif seg:
+                eng.predict_seg_u8_submit(k, u8[k], dh[k], ch[k], mhost[k], CONF, IOU, MAX_DET)
             else:
                 eng.predict_u8_submit(k, u8[k], dh[k], ch[k], CONF, IOU, MAX_DET)
 
@@ -589,7 +595,8 @@ def main():
                        "gather": (gatherer.describe() if gatherer else None)},
             "e2e": {"value": round(e2e_val, 1) if e2e_val else None, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 640 * 640,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": f"yb_predict_u8_submit/_wait, {E2E_SLOTS} slots (pinned host uint8 in, host detections out)" +
+                    "api": (f"yb_predict_seg_u8_submit/_wait, {E2E_SLOTS} slots (pinned host uint8 in; detections + {MASK_CAP} byte masks per image out)" if seg else
+                            f"yb_predict_u8_submit/_wait, {E2E_SLOTS} slots (pinned host uint8 in, host detections out)") +
                            (", detections of all ranks gathered before the D2H copy" if world > 1 else "")},
             "gpu_launches": (eng.launches_per_forward() + 2 + (1 if seg else 0) + (3 if world > 1 else 0)) * args.steps,
             "launches_per_step": eng.launches_per_forward() + 2 + (1 if seg else 0) + (3 if world > 1 else 0),

@@ -133,6 +133,14 @@ const char* yb_expected_tensor_name(const yb_engine* e, int32_t i);
 int32_t yb_forward(yb_engine* e, const void* in, int32_t in_dtype, int32_t batch,
                    float* out_pred, float* out_proto, void* stream);
 
+/* yb_forward on images that are NOT yet padded to the planned size: `in` is (B,3,src_height,src_width) contiguous with
+ * src <= the engine's height / width, and the right / bottom padding with the value 114 that `Detector.ImagePredict`
+ * applies before the /255 (Models/Detector.cs:35-41: pad to a multiple of 32) is produced inside the first kernel
+ * (the stem's loads) instead of by a separate pad pass.  Float inputs must already be scaled to [0,1] (the padded
+ * pixels are 114/255). */
+int32_t yb_forward_padded(yb_engine* e, const void* in, int32_t in_dtype, int32_t batch, int32_t src_height, int32_t src_width,
+                          float* out_pred, float* out_proto, void* stream);
+
 /* Replaces: `Ops.non_max_suppression(prediction, conf_thres, iou_thres, .., max_det, nc, ..,
  * max_nms, max_wh)` (Utils/Ops.cs:239-371), non-rotated, non-end2end path, incl. the
  * torchvision.ops.nms call at :357.
@@ -243,6 +251,16 @@ int32_t yb_predict_u8_submit(yb_engine* e, int32_t slot, const uint8_t* images_h
                              float conf_thres, float iou_thres, int32_t max_det, float* dets_host,
                              int32_t* counts_host);
 int32_t yb_predict_u8_wait(yb_engine* e, int32_t slot);
+
+/* Replaces: the body of `Segmenter.ImagePredict` (Models/Segmenter.cs:28-84) for a batch of equally sized images on a
+ * segment engine: as yb_predict_u8_submit, plus the instance masks of the first `mask_cap` kept detections of every
+ * image (score order) - `Ops.process_mask(.., upsample: true)` - copied to the host.
+ *   dets_host   float32 (B, max_det, 38);  counts_host int32 (B)
+ *   masks_host  uint8 (B, mask_cap, H, W), 1 where mask > 0; planes >= min(counts[b], mask_cap) are not written
+ * Wait with yb_predict_u8_wait(slot). */
+int32_t yb_predict_seg_u8_submit(yb_engine* e, int32_t slot, const uint8_t* images_host, int32_t batch, float conf_thres,
+                                 float iou_thres, int32_t max_det, int32_t mask_cap, float* dets_host, int32_t* counts_host,
+                                 uint8_t* masks_host);
 
 /* Validation-side post-processing (csrc/val.cu), batched over the images of a step.
  * yb_box_iou  replaces `Metrics.box_iou(box1, box2)` (Utils/Metrics.cs:16-34): out (n, m) float32, xyxy boxes.

@@ -348,3 +348,27 @@ def test_box_iou_and_match_predictions_vs_oracle(y):
         assert not correct[b, n:].any()
         total += int(exp.sum())
     assert total > 100
+
+
+def test_predict_seg_u8_end_to_end(y):
+    """yb_predict_seg_u8_submit / _wait (Segmenter.ImagePredict for a batch): host uint8 images in, rows + the first
+    mask_cap byte masks per image out == forward + nms + masks called one by one."""
+    m = oracle_model("v8", "segment", "n")
+    B, H, W, CAP = 2, 160, 192, 16
+    e = make_engine(y, m, "f32", B, H, W, task="segment")
+    u8 = synth_image(B, H, W, dtype=torch.uint8)
+    pred, proto = e.forward(u8.cuda())
+    dets, counts, _ = y.nms(pred, 0.25, 0.45, 300, 80)
+    ref_masks = y.masks(proto, dets, counts, H, W)
+    dh = torch.empty((B, 300, 38), dtype=torch.float32).pin_memory()
+    ch = torch.empty((B,), dtype=torch.int32).pin_memory()
+    mh = torch.zeros((B, CAP, H, W), dtype=torch.uint8).pin_memory()
+    for slot in (0, 3):
+        e.predict_seg_u8_submit(slot, u8.pin_memory(), dh, ch, mh, 0.25, 0.45, 300)
+        e.predict_u8_wait(slot)
+        assert torch.equal(ch, counts.cpu()) and torch.equal(dh, dets.cpu())
+        for b in range(B):
+            n = min(int(counts[b]), CAP)
+            assert n > 0 and torch.equal(mh[b, :n], ref_masks[b, :n].cpu())
+    with pytest.raises(y.YbError):  # detect entry point on a segment engine
+        e.predict_u8_submit(0, u8.pin_memory(), dh, ch, 0.25, 0.45, 300)

@@ -45,6 +45,7 @@ SIGNATURES = {
     "yb_num_expected_tensors": (c_i32, [c_vp]),
     "yb_expected_tensor_name": (c_cp, [c_vp, c_i32]),
     "yb_forward": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "yb_forward_padded": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "yb_nms": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "yb_box_iou": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp]),
     "yb_match_predictions": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
@@ -66,6 +67,7 @@ SIGNATURES = {
     "yb_predict_u8": (c_i32, [c_vp, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp, c_vp]),
     "yb_predict_u8_submit": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp]),
     "yb_predict_u8_wait": (c_i32, [c_vp, c_i32]),
+    "yb_predict_seg_u8_submit": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_f32, c_f32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "yb_predict_u8_submit_gather": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_i32, c_f32, c_f32, c_i32, c_vp, c_vp]),
     "yb_comm_handle_bytes": (c_i32, []),
     "yb_comm_create": (c_i32, [c_i32, c_i32, c_i32, C.c_int64, c_i32, C.POINTER(c_vp)]),

@@ -121,9 +121,11 @@ class _YoloModule:
             self._engines[key] = e
         return e
 
-    def forward(self, x):
+    def forward(self, x, padded_hw=None):
         """Models/Yolo.cs:92-134 in eval mode: returns (inference, preds) with
-        inference["boxes"] (B, 4+nc[+32], A) float32 [+ inference["proto"] (B,32,H/4,W/4)]."""
+        inference["boxes"] (B, 4+nc[+32], A) float32 [+ inference["proto"] (B,32,H/4,W/4)].
+        padded_hw: run on the input padded right / bottom with 114 to this size (Detector.cs:35-41) without
+        materialising the padded tensor."""
         if self.training:
             raise NotImplementedError("train-mode forward")
         if x.dim() != 4 or x.shape[1] != 3:
@@ -134,6 +136,8 @@ class _YoloModule:
             x = x.float()
         x = x.contiguous()
         B, _, H, W = x.shape
+        if padded_hw is not None:
+            H, W = padded_hw
         e = self._engine(H, W, B)
         if self.task == "segment":
             pred, proto = e.forward(x)
@@ -227,12 +231,11 @@ class Detector:
         img = orgImage.to(torch.device("cuda", self.config.DeviceIndex))
         if img.dtype != torch.uint8:
             raise ValueError("ImagePredict expects a uint8 (3,H,W) image tensor")
-        x = img.unsqueeze(0)
+        x = img.unsqueeze(0).contiguous()
         h, w = x.shape[2], x.shape[3]
         ph, pw = (32 - h % 32) % 32, (32 - w % 32) % 32
-        if ph or pw:
-            x = torch.nn.functional.pad(x, (0, pw, 0, ph), mode="constant", value=114)
-        inference, _ = self.yolo.eval().forward(x)  # u8 input: the /255 is fused into the first kernel
+        # u8 input: the pad-114 to a multiple of 32 and the /255 are both fused into the first kernel's loads
+        inference, _ = self.yolo.eval().forward(x, padded_hw=(h + ph, w + pw))
         out, _ = Ops.non_max_suppression(inference["boxes"], conf, iou)
         return _to_results(out[0].cpu())
 
@@ -257,18 +260,17 @@ class Segmenter(Detector):
         img = orgImage.to(torch.device("cuda", self.config.DeviceIndex))
         if img.dtype != torch.uint8:
             raise ValueError("ImagePredict expects a uint8 (3,H,W) image tensor")
-        x = img.unsqueeze(0)
+        x = img.unsqueeze(0).contiguous()
         h, w = x.shape[2], x.shape[3]
         ph, pw = (32 - h % 32) % 32, (32 - w % 32) % 32
-        if ph or pw:
-            x = torch.nn.functional.pad(x, (0, pw, 0, ph), mode="constant", value=114)
-        inference, _ = self.yolo.eval().forward(x)
+        inference, _ = self.yolo.eval().forward(x, padded_hw=(h + ph, w + pw))
         pred, proto = inference["boxes"], inference["proto"]
+        Hp, Wp = h + ph, w + pw  # masks cover the padded input (Segmenter.cs:54)
         dets, counts, _ = _nms(pred, conf, iou, 300, self.config.NumberClass)
         n = int(counts[0].item())
         if n == 0:
             return []
-        masks = _masks(proto, dets, counts, x.shape[2], x.shape[3])[0, :n]
+        masks = _masks(proto, dets, counts, Hp, Wp)[0, :n]
         rows = dets[0, :n].clone()
         rows[:, [0, 2]] = rows[:, [0, 2]].clamp(0, w)   # clip_boxes: x to [0, width], y to [0, height]
         rows[:, [1, 3]] = rows[:, [1, 3]].clamp(0, h)

@@ -72,7 +72,7 @@ template <typename T>
 int launch_upsample2x(const View& in, const View& out, int B, cudaStream_t s);
 // network input (B,3,H,W) NCHW of dtype u8/f16/f32 -> NHWC T with pitch/coff from `out`
 template <typename T>
-int launch_input_to_nhwc(const void* in, int in_dtype, const View& out, int B, cudaStream_t s);
+int launch_input_to_nhwc(const void* in, int in_dtype, const View& out, int B, cudaStream_t s, int src_H = 0, int src_W = 0);
 // read back a view as NCHW fp32 (debug)
 template <typename T>
 int launch_view_to_nchw_f32(const View& in, float* out, int B, cudaStream_t s);
@@ -99,6 +99,7 @@ int launch_proto_out(const View& in, float* out, int B, cudaStream_t s);
 struct TcConvPlan;  // opaque: tensor maps + tiling for one conv layer
 TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err);
 void tc_conv_plan_destroy(TcConvPlan* plan);
+std::string tc_conv_plan_describe(const TcConvPlan* plan);  // tiling summary (YB_DEBUG_PLANS)
 // Cross-layer overlap (DESIGN 4.1 "layer chaining"): instead of waiting for the whole previous grid
 // (griddepcontrol.wait) a conv may start a tile as soon as the images it reads are complete in its producer.
 //   done_ctr   this launch's per-image completion counters (rows x N tiles stored), or nullptr
@@ -114,7 +115,7 @@ int tc_conv_rows_per_image(const TcConvPlan* plan);  // rows x N tiles one image
 bool tc_conv_supported(const ConvParams& p);
 // stem: NCHW u8/f16/f32 input -> 3x3 s2 conv (Cin=3) + bias + SiLU -> NHWC fp16
 int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const __half* w16 /*[Cout][32]*/,
-                    const float* bias, const View& out, cudaStream_t s);
+                    const float* bias, const View& out, cudaStream_t s, int src_H = 0, int src_W = 0);  // src_*: unpadded source size
 
 // ---- nms.cu ----
 int nms_launch(const float* pred, int B, int C, int A, int nc, float conf, float iou, int max_det,
@@ -136,6 +137,6 @@ int conv_backward_data(const float* dz, const float* w, int N, int H, int W, int
 int conv_backward_weight(const float* x, const float* dz, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                          float* dw, cudaStream_t s);
 int masks_launch(const float* proto, const float* dets, const int* counts, int B, int max_det, int nm,
-                 int mh, int mw, int H, int W, uint8_t* masks, cudaStream_t s);
+                 int mh, int mw, int H, int W, uint8_t* masks, cudaStream_t s, int mask_cap = 0);  // mask_cap: masks per image (0 = max_det)
 
 }  // namespace yb

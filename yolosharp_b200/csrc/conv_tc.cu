@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -1117,6 +1118,15 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
   return plan;
 }
 
+std::string tc_conv_plan_describe(const TcConvPlan* plan) {
+  const TcArgs& a = plan->args;
+  char buf[256];
+  snprintf(buf, sizeof(buf), "mode %d BK %d chunks %d n_tile %d x%d stages a/b %d/%d resident %d dual %d issuers %d groups %d acc %d occ %d "
+           "threads %d smem %zu KiB grid %d", a.mode, a.BK, a.chunks, a.n_tile, a.n_tiles, a.stages_a, a.stages_b, a.b_resident, a.dual,
+           a.n_issuers, a.n_groups, a.n_acc, plan->occ, plan->threads, plan->smem / 1024, plan->grid);
+  return buf;
+}
+
 void tc_conv_plan_destroy(TcConvPlan* plan) {
   if (plan && plan->wpk) cudaFree(plan->wpk);
   delete plan;
@@ -1214,6 +1224,11 @@ struct StemArgs {
   __half* out;
   int out_pitch, out_coff;
   int B, H, W, Ho, Wo, Cout;
+  // Detector.ImagePredict pads the image right / bottom to a multiple of 32 with the value 114 before the /255
+  // (Models/Detector.cs:35-41): the caller's tensor is (B, 3, src_H, src_W) with src <= H, W and the padding is
+  // produced here instead of by a separate pad kernel.  pad_h2 = the padded pixel as two fp16 (already scaled).
+  int src_H, src_W;
+  uint32_t pad_h2;
   int tiles_w, tiles_h, total_tiles;
   uint32_t tmem_cols;
   uint64_t m_tpi, m_tw;  // magic numbers for / tiles_per_img and / tiles_w (fdiv)
@@ -1252,6 +1267,34 @@ __device__ __forceinline__ uint2 stem_load4(const void* in, size_t rowbase, int 
     r.y = pack_h2(v.x, v.y);
   }
   return r;
+}
+
+// one input element as fp16 bits (same arithmetic as stem_load4)
+template <int DT>
+__device__ __forceinline__ uint32_t stem_load1(const void* in, size_t i) {
+  if (DT == YB_F16) return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(in) + i);
+  if (DT == YB_U8) {
+    const __half k = __float2half_rn(1.0f / 255.0f);
+    const uint32_t x = 0x6400u | (uint32_t)__ldg(reinterpret_cast<const uint8_t*>(in) + i);
+    const unsigned short xs = (unsigned short)x;
+    const __half h = __hfma(*reinterpret_cast<const __half*>(&xs), k, __hmul(k, __float2half_rn(-1024.0f)));
+    return (uint32_t)*reinterpret_cast<const unsigned short*>(&h);
+  }
+  const __half h = __float2half_rn(__ldg(reinterpret_cast<const float*>(in) + i));
+  return (uint32_t)*reinterpret_cast<const unsigned short*>(&h);
+}
+
+// four columns col .. col+3 of a SOURCE row that may end before them (ragged width / odd row alignment): columns
+// < 0 are the conv's zero padding, columns >= src_W the 114-padding of the image
+template <int DT>
+__device__ __forceinline__ uint2 stem_load4_ragged(const void* in, size_t rowbase, int col, int src_W, uint32_t pad1) {
+  uint32_t e[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int c = col + j;
+    e[j] = c < 0 ? 0u : (c >= src_W ? pad1 : stem_load1<DT>(in, rowbase + c));
+  }
+  return make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
 }
 
 template <int DT>
@@ -1310,7 +1353,9 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_con
     }
   } else {
     const int tx = tid & (ST_TW - 1), ty = tid / ST_TW;  // output pixel inside the tile
-    const size_t plane = (size_t)a.H * a.W;
+    const size_t plane = (size_t)a.src_H * a.src_W;
+    const bool ragged = a.src_W != a.W || a.src_H != a.H;  // padded source: rows may be misaligned and end early
+    const uint32_t pad1 = a.pad_h2 & 0xffffu;
     auto gather = [&](int tile, uint2 (&v)[9]) {
       const int n = fdiv(tile, a.m_tpi), r = tile - n * tiles_per_img;
       const int th = fdiv(r, a.m_tw);
@@ -1321,10 +1366,18 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_con
       for (int kh = 0; kh < 3; kh++) {
         const int hi_ = ho * 2 + kh - 1;
         const bool row_ok = pix_ok && hi_ >= 0 && hi_ < a.H;
-        const size_t rowbase = (size_t)n * 3 * plane + (size_t)(row_ok ? hi_ : 0) * a.W;
+        const bool in_src = hi_ < a.src_H;
+        const size_t rowbase = (size_t)n * 3 * plane + (size_t)((row_ok && in_src) ? hi_ : 0) * a.src_W;
 #pragma unroll
-        for (int c = 0; c < 3; c++)
-          v[kh * 3 + c] = row_ok ? stem_load4<DT>(a.in, rowbase + c * plane, col, wo > 0) : make_uint2(0u, 0u);
+        for (int c = 0; c < 3; c++) {
+          uint2 g = make_uint2(0u, 0u);
+          if (row_ok) {
+            if (!ragged) g = stem_load4<DT>(a.in, rowbase + c * plane, col, wo > 0);
+            else if (in_src) g = stem_load4_ragged<DT>(a.in, rowbase + c * plane, col, a.src_W, pad1);
+            else g = make_uint2(wo > 0 ? a.pad_h2 : 0u, a.pad_h2);  // a row of the bottom padding
+          }
+          v[kh * 3 + c] = g;
+        }
       }
     };
     uint2 v[9];
@@ -1379,7 +1432,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4) stem_tc_kernel(const __grid_con
 }
 
 int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const __half* w16, const float* bias,
-                    const View& out, cudaStream_t s) {
+                    const View& out, cudaStream_t s, int src_H, int src_W) {
   if (out.C % 16 || out.C > 256 || out.coff % 8 || out.pitch % 8 || (W & 1) || (H & 1)) {
     set_error("stem: output channels must be a multiple of 16 and <= 256, input height/width even");
     return YB_ERR_SHAPE;
@@ -1390,6 +1443,16 @@ int launch_stem_f16(const void* in, int in_dtype, int B, int H, int W, const __h
   a.out = reinterpret_cast<__half*>(out.base);
   a.out_pitch = out.pitch; a.out_coff = out.coff;
   a.B = B; a.H = H; a.W = W; a.Ho = H / 2; a.Wo = W / 2; a.Cout = out.C;
+  a.src_H = src_H > 0 ? src_H : H; a.src_W = src_W > 0 ? src_W : W;
+  if (a.src_H > H || a.src_W > W) { set_error("stem: source image larger than the planned input"); return YB_ERR_SHAPE; }
+  {
+    // the padded pixel: u8 input -> half(114 * half(1/255)) exactly as a loaded 114 would come out; float inputs are
+    // already scaled by the caller (pad(x, 114) / 255, Detector.cs:41) -> half(114 / 255)
+    const __half k = __float2half_rn(1.0f / 255.0f);
+    const __half pv = in_dtype == YB_U8 ? __float2half_rn(114.0f * __half2float(k)) : __float2half_rn(114.0f / 255.0f);
+    const unsigned short bits = *reinterpret_cast<const unsigned short*>(&pv);
+    a.pad_h2 = (uint32_t)bits | ((uint32_t)bits << 16);
+  }
   a.tiles_w = (a.Wo + ST_TW - 1) / ST_TW;
   a.tiles_h = (a.Ho + ST_TH - 1) / ST_TH;
   a.total_tiles = B * a.tiles_w * a.tiles_h;

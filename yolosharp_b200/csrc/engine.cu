@@ -14,6 +14,7 @@
 #include <memory>
 #include <vector>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <tuple>
@@ -90,6 +91,7 @@ struct yb_engine {
   int* tile_ctr = nullptr;  // one dynamic-scheduler counter per op, zeroed at the start of every forward
   int* done_ctr = nullptr;  // layer chaining: [op][image] rows stored (same allocation as tile_ctr, zeroed with it)
   int chain = 0;  // 0 off, 1 chained, 2 publish counters only (experiments)
+  int src_h = 0, src_w = 0;  // size of the caller's (unpadded) images for the forward being enqueued (yb_forward_padded)
   bool finalized = false;
   int esize = 4;  // bytes per activation element
   int A = 0, pred_c = 0;
@@ -105,6 +107,9 @@ struct yb_engine {
     float* dets = nullptr;
     int* counts = nullptr;
     int max_det = 0;
+    float* proto = nullptr;    // segment engines
+    uint8_t* masks = nullptr;  // (max_batch, mask_cap, H, W)
+    int mask_cap = 0;
     cudaStream_t stream = nullptr;
   };
   static const int kSlots = 4;
@@ -113,9 +118,9 @@ struct yb_engine {
   bool arena_used = false;
   // CUDA graph cache
   struct GraphKey {
-    const void* in; int dtype; int B; float* pred; float* proto;
+    const void* in; int dtype; int B; float* pred; float* proto; int src_h, src_w;
     bool operator<(const GraphKey& o) const {
-      return std::tie(in, dtype, B, pred, proto) < std::tie(o.in, o.dtype, o.B, o.pred, o.proto);
+      return std::tie(in, dtype, B, pred, proto, src_h, src_w) < std::tie(o.in, o.dtype, o.B, o.pred, o.proto, o.src_h, o.src_w);
     }
   };
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -711,13 +716,13 @@ static int run_ops(yb_engine* e, const void* in, int in_dtype, int B, float* out
       case OP_CONV: {
         if (i == 0 && e->has_stem_tc) {
           rc = launch_stem_f16(in, in_dtype, B, e->cfg.height, e->cfg.width, op.w_f16, op.bias,
-                               make_view(e, op.out), s);
+                               make_view(e, op.out), s, e->src_h, e->src_w);
           if (rc) return rc;
           input_converted = true;  // the stem reads the caller's NCHW tensor directly
           break;
         }
         if (!input_converted) {
-          rc = launch_input_to_nhwc<T>(in, in_dtype, make_view(e, e->input_nhwc), B, s);
+          rc = launch_input_to_nhwc<T>(in, in_dtype, make_view(e, e->input_nhwc), B, s, e->src_h, e->src_w);
           if (rc) return rc;
           input_converted = true;
         }
@@ -889,6 +894,8 @@ void yb_destroy(yb_engine* e) {
     if (st.pred) cudaFree(st.pred);
     if (st.dets) cudaFree(st.dets);
     if (st.counts) cudaFree(st.counts);
+    if (st.proto) cudaFree(st.proto);
+    if (st.masks) cudaFree(st.masks);
     if (st.stream) cudaStreamDestroy(st.stream);
   }
   if (e->arena_free) cudaEventDestroy(e->arena_free);
@@ -1003,6 +1010,8 @@ int32_t yb_finalize_weights(yb_engine* e) {
         op.plan = tc_conv_plan_create(p, &err);
         if (!op.plan) { set_error("tcgen05 plan failed for " + op.name + ": " + err); return YB_ERR_CUDA; }
         op.use_tc = true;
+        if (getenv("YB_DEBUG_PLANS")) fprintf(stderr, "[plan] %-30s k%d s%d %4d->%4d @%dx%d  %s\n", op.name.c_str(), op.k, op.s, op.cin, op.cout,
+                                              p.Ho, p.Wo, tc_conv_plan_describe(op.plan).c_str());
       }
     }
   }
@@ -1048,7 +1057,18 @@ int32_t yb_finalize_weights(yb_engine* e) {
 
 int32_t yb_forward(yb_engine* e, const void* in, int32_t in_dtype, int32_t batch, float* out_pred,
                    float* out_proto, void* stream) {
+  if (!e) { set_error("yb_forward: null argument"); return YB_ERR_INVALID_ARG; }
+  return yb_forward_padded(e, in, in_dtype, batch, e->cfg.height, e->cfg.width, out_pred, out_proto, stream);
+}
+
+int32_t yb_forward_padded(yb_engine* e, const void* in, int32_t in_dtype, int32_t batch, int32_t src_height, int32_t src_width,
+                          float* out_pred, float* out_proto, void* stream) {
   if (!e || !in || !out_pred) { set_error("yb_forward: null argument"); return YB_ERR_INVALID_ARG; }
+  if (src_height <= 0 || src_width <= 0 || src_height > e->cfg.height || src_width > e->cfg.width) {
+    set_error("yb_forward_padded: source size must be within the planned input size");
+    return YB_ERR_INVALID_ARG;
+  }
+  e->src_h = src_height; e->src_w = src_width;
   if (!e->finalized) { set_error("yb_forward: call yb_finalize_weights first"); return YB_ERR_STATE; }
   if (batch <= 0 || batch > e->cfg.max_batch) { set_error("yb_forward: batch outside [1, max_batch]"); return YB_ERR_INVALID_ARG; }
   if (in_dtype != YB_U8 && in_dtype != YB_F16 && in_dtype != YB_F32) { set_error("yb_forward: in_dtype must be u8/f16/f32"); return YB_ERR_INVALID_ARG; }
@@ -1061,7 +1081,7 @@ int32_t yb_forward(yb_engine* e, const void* in, int32_t in_dtype, int32_t batch
                : run_ops<float>(e, in, in_dtype, batch, out_pred, out_proto, st);
   };
   if (e->cfg.flags & YB_FLAG_NO_GRAPH) return run(s);
-  yb_engine::GraphKey key{in, in_dtype, batch, out_pred, out_proto};
+  yb_engine::GraphKey key{in, in_dtype, batch, out_pred, out_proto, src_height, src_width};
   auto it = e->graphs.find(key);
   if (it != e->graphs.end()) {
     YB_CUDA_CHECK(cudaGraphLaunch(it->second, s));
@@ -1215,11 +1235,13 @@ int32_t yb_conv_backward_weight(const float* x, const float* dz, int32_t n, int3
 static int32_t predict_enqueue(yb_engine* e, yb_engine::Stage& st, const uint8_t* images_host, int32_t batch,
                                float conf_thres, float iou_thres, int32_t max_det, float* dets_host,
                                int32_t* counts_host, cudaStream_t s, const char* who, yb_comm* comm = nullptr,
-                               int comm_slot = 0) {
+                               int comm_slot = 0, uint8_t* masks_host = nullptr, int32_t mask_cap = 0) {
   if (!e || !images_host || !dets_host || !counts_host) { set_error(std::string(who) + ": null argument"); return YB_ERR_INVALID_ARG; }
   if (!e->finalized) { set_error(std::string(who) + ": call yb_finalize_weights first"); return YB_ERR_STATE; }
   if (batch <= 0 || batch > e->cfg.max_batch) { set_error(std::string(who) + ": batch outside [1, max_batch]"); return YB_ERR_INVALID_ARG; }
-  if (e->cfg.task != YB_TASK_DETECT) { set_error(std::string(who) + ": detect engines only"); return YB_ERR_NOT_IMPLEMENTED; }
+  const bool seg = e->cfg.task == YB_TASK_SEGMENT;
+  if (seg != (masks_host != nullptr)) { set_error(std::string(who) + (seg ? ": segment engines go through yb_predict_seg_u8_submit" : ": masks requested from a detect engine")); return YB_ERR_INVALID_ARG; }
+  if (seg && (comm || mask_cap <= 0 || mask_cap > max_det)) { set_error(std::string(who) + ": need 0 < mask_cap <= max_det (and no exchange) for segment engines"); return YB_ERR_INVALID_ARG; }
   if (max_det <= 0 || max_det > 1024) { set_error(std::string(who) + ": max_det outside [1,1024]"); return YB_ERR_INVALID_ARG; }
   YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
   const size_t img_bytes = (size_t)3 * e->cfg.height * e->cfg.width;
@@ -1240,7 +1262,17 @@ static int32_t predict_enqueue(yb_engine* e, yb_engine::Stage& st, const uint8_t
   // copies, NMS and D2H copies still overlap the other slot's forward)
   if (!e->arena_free) YB_CUDA_CHECK(cudaEventCreateWithFlags(&e->arena_free, cudaEventDisableTiming));
   if (e->arena_used) YB_CUDA_CHECK(cudaStreamWaitEvent(s, e->arena_free, 0));
-  int rc = yb_forward(e, st.in, YB_U8, batch, st.pred, nullptr, (void*)s);
+  const int mh = e->cfg.height / 4, mw = e->cfg.width / 4;
+  if (seg) {
+    if (!st.proto) YB_CUDA_CHECK(cudaMalloc((void**)&st.proto, (size_t)e->cfg.max_batch * 32 * mh * mw * sizeof(float)));
+    if (st.mask_cap < mask_cap) {
+      if (st.masks) cudaFree(st.masks);
+      st.masks = nullptr;
+      YB_CUDA_CHECK(cudaMalloc((void**)&st.masks, (size_t)e->cfg.max_batch * mask_cap * e->cfg.height * e->cfg.width));
+      st.mask_cap = mask_cap;
+    }
+  }
+  int rc = yb_forward(e, st.in, YB_U8, batch, st.pred, seg ? st.proto : nullptr, (void*)s);
   if (rc) return rc;
   YB_CUDA_CHECK(cudaEventRecord(e->arena_free, s));
   e->arena_used = true;
@@ -1276,6 +1308,13 @@ static int32_t predict_enqueue(yb_engine* e, yb_engine::Stage& st, const uint8_t
   YB_CUDA_CHECK(cudaMemcpyAsync(dets_host, st.dets, (size_t)batch * max_det * row_w * sizeof(float),
                                 cudaMemcpyDeviceToHost, s));
   YB_CUDA_CHECK(cudaMemcpyAsync(counts_host, st.counts, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (seg) {
+    // Segmenter.cs:54: process_mask(upsample: true) of the kept rows; masks beyond an image's count are left untouched
+    rc = masks_launch(st.proto, st.dets, st.counts, batch, max_det, 32, mh, mw, e->cfg.height, e->cfg.width, st.masks, s, mask_cap);
+    if (rc) return rc;
+    YB_CUDA_CHECK(cudaMemcpyAsync(masks_host, st.masks, (size_t)batch * mask_cap * e->cfg.height * e->cfg.width,
+                                  cudaMemcpyDeviceToHost, s));
+  }
   return YB_OK;
 }
 
@@ -1312,6 +1351,19 @@ int32_t yb_predict_u8_submit_gather(yb_engine* e, yb_comm* comm, int32_t slot, c
   }
   return predict_enqueue(e, st, images_host, batch, conf_thres, iou_thres, max_det, all_dets_host, all_counts_host,
                          st.stream, "yb_predict_u8_submit_gather", comm, slot);
+}
+
+int32_t yb_predict_seg_u8_submit(yb_engine* e, int32_t slot, const uint8_t* images_host, int32_t batch, float conf_thres,
+                                 float iou_thres, int32_t max_det, int32_t mask_cap, float* dets_host, int32_t* counts_host,
+                                 uint8_t* masks_host) {
+  if (!e || !masks_host || slot < 0 || slot >= yb_engine::kSlots) { set_error("yb_predict_seg_u8_submit: bad engine / masks / slot (0..3)"); return YB_ERR_INVALID_ARG; }
+  yb_engine::Stage& st = e->stage[1 + slot];
+  if (!st.stream) {
+    YB_CUDA_CHECK(cudaSetDevice(e->cfg.device));
+    YB_CUDA_CHECK(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+  }
+  return predict_enqueue(e, st, images_host, batch, conf_thres, iou_thres, max_det, dets_host, counts_host, st.stream,
+                         "yb_predict_seg_u8_submit", nullptr, 0, masks_host, mask_cap);
 }
 
 int32_t yb_predict_u8_wait(yb_engine* e, int32_t slot) {

@@ -371,25 +371,31 @@ __device__ __forceinline__ float load_input(const void* in, int dtype, size_t i)
 }
 
 template <typename T>
-__global__ void input_to_nhwc_kernel(const void* in, int dtype, View out, size_t npix_total) {
+__global__ void input_to_nhwc_kernel(const void* in, int dtype, View out, size_t npix_total, int src_H, int src_W) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= npix_total) return;
-  const size_t HW = (size_t)out.H * out.W;
+  const size_t HW = (size_t)out.H * out.W, sHW = (size_t)src_H * src_W;
   const size_t n = idx / HW, pix = idx - n * HW;
+  const int y = (int)(pix / out.W), x = (int)(pix - (size_t)y * out.W);
   T* dst = reinterpret_cast<T*>(out.base) + idx * out.pitch + out.coff;
+  // right / bottom padding with 114 before the /255 (Detector.cs:35-41): pad(x, 114) / 255
+  const bool inside = y < src_H && x < src_W;
 #pragma unroll
-  for (int c = 0; c < 3; c++) dst[c] = from_f<T>(load_input(in, dtype, (n * 3 + c) * HW + pix));
+  for (int c = 0; c < 3; c++)
+    dst[c] = from_f<T>(inside ? load_input(in, dtype, (n * 3 + c) * sHW + (size_t)y * src_W + x) : __fdiv_rn(114.0f, 255.0f));
 }
 
 template <typename T>
-int launch_input_to_nhwc(const void* in, int in_dtype, const View& out, int B, cudaStream_t s) {
+int launch_input_to_nhwc(const void* in, int in_dtype, const View& out, int B, cudaStream_t s, int src_H, int src_W) {
   const size_t total = (size_t)B * out.H * out.W;
-  input_to_nhwc_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_dtype, out, total);
+  if (src_H <= 0) src_H = out.H;
+  if (src_W <= 0) src_W = out.W;
+  input_to_nhwc_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(in, in_dtype, out, total, src_H, src_W);
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
-template int launch_input_to_nhwc<float>(const void*, int, const View&, int, cudaStream_t);
-template int launch_input_to_nhwc<__half>(const void*, int, const View&, int, cudaStream_t);
+template int launch_input_to_nhwc<float>(const void*, int, const View&, int, cudaStream_t, int, int);
+template int launch_input_to_nhwc<__half>(const void*, int, const View&, int, cudaStream_t, int, int);
 
 template <typename T>
 __global__ void view_to_nchw_kernel(View in, float* out, size_t total) {

@@ -525,11 +525,11 @@ int nms_launch(const float* pred, int B, int C, int A, int nc, float conf, float
 // One block per (detection, output row tile): the needed low-res rows are produced on the fly.
 // ------------------------------------------------------------------------------------------
 __global__ void masks_kernel(const float* __restrict__ proto, const float* __restrict__ dets,
-                             const int* __restrict__ counts, int max_det, int nm, int mh, int mw, int H, int W,
+                             const int* __restrict__ counts, int max_det, int mask_cap, int nm, int mh, int mw, int H, int W,
                              uint8_t* __restrict__ masks) {
   extern __shared__ float mk_smem[];  // [mh*mw] cropped low-res mask of this detection
   const int det = blockIdx.x, b = blockIdx.y;
-  if (det >= counts[b]) return;
+  if (det >= counts[b]) return;  // grid.x = mask_cap: only the first mask_cap detections of an image get a mask
   const int row_w = 6 + nm;
   const float* d = dets + ((size_t)b * max_det + det) * row_w;
   const float* pr = proto + (size_t)b * nm * mh * mw;
@@ -556,7 +556,7 @@ __global__ void masks_kernel(const float* __restrict__ proto, const float* __res
   // ATen upsample_bilinear2d, align_corners=false: src = max(0, (dst + 0.5) * scale - 0.5),
   // scale = in/out
   const float sh = (float)mh / (float)H, sw = (float)mw / (float)W;
-  uint8_t* out = masks + ((size_t)b * max_det + det) * H * W;
+  uint8_t* out = masks + ((size_t)b * mask_cap + det) * H * W;
   // 4 consecutive pixels per thread -> one 32-bit store (the output, n x H x W bytes, is the HBM traffic)
   const int W4 = W >> 2;
   for (int i = threadIdx.x; i < H * W4; i += blockDim.x) {
@@ -591,7 +591,7 @@ __global__ void masks_kernel(const float* __restrict__ proto, const float* __res
 }
 
 int masks_launch(const float* proto, const float* dets, const int* counts, int B, int max_det, int nm,
-                 int mh, int mw, int H, int W, uint8_t* masks, cudaStream_t s) {
+                 int mh, int mw, int H, int W, uint8_t* masks, cudaStream_t s, int mask_cap) {
   const size_t smem = (size_t)mh * mw * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("yb_masks: proto map too large");
@@ -602,7 +602,8 @@ int masks_launch(const float* proto, const float* dets, const int* counts, int B
     YB_CUDA_CHECK(cudaFuncSetAttribute(masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  masks_kernel<<<dim3(max_det, B), 512, smem, s>>>(proto, dets, counts, max_det, nm, mh, mw, H, W, masks);
+  if (mask_cap <= 0 || mask_cap > max_det) mask_cap = max_det;
+  masks_kernel<<<dim3(mask_cap, B), 512, smem, s>>>(proto, dets, counts, max_det, mask_cap, nm, mh, mw, H, W, masks);
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -79,7 +79,7 @@ class Engine:
     def forward(self, x, out_pred=None, out_proto=None, stream=None):
         """x: CUDA (B,3,H,W) uint8 / float16 / float32 -> pred float32 (B, C, A) [, proto]."""
         assert x.is_cuda and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3
-        assert x.shape[2] == self.height and x.shape[3] == self.width, "engine was planned for another input size"
+        assert x.shape[2] <= self.height and x.shape[3] <= self.width, "engine was planned for a smaller input size"
         code = {torch.uint8: L.YB_U8, torch.float16: L.YB_F16, torch.float32: L.YB_F32}[x.dtype]
         B = x.shape[0]
         if out_pred is None:
@@ -89,8 +89,9 @@ class Engine:
             if out_proto is None:
                 out_proto = torch.empty((B, 32, self.height // 4, self.width // 4), dtype=torch.float32, device=x.device)
             proto_ptr = C.c_void_p(out_proto.data_ptr())
-        L.check(L.lib().yb_forward(self._h, C.c_void_p(x.data_ptr()), code, B, C.c_void_p(out_pred.data_ptr()),
-                                   proto_ptr, _stream_ptr(stream)))
+        # smaller images are padded right / bottom with 114 inside the first kernel (Detector.cs:35-41)
+        L.check(L.lib().yb_forward_padded(self._h, C.c_void_p(x.data_ptr()), code, B, x.shape[2], x.shape[3],
+                                          C.c_void_p(out_pred.data_ptr()), proto_ptr, _stream_ptr(stream)))
         return (out_pred, out_proto) if self.task == "segment" else out_pred
 
     def predict_u8(self, images_host, conf_thres=0.25, iou_thres=0.45, max_det=300, dets_host=None, counts_host=None,
@@ -121,6 +122,16 @@ class Engine:
         L.check(L.lib().yb_predict_u8_submit_gather(self._h, comm._h, slot, C.c_void_p(images_host.data_ptr()),
                                                     images_host.shape[0], conf_thres, iou_thres, max_det,
                                                     C.c_void_p(all_dets_host.data_ptr()), C.c_void_p(all_counts_host.data_ptr())))
+
+    def predict_seg_u8_submit(self, slot, images_host, dets_host, counts_host, masks_host, conf_thres=0.25, iou_thres=0.45,
+                              max_det=300):
+        """yb_predict_seg_u8_submit: segment engines; masks_host uint8 (B, mask_cap, H, W) pinned."""
+        assert not images_host.is_cuda and images_host.dtype == torch.uint8 and images_host.is_contiguous()
+        assert masks_host.dtype == torch.uint8 and masks_host.is_contiguous() and masks_host.dim() == 4
+        L.check(L.lib().yb_predict_seg_u8_submit(self._h, slot, C.c_void_p(images_host.data_ptr()), images_host.shape[0],
+                                                 conf_thres, iou_thres, max_det, masks_host.shape[1],
+                                                 C.c_void_p(dets_host.data_ptr()), C.c_void_p(counts_host.data_ptr()),
+                                                 C.c_void_p(masks_host.data_ptr())))
 
     def predict_u8_wait(self, slot):
         L.check(L.lib().yb_predict_u8_wait(self._h, slot))
