@@ -210,6 +210,27 @@ int32_t yb_conv_backward_data(const float* dz, const float* w, int32_t n, int32_
 int32_t yb_conv_backward_weight(const float* x, const float* dz, int32_t n, int32_t height, int32_t width, int32_t cin,
                                 int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dw, void* stream);
 
+/* Replaces (training path, tensor cores): the same three convolution passes as the fp32 parity kernels above -
+ * `Conv2d.forward` and the dgrad / wgrad libtorch runs behind `loss.backward()` (Modules/Convs.cs:44,
+ * Utils/Amp.cs:260-286) - as tcgen05 implicit GEMMs with TF32 operands and fp32 accumulation (the arithmetic class of
+ * libtorch's own CUDA convolutions, whose cuDNN path allows TF32 by default).  Same tensors and layouts as
+ * yb_conv_forward_f32 / yb_conv_backward_*, except that `w` is always the checkpoint layout (Cout, Cin, k, k).
+ * Supported: cin % 8 == 0, cout % 8 == 0, k in {1, 3}, stride in {1, 2}, pad == k / 2 (stride-2 dgrad: even height /
+ * width); anything else returns YB_ERR_SHAPE and the caller uses the fp32 kernels (the 3-channel stem).
+ *   workspace  dev scratch of at least yb_conv_tc_workspace_bytes(...) bytes (re-packed weights / split-K partials of
+ *              the weight gradient); may be shared by all calls of one stream. */
+int64_t yb_conv_tc_workspace_bytes(int32_t n, int32_t height, int32_t width, int32_t cin, int32_t cout, int32_t k,
+                                   int32_t stride);
+int32_t yb_conv_forward_tc(const float* x, const float* w, const float* bias, int32_t n, int32_t height, int32_t width,
+                           int32_t cin, int32_t cout, int32_t k, int32_t stride, int32_t pad, float* z, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+int32_t yb_conv_backward_data_tc(const float* dz, const float* w, int32_t n, int32_t height, int32_t width, int32_t cin,
+                                 int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dx, void* workspace,
+                                 int64_t workspace_bytes, void* stream);
+int32_t yb_conv_backward_weight_tc(const float* x, const float* dz, int32_t n, int32_t height, int32_t width, int32_t cin,
+                                   int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dw, void* workspace,
+                                   int64_t workspace_bytes, void* stream);
+
 /* Replaces (training path of YOLOv11, fp32 parity kernels): the forward and the autograd backward of the depthwise 3x3
  * convolutions - `Convs.DWConv` (Modules/Convs.cs:108-114; groups = gcd(c1, c2) = c for every use in Yolov11: the
  * class branch of the head, Head.cs:50, and `Attention.pe`, Block.cs:746), stride 1, padding 1.

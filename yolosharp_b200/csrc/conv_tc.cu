@@ -865,10 +865,19 @@ bool tc_conv_supported(const ConvParams& p) {
   return true;
 }
 
+// Experiment knob (tools/exp_dual.py): YB_PLAN_SMALL=1 sizes every plan for half an SM (<= 104 KiB of rings, <= 256
+// TMEM columns, 352 threads) and launches one CTA per SM, so that kernels of TWO concurrent streams (two half-batch
+// engines) are co-resident on every SM and each fills the other's pipeline bubbles.
+static int plan_small() {
+  const char* v = getenv("YB_PLAN_SMALL");
+  return v ? atoi(v) : 0;
+}
+
 static int pick_n_tile(int cout) {
-  if (cout <= 256) return cout;
+  const int cap = plan_small() ? 128 : 256;
+  if (cout <= cap) return cout;
   int best = 16;
-  for (int n = 16; n <= 256; n += 16)
+  for (int n = 16; n <= cap; n += 16)
     if (cout % n == 0) best = n;
   return best;
 }
@@ -1028,7 +1037,7 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     // weight re-fetch per tile
     a.b_resident = (a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= budget) ? 1 : 0;
     // resident weights at one CTA/SM beat re-fetched weights at two CTAs/SM
-    if (occ == 2 && !small && !a.b_resident && a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= 200 * 1024) continue;
+    if (occ == 2 && !plan_small() && !small && !a.b_resident && a.n_tiles == 1 && b_all + 3 * (size_t)a.a_stride <= 200 * 1024) continue;
     if (a.b_resident) {
       a.stages_a = (int)std::min<size_t>(a.mode != TC_TAP ? (a.chunks > 1 ? 8 : 6) : TC_MAX_STAGES, (budget - b_all) / a.a_stride);
       a.stages_b = 0;
@@ -1045,7 +1054,7 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     }
     const bool fits = a.stages_a >= 2 && (a.b_resident || a.stages_b >= ((occ == 2 && a.mode != TC_TAP) ? 3 : 2)) &&
                       (size_t)a.stages_a * a.a_stride + (a.b_resident ? b_all : (size_t)a.stages_b * a.b_stride) <= budget;
-    if (fits && (occ == 1 || small || a.stages_a >= 3)) { plan->occ = occ; break; }
+    if (fits && (occ == 1 || small || a.stages_a >= 3 || plan_small())) { plan->occ = occ; break; }
     if (occ == 1) a.stages_a = 0;  // reported below
   }
   // epilogue groups: one per accumulator buffer at one CTA/SM (608 threads); two when two CTAs share the SM
@@ -1114,6 +1123,7 @@ TcConvPlan* tc_conv_plan_create(const ConvParams& p, std::string* err) {
     }
   }
   plan->grid = num_sms * plan->occ;
+  if (plan_small() && plan->occ == 2) plan->grid = num_sms;  // the SM's other half belongs to the other stream's kernel
   plan->small = m_tiles * a.n_tiles <= 2 * 148;
   return plan;
 }

@@ -1,0 +1,721 @@
+// Tensor-core convolutions of the TRAINING step (fp32 storage, TF32 tcgen05 MMAs, fp32 accumulate in TMEM).
+//
+// Replaces, on the training path, what libtorch runs behind `Conv2d.forward` and `loss.backward()` for the Conv
+// blocks of the reference (Modules/Convs.cs:44; Utils/Amp.cs:260-286 calls forward / backward / optimizer.step):
+// forward, data gradient and weight gradient of a dense k x k convolution (k in {1, 3}, stride in {1, 2}), on the
+// NHWC fp32 activations the training step keeps.  libtorch's own CUDA convolutions run TF32 tensor-core math by
+// default (cudnn.allow_tf32), so TF32 products with fp32 accumulation are the reference's arithmetic class here;
+// the fp32 CUDA-core kernels (yb_conv_forward_f32 / yb_conv_backward_*) stay as the parity twins these are tested
+// against.
+//
+//   tf_conv_kernel   one implicit-GEMM kernel for forward AND data gradient.  M = 128 output positions (a BW x BH
+//                    rectangle of one image, or 128 consecutive positions of the flattened batch for 1x1), N = output
+//                    channels (tile <= 256), K = taps x input channels.  Both operands K-major: A = NHWC activations
+//                    (one 4-D TMA box per tap and 32-channel slab, zero fill = padding, traversal stride = conv
+//                    stride), B = weights re-packed per step as [tap][N][K] (3-D TMA box).  A launch is described
+//                    by a TAP TABLE (box offset dh, dw + weight slab per tap), which covers
+//                      forward          out(y,x) = sum_t in(y*s + kh - p, x*s + kw - p) W[kh][kw]
+//                      dgrad, stride 1  dx(y,x)  = sum_t dz(y + p - kh, x + p - kw) W^T[kh][kw]
+//                      dgrad, stride 2  four launches, one per output parity (py, px), each with the taps whose
+//                                       (py + p - kh) and (px + p - kw) are even, writing every second position
+//   tf_wgrad_kernel  dW[co][tap][ci] = sum_pixels dz[pix][co] * x[pix + tap][ci]: K = pixels, so both operands are
+//                    MN-major - exactly the NHWC tiles TMA delivers (64 pixels x 32 channels, 128-byte rows).  One CTA
+//                    owns 128 output channels x (taps x 32 nb) input channels in TMEM (<= 512 columns), walks its share
+//                    of the pixel tiles (split-K over pixels) and stores a partial; a fixed-order fold sums the
+//                    partials into the checkpoint layout (deterministic, no atomics).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace yb {
+
+typedef CUresult (*TfEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TfEncodeFn tf_encode_fn() {
+  static TfEncodeFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = (TfEncodeFn)p;
+  return fn;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t tf_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16, uint32_t layout) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)lbo16 << 16) | ((uint64_t)sbo16 << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)layout << 61);
+}
+
+constexpr int TF_MAX_STAGES = 8;
+constexpr int TF_THREADS = 192;  // warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2-5 epilogue
+
+// ------------------------------------------------------------------------------------------
+// forward / data gradient
+// ------------------------------------------------------------------------------------------
+struct TfArgs {
+  CUtensorMap tmA, tmB;
+  float* out;
+  const float* bias;                // [n_out] or nullptr
+  long long o_img, o_row, o_pix;    // element strides of the output addressing
+  long long o_off;
+  int n_out;                        // valid output channels (columns >= n_out are not stored)
+  int Ho, Wo, imgs;                 // extent of the output position grid the tiles cover
+  int tiles_w, tiles_h, n_tiles, n_tile, total_tiles;
+  int BW, BH;
+  int in_stride;                    // A box origin = (w0 * in_stride + dw, h0 * in_stride + dh)
+  int ntaps;
+  int dh[9], dw[9], slab[9];
+  int chunks, KK;                   // K slabs per tap, MMAs (K = 8) per slab
+  int BK;
+  int stages;
+  uint32_t a_stride, b_stride, a_bytes, b_bytes;
+  uint32_t layout, sbo16;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(TF_THREADS, 1) tf_conv_kernel(const __grid_constant__ TfArgs a) {
+  extern __shared__ __align__(1024) uint8_t tf_smem[];
+  __shared__ __align__(8) uint64_t bars[2 * TF_MAX_STAGES + 4];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(tf_smem) + 1023u) & ~1023u;
+  const uint32_t smemA = smem0, smemB = smem0 + a.stages * a.a_stride;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[TF_MAX_STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * TF_MAX_STAGES]), tempty0 = smem_u32(&bars[2 * TF_MAX_STAGES + 2]);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int tiles_per_img = a.tiles_w * a.tiles_h;
+  const int ksteps = a.ntaps * a.chunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmB) : "memory");
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+        const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
+        const int th = r / a.tiles_w, tw = r - th * a.tiles_w;
+        const int wbase = tw * a.BW * a.in_stride, hbase = th * a.BH * a.in_stride;
+        for (int t = 0; t < a.ntaps; t++)
+          for (int ch = 0; ch < a.chunks; ch++) {
+            mbar_wait(empty0 + 8 * st, ph ^ 1);
+            mbar_arrive_expect_tx(full0 + 8 * st, a.a_bytes + a.b_bytes);
+            tma_load_4d(smemA + st * a.a_stride, &a.tmA, full0 + 8 * st, ch * a.BK, wbase + a.dw[t], hbase + a.dh[t], img);
+            tma_load_3d(smemB + st * a.b_stride, &a.tmB, full0 + 8 * st, ch * a.BK, nt * a.n_tile, a.slab[t]);
+            if (++st == a.stages) { st = 0; ph ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D fp32 (bit 4), A / B format TF32 (2 at bits 7 and 10), K-major both, N >> 3 at 17, M >> 4 at 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int st = 0, li = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, li++) {
+        const int acc = li & 1;
+        mbar_wait(tempty0 + 8 * acc, ((uint32_t)(li >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * a.n_tile;
+        uint32_t accf = 0;
+        for (int ks = 0; ks < ksteps; ks++) {
+          mbar_wait(full0 + 8 * st, ph);
+          tc_fence_after();
+          const uint32_t sa = smemA + st * a.a_stride, sb = smemB + st * a.b_stride;
+          for (int k = 0; k < a.KK; k++) {  // 8 fp32 = 32 bytes per K step inside the swizzled row
+            umma_tf32(d_tmem, tf_desc(sa + 32 * k, 1, a.sbo16, a.layout), tf_desc(sb + 32 * k, 1, a.sbo16, a.layout), idesc, accf);
+            accf = 1;
+          }
+          umma_commit(empty0 + 8 * st);
+          if (++st == a.stages) { st = 0; ph ^= 1; }
+        }
+        umma_commit(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    int li = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, li++) {
+      const int acc = li & 1;
+      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+      const int img = mt / tiles_per_img, r = mt - img * tiles_per_img;
+      const int th = r / a.tiles_w, tw = r - th * a.tiles_w;
+      const int hl = row / a.BW, wl = row - hl * a.BW;
+      const int ho = th * a.BH + hl, wo = tw * a.BW + wl;
+      const bool valid = hl < a.BH && ho < a.Ho && wo < a.Wo;
+      const int n0 = nt * a.n_tile;
+      float* orow = a.out + (long long)img * a.o_img + (long long)ho * a.o_row + (long long)wo * a.o_pix + a.o_off + n0;
+      mbar_wait(tfull0 + 8 * acc, (uint32_t)(li >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * a.n_tile;
+      for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            const int c = n0 + c0 + g * 4;
+            if (c < a.n_out) {  // n_out is a multiple of 4
+              float4 o = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                                     __uint_as_float(v[g * 4 + 3]));
+              if (a.bias) {
+                const float4 b = *reinterpret_cast<const float4*>(a.bias + c);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              *reinterpret_cast<float4*>(orow + c0 + g * 4) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+  }
+}
+
+// w (Cout, Cin, k, k) checkpoint layout -> wf [tap][Cout][Cin] (forward B operand: rows = output channels, K = Cin)
+//                                        -> wb [tap][Cin][Cout] (dgrad B operand: rows = input channels, K = Cout)
+__global__ void tf_pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wb, int Cout,
+                                       int Cin, int taps) {
+  const long long n = (long long)Cout * Cin * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const long long q = i / taps;
+    const int ci = (int)(q % Cin), co = (int)(q / Cin);
+    const float v = w[i];
+    if (wf) wf[((size_t)t * Cout + co) * Cin + ci] = v;
+    if (wb) wb[((size_t)t * Cin + ci) * Cout + co] = v;
+  }
+}
+
+static int tf_num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+// One launch of tf_conv_kernel.  in: NHWC (N, Hi, Wi, Kc) fp32; wpk: [taps][Nc][Kc] fp32; out addressing given by strides.
+struct TfLaunch {
+  const float* in; int N, Hi, Wi, Kc;
+  const float* wpk; int Nc, taps_total;
+  float* out; long long o_img, o_row, o_pix, o_off;
+  const float* bias;
+  int Ho, Wo;        // output position grid
+  int in_stride;
+  int ntaps; int dh[9], dw[9], slab[9];
+  bool flat;         // 1x1 stride 1, dense output: flatten the batch into one position dimension
+};
+
+static int tf_conv_launch(const TfLaunch& L, cudaStream_t s) {
+  TfEncodeFn encode = tf_encode_fn();
+  if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found"); return YB_ERR_CUDA; }
+  TfArgs a;
+  memset(&a, 0, sizeof(a));
+  a.out = L.out; a.bias = L.bias;
+  a.o_img = L.o_img; a.o_row = L.o_row; a.o_pix = L.o_pix; a.o_off = L.o_off;
+  a.n_out = L.Nc;
+  a.in_stride = L.in_stride;
+  a.ntaps = L.ntaps;
+  for (int t = 0; t < L.ntaps; t++) { a.dh[t] = L.dh[t]; a.dw[t] = L.dw[t]; a.slab[t] = L.slab[t]; }
+  a.BK = L.Kc >= 32 ? 32 : (L.Kc >= 16 ? 16 : 8);
+  a.chunks = (L.Kc + a.BK - 1) / a.BK;
+  a.KK = a.BK / 8;
+  const uint32_t row_bytes = a.BK * 4;
+  a.layout = a.BK == 32 ? 2 : (a.BK == 16 ? 4 : 6);
+  a.sbo16 = (8 * row_bytes) >> 4;
+  const CUtensorMapSwizzle swz = a.BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : (a.BK == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  a.n_tile = std::min(256, (L.Nc + 15) / 16 * 16);
+  a.n_tiles = (L.Nc + a.n_tile - 1) / a.n_tile;
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t box[4], estr[4];
+  if (L.flat) {
+    const cuuint64_t npix = (cuuint64_t)L.N * L.Hi * L.Wi;
+    gdim[0] = L.Kc; gdim[1] = npix; gdim[2] = 1; gdim[3] = 1;
+    gstr[0] = (cuuint64_t)L.Kc * 4; gstr[1] = gstr[0] * npix; gstr[2] = gstr[1];
+    a.BW = 128; a.BH = 1;
+    a.imgs = 1; a.Ho = 1; a.Wo = (int)npix;
+    box[0] = a.BK; box[1] = 128; box[2] = 1; box[3] = 1;
+    estr[0] = estr[1] = estr[2] = estr[3] = 1;
+  } else {
+    gdim[0] = L.Kc; gdim[1] = L.Wi; gdim[2] = L.Hi; gdim[3] = L.N;
+    gstr[0] = (cuuint64_t)L.Kc * 4; gstr[1] = gstr[0] * L.Wi; gstr[2] = gstr[1] * L.Hi;
+    a.imgs = L.N; a.Ho = L.Ho; a.Wo = L.Wo;
+    double best = -1;
+    for (int bw = 1; bw <= std::min(L.Wo, 128); bw++) {
+      const int bh = std::min(L.Ho, 128 / bw);
+      if (bw * L.in_stride > 256 || bh * L.in_stride > 256) continue;
+      const double tiles = (double)((L.Wo + bw - 1) / bw) * ((L.Ho + bh - 1) / bh);
+      const double eff = (double)L.Wo * L.Ho / (tiles * 128.0);
+      if (eff > best + 1e-9 || (eff > best - 1e-9 && bw > a.BW)) { best = eff; a.BW = bw; a.BH = bh; }
+    }
+    box[0] = a.BK; box[1] = a.BW * L.in_stride; box[2] = a.BH * L.in_stride; box[3] = 1;
+    estr[0] = 1; estr[1] = L.in_stride; estr[2] = L.in_stride; estr[3] = 1;
+  }
+  CUresult cr = encode(&a.tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(L.in), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { set_error("tf32 conv: cuTensorMapEncodeTiled(A) failed with code " + std::to_string((int)cr)); return YB_ERR_CUDA; }
+  {
+    cuuint64_t bd[3] = {(cuuint64_t)L.Kc, (cuuint64_t)L.Nc, (cuuint64_t)L.taps_total};
+    cuuint64_t bs[2] = {(cuuint64_t)L.Kc * 4, (cuuint64_t)L.Kc * 4 * L.Nc};
+    cuuint32_t bb[3] = {(cuuint32_t)a.BK, (cuuint32_t)a.n_tile, 1};
+    cuuint32_t be[3] = {1, 1, 1};
+    cr = encode(&a.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(L.wpk), bd, bs, bb, be, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("tf32 conv: cuTensorMapEncodeTiled(B) failed with code " + std::to_string((int)cr)); return YB_ERR_CUDA; }
+  }
+  a.tiles_w = (a.Wo + a.BW - 1) / a.BW;
+  a.tiles_h = (a.Ho + a.BH - 1) / a.BH;
+  a.total_tiles = a.imgs * a.tiles_w * a.tiles_h * a.n_tiles;
+  a.a_bytes = (uint32_t)(a.BW * a.BH) * row_bytes;  // the box has BW*BH <= 128 rows; rows past it are never stored
+  a.b_bytes = (uint32_t)a.n_tile * row_bytes;
+  a.a_stride = (128 * row_bytes + 1023) / 1024 * 1024;
+  a.b_stride = (a.n_tile * row_bytes + 1023) / 1024 * 1024;
+  a.stages = (int)std::min<size_t>(TF_MAX_STAGES, (size_t)(190 * 1024) / (a.a_stride + a.b_stride));
+  if (a.stages < 2) { set_error("tf32 conv: tile does not fit in shared memory"); return YB_ERR_SHAPE; }
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * a.n_tile)) cols <<= 1;
+  a.tmem_cols = cols;
+  const size_t smem = (size_t)a.stages * (a.a_stride + a.b_stride) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    YB_CUDA_CHECK(cudaFuncSetAttribute(tf_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int grid = std::min(a.total_tiles, tf_num_sms());
+  tf_conv_kernel<<<grid, TF_THREADS, smem, s>>>(a);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+size_t tf_conv_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride);
+
+static bool tf_shape_ok(int Cin, int Cout, int k, int stride, int pad) {
+  return Cin % 8 == 0 && Cout % 8 == 0 && (k == 1 || k == 3) && (stride == 1 || stride == 2) && pad == k / 2;
+}
+
+int tf_conv_forward(const float* x, const float* w, const float* bias, int N, int H, int W, int Cin, int Cout, int k, int stride,
+                    int pad, float* z, float* ws, size_t ws_bytes, cudaStream_t s) {
+  if (!tf_shape_ok(Cin, Cout, k, stride, pad)) { set_error("tf32 conv: channels must be multiples of 8, k in {1,3}, stride in {1,2}, pad = k/2"); return YB_ERR_SHAPE; }
+  const size_t wn = (size_t)Cout * Cin * k * k;
+  if (ws_bytes < wn * 4) { set_error("tf32 conv forward: workspace too small"); return YB_ERR_INVALID_ARG; }
+  tf_pack_weights_kernel<<<(unsigned)std::min<size_t>((wn + 255) / 256, 1024), 256, 0, s>>>(w, ws, nullptr, Cout, Cin, k * k);
+  TfLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.in = x; L.N = N; L.Hi = H; L.Wi = W; L.Kc = Cin;
+  L.wpk = ws; L.Nc = Cout; L.taps_total = k * k;
+  L.Ho = (H + 2 * pad - k) / stride + 1; L.Wo = (W + 2 * pad - k) / stride + 1;
+  L.out = z; L.o_pix = Cout; L.o_row = (long long)L.Wo * Cout; L.o_img = (long long)L.Ho * L.o_row; L.o_off = 0;
+  L.bias = bias;
+  L.in_stride = stride;
+  L.ntaps = k * k;
+  for (int t = 0; t < k * k; t++) { L.dh[t] = t / k - pad; L.dw[t] = t % k - pad; L.slab[t] = t; }
+  L.flat = (k == 1 && stride == 1);
+  return tf_conv_launch(L, s);
+}
+
+int tf_conv_backward_data(const float* dz, const float* w, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                          float* dx, float* ws, size_t ws_bytes, cudaStream_t s) {
+  if (!tf_shape_ok(Cin, Cout, k, stride, pad) || (stride == 2 && ((H | W) & 1))) {
+    set_error("tf32 dgrad: channels must be multiples of 8, k in {1,3}, stride in {1,2} (even size for stride 2), pad = k/2");
+    return YB_ERR_SHAPE;
+  }
+  const size_t wn = (size_t)Cout * Cin * k * k;
+  if (ws_bytes < wn * 4) { set_error("tf32 dgrad: workspace too small"); return YB_ERR_INVALID_ARG; }
+  tf_pack_weights_kernel<<<(unsigned)std::min<size_t>((wn + 255) / 256, 1024), 256, 0, s>>>(w, nullptr, ws, Cout, Cin, k * k);
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  TfLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.in = dz; L.N = N; L.Hi = Ho; L.Wi = Wo; L.Kc = Cout;
+  L.wpk = ws; L.Nc = Cin; L.taps_total = k * k;
+  L.out = dx; L.bias = nullptr;
+  L.in_stride = 1;
+  if (stride == 1) {
+    L.Ho = H; L.Wo = W;
+    L.o_pix = Cin; L.o_row = (long long)W * Cin; L.o_img = (long long)H * L.o_row; L.o_off = 0;
+    L.ntaps = k * k;
+    for (int t = 0; t < k * k; t++) { L.dh[t] = pad - t / k; L.dw[t] = pad - t % k; L.slab[t] = t; }
+    L.flat = (k == 1);
+    return tf_conv_launch(L, s);
+  }
+  // stride 2: dx(2a + py, 2b + px) = sum over taps with (py + pad - kh), (px + pad - kw) even of dz(a + (py+pad-kh)/2, b + ...)
+  // k = 1 (pad 0): only parity (0,0) receives gradient; the other positions are zero.
+  if (k == 1) YB_CUDA_CHECK(cudaMemsetAsync(dx, 0, (size_t)N * H * W * Cin * sizeof(float), s));
+  for (int py = 0; py < 2; py++)
+    for (int px = 0; px < 2; px++) {
+      L.ntaps = 0;
+      for (int kh = 0; kh < k; kh++)
+        for (int kw = 0; kw < k; kw++) {
+          const int eh = py + pad - kh, ew = px + pad - kw;
+          if ((eh & 1) || (ew & 1)) continue;
+          // arithmetic shift: eh in {-1..2} is even here, so eh / 2 is exact for 0 and 2; eh = -2 cannot occur (kh <= 2, pad = 1)
+          L.dh[L.ntaps] = eh / 2; L.dw[L.ntaps] = ew / 2; L.slab[L.ntaps] = kh * k + kw;
+          L.ntaps++;
+        }
+      if (L.ntaps == 0) continue;  // k = 1, odd parity: stays zero
+      L.Ho = H / 2; L.Wo = W / 2;
+      L.o_pix = 2LL * Cin; L.o_row = 2LL * W * Cin; L.o_img = (long long)H * W * Cin;
+      L.o_off = ((long long)py * W + px) * Cin;
+      L.flat = false;
+      const int rc = tf_conv_launch(L, s);
+      if (rc) return rc;
+    }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------
+constexpr int WG_PW = 8, WG_PH = 8;          // pixel tile of the dz grid (64 pixels = 8 MMAs of K = 8)
+constexpr int WG_BLK = WG_PW * WG_PH * 128;  // bytes of one 32-channel block of a pixel tile (64 rows x 128 B)
+constexpr int WG_A_STAGES = 2;
+
+struct WgArgs {
+  CUtensorMap tmDz, tmX;
+  float* part;      // [split][co_pad][tap][ci_pad]
+  int Cout, Cin, taps, ksz, stride, pad;
+  int nb;           // 32-channel input blocks per CTA (N = nb * 32 columns per tap)
+  int co_blocks;    // 32-channel output blocks loaded per CTA (<= 4)
+  int co_tiles, ci_tiles, splits;
+  int imgs, tiles_w, tiles_h, pix_tiles;
+  int b_stages;
+  int co_pad, ci_pad;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_constant__ WgArgs a) {
+  extern __shared__ __align__(1024) uint8_t wg_smem[];
+  __shared__ __align__(8) uint64_t bars[2 * WG_A_STAGES + 2 * 16 + 1];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem0 = (smem_u32(wg_smem) + 1023u) & ~1023u;
+  const uint32_t a_stride = 4 * WG_BLK, b_stride = (uint32_t)a.nb * WG_BLK;
+  const uint32_t smemA = smem0, smemB = smem0 + WG_A_STAGES * a_stride;
+  const uint32_t afull = smem_u32(&bars[0]), aempty = smem_u32(&bars[WG_A_STAGES]);
+  const uint32_t bfull = smem_u32(&bars[2 * WG_A_STAGES]), bempty = smem_u32(&bars[2 * WG_A_STAGES + 16]);
+  const uint32_t done = smem_u32(&bars[2 * WG_A_STAGES + 32]);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_A_STAGES; s++) { mbar_init(afull + 8 * s, 1); mbar_init(aempty + 8 * s, 1); }
+    for (int s = 0; s < a.b_stages; s++) { mbar_init(bfull + 8 * s, 1); mbar_init(bempty + 8 * s, 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // rows of the dz stages that are never loaded (Cout < 128) must not hold NaN bit patterns: 0 * NaN would poison nothing
+  // (every accumulator row depends on its own A row only), but keep the tensor pipe away from denormal/NaN slow paths
+  for (uint32_t i = threadIdx.x; i < WG_A_STAGES * a_stride / 16; i += TF_THREADS) st_shared_v4(smemA + i * 16, make_int4(0, 0, 0, 0));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  // CTA -> (output-channel tile, input-channel tile, pixel split)
+  const int split = blockIdx.x % a.splits;
+  const int pair = blockIdx.x / a.splits;
+  const int ci_t = pair % a.ci_tiles, co_t = pair / a.ci_tiles;
+  const int tiles_per_img = a.tiles_w * a.tiles_h;
+  const int my_tiles = split < a.pix_tiles ? (a.pix_tiles - split + a.splits - 1) / a.splits : 0;
+  const int ncols = a.nb * 32;  // accumulator columns per tap
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmDz) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmX) : "memory");
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int i = 0; i < my_tiles; i++) {
+        const int pt = split + i * a.splits;
+        const int img = pt / tiles_per_img, r = pt - img * tiles_per_img;
+        const int th = r / a.tiles_w, tw = r - th * a.tiles_w;
+        const int w0 = tw * WG_PW, h0 = th * WG_PH;
+        mbar_wait(aempty + 8 * sa, pa ^ 1);
+        mbar_arrive_expect_tx(afull + 8 * sa, (uint32_t)a.co_blocks * WG_BLK);
+        for (int b = 0; b < a.co_blocks; b++)
+          tma_load_4d(smemA + sa * a_stride + b * WG_BLK, &a.tmDz, afull + 8 * sa, co_t * 128 + b * 32, w0, h0, img);
+        if (++sa == WG_A_STAGES) { sa = 0; pa ^= 1; }
+        for (int t = 0; t < a.taps; t++) {
+          const int kh = t / a.ksz, kw = t - kh * a.ksz;
+          mbar_wait(bempty + 8 * sb, pb ^ 1);
+          mbar_arrive_expect_tx(bfull + 8 * sb, (uint32_t)a.nb * WG_BLK);
+          for (int b = 0; b < a.nb; b++)
+            tma_load_4d(smemB + sb * b_stride + b * WG_BLK, &a.tmX, bfull + 8 * sb, (ci_t * a.nb + b) * 32,
+                        w0 * a.stride + kw - a.pad, h0 * a.stride + kh - a.pad, img);
+          if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D fp32, A / B TF32, BOTH MN-major (bits 15, 16): operands are [pixel][channel] tiles, K runs over pixels
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(ncols >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      const uint32_t lbo16 = WG_BLK >> 4, sbo16 = 1024 >> 4;  // next 32-channel block; next group of 8 pixels
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int i = 0; i < my_tiles; i++) {
+        mbar_wait(afull + 8 * sa, pa);
+        tc_fence_after();
+        const uint32_t A0 = smemA + sa * a_stride;
+        for (int t = 0; t < a.taps; t++) {
+          mbar_wait(bfull + 8 * sb, pb);
+          tc_fence_after();
+          const uint32_t B0 = smemB + sb * b_stride;
+          const uint32_t d_tmem = tmem_base + t * ncols;
+#pragma unroll
+          for (int ks = 0; ks < WG_PW * WG_PH / 8; ks++)  // 8 pixels = one 1 KiB swizzle atom per block
+            umma_tf32(d_tmem, tf_desc(A0 + ks * 1024, lbo16, sbo16, 2), tf_desc(B0 + ks * 1024, lbo16, sbo16, 2), idesc,
+                      (i > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(bempty + 8 * sb);
+          if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+        }
+        umma_commit(aempty + 8 * sa);
+        if (++sa == WG_A_STAGES) { sa = 0; pa ^= 1; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = co_t * 128 + q * 32 + lane;
+    if (my_tiles > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+    }
+    float* prow = a.part + (((size_t)split * a.co_pad + co) * a.taps) * a.ci_pad + (size_t)ci_t * ncols;
+    for (int t = 0; t < a.taps; t++)
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        uint32_t v[16];
+        if (my_tiles > 0) {
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + t * ncols + c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j++) v[j] = 0u;
+        }
+        if (co < a.Cout) {
+#pragma unroll
+          for (int g = 0; g < 4; g++)
+            *reinterpret_cast<float4*>(prow + (size_t)t * a.ci_pad + c0 + g * 4) =
+                make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                            __uint_as_float(v[g * 4 + 3]));
+        }
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+  }
+}
+
+// dw[co][ci][tap] = sum over splits (fixed order) of part[split][co][tap][ci]
+__global__ void tf_wgrad_fold_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cout, int Cin, int taps, int splits,
+                                     int co_pad, int ci_pad) {
+  const long long n = (long long)Cout * Cin * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const long long q = i / taps;
+    const int ci = (int)(q % Cin), co = (int)(q / Cin);
+    float acc = 0.f;
+    for (int s = 0; s < splits; s++) acc += part[(((size_t)s * co_pad + co) * taps + t) * ci_pad + ci];
+    dw[i] = acc;
+  }
+}
+
+struct WgPlan { int nb, co_tiles, ci_tiles, splits, co_pad, ci_pad, pix_tiles, tiles_w, tiles_h; };
+static WgPlan wg_plan(int N, int H, int W, int Cin, int Cout, int k, int stride, int pad) {
+  WgPlan p;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int taps = k * k;
+  const int ci_blocks = (Cin + 31) / 32;
+  p.nb = std::max(1, std::min(ci_blocks, 256 / (32 * taps) > 0 ? 256 / (32 * taps) : 1));  // taps * nb * 32 <= 288 columns
+  if (taps == 1) p.nb = std::min(ci_blocks, 8);
+  p.ci_tiles = (ci_blocks + p.nb - 1) / p.nb;
+  p.co_tiles = (Cout + 127) / 128;
+  p.co_pad = p.co_tiles * 128;
+  p.ci_pad = p.ci_tiles * p.nb * 32;
+  p.tiles_w = (Wo + WG_PW - 1) / WG_PW;
+  p.tiles_h = (Ho + WG_PH - 1) / WG_PH;
+  p.pix_tiles = N * p.tiles_w * p.tiles_h;
+  const int pairs = p.co_tiles * p.ci_tiles;
+  p.splits = std::max(1, std::min(p.pix_tiles, (2 * tf_num_sms() + pairs - 1) / pairs));
+  p.splits = std::min(p.splits, 64);
+  return p;
+}
+
+size_t tf_conv_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride) {
+  const WgPlan p = wg_plan(N, H, W, Cin, Cout, k, stride, k / 2);
+  const size_t part = (size_t)p.splits * p.co_pad * k * k * p.ci_pad * 4;
+  const size_t wpk = (size_t)Cout * Cin * k * k * 4;
+  return std::max(part, wpk) + 256;
+}
+
+int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
+                            float* dw, float* ws, size_t ws_bytes, cudaStream_t s) {
+  if (!tf_shape_ok(Cin, Cout, k, stride, pad)) { set_error("tf32 wgrad: channels must be multiples of 8, k in {1,3}, stride in {1,2}, pad = k/2"); return YB_ERR_SHAPE; }
+  TfEncodeFn encode = tf_encode_fn();
+  if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found"); return YB_ERR_CUDA; }
+  const WgPlan p = wg_plan(N, H, W, Cin, Cout, k, stride, pad);
+  const size_t part_bytes = (size_t)p.splits * p.co_pad * k * k * p.ci_pad * 4;
+  if (ws_bytes < part_bytes) { set_error("tf32 wgrad: workspace too small"); return YB_ERR_INVALID_ARG; }
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  WgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.part = ws;
+  a.Cout = Cout; a.Cin = Cin; a.taps = k * k; a.ksz = k; a.stride = stride; a.pad = pad;
+  a.nb = p.nb; a.co_tiles = p.co_tiles; a.ci_tiles = p.ci_tiles; a.splits = p.splits;
+  a.co_blocks = std::min(4, (Cout + 31) / 32);
+  a.imgs = N; a.tiles_w = p.tiles_w; a.tiles_h = p.tiles_h; a.pix_tiles = p.pix_tiles;
+  a.co_pad = p.co_pad; a.ci_pad = p.ci_pad;
+  const size_t b_stride = (size_t)p.nb * WG_BLK;
+  a.b_stages = (int)std::min<size_t>(16, ((size_t)190 * 1024 - (size_t)WG_A_STAGES * 4 * WG_BLK) / b_stride);
+  if (a.b_stages < 2) { set_error("tf32 wgrad: tile does not fit in shared memory"); return YB_ERR_SHAPE; }
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(a.taps * p.nb * 32)) cols <<= 1;
+  a.tmem_cols = cols;
+  {
+    cuuint64_t gd[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+    cuuint64_t gs[3] = {(cuuint64_t)Cout * 4, (cuuint64_t)Cout * 4 * Wo, (cuuint64_t)Cout * 4 * Wo * Ho};
+    cuuint32_t bx[4] = {32, WG_PW, WG_PH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult cr = encode(&a.tmDz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(dz), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("tf32 wgrad: cuTensorMapEncodeTiled(dz) failed with code " + std::to_string((int)cr)); return YB_ERR_CUDA; }
+  }
+  {
+    cuuint64_t gd[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gs[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cin * 4 * W, (cuuint64_t)Cin * 4 * W * H};
+    cuuint32_t bx[4] = {32, (cuuint32_t)(WG_PW * stride), (cuuint32_t)(WG_PH * stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult cr = encode(&a.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { set_error("tf32 wgrad: cuTensorMapEncodeTiled(x) failed with code " + std::to_string((int)cr)); return YB_ERR_CUDA; }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    YB_CUDA_CHECK(cudaFuncSetAttribute(tf_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = (size_t)WG_A_STAGES * 4 * WG_BLK + (size_t)a.b_stages * b_stride + 1024;
+  const int grid = p.co_tiles * p.ci_tiles * p.splits;
+  tf_wgrad_kernel<<<grid, TF_THREADS, smem, s>>>(a);
+  YB_CUDA_CHECK(cudaGetLastError());
+  const size_t n = (size_t)Cout * Cin * k * k;
+  tf_wgrad_fold_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 2048), 256, 0, s>>>(ws, dw, Cout, Cin, k * k, p.splits, p.co_pad, p.ci_pad);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+static bool tf_have_dev(const char* who) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error(std::string(who) + ": no CUDA device");
+    return false;
+  }
+  return true;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" {
+
+int64_t yb_conv_tc_workspace_bytes(int32_t n, int32_t height, int32_t width, int32_t cin, int32_t cout, int32_t k, int32_t stride) {
+  if (n <= 0 || height <= 0 || width <= 0 || cin <= 0 || cout <= 0 || k <= 0 || stride <= 0) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return 0; }
+  return (int64_t)tf_conv_workspace_bytes(n, height, width, cin, cout, k, stride);
+}
+
+int32_t yb_conv_forward_tc(const float* x, const float* w, const float* bias, int32_t n, int32_t height, int32_t width, int32_t cin,
+                           int32_t cout, int32_t k, int32_t stride, int32_t pad, float* z, void* workspace, int64_t workspace_bytes,
+                           void* stream) {
+  if (!x || !w || !z || !workspace) { set_error("yb_conv_forward_tc: null argument"); return YB_ERR_INVALID_ARG; }
+  if (n <= 0 || height <= 0 || width <= 0 || cin <= 0 || cout <= 0) { set_error("yb_conv_forward_tc: bad shape"); return YB_ERR_SHAPE; }
+  if (!tf_have_dev("yb_conv_forward_tc")) return YB_ERR_NO_DEVICE;
+  return tf_conv_forward(x, w, bias, n, height, width, cin, cout, k, stride, pad, z, (float*)workspace, (size_t)workspace_bytes,
+                         (cudaStream_t)stream);
+}
+
+int32_t yb_conv_backward_data_tc(const float* dz, const float* w, int32_t n, int32_t height, int32_t width, int32_t cin, int32_t cout,
+                                 int32_t k, int32_t stride, int32_t pad, float* dx, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  if (!dz || !w || !dx || !workspace) { set_error("yb_conv_backward_data_tc: null argument"); return YB_ERR_INVALID_ARG; }
+  if (n <= 0 || height <= 0 || width <= 0 || cin <= 0 || cout <= 0) { set_error("yb_conv_backward_data_tc: bad shape"); return YB_ERR_SHAPE; }
+  if (!tf_have_dev("yb_conv_backward_data_tc")) return YB_ERR_NO_DEVICE;
+  return tf_conv_backward_data(dz, w, n, height, width, cin, cout, k, stride, pad, dx, (float*)workspace, (size_t)workspace_bytes,
+                               (cudaStream_t)stream);
+}
+
+int32_t yb_conv_backward_weight_tc(const float* x, const float* dz, int32_t n, int32_t height, int32_t width, int32_t cin,
+                                   int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dw, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
+  if (!x || !dz || !dw || !workspace) { set_error("yb_conv_backward_weight_tc: null argument"); return YB_ERR_INVALID_ARG; }
+  if (n <= 0 || height <= 0 || width <= 0 || cin <= 0 || cout <= 0) { set_error("yb_conv_backward_weight_tc: bad shape"); return YB_ERR_SHAPE; }
+  if (!tf_have_dev("yb_conv_backward_weight_tc")) return YB_ERR_NO_DEVICE;
+  return tf_conv_backward_weight(x, dz, n, height, width, cin, cout, k, stride, pad, dw, (float*)workspace, (size_t)workspace_bytes,
+                                 (cudaStream_t)stream);
+}
+
+}  // extern "C"

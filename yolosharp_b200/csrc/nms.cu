@@ -126,6 +126,10 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
   unsigned* frow = ckey + NMS_FAST_N;                                    // [32] chunk bit-matrix rows, [32..63] long segments
   unsigned short* segs = reinterpret_cast<unsigned short*>(frow + 64);   // [NMS_FAST_N] segment starts
   unsigned char* keepf = reinterpret_cast<unsigned char*>(segs + NMS_FAST_N);      // [NMS_FAST_N]
+  // kept list of every class segment (ranks, at the segment's own positions).  It lives in the part of the key area
+  // the fast path never touches (n <= NMS_FAST_N keys in use), so `ckey` is read-only while segments are processed:
+  // a warp that scans past the end of its own segment reads a neighbour's class bits, never data being written.
+  unsigned short* klist = reinterpret_cast<unsigned short*>(skeys + NMS_FAST_N);   // [NMS_FAST_N]
   unsigned long long* keys = gkeys + (size_t)b * key_cap;
   if (tid < 8) misc[tid] = 0;
   __syncthreads();
@@ -236,8 +240,8 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
           bool sup = false;
           for (int t = 0; t < kcount; t += 2) {  // two kept boxes per step (independent chains)
             const bool has1 = t + 1 < kcount;
-            const float4 k0 = fbox[ckey[s_begin + t] & 0xFFFu];
-            const float4 k1 = fbox[ckey[s_begin + (has1 ? t + 1 : t)] & 0xFFFu];
+            const float4 k0 = fbox[klist[s_begin + t]];
+            const float4 k1 = fbox[klist[s_begin + (has1 ? t + 1 : t)]];
             const bool s0 = iou_gt4(k0, mine, iou_thres), s1 = iou_gt4(k1, mine, iou_thres);
             sup = sup || s0 || (has1 && s1);
           }
@@ -255,9 +259,7 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
           }
           __syncwarp();
           if ((keptmask >> lane) & 1u) {
-            // class bits stay in place: a neighbouring warp scanning past its own segment must never see a
-            // foreign class here
-            ckey[s_begin + kcount + __popc(keptmask & ((1u << lane) - 1u))] = (cls << 12) | (unsigned)rank;
+            klist[s_begin + kcount + __popc(keptmask & ((1u << lane) - 1u))] = (unsigned short)rank;
             keepf[rank] = 1;
           }
           __syncwarp();
@@ -292,9 +294,9 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
             if (valid) {
               // two kept boxes per step: independent smem chains and IoU arithmetic in flight
               for (int k = warp; k < kcount; k += 64) {
-                const float4 k0 = fbox[ckey[s_begin + k] & 0xFFFu];
+                const float4 k0 = fbox[klist[s_begin + k]];
                 const bool has1 = k + 32 < kcount;
-                const float4 k1 = fbox[ckey[s_begin + (has1 ? k + 32 : k)] & 0xFFFu];
+                const float4 k1 = fbox[klist[s_begin + (has1 ? k + 32 : k)]];
                 const bool s0 = iou_gt4(k0, mine, iou_thres), s1 = iou_gt4(k1, mine, iou_thres);
                 sup = sup || s0 || (has1 && s1);
               }
@@ -315,7 +317,7 @@ nms_kernel(const float* __restrict__ pred, int C, int A, int nc, float conf_thre
               kn++;
             }
             if ((keptmask >> lane) & 1u) {
-              ckey[s_begin + kcount + __popc(keptmask & ((1u << lane) - 1u))] = (cls << 12) | (unsigned)rank;
+              klist[s_begin + kcount + __popc(keptmask & ((1u << lane) - 1u))] = (unsigned short)rank;
               keepf[rank] = 1;
             }
             __syncwarp();
