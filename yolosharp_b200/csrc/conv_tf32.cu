@@ -19,7 +19,9 @@
 //                      dgrad, stride 2  four launches, one per output parity (py, px), each with the taps whose
 //                                       (py + p - kh) and (px + p - kw) are even, writing every second position
 //   tf_wgrad_kernel  dW[co][tap][ci] = sum_pixels dz[pix][co] * x[pix + tap][ci]: K = pixels, so both operands are
-//                    MN-major - exactly the NHWC tiles TMA delivers (64 pixels x 32 channels, 128-byte rows).  One CTA
+//                    MN-major - exactly the NHWC tiles TMA delivers (64 pixels x 32 channels, 128-byte rows, written
+//                    with SWIZZLE_128B_ATOM_32B: the one shared-memory layout tcgen05 accepts for MN-major 32-bit
+//                    operands, UMMA layout type SWIZZLE_128B_BASE32B).  One CTA
 //                    owns 128 output channels x (taps x 32 nb) input channels in TMEM (<= 512 columns), walks its share
 //                    of the pixel tiles (split-K over pixels) and stores a partial; a fixed-order fold sums the
 //                    partials into the checkpoint layout (deterministic, no atomics).
@@ -508,7 +510,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
       // D fp32, A / B TF32, BOTH MN-major (bits 15, 16): operands are [pixel][channel] tiles, K runs over pixels
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(ncols >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
-      const uint32_t lbo16 = WG_BLK >> 4, sbo16 = 1024 >> 4;  // next 32-channel block; next group of 8 pixels
+      // MN-major 32-bit operands have ONE legal shared-memory layout: 128-byte rows (32 channels of one pixel) swizzled
+      // in 32-byte units over groups of 4 rows (UMMA layout type 1 = SWIZZLE_128B_BASE32B, written by TMA's
+      // SWIZZLE_128B_ATOM_32B).  LBO = next 32-channel block, SBO = next group of 4 pixels (K atoms of 4).
+      const uint32_t lbo16 = WG_BLK >> 4, sbo16 = 512 >> 4;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int i = 0; i < my_tiles; i++) {
@@ -521,8 +526,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
           const uint32_t B0 = smemB + sb * b_stride;
           const uint32_t d_tmem = tmem_base + t * ncols;
 #pragma unroll
-          for (int ks = 0; ks < WG_PW * WG_PH / 8; ks++)  // 8 pixels = one 1 KiB swizzle atom per block
-            umma_tf32(d_tmem, tf_desc(A0 + ks * 1024, lbo16, sbo16, 2), tf_desc(B0 + ks * 1024, lbo16, sbo16, 2), idesc,
+          for (int ks = 0; ks < WG_PW * WG_PH / 8; ks++)  // 8 pixels (K = 8) = 1 KiB = two 4-row swizzle atoms per block
+            umma_tf32(d_tmem, tf_desc(A0 + ks * 1024, lbo16, sbo16, 1), tf_desc(B0 + ks * 1024, lbo16, sbo16, 1), idesc,
                       (i > 0 || ks > 0) ? 1u : 0u);
           umma_commit(bempty + 8 * sb);
           if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
@@ -588,7 +593,7 @@ static WgPlan wg_plan(int N, int H, int W, int Cin, int Cout, int k, int stride,
   const int taps = k * k;
   const int ci_blocks = (Cin + 31) / 32;
   p.nb = std::max(1, std::min(ci_blocks, 256 / (32 * taps) > 0 ? 256 / (32 * taps) : 1));  // taps * nb * 32 <= 288 columns
-  if (taps == 1) p.nb = std::min(ci_blocks, 8);
+  if (taps == 1) p.nb = std::min(ci_blocks, 4);  // 4 x 8 KiB per stage: three stages beside the dz ring
   p.ci_tiles = (ci_blocks + p.nb - 1) / p.nb;
   p.co_tiles = (Cout + 127) / 128;
   p.co_pad = p.co_tiles * 128;
@@ -638,7 +643,7 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
     cuuint32_t bx[4] = {32, WG_PW, WG_PH, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult cr = encode(&a.tmDz, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(dz), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("tf32 wgrad: cuTensorMapEncodeTiled(dz) failed with code " + std::to_string((int)cr)); return YB_ERR_CUDA; }
   }
   {
@@ -647,7 +652,7 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
     cuuint32_t bx[4] = {32, (cuuint32_t)(WG_PW * stride), (cuuint32_t)(WG_PH * stride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult cr = encode(&a.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { set_error("tf32 wgrad: cuTensorMapEncodeTiled(x) failed with code " + std::to_string((int)cr)); return YB_ERR_CUDA; }
   }
   static bool attr_set = false;

@@ -325,6 +325,60 @@ def conv_backward(x, dz, w, stride=1, pad=None, stream=None):
     return dx, dw
 
 
+def conv_tc_supported(cin, cout, k, stride, pad, H=0, W=0):
+    """Shapes the TF32 tensor-core training convolutions take (everything else: the fp32 kernels)."""
+    return cin % 8 == 0 and cout % 8 == 0 and k in (1, 3) and stride in (1, 2) and pad == k // 2 and \
+        (stride == 1 or (H % 2 == 0 and W % 2 == 0))
+
+
+class ConvWorkspace:
+    """Device scratch shared by the yb_conv_*_tc calls of one stream (re-packed weights / split-K partials); grows on
+    demand, so a step allocates it once."""
+
+    def __init__(self, device):
+        self.device, self.buf = device, None
+
+    def get(self, N, H, W, Cin, Cout, k, stride):
+        need = int(L.lib().yb_conv_tc_workspace_bytes(N, H, W, Cin, Cout, k, stride))
+        if self.buf is None or self.buf.numel() < need:
+            self.buf = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+def conv_forward_tc(x, w, bias=None, stride=1, pad=None, ws=None, stream=None):
+    """yb_conv_forward_tc: x (N,H,W,Cin) NHWC float32, w (Cout,Cin,k,k) -> z (N,Ho,Wo,Cout); TF32 tcgen05 MMAs."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    N, H, W, Cin = x.shape
+    Cout, _, k, _ = w.shape
+    pad = k // 2 if pad is None else pad
+    ws = ws or ConvWorkspace(x.device)
+    buf = ws.get(N, H, W, Cin, Cout, k, stride)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    z = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    L.check(L.lib().yb_conv_forward_tc(C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()),
+                                       C.c_void_p(bias.data_ptr()) if bias is not None else None, N, H, W, Cin, Cout, k, stride, pad,
+                                       C.c_void_p(z.data_ptr()), C.c_void_p(buf.data_ptr()), buf.numel(), _stream_ptr(stream)))
+    return z
+
+
+def conv_backward_tc(x, dz, w, stride=1, pad=None, ws=None, stream=None, need_dx=True):
+    """yb_conv_backward_data_tc / _weight_tc -> (dx, dw); same tensors as conv_backward."""
+    for t in (x, dz, w):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    N, H, W, Cin = x.shape
+    Cout, _, k, _ = w.shape
+    pad = k // 2 if pad is None else pad
+    ws = ws or ConvWorkspace(x.device)
+    buf = ws.get(N, H, W, Cin, Cout, k, stride)
+    dx, dw = (torch.empty_like(x) if need_dx else None), torch.empty_like(w)
+    if need_dx:
+        L.check(L.lib().yb_conv_backward_data_tc(C.c_void_p(dz.data_ptr()), C.c_void_p(w.data_ptr()), N, H, W, Cin, Cout, k, stride, pad,
+                                                 C.c_void_p(dx.data_ptr()), C.c_void_p(buf.data_ptr()), buf.numel(), _stream_ptr(stream)))
+    L.check(L.lib().yb_conv_backward_weight_tc(C.c_void_p(x.data_ptr()), C.c_void_p(dz.data_ptr()), N, H, W, Cin, Cout, k, stride, pad,
+                                               C.c_void_p(dw.data_ptr()), C.c_void_p(buf.data_ptr()), buf.numel(), _stream_ptr(stream)))
+    return dx, dw
+
+
 def dwconv3x3_forward(x, w, stream=None):
     """yb_dwconv3x3_forward_f32: x (N,H,W,C) NHWC float32, w (C,1,3,3) -> z (N,H,W,C) (stride 1, pad 1)."""
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and w.is_cuda and w.is_contiguous()

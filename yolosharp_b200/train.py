@@ -58,14 +58,31 @@ def warmup_lrs(ni, nw, initial_lr, lam, warmup_bias_lr=0.1):
 class KernelOps:
     """The C-ABI kernels (no fallback: importing this on a machine without the CUDA library fails loudly)."""
 
-    def __init__(self):
+    def __init__(self, tensor_cores=True):
+        """tensor_cores: dense convolutions (forward, dgrad, wgrad) on the TF32 tcgen05 kernels (csrc/conv_tf32.cu) where
+        their shape rule holds (channels % 8, k in {1, 3}); False = the fp32 CUDA-core parity kernels everywhere."""
         from . import engine as E
         self.E = E
+        self.tc = bool(tensor_cores)
+        self.ws = None
+
+    def _tc_ok(self, x, w, stride, pad):
+        Cout, Cin, k, _ = w.shape
+        return self.tc and self.E.conv_tc_supported(Cin, Cout, k, stride, pad, x.shape[1], x.shape[2])
+
+    def _ws(self, x):
+        if self.ws is None:
+            self.ws = self.E.ConvWorkspace(x.device)
+        return self.ws
 
     def conv_forward(self, x, w, bias, stride, pad):
+        if self._tc_ok(x, w, stride, pad):
+            return self.E.conv_forward_tc(x.contiguous(), w.contiguous(), bias, stride, pad, ws=self._ws(x))
         return self.E.conv_forward(x, w, bias, stride, pad)
 
     def conv_backward(self, x, dz, w, stride, pad):
+        if self._tc_ok(x, w, stride, pad):
+            return self.E.conv_backward_tc(x.contiguous(), dz.contiguous(), w.contiguous(), stride, pad, ws=self._ws(x))
         return self.E.conv_backward(x, dz.contiguous(), w, stride, pad)
 
     def bn_silu_forward(self, z, gamma, beta, rm, rv, act):
