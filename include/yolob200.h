@@ -283,6 +283,16 @@ int32_t yb_predict_seg_u8_submit(yb_engine* e, int32_t slot, const uint8_t* imag
                                  float iou_thres, int32_t max_det, int32_t mask_cap, float* dets_host, int32_t* counts_host,
                                  uint8_t* masks_host);
 
+/* Replaces: `Detect.postprocess` + `Detect.get_topk_index` (Modules/Head.cs:117-127, 175-196) - the NMS-free tail an
+ * end2end head runs instead of non_max_suppression (`Config.End2End` defaults to true, Data/Config.cs:239): the
+ * k = min(max_det, A) anchors with the largest best-class score, then the k largest of their k x nc class scores.
+ *   pred  dev float32 (B, channels >= 4 + nc, A), channel-major as written by yb_forward (rows 0-3 xywh, then scores)
+ *   out   dev float32 (B, k, 6) rows [x, y, w, h, score, class], score-descending;  idx  dev int32 (B, k) anchor of
+ *         every row, or NULL;  agnostic != 0 = the `agnostic_nms` branch (one row per selected anchor, its best class).
+ * Equal scores are taken in index order (torch.topk leaves that choice unspecified).  max_det <= 1024. */
+int32_t yb_topk_postprocess(const float* pred, int32_t batch, int32_t channels, int32_t anchors, int32_t nc,
+                            int32_t max_det, int32_t agnostic, float* out, int32_t* idx, void* stream);
+
 /* Validation-side post-processing (csrc/val.cu), batched over the images of a step.
  * yb_box_iou  replaces `Metrics.box_iou(box1, box2)` (Utils/Metrics.cs:16-34): out (n, m) float32, xyxy boxes.
  * yb_match_predictions  replaces the per-image `match_predictions(pred_classes, true_classes, iou)` loop of

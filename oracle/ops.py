@@ -191,3 +191,26 @@ def segmenter_predict(model, img_u8_chw, conf, iou, nc=80, pre=preprocess):
     if (x.shape[2], x.shape[3]) != (h, w):
         masks = torch.nn.functional.interpolate(masks[None].float(), size=(h, w), mode="bilinear", align_corners=False)[0]
     return rows, masks.to(torch.uint8), to_yolo_results(rows)
+
+
+def e2e_postprocess(y, max_det, nc, agnostic=False):
+    """Head.cs:117-127 (`postprocess`) + 175-196 (`get_topk_index`): y (B, 4 + nc, A), the end2end head's decoded output
+    -> (rows (B, k, 6) [box, score, class], idx (B, k) anchor of every row).  `forward` calls it as
+    postprocess(y.permute(0, 2, 1)) (Head.cs:107-111)."""
+    preds = y.permute(0, 2, 1)
+    boxes, scores = preds.split([4, nc], dim=-1)                       # Head.cs:120-122
+    batch_size, anchors, _ = scores.shape
+    k = min(max_det, anchors)                                           # Head.cs:182
+    if agnostic:                                                        # Head.cs:183-189
+        scores, labels = scores.max(dim=-1, keepdim=True)
+        scores, indices = scores.topk(k, dim=1)
+        labels = labels.gather(1, indices)
+        conf, idx = labels.float(), indices
+    else:
+        ori_index = scores.max(dim=-1).values.topk(k).indices.unsqueeze(-1)          # Head.cs:190
+        scores = scores.gather(dim=1, index=ori_index.repeat(1, 1, nc))              # Head.cs:191
+        scores, index = scores.flatten(1).topk(k)                                    # Head.cs:192
+        idx = ori_index[torch.arange(batch_size)[..., None], torch.div(index, nc, rounding_mode="floor")]  # Head.cs:193
+        scores, conf = scores[..., None], (index % nc)[..., None].float()            # Head.cs:194
+    boxes = boxes.gather(dim=1, index=idx.repeat(1, 1, 4))                           # Head.cs:125
+    return torch.cat([boxes, scores, conf], dim=-1), idx.squeeze(-1)                 # Head.cs:126

@@ -86,15 +86,53 @@ def test_train_step_kernels_gpu():
     _compare(TrainStepV8, KernelOps(tensor_cores=False), "cuda", 1e-3)
 
 
+def _compare_tc(step_cls, ops_cls, arch):
+    """TF32 tensor-core step against the SAME step on the fp32 parity kernels.  The task-aligned assigner is discrete
+    (top-k per target): a 1e-3 perturbation of the head outputs can move an assignment and with it the loss by
+    percents, which says nothing about the kernels.  So the comparison is split at the loss: (1) train-mode head outputs
+    of both paths on the same batch, (2) both backward passes driven by the SAME loss gradient (the fp32 path's),
+    (3) the whole step end to end with a loose bound on the loss items."""
+    torch.manual_seed(0)
+    m = oracle_model(arch, "detect", "n")
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    B, H, W = 2, 64, (64 if arch == "v11" else 96)
+    x = synth_image(B, H, W).cuda()
+    targets = _targets(B)
+    a = step_cls(sd0, "n", 80, device="cuda", ops=ops_cls(tensor_cores=False), lr=1e-3)
+    b = step_cls(sd0, "n", 80, device="cuda", ops=ops_cls(tensor_cores=True), lr=1e-3)
+    ba, sa = a.forward(x)
+    bb, sb = b.forward(x)
+
+    def rel(u, v):
+        return float((u - v).abs().max() / v.pow(2).mean().sqrt())
+    e_box, e_cls = rel(bb, ba), rel(sb, sa)
+    items, gb, gs = a.ops.detection_loss(ba, sa, targets, H, W)
+    a.P.grad.zero_()
+    b.P.grad.zero_()
+    a.backward(gb, gs)
+    b.backward(gb, gs)
+    gmax = float(a.P.grad.abs().max())
+    worst = ("", 0.0)
+    for k in a.P.names:
+        ga, gbk = a.P.g(k), b.P.g(k)
+        # tensors whose whole gradient is rounding noise (see _compare) are judged against the step's gradient scale
+        err = float((gbk - ga).abs().max()) / max(float(ga.abs().max()), 1e-2 * gmax)
+        worst = max(worst, (k, err), key=lambda t: t[1])
+    print(f"{arch}: head outputs box {e_box:.2e} cls {e_cls:.2e} (max abs / rms); worst parameter gradient {worst[0]} {worst[1]:.2e}")
+    assert e_box < 2e-2 and e_cls < 2e-2
+    assert worst[1] < 5e-2, worst
+    c = step_cls(sd0, "n", 80, device="cuda", ops=ops_cls(tensor_cores=True), lr=1e-3)
+    it_tc = c.step(x, targets).cpu()
+    np.testing.assert_allclose(it_tc.numpy(), items.cpu().numpy(), rtol=0.15)
+
+
 @pytest.mark.gpu
 def test_train_step_tensor_cores_gpu():
-    """The same step with every dense convolution (forward, dgrad, wgrad) on the TF32 tcgen05 kernels - the default of
-    KernelOps, the arithmetic class of libtorch's own CUDA convolutions.  TF32 keeps 10 mantissa bits per operand: loss
-    items within 5e-3, every parameter gradient within 10 % of its tensor's largest entry after ~60 layers of backward
-    (observed worst printed by the assertion message), Adam's first step within 2.1 lr."""
+    """Every dense convolution (forward, dgrad, wgrad) on the TF32 tcgen05 kernels - the default of KernelOps, the
+    arithmetic class of libtorch's own CUDA convolutions."""
     import yolosharp_b200  # noqa: F401
     from yolosharp_b200.train import KernelOps, TrainStepV8
-    _compare(TrainStepV8, KernelOps(), "cuda", 5e-3)
+    _compare_tc(TrainStepV8, KernelOps, "v8")
 
 
 def test_lr_schedule_and_warmup():
@@ -208,7 +246,7 @@ def test_train_step_v11_tensor_cores_gpu():
     """YOLOv11n step with the dense convolutions on the TF32 tcgen05 kernels (depthwise conv / attention stay fp32)."""
     import yolosharp_b200  # noqa: F401
     from yolosharp_b200.train_v11 import KernelOpsV11, TrainStepV11
-    _compare(TrainStepV11, KernelOpsV11(), "cuda", 5e-3, arch="v11")
+    _compare_tc(TrainStepV11, KernelOpsV11, "v11")
 
 
 @pytest.mark.gpu

@@ -12,7 +12,7 @@ class TorchOps:
     def conv_forward(self, x, w, bias, stride, pad):
         return F.conv2d(x.permute(0, 3, 1, 2), w, bias, stride, pad).permute(0, 2, 3, 1).contiguous()
 
-    def conv_backward(self, x, dz, w, stride, pad):
+    def conv_backward(self, x, dz, w, stride, pad, need_dx=True):
         xn, dzn = x.permute(0, 3, 1, 2), dz.permute(0, 3, 1, 2)
         dx = torch.nn.grad.conv2d_input(xn.shape, w, dzn, stride, pad)
         dw = torch.nn.grad.conv2d_weight(xn, w.shape, dzn, stride, pad)

@@ -20,7 +20,13 @@ namespace yb {
 
 namespace {
 
-constexpr int BN_TX = 32, BN_TY = 8, BN_ROWS_PER_BLOCK = 256;
+constexpr int BN_TX = 32, BN_TY = 8, BN_ROWS_PER_BLOCK = 256, BN_MAX_SLABS = 512;
+// rows per slab: 256, or more for tall matrices so that the serial fold of the per-slab partials (bn_finish_kernel, one
+// thread per channel) stays <= 512 steps (the 1.6 M-row first layers had 6 400 slabs: 16 us per fold, 243 folds a step)
+static int bn_rows_per_block(long long M) {
+  const long long r = (M + BN_MAX_SLABS - 1) / BN_MAX_SLABS;
+  return (int)std::max<long long>(BN_ROWS_PER_BLOCK, (r + BN_TY - 1) / BN_TY * BN_TY);
+}
 
 __device__ __forceinline__ float silu_f(float u) { return u / (1.f + expf(-u)); }
 __device__ __forceinline__ float silu_grad(float u) {
@@ -35,14 +41,14 @@ __global__ void __launch_bounds__(BN_TX* BN_TY) bn_partial_kernel(int mode, int 
                                                                 long long M, int C, int pitch, int dpitch,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                float* __restrict__ p0, float* __restrict__ p1) {
+                                                                float* __restrict__ p0, float* __restrict__ p1, int rpb) {
   const int c = blockIdx.x * BN_TX + threadIdx.x;
-  const long long r0 = (long long)blockIdx.y * BN_ROWS_PER_BLOCK;
+  const long long r0 = (long long)blockIdx.y * rpb;
   float a0 = 0.f, a1 = 0.f;
   if (c < C) {
     const float mu = mode ? mean[c] : 0.f;
     const float is = mode == 2 ? invstd[c] : 0.f, ga = mode == 2 ? gamma[c] : 0.f, be = mode == 2 ? beta[c] : 0.f;
-    for (long long r = r0 + threadIdx.y; r < min(M, r0 + BN_ROWS_PER_BLOCK); r += BN_TY) {
+    for (long long r = r0 + threadIdx.y; r < min(M, r0 + rpb); r += BN_TY) {
       const float v = z[r * pitch + c];
       if (mode == 0) {
         a0 += v;
@@ -131,15 +137,16 @@ int bn_silu_train_forward(const float* z, long long M, int C, int pitch, const f
     set_error("yb_bn_silu_train_forward: bad shape");
     return YB_ERR_SHAPE;
   }
-  const int slabs = (int)((M + BN_ROWS_PER_BLOCK - 1) / BN_ROWS_PER_BLOCK);
+  const int rpb = bn_rows_per_block(M);
+  const int slabs = (int)((M + rpb - 1) / rpb);
   float* part = nullptr;
   YB_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)slabs * C * sizeof(float), s));
   const dim3 grid((C + BN_TX - 1) / BN_TX, slabs), block(BN_TX, BN_TY);
   const int fb = 128, fg = (C + fb - 1) / fb;
-  bn_partial_kernel<<<grid, block, 0, s>>>(0, act, z, nullptr, M, C, pitch, 0, nullptr, nullptr, nullptr, nullptr, part, nullptr);
+  bn_partial_kernel<<<grid, block, 0, s>>>(0, act, z, nullptr, M, C, pitch, 0, nullptr, nullptr, nullptr, nullptr, part, nullptr, rpb);
   bn_finish_kernel<<<fg, fb, 0, s>>>(0, part, nullptr, slabs, C, M, eps, momentum, save_mean, save_invstd, nullptr, nullptr, nullptr,
                                      nullptr);
-  bn_partial_kernel<<<grid, block, 0, s>>>(1, act, z, nullptr, M, C, pitch, 0, save_mean, nullptr, nullptr, nullptr, part, nullptr);
+  bn_partial_kernel<<<grid, block, 0, s>>>(1, act, z, nullptr, M, C, pitch, 0, save_mean, nullptr, nullptr, nullptr, part, nullptr, rpb);
   bn_finish_kernel<<<fg, fb, 0, s>>>(1, part, nullptr, slabs, C, M, eps, momentum, save_mean, save_invstd, running_mean, running_var,
                                      nullptr, nullptr);
   const long long total = M * C;
@@ -156,12 +163,13 @@ int bn_silu_backward(const float* z, const float* dy, long long M, int C, int pi
     set_error("yb_bn_silu_backward: bad shape");
     return YB_ERR_SHAPE;
   }
-  const int slabs = (int)((M + BN_ROWS_PER_BLOCK - 1) / BN_ROWS_PER_BLOCK);
+  const int rpb = bn_rows_per_block(M);
+  const int slabs = (int)((M + rpb - 1) / rpb);
   float* part = nullptr;
   YB_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)2 * slabs * C * sizeof(float), s));
   const dim3 grid((C + BN_TX - 1) / BN_TX, slabs), block(BN_TX, BN_TY);
   bn_partial_kernel<<<grid, block, 0, s>>>(2, act, z, dy, M, C, pitch, dpitch, save_mean, save_invstd, gamma, beta, part,
-                                          part + (size_t)slabs * C);
+                                          part + (size_t)slabs * C, rpb);
   bn_finish_kernel<<<(C + 127) / 128, 128, 0, s>>>(2, part, part + (size_t)slabs * C, slabs, C, M, 0.f, 0.f, nullptr, nullptr, nullptr,
                                                    nullptr, dgamma, dbeta);
   const long long total = M * C;

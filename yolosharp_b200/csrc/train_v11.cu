@@ -276,6 +276,210 @@ __global__ void __launch_bounds__(AT_THREADS) attn_backward_kv_kernel(const floa
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tiled attention (the path that runs for the network's shapes: N = 400 tokens at 640 x 640, kd = 32, hd = 64).
+// The row kernels above launch one CTA per (token, head, image) and every CTA streams the head's whole K and V from
+// L2 (25 600 CTAs x 150 KB for one YOLOv11s layer at batch 16: 13 ms forward + backward).  Here a CTA owns a tile of
+// AT_T = 16 tokens of one (head, image) and keeps the head's K and V (or Q and dO) in shared memory:
+//   row strides kd + 1 / hd + 1 make both access patterns - lanes over tokens (score / dP dot products) and lanes
+//   over channels (P.V, dS.K accumulations) - bank-conflict free;  8 warps, two token rows per warp share every
+//   shared-memory operand they read.  Same arithmetic order per output as the row kernels (sequential over the
+//   reduction index), same saved statistics.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int AT_T = 16;
+constexpr int ATT_THREADS = 256;  // 8 warps x 2 rows
+
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// rows of one head of a (B, N, nh, dim) tensor -> shared memory with row stride `ld`
+__device__ __forceinline__ void load_head(float* dst, const float* src, int b, int h, int N, int nh, int dim, int ld, int row0,
+                                          int rows) {
+  for (int idx = threadIdx.x; idx < rows * dim; idx += ATT_THREADS) {
+    const int r = idx / dim, d = idx - r * dim;
+    const int tok = row0 + r;
+    dst[r * ld + d] = tok < N ? src[(((size_t)b * N + tok) * nh + h) * dim + d] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS) attn_forward_tiled(const float* __restrict__ q, const float* __restrict__ k,
+                                                                  const float* __restrict__ v, float* __restrict__ out,
+                                                                  float* __restrict__ row_max, float* __restrict__ row_sum, int N,
+                                                                  int nh, int kd, int hd, float scale) {
+  extern __shared__ float sm[];
+  const int ldk = kd + 1, ldv = hd + 1;
+  float* Ks = sm;                  // [N][kd + 1]
+  float* Vs = Ks + (size_t)N * ldk;  // [N][hd + 1]
+  float* Qs = Vs + (size_t)N * ldv;  // [AT_T][kd]
+  float* Ps = Qs + AT_T * kd;      // [AT_T][N]
+  const int i0 = blockIdx.x * AT_T, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  load_head(Ks, k, b, h, N, nh, kd, ldk, 0, N);
+  load_head(Vs, v, b, h, N, nh, hd, ldv, 0, N);
+  load_head(Qs, q, b, h, N, nh, kd, kd, i0, AT_T);
+  __syncthreads();
+  const int r0 = warp * 2, r1 = r0 + 1;
+  float* p0 = Ps + (size_t)r0 * N;
+  float* p1 = Ps + (size_t)r1 * N;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  for (int j = lane; j < N; j += 32) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int d = 0; d < kd; d++) {
+      const float kv = Ks[j * ldk + d];
+      s0 = fmaf(Qs[r0 * kd + d], kv, s0);
+      s1 = fmaf(Qs[r1 * kd + d], kv, s1);
+    }
+    s0 *= scale; s1 *= scale;
+    p0[j] = s0; p1[j] = s1;
+    m0 = fmaxf(m0, s0); m1 = fmaxf(m1, s1);
+  }
+  m0 = warp_max(m0); m1 = warp_max(m1);
+  float l0 = 0.f, l1 = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    const float e0 = expf(p0[j] - m0), e1 = expf(p1[j] - m1);
+    p0[j] = e0; p1[j] = e1;
+    l0 += e0; l1 += e1;
+  }
+  l0 = warp_sum(l0); l1 = warp_sum(l1);
+  __syncwarp();
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  for (int d = lane; d < hd; d += 32) {
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < N; j++) {
+      const float vv = Vs[j * ldv + d];
+      o0 = fmaf(p0[j], vv, o0);
+      o1 = fmaf(p1[j], vv, o1);
+    }
+    if (i0 + r0 < N) out[(((size_t)b * N + i0 + r0) * nh + h) * hd + d] = o0 * inv0;
+    if (i0 + r1 < N) out[(((size_t)b * N + i0 + r1) * nh + h) * hd + d] = o1 * inv1;
+  }
+  if (lane == 0 && row_max) {
+    if (i0 + r0 < N) { row_max[((size_t)b * nh + h) * N + i0 + r0] = m0; row_sum[((size_t)b * nh + h) * N + i0 + r0] = l0; }
+    if (i0 + r1 < N) { row_max[((size_t)b * nh + h) * N + i0 + r1] = m1; row_sum[((size_t)b * nh + h) * N + i0 + r1] = l1; }
+  }
+}
+
+// per query tile: D_i = sum_j p_ij dP_ij, dS_ij = p_ij (dP_ij - D_i), dQ_i = scale sum_j dS_ij k_j
+__global__ void __launch_bounds__(ATT_THREADS) attn_backward_q_tiled(const float* __restrict__ q, const float* __restrict__ k,
+                                                                     const float* __restrict__ v, const float* __restrict__ dout,
+                                                                     const float* __restrict__ row_max, const float* __restrict__ row_sum,
+                                                                     float* __restrict__ row_d, float* __restrict__ dq, int N, int nh,
+                                                                     int kd, int hd, float scale) {
+  extern __shared__ float sm[];
+  const int ldk = kd + 1, ldv = hd + 1;
+  float* Ks = sm;
+  float* Vs = Ks + (size_t)N * ldk;
+  float* Qs = Vs + (size_t)N * ldv;  // [AT_T][kd]
+  float* Os = Qs + AT_T * kd;        // [AT_T][hd] dO rows
+  float* Ps = Os + AT_T * hd;        // [AT_T][N]
+  const int i0 = blockIdx.x * AT_T, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  load_head(Ks, k, b, h, N, nh, kd, ldk, 0, N);
+  load_head(Vs, v, b, h, N, nh, hd, ldv, 0, N);
+  load_head(Qs, q, b, h, N, nh, kd, kd, i0, AT_T);
+  load_head(Os, dout, b, h, N, nh, hd, hd, i0, AT_T);
+  __syncthreads();
+  for (int rr = 0; rr < 2; rr++) {
+    const int r = warp * 2 + rr, i = i0 + r;
+    if (i >= N) continue;  // warp-uniform
+    const size_t st = ((size_t)b * nh + h) * N + i;
+    const float mx = row_max[st], inv = 1.0f / row_sum[st];
+    float* pr = Ps + (size_t)r * N;
+    float dsum = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < kd; d++) s = fmaf(Qs[r * kd + d], Ks[j * ldk + d], s);
+      for (int d = 0; d < hd; d++) dp = fmaf(Os[r * hd + d], Vs[j * ldv + d], dp);
+      const float pj = expf(s * scale - mx) * inv;
+      pr[j] = pj;
+      dsum = fmaf(pj, dp, dsum);
+    }
+    const float D = warp_sum(dsum);
+    for (int j = lane; j < N; j += 32) {
+      float dp = 0.f;
+      for (int d = 0; d < hd; d++) dp = fmaf(Os[r * hd + d], Vs[j * ldv + d], dp);
+      pr[j] = pr[j] * (dp - D);
+    }
+    __syncwarp();
+    for (int d = lane; d < kd; d += 32) {
+      float a = 0.f;
+      for (int j = 0; j < N; j++) a = fmaf(pr[j], Ks[j * ldk + d], a);
+      dq[(((size_t)b * N + i) * nh + h) * kd + d] = a * scale;
+    }
+    if (lane == 0) row_d[st] = D;
+  }
+}
+
+// per key tile: dV_j = sum_i p_ij dO_i, dK_j = scale sum_i dS_ij q_i
+__global__ void __launch_bounds__(ATT_THREADS) attn_backward_kv_tiled(const float* __restrict__ q, const float* __restrict__ k,
+                                                                      const float* __restrict__ v, const float* __restrict__ dout,
+                                                                      const float* __restrict__ row_max, const float* __restrict__ row_sum,
+                                                                      const float* __restrict__ row_d, float* __restrict__ dk,
+                                                                      float* __restrict__ dv, int N, int nh, int kd, int hd, float scale) {
+  extern __shared__ float sm[];
+  const int ldk = kd + 1, ldv = hd + 1;
+  float* Qs = sm;                       // [N][kd + 1] all queries of the head
+  float* Os = Qs + (size_t)N * ldk;     // [N][hd + 1] all dO rows
+  float* St = Os + (size_t)N * ldv;     // [3][N] row max | 1 / row sum | D
+  float* Kt = St + 3 * (size_t)N;       // [AT_T][kd]
+  float* Vt = Kt + AT_T * kd;           // [AT_T][hd]
+  float* Ps = Vt + AT_T * hd;           // [AT_T][N]
+  const int j0 = blockIdx.x * AT_T, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  load_head(Qs, q, b, h, N, nh, kd, ldk, 0, N);
+  load_head(Os, dout, b, h, N, nh, hd, ldv, 0, N);
+  load_head(Kt, k, b, h, N, nh, kd, kd, j0, AT_T);
+  load_head(Vt, v, b, h, N, nh, hd, hd, j0, AT_T);
+  for (int i = threadIdx.x; i < N; i += ATT_THREADS) {
+    const size_t st = ((size_t)b * nh + h) * N + i;
+    St[i] = row_max[st];
+    St[N + i] = 1.0f / row_sum[st];
+    St[2 * N + i] = row_d[st];
+  }
+  __syncthreads();
+  for (int rr = 0; rr < 2; rr++) {
+    const int r = warp * 2 + rr, j = j0 + r;
+    if (j >= N) continue;  // warp-uniform
+    float* pr = Ps + (size_t)r * N;
+    for (int i = lane; i < N; i += 32) {
+      float s = 0.f;
+      for (int d = 0; d < kd; d++) s = fmaf(Qs[i * ldk + d], Kt[r * kd + d], s);
+      pr[i] = expf(s * scale - St[i]) * St[N + i];
+    }
+    __syncwarp();
+    for (int d = lane; d < hd; d += 32) {
+      float a = 0.f;
+      for (int i = 0; i < N; i++) a = fmaf(pr[i], Os[i * ldv + d], a);
+      dv[(((size_t)b * N + j) * nh + h) * hd + d] = a;
+    }
+    __syncwarp();
+    for (int i = lane; i < N; i += 32) {
+      float dp = 0.f;
+      for (int d = 0; d < hd; d++) dp = fmaf(Os[i * ldv + d], Vt[r * hd + d], dp);
+      pr[i] = pr[i] * (dp - St[2 * N + i]);
+    }
+    __syncwarp();
+    for (int d = lane; d < kd; d += 32) {
+      float a = 0.f;
+      for (int i = 0; i < N; i++) a = fmaf(pr[i], Qs[i * ldk + d], a);
+      dk[(((size_t)b * N + j) * nh + h) * kd + d] = a * scale;
+    }
+  }
+}
+
+static size_t attn_tiled_smem(int N, int kd, int hd, int which) {  // floats; which: 0 forward, 1 backward q, 2 backward kv
+  const size_t heads = (size_t)N * (kd + 1) + (size_t)N * (hd + 1);
+  if (which == 0) return heads + (size_t)AT_T * kd + (size_t)AT_T * N;
+  if (which == 1) return heads + (size_t)AT_T * (kd + hd) + (size_t)AT_T * N;
+  return heads + 3 * (size_t)N + (size_t)AT_T * (kd + hd) + (size_t)AT_T * N;
+}
+static bool attn_tiled_ok(int N, int kd, int hd) { return attn_tiled_smem(N, kd, hd, 2) * sizeof(float) <= 200 * 1024; }
+
 static int attn_check(int B, int N, int nh, int kd, int hd, size_t smem_floats) {
   if (B <= 0 || N <= 0 || nh <= 0 || kd <= 0 || hd <= 0) { set_error("attention: bad shape"); return YB_ERR_SHAPE; }
   if (smem_floats * sizeof(float) > 200 * 1024) { set_error("attention: N too large for the shared-memory score rows"); return YB_ERR_NOT_IMPLEMENTED; }
@@ -286,6 +490,13 @@ int attention_forward_f32(const float* q, const float* k, const float* v, int B,
                           float* out, float* row_max, float* row_sum, cudaStream_t s) {
   const size_t smem = (size_t)N + kd;
   if (int rc = attn_check(B, N, nh, kd, hd, smem)) return rc;
+  if (attn_tiled_ok(N, kd, hd)) {
+    YB_CUDA_CHECK(cudaFuncSetAttribute(attn_forward_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attn_forward_tiled<<<dim3((N + AT_T - 1) / AT_T, nh, B), ATT_THREADS, attn_tiled_smem(N, kd, hd, 0) * sizeof(float), s>>>(
+        q, k, v, out, row_max, row_sum, N, nh, kd, hd, scale);
+    YB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   YB_CUDA_CHECK(cudaFuncSetAttribute(attn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   attn_forward_kernel<<<dim3(N, nh, B), AT_THREADS, smem * sizeof(float), s>>>(q, k, v, out, row_max, row_sum, N, nh, kd, hd, scale);
   YB_CUDA_CHECK(cudaGetLastError());
@@ -301,7 +512,16 @@ int attention_backward_f32(const float* q, const float* k, const float* v, const
   YB_CUDA_CHECK(cudaMallocAsync((void**)&stats, (3 * n + (size_t)B * N * nh * hd) * sizeof(float), s));
   float* tmp_out = stats + 3 * n;  // the forward output is recomputed only for its row statistics
   int rc = attention_forward_f32(q, k, v, B, N, nh, kd, hd, scale, tmp_out, stats, stats + n, s);
-  if (!rc) {
+  if (!rc && attn_tiled_ok(N, kd, hd)) {
+    cudaFuncSetAttribute(attn_backward_q_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(attn_backward_kv_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const dim3 grid((N + AT_T - 1) / AT_T, nh, B);
+    attn_backward_q_tiled<<<grid, ATT_THREADS, attn_tiled_smem(N, kd, hd, 1) * sizeof(float), s>>>(q, k, v, dout, stats, stats + n,
+                                                                                                   stats + 2 * n, dq, N, nh, kd, hd, scale);
+    attn_backward_kv_tiled<<<grid, ATT_THREADS, attn_tiled_smem(N, kd, hd, 2) * sizeof(float), s>>>(q, k, v, dout, stats, stats + n,
+                                                                                                    stats + 2 * n, dk, dv, N, nh, kd, hd, scale);
+    if (cudaGetLastError() != cudaSuccess) { set_error("attention backward launch failed"); rc = YB_ERR_CUDA; }
+  } else if (!rc) {
     cudaFuncSetAttribute(attn_backward_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(attn_backward_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attn_backward_q_kernel<<<dim3(N, nh, B), AT_THREADS, smem_q * sizeof(float), s>>>(q, k, v, dout, stats, stats + n, stats + 2 * n,

@@ -206,6 +206,20 @@ def nms(pred, conf_thres=0.25, iou_thres=0.45, max_det=300, nc=0, max_nms=30000,
     return dets, counts, keep
 
 
+def topk_postprocess(pred, max_det=300, nc=0, agnostic=False, stream=None):
+    """yb_topk_postprocess (end2end heads, Head.cs:117-127, 175-196): pred CUDA float32 (B, 4+nc, A) ->
+    rows (B, k, 6) [x, y, w, h, score, class] sorted by score, anchor index of every row (B, k)."""
+    assert pred.is_cuda and pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3
+    B, Cc, A = pred.shape
+    ncc = nc or Cc - 4
+    k = min(max_det, A)
+    out = torch.empty((B, k, 6), dtype=torch.float32, device=pred.device)
+    idx = torch.empty((B, k), dtype=torch.int32, device=pred.device)
+    L.check(L.lib().yb_topk_postprocess(C.c_void_p(pred.data_ptr()), B, Cc, A, ncc, max_det, 1 if agnostic else 0,
+                                        C.c_void_p(out.data_ptr()), C.c_void_p(idx.data_ptr()), _stream_ptr(stream)))
+    return out, idx
+
+
 def masks(proto, dets, counts, height, width, stream=None, out=None):
     """yb_masks: proto (B,32,mh,mw) f32, dets (B,max_det,38), counts -> uint8 (B,max_det,H,W)."""
     B, nm, mh, mw = proto.shape

@@ -68,7 +68,17 @@ class KernelOps:
 
     def _tc_ok(self, x, w, stride, pad):
         Cout, Cin, k, _ = w.shape
-        return self.tc and self.E.conv_tc_supported(Cin, Cout, k, stride, pad, x.shape[1], x.shape[2])
+        return self.tc and self.E.conv_tc_supported((Cin + 7) // 8 * 8, Cout, k, stride, pad, x.shape[1], x.shape[2])
+
+    @staticmethod
+    def _pad8(x, w):
+        """The 3-channel stem (Yolo.cs:53): input channels zero-padded to 8 so that it also runs on the tensor cores
+        (zero channels contribute exact zeros; the padded gradient columns are dropped)."""
+        Cin = w.shape[1]
+        cp = (Cin + 7) // 8 * 8
+        if cp == Cin:
+            return x.contiguous(), w.contiguous(), Cin
+        return torch.nn.functional.pad(x, (0, cp - Cin)), torch.nn.functional.pad(w, (0, 0, 0, 0, 0, cp - Cin)), Cin
 
     def _ws(self, x):
         if self.ws is None:
@@ -77,12 +87,19 @@ class KernelOps:
 
     def conv_forward(self, x, w, bias, stride, pad):
         if self._tc_ok(x, w, stride, pad):
-            return self.E.conv_forward_tc(x.contiguous(), w.contiguous(), bias, stride, pad, ws=self._ws(x))
+            xp, wp, _ = self._pad8(x, w)
+            return self.E.conv_forward_tc(xp, wp, bias, stride, pad, ws=self._ws(x))
         return self.E.conv_forward(x, w, bias, stride, pad)
 
-    def conv_backward(self, x, dz, w, stride, pad):
+    def conv_backward(self, x, dz, w, stride, pad, need_dx=True):
+        """-> (dx or None when the caller does not need it (the network input), dw)."""
         if self._tc_ok(x, w, stride, pad):
-            return self.E.conv_backward_tc(x.contiguous(), dz.contiguous(), w.contiguous(), stride, pad, ws=self._ws(x))
+            xp, wp, Cin = self._pad8(x, w)
+            dx, dw = self.E.conv_backward_tc(xp, dz.contiguous(), wp, stride, pad, ws=self._ws(x), need_dx=need_dx)
+            if wp.shape[1] != Cin:
+                dw = dw[:, :Cin].contiguous()
+                dx = dx[..., :Cin].contiguous() if dx is not None else None
+            return dx, dw
         return self.E.conv_backward(x, dz.contiguous(), w, stride, pad)
 
     def bn_silu_forward(self, z, gamma, beta, rm, rv, act):
@@ -140,6 +157,7 @@ class _Conv:
 
     def __init__(self, net, name, k=1, s=1, act=True):
         self.net, self.name, self.k, self.s, self.act = net, name, k, s, act
+        self.need_dx = True  # False for the first layer: nothing consumes the gradient of the images
 
     def forward(self, x):
         P, ops = self.net.P, self.net.ops
@@ -154,7 +172,7 @@ class _Conv:
         P, ops = self.net.P, self.net.ops
         dz, dg, db = ops.bn_silu_backward(self.z, dy, P.p(self.name + ".bn.weight"), P.p(self.name + ".bn.bias"), self.mean,
                                           self.invstd, self.act)
-        dx, dw = ops.conv_backward(self.x, dz, P.p(self.name + ".conv.weight"), self.s, self.k // 2)
+        dx, dw = ops.conv_backward(self.x, dz, P.p(self.name + ".conv.weight"), self.s, self.k // 2, need_dx=self.need_dx)
         P.g(self.name + ".conv.weight").copy_(dw)
         P.g(self.name + ".bn.weight").copy_(dg)
         P.g(self.name + ".bn.bias").copy_(db)
@@ -312,6 +330,7 @@ class TrainStepV8:
             _C2f(N, "model.15", w[2], dp[0], False), _Conv(N, "model.16", 3, 2), "cat", _C2f(N, "model.18", w[3], dp[0], False),
             _Conv(N, "model.19", 3, 2), "cat", _C2f(N, "model.21", w[4], dp[0], False),
         ]
+        self.layers[0].need_dx = False
         self.detect = _Detect(N, "model.22", nc, (w[2], w[3], w[4]))
         self.output_indexs = (4, 6, 9, 12, 15, 18, 21)  # Yolo.cs:13
         self.concat_index = (1, 0, 3, 2)                 # Yolo.cs:14

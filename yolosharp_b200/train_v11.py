@@ -270,6 +270,7 @@ class TrainStepV11(TrainStepV8):
             _C3k2(N, "model.16", w[2], n, c3k), _Conv(N, "model.17", 3, 2), "cat", _C3k2(N, "model.19", w[3], n, c3k),
             _Conv(N, "model.20", 3, 2), "cat", _C3k2(N, "model.22", w[4], n, True),
         ]
+        self.layers[0].need_dx = False
         self.detect = _DetectV11(N, "model.23", nc, (w[2], w[3], w[4]))
         self.output_indexs = (4, 6, 10, 13, 16, 19, 22)  # Yolo.cs:202
         self.concat_index = (1, 0, 3, 2)
