@@ -52,3 +52,20 @@ for p, q in zip(la, lb):
     print(f"{p.name:28s} {str(tuple(p.z.shape)):22s} {float(d.pow(2).mean().sqrt() / rms):.2e} {float(d.abs().max() / rms):.2e}")
 for u, v, n in ((oa[0], ob[0], "boxes"), (oa[1], ob[1], "scores")):
     print(n, float((v - u).pow(2).mean().sqrt() / u.pow(2).mean().sqrt()), float((v - u).abs().max() / u.pow(2).mean().sqrt()))
+
+# ---- backward: both paths driven by the fp32 path's loss gradient ----
+from bench import synth_targets  # noqa: E402
+targets = synth_targets(B, 5)
+items, gb, gs = a.ops.detection_loss(oa[0], oa[1], targets, H, W)
+a.P.grad.zero_(); b.P.grad.zero_()
+a.backward(gb, gs); b.backward(gb, gs)
+ga, gt = a.P.grad.double(), b.P.grad.double()
+print(f"# flat gradient: rel L2 {float((gt - ga).norm() / ga.norm()):.3e} cosine {float((gt * ga).sum() / (gt.norm() * ga.norm())):.6f}")
+print("# per conv weight (network order): rel L2 of the gradient tensor, its share of the flat gradient norm")
+tot = float(ga.norm())
+for p in la:
+    for suffix in (".conv.weight",):
+        k = p.name + suffix
+        if k in a.P.off:
+            u, v = a.P.g(k).double(), b.P.g(k).double()
+            print(f"{k:40s} {float((v - u).norm() / u.norm().clamp_min(1e-30)):.2e} {float(u.norm()) / tot:.2e}")

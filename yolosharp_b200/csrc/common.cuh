@@ -91,6 +91,22 @@ int launch_pixel_shuffle2(const View& in, const View& out, int B, cudaStream_t s
 template <typename T>
 int launch_attention(const View& qkv, const View& out, const View& vout, int B, int nh, int kd, int hd, float scale,
                      cudaStream_t s);
+// Tiled attention forward for kd = 32, hd = 64 (every YOLOv11 size: num_heads = c / 64, key_dim = 32), shared by the
+// inference engine (T = __half / float, q|k|v interleaved per head in the qkv conv output) and the training step (fp32,
+// separate q, k, v): element strides describe where token t of head h of image b lives.
+struct AttnIO {
+  const void *q, *k, *v;          // element type T
+  long long in_tok, in_img;       // element strides between tokens / images of q and k
+  long long v_tok, v_img;         // the same for v
+  long long q_head, k_head, v_head;  // element offset of head h: h * q_head etc. (already includes nothing else)
+  void* out;                      // type T, (B, N, nh * 64)-like with out_tok / out_img / head offset h * 64
+  long long out_tok, out_img;
+  void* vout;                     // optional dense copy of v (same addressing as out), type T
+  float *row_max, *row_sum;       // optional (B, nh, N) fp32 softmax statistics for the backward pass
+};
+template <typename T>
+int launch_attention_tiled_32x64(const AttnIO& io, int B, int N, int nh, float scale, cudaStream_t s);
+bool attention_tiled_32x64_fits(int N);
 // proto (B,h,w,32) NHWC T -> (B,32,h,w) fp32
 template <typename T>
 int launch_proto_out(const View& in, float* out, int B, cudaStream_t s);

@@ -164,9 +164,101 @@ __global__ void dwconv3x3_kernel(ConvParams p, size_t total) {
   reinterpret_cast<T*>(p.out.base)[pix * p.out.pitch + p.out.coff + c] = from_f<T>(v);
 }
 
+// fp16 path, channels in groups of 8 (one 16-byte vector): a thread produces DW_PIX adjacent output pixels of one row
+// for 8 channels from a 3 x (DW_PIX + 2) window of 16-byte loads (4.5 loads per output instead of 9 scalar ones), the
+// 72 weights of its channel group in registers.  Consecutive threads = consecutive channel groups: every load / store
+// instruction of a warp covers whole contiguous pixel rows.  (The scalar kernel above ran the YOLOv11 head's depthwise
+// convs at 4 % of the HBM roofline: 1.2 ms of the 4.7 ms YOLOv11s forward at batch 32.)
+constexpr int DW_PIX = 4;
+__global__ void __launch_bounds__(256) dwconv3x3_h8_kernel(ConvParams p, int groups8, int wtiles, int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = idx % groups8;
+  int t = idx / groups8;
+  const int wt = t % wtiles; t /= wtiles;
+  const int ho = t % p.Ho;
+  const int n = t / p.Ho;
+  const int c = g * 8;
+  const int wo0 = wt * DW_PIX;
+  const __half* in = reinterpret_cast<const __half*>(p.in.base) + p.in.coff + c;
+  const float* w = reinterpret_cast<const float*>(p.w);
+  float acc[DW_PIX][8];
+#pragma unroll
+  for (int q = 0; q < DW_PIX; q++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[q][j] = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; kh++) {
+    const int hi = ho + kh - 1;
+    if (hi < 0 || hi >= p.in.H) continue;
+    float wk[3][8];
+#pragma unroll
+    for (int kw = 0; kw < 3; kw++) {
+      const float4 a = *reinterpret_cast<const float4*>(w + (kh * 3 + kw) * p.Cout + c);
+      const float4 b = *reinterpret_cast<const float4*>(w + (kh * 3 + kw) * p.Cout + c + 4);
+      wk[kw][0] = a.x; wk[kw][1] = a.y; wk[kw][2] = a.z; wk[kw][3] = a.w;
+      wk[kw][4] = b.x; wk[kw][5] = b.y; wk[kw][6] = b.z; wk[kw][7] = b.w;
+    }
+    const __half* row = in + (size_t)(n * p.in.H + hi) * p.in.W * p.in.pitch;
+#pragma unroll
+    for (int col = 0; col < DW_PIX + 2; col++) {
+      const int wi = wo0 + col - 1;
+      if (wi < 0 || wi >= p.in.W) continue;
+      const int4 v = *reinterpret_cast<const int4*>(row + (size_t)wi * p.in.pitch);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 4; j++) { const float2 f = __half22float2(h[j]); x[2 * j] = f.x; x[2 * j + 1] = f.y; }
+#pragma unroll
+      for (int kw = 0; kw < 3; kw++) {
+        const int q = col - kw;  // output pixel this column feeds through tap kw
+        if (q >= 0 && q < DW_PIX) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[q][j] = fmaf(x[j], wk[kw][j], acc[q][j]);
+        }
+      }
+    }
+  }
+  const float4 b0 = *reinterpret_cast<const float4*>(p.bias + c), b1 = *reinterpret_cast<const float4*>(p.bias + c + 4);
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const __half* res = reinterpret_cast<const __half*>(p.res.base);
+#pragma unroll
+  for (int q = 0; q < DW_PIX; q++) {
+    const int wo = wo0 + q;
+    if (wo >= p.Wo) break;
+    const size_t pix = ((size_t)n * p.Ho + ho) * p.Wo + wo;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      v[j] = acc[q][j] + bb[j];
+      if (p.act == ACT_SILU) v[j] = silu_f(v[j]);
+    }
+    if (res) {
+      const int4 rv = *reinterpret_cast<const int4*>(res + pix * p.res.pitch + p.res.coff + c);
+      const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+      for (int j = 0; j < 4; j++) { const float2 f = __half22float2(rh[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+    }
+    int4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; j++) oh[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<int4*>(reinterpret_cast<__half*>(p.out.base) + pix * p.out.pitch + p.out.coff + c) = o;
+  }
+}
+
 template <typename T>
 int launch_dwconv3x3(const ConvParams& p, cudaStream_t s) {
   const size_t total = (size_t)p.B * p.Ho * p.Wo * p.Cout;
+  if (sizeof(T) == 2 && p.Cout % 8 == 0 && p.in.pitch % 8 == 0 && p.in.coff % 8 == 0 && p.out.pitch % 8 == 0 && p.out.coff % 8 == 0 &&
+      (!p.res.base || (p.res.pitch % 8 == 0 && p.res.coff % 8 == 0)) && p.stride == 1 && p.Ho == p.in.H && p.Wo == p.in.W &&
+      total / 8 < (size_t)1 << 30) {
+    const int groups8 = p.Cout / 8, wtiles = (p.Wo + DW_PIX - 1) / DW_PIX;
+    const int tot = p.B * p.Ho * wtiles * groups8;
+    dwconv3x3_h8_kernel<<<(tot + 255) / 256, 256, 0, s>>>(p, groups8, wtiles, tot);
+    YB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   dwconv3x3_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p, total);
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -672,6 +764,144 @@ __global__ void __launch_bounds__(256) attention_kernel(View qkv, View out, View
   }
 }
 
+// Tiled variant for kd = 32, hd = 64 (all YOLOv11 sizes), used when a head's K and V fit in shared memory (N <= 416
+// tokens: every 640 x 640 model).  The row kernel above re-streams K and V through shared memory for every 8 query rows
+// (6 400 CTAs x 77 KB and 100 block-wide barriers each for YOLOv11s at batch 32: 0.88 ms, 19 % of the forward).  A first
+// tiled version with scalar shared-memory reads was no faster (1.0 ms): three LDS per two FMAs made it shared-memory
+// bound.  This one is register-blocked:
+//   * a CTA owns 16 query rows of one (head, image); K (row stride 36 floats) and V (stride 64) stay resident as fp32
+//   * scores: a warp owns 2 query rows, held in 64 registers; a lane owns one key per block of 32 and reads its K row
+//     with 8 conflict-free LDS.128 -> 64 FMAs per 8 loads
+//   * P.V: a lane owns channels 2*lane, 2*lane+1 for both rows; per 4 keys: 4 LDS.64 of V + 2 broadcast LDS.128 of P
+//     for 16 FMAs
+// Per-output summation order is unchanged (sequential over d, then over j).
+constexpr int ATI_T = 16, ATI_KD = 32, ATI_HD = 64, ATI_LDK = 36;
+__device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) attention_tiled_32x64_kernel(AttnIO io, int N, int nh, float scale) {
+  extern __shared__ __align__(16) float at_smem[];
+  const int NK = (N + 31) & ~31, NP = (N + 3) & ~3;
+  float* Ks = at_smem;                          // [NK][36], rows >= N zero
+  float* Vs = Ks + (size_t)NK * ATI_LDK;        // [NP][64], rows >= N zero
+  float* Qs = Vs + (size_t)NP * ATI_HD;         // [16][32]
+  float* Ps = Qs + ATI_T * ATI_KD;              // [16][NP]
+  const int i0 = blockIdx.x * ATI_T, head = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* qb = reinterpret_cast<const T*>(io.q) + (size_t)b * io.in_img + (size_t)head * io.q_head;
+  const T* kb = reinterpret_cast<const T*>(io.k) + (size_t)b * io.in_img + (size_t)head * io.k_head;
+  const T* vb = reinterpret_cast<const T*>(io.v) + (size_t)b * io.v_img + (size_t)head * io.v_head;
+  T* vo = reinterpret_cast<T*>(io.vout);
+  // fill: 4 channels per thread and step
+  for (int t = threadIdx.x; t < NK * (ATI_KD / 4); t += 256) {
+    const int j = t >> 3, d = (t & 7) * 4;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < N) {
+      const T* src = kb + (size_t)j * io.in_tok + d;
+      f = make_float4(to_f<T>(src[0]), to_f<T>(src[1]), to_f<T>(src[2]), to_f<T>(src[3]));
+    }
+    *reinterpret_cast<float4*>(Ks + (size_t)j * ATI_LDK + d) = f;
+  }
+  for (int t = threadIdx.x; t < NP * (ATI_HD / 4); t += 256) {
+    const int j = t >> 4, d = (t & 15) * 4;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < N) {
+      const T* src = vb + (size_t)j * io.v_tok + d;
+      f = make_float4(to_f<T>(src[0]), to_f<T>(src[1]), to_f<T>(src[2]), to_f<T>(src[3]));
+      if (vo && j >= i0 && j < i0 + ATI_T) {  // the dense copy of v the positional-encoding conv reads
+        T* dst = vo + (size_t)b * io.out_img + (size_t)j * io.out_tok + head * ATI_HD + d;
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+      }
+    }
+    *reinterpret_cast<float4*>(Vs + (size_t)j * ATI_HD + d) = f;
+  }
+  for (int t = threadIdx.x; t < ATI_T * ATI_KD; t += 256) {
+    const int r = t >> 5, d = t & 31;
+    Qs[t] = (i0 + r < N) ? to_f<T>(qb[(size_t)(i0 + r) * io.in_tok + d]) : 0.f;
+  }
+  __syncthreads();
+  const int r0 = warp * 2, r1 = r0 + 1;
+  float* p0 = Ps + (size_t)r0 * NP;
+  float* p1 = Ps + (size_t)r1 * NP;
+  float q0[ATI_KD], q1[ATI_KD];
+#pragma unroll
+  for (int d = 0; d < ATI_KD; d += 4) {
+    const float4 a = lds128(Qs + r0 * ATI_KD + d), c = lds128(Qs + r1 * ATI_KD + d);
+    q0[d] = a.x; q0[d + 1] = a.y; q0[d + 2] = a.z; q0[d + 3] = a.w;
+    q1[d] = c.x; q1[d + 1] = c.y; q1[d + 2] = c.z; q1[d + 3] = c.w;
+  }
+  float m0 = -INFINITY, m1 = -INFINITY;
+  for (int j = lane; j < NK; j += 32) {
+    const float* kr = Ks + (size_t)j * ATI_LDK;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < ATI_KD; d += 4) {
+      const float4 kv = lds128(kr + d);
+      s0 = fmaf(q0[d], kv.x, s0); s1 = fmaf(q1[d], kv.x, s1);
+      s0 = fmaf(q0[d + 1], kv.y, s0); s1 = fmaf(q1[d + 1], kv.y, s1);
+      s0 = fmaf(q0[d + 2], kv.z, s0); s1 = fmaf(q1[d + 2], kv.z, s1);
+      s0 = fmaf(q0[d + 3], kv.w, s0); s1 = fmaf(q1[d + 3], kv.w, s1);
+    }
+    if (j < N) {
+      s0 *= scale; s1 *= scale;
+      p0[j] = s0; p1[j] = s1;
+      m0 = fmaxf(m0, s0); m1 = fmaxf(m1, s1);
+    } else if (j < NP) {
+      p0[j] = -INFINITY; p1[j] = -INFINITY;  // exp -> 0: padded keys contribute nothing
+    }
+  }
+  for (int o = 16; o; o >>= 1) { m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o)); }
+  float l0 = 0.f, l1 = 0.f;
+  for (int j = lane; j < NP; j += 32) {
+    const float e0 = expf(p0[j] - m0), e1 = expf(p1[j] - m1);
+    p0[j] = e0; p1[j] = e1;
+    l0 += e0; l1 += e1;
+  }
+  for (int o = 16; o; o >>= 1) { l0 += __shfl_xor_sync(0xffffffffu, l0, o); l1 += __shfl_xor_sync(0xffffffffu, l1, o); }
+  __syncwarp();
+  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+  const float* vcol = Vs + 2 * lane;
+  for (int j = 0; j < NP; j += 4) {
+    const float4 pa = lds128(p0 + j), pb = lds128(p1 + j);
+    const float2 v0 = *reinterpret_cast<const float2*>(vcol + (size_t)j * ATI_HD);
+    const float2 v1 = *reinterpret_cast<const float2*>(vcol + (size_t)(j + 1) * ATI_HD);
+    const float2 v2 = *reinterpret_cast<const float2*>(vcol + (size_t)(j + 2) * ATI_HD);
+    const float2 v3 = *reinterpret_cast<const float2*>(vcol + (size_t)(j + 3) * ATI_HD);
+    a00 = fmaf(pa.x, v0.x, a00); a01 = fmaf(pa.x, v0.y, a01); a10 = fmaf(pb.x, v0.x, a10); a11 = fmaf(pb.x, v0.y, a11);
+    a00 = fmaf(pa.y, v1.x, a00); a01 = fmaf(pa.y, v1.y, a01); a10 = fmaf(pb.y, v1.x, a10); a11 = fmaf(pb.y, v1.y, a11);
+    a00 = fmaf(pa.z, v2.x, a00); a01 = fmaf(pa.z, v2.y, a01); a10 = fmaf(pb.z, v2.x, a10); a11 = fmaf(pb.z, v2.y, a11);
+    a00 = fmaf(pa.w, v3.x, a00); a01 = fmaf(pa.w, v3.y, a01); a10 = fmaf(pb.w, v3.x, a10); a11 = fmaf(pb.w, v3.y, a11);
+  }
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  T* ob = reinterpret_cast<T*>(io.out) + (size_t)b * io.out_img + head * ATI_HD + 2 * lane;
+  if (i0 + r0 < N) { T* o = ob + (size_t)(i0 + r0) * io.out_tok; o[0] = from_f<T>(a00 * inv0); o[1] = from_f<T>(a01 * inv0); }
+  if (i0 + r1 < N) { T* o = ob + (size_t)(i0 + r1) * io.out_tok; o[0] = from_f<T>(a10 * inv1); o[1] = from_f<T>(a11 * inv1); }
+  if (lane == 0 && io.row_max) {
+    if (i0 + r0 < N) { io.row_max[((size_t)b * nh + head) * N + i0 + r0] = m0; io.row_sum[((size_t)b * nh + head) * N + i0 + r0] = l0; }
+    if (i0 + r1 < N) { io.row_max[((size_t)b * nh + head) * N + i0 + r1] = m1; io.row_sum[((size_t)b * nh + head) * N + i0 + r1] = l1; }
+  }
+}
+
+static size_t ati_smem_bytes(int N) {
+  const size_t NK = (N + 31) & ~31, NP = (N + 3) & ~3;
+  return (NK * ATI_LDK + NP * ATI_HD + (size_t)ATI_T * ATI_KD + (size_t)ATI_T * NP) * sizeof(float);
+}
+bool attention_tiled_32x64_fits(int N) { return ati_smem_bytes(N) <= 200 * 1024; }
+
+template <typename T>
+int launch_attention_tiled_32x64(const AttnIO& io, int B, int N, int nh, float scale, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    YB_CUDA_CHECK(cudaFuncSetAttribute(attention_tiled_32x64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  attention_tiled_32x64_kernel<T><<<dim3((N + ATI_T - 1) / ATI_T, nh, B), 256, ati_smem_bytes(N), s>>>(io, N, nh, scale);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+template int launch_attention_tiled_32x64<float>(const AttnIO&, int, int, int, float, cudaStream_t);
+template int launch_attention_tiled_32x64<__half>(const AttnIO&, int, int, int, float, cudaStream_t);
+
 template <typename T>
 int launch_attention(const View& qkv, const View& out, const View& vout, int B, int nh, int kd, int hd, float scale,
                      cudaStream_t s) {
@@ -679,6 +909,22 @@ int launch_attention(const View& qkv, const View& out, const View& vout, int B, 
   if (kd > 64 || hd > 128) {
     set_error("attention: key_dim <= 64 and head_dim <= 128 supported");
     return YB_ERR_SHAPE;
+  }
+  {
+    static const bool no_tiled = getenv("YB_ATTN_ROWS") != nullptr;  // experiments: the row-streaming kernel below
+    if (kd == ATI_KD && hd == ATI_HD && attention_tiled_32x64_fits(N) && !no_tiled) {
+      const int per = 2 * kd + hd;
+      AttnIO io;
+      const T* base = reinterpret_cast<const T*>(qkv.base) + qkv.coff;
+      io.q = base; io.k = base + kd; io.v = base + 2 * kd;
+      io.in_tok = io.v_tok = qkv.pitch; io.in_img = io.v_img = (long long)N * qkv.pitch;
+      io.q_head = io.k_head = io.v_head = per;
+      io.out = reinterpret_cast<T*>(out.base) + out.coff; io.out_tok = out.pitch; io.out_img = (long long)N * out.pitch;
+      io.vout = reinterpret_cast<T*>(vout.base) + vout.coff;
+      io.row_max = io.row_sum = nullptr;
+      if (vout.pitch != out.pitch) { set_error("attention: out and v copy must share their pitch"); return YB_ERR_SHAPE; }
+      return launch_attention_tiled_32x64<T>(io, B, N, nh, scale, s);
+    }
   }
   const int nwarps = 8;
   const size_t smem = ((size_t)nwarps * N + 32 * (kd + 1) + 32 * hd) * sizeof(float);

@@ -490,6 +490,16 @@ int attention_forward_f32(const float* q, const float* k, const float* v, int B,
                           float* out, float* row_max, float* row_sum, cudaStream_t s) {
   const size_t smem = (size_t)N + kd;
   if (int rc = attn_check(B, N, nh, kd, hd, smem)) return rc;
+  if (kd == 32 && hd == 64 && attention_tiled_32x64_fits(N)) {  // register-blocked kernel shared with the inference engine
+    AttnIO io;
+    io.q = q; io.k = k; io.v = v;
+    io.in_tok = (long long)nh * kd; io.in_img = (long long)N * nh * kd;
+    io.v_tok = (long long)nh * hd; io.v_img = (long long)N * nh * hd;
+    io.q_head = io.k_head = kd; io.v_head = hd;
+    io.out = out; io.out_tok = (long long)nh * hd; io.out_img = (long long)N * nh * hd;
+    io.vout = nullptr; io.row_max = row_max; io.row_sum = row_sum;
+    return launch_attention_tiled_32x64<float>(io, B, N, nh, scale, s);
+  }
   if (attn_tiled_ok(N, kd, hd)) {
     YB_CUDA_CHECK(cudaFuncSetAttribute(attn_forward_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attn_forward_tiled<<<dim3((N + AT_T - 1) / AT_T, nh, B), ATT_THREADS, attn_tiled_smem(N, kd, hd, 0) * sizeof(float), s>>>(
