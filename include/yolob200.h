@@ -293,6 +293,23 @@ int32_t yb_predict_seg_u8_submit(yb_engine* e, int32_t slot, const uint8_t* imag
 int32_t yb_topk_postprocess(const float* pred, int32_t batch, int32_t channels, int32_t anchors, int32_t nc,
                             int32_t max_det, int32_t agnostic, float* out, int32_t* idx, void* stream);
 
+/* Decode tails of the OBB and Pose heads and the rotated NMS (csrc/heads.cu), fp32.
+ * yb_obb_decode   replaces `Obb._inference` (Modules/Head.cs:410-436 on top of Detect._inference :204-223): DFL expectation
+ *                 of box_logits (B, 4*reg_max, A), angle = (sigmoid(angle_logits (B,1,A)) - 0.25) * pi, `Tal.dist2rbox`
+ *                 (Utils/Tal.cs:389-408) with anchors (2, A) / strides (A), class sigmoid -> out (B, 4 + nc + 1, A)
+ * yb_pose_decode  replaces `Pose.kpts_decode` (Modules/Head.cs:595-609): kpts (B, nk, A) -> out, keypoint_dim 2 or 3
+ * yb_probiou      replaces `Metrics.batch_probiou` (Utils/Metrics.cs:223-254): xywhr (n, 5) x (m, 5) -> (n, m)
+ * yb_nms_rotated  replaces `Ops.nms_rotated(boxes, scores, threshold)` (Utils/Ops.cs:373-401, use_triu): keep (n) int32
+ *                 receives the kept original indices in score order, count (1) their number. All pointers device. */
+int32_t yb_obb_decode(const float* box_logits, const float* cls_logits, const float* angle_logits, const float* anchors,
+                      const float* strides, int32_t batch, int32_t anchors_n, int32_t nc, int32_t reg_max, float* out,
+                      void* stream);
+int32_t yb_pose_decode(const float* kpts, const float* anchors, const float* strides, int32_t batch, int32_t anchors_n,
+                       int32_t nk, int32_t keypoint_dim, float* out, void* stream);
+int32_t yb_probiou(const float* obb1, int32_t n, const float* obb2, int32_t m, float eps, float* out, void* stream);
+int32_t yb_nms_rotated(const float* boxes, const float* scores, int32_t n, float threshold, int32_t* keep, int32_t* count,
+                       void* stream);
+
 /* Validation-side post-processing (csrc/val.cu), batched over the images of a step.
  * yb_box_iou  replaces `Metrics.box_iou(box1, box2)` (Utils/Metrics.cs:16-34): out (n, m) float32, xyxy boxes.
  * yb_match_predictions  replaces the per-image `match_predictions(pred_classes, true_classes, iou)` loop of

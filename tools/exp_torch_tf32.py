@@ -32,9 +32,12 @@ def run(tf32, head_grads=None):
     m.zero_grad()
     _, preds = m(x)
     boxes, scores = preds["boxes"], preds["scores"]
-    if head_grads is None:
-        loss, _ = crit(preds, batch)
-        gb, gs = torch.autograd.grad(loss.sum(), (boxes, scores), retain_graph=True)
+    if head_grads is None:  # the oracle loss is CPU code: differentiate it on detached host copies of the head outputs
+        bc, sc = boxes.detach().cpu().requires_grad_(True), scores.detach().cpu().requires_grad_(True)
+        loss, _ = crit({"boxes": bc, "scores": sc, "feats": [f.detach().cpu() for f in preds["feats"]]},
+                       {k: v.cpu() for k, v in batch.items()})
+        gb, gs = torch.autograd.grad(loss.sum(), (bc, sc))
+        gb, gs = gb.cuda(), gs.cuda()
     else:
         gb, gs = head_grads
     torch.autograd.backward((boxes, scores), (gb, gs))

@@ -37,6 +37,9 @@ __device__ __forceinline__ float silu_grad(float u) {
 // mode 0: sum z                      -> p0
 // mode 1: sum (z - mean)^2           -> p0
 // mode 2: sum g, sum g * xhat        -> p0, p1   (g = dy * SiLU'(gamma*xhat+beta))
+// mode 3: sum (z - K), sum (z - K)^2 -> p0, p1   one pass over z for mean AND variance; K = z[row 0][c] is a shift close to
+//         the mean (a sample of the channel), so var = (S2 - S1^2 / M) / M cancels at most a few bits
+//         (relative error ~ eps * (1 + (K - mean)^2 / var)); the two-pass modes 0 / 1 read every activation twice
 __global__ void __launch_bounds__(BN_TX* BN_TY) bn_partial_kernel(int mode, int act, const float* __restrict__ z, const float* __restrict__ dy,
                                                                 long long M, int C, int pitch, int dpitch,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(BN_TX* BN_TY) bn_partial_kernel(int mode, int 
   const long long r0 = (long long)blockIdx.y * rpb;
   float a0 = 0.f, a1 = 0.f;
   if (c < C) {
-    const float mu = mode ? mean[c] : 0.f;
+    const float mu = mode == 3 ? z[c] : (mode ? mean[c] : 0.f);
     const float is = mode == 2 ? invstd[c] : 0.f, ga = mode == 2 ? gamma[c] : 0.f, be = mode == 2 ? beta[c] : 0.f;
     for (long long r = r0 + threadIdx.y; r < min(M, r0 + rpb); r += BN_TY) {
       const float v = z[r * pitch + c];
@@ -55,6 +58,10 @@ __global__ void __launch_bounds__(BN_TX* BN_TY) bn_partial_kernel(int mode, int 
       } else if (mode == 1) {
         const float d = v - mu;
         a0 += d * d;
+      } else if (mode == 3) {
+        const float d = v - mu;
+        a0 += d;
+        a1 = fmaf(d, d, a1);
       } else {
         const float xh = (v - mu) * is;
         const float g = dy[r * dpitch + c] * (act ? silu_grad(ga * xh + be) : 1.f);
@@ -71,7 +78,7 @@ __global__ void __launch_bounds__(BN_TX* BN_TY) bn_partial_kernel(int mode, int 
     float t0 = 0.f, t1 = 0.f;
     for (int k = 0; k < BN_TY; k++) { t0 += s0[k][threadIdx.x]; t1 += s1[k][threadIdx.x]; }
     p0[(size_t)blockIdx.y * C + c] = t0;
-    if (mode == 2) p1[(size_t)blockIdx.y * C + c] = t1;
+    if (mode >= 2) p1[(size_t)blockIdx.y * C + c] = t1;
   }
 }
 
@@ -85,9 +92,21 @@ __global__ void bn_finish_kernel(int step, const float* __restrict__ p0, const f
   float t0 = 0.f, t1 = 0.f;
   for (int s = 0; s < slabs; s++) {
     t0 += p0[(size_t)s * C + c];
-    if (step == 2) t1 += p1[(size_t)s * C + c];
+    if (step >= 2) t1 += p1[(size_t)s * C + c];
   }
-  if (step == 0) {
+  if (step == 3) {  // shifted sums (mode 3): running_mean carries the shift pointer's value z[0][c] via `dgamma`
+    const float K = dgamma[c];
+    const float d = t0 / (float)M;
+    const float mu = K + d;
+    const float var = fmaxf(t1 / (float)M - d * d, 0.f);  // biased: used for normalisation
+    mean[c] = mu;
+    invstd[c] = 1.f / sqrtf(var + eps);
+    if (running_mean) {
+      const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+  } else if (step == 0) {
     mean[c] = t0 / (float)M;
   } else if (step == 1) {
     const float var = t0 / (float)M;  // biased: used for normalisation
@@ -128,6 +147,45 @@ __global__ void bn_silu_dz_kernel(const float* __restrict__ z, const float* __re
   dz[r * opitch + c] = gamma[c] * invstd[c] * (g - dbeta[c] * inv_m - xh * dgamma[c] * inv_m);
 }
 
+// 4 channels per thread (C, pitches multiples of 4; 32-bit index math): the scalar kernels above spend a 64-bit division
+// per element
+__global__ void bn_silu_apply4_kernel(const float* __restrict__ z, int total4, int C4, int pitch, int opitch,
+                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, int act, float* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int r = i / C4, c = (i - r * C4) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(z + (size_t)r * pitch + c);
+  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+  float4 u;
+  u.x = ga.x * (v.x - mu.x) * is.x + be.x; u.y = ga.y * (v.y - mu.y) * is.y + be.y;
+  u.z = ga.z * (v.z - mu.z) * is.z + be.z; u.w = ga.w * (v.w - mu.w) * is.w + be.w;
+  if (act) { u.x = silu_f(u.x); u.y = silu_f(u.y); u.z = silu_f(u.z); u.w = silu_f(u.w); }
+  *reinterpret_cast<float4*>(y + (size_t)r * opitch + c) = u;
+}
+
+__global__ void bn_silu_dz4_kernel(const float* __restrict__ z, const float* __restrict__ dy, int total4, int C4, int pitch, int dpitch,
+                                   int opitch, float inv_m, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                   const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int r = i / C4, c = (i - r * C4) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(z + (size_t)r * pitch + c);
+  const float4 d = *reinterpret_cast<const float4*>(dy + (size_t)r * dpitch + c);
+  const float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float is = invstd[c + j], ga = gamma[c + j];
+    const float xh = (vv[j] - mean[c + j]) * is;
+    const float g = dd[j] * (act ? silu_grad(ga * xh + beta[c + j]) : 1.f);
+    o[j] = ga * is * (g - dbeta[c + j] * inv_m - xh * dgamma[c + j] * inv_m);
+  }
+  *reinterpret_cast<float4*>(dz + (size_t)r * opitch + c) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
 }  // namespace
 
 int bn_silu_train_forward(const float* z, long long M, int C, int pitch, const float* gamma, const float* beta, float eps,
@@ -140,17 +198,22 @@ int bn_silu_train_forward(const float* z, long long M, int C, int pitch, const f
   const int rpb = bn_rows_per_block(M);
   const int slabs = (int)((M + rpb - 1) / rpb);
   float* part = nullptr;
-  YB_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)slabs * C * sizeof(float), s));
+  YB_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)2 * slabs * C * sizeof(float), s));
   const dim3 grid((C + BN_TX - 1) / BN_TX, slabs), block(BN_TX, BN_TY);
   const int fb = 128, fg = (C + fb - 1) / fb;
-  bn_partial_kernel<<<grid, block, 0, s>>>(0, act, z, nullptr, M, C, pitch, 0, nullptr, nullptr, nullptr, nullptr, part, nullptr, rpb);
-  bn_finish_kernel<<<fg, fb, 0, s>>>(0, part, nullptr, slabs, C, M, eps, momentum, save_mean, save_invstd, nullptr, nullptr, nullptr,
-                                     nullptr);
-  bn_partial_kernel<<<grid, block, 0, s>>>(1, act, z, nullptr, M, C, pitch, 0, save_mean, nullptr, nullptr, nullptr, part, nullptr, rpb);
-  bn_finish_kernel<<<fg, fb, 0, s>>>(1, part, nullptr, slabs, C, M, eps, momentum, save_mean, save_invstd, running_mean, running_var,
-                                     nullptr, nullptr);
+  // one pass over z: per-slab sums of (z - K) and (z - K)^2 about the shift K = z[row 0], folded in slab order
+  bn_partial_kernel<<<grid, block, 0, s>>>(3, act, z, nullptr, M, C, pitch, 0, nullptr, nullptr, nullptr, nullptr, part,
+                                          part + (size_t)slabs * C, rpb);
+  bn_finish_kernel<<<fg, fb, 0, s>>>(3, part, part + (size_t)slabs * C, slabs, C, M, eps, momentum, save_mean, save_invstd, running_mean,
+                                     running_var, const_cast<float*>(z) /* the shift row, read only */, nullptr);
   const long long total = M * C;
-  bn_silu_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, M, C, pitch, ypitch, save_mean, save_invstd, gamma, beta, act, y);
+  if (C % 4 == 0 && pitch % 4 == 0 && ypitch % 4 == 0 && total / 4 < (1ll << 31) && ((uintptr_t)z % 16 == 0) && ((uintptr_t)y % 16 == 0)) {
+    const int total4 = (int)(total / 4);
+    bn_silu_apply4_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(z, total4, C / 4, pitch, ypitch, save_mean, save_invstd, gamma,
+                                                                          beta, act, y);
+  } else {
+    bn_silu_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, M, C, pitch, ypitch, save_mean, save_invstd, gamma, beta, act, y);
+  }
   YB_CUDA_CHECK(cudaGetLastError());
   YB_CUDA_CHECK(cudaFreeAsync(part, s));
   return YB_OK;
@@ -173,8 +236,15 @@ int bn_silu_backward(const float* z, const float* dy, long long M, int C, int pi
   bn_finish_kernel<<<(C + 127) / 128, 128, 0, s>>>(2, part, part + (size_t)slabs * C, slabs, C, M, 0.f, 0.f, nullptr, nullptr, nullptr,
                                                    nullptr, dgamma, dbeta);
   const long long total = M * C;
-  bn_silu_dz_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, dy, M, C, pitch, dpitch, zpitch, save_mean, save_invstd, gamma, beta,
-                                                                act, dgamma, dbeta, dz);
+  if (C % 4 == 0 && pitch % 4 == 0 && dpitch % 4 == 0 && zpitch % 4 == 0 && total / 4 < (1ll << 31) && ((uintptr_t)z % 16 == 0) &&
+      ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dz % 16 == 0)) {
+    const int total4 = (int)(total / 4);
+    bn_silu_dz4_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(z, dy, total4, C / 4, pitch, dpitch, zpitch, 1.f / (float)M, save_mean,
+                                                                       save_invstd, gamma, beta, act, dgamma, dbeta, dz);
+  } else {
+    bn_silu_dz_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, dy, M, C, pitch, dpitch, zpitch, save_mean, save_invstd, gamma, beta,
+                                                                  act, dgamma, dbeta, dz);
+  }
   YB_CUDA_CHECK(cudaGetLastError());
   YB_CUDA_CHECK(cudaFreeAsync(part, s));
   return YB_OK;

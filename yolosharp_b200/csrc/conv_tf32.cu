@@ -434,6 +434,8 @@ struct WgArgs {
   int co_tiles, ci_tiles, splits;
   int imgs, tiles_w, tiles_h, pix_tiles;
   int b_stages;
+  int halo;         // 3x3 stride 1: ONE (PH+2) x (PW+2) input tile per pixel tile serves all nine taps (row-shifted windows)
+  uint32_t xblk;    // bytes reserved per 32-channel block of an x stage (1 KiB aligned)
   int co_pad, ci_pad;
   uint32_t tmem_cols;
 };
@@ -444,7 +446,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(wg_smem) + 1023u) & ~1023u;
-  const uint32_t a_stride = 4 * WG_BLK, b_stride = (uint32_t)a.nb * WG_BLK;
+  const uint32_t a_stride = 4 * WG_BLK, b_stride = (uint32_t)a.nb * a.xblk;
   const uint32_t smemA = smem0, smemB = smem0 + WG_A_STAGES * a_stride;
   const uint32_t afull = smem_u32(&bars[0]), aempty = smem_u32(&bars[WG_A_STAGES]);
   const uint32_t bfull = smem_u32(&bars[2 * WG_A_STAGES]), bempty = smem_u32(&bars[2 * WG_A_STAGES + 16]);
@@ -494,14 +496,24 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
         for (int b = 0; b < a.co_blocks; b++)
           tma_load_4d(smemA + sa * a_stride + b * WG_BLK, &a.tmDz, afull + 8 * sa, co_t * 128 + b * 32, w0, h0, img);
         if (++sa == WG_A_STAGES) { sa = 0; pa ^= 1; }
-        for (int t = 0; t < a.taps; t++) {
-          const int kh = t / a.ksz, kw = t - kh * a.ksz;
+        if (a.halo) {
+          // one box of (PH + 2) x (PW + 2) input pixels per 32-channel block: tap (kh, kw) of output row h reads its 8
+          // pixels from rows (h + kh) * (PW + 2) + kw .. + 7 of it
           mbar_wait(bempty + 8 * sb, pb ^ 1);
-          mbar_arrive_expect_tx(bfull + 8 * sb, (uint32_t)a.nb * WG_BLK);
+          mbar_arrive_expect_tx(bfull + 8 * sb, (uint32_t)a.nb * (WG_PW + 2) * (WG_PH + 2) * 128);
           for (int b = 0; b < a.nb; b++)
-            tma_load_4d(smemB + sb * b_stride + b * WG_BLK, &a.tmX, bfull + 8 * sb, (ci_t * a.nb + b) * 32,
-                        w0 * a.stride + kw - a.pad, h0 * a.stride + kh - a.pad, img);
+            tma_load_4d(smemB + sb * b_stride + b * a.xblk, &a.tmX, bfull + 8 * sb, (ci_t * a.nb + b) * 32, w0 - a.pad, h0 - a.pad, img);
           if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+        } else {
+          for (int t = 0; t < a.taps; t++) {
+            const int kh = t / a.ksz, kw = t - kh * a.ksz;
+            mbar_wait(bempty + 8 * sb, pb ^ 1);
+            mbar_arrive_expect_tx(bfull + 8 * sb, (uint32_t)a.nb * WG_BLK);
+            for (int b = 0; b < a.nb; b++)
+              tma_load_4d(smemB + sb * b_stride + b * a.xblk, &a.tmX, bfull + 8 * sb, (ci_t * a.nb + b) * 32,
+                          w0 * a.stride + kw - a.pad, h0 * a.stride + kh - a.pad, img);
+            if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+          }
         }
       }
     }
@@ -520,17 +532,34 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
         mbar_wait(afull + 8 * sa, pa);
         tc_fence_after();
         const uint32_t A0 = smemA + sa * a_stride;
-        for (int t = 0; t < a.taps; t++) {
+        const uint32_t xlbo16 = a.xblk >> 4;
+        if (a.halo) {
           mbar_wait(bfull + 8 * sb, pb);
           tc_fence_after();
           const uint32_t B0 = smemB + sb * b_stride;
-          const uint32_t d_tmem = tmem_base + t * ncols;
+          for (int t = 0; t < 9; t++) {
+            const int kh = t / 3, kw = t - kh * 3;
+            const uint32_t d_tmem = tmem_base + t * ncols;
 #pragma unroll
-          for (int ks = 0; ks < WG_PW * WG_PH / 8; ks++)  // 8 pixels (K = 8) = 1 KiB = two 4-row swizzle atoms per block
-            umma_tf32(d_tmem, tf_desc(A0 + ks * 1024, lbo16, sbo16, 1), tf_desc(B0 + ks * 1024, lbo16, sbo16, 1), idesc,
-                      (i > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < WG_PH; ks++)  // output row ks: input rows start at ((ks + kh) * (PW + 2) + kw)
+              umma_tf32(d_tmem, tf_desc(A0 + ks * 1024, lbo16, sbo16, 1),
+                        tf_desc(B0 + (uint32_t)((ks + kh) * (WG_PW + 2) + kw) * 128, xlbo16, sbo16, 1), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          }
           umma_commit(bempty + 8 * sb);
           if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+        } else {
+          for (int t = 0; t < a.taps; t++) {
+            mbar_wait(bfull + 8 * sb, pb);
+            tc_fence_after();
+            const uint32_t B0 = smemB + sb * b_stride;
+            const uint32_t d_tmem = tmem_base + t * ncols;
+#pragma unroll
+            for (int ks = 0; ks < WG_PW * WG_PH / 8; ks++)  // 8 pixels (K = 8) = 1 KiB = two 4-row swizzle atoms per block
+              umma_tf32(d_tmem, tf_desc(A0 + ks * 1024, lbo16, sbo16, 1), tf_desc(B0 + ks * 1024, xlbo16, sbo16, 1), idesc,
+                        (i > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(bempty + 8 * sb);
+            if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+          }
         }
         umma_commit(aempty + 8 * sa);
         if (++sa == WG_A_STAGES) { sa = 0; pa ^= 1; }
@@ -631,7 +660,14 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
   a.co_blocks = std::min(4, (Cout + 31) / 32);
   a.imgs = N; a.tiles_w = p.tiles_w; a.tiles_h = p.tiles_h; a.pix_tiles = p.pix_tiles;
   a.co_pad = p.co_pad; a.ci_pad = p.ci_pad;
-  const size_t b_stride = (size_t)p.nb * WG_BLK;
+  // 3x3 stride 1: the input tile with its halo is loaded once per pixel tile and the nine taps are row-shifted MMA windows
+  // into it (the per-tap form moved 9 x 8 KiB of x per 64 pixels and was bound by L2 -> SM delivery).  The shifted start
+  // relies on tcgen05 applying the 32-byte-atom swizzle on absolute shared-memory address bits, as the K-major halo tile
+  // of conv_tc.cu does for the 16-byte-atom modes; tests/test_gpu_conv_tc.py's bit-exact case covers it.
+  static const bool no_halo = getenv("YB_WGRAD_NO_HALO") != nullptr;
+  a.halo = (k == 3 && stride == 1 && !no_halo) ? 1 : 0;
+  a.xblk = a.halo ? (uint32_t)(((WG_PW + 2) * (WG_PH + 2) * 128 + 1023) / 1024 * 1024) : (uint32_t)WG_BLK;
+  const size_t b_stride = (size_t)p.nb * a.xblk;
   a.b_stages = (int)std::min<size_t>(16, ((size_t)190 * 1024 - (size_t)WG_A_STAGES * 4 * WG_BLK) / b_stride);
   if (a.b_stages < 2) { set_error("tf32 wgrad: tile does not fit in shared memory"); return YB_ERR_SHAPE; }
   uint32_t cols = 32;
@@ -649,7 +685,7 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
   {
     cuuint64_t gd[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t gs[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cin * 4 * W, (cuuint64_t)Cin * 4 * W * H};
-    cuuint32_t bx[4] = {32, (cuuint32_t)(WG_PW * stride), (cuuint32_t)(WG_PH * stride), 1};
+    cuuint32_t bx[4] = {32, (cuuint32_t)(a.halo ? WG_PW + 2 : WG_PW * stride), (cuuint32_t)(a.halo ? WG_PH + 2 : WG_PH * stride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult cr = encode(&a.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -777,6 +777,18 @@ __global__ void __launch_bounds__(256) attention_kernel(View qkv, View out, View
 // Per-output summation order is unchanged (sequential over d, then over j).
 constexpr int ATI_T = 16, ATI_KD = 32, ATI_HD = 64, ATI_LDK = 36;
 __device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// four consecutive elements (16 / 8 bytes, aligned) as fp32: one vector load instead of four scalar ones - the scalar
+// fill of K and V made every warp instruction touch 16 sectors for 128 useful bytes and cost 2/3 of the kernel
+template <typename T> __device__ __forceinline__ float4 ld4(const T* p);
+template <> __device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 ld4<__half>(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void cp4(T* dst, const T* src);
+template <> __device__ __forceinline__ void cp4<float>(float* dst, const float* src) { *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src); }
+template <> __device__ __forceinline__ void cp4<__half>(__half* dst, const __half* src) { *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src); }
 
 template <typename T>
 __global__ void __launch_bounds__(256) attention_tiled_32x64_kernel(AttnIO io, int N, int nh, float scale) {
@@ -792,28 +804,42 @@ __global__ void __launch_bounds__(256) attention_tiled_32x64_kernel(AttnIO io, i
   const T* kb = reinterpret_cast<const T*>(io.k) + (size_t)b * io.in_img + (size_t)head * io.k_head;
   const T* vb = reinterpret_cast<const T*>(io.v) + (size_t)b * io.v_img + (size_t)head * io.v_head;
   T* vo = reinterpret_cast<T*>(io.vout);
-  // fill: 4 channels per thread and step
-  for (int t = threadIdx.x; t < NK * (ATI_KD / 4); t += 256) {
-    const int j = t >> 3, d = (t & 7) * 4;
-    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < N) {
-      const T* src = kb + (size_t)j * io.in_tok + d;
-      f = make_float4(to_f<T>(src[0]), to_f<T>(src[1]), to_f<T>(src[2]), to_f<T>(src[3]));
+  // fill: 4 channels per thread and step, 8 independent vector loads in flight per thread (with one CTA of 8 warps per
+  // SM a load-convert-store loop exposes the full L2 latency on every iteration: 38 iterations x ~700 cycles was 2/3 of
+  // the kernel)
+  constexpr int U = 8;
+  for (int t0 = threadIdx.x; t0 < NK * (ATI_KD / 4); t0 += 256 * U) {
+    float4 f[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * 256, j = t >> 3, d = (t & 7) * 4;
+      f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < NK * (ATI_KD / 4) && j < N) f[u] = ld4<T>(kb + (size_t)j * io.in_tok + d);
     }
-    *reinterpret_cast<float4*>(Ks + (size_t)j * ATI_LDK + d) = f;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * 256, j = t >> 3, d = (t & 7) * 4;
+      if (t < NK * (ATI_KD / 4)) *reinterpret_cast<float4*>(Ks + (size_t)j * ATI_LDK + d) = f[u];
+    }
   }
-  for (int t = threadIdx.x; t < NP * (ATI_HD / 4); t += 256) {
-    const int j = t >> 4, d = (t & 15) * 4;
-    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < N) {
-      const T* src = vb + (size_t)j * io.v_tok + d;
-      f = make_float4(to_f<T>(src[0]), to_f<T>(src[1]), to_f<T>(src[2]), to_f<T>(src[3]));
-      if (vo && j >= i0 && j < i0 + ATI_T) {  // the dense copy of v the positional-encoding conv reads
-        T* dst = vo + (size_t)b * io.out_img + (size_t)j * io.out_tok + head * ATI_HD + d;
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+  for (int t0 = threadIdx.x; t0 < NP * (ATI_HD / 4); t0 += 256 * U) {
+    float4 f[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * 256, j = t >> 4, d = (t & 15) * 4;
+      f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < NP * (ATI_HD / 4) && j < N) {
+        const T* src = vb + (size_t)j * io.v_tok + d;
+        f[u] = ld4<T>(src);
+        if (vo && j >= i0 && j < i0 + ATI_T)  // the dense copy of v the positional-encoding conv reads
+          cp4<T>(vo + (size_t)b * io.out_img + (size_t)j * io.out_tok + head * ATI_HD + d, src);
       }
     }
-    *reinterpret_cast<float4*>(Vs + (size_t)j * ATI_HD + d) = f;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * 256, j = t >> 4, d = (t & 15) * 4;
+      if (t < NP * (ATI_HD / 4)) *reinterpret_cast<float4*>(Vs + (size_t)j * ATI_HD + d) = f[u];
+    }
   }
   for (int t = threadIdx.x; t < ATI_T * ATI_KD; t += 256) {
     const int r = t >> 5, d = t & 31;
@@ -912,7 +938,8 @@ int launch_attention(const View& qkv, const View& out, const View& vout, int B, 
   }
   {
     static const bool no_tiled = getenv("YB_ATTN_ROWS") != nullptr;  // experiments: the row-streaming kernel below
-    if (kd == ATI_KD && hd == ATI_HD && attention_tiled_32x64_fits(N) && !no_tiled) {
+    if (kd == ATI_KD && hd == ATI_HD && attention_tiled_32x64_fits(N) && !no_tiled && qkv.pitch % 4 == 0 && qkv.coff % 4 == 0 &&
+        out.pitch % 4 == 0 && out.coff % 4 == 0 && vout.coff % 4 == 0) {
       const int per = 2 * kd + hd;
       AttnIO io;
       const T* base = reinterpret_cast<const T*>(qkv.base) + qkv.coff;

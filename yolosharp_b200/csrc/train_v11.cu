@@ -297,13 +297,33 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// rows of one head of a (B, N, nh, dim) tensor -> shared memory with row stride `ld`
+// rows of one head of a (B, N, nh, dim) tensor -> shared memory with row stride `ld` (dim a multiple of 4, 16-byte aligned
+// rows in global memory).  Eight independent 16-byte loads are in flight per thread: with one CTA of 8 warps per SM a
+// load-store loop of scalar loads exposed the full L2 latency per element (the two backward kernels spent ~85 us per CTA).
 __device__ __forceinline__ void load_head(float* dst, const float* src, int b, int h, int N, int nh, int dim, int ld, int row0,
                                           int rows) {
-  for (int idx = threadIdx.x; idx < rows * dim; idx += ATT_THREADS) {
-    const int r = idx / dim, d = idx - r * dim;
-    const int tok = row0 + r;
-    dst[r * ld + d] = tok < N ? src[(((size_t)b * N + tok) * nh + h) * dim + d] : 0.f;
+  constexpr int U = 8;
+  const int d4 = dim >> 2, total = rows * d4;
+  for (int t0 = threadIdx.x; t0 < total; t0 += ATT_THREADS * U) {
+    float4 f[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * ATT_THREADS;
+      f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < total) {
+        const int r = t / d4, d = (t - r * d4) * 4, tok = row0 + r;
+        if (tok < N) f[u] = *reinterpret_cast<const float4*>(src + (((size_t)b * N + tok) * nh + h) * dim + d);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * ATT_THREADS;
+      if (t < total) {
+        const int r = t / d4, d = (t - r * d4) * 4;
+        float* o = dst + r * ld + d;  // ld may be odd (kd + 1): scalar stores
+        o[0] = f[u].x; o[1] = f[u].y; o[2] = f[u].z; o[3] = f[u].w;
+      }
+    }
   }
 }
 

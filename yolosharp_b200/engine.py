@@ -220,6 +220,53 @@ def topk_postprocess(pred, max_det=300, nc=0, agnostic=False, stream=None):
     return out, idx
 
 
+def _f32c(t):
+    assert t.is_cuda and t.dtype == torch.float32
+    return t.contiguous()
+
+
+def obb_decode(box_logits, cls_logits, angle_logits, anchors, strides, reg_max=16, stream=None):
+    """yb_obb_decode: (B,4*reg_max,A), (B,nc,A), (B,1,A), anchors (2,A), strides (A) -> (B, 4+nc+1, A)."""
+    box_logits, cls_logits, angle_logits, anchors, strides = map(_f32c, (box_logits, cls_logits, angle_logits, anchors, strides))
+    B, _, A = box_logits.shape
+    nc = cls_logits.shape[1]
+    out = torch.empty((B, 4 + nc + 1, A), dtype=torch.float32, device=box_logits.device)
+    L.check(L.lib().yb_obb_decode(C.c_void_p(box_logits.data_ptr()), C.c_void_p(cls_logits.data_ptr()), C.c_void_p(angle_logits.data_ptr()),
+                                  C.c_void_p(anchors.data_ptr()), C.c_void_p(strides.data_ptr()), B, A, nc, reg_max,
+                                  C.c_void_p(out.data_ptr()), _stream_ptr(stream)))
+    return out
+
+
+def pose_decode(kpts, anchors, strides, keypoint_dim=3, stream=None):
+    """yb_pose_decode: kpts (B, nk, A) -> decoded (B, nk, A)."""
+    kpts, anchors, strides = map(_f32c, (kpts, anchors, strides))
+    B, nk, A = kpts.shape
+    out = torch.empty_like(kpts)
+    L.check(L.lib().yb_pose_decode(C.c_void_p(kpts.data_ptr()), C.c_void_p(anchors.data_ptr()), C.c_void_p(strides.data_ptr()), B, A, nk,
+                                   keypoint_dim, C.c_void_p(out.data_ptr()), _stream_ptr(stream)))
+    return out
+
+
+def probiou(obb1, obb2, eps=1e-7, stream=None):
+    """yb_probiou: xywhr (n,5) x (m,5) -> (n,m)."""
+    obb1, obb2 = _f32c(obb1), _f32c(obb2)
+    out = torch.empty((obb1.shape[0], obb2.shape[0]), dtype=torch.float32, device=obb1.device)
+    L.check(L.lib().yb_probiou(C.c_void_p(obb1.data_ptr()), obb1.shape[0], C.c_void_p(obb2.data_ptr()), obb2.shape[0], eps,
+                               C.c_void_p(out.data_ptr()), _stream_ptr(stream)))
+    return out
+
+
+def nms_rotated(boxes, scores, threshold=0.45, stream=None):
+    """yb_nms_rotated: boxes (n,5) xywhr, scores (n) -> kept original indices in score order (int64)."""
+    boxes, scores = _f32c(boxes), _f32c(scores)
+    n = boxes.shape[0]
+    keep = torch.empty((max(n, 1),), dtype=torch.int32, device=boxes.device)
+    count = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
+    L.check(L.lib().yb_nms_rotated(C.c_void_p(boxes.data_ptr()), C.c_void_p(scores.data_ptr()), n, threshold,
+                                   C.c_void_p(keep.data_ptr()), C.c_void_p(count.data_ptr()), _stream_ptr(stream)))
+    return keep[:int(count.item())].long()
+
+
 def masks(proto, dets, counts, height, width, stream=None, out=None):
     """yb_masks: proto (B,32,mh,mw) f32, dets (B,max_det,38), counts -> uint8 (B,max_det,H,W)."""
     B, nm, mh, mw = proto.shape
