@@ -267,7 +267,12 @@ def train_main(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     m = oracle_model(arch, task, size)
     tc = args.train_kernels == "tc"
-    st = TrainStepV11({k: v.detach().clone() for k, v in m.state_dict().items()}, size, 80, device=dev, ops=KernelOpsV11(tensor_cores=tc))
+    native = args.train_impl == "native" and tc
+    if native:  # ONE C-ABI call per step (csrc/train_step.cu); the flat buffers are torch tensors of this process
+        from yolosharp_b200.train_native import NativeTrainer
+        st = NativeTrainer({k: v.detach().clone() for k, v in m.state_dict().items()}, "v11", size, 80, device=dev, max_batch=B)
+    else:
+        st = TrainStepV11({k: v.detach().clone() for k, v in m.state_dict().items()}, size, 80, device=dev, ops=KernelOpsV11(tensor_cores=tc))
     del m
     xs = [synth_image(B, 640, 640, seed=300 + rank * 4 + i).to(dev) for i in range(2)]
     ts = [synth_targets(B, 400 + rank * 4 + i) for i in range(2)]
@@ -298,8 +303,8 @@ def train_main(args, rank, world, local_rank):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(n2):
-        x = u8[i & 1].to(dev, non_blocking=True).float().div_(255.0)
-        host_items = st.step(x, ts[i & 1]).cpu()
+        x = u8[i & 1].to(dev, non_blocking=True)
+        host_items = st.step(x if native else x.float().div_(255.0), ts[i & 1]).cpu()  # the native step divides by 255 itself
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], device=dev)
     if world > 1:
@@ -311,10 +316,11 @@ def train_main(args, rank, world, local_rank):
         print(json.dumps({"metric": f"train images/sec YOLO{model} 3x640x640", "value": round(value, 2), "unit": "images/s",
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 2),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if tc else "f32",
-                          "data": "synthetic", "config": config, "clocks": clocks,
+                          "data": "synthetic", "config": dict(config, step="native (yb_train_step)" if native else "python graph walk"), "clocks": clocks,
                           "e2e": {"value": round(world * B * n2 / float(t.item()), 2), "unit": "images/s",
                                   "h2d_bytes_per_step": B * 3 * 640 * 640, "d2h_bytes_per_step": 12, "steps": n2,
-                                  "api": "TrainStepV11.step over the C-ABI training kernels (pinned uint8 images in, loss items out)"},
+                                  "api": ("yb_train_backward + yb_train_apply (one native graph walk per step; pinned uint8 images in, loss items out)"
+                                          if native else "TrainStepV11.step over the C-ABI training kernels (pinned uint8 images in, loss items out)")},
                           "loss_items": [round(float(v), 4) for v in host_items],
                           "roofline": {"bound": "tensor", "achieved": round(tflops, 2), "peak": peaks["tc"], "unit": "TFLOP/s",
                                        "frac": round(tflops / peaks["tc"], 5), "traffic": None,
@@ -337,6 +343,8 @@ def main():
     ap.add_argument("--model", default="v8n", choices=sorted(MODELS))
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--gather", default="comm", choices=["comm", "nccl"], help="N > 1: detection exchange")
+    ap.add_argument("--train-impl", default="native", choices=["native", "python"],
+                    help="--mode train: the native step (csrc/train_step.cu) or the Python graph walk over the same kernels")
     ap.add_argument("--train-kernels", default="tc", choices=["tc", "f32"],
                     help="--mode train: dense convolutions on the TF32 tcgen05 kernels (default) or the fp32 parity kernels")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],

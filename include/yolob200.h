@@ -231,6 +231,41 @@ int32_t yb_conv_backward_weight_tc(const float* x, const float* dz, int32_t n, i
                                    int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dw, void* workspace,
                                    int64_t workspace_bytes, void* stream);
 
+/* Replaces: `AMPWrapper.TrainStep` (Utils/Amp.cs:260-286: yolo.forward -> loss -> loss.backward() -> optimizer.step()) for
+ * the YOLOv8 / YOLOv11 detect models as ONE call (csrc/train_step.cu): train-mode forward with batch-statistics
+ * BatchNorm, v8DetectionLoss, backward through the whole graph (TF32 tcgen05 convolutions), AdamW per name group
+ * (YoloBaseTaskModel.cs:142-160: the "bias" group first).
+ *   yb_trainer_create   cfg: arch (8 | 11), size, nc, device, max_batch, height, width (task detect);
+ *                       flags & YB_FLAG_DRY_RUN builds the parameter layout only (no device memory)
+ *   yb_trainer_tensor_info  kind 0: trained parameters, kind 1: BatchNorm running statistics; names are the reference's
+ *                       state_dict keys, offset / count locate the tensor in the flat buffer of its kind
+ *   yb_trainer_flat_size    kind 0: floats of the parameter buffers, 1: of the running-statistics buffer,
+ *                       2: floats of the leading "bias" group inside the parameter buffers
+ *   yb_trainer_bind     the caller owns the flat fp32 device buffers (parameters, gradients, Adam m / v, running stats):
+ *                       a TorchSharp / PyTorch host wraps them as tensors, loads a checkpoint into them, reads gradients
+ *                       and all-reduces the gradient buffer between yb_train_backward and yb_train_apply (DDP)
+ *   yb_train_backward   images dev (B, 3, H, W) u8 (divided by 255 as Detector.cs:41) or f32; targets HOST float32
+ *                       (n, 6) rows [image, class, x, y, w, h] normalised; loss_items HOST float[3] or NULL
+ *   yb_train_apply      one AdamW step (betas 0.9 / 0.999, eps 1e-8) with the two group learning rates
+ *   yb_train_step       = yb_train_backward + yb_train_apply (single device)
+ *   yb_get_grad / yb_get_tensor  copy one named gradient / parameter / running statistic to the host */
+typedef struct yb_trainer yb_trainer;
+int32_t yb_trainer_create(const yb_config* cfg, yb_trainer** out);
+void yb_trainer_destroy(yb_trainer* t);
+int32_t yb_trainer_num_tensors(const yb_trainer* t, int32_t kind);
+int32_t yb_trainer_tensor_info(const yb_trainer* t, int32_t kind, int32_t index, const char** name, int64_t* offset,
+                               int64_t* count, int32_t* ndim, const int64_t** shape);
+int64_t yb_trainer_flat_size(const yb_trainer* t, int32_t kind);
+int32_t yb_trainer_bind(yb_trainer* t, float* params, float* grads, float* adam_m, float* adam_v, float* running_stats);
+int32_t yb_train_backward(yb_trainer* t, const void* images, int32_t in_dtype, int32_t batch, const float* targets_host,
+                          int32_t n_targets, float* loss_items_host, void* stream);
+int32_t yb_train_apply(yb_trainer* t, float lr_bias, float lr_other, float weight_decay, void* stream);
+int32_t yb_train_step(yb_trainer* t, const void* images, int32_t in_dtype, int32_t batch, const float* targets_host,
+                      int32_t n_targets, float lr_bias, float lr_other, float weight_decay, float* loss_items_host,
+                      void* stream);
+int32_t yb_get_grad(yb_trainer* t, const char* name, float* out_host, int64_t count);
+int32_t yb_get_tensor(yb_trainer* t, const char* name, float* out_host, int64_t count);
+
 /* Replaces (training path of YOLOv11, fp32 parity kernels): the forward and the autograd backward of the depthwise 3x3
  * convolutions - `Convs.DWConv` (Modules/Convs.cs:108-114; groups = gcd(c1, c2) = c for every use in Yolov11: the
  * class branch of the head, Head.cs:50, and `Attention.pe`, Block.cs:746), stride 1, padding 1.

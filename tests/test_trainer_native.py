@@ -1,0 +1,90 @@
+"""The native training step (csrc/train_step.cu, one C-ABI call per step) against its executable specification, the
+Python step of yolosharp_b200/train.py / train_v11.py over the same kernels (which in turn is pinned to autograd through
+the oracle, tests/test_train_step.py).  CPU: the parameter layout (names, shapes, bias group) against the oracle model's
+state_dict.  GPU: one step on the same weights and batch - loss items, every parameter gradient, updated weights,
+BatchNorm running statistics."""
+import pytest
+import torch
+
+from tests.test_train_step import _targets
+from tests.util import oracle_model, synth_image
+
+
+@pytest.mark.parametrize("arch,size", [("v8", "n"), ("v8", "s"), ("v8", "m"), ("v8", "x"), ("v11", "n"), ("v11", "s"), ("v11", "m"),
+                                       ("v11", "x")])
+def test_native_trainer_layout_matches_reference_state_dict(arch, size):
+    from yolosharp_b200.train_native import NativeTrainer
+    sd = oracle_model(arch, "detect", size).state_dict()
+    t = NativeTrainer(None, arch, size, 80, device="cpu")  # dry run: layout only
+    want_p = {k: tuple(v.shape) for k, v in sd.items() if v.dtype.is_floating_point and v.numel() > 0 and ".dfl." not in k and
+              not k.endswith(("running_mean", "running_var"))}
+    want_s = {k: tuple(v.shape) for k, v in sd.items() if k.endswith(("running_mean", "running_var"))}
+    assert {k: s for k, (_, _, s) in t.params.items()} == want_p
+    assert {k: s for k, (_, _, s) in t.stats.items()} == want_s
+    # flat layout: contiguous, the "bias" group first (YoloBaseTaskModel.cs:144-153)
+    offs = sorted((o, c, k) for k, (o, c, _) in t.params.items())
+    pos = 0
+    for o, c, k in offs:
+        assert o == pos
+        pos += c
+        assert ("bias" in k) == (o < t.n_bias)
+    t.close()
+
+
+def _run_pair(arch, B, H, W, py_cls, ops_cls):
+    from yolosharp_b200.train_native import NativeTrainer
+    torch.manual_seed(0)
+    m = oracle_model(arch, "detect", "n")
+    sd0 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = synth_image(B, H, W).cuda()
+    targets = _targets(B)
+    a = py_cls(sd0, "n", 80, device="cuda", ops=ops_cls(tensor_cores=True), lr=1e-3)
+    b = NativeTrainer(sd0, arch, "n", 80, device="cuda", max_batch=B, height=H, width=W, lr=1e-3)
+    ia = a.step(x, targets).cpu()
+    ib = b.step(x, targets)
+    torch.cuda.synchronize()
+    return a, b, ia, ib
+
+
+def _check(a, b, ia, ib):
+    torch.testing.assert_close(ib, ia, rtol=1e-5, atol=1e-6)
+    gmax = float(a.P.grad.abs().max())
+    worst = ("", 0.0)
+    for k in a.P.names:
+        ga, gb = a.P.g(k), b.g(k)
+        err = float((gb - ga).abs().max()) / max(float(ga.abs().max()), 1e-4 * gmax)
+        worst = max(worst, (k, err), key=lambda t: t[1])
+        torch.testing.assert_close(b.p(k), a.P.p(k), rtol=1e-5, atol=2.1e-3)  # Adam's first step: +-lr on a sign flip of a ~0 gradient
+    print(f"worst parameter gradient vs the Python step: {worst[0]} {worst[1]:.2e}")
+    assert worst[1] < 1e-4, worst
+    for k, v in a.P.buffers.items():
+        torch.testing.assert_close(b.p(k), v, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_native_train_step_v8_matches_python_step():
+    from yolosharp_b200.train import KernelOps, TrainStepV8
+    _check(*_run_pair("v8", 2, 64, 96, TrainStepV8, KernelOps))
+
+
+@pytest.mark.gpu
+def test_native_train_step_v11_matches_python_step():
+    from yolosharp_b200.train_v11 import KernelOpsV11, TrainStepV11
+    _check(*_run_pair("v11", 2, 64, 64, TrainStepV11, KernelOpsV11))
+
+
+@pytest.mark.gpu
+def test_native_train_step_u8_images_and_second_step():
+    """uint8 images (divided by 255 inside the library) and a second step on the updated weights stay finite and move."""
+    from yolosharp_b200.train_native import NativeTrainer
+    torch.manual_seed(0)
+    m = oracle_model("v8", "detect", "n")
+    t = NativeTrainer(m.state_dict(), "v8", "n", 80, device="cuda", max_batch=2, height=64, width=96, lr=1e-3)
+    u8 = synth_image(2, 64, 96, dtype=torch.uint8).cuda()
+    i1 = t.step(u8, _targets(2))
+    w1 = t.flat.clone()
+    i2 = t.step(u8, _targets(2))
+    assert torch.isfinite(i1).all() and torch.isfinite(i2).all() and not torch.equal(w1, t.flat)
+    f = NativeTrainer(m.state_dict(), "v8", "n", 80, device="cuda", max_batch=2, height=64, width=96, lr=1e-3)
+    j1 = f.step(u8.float() / 255.0, _targets(2))
+    torch.testing.assert_close(j1, i1, rtol=1e-6, atol=1e-7)

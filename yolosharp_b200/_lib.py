@@ -68,6 +68,18 @@ SIGNATURES = {
     "yb_conv_forward_tc": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, C.c_int64, c_vp]),
     "yb_conv_backward_data_tc": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, C.c_int64, c_vp]),
     "yb_conv_backward_weight_tc": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, C.c_int64, c_vp]),
+    "yb_trainer_create": (c_i32, [C.POINTER(yb_config), C.POINTER(c_vp)]),
+    "yb_trainer_destroy": (None, [c_vp]),
+    "yb_trainer_num_tensors": (c_i32, [c_vp, c_i32]),
+    "yb_trainer_tensor_info": (c_i32, [c_vp, c_i32, c_i32, C.POINTER(c_cp), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(c_i32),
+                                       C.POINTER(C.POINTER(C.c_int64))]),
+    "yb_trainer_flat_size": (C.c_int64, [c_vp, c_i32]),
+    "yb_trainer_bind": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "yb_train_backward": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp]),
+    "yb_train_apply": (c_i32, [c_vp, c_f32, c_f32, c_f32, c_vp]),
+    "yb_train_step": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_f32, c_f32, c_f32, c_vp, c_vp]),
+    "yb_get_grad": (c_i32, [c_vp, c_cp, c_vp, C.c_int64]),
+    "yb_get_tensor": (c_i32, [c_vp, c_cp, c_vp, C.c_int64]),
     "yb_dwconv3x3_forward_f32": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "yb_dwconv3x3_backward_f32": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "yb_attention_forward_f32": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),

@@ -282,6 +282,8 @@ static int tf_conv_launch(const TfLaunch& L, cudaStream_t s) {
   const CUtensorMapSwizzle swz = a.BK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : (a.BK == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   a.n_tile = std::min(256, (L.Nc + 15) / 16 * 16);
   a.n_tiles = (L.Nc + a.n_tile - 1) / a.n_tile;
+  // (Tried: narrower N tiles for the 20 x 20 / 40 x 40 levels so that every SM gets a tile - 4.8 -> 5.1 ms over the step's
+  //  177 launches: the extra activation re-reads and shorter MMAs cost more than the idle SMs, profiles/r2_ncu_tf_conv.txt.)
   cuuint64_t gdim[4], gstr[3];
   cuuint32_t box[4], estr[4];
   if (L.flat) {
@@ -432,9 +434,10 @@ struct WgArgs {
   int nb;           // 32-channel input blocks per CTA (N = nb * 32 columns per tap)
   int co_blocks;    // 32-channel output blocks loaded per CTA (<= 4)
   int co_tiles, ci_tiles, splits;
+  int tpc, tap_groups;  // taps per CTA (3 = one kh row of a 3x3, 1 for 1x1) and groups of them
   int imgs, tiles_w, tiles_h, pix_tiles;
   int b_stages;
-  int halo;         // 3x3 stride 1: ONE (PH+2) x (PW+2) input tile per pixel tile serves all nine taps (row-shifted windows)
+  int halo;         // 3x3 stride 1: ONE PH x (PW+2) input tile per pixel tile serves the three taps of a kh row (row-shifted windows)
   uint32_t xblk;    // bytes reserved per 32-channel block of an x stage (1 KiB aligned)
   int co_pad, ci_pad;
   uint32_t tmem_cols;
@@ -474,8 +477,10 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
 
   // CTA -> (output-channel tile, input-channel tile, pixel split)
   const int split = blockIdx.x % a.splits;
-  const int pair = blockIdx.x / a.splits;
+  const int rest = blockIdx.x / a.splits;
+  const int tg = rest % a.tap_groups, pair = rest / a.tap_groups;
   const int ci_t = pair % a.ci_tiles, co_t = pair / a.ci_tiles;
+  const int tap0 = tg * a.tpc;
   const int tiles_per_img = a.tiles_w * a.tiles_h;
   const int my_tiles = split < a.pix_tiles ? (a.pix_tiles - split + a.splits - 1) / a.splits : 0;
   const int ncols = a.nb * 32;  // accumulator columns per tap
@@ -497,15 +502,17 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
           tma_load_4d(smemA + sa * a_stride + b * WG_BLK, &a.tmDz, afull + 8 * sa, co_t * 128 + b * 32, w0, h0, img);
         if (++sa == WG_A_STAGES) { sa = 0; pa ^= 1; }
         if (a.halo) {
-          // one box of (PH + 2) x (PW + 2) input pixels per 32-channel block: tap (kh, kw) of output row h reads its 8
-          // pixels from rows (h + kh) * (PW + 2) + kw .. + 7 of it
+          // one box of PH x (PW + 2) input pixels per 32-channel block for the kh row of this CTA: tap (kh, kw) of output
+          // row h reads its 8 pixels from rows h * (PW + 2) + kw .. + 7 of it
+          const int kh = tap0 / 3;
           mbar_wait(bempty + 8 * sb, pb ^ 1);
-          mbar_arrive_expect_tx(bfull + 8 * sb, (uint32_t)a.nb * (WG_PW + 2) * (WG_PH + 2) * 128);
+          mbar_arrive_expect_tx(bfull + 8 * sb, (uint32_t)a.nb * (WG_PW + 2) * WG_PH * 128);
           for (int b = 0; b < a.nb; b++)
-            tma_load_4d(smemB + sb * b_stride + b * a.xblk, &a.tmX, bfull + 8 * sb, (ci_t * a.nb + b) * 32, w0 - a.pad, h0 - a.pad, img);
+            tma_load_4d(smemB + sb * b_stride + b * a.xblk, &a.tmX, bfull + 8 * sb, (ci_t * a.nb + b) * 32, w0 - a.pad, h0 + kh - a.pad, img);
           if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
         } else {
-          for (int t = 0; t < a.taps; t++) {
+          for (int tt = 0; tt < a.tpc; tt++) {
+            const int t = tap0 + tt;
             const int kh = t / a.ksz, kw = t - kh * a.ksz;
             mbar_wait(bempty + 8 * sb, pb ^ 1);
             mbar_arrive_expect_tx(bfull + 8 * sb, (uint32_t)a.nb * WG_BLK);
@@ -537,22 +544,21 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
           mbar_wait(bfull + 8 * sb, pb);
           tc_fence_after();
           const uint32_t B0 = smemB + sb * b_stride;
-          for (int t = 0; t < 9; t++) {
-            const int kh = t / 3, kw = t - kh * 3;
-            const uint32_t d_tmem = tmem_base + t * ncols;
+          for (int kw = 0; kw < 3; kw++) {
+            const uint32_t d_tmem = tmem_base + kw * ncols;
 #pragma unroll
-            for (int ks = 0; ks < WG_PH; ks++)  // output row ks: input rows start at ((ks + kh) * (PW + 2) + kw)
+            for (int ks = 0; ks < WG_PH; ks++)  // output row ks: its 8 input pixels start at row ks * (PW + 2) + kw of the box
               umma_tf32(d_tmem, tf_desc(A0 + ks * 1024, lbo16, sbo16, 1),
-                        tf_desc(B0 + (uint32_t)((ks + kh) * (WG_PW + 2) + kw) * 128, xlbo16, sbo16, 1), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+                        tf_desc(B0 + (uint32_t)(ks * (WG_PW + 2) + kw) * 128, xlbo16, sbo16, 1), idesc, (i > 0 || ks > 0) ? 1u : 0u);
           }
           umma_commit(bempty + 8 * sb);
           if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
         } else {
-          for (int t = 0; t < a.taps; t++) {
+          for (int tt = 0; tt < a.tpc; tt++) {
             mbar_wait(bfull + 8 * sb, pb);
             tc_fence_after();
             const uint32_t B0 = smemB + sb * b_stride;
-            const uint32_t d_tmem = tmem_base + t * ncols;
+            const uint32_t d_tmem = tmem_base + tt * ncols;
 #pragma unroll
             for (int ks = 0; ks < WG_PW * WG_PH / 8; ks++)  // 8 pixels (K = 8) = 1 KiB = two 4-row swizzle atoms per block
               umma_tf32(d_tmem, tf_desc(A0 + ks * 1024, lbo16, sbo16, 1), tf_desc(B0 + ks * 1024, xlbo16, sbo16, 1), idesc,
@@ -574,11 +580,12 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
       tc_fence_after();
     }
     float* prow = a.part + (((size_t)split * a.co_pad + co) * a.taps) * a.ci_pad + (size_t)ci_t * ncols;
-    for (int t = 0; t < a.taps; t++)
+    for (int tt = 0; tt < a.tpc; tt++)
       for (int c0 = 0; c0 < ncols; c0 += 16) {
+        const int t = tap0 + tt;
         uint32_t v[16];
         if (my_tiles > 0) {
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + t * ncols + c0, v);
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tt * ncols + c0, v);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -615,14 +622,16 @@ __global__ void tf_wgrad_fold_kernel(const float* __restrict__ part, float* __re
   }
 }
 
-struct WgPlan { int nb, co_tiles, ci_tiles, splits, co_pad, ci_pad, pix_tiles, tiles_w, tiles_h; };
+struct WgPlan { int nb, co_tiles, ci_tiles, splits, co_pad, ci_pad, pix_tiles, tiles_w, tiles_h, tpc, tap_groups; };
 static WgPlan wg_plan(int N, int H, int W, int Cin, int Cout, int k, int stride, int pad) {
   WgPlan p;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const int taps = k * k;
   const int ci_blocks = (Cin + 31) / 32;
-  p.nb = std::max(1, std::min(ci_blocks, 256 / (32 * taps) > 0 ? 256 / (32 * taps) : 1));  // taps * nb * 32 <= 288 columns
-  if (taps == 1) p.nb = std::min(ci_blocks, 4);  // 4 x 8 KiB per stage: three stages beside the dz ring
+  // a CTA owns 128 output channels x (tpc taps x nb * 32 input channels) in TMEM: tpc = 3 (one kh row of a 3x3) x up to
+  // 128 channels = 384 columns.  (The first version kept all nine taps of 32 input channels: N = 32 per MMA, and a
+  // TF32 M=128 MMA costs ~110 cycles whatever its N - 8.7 % tensor activity, profiles/r2_ncu_tf_wgrad.txt.)
+  p.nb = std::min(ci_blocks, 4);
   p.ci_tiles = (ci_blocks + p.nb - 1) / p.nb;
   p.co_tiles = (Cout + 127) / 128;
   p.co_pad = p.co_tiles * 128;
@@ -630,7 +639,9 @@ static WgPlan wg_plan(int N, int H, int W, int Cin, int Cout, int k, int stride,
   p.tiles_w = (Wo + WG_PW - 1) / WG_PW;
   p.tiles_h = (Ho + WG_PH - 1) / WG_PH;
   p.pix_tiles = N * p.tiles_w * p.tiles_h;
-  const int pairs = p.co_tiles * p.ci_tiles;
+  p.tpc = taps == 9 ? 3 : 1;
+  p.tap_groups = taps / p.tpc;
+  const int pairs = p.co_tiles * p.ci_tiles * p.tap_groups;
   p.splits = std::max(1, std::min(p.pix_tiles, (2 * tf_num_sms() + pairs - 1) / pairs));
   p.splits = std::min(p.splits, 64);
   return p;
@@ -657,6 +668,7 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
   a.part = ws;
   a.Cout = Cout; a.Cin = Cin; a.taps = k * k; a.ksz = k; a.stride = stride; a.pad = pad;
   a.nb = p.nb; a.co_tiles = p.co_tiles; a.ci_tiles = p.ci_tiles; a.splits = p.splits;
+  a.tpc = p.tpc; a.tap_groups = p.tap_groups;
   a.co_blocks = std::min(4, (Cout + 31) / 32);
   a.imgs = N; a.tiles_w = p.tiles_w; a.tiles_h = p.tiles_h; a.pix_tiles = p.pix_tiles;
   a.co_pad = p.co_pad; a.ci_pad = p.ci_pad;
@@ -666,12 +678,12 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
   // of conv_tc.cu does for the 16-byte-atom modes; tests/test_gpu_conv_tc.py's bit-exact case covers it.
   static const bool no_halo = getenv("YB_WGRAD_NO_HALO") != nullptr;
   a.halo = (k == 3 && stride == 1 && !no_halo) ? 1 : 0;
-  a.xblk = a.halo ? (uint32_t)(((WG_PW + 2) * (WG_PH + 2) * 128 + 1023) / 1024 * 1024) : (uint32_t)WG_BLK;
+  a.xblk = a.halo ? (uint32_t)(((WG_PW + 2) * WG_PH * 128 + 1023) / 1024 * 1024) : (uint32_t)WG_BLK;
   const size_t b_stride = (size_t)p.nb * a.xblk;
   a.b_stages = (int)std::min<size_t>(16, ((size_t)190 * 1024 - (size_t)WG_A_STAGES * 4 * WG_BLK) / b_stride);
   if (a.b_stages < 2) { set_error("tf32 wgrad: tile does not fit in shared memory"); return YB_ERR_SHAPE; }
   uint32_t cols = 32;
-  while (cols < (uint32_t)(a.taps * p.nb * 32)) cols <<= 1;
+  while (cols < (uint32_t)(a.tpc * p.nb * 32)) cols <<= 1;
   a.tmem_cols = cols;
   {
     cuuint64_t gd[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
@@ -685,7 +697,7 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
   {
     cuuint64_t gd[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t gs[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cin * 4 * W, (cuuint64_t)Cin * 4 * W * H};
-    cuuint32_t bx[4] = {32, (cuuint32_t)(a.halo ? WG_PW + 2 : WG_PW * stride), (cuuint32_t)(a.halo ? WG_PH + 2 : WG_PH * stride), 1};
+    cuuint32_t bx[4] = {32, (cuuint32_t)(a.halo ? WG_PW + 2 : WG_PW * stride), (cuuint32_t)(a.halo ? WG_PH : WG_PH * stride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult cr = encode(&a.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -697,7 +709,7 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
     attr_set = true;
   }
   const size_t smem = (size_t)WG_A_STAGES * 4 * WG_BLK + (size_t)a.b_stages * b_stride + 1024;
-  const int grid = p.co_tiles * p.ci_tiles * p.splits;
+  const int grid = p.co_tiles * p.ci_tiles * p.tap_groups * p.splits;
   tf_wgrad_kernel<<<grid, TF_THREADS, smem, s>>>(a);
   YB_CUDA_CHECK(cudaGetLastError());
   const size_t n = (size_t)Cout * Cin * k * k;

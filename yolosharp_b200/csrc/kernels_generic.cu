@@ -769,13 +769,13 @@ __global__ void __launch_bounds__(256) attention_kernel(View qkv, View out, View
 // (6 400 CTAs x 77 KB and 100 block-wide barriers each for YOLOv11s at batch 32: 0.88 ms, 19 % of the forward).  A first
 // tiled version with scalar shared-memory reads was no faster (1.0 ms): three LDS per two FMAs made it shared-memory
 // bound.  This one is register-blocked:
-//   * a CTA owns 16 query rows of one (head, image); K (row stride 36 floats) and V (stride 64) stay resident as fp32
+//   * a CTA (16 warps) owns 32 query rows of one (head, image); K (row stride 36 floats) and V (stride 64) stay resident as fp32
 //   * scores: a warp owns 2 query rows, held in 64 registers; a lane owns one key per block of 32 and reads its K row
 //     with 8 conflict-free LDS.128 -> 64 FMAs per 8 loads
 //   * P.V: a lane owns channels 2*lane, 2*lane+1 for both rows; per 4 keys: 4 LDS.64 of V + 2 broadcast LDS.128 of P
 //     for 16 FMAs
 // Per-output summation order is unchanged (sequential over d, then over j).
-constexpr int ATI_T = 16, ATI_KD = 32, ATI_HD = 64, ATI_LDK = 36;
+constexpr int ATI_T = 32, ATI_KD = 32, ATI_HD = 64, ATI_LDK = 36, ATI_THREADS = 512;  // 16 warps x 2 query rows
 __device__ __forceinline__ float4 lds128(const float* p) { return *reinterpret_cast<const float4*>(p); }
 // four consecutive elements (16 / 8 bytes, aligned) as fp32: one vector load instead of four scalar ones - the scalar
 // fill of K and V made every warp instruction touch 16 sectors for 128 useful bytes and cost 2/3 of the kernel
@@ -791,7 +791,7 @@ template <> __device__ __forceinline__ void cp4<float>(float* dst, const float* 
 template <> __device__ __forceinline__ void cp4<__half>(__half* dst, const __half* src) { *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src); }
 
 template <typename T>
-__global__ void __launch_bounds__(256) attention_tiled_32x64_kernel(AttnIO io, int N, int nh, float scale) {
+__global__ void __launch_bounds__(ATI_THREADS, 1) attention_tiled_32x64_kernel(AttnIO io, int N, int nh, float scale) {
   extern __shared__ __align__(16) float at_smem[];
   const int NK = (N + 31) & ~31, NP = (N + 3) & ~3;
   float* Ks = at_smem;                          // [NK][36], rows >= N zero
@@ -808,40 +808,44 @@ __global__ void __launch_bounds__(256) attention_tiled_32x64_kernel(AttnIO io, i
   // SM a load-convert-store loop exposes the full L2 latency on every iteration: 38 iterations x ~700 cycles was 2/3 of
   // the kernel)
   constexpr int U = 8;
-  for (int t0 = threadIdx.x; t0 < NK * (ATI_KD / 4); t0 += 256 * U) {
+  for (int t0 = threadIdx.x; t0 < NK * (ATI_KD / 4); t0 += ATI_THREADS * U) {
     float4 f[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const int t = t0 + u * 256, j = t >> 3, d = (t & 7) * 4;
+      const int t = t0 + u * ATI_THREADS, j = t >> 3, d = (t & 7) * 4;
       f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (t < NK * (ATI_KD / 4) && j < N) f[u] = ld4<T>(kb + (size_t)j * io.in_tok + d);
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const int t = t0 + u * 256, j = t >> 3, d = (t & 7) * 4;
+      const int t = t0 + u * ATI_THREADS, j = t >> 3, d = (t & 7) * 4;
       if (t < NK * (ATI_KD / 4)) *reinterpret_cast<float4*>(Ks + (size_t)j * ATI_LDK + d) = f[u];
     }
   }
-  for (int t0 = threadIdx.x; t0 < NP * (ATI_HD / 4); t0 += 256 * U) {
+  for (int t0 = threadIdx.x; t0 < NP * (ATI_HD / 4); t0 += ATI_THREADS * U) {
     float4 f[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const int t = t0 + u * 256, j = t >> 4, d = (t & 15) * 4;
+      const int t = t0 + u * ATI_THREADS, j = t >> 4, d = (t & 15) * 4;
       f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (t < NP * (ATI_HD / 4) && j < N) {
-        const T* src = vb + (size_t)j * io.v_tok + d;
-        f[u] = ld4<T>(src);
-        if (vo && j >= i0 && j < i0 + ATI_T)  // the dense copy of v the positional-encoding conv reads
-          cp4<T>(vo + (size_t)b * io.out_img + (size_t)j * io.out_tok + head * ATI_HD + d, src);
+        f[u] = ld4<T>(vb + (size_t)j * io.v_tok + d);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const int t = t0 + u * 256, j = t >> 4, d = (t & 15) * 4;
+      const int t = t0 + u * ATI_THREADS, j = t >> 4, d = (t & 15) * 4;
       if (t < NP * (ATI_HD / 4)) *reinterpret_cast<float4*>(Vs + (size_t)j * ATI_HD + d) = f[u];
     }
   }
-  for (int t = threadIdx.x; t < ATI_T * ATI_KD; t += 256) {
+  // the dense copy of v that the positional-encoding conv reads: this CTA's 32 rows, one vector per thread.  (Inside the
+  // fill loop above these stores sat between the batched loads and each waited for its own load: 45 % of the kernel's
+  // stall samples, profiles/r2_ncu_attention_tiled.txt.)
+  if (vo) {
+    const int r = threadIdx.x >> 4, d = (threadIdx.x & 15) * 4, j = i0 + r;
+    if (j < N) cp4<T>(vo + (size_t)b * io.out_img + (size_t)j * io.out_tok + head * ATI_HD + d, vb + (size_t)j * io.v_tok + d);
+  }
+  for (int t = threadIdx.x; t < ATI_T * ATI_KD; t += ATI_THREADS) {
     const int r = t >> 5, d = t & 31;
     Qs[t] = (i0 + r < N) ? to_f<T>(qb[(size_t)(i0 + r) * io.in_tok + d]) : 0.f;
   }
@@ -912,16 +916,16 @@ static size_t ati_smem_bytes(int N) {
   const size_t NK = (N + 31) & ~31, NP = (N + 3) & ~3;
   return (NK * ATI_LDK + NP * ATI_HD + (size_t)ATI_T * ATI_KD + (size_t)ATI_T * NP) * sizeof(float);
 }
-bool attention_tiled_32x64_fits(int N) { return ati_smem_bytes(N) <= 200 * 1024; }
+bool attention_tiled_32x64_fits(int N) { return ati_smem_bytes(N) <= 227 * 1024; }
 
 template <typename T>
 int launch_attention_tiled_32x64(const AttnIO& io, int B, int N, int nh, float scale, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    YB_CUDA_CHECK(cudaFuncSetAttribute(attention_tiled_32x64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    YB_CUDA_CHECK(cudaFuncSetAttribute(attention_tiled_32x64_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  attention_tiled_32x64_kernel<T><<<dim3((N + ATI_T - 1) / ATI_T, nh, B), 256, ati_smem_bytes(N), s>>>(io, N, nh, scale);
+  attention_tiled_32x64_kernel<T><<<dim3((N + ATI_T - 1) / ATI_T, nh, B), ATI_THREADS, ati_smem_bytes(N), s>>>(io, N, nh, scale);
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
