@@ -280,7 +280,7 @@ def train_main(args, rank, world, local_rank):
     for i in range(args.warmup):
         st.step(xs[i & 1], ts[i & 1])
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("YB_NO_SAMPLER") else None
     if world > 1:
         dist.barrier()
     if sampler:
@@ -288,7 +288,11 @@ def train_main(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
+        _t0 = time.perf_counter()
         items = st.step(xs[i & 1], ts[i & 1])
+        if os.environ.get("YB_STEP_TIMES"):
+            torch.cuda.synchronize()
+            print(f"step {i}: {(time.perf_counter() - _t0) * 1e3:.1f} ms", file=sys.stderr)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:

@@ -49,14 +49,23 @@ def _run_pair(arch, B, H, W, py_cls, ops_cls):
 def _check(a, b, ia, ib):
     torch.testing.assert_close(ib, ia, rtol=1e-5, atol=1e-6)
     gmax = float(a.P.grad.abs().max())
-    worst = ("", 0.0)
+    errs = []
     for k in a.P.names:
         ga, gb = a.P.g(k), b.g(k)
-        err = float((gb - ga).abs().max()) / max(float(ga.abs().max()), 1e-4 * gmax)
-        worst = max(worst, (k, err), key=lambda t: t[1])
+        # same kernels, but the native walk writes through channel-slice views where the Python walk copies, so a few sums
+        # are formed in another order: tensors whose gradient is mathematically ~0 (the BatchNorm bias of SPPF.cv1, see
+        # test_train_step._compare) differ by their rounding noise - judged against the step's gradient scale
+        errs.append((float((gb - ga).abs().max()) / max(float(ga.abs().max()), 1e-3 * gmax), k))
         torch.testing.assert_close(b.p(k), a.P.p(k), rtol=1e-5, atol=2.1e-3)  # Adam's first step: +-lr on a sign flip of a ~0 gradient
-    print(f"worst parameter gradient vs the Python step: {worst[0]} {worst[1]:.2e}")
-    assert worst[1] < 1e-4, worst
+    errs.sort(reverse=True)
+    ga, gb = a.P.grad.double(), torch.cat([b.g(k).reshape(-1) for k in a.P.names]).double()
+    l2 = float((gb - ga).norm() / ga.norm())
+    print("worst parameter gradients vs the Python step: " + ", ".join(f"{k} {e:.2e}" for e, k in errs[:3]) + f"; flat rel L2 {l2:.2e}")
+    # same kernels in the same order: bit-level agreement (the nearest-2x upsample backward sums its 2 x 2 block in ATen's
+    # order for that reason).  Input sizes are the ones at which the Python walk itself is run-to-run deterministic - its
+    # max-pool backward is ATen's atomicAdd kernel, and at 128 x 160 two Python steps differ from each other by 1e-3 of the
+    # flat gradient (tools/dbg_native_determinism.py); the native step is bitwise reproducible at every size.
+    assert l2 < 1e-6 and errs[0][0] < 1e-4, (l2, errs[:4])
     for k, v in a.P.buffers.items():
         torch.testing.assert_close(b.p(k), v, rtol=1e-5, atol=1e-6)
 
@@ -70,7 +79,7 @@ def test_native_train_step_v8_matches_python_step():
 @pytest.mark.gpu
 def test_native_train_step_v11_matches_python_step():
     from yolosharp_b200.train_v11 import KernelOpsV11, TrainStepV11
-    _check(*_run_pair("v11", 2, 64, 64, TrainStepV11, KernelOpsV11))
+    _check(*_run_pair("v11", 2, 128, 128, TrainStepV11, KernelOpsV11))
 
 
 @pytest.mark.gpu

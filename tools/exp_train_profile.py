@@ -14,11 +14,16 @@ from yolosharp_b200.train_v11 import KernelOpsV11, TrainStepV11  # noqa: E402
 
 model = sys.argv[1] if len(sys.argv) > 1 else "v11s"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-tc = (sys.argv[3] if len(sys.argv) > 3 else "tc") == "tc"
+mode = sys.argv[3] if len(sys.argv) > 3 else "tc"   # tc | f32 (Python graph walk) | native (csrc/train_step.cu)
+tc = mode != "f32"
 arch, size, task, _ = MODELS[model]
 dev = torch.device("cuda", 0)
 m = oracle_model(arch, task, size)
-st = TrainStepV11({k: v.detach().clone() for k, v in m.state_dict().items()}, size, 80, device=dev, ops=KernelOpsV11(tensor_cores=tc))
+if mode == "native":
+    from yolosharp_b200.train_native import NativeTrainer
+    st = NativeTrainer({k: v.detach().clone() for k, v in m.state_dict().items()}, "v11", size, 80, device=dev, max_batch=B)
+else:
+    st = TrainStepV11({k: v.detach().clone() for k, v in m.state_dict().items()}, size, 80, device=dev, ops=KernelOpsV11(tensor_cores=tc))
 x, t = synth_image(B, 640, 640, seed=1).to(dev), synth_targets(B, 2)
 for _ in range(2):
     st.step(x, t)
@@ -28,7 +33,7 @@ e0.record()
 st.step(x, t)
 e1.record()
 torch.cuda.synchronize()
-print(f"# {model} batch {B} kernels {'tc' if tc else 'f32'}: step {e0.elapsed_time(e1):.2f} ms (CUDA events)")
+print(f"# {model} batch {B} {mode}: step {e0.elapsed_time(e1):.2f} ms (CUDA events)")
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     st.step(x, t)
     torch.cuda.synchronize()
@@ -36,5 +41,5 @@ rows = [(e.key, e.device_time_total / 1e3, e.count) for e in prof.key_averages()
 rows.sort(key=lambda r: -r[1])
 tot = sum(r[1] for r in rows)
 print(f"# device time {tot:.2f} ms in {sum(r[2] for r in rows)} kernels")
-for k, ms, n in rows[:25]:
+for k, ms, n in rows[:30]:
     print(f"{ms:9.3f} ms {100 * ms / tot:5.1f}% {n:5d}x  {k[:110]}")

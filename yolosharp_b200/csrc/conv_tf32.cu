@@ -253,6 +253,7 @@ static int tf_num_sms() {
 // One launch of tf_conv_kernel.  in: NHWC (N, Hi, Wi, Kc) fp32; wpk: [taps][Nc][Kc] fp32; out addressing given by strides.
 struct TfLaunch {
   const float* in; int N, Hi, Wi, Kc;
+  int in_pitch;      // elements between consecutive pixels of `in` (>= Kc: `in` may be a channel slice of a wider NHWC buffer)
   const float* wpk; int Nc, taps_total;
   float* out; long long o_img, o_row, o_pix, o_off;
   const float* bias;
@@ -289,14 +290,14 @@ static int tf_conv_launch(const TfLaunch& L, cudaStream_t s) {
   if (L.flat) {
     const cuuint64_t npix = (cuuint64_t)L.N * L.Hi * L.Wi;
     gdim[0] = L.Kc; gdim[1] = npix; gdim[2] = 1; gdim[3] = 1;
-    gstr[0] = (cuuint64_t)L.Kc * 4; gstr[1] = gstr[0] * npix; gstr[2] = gstr[1];
+    gstr[0] = (cuuint64_t)(L.in_pitch ? L.in_pitch : L.Kc) * 4; gstr[1] = gstr[0] * npix; gstr[2] = gstr[1];
     a.BW = 128; a.BH = 1;
     a.imgs = 1; a.Ho = 1; a.Wo = (int)npix;
     box[0] = a.BK; box[1] = 128; box[2] = 1; box[3] = 1;
     estr[0] = estr[1] = estr[2] = estr[3] = 1;
   } else {
     gdim[0] = L.Kc; gdim[1] = L.Wi; gdim[2] = L.Hi; gdim[3] = L.N;
-    gstr[0] = (cuuint64_t)L.Kc * 4; gstr[1] = gstr[0] * L.Wi; gstr[2] = gstr[1] * L.Hi;
+    gstr[0] = (cuuint64_t)(L.in_pitch ? L.in_pitch : L.Kc) * 4; gstr[1] = gstr[0] * L.Wi; gstr[2] = gstr[1] * L.Hi;
     a.imgs = L.N; a.Ho = L.Ho; a.Wo = L.Wo;
     double best = -1;
     for (int bw = 1; bw <= std::min(L.Wo, 128); bw++) {
@@ -352,14 +353,15 @@ static bool tf_shape_ok(int Cin, int Cout, int k, int stride, int pad) {
 }
 
 int tf_conv_forward(const float* x, const float* w, const float* bias, int N, int H, int W, int Cin, int Cout, int k, int stride,
-                    int pad, float* z, float* ws, size_t ws_bytes, cudaStream_t s) {
+                    int pad, float* z, float* ws, size_t ws_bytes, cudaStream_t s, int x_pitch) {
+  if (x_pitch && (x_pitch < Cin || x_pitch % 4 || ((uintptr_t)x & 15))) { set_error("tf32 conv: input view must be 16-byte aligned with a pitch multiple of 4"); return YB_ERR_SHAPE; }
   if (!tf_shape_ok(Cin, Cout, k, stride, pad)) { set_error("tf32 conv: channels must be multiples of 8, k in {1,3}, stride in {1,2}, pad = k/2"); return YB_ERR_SHAPE; }
   const size_t wn = (size_t)Cout * Cin * k * k;
   if (ws_bytes < wn * 4) { set_error("tf32 conv forward: workspace too small"); return YB_ERR_INVALID_ARG; }
   tf_pack_weights_kernel<<<(unsigned)std::min<size_t>((wn + 255) / 256, 1024), 256, 0, s>>>(w, ws, nullptr, Cout, Cin, k * k);
   TfLaunch L;
   memset(&L, 0, sizeof(L));
-  L.in = x; L.N = N; L.Hi = H; L.Wi = W; L.Kc = Cin;
+  L.in = x; L.N = N; L.Hi = H; L.Wi = W; L.Kc = Cin; L.in_pitch = x_pitch;
   L.wpk = ws; L.Nc = Cout; L.taps_total = k * k;
   L.Ho = (H + 2 * pad - k) / stride + 1; L.Wo = (W + 2 * pad - k) / stride + 1;
   L.out = z; L.o_pix = Cout; L.o_row = (long long)L.Wo * Cout; L.o_img = (long long)L.Ho * L.o_row; L.o_off = 0;
@@ -608,17 +610,21 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
   }
 }
 
-// dw[co][ci][tap] = sum over splits (fixed order) of part[split][co][tap][ci]
+// dw[co][ci][tap] = sum over splits (fixed order) of part[split][co][tap][ci].  Threads run over (co, tap, ci) with ci
+// fastest, so the `splits` reads per output are coalesced (the partials are `splits` times the size of the result; the
+// scattered write happens once).
 __global__ void tf_wgrad_fold_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cout, int Cin, int taps, int splits,
                                      int co_pad, int ci_pad) {
   const long long n = (long long)Cout * Cin * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(i % taps);
-    const long long q = i / taps;
-    const int ci = (int)(q % Cin), co = (int)(q / Cin);
+    const int ci = (int)(i % Cin);
+    const long long q = i / Cin;
+    const int t = (int)(q % taps), co = (int)(q / taps);
+    const float* src = part + ((size_t)co * taps + t) * ci_pad + ci;
+    const size_t sstride = (size_t)co_pad * taps * ci_pad;
     float acc = 0.f;
-    for (int s = 0; s < splits; s++) acc += part[(((size_t)s * co_pad + co) * taps + t) * ci_pad + ci];
-    dw[i] = acc;
+    for (int s = 0; s < splits; s++) acc += src[(size_t)s * sstride];
+    dw[((size_t)co * Cin + ci) * taps + t] = acc;
   }
 }
 
@@ -655,7 +661,9 @@ size_t tf_conv_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, in
 }
 
 int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
-                            float* dw, float* ws, size_t ws_bytes, cudaStream_t s) {
+                            float* dw, float* ws, size_t ws_bytes, cudaStream_t s, int x_pitch) {
+  if (x_pitch && (x_pitch < Cin || x_pitch % 4 || ((uintptr_t)x & 15))) { set_error("tf32 wgrad: input view must be 16-byte aligned with a pitch multiple of 4"); return YB_ERR_SHAPE; }
+  const int xp = x_pitch ? x_pitch : Cin;
   if (!tf_shape_ok(Cin, Cout, k, stride, pad)) { set_error("tf32 wgrad: channels must be multiples of 8, k in {1,3}, stride in {1,2}, pad = k/2"); return YB_ERR_SHAPE; }
   TfEncodeFn encode = tf_encode_fn();
   if (!encode) { set_error("cuTensorMapEncodeTiled entry point not found"); return YB_ERR_CUDA; }
@@ -696,7 +704,7 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
   }
   {
     cuuint64_t gd[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t gs[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cin * 4 * W, (cuuint64_t)Cin * 4 * W * H};
+    cuuint64_t gs[3] = {(cuuint64_t)xp * 4, (cuuint64_t)xp * 4 * W, (cuuint64_t)xp * 4 * W * H};
     cuuint32_t bx[4] = {32, (cuuint32_t)(a.halo ? WG_PW + 2 : WG_PW * stride), (cuuint32_t)(a.halo ? WG_PH : WG_PH * stride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult cr = encode(&a.tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -748,7 +756,7 @@ int32_t yb_conv_forward_tc(const float* x, const float* w, const float* bias, in
   if (n <= 0 || height <= 0 || width <= 0 || cin <= 0 || cout <= 0) { set_error("yb_conv_forward_tc: bad shape"); return YB_ERR_SHAPE; }
   if (!tf_have_dev("yb_conv_forward_tc")) return YB_ERR_NO_DEVICE;
   return tf_conv_forward(x, w, bias, n, height, width, cin, cout, k, stride, pad, z, (float*)workspace, (size_t)workspace_bytes,
-                         (cudaStream_t)stream);
+                         (cudaStream_t)stream, 0);
 }
 
 int32_t yb_conv_backward_data_tc(const float* dz, const float* w, int32_t n, int32_t height, int32_t width, int32_t cin, int32_t cout,
@@ -768,7 +776,7 @@ int32_t yb_conv_backward_weight_tc(const float* x, const float* dz, int32_t n, i
   if (n <= 0 || height <= 0 || width <= 0 || cin <= 0 || cout <= 0) { set_error("yb_conv_backward_weight_tc: bad shape"); return YB_ERR_SHAPE; }
   if (!tf_have_dev("yb_conv_backward_weight_tc")) return YB_ERR_NO_DEVICE;
   return tf_conv_backward_weight(x, dz, n, height, width, cin, cout, k, stride, pad, dw, (float*)workspace, (size_t)workspace_bytes,
-                                 (cudaStream_t)stream);
+                                 (cudaStream_t)stream, 0);
 }
 
 }  // extern "C"

@@ -30,11 +30,11 @@ namespace yb {
 
 // entry points of the other translation units this step is made of
 int tf_conv_forward(const float* x, const float* w, const float* bias, int N, int H, int W, int Cin, int Cout, int k, int stride,
-                    int pad, float* z, float* ws, size_t ws_bytes, cudaStream_t s);
+                    int pad, float* z, float* ws, size_t ws_bytes, cudaStream_t s, int x_pitch);
 int tf_conv_backward_data(const float* dz, const float* w, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                           float* dx, float* ws, size_t ws_bytes, cudaStream_t s);
 int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
-                            float* dw, float* ws, size_t ws_bytes, cudaStream_t s);
+                            float* dw, float* ws, size_t ws_bytes, cudaStream_t s, int x_pitch);
 size_t tf_conv_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride);
 int dwconv3x3_forward_f32(const float* x, const float* w, int N, int H, int W, int C, float* z, cudaStream_t s);
 int dwconv3x3_backward_f32(const float* x, const float* dz, const float* w, int N, int H, int W, int C, float* dx, float* dw,
@@ -60,23 +60,29 @@ __global__ void slice_copy_kernel(float* __restrict__ dst, int dpitch, int dcoff
   float* d = dst + r * dpitch + dcoff + c;
   *d = accumulate ? *d + v : v;
 }
-__global__ void add_kernel(float* __restrict__ out, const float* __restrict__ a, const float* __restrict__ b, long long n) {
+// out = a + b on channel-slice views (row pitches may differ)
+__global__ void add_kernel(float* __restrict__ out, int opitch, const float* __restrict__ a, int apitch, const float* __restrict__ b,
+                           int bpitch, long long rows, int C) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = a[i] + b[i];
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = (int)(i - r * C);
+  out[r * opitch + c] = a[r * apitch + c] + b[r * bpitch + c];
 }
 // nearest 2x upsample (Yolo.cs:70-84 `Upsample(scale_factor: 2)`), NHWC
-__global__ void up2_forward_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C) {
+__global__ void up2_forward_kernel(const float* __restrict__ x, int xpitch, float* __restrict__ y, int ypitch, int N, int H, int W, int C) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)N * 2 * H * 2 * W * C;
   if (i >= n) return;
   const int c = (int)(i % C);
-  long long p = i / C;
+  const long long po = i / C;
+  long long p = po;
   const int wo = (int)(p % (2 * W)); p /= 2 * W;
   const int ho = (int)(p % (2 * H));
   const int b = (int)(p / (2 * H));
-  y[i] = x[(((long long)b * H + ho / 2) * W + wo / 2) * C + c];
+  y[po * ypitch + c] = x[(((long long)b * H + ho / 2) * W + wo / 2) * xpitch + c];
 }
-__global__ void up2_backward_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C) {
+__global__ void up2_backward_kernel(const float* __restrict__ dy, int dpitch, float* __restrict__ dx, int N, int H, int W, int C) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)N * H * W * C;
   if (i >= n) return;
@@ -85,14 +91,17 @@ __global__ void up2_backward_kernel(const float* __restrict__ dy, float* __restr
   const int w = (int)(p % W); p /= W;
   const int h = (int)(p % H);
   const int b = (int)(p / H);
-  const float* r0 = dy + (((long long)b * 2 * H + 2 * h) * 2 * W + 2 * w) * C + c;
-  const float* r1 = r0 + (long long)2 * W * C;
-  dx[i] = (r0[0] + r0[C]) + (r1[0] + r1[C]);  // the 2 x 2 block in row-major order, as `sum((2, 4))` of the reshaped tensor
+  const float* r0 = dy + (((long long)b * 2 * H + 2 * h) * 2 * W + 2 * w) * dpitch + c;
+  const float* r1 = r0 + (long long)2 * W * dpitch;
+  // the 2 x 2 block summed sequentially in row-major order: the order of ATen's `sum((2, 4))` on the reshaped tensor.  (A
+  // pairwise sum differs in the last bit of a few elements; through ~25 TF32 layers of backward that grew to 1e-3 of the
+  // flat gradient - tools/dbg_native_determinism.py - so the order is part of the specification.)
+  dx[i] = ((r0[0] + r0[dpitch]) + r1[0]) + r1[dpitch];  // the 2 x 2 block in row-major order, as `sum((2, 4))` of the reshaped tensor
 }
 // MaxPool2d(5, 1, 2) (Block.cs:275-279), NHWC, -inf padding; idx = flattened input position h * W + w of the maximum
 // (first maximum in (kh, kw) scan order, as ATen's max_pool2d_with_indices)
-__global__ void pool5_forward_kernel(const float* __restrict__ x, float* __restrict__ y, int* __restrict__ idx, int N, int H, int W,
-                                     int C) {
+__global__ void pool5_forward_kernel(const float* __restrict__ x, int xpitch, float* __restrict__ y, int ypitch, int* __restrict__ idx, int N,
+                                     int H, int W, int C) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)N * H * W * C;
   if (i >= n) return;
@@ -109,17 +118,17 @@ __global__ void pool5_forward_kernel(const float* __restrict__ x, float* __restr
     for (int dw = -2; dw <= 2; dw++) {
       const int ww = w + dw;
       if (ww < 0 || ww >= W) continue;
-      const float v = x[(((long long)b * H + hh) * W + ww) * C + c];
+      const float v = x[(((long long)b * H + hh) * W + ww) * xpitch + c];
       if (v > m || mi < 0 || v != v) { m = v; mi = hh * W + ww; }
     }
   }
-  y[i] = m;
+  y[(i / C) * ypitch + c] = m;
   idx[i] = mi;
 }
 // backward as a gather: input position (h, w) receives the gradient of every output in its 5 x 5 neighbourhood whose
 // argmax it is, summed in (dh, dw) order - deterministic, no atomics
-__global__ void pool5_backward_kernel(const float* __restrict__ dy, const int* __restrict__ idx, float* __restrict__ dx, int N, int H,
-                                      int W, int C) {
+__global__ void pool5_backward_kernel(const float* __restrict__ dy, int dpitch, const int* __restrict__ idx, float* __restrict__ dx, int N,
+                                      int H, int W, int C) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)N * H * W * C;
   if (i >= n) return;
@@ -136,8 +145,8 @@ __global__ void pool5_backward_kernel(const float* __restrict__ dy, const int* _
     for (int dw = -2; dw <= 2; dw++) {
       const int ww = w + dw;
       if (ww < 0 || ww >= W) continue;
-      const long long o = (((long long)b * H + hh) * W + ww) * C + c;
-      if (idx[o] == me) acc += dy[o];
+      const long long o = ((long long)b * H + hh) * W + ww;
+      if (idx[o * C + c] == me) acc += dy[o * dpitch + c];
     }
   }
   dx[i] = acc;
@@ -220,12 +229,21 @@ static inline unsigned nb(long long n, int t = 256) { return (unsigned)((n + t -
 // ---------------------------------------------------------------------------------------------------------------
 // tensors, arena, parameters
 // ---------------------------------------------------------------------------------------------------------------
+// NHWC tensor or a channel-slice VIEW of one: element (n, h, w, c) at p[((n*H + h)*W + w) * pitch + c].  Views replace the
+// chunk / cat copies of the graph (Block.cs:391-396): producers write their slice of the concat buffer, consumers read theirs.
 struct T4 {
   float* p = nullptr;
-  int N = 0, H = 0, W = 0, C = 0;
+  int N = 0, H = 0, W = 0, C = 0, pitch = 0;
   long long rows() const { return (long long)N * H * W; }
   long long numel() const { return rows() * C; }
+  bool dense() const { return pitch == C; }
 };
+static T4 view(const T4& t, int c0, int C) {
+  T4 v = t;
+  v.p = t.p + c0;
+  v.C = C;
+  return v;
+}
 
 struct Entry { std::string name; std::vector<int64_t> shape; long long off = 0, count = 0; int kind = 0; };  // kind 0 parameter, 1 running stat
 
@@ -251,7 +269,7 @@ struct Net {
     return p;
   }
   T4 make(int N_, int H_, int W_, int C_) {
-    T4 t; t.N = N_; t.H = H_; t.W = W_; t.C = C_;
+    T4 t; t.N = N_; t.H = H_; t.W = W_; t.C = C_; t.pitch = C_;
     t.p = alloc(t.numel());
     return t;
   }
@@ -262,32 +280,36 @@ struct Net {
   void check_launch() { if (!rc && cudaGetLastError() != cudaSuccess) { rc = YB_ERR_CUDA; set_error("yb_train_step: kernel launch failed"); } }
 };
 
-static T4 slice(Net& n, const T4& x, int c0, int C) {  // contiguous copy of channels [c0, c0 + C)
-  T4 y = n.make(x.N, x.H, x.W, C);
-  if (n.rc) return y;
-  slice_copy_kernel<<<nb(y.numel()), 256, 0, n.s>>>(y.p, C, 0, x.p, x.C, c0, x.rows(), C, 0);
-  n.check_launch();
-  return y;
-}
 static void put(Net& n, const T4& dst, int c0, const T4& src, bool accumulate = false) {  // dst[..., c0 : c0 + src.C] (+)= src
   if (n.rc) return;
-  slice_copy_kernel<<<nb(src.numel()), 256, 0, n.s>>>(dst.p, dst.C, c0, src.p, src.C, 0, src.rows(), src.C, accumulate ? 1 : 0);
+  slice_copy_kernel<<<nb(src.numel()), 256, 0, n.s>>>(dst.p, dst.pitch, c0, src.p, src.pitch, 0, src.rows(), src.C, accumulate ? 1 : 0);
+  n.check_launch();
+}
+static T4 dense_copy(Net& n, const T4& x) {  // contiguous copy of a view (kernels that take no pitch)
+  if (x.dense()) return x;
+  T4 y = n.make(x.N, x.H, x.W, x.C);
+  put(n, y, 0, x);
+  return y;
+}
+static void add_into(Net& n, const T4& out, const T4& a, const T4& b) {
+  if (n.rc) return;
+  add_kernel<<<nb(a.numel()), 256, 0, n.s>>>(out.p, out.pitch, a.p, a.pitch, b.p, b.pitch, a.rows(), a.C);
   n.check_launch();
 }
 static T4 add(Net& n, const T4& a, const T4& b) {
   T4 y = n.make(a.N, a.H, a.W, a.C);
-  if (n.rc) return y;
-  add_kernel<<<nb(y.numel()), 256, 0, n.s>>>(y.p, a.p, b.p, y.numel());
-  n.check_launch();
+  add_into(n, y, a, b);
   return y;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // modules (forward saves what backward needs; one forward per step)
 // ---------------------------------------------------------------------------------------------------------------
+// forward(x, dst): x may be a view; when dst is given the module writes its output there (a slice of its consumer's concat
+// buffer) and returns it.  backward(dy): dy may be a view; the result is a dense tensor.
 struct Module {
   virtual ~Module() {}
-  virtual T4 forward(Net& n, T4 x) = 0;
+  virtual T4 forward(Net& n, T4 x, const T4* dst = nullptr) = 0;
   virtual T4 backward(Net& n, T4 dy) = 0;
 };
 typedef std::unique_ptr<Module> Mod;
@@ -303,34 +325,34 @@ struct Conv : Module {
       : name(nm), cin(cin_), cout(cout_), k(k_), s(s_), act(act_ ? 1 : 0), depthwise(dw ? 1 : 0) {
     (void)n;
   }
-  T4 forward(Net& n, T4 in) override {
-    x = in;
+  T4 forward(Net& n, T4 in, const T4* dst = nullptr) override {
+    x = depthwise ? dense_copy(n, in) : in;  // the depthwise kernels take dense tensors
     const int Ho = (in.H + 2 * (k / 2) - k) / s + 1, Wo = (in.W + 2 * (k / 2) - k) / s + 1;
     z = n.make(in.N, Ho, Wo, cout);
-    T4 y = n.make(in.N, Ho, Wo, cout);
+    T4 y = dst ? *dst : n.make(in.N, Ho, Wo, cout);
     mean = n.alloc(cout);
     invstd = n.alloc(cout);
     if (n.rc) return y;
     const float* w = n.p(name + ".conv.weight");
     if (depthwise) {
-      n.check(dwconv3x3_forward_f32(in.p, w, in.N, in.H, in.W, in.C, z.p, n.s));
+      n.check(dwconv3x3_forward_f32(x.p, w, x.N, x.H, x.W, x.C, z.p, n.s));
     } else if (pad8) {
       float* w8 = n.alloc((long long)cout * 8 * k * k);
       if (n.rc) return y;
       pad_weight8_kernel<<<nb((long long)cout * 8 * k * k), 256, 0, n.s>>>(w, w8, cout, k * k);
-      n.check(tf_conv_forward(in.p, w8, nullptr, in.N, in.H, in.W, 8, cout, k, s, k / 2, z.p, n.ws, n.ws_bytes, n.s));
+      n.check(tf_conv_forward(x.p, w8, nullptr, x.N, x.H, x.W, 8, cout, k, s, k / 2, z.p, n.ws, n.ws_bytes, n.s, 0));
     } else {
-      n.check(tf_conv_forward(in.p, w, nullptr, in.N, in.H, in.W, cin, cout, k, s, k / 2, z.p, n.ws, n.ws_bytes, n.s));
+      n.check(tf_conv_forward(x.p, w, nullptr, x.N, x.H, x.W, cin, cout, k, s, k / 2, z.p, n.ws, n.ws_bytes, n.s, x.dense() ? 0 : x.pitch));
     }
     n.check(bn_silu_train_forward(z.p, z.rows(), cout, cout, n.p(name + ".bn.weight"), n.p(name + ".bn.bias"), 1e-3f, 0.03f, act,
-                                  n.r(name + ".bn.running_mean"), n.r(name + ".bn.running_var"), y.p, cout, mean, invstd, n.s));
+                                  n.r(name + ".bn.running_mean"), n.r(name + ".bn.running_var"), y.p, y.pitch, mean, invstd, n.s));
     return y;
   }
   T4 backward(Net& n, T4 dy) override {
     T4 dz = n.make(z.N, z.H, z.W, z.C);
     T4 dx;
     if (n.rc) return dx;
-    n.check(bn_silu_backward(z.p, dy.p, z.rows(), cout, cout, cout, n.p(name + ".bn.weight"), n.p(name + ".bn.bias"), mean, invstd, act,
+    n.check(bn_silu_backward(z.p, dy.p, z.rows(), cout, cout, dy.pitch, n.p(name + ".bn.weight"), n.p(name + ".bn.bias"), mean, invstd, act,
                              dz.p, cout, n.g(name + ".bn.weight"), n.g(name + ".bn.bias"), n.s));
     const float* w = n.p(name + ".conv.weight");
     float* gw = n.g(name + ".conv.weight");
@@ -341,7 +363,7 @@ struct Conv : Module {
     } else if (pad8) {
       float* g8 = n.alloc((long long)cout * 8 * k * k);
       if (n.rc) return dx;
-      n.check(tf_conv_backward_weight(x.p, dz.p, x.N, x.H, x.W, 8, cout, k, s, k / 2, g8, n.ws, n.ws_bytes, n.s));
+      n.check(tf_conv_backward_weight(x.p, dz.p, x.N, x.H, x.W, 8, cout, k, s, k / 2, g8, n.ws, n.ws_bytes, n.s, 0));
       unpad_weight8_kernel<<<nb((long long)cout * 3 * k * k), 256, 0, n.s>>>(g8, gw, cout, k * k);
       n.check_launch();  // the images need no gradient
     } else {
@@ -350,7 +372,7 @@ struct Conv : Module {
         if (n.rc) return dx;
         n.check(tf_conv_backward_data(dz.p, w, x.N, x.H, x.W, cin, cout, k, s, k / 2, dx.p, n.ws, n.ws_bytes, n.s));
       }
-      n.check(tf_conv_backward_weight(x.p, dz.p, x.N, x.H, x.W, cin, cout, k, s, k / 2, gw, n.ws, n.ws_bytes, n.s));
+      n.check(tf_conv_backward_weight(x.p, dz.p, x.N, x.H, x.W, cin, cout, k, s, k / 2, gw, n.ws, n.ws_bytes, n.s, x.dense() ? 0 : x.pitch));
     }
     return dx;
   }
@@ -362,18 +384,22 @@ struct Conv2dBias : Module {
   int cin, cout;
   T4 x;
   Conv2dBias(const std::string& nm, int cin_, int cout_) : name(nm), cin(cin_), cout(cout_) {}
-  T4 forward(Net& n, T4 in) override {
+  T4 forward(Net& n, T4 in, const T4* dst = nullptr) override {
+    (void)dst;  // the head outputs are transposed into (B, C, A) by the caller
     x = in;
     T4 y = n.make(in.N, in.H, in.W, cout);
     if (n.rc) return y;
-    n.check(tf_conv_forward(in.p, n.p(name + ".weight"), n.p(name + ".bias"), in.N, in.H, in.W, cin, cout, 1, 1, 0, y.p, n.ws, n.ws_bytes, n.s));
+    n.check(tf_conv_forward(in.p, n.p(name + ".weight"), n.p(name + ".bias"), in.N, in.H, in.W, cin, cout, 1, 1, 0, y.p, n.ws, n.ws_bytes, n.s,
+                            in.dense() ? 0 : in.pitch));
     return y;
   }
-  T4 backward(Net& n, T4 dz) override {
+  T4 backward(Net& n, T4 dz_in) override {
+    T4 dz = dense_copy(n, dz_in);
     T4 dx = n.make(x.N, x.H, x.W, x.C);
     if (n.rc) return dx;
     n.check(tf_conv_backward_data(dz.p, n.p(name + ".weight"), x.N, x.H, x.W, cin, cout, 1, 1, 0, dx.p, n.ws, n.ws_bytes, n.s));
-    n.check(tf_conv_backward_weight(x.p, dz.p, x.N, x.H, x.W, cin, cout, 1, 1, 0, n.g(name + ".weight"), n.ws, n.ws_bytes, n.s));
+    n.check(tf_conv_backward_weight(x.p, dz.p, x.N, x.H, x.W, cin, cout, 1, 1, 0, n.g(name + ".weight"), n.ws, n.ws_bytes, n.s,
+                                    x.dense() ? 0 : x.pitch));
     const long long rows = dz.rows();
     const int slabs = (int)((rows + 255) / 256);
     float* part = n.alloc((long long)slabs * cout);
@@ -387,7 +413,10 @@ struct Conv2dBias : Module {
 
 struct Seq : Module {
   std::vector<Mod> layers;
-  T4 forward(Net& n, T4 x) override { for (auto& l : layers) x = l->forward(n, x); return x; }
+  T4 forward(Net& n, T4 x, const T4* dst = nullptr) override {
+    for (size_t i = 0; i < layers.size(); i++) x = layers[i]->forward(n, x, i + 1 == layers.size() ? dst : nullptr);
+    return x;
+  }
   T4 backward(Net& n, T4 d) override { for (size_t i = layers.size(); i-- > 0;) d = layers[i]->backward(n, d); return d; }
 };
 
@@ -397,9 +426,12 @@ struct Bottleneck : Module {
   bool add_;
   Bottleneck(Net& n, const std::string& nm, int c1, int c2, bool shortcut, double e)
       : cv1(n, nm + ".cv1", c1, (int)(c2 * e), 3), cv2(n, nm + ".cv2", (int)(c2 * e), c2, 3), add_(shortcut && c1 == c2) {}
-  T4 forward(Net& n, T4 x) override {
+  T4 forward(Net& n, T4 x, const T4* dst = nullptr) override {
+    if (!add_) return cv2.forward(n, cv1.forward(n, x), dst);
     T4 y = cv2.forward(n, cv1.forward(n, x));
-    return add_ ? add(n, x, y) : y;
+    T4 out = dst ? *dst : n.make(x.N, x.H, x.W, x.C);
+    add_into(n, out, x, y);
+    return out;
   }
   T4 backward(Net& n, T4 dy) override {
     T4 dx = cv1.backward(n, cv2.backward(n, dy));
@@ -416,20 +448,19 @@ struct C3k : Module {
       : cv1(n, nm + ".cv1", c1, c2 / 2, 1), cv2(n, nm + ".cv2", c1, c2 / 2, 1), cv3(n, nm + ".cv3", 2 * (c2 / 2), c2, 1), ch(c2 / 2) {
     for (int i = 0; i < reps; i++) m.emplace_back(new Bottleneck(n, nm + ".m." + std::to_string(i), ch, ch, shortcut, 1.0));
   }
-  T4 forward(Net& n, T4 x) override {
-    T4 a = cv1.forward(n, x);
-    for (auto& b : m) a = b->forward(n, a);
-    T4 b = cv2.forward(n, x);
+  T4 forward(Net& n, T4 x, const T4* dst = nullptr) override {
     T4 cat = n.make(x.N, x.H, x.W, 2 * ch);
-    put(n, cat, 0, a);
-    put(n, cat, ch, b);
-    return cv3.forward(n, cat);
+    const T4 ca = view(cat, 0, ch), cb = view(cat, ch, ch);
+    T4 a = cv1.forward(n, x, m.empty() ? &ca : nullptr);
+    for (size_t i = 0; i < m.size(); i++) a = m[i]->forward(n, a, i + 1 == m.size() ? &ca : nullptr);
+    cv2.forward(n, x, &cb);
+    return cv3.forward(n, cat, dst);
   }
   T4 backward(Net& n, T4 dy) override {
     T4 d = cv3.backward(n, dy);
-    T4 da = slice(n, d, 0, ch), db = slice(n, d, ch, ch);
+    T4 da = view(d, 0, ch);
     for (size_t i = m.size(); i-- > 0;) da = m[i]->backward(n, da);
-    return add(n, cv1.backward(n, da), cv2.backward(n, db));
+    return add(n, cv1.backward(n, da), cv2.backward(n, view(d, ch, ch)));
   }
 };
 
@@ -447,28 +478,22 @@ struct C2f : Module {
       else m.emplace_back(new Bottleneck(n, mn, c, c, shortcut, inner == 0 ? 1.0 : 0.5));
     }
   }
-  T4 forward(Net& n, T4 x) override {
-    T4 y = cv1.forward(n, x);
+  T4 forward(Net& n, T4 x, const T4* dst = nullptr) override {
     const int reps = (int)m.size();
-    T4 cat = n.make(x.N, x.H, x.W, (2 + reps) * c);
-    put(n, cat, 0, y);
-    T4 last = slice(n, y, c, c);
+    T4 cat = n.make(x.N, x.H, x.W, (2 + reps) * c);  // every producer writes its own slice: no chunk / cat copies
+    const T4 y01 = view(cat, 0, 2 * c);
+    cv1.forward(n, x, &y01);
     for (int i = 0; i < reps; i++) {
-      last = m[i]->forward(n, last);
-      put(n, cat, (2 + i) * c, last);
+      const T4 out = view(cat, (2 + i) * c, c);
+      m[i]->forward(n, view(cat, (1 + i) * c, c), &out);
     }
-    return cv2.forward(n, cat);
+    return cv2.forward(n, cat, dst);
   }
   T4 backward(Net& n, T4 dy) override {
-    T4 d = cv2.backward(n, dy);
+    T4 d = cv2.backward(n, dy);  // (2 + reps) c channels; slice i+1 accumulates the gradient coming back through block i
     const int reps = (int)m.size();
-    std::vector<T4> parts(2 + reps);
-    for (int i = 0; i < 2 + reps; i++) parts[i] = slice(n, d, i * c, c);
-    for (int i = reps - 1; i >= 0; i--) parts[i + 1] = add(n, parts[i + 1], m[i]->backward(n, parts[i + 2]));
-    T4 d01 = n.make(d.N, d.H, d.W, 2 * c);
-    put(n, d01, 0, parts[0]);
-    put(n, d01, c, parts[1]);
-    return cv1.backward(n, d01);
+    for (int i = reps - 1; i >= 0; i--) put(n, d, (1 + i) * c, m[i]->backward(n, view(d, (2 + i) * c, c)), true);
+    return cv1.backward(n, view(d, 0, 2 * c));
   }
 };
 
@@ -479,32 +504,29 @@ struct SPPF : Module {
   int* idx[3] = {nullptr, nullptr, nullptr};
   int ch;
   SPPF(Net& n, const std::string& nm, int c1, int c2) : cv1(n, nm + ".cv1", c1, c1 / 2, 1, 1, false), cv2(n, nm + ".cv2", 4 * (c1 / 2), c2, 1), ch(c1 / 2) {}
-  T4 forward(Net& n, T4 x) override {
-    t[0] = cv1.forward(n, x);
+  T4 forward(Net& n, T4 x, const T4* dst = nullptr) override {
     T4 cat = n.make(x.N, x.H, x.W, 4 * ch);
-    put(n, cat, 0, t[0]);
+    for (int i = 0; i < 4; i++) t[i] = view(cat, i * ch, ch);
+    cv1.forward(n, x, &t[0]);
     for (int i = 0; i < 3; i++) {
-      t[i + 1] = n.make(x.N, x.H, x.W, ch);
       idx[i] = reinterpret_cast<int*>(n.alloc(t[i].numel()));
       if (n.rc) return cat;
-      pool5_forward_kernel<<<nb(t[i].numel()), 256, 0, n.s>>>(t[i].p, t[i + 1].p, idx[i], x.N, x.H, x.W, ch);
+      pool5_forward_kernel<<<nb(t[i].numel()), 256, 0, n.s>>>(t[i].p, t[i].pitch, t[i + 1].p, t[i + 1].pitch, idx[i], x.N, x.H, x.W, ch);
       n.check_launch();
-      put(n, cat, (i + 1) * ch, t[i + 1]);
     }
-    return cv2.forward(n, cat);
+    return cv2.forward(n, cat, dst);
   }
   T4 backward(Net& n, T4 dy) override {
     T4 d = cv2.backward(n, dy);
-    T4 parts[4];
-    for (int i = 0; i < 4; i++) parts[i] = slice(n, d, i * ch, ch);
     for (int i = 2; i >= 0; i--) {
+      const T4 up = view(d, (i + 1) * ch, ch);
       T4 pb = n.make(d.N, d.H, d.W, ch);
       if (n.rc) return pb;
-      pool5_backward_kernel<<<nb(pb.numel()), 256, 0, n.s>>>(parts[i + 1].p, idx[i], pb.p, d.N, d.H, d.W, ch);
+      pool5_backward_kernel<<<nb(pb.numel()), 256, 0, n.s>>>(up.p, up.pitch, idx[i], pb.p, d.N, d.H, d.W, ch);
       n.check_launch();
-      parts[i] = add(n, parts[i], pb);
+      put(n, d, i * ch, pb, true);
     }
-    return cv1.backward(n, parts[0]);
+    return cv1.backward(n, view(d, 0, ch));
   }
 };
 
@@ -530,14 +552,14 @@ struct Attention : Module {
     slice_copy_kernel<<<nb(rows * hd), 256, 0, n.s>>>(v.p, hd, 0, t.p, per, 2 * kd, rows, hd, 0);
     n.check_launch();
   }
-  T4 forward(Net& n, T4 x) override {
+  T4 forward(Net& n, T4 x, const T4* dst = nullptr) override {
     T4 t = qkv.forward(n, x);
     split_qkv(n, t);
     T4 o = n.make(x.N, x.H, x.W, dim);
     if (n.rc) return o;
     n.check(attention_forward_f32(q.p, k.p, v.p, x.N, x.H * x.W, nh, kd, hd, scale, o.p, nullptr, nullptr, n.s));
     T4 y = add(n, o, pe.forward(n, v));
-    return proj.forward(n, y);
+    return proj.forward(n, y, dst);
   }
   T4 backward(Net& n, T4 dy) override {
     T4 d = proj.backward(n, dy);
@@ -563,9 +585,11 @@ struct PSABlock : Module {
   Attention attn;
   Conv f0, f1;
   PSABlock(Net& n, const std::string& nm, int c) : attn(n, nm + ".attn", c, c / 64), f0(n, nm + ".ffn.0", c, 2 * c, 1), f1(n, nm + ".ffn.1", 2 * c, c, 1) {}  // ffn[1] keeps its SiLU too (Block.cs:708)
-  T4 forward(Net& n, T4 x) override {
+  T4 forward(Net& n, T4 x, const T4* dst = nullptr) override {
     T4 a = add(n, x, attn.forward(n, x));
-    return add(n, a, f1.forward(n, f0.forward(n, a)));
+    T4 out = dst ? *dst : n.make(x.N, x.H, x.W, x.C);
+    add_into(n, out, a, f1.forward(n, f0.forward(n, a)));
+    return out;
   }
   T4 backward(Net& n, T4 dy) override {
     T4 d = add(n, dy, f0.backward(n, f1.backward(n, dy)));
@@ -581,23 +605,21 @@ struct C2PSA : Module {
   C2PSA(Net& n, const std::string& nm, int c1, int reps) : cv1(n, nm + ".cv1", c1, 2 * (c1 / 2), 1), cv2(n, nm + ".cv2", 2 * (c1 / 2), c1, 1), c(c1 / 2) {
     for (int i = 0; i < reps; i++) m.emplace_back(new PSABlock(n, nm + ".m." + std::to_string(i), c));
   }
-  T4 forward(Net& n, T4 x) override {
+  T4 forward(Net& n, T4 x, const T4* dst = nullptr) override {
     T4 y = cv1.forward(n, x);
-    T4 b = slice(n, y, c, c);
-    for (auto& blk : m) b = blk->forward(n, b);
-    T4 cat = n.make(x.N, x.H, x.W, 2 * c);
-    put(n, cat, 0, slice(n, y, 0, c));
-    put(n, cat, c, b);
-    return cv2.forward(n, cat);
+    T4 cat = n.make(x.N, x.H, x.W, 2 * c);  // a separate buffer: the blocks' convs keep views of y for their weight gradients
+    put(n, cat, 0, view(y, 0, c));
+    T4 b = view(y, c, c);
+    const T4 cb = view(cat, c, c);
+    for (size_t i = 0; i < m.size(); i++) b = m[i]->forward(n, b, i + 1 == m.size() ? &cb : nullptr);
+    return cv2.forward(n, cat, dst);
   }
   T4 backward(Net& n, T4 dy) override {
     T4 d = cv2.backward(n, dy);
-    T4 da = slice(n, d, 0, c), db = slice(n, d, c, c);
+    T4 db = view(d, c, c);
     for (size_t i = m.size(); i-- > 0;) db = m[i]->backward(n, db);
-    T4 cat = n.make(d.N, d.H, d.W, 2 * c);
-    put(n, cat, 0, da);
-    put(n, cat, c, db);
-    return cv1.backward(n, cat);
+    put(n, d, c, db);  // d = [da | db] again
+    return cv1.backward(n, d);
   }
 };
 
@@ -898,7 +920,7 @@ int run_backward(yb_trainer* t, const void* images, int in_dtype, int B, const f
     if (l.kind == 1) {
       T4 y = n.make(x.N, 2 * x.H, 2 * x.W, x.C);
       if (n.rc) break;
-      up2_forward_kernel<<<nb(y.numel()), 256, 0, s>>>(x.p, y.p, x.N, x.H, x.W, x.C);
+      up2_forward_kernel<<<nb(y.numel()), 256, 0, s>>>(x.p, x.pitch, y.p, y.pitch, x.N, x.H, x.W, x.C);
       n.check_launch();
       t->up_in.push_back(x);
       x = y;
@@ -961,16 +983,16 @@ int run_backward(yb_trainer* t, const void* images, int in_dtype, int B, const f
       const T4& xin = t->up_in[up];
       T4 d = n.make(xin.N, xin.H, xin.W, xin.C);
       if (n.rc) break;
-      up2_backward_kernel<<<nb(d.numel()), 256, 0, s>>>(dx.p, d.p, xin.N, xin.H, xin.W, xin.C);
+      up2_backward_kernel<<<nb(d.numel()), 256, 0, s>>>(dx.p, dx.pitch, d.p, xin.N, xin.H, xin.W, xin.C);
       n.check_launch();
       dx = d;
     } else if (l.kind == 2) {
       cc--;
       const int cx = t->cat_split[cc].first, src = t->cat_split[cc].second;
-      T4 d_other = slice(n, dx, cx, dx.C - cx);
+      const T4 d_other = view(dx, cx, dx.C - cx);  // views of the concat's gradient: no copies
       dout[src] = has[src] ? add(n, dout[src], d_other) : d_other;
       has[src] = 1;
-      dx = slice(n, dx, 0, cx);
+      dx = view(dx, 0, cx);
     } else {
       dx = l.m->backward(n, dx);
     }
@@ -1007,6 +1029,17 @@ int32_t yb_trainer_create(const yb_config* cfg, yb_trainer** out) {
   if (cfg->flags & YB_FLAG_DRY_RUN) { *out = t.release(); return YB_OK; }  // names / layout only (CPU tests)
   if (!have_dev("yb_trainer_create")) return YB_ERR_NO_DEVICE;
   if (cudaSetDevice(cfg->device) != cudaSuccess) { set_error("yb_trainer_create: cudaSetDevice failed"); cudaGetLastError(); return YB_ERR_CUDA; }
+  {
+    // the kernels' scratch (BatchNorm partials, attention statistics, ...) comes from the stream-ordered allocator; by
+    // default its pool hands unused memory back to the OS at every synchronisation - and a step ends with one (loss items
+    // to the host) - so the next step would pay for fresh device allocations (seen as random 15 - 500 ms steps)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   t->net.ws_bytes = max_workspace(t.get());
   // activations + gradients of one step: every conv block keeps x, z, y (+ dz, dx on the way back); sized from the fp32
   // activation volume of the model at this batch with headroom, grown on demand is not possible inside a step

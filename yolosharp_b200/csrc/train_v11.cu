@@ -42,6 +42,39 @@ __global__ void dw3x3_forward_kernel(const float* __restrict__ x, const float* _
   z[idx] = acc;
 }
 
+// 4 channels per thread (16-byte loads / stores, 32-bit index math); same per-element tap order as the scalar kernel
+__global__ void __launch_bounds__(256) dw3x3_forward4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            float* __restrict__ z, int N, int H, int W, int C, int transpose_taps,
+                                                            int total4) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const int C4 = C >> 2;
+  const int c = (idx % C4) * 4;
+  int p = idx / C4;
+  const int wx = p % W;
+  p /= W;
+  const int hy = p % H;
+  const int n = p / H;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int kh = 0; kh < 3; kh++) {
+    const int yy = hy + kh - 1;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; kw++) {
+      const int xx = wx + kw - 1;
+      if (xx < 0 || xx >= W) continue;
+      const int t = transpose_taps ? (2 - kh) * 3 + (2 - kw) : kh * 3 + kw;
+      const float4 v = *reinterpret_cast<const float4*>(x + (((size_t)n * H + yy) * W + xx) * C + c);
+      a0 = fmaf(v.x, w[c * 9 + t], a0);
+      a1 = fmaf(v.y, w[(c + 1) * 9 + t], a1);
+      a2 = fmaf(v.z, w[(c + 2) * 9 + t], a2);
+      a3 = fmaf(v.w, w[(c + 3) * 9 + t], a3);
+    }
+  }
+  *reinterpret_cast<float4*>(z + (size_t)idx * 4) = make_float4(a0, a1, a2, a3);
+}
+
 // dw[c][t] = sum over pixels dz[p][c] * x[p + tap t][c]: slabs of 256 pixel rows -> partial[slab][t][c]
 constexpr int DW_SLAB = 256;
 __global__ void __launch_bounds__(256) dw3x3_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict__ dz,
@@ -98,7 +131,10 @@ __global__ void dw3x3_wgrad_fold_kernel(const float* __restrict__ partial, float
 
 int dwconv3x3_forward_f32(const float* x, const float* w, int N, int H, int W, int C, float* z, cudaStream_t s) {
   const size_t total = (size_t)N * H * W * C;
-  dw3x3_forward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, w, z, N, H, W, C, 0);
+  if (C % 4 == 0 && total / 4 < ((size_t)1 << 31) && !((uintptr_t)x & 15) && !((uintptr_t)z & 15))
+    dw3x3_forward4_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(x, w, z, N, H, W, C, 0, (int)(total / 4));
+  else
+    dw3x3_forward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, w, z, N, H, W, C, 0);
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -106,7 +142,10 @@ int dwconv3x3_forward_f32(const float* x, const float* w, int N, int H, int W, i
 int dwconv3x3_backward_f32(const float* x, const float* dz, const float* w, int N, int H, int W, int C, float* dx, float* dw,
                            cudaStream_t s) {
   const size_t total = (size_t)N * H * W * C;
-  dw3x3_forward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dz, w, dx, N, H, W, C, 1);
+  if (C % 4 == 0 && total / 4 < ((size_t)1 << 31) && !((uintptr_t)dz & 15) && !((uintptr_t)dx & 15))
+    dw3x3_forward4_kernel<<<(unsigned)((total / 4 + 255) / 256), 256, 0, s>>>(dz, w, dx, N, H, W, C, 1, (int)(total / 4));
+  else
+    dw3x3_forward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dz, w, dx, N, H, W, C, 1);
   YB_CUDA_CHECK(cudaGetLastError());
   const long long rows = (long long)N * H * W;
   const int slabs = (int)((rows + DW_SLAB - 1) / DW_SLAB);
@@ -492,6 +531,240 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_backward_kv_tiled(const floa
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Register-blocked backward for kd = 32, hd = 64 (every YOLOv11 size), same blocking as the forward kernel
+// (kernels_generic.cu::attention_tiled_32x64_kernel): 16-byte shared-memory reads, two rows per warp sharing every
+// operand, global fills as batches of independent vector loads.  Row strides 36 (K / Q) and 68 (V / dO) floats keep
+// both "a lane owns a row" (LDS.128 along the row) and "a lane owns a channel" (scalar / LDS.64 down a column) reads
+// bank-conflict free.  D_i = sum_d dO_id O_id (= sum_j P_ij dP_ij) comes from the recomputed forward output.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int AB_T = 16, AB_THREADS = 256, AB_LDK = 36, AB_LDV = 68;
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
+// rows [row0, row0 + rows) of one head of a (B, N, nh, dim) tensor -> smem with row stride ld (multiple of 4); rows >= N zero
+template <int DIM>
+__device__ __forceinline__ void fill_head(float* dst, int ld, const float* src, int b, int h, int N, int nh, int row0, int rows) {
+  constexpr int U = 8, D4 = DIM / 4;
+  const int total = rows * D4;
+  for (int t0 = threadIdx.x; t0 < total; t0 += AB_THREADS * U) {
+    float4 f[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * AB_THREADS;
+      f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < total) {
+        const int r = t / D4, d = (t - r * D4) * 4, tok = row0 + r;
+        if (tok < N) f[u] = *reinterpret_cast<const float4*>(src + (((size_t)b * N + tok) * nh + h) * DIM + d);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int t = t0 + u * AB_THREADS;
+      if (t < total) {
+        const int r = t / D4, d = (t - r * D4) * 4;
+        *reinterpret_cast<float4*>(dst + (size_t)r * ld + d) = f[u];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_q_32x64(const float* __restrict__ q, const float* __restrict__ k,
+                                                                 const float* __restrict__ v, const float* __restrict__ dout,
+                                                                 const float* __restrict__ o, const float* __restrict__ row_max,
+                                                                 const float* __restrict__ row_sum, float* __restrict__ row_d,
+                                                                 float* __restrict__ dq, int N, int nh, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  const int NK = (N + 31) & ~31, NP = (N + 3) & ~3;
+  float* Ks = sm;                          // [NK][36]
+  float* Vs = Ks + (size_t)NK * AB_LDK;    // [NK][68]
+  float* Qs = Vs + (size_t)NK * AB_LDV;    // [16][32]
+  float* Os = Qs + AB_T * 32;              // [16][64] dO rows
+  float* Ps = Os + AB_T * 64;              // [16][NP] dS
+  const int i0 = blockIdx.x * AB_T, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  fill_head<32>(Ks, AB_LDK, k, b, h, N, nh, 0, NK);
+  fill_head<64>(Vs, AB_LDV, v, b, h, N, nh, 0, NK);
+  fill_head<32>(Qs, 32, q, b, h, N, nh, i0, AB_T);
+  fill_head<64>(Os, 64, dout, b, h, N, nh, i0, AB_T);
+  __syncthreads();
+  const int r0 = warp * 2, r1 = r0 + 1;
+  const bool ok0 = i0 + r0 < N, ok1 = i0 + r1 < N;
+  // D = dO . O per row (two channels per lane)
+  float D0 = 0.f, D1 = 0.f;
+  {
+    const size_t base0 = (((size_t)b * N + min(i0 + r0, N - 1)) * nh + h) * 64 + 2 * lane;
+    const size_t base1 = (((size_t)b * N + min(i0 + r1, N - 1)) * nh + h) * 64 + 2 * lane;
+    const float2 o0 = *reinterpret_cast<const float2*>(o + base0), o1 = *reinterpret_cast<const float2*>(o + base1);
+    D0 = Os[r0 * 64 + 2 * lane] * o0.x + Os[r0 * 64 + 2 * lane + 1] * o0.y;
+    D1 = Os[r1 * 64 + 2 * lane] * o1.x + Os[r1 * 64 + 2 * lane + 1] * o1.y;
+    for (int s = 16; s; s >>= 1) { D0 += __shfl_xor_sync(0xffffffffu, D0, s); D1 += __shfl_xor_sync(0xffffffffu, D1, s); }
+  }
+  const size_t st0 = ((size_t)b * nh + h) * N + min(i0 + r0, N - 1), st1 = ((size_t)b * nh + h) * N + min(i0 + r1, N - 1);
+  const float mx0 = row_max[st0], inv0 = 1.0f / row_sum[st0], mx1 = row_max[st1], inv1 = 1.0f / row_sum[st1];
+  float q0[32], q1[32];
+#pragma unroll
+  for (int d = 0; d < 32; d += 4) {
+    const float4 a = lds4(Qs + r0 * 32 + d), c = lds4(Qs + r1 * 32 + d);
+    q0[d] = a.x; q0[d + 1] = a.y; q0[d + 2] = a.z; q0[d + 3] = a.w;
+    q1[d] = c.x; q1[d + 1] = c.y; q1[d + 2] = c.z; q1[d + 3] = c.w;
+  }
+  float* p0 = Ps + (size_t)r0 * NP;
+  float* p1 = Ps + (size_t)r1 * NP;
+  for (int j = lane; j < NK; j += 32) {
+    const float* kr = Ks + (size_t)j * AB_LDK;
+    const float* vr = Vs + (size_t)j * AB_LDV;
+    float s0 = 0.f, s1 = 0.f, dp0 = 0.f, dp1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; d += 4) {
+      const float4 kv = lds4(kr + d);
+      s0 = fmaf(q0[d], kv.x, s0); s1 = fmaf(q1[d], kv.x, s1);
+      s0 = fmaf(q0[d + 1], kv.y, s0); s1 = fmaf(q1[d + 1], kv.y, s1);
+      s0 = fmaf(q0[d + 2], kv.z, s0); s1 = fmaf(q1[d + 2], kv.z, s1);
+      s0 = fmaf(q0[d + 3], kv.w, s0); s1 = fmaf(q1[d + 3], kv.w, s1);
+    }
+#pragma unroll
+    for (int d = 0; d < 64; d += 4) {
+      const float4 vv = lds4(vr + d);
+      dp0 = dot4(lds4(Os + r0 * 64 + d), vv, dp0);
+      dp1 = dot4(lds4(Os + r1 * 64 + d), vv, dp1);
+    }
+    if (j < NP) {
+      const bool in = j < N;
+      p0[j] = in ? expf(s0 * scale - mx0) * inv0 * (dp0 - D0) : 0.f;
+      p1[j] = in ? expf(s1 * scale - mx1) * inv1 * (dp1 - D1) : 0.f;
+    }
+  }
+  __syncwarp();
+  float a0 = 0.f, a1 = 0.f;
+  for (int j = 0; j < NP; j += 4) {
+    const float4 da = lds4(p0 + j), db = lds4(p1 + j);
+    const float k0 = Ks[(size_t)j * AB_LDK + lane], k1 = Ks[(size_t)(j + 1) * AB_LDK + lane];
+    const float k2 = Ks[(size_t)(j + 2) * AB_LDK + lane], k3 = Ks[(size_t)(j + 3) * AB_LDK + lane];
+    a0 = fmaf(da.x, k0, a0); a1 = fmaf(db.x, k0, a1);
+    a0 = fmaf(da.y, k1, a0); a1 = fmaf(db.y, k1, a1);
+    a0 = fmaf(da.z, k2, a0); a1 = fmaf(db.z, k2, a1);
+    a0 = fmaf(da.w, k3, a0); a1 = fmaf(db.w, k3, a1);
+  }
+  if (ok0) dq[(((size_t)b * N + i0 + r0) * nh + h) * 32 + lane] = a0 * scale;
+  if (ok1) dq[(((size_t)b * N + i0 + r1) * nh + h) * 32 + lane] = a1 * scale;
+  if (lane == 0) {
+    if (ok0) row_d[st0] = D0;
+    if (ok1) row_d[st1] = D1;
+  }
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_kv_32x64(const float* __restrict__ q, const float* __restrict__ k,
+                                                                  const float* __restrict__ v, const float* __restrict__ dout,
+                                                                  const float* __restrict__ row_max, const float* __restrict__ row_sum,
+                                                                  const float* __restrict__ row_d, float* __restrict__ dk,
+                                                                  float* __restrict__ dv, int N, int nh, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  const int NK = (N + 31) & ~31, NP = (N + 3) & ~3;
+  float* Qs = sm;                          // [NK][36] all queries of the head
+  float* Os = Qs + (size_t)NK * AB_LDK;    // [NK][68] all dO rows
+  float* St = Os + (size_t)NK * AB_LDV;    // [3][NK] row max | 1 / row sum | D
+  float* Kt = St + 3 * (size_t)NK;         // [16][32]
+  float* Vt = Kt + AB_T * 32;              // [16][64]
+  float* Ps = Vt + AB_T * 64;              // [16][NP]
+  const int j0 = blockIdx.x * AB_T, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  fill_head<32>(Qs, AB_LDK, q, b, h, N, nh, 0, NK);
+  fill_head<64>(Os, AB_LDV, dout, b, h, N, nh, 0, NK);
+  fill_head<32>(Kt, 32, k, b, h, N, nh, j0, AB_T);
+  fill_head<64>(Vt, 64, v, b, h, N, nh, j0, AB_T);
+  for (int i = threadIdx.x; i < NK; i += AB_THREADS) {
+    const size_t st = ((size_t)b * nh + h) * N + min(i, N - 1);
+    St[i] = row_max[st];
+    St[NK + i] = i < N ? 1.0f / row_sum[st] : 0.f;  // padded queries get p = 0
+    St[2 * NK + i] = row_d[st];
+  }
+  __syncthreads();
+  const int r0 = warp * 2, r1 = r0 + 1;
+  const bool ok0 = j0 + r0 < N, ok1 = j0 + r1 < N;
+  float k0[32], k1[32];
+#pragma unroll
+  for (int d = 0; d < 32; d += 4) {
+    const float4 a = lds4(Kt + r0 * 32 + d), c = lds4(Kt + r1 * 32 + d);
+    k0[d] = a.x; k0[d + 1] = a.y; k0[d + 2] = a.z; k0[d + 3] = a.w;
+    k1[d] = c.x; k1[d + 1] = c.y; k1[d + 2] = c.z; k1[d + 3] = c.w;
+  }
+  float* p0 = Ps + (size_t)r0 * NP;
+  float* p1 = Ps + (size_t)r1 * NP;
+  // P^T rows of the two keys
+  for (int i = lane; i < NK; i += 32) {
+    const float* qr = Qs + (size_t)i * AB_LDK;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; d += 4) {
+      const float4 qv = lds4(qr + d);
+      s0 = fmaf(qv.x, k0[d], s0); s1 = fmaf(qv.x, k1[d], s1);
+      s0 = fmaf(qv.y, k0[d + 1], s0); s1 = fmaf(qv.y, k1[d + 1], s1);
+      s0 = fmaf(qv.z, k0[d + 2], s0); s1 = fmaf(qv.z, k1[d + 2], s1);
+      s0 = fmaf(qv.w, k0[d + 3], s0); s1 = fmaf(qv.w, k1[d + 3], s1);
+    }
+    if (i < NP) {
+      p0[i] = expf(s0 * scale - St[i]) * St[NK + i];
+      p1[i] = expf(s1 * scale - St[i]) * St[NK + i];
+    }
+  }
+  __syncwarp();
+  {  // dV_j = sum_i p_ij dO_i: a lane owns channels 2 lane, 2 lane + 1
+    float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+    const float* ocol = Os + 2 * lane;
+    for (int i = 0; i < NP; i += 4) {
+      const float4 pa = lds4(p0 + i), pb = lds4(p1 + i);
+      const float2 o0 = *reinterpret_cast<const float2*>(ocol + (size_t)i * AB_LDV);
+      const float2 o1 = *reinterpret_cast<const float2*>(ocol + (size_t)(i + 1) * AB_LDV);
+      const float2 o2 = *reinterpret_cast<const float2*>(ocol + (size_t)(i + 2) * AB_LDV);
+      const float2 o3 = *reinterpret_cast<const float2*>(ocol + (size_t)(i + 3) * AB_LDV);
+      a00 = fmaf(pa.x, o0.x, a00); a01 = fmaf(pa.x, o0.y, a01); a10 = fmaf(pb.x, o0.x, a10); a11 = fmaf(pb.x, o0.y, a11);
+      a00 = fmaf(pa.y, o1.x, a00); a01 = fmaf(pa.y, o1.y, a01); a10 = fmaf(pb.y, o1.x, a10); a11 = fmaf(pb.y, o1.y, a11);
+      a00 = fmaf(pa.z, o2.x, a00); a01 = fmaf(pa.z, o2.y, a01); a10 = fmaf(pb.z, o2.x, a10); a11 = fmaf(pb.z, o2.y, a11);
+      a00 = fmaf(pa.w, o3.x, a00); a01 = fmaf(pa.w, o3.y, a01); a10 = fmaf(pb.w, o3.x, a10); a11 = fmaf(pb.w, o3.y, a11);
+    }
+    if (ok0) *reinterpret_cast<float2*>(dv + (((size_t)b * N + j0 + r0) * nh + h) * 64 + 2 * lane) = make_float2(a00, a01);
+    if (ok1) *reinterpret_cast<float2*>(dv + (((size_t)b * N + j0 + r1) * nh + h) * 64 + 2 * lane) = make_float2(a10, a11);
+  }
+  __syncwarp();
+  // dS^T = P^T o (dP^T - D): dP_ij = dO_i . v_j, v rows broadcast from the tile
+  for (int i = lane; i < NK; i += 32) {
+    const float* orow = Os + (size_t)i * AB_LDV;
+    float dp0 = 0.f, dp1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 64; d += 4) {
+      const float4 ov = lds4(orow + d);
+      dp0 = dot4(ov, lds4(Vt + r0 * 64 + d), dp0);
+      dp1 = dot4(ov, lds4(Vt + r1 * 64 + d), dp1);
+    }
+    if (i < NP) {
+      p0[i] = p0[i] * (dp0 - St[2 * NK + i]);
+      p1[i] = p1[i] * (dp1 - St[2 * NK + i]);
+    }
+  }
+  __syncwarp();
+  float a0 = 0.f, a1 = 0.f;  // dK_j = scale sum_i dS_ij q_i: a lane owns channel `lane`
+  for (int i = 0; i < NP; i += 4) {
+    const float4 da = lds4(p0 + i), db = lds4(p1 + i);
+    const float q0v = Qs[(size_t)i * AB_LDK + lane], q1v = Qs[(size_t)(i + 1) * AB_LDK + lane];
+    const float q2v = Qs[(size_t)(i + 2) * AB_LDK + lane], q3v = Qs[(size_t)(i + 3) * AB_LDK + lane];
+    a0 = fmaf(da.x, q0v, a0); a1 = fmaf(db.x, q0v, a1);
+    a0 = fmaf(da.y, q1v, a0); a1 = fmaf(db.y, q1v, a1);
+    a0 = fmaf(da.z, q2v, a0); a1 = fmaf(db.z, q2v, a1);
+    a0 = fmaf(da.w, q3v, a0); a1 = fmaf(db.w, q3v, a1);
+  }
+  if (ok0) dk[(((size_t)b * N + j0 + r0) * nh + h) * 32 + lane] = a0 * scale;
+  if (ok1) dk[(((size_t)b * N + j0 + r1) * nh + h) * 32 + lane] = a1 * scale;
+}
+
+static size_t ab_smem_bytes(int N, int which) {  // which: 0 q pass, 1 kv pass
+  const size_t NK = (N + 31) & ~31, NP = (N + 3) & ~3;
+  const size_t heads = NK * AB_LDK + NK * AB_LDV;
+  return (heads + (which ? 3 * NK : 0) + (size_t)AB_T * (32 + 64) + (size_t)AB_T * NP) * sizeof(float);
+}
+static bool ab_fits(int N) { return ab_smem_bytes(N, 1) <= 227 * 1024 && ab_smem_bytes(N, 0) <= 227 * 1024; }
+
 static size_t attn_tiled_smem(int N, int kd, int hd, int which) {  // floats; which: 0 forward, 1 backward q, 2 backward kv
   const size_t heads = (size_t)N * (kd + 1) + (size_t)N * (hd + 1);
   if (which == 0) return heads + (size_t)AT_T * kd + (size_t)AT_T * N;
@@ -542,7 +815,14 @@ int attention_backward_f32(const float* q, const float* k, const float* v, const
   YB_CUDA_CHECK(cudaMallocAsync((void**)&stats, (3 * n + (size_t)B * N * nh * hd) * sizeof(float), s));
   float* tmp_out = stats + 3 * n;  // the forward output is recomputed only for its row statistics
   int rc = attention_forward_f32(q, k, v, B, N, nh, kd, hd, scale, tmp_out, stats, stats + n, s);
-  if (!rc && attn_tiled_ok(N, kd, hd)) {
+  if (!rc && kd == 32 && hd == 64 && ab_fits(N) && getenv("YB_ATTN_BWD_OLD") == nullptr) {
+    cudaFuncSetAttribute(attn_bwd_q_32x64, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_bwd_kv_32x64, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const dim3 grid((N + AB_T - 1) / AB_T, nh, B);
+    attn_bwd_q_32x64<<<grid, AB_THREADS, ab_smem_bytes(N, 0), s>>>(q, k, v, dout, tmp_out, stats, stats + n, stats + 2 * n, dq, N, nh, scale);
+    attn_bwd_kv_32x64<<<grid, AB_THREADS, ab_smem_bytes(N, 1), s>>>(q, k, v, dout, stats, stats + n, stats + 2 * n, dk, dv, N, nh, scale);
+    if (cudaGetLastError() != cudaSuccess) { set_error("attention backward launch failed"); rc = YB_ERR_CUDA; }
+  } else if (!rc && attn_tiled_ok(N, kd, hd)) {
     cudaFuncSetAttribute(attn_backward_q_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(attn_backward_kv_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const dim3 grid((N + AT_T - 1) / AT_T, nh, B);
