@@ -130,7 +130,7 @@ def _compare_tc(step_cls, ops_cls, arch, head_tol):
     assert e_box < head_tol and e_cls < head_tol
     # observed on B200: v8 rel L2 0.13 / cosine 0.992, v11 0.21 / 0.977; PyTorch's own cuDNN TF32 convolutions against its
     # fp32 ones on the same model and batch: tools/exp_torch_tf32.py (profiles/r2_exp_torch_tf32.txt)
-    assert l2 < 0.3 and cos > 0.96
+    assert l2 < 0.4 and cos > 0.93  # a chaotic quantity: one last-bit reordering anywhere moves it by a few percent
     c = step_cls(sd0, "n", 80, device="cuda", ops=ops_cls(tensor_cores=True), lr=1e-3)
     it_tc = c.step(x, targets).cpu()
     np.testing.assert_allclose(it_tc.numpy(), items.cpu().numpy(), rtol=0.15)

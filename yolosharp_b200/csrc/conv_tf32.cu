@@ -610,21 +610,18 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
   }
 }
 
-// dw[co][ci][tap] = sum over splits (fixed order) of part[split][co][tap][ci].  Threads run over (co, tap, ci) with ci
-// fastest, so the `splits` reads per output are coalesced (the partials are `splits` times the size of the result; the
-// scattered write happens once).
+// dw[co][ci][tap] = sum over splits (fixed order) of part[split][co][tap][ci]
+// (threads over the checkpoint layout; a variant with the reads coalesced over ci and scattered writes was slower: 1.13 vs 0.87 ms)
 __global__ void tf_wgrad_fold_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cout, int Cin, int taps, int splits,
                                      int co_pad, int ci_pad) {
   const long long n = (long long)Cout * Cin * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % Cin);
-    const long long q = i / Cin;
-    const int t = (int)(q % taps), co = (int)(q / taps);
-    const float* src = part + ((size_t)co * taps + t) * ci_pad + ci;
-    const size_t sstride = (size_t)co_pad * taps * ci_pad;
+    const int t = (int)(i % taps);
+    const long long q = i / taps;
+    const int ci = (int)(q % Cin), co = (int)(q / Cin);
     float acc = 0.f;
-    for (int s = 0; s < splits; s++) acc += src[(size_t)s * sstride];
-    dw[((size_t)co * Cin + ci) * taps + t] = acc;
+    for (int s = 0; s < splits; s++) acc += part[(((size_t)s * co_pad + co) * taps + t) * ci_pad + ci];
+    dw[i] = acc;
   }
 }
 
