@@ -231,6 +231,16 @@ int32_t yb_conv_backward_weight_tc(const float* x, const float* dz, int32_t n, i
                                    int32_t cout, int32_t k, int32_t stride, int32_t pad, float* dw, void* workspace,
                                    int64_t workspace_bytes, void* stream);
 
+/* The 3-channel stem of the training step (model.0 = Conv(3, C, k 3, s 2), Models/Yolo.cs:53) in fp32 on CUDA cores: one
+ * K = 3 x 9 contraction per output is too thin for a tensor-core tile (the padded-to-8 TF32 form was bound by the TMA row
+ * rate).  x dev float32 NHWC with `x_channels` >= 3 channels per pixel (the first 3 are read); w (C, 3, 3, 3) checkpoint
+ * layout; z / dz (N, H/2, W/2, C); C % 8 == 0, C <= 128, even H and W; workspace >= yb_conv_tc_workspace_bytes(...). */
+int32_t yb_stem_conv_forward_f32(const float* x, int32_t x_channels, const float* w, int32_t n, int32_t height, int32_t width,
+                                 int32_t cout, float* z, void* stream);
+int32_t yb_stem_conv_backward_weight_f32(const float* x, int32_t x_channels, const float* dz, int32_t n, int32_t height,
+                                         int32_t width, int32_t cout, float* dw, void* workspace, int64_t workspace_bytes,
+                                         void* stream);
+
 /* Replaces: `AMPWrapper.TrainStep` (Utils/Amp.cs:260-286: yolo.forward -> loss -> loss.backward() -> optimizer.step()) for
  * the YOLOv8 / YOLOv11 detect models as ONE call (csrc/train_step.cu): train-mode forward with batch-statistics
  * BatchNorm, v8DetectionLoss, backward through the whole graph (TF32 tcgen05 convolutions), AdamW per name group

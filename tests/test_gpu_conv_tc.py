@@ -97,6 +97,31 @@ def test_conv_tc_exact_on_tf32_representable_inputs():
 
 
 @gpu
+@pytest.mark.parametrize("N,H,W,C,xc", [(2, 64, 96, 16, 3), (1, 32, 32, 32, 8), (2, 40, 24, 80, 8), (1, 640, 640, 32, 8)])
+def test_stem_conv_forward_and_wgrad_vs_torch(N, H, W, C, xc):
+    """The fp32 CUDA-core stem kernels (yb_stem_conv_*): x with 3 or 8 (zero-padded) channels per pixel."""
+    import yolosharp_b200.engine as E
+    g = torch.Generator().manual_seed(5)
+    x3 = torch.randn(N, H, W, 3, generator=g)
+    w = torch.randn(C, 3, 3, 3, generator=g) / 27 ** 0.5
+    dz = torch.randn(N, H // 2, W // 2, C, generator=g)
+    xt = x3.permute(0, 3, 1, 2).contiguous().cuda()
+    wt = w.clone().cuda().requires_grad_(True)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        zt = torch.nn.functional.conv2d(xt, wt, None, stride=2, padding=1)
+        zt.backward(dz.permute(0, 3, 1, 2).contiguous().cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    x = torch.nn.functional.pad(x3, (0, xc - 3)).contiguous().cuda()
+    z = E.stem_conv_forward(x, w.cuda())
+    dw = E.stem_conv_backward_weight(x, dz.cuda(), w.shape)
+    torch.testing.assert_close(z, zt.detach().permute(0, 2, 3, 1), rtol=1e-4, atol=1e-5)
+    assert _rel(dw, wt.grad) < 1e-4
+
+
+@gpu
 def test_conv_tc_rejects_unsupported_shapes():
     import yolosharp_b200.engine as E
     from yolosharp_b200._lib import YbError

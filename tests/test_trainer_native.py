@@ -84,7 +84,7 @@ def test_native_train_step_v11_matches_python_step():
 
 @pytest.mark.gpu
 def test_native_train_step_u8_images_and_second_step():
-    """uint8 images (divided by 255 inside the library) and a second step on the updated weights stay finite and move."""
+    """uint8 images (scaled by 1/255 inside the library, YoloDataset.cs:140) and a second step on the updated weights stay finite and move."""
     from yolosharp_b200.train_native import NativeTrainer
     torch.manual_seed(0)
     m = oracle_model("v8", "detect", "n")
@@ -95,5 +95,5 @@ def test_native_train_step_u8_images_and_second_step():
     i2 = t.step(u8, _targets(2))
     assert torch.isfinite(i1).all() and torch.isfinite(i2).all() and not torch.equal(w1, t.flat)
     f = NativeTrainer(m.state_dict(), "v8", "n", 80, device="cuda", max_batch=2, height=64, width=96, lr=1e-3)
-    j1 = f.step(u8.float() / 255.0, _targets(2))
+    j1 = f.step(u8.float().mul(1 / 255.0), _targets(2))
     torch.testing.assert_close(j1, i1, rtol=1e-6, atol=1e-7)

@@ -101,7 +101,7 @@ struct TfArgs {
   uint32_t tmem_cols;
 };
 
-__global__ void __launch_bounds__(TF_THREADS, 1) tf_conv_kernel(const __grid_constant__ TfArgs a) {
+__global__ void __launch_bounds__(TF_THREADS, 2) tf_conv_kernel(const __grid_constant__ TfArgs a) {
   extern __shared__ __align__(1024) uint8_t tf_smem[];
   __shared__ __align__(8) uint64_t bars[2 * TF_MAX_STAGES + 4];
   __shared__ uint32_t tmem_slot;
@@ -329,18 +329,26 @@ static int tf_conv_launch(const TfLaunch& L, cudaStream_t s) {
   a.b_bytes = (uint32_t)a.n_tile * row_bytes;
   a.a_stride = (128 * row_bytes + 1023) / 1024 * 1024;
   a.b_stride = (a.n_tile * row_bytes + 1023) / 1024 * 1024;
-  a.stages = (int)std::min<size_t>(TF_MAX_STAGES, (size_t)(190 * 1024) / (a.a_stride + a.b_stride));
-  if (a.stages < 2) { set_error("tf32 conv: tile does not fit in shared memory"); return YB_ERR_SHAPE; }
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * a.n_tile)) cols <<= 1;
   a.tmem_cols = cols;
+  // Two CTAs per SM when there are tiles for them and a CTA fits half an SM (<= 256 TMEM columns, a ring of >= 3 stages in
+  // ~100 KiB): with one producer thread, one MMA thread and four epilogue warps per CTA the kernel is latency bound
+  // (ncu: issue active 10 - 18 %, long-scoreboard / wait stalls, profiles/r2_ncu_tf_conv_big.txt); a second CTA fills
+  // the other's load -> MMA -> epilogue bubbles, as in conv_tc_kernel.
+  static const bool occ1 = getenv("YB_TF_OCC1") != nullptr;
+  const size_t per_stage = (size_t)a.a_stride + a.b_stride;
+  int occ = 1;
+  if (!occ1 && cols <= 256 && (size_t)(100 * 1024) / per_stage >= 3 && a.total_tiles >= 2 * tf_num_sms()) occ = 2;
+  a.stages = (int)std::min<size_t>(TF_MAX_STAGES, (size_t)((occ == 2 ? 100 : 190) * 1024) / per_stage);
+  if (a.stages < 2) { set_error("tf32 conv: tile does not fit in shared memory"); return YB_ERR_SHAPE; }
   const size_t smem = (size_t)a.stages * (a.a_stride + a.b_stride) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     YB_CUDA_CHECK(cudaFuncSetAttribute(tf_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  const int grid = std::min(a.total_tiles, tf_num_sms());
+  const int grid = std::min(a.total_tiles, occ * tf_num_sms());
   tf_conv_kernel<<<grid, TF_THREADS, smem, s>>>(a);
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -654,7 +662,7 @@ size_t tf_conv_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, in
   const WgPlan p = wg_plan(N, H, W, Cin, Cout, k, stride, k / 2);
   const size_t part = (size_t)p.splits * p.co_pad * k * k * p.ci_pad * 4;
   const size_t wpk = (size_t)Cout * Cin * k * k * 4;
-  return std::max(part, wpk) + 256;
+  return std::max(std::max(part, wpk), (size_t)148 * 4 * 27 * 128 * sizeof(float)) + 256;
 }
 
 int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
@@ -723,6 +731,165 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// The 3-channel stem (model.0: Conv(3, C, k = 3, s = 2), Yolo.cs:53) on CUDA cores, fp32.
+// On the tensor-core path the stem ran with its input zero-padded to 8 channels: K = 8 per tap means one tiny MMA per TMA
+// box of 128 strided 32-byte rows, and both passes were bound by the TMA row rate - forward 239 us and wgrad 1 288 us of a
+// 24.6 ms step (profiles/r2_ncu_tf_conv_big.txt, r2_ncu_tf_wgrad_big.txt), for 0.3 % of the step's FLOPs.  Here:
+//   forward   one thread per output pixel and 32-channel group: its 27 inputs in registers, weights [27][C] in shared memory
+//   wgrad     dW[co][ci][kh][kw] = sum over pixels of dz[p][co] * x[window(p)][ci][kh][kw]: a block stages 128 pixels (their
+//             27-value windows and dz rows) in shared memory, thread (co lane, tap group) accumulates its share of the
+//             27 x C products; per-block partials are folded in block order (deterministic)
+// x is NHWC with `xc` channels per pixel of which the first 3 are used (the native step keeps an 8-channel input).
+// ------------------------------------------------------------------------------------------
+constexpr int ST_PIX = 128;
+
+__global__ void __launch_bounds__(256) stem3_forward_kernel(const float* __restrict__ x, int xc, const float* __restrict__ w,
+                                                           float* __restrict__ z, int N, int H, int W, int Ho, int Wo, int C) {
+  extern __shared__ float sw[];  // [27][C]: k = (kh * 3 + kw) * 3 + ci
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) {
+    const int co = i % C, k = i / C;
+    const int ci = k % 3, t = k / 3;
+    sw[i] = w[(co * 3 + ci) * 9 + t];
+  }
+  __syncthreads();
+  const int groups = (C + 31) / 32;
+  const long long total = (long long)N * Ho * Wo * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    long long p = idx / groups;
+    const int wo = (int)(p % Wo);
+    p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float in[27];
+#pragma unroll
+    for (int kh = 0; kh < 3; kh++) {
+      const int hi = 2 * ho + kh - 1;
+#pragma unroll
+      for (int kw = 0; kw < 3; kw++) {
+        const int wi = 2 * wo + kw - 1;
+        const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+        const float* px = x + (((size_t)n * H + (ok ? hi : 0)) * W + (ok ? wi : 0)) * xc;
+#pragma unroll
+        for (int ci = 0; ci < 3; ci++) in[(kh * 3 + kw) * 3 + ci] = ok ? px[ci] : 0.f;
+      }
+    }
+    const int c0 = g * 32, cn = min(32, C - c0);
+    float* out = z + ((size_t)(n * Ho + ho) * Wo + wo) * C + c0;
+    for (int c = 0; c < cn; c += 4) {  // C is a multiple of 8
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 27; k++) {
+        const float4 wv = *reinterpret_cast<const float4*>(sw + k * C + c0 + c);
+        a0 = fmaf(in[k], wv.x, a0); a1 = fmaf(in[k], wv.y, a1); a2 = fmaf(in[k], wv.z, a2); a3 = fmaf(in[k], wv.w, a3);
+      }
+      *reinterpret_cast<float4*>(out + c) = make_float4(a0, a1, a2, a3);
+    }
+  }
+}
+
+// grid.x blocks walk the pixel tiles with stride gridDim.x; partial[block][27][C]
+__global__ void __launch_bounds__(256) stem3_wgrad_partial_kernel(const float* __restrict__ x, int xc, const float* __restrict__ dz,
+                                                                 float* __restrict__ partial, int N, int H, int W, int Ho, int Wo, int C) {
+  extern __shared__ float sm[];
+  float* xs = sm;                 // [ST_PIX][28] windows (27 used, row padded)
+  float* ds = sm + ST_PIX * 28;   // [ST_PIX][C]
+  const long long rows = (long long)N * Ho * Wo;
+  const long long tiles = (rows + ST_PIX - 1) / ST_PIX;
+  const int lane_c = threadIdx.x & 31, grp = threadIdx.x >> 5;  // 8 tap groups: taps k = grp, grp + 8, ... (<= 4 each)
+  const int cgroups = (C + 31) / 32;
+  float acc[4][4];                 // [tap slot][channel group] (C <= 128)
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long p0 = tile * ST_PIX;
+    __syncthreads();
+    for (int i = threadIdx.x; i < ST_PIX * 27; i += 256) {
+      const int pl = i / 27, k = i - pl * 27;
+      const long long p = p0 + pl;
+      float v = 0.f;
+      if (p < rows) {
+        const int wo = (int)(p % Wo);
+        const long long q = p / Wo;
+        const int ho = (int)(q % Ho), n = (int)(q / Ho);
+        const int t = k / 3, ci = k - t * 3, kh = t / 3, kw = t - kh * 3;
+        const int hi = 2 * ho + kh - 1, wi = 2 * wo + kw - 1;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[(((size_t)n * H + hi) * W + wi) * xc + ci];
+      }
+      xs[pl * 28 + k] = v;
+    }
+    for (int i = threadIdx.x; i < ST_PIX * C; i += 256) {
+      const int pl = i / C, c = i - pl * C;
+      ds[i] = (p0 + pl < rows) ? dz[(p0 + pl) * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int pl = 0; pl < ST_PIX; pl++) {
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        if (b < cgroups) {
+          const int c = b * 32 + lane_c;
+          const float g = c < C ? ds[pl * C + c] : 0.f;
+#pragma unroll
+          for (int a = 0; a < 4; a++) {
+            const int k = grp + 8 * a;
+            if (k < 27) acc[a][b] = fmaf(g, xs[pl * 28 + k], acc[a][b]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int k = grp + 8 * a;
+    if (k >= 27) continue;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int c = b * 32 + lane_c;
+      if (b < cgroups && c < C) partial[((size_t)blockIdx.x * 27 + k) * C + c] = acc[a][b];
+    }
+  }
+}
+__global__ void stem3_wgrad_fold_kernel(const float* __restrict__ partial, int blocks, int C, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (k, c)
+  if (i >= 27 * C) return;
+  const int k = i / C, c = i - k * C;
+  float s = 0.f;
+  for (int b = 0; b < blocks; b++) s += partial[((size_t)b * 27 + k) * C + c];
+  const int ci = k % 3, t = k / 3;
+  dw[(c * 3 + ci) * 9 + t] = s;
+}
+
+int stem3_forward(const float* x, int xc, const float* w, int N, int H, int W, int C, float* z, cudaStream_t s) {
+  if (C % 8 || C > 128 || (H & 1) || (W & 1) || xc < 3) { set_error("stem conv: C % 8 == 0, C <= 128, even input size"); return YB_ERR_SHAPE; }
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo * ((C + 31) / 32);
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  stem3_forward_kernel<<<grid, 256, (size_t)27 * C * sizeof(float), s>>>(x, xc, w, z, N, H, W, Ho, Wo, C);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+size_t stem3_wgrad_workspace_bytes(int C) { return (size_t)148 * 4 * 27 * C * sizeof(float); }
+int stem3_backward_weight(const float* x, int xc, const float* dz, int N, int H, int W, int C, float* dw, float* ws, size_t ws_bytes,
+                          cudaStream_t s) {
+  if (C % 8 || C > 128 || (H & 1) || (W & 1) || xc < 3) { set_error("stem wgrad: C % 8 == 0, C <= 128, even input size"); return YB_ERR_SHAPE; }
+  const int blocks = 148 * 4;
+  if (ws_bytes < stem3_wgrad_workspace_bytes(C)) { set_error("stem wgrad: workspace too small"); return YB_ERR_INVALID_ARG; }
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t smem = (size_t)(ST_PIX * 28 + ST_PIX * C) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    YB_CUDA_CHECK(cudaFuncSetAttribute(stem3_wgrad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  stem3_wgrad_partial_kernel<<<blocks, 256, smem, s>>>(x, xc, dz, ws, N, H, W, Ho, Wo, C);
+  stem3_wgrad_fold_kernel<<<(27 * C + 127) / 128, 128, 0, s>>>(ws, blocks, C, dw);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 static bool tf_have_dev(const char* who) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -774,6 +941,20 @@ int32_t yb_conv_backward_weight_tc(const float* x, const float* dz, int32_t n, i
   if (!tf_have_dev("yb_conv_backward_weight_tc")) return YB_ERR_NO_DEVICE;
   return tf_conv_backward_weight(x, dz, n, height, width, cin, cout, k, stride, pad, dw, (float*)workspace, (size_t)workspace_bytes,
                                  (cudaStream_t)stream, 0);
+}
+
+int32_t yb_stem_conv_forward_f32(const float* x, int32_t x_channels, const float* w, int32_t n, int32_t height, int32_t width,
+                                 int32_t cout, float* z, void* stream) {
+  if (!x || !w || !z || n <= 0 || height <= 0 || width <= 0 || cout <= 0) { set_error("yb_stem_conv_forward_f32: bad argument"); return YB_ERR_INVALID_ARG; }
+  if (!tf_have_dev("yb_stem_conv_forward_f32")) return YB_ERR_NO_DEVICE;
+  return stem3_forward(x, x_channels, w, n, height, width, cout, z, (cudaStream_t)stream);
+}
+
+int32_t yb_stem_conv_backward_weight_f32(const float* x, int32_t x_channels, const float* dz, int32_t n, int32_t height, int32_t width,
+                                         int32_t cout, float* dw, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!x || !dz || !dw || !workspace || n <= 0 || height <= 0 || width <= 0 || cout <= 0) { set_error("yb_stem_conv_backward_weight_f32: bad argument"); return YB_ERR_INVALID_ARG; }
+  if (!tf_have_dev("yb_stem_conv_backward_weight_f32")) return YB_ERR_NO_DEVICE;
+  return stem3_backward_weight(x, x_channels, dz, n, height, width, cout, dw, (float*)workspace, (size_t)workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -36,6 +36,9 @@ int tf_conv_backward_data(const float* dz, const float* w, int N, int H, int W, 
 int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                             float* dw, float* ws, size_t ws_bytes, cudaStream_t s, int x_pitch);
 size_t tf_conv_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride);
+int stem3_forward(const float* x, int xc, const float* w, int N, int H, int W, int C, float* z, cudaStream_t s);
+int stem3_backward_weight(const float* x, int xc, const float* dz, int N, int H, int W, int C, float* dw, float* ws, size_t ws_bytes,
+                          cudaStream_t s);
 int dwconv3x3_forward_f32(const float* x, const float* w, int N, int H, int W, int C, float* z, cudaStream_t s);
 int dwconv3x3_backward_f32(const float* x, const float* dz, const float* w, int N, int H, int W, int C, float* dx, float* dw,
                            cudaStream_t s);
@@ -193,7 +196,9 @@ __global__ void colsum_fold_kernel(const float* __restrict__ part, int slabs, in
   for (int s = 0; s < slabs; s++) t += part[(size_t)s * C + c];
   out[c] = t;
 }
-// images (B, 3, H, W) NCHW u8 (/255, Detector.cs:41) or f32 -> NHWC fp32 with the channels zero-padded to 8
+// images (B, 3, H, W) NCHW u8 or f32 -> NHWC fp32 with the channels zero-padded to 8.  u8 pixels are scaled the way the
+// training loader does it, `img.mul(1 / 255.0f)` (Data/YoloDataset.cs:140): a multiply by the rounded reciprocal, which is
+// also what torch's CUDA `x / 255` computes; a true division differs by one ulp on ~40% of the pixel values.
 __global__ void images_to_nhwc8_kernel(const void* __restrict__ in, int is_u8, float* __restrict__ out, int B, int H, int W) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)B * H * W;
@@ -204,7 +209,7 @@ __global__ void images_to_nhwc8_kernel(const void* __restrict__ in, int is_u8, f
   float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int c = 0; c < 3; c++) {
     const long long src = ((long long)b * 3 + c) * hw + p;
-    v[c] = is_u8 ? (float)reinterpret_cast<const uint8_t*>(in)[src] / 255.0f : reinterpret_cast<const float*>(in)[src];
+    v[c] = is_u8 ? (float)reinterpret_cast<const uint8_t*>(in)[src] * (1.0f / 255.0f) : reinterpret_cast<const float*>(in)[src];
   }
   float4* o = reinterpret_cast<float4*>(out + i * 8);
   o[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -336,6 +341,8 @@ struct Conv : Module {
     const float* w = n.p(name + ".conv.weight");
     if (depthwise) {
       n.check(dwconv3x3_forward_f32(x.p, w, x.N, x.H, x.W, x.C, z.p, n.s));
+    } else if (pad8 && k == 3 && s == 2 && cout % 8 == 0 && cout <= 128) {
+      n.check(stem3_forward(x.p, 8, w, x.N, x.H, x.W, cout, z.p, n.s));  // the 3-channel stem: fp32 CUDA cores (conv_tf32.cu)
     } else if (pad8) {
       float* w8 = n.alloc((long long)cout * 8 * k * k);
       if (n.rc) return y;
@@ -360,6 +367,8 @@ struct Conv : Module {
       dx = n.make(x.N, x.H, x.W, x.C);
       if (n.rc) return dx;
       n.check(dwconv3x3_backward_f32(x.p, dz.p, w, x.N, x.H, x.W, x.C, dx.p, gw, n.s));
+    } else if (pad8 && k == 3 && s == 2 && cout % 8 == 0 && cout <= 128) {
+      n.check(stem3_backward_weight(x.p, 8, dz.p, x.N, x.H, x.W, cout, gw, n.ws, n.ws_bytes, n.s));  // the images need no gradient
     } else if (pad8) {
       float* g8 = n.alloc((long long)cout * 8 * k * k);
       if (n.rc) return dx;

@@ -440,6 +440,34 @@ def conv_backward_tc(x, dz, w, stride=1, pad=None, ws=None, stream=None, need_dx
     return dx, dw
 
 
+def stem_conv_supported(w, stride, pad, H, W):
+    return tuple(w.shape[1:]) == (3, 3, 3) and stride == 2 and pad == 1 and w.shape[0] % 8 == 0 and w.shape[0] <= 128 and H % 2 == 0 and W % 2 == 0
+
+
+def stem_conv_forward(x, w, stream=None):
+    """yb_stem_conv_forward_f32: x (N,H,W,>=3) NHWC float32, w (C,3,3,3) -> z (N,H/2,W/2,C)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and w.is_cuda and w.is_contiguous()
+    N, H, W, xc = x.shape
+    Cout = w.shape[0]
+    z = torch.empty((N, H // 2, W // 2, Cout), dtype=torch.float32, device=x.device)
+    L.check(L.lib().yb_stem_conv_forward_f32(C.c_void_p(x.data_ptr()), xc, C.c_void_p(w.data_ptr()), N, H, W, Cout, C.c_void_p(z.data_ptr()),
+                                             _stream_ptr(stream)))
+    return z
+
+
+def stem_conv_backward_weight(x, dz, w_shape, ws=None, stream=None):
+    """yb_stem_conv_backward_weight_f32 -> dw (C,3,3,3)."""
+    assert x.is_cuda and dz.is_cuda and x.is_contiguous() and dz.is_contiguous()
+    N, H, W, xc = x.shape
+    Cout = dz.shape[-1]
+    ws = ws or ConvWorkspace(x.device)
+    buf = ws.get(N, H, W, 8, Cout, 3, 2)
+    dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
+    L.check(L.lib().yb_stem_conv_backward_weight_f32(C.c_void_p(x.data_ptr()), xc, C.c_void_p(dz.data_ptr()), N, H, W, Cout,
+                                                     C.c_void_p(dw.data_ptr()), C.c_void_p(buf.data_ptr()), buf.numel(), _stream_ptr(stream)))
+    return dw
+
+
 def dwconv3x3_forward(x, w, stream=None):
     """yb_dwconv3x3_forward_f32: x (N,H,W,C) NHWC float32, w (C,1,3,3) -> z (N,H,W,C) (stride 1, pad 1)."""
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and w.is_cuda and w.is_contiguous()

@@ -86,6 +86,8 @@ class KernelOps:
         return self.ws
 
     def conv_forward(self, x, w, bias, stride, pad):
+        if self.tc and bias is None and self.E.stem_conv_supported(w, stride, pad, x.shape[1], x.shape[2]):
+            return self.E.stem_conv_forward(x.contiguous(), w.contiguous())  # the 3-channel stem: fp32 CUDA cores
         if self._tc_ok(x, w, stride, pad):
             xp, wp, _ = self._pad8(x, w)
             return self.E.conv_forward_tc(xp, wp, bias, stride, pad, ws=self._ws(x))
@@ -93,6 +95,8 @@ class KernelOps:
 
     def conv_backward(self, x, dz, w, stride, pad, need_dx=True):
         """-> (dx or None when the caller does not need it (the network input), dw)."""
+        if self.tc and not need_dx and self.E.stem_conv_supported(w, stride, pad, x.shape[1], x.shape[2]):
+            return None, self.E.stem_conv_backward_weight(x.contiguous(), dz.contiguous(), w.shape, ws=self._ws(x))
         if self._tc_ok(x, w, stride, pad):
             xp, wp, Cin = self._pad8(x, w)
             dx, dw = self.E.conv_backward_tc(xp, dz.contiguous(), wp, stride, pad, ws=self._ws(x), need_dx=need_dx)
