@@ -125,3 +125,43 @@ def test_sharded_predict_gathers_all_ranks_world2():
     global image order, bit-identical to single-GPU predicts of the same shards (BASELINE configs[2] mechanics)."""
     _need(2)
     assert _run(_predict_worker, 2) == [(0, True), (1, True)]
+
+
+def _train_worker(rank, world, port, q):
+    _init(rank, world, port)
+    try:
+        from yolosharp_b200.train_native import NativeTrainer
+        from tests.test_train_step import _targets
+        from tests.util import oracle_model, synth_image
+        torch.manual_seed(0)
+        sd = {k: v.detach().clone() for k, v in oracle_model("v8", "detect", "n").state_dict().items()}
+        B, H, W = 2, 64, 96
+        shards = [(synth_image(B, H, W, seed=70 + r).cuda(), _targets(B, seed=r)) for r in range(world)]
+        mk = lambda: NativeTrainer(sd, "v8", "n", 80, device=torch.device("cuda", rank), max_batch=B, height=H, width=W, lr=1e-3)
+        # what every rank should hold after the all-reduce: the sum of the per-shard gradients, each taken on its own
+        want = None
+        for x, t in shards:
+            solo = mk()
+            solo.group = False  # no collective
+            solo.step(x, t)
+            want = solo.grad.clone() if want is None else want + solo.grad
+        ddp = mk()
+        ddp.step(*shards[rank])
+        torch.cuda.synchronize()
+        scale = float(want.abs().max())
+        err = float((ddp.grad - want).abs().max()) / scale
+        # the updated weights must be the same on every rank (same summed gradient, same AdamW)
+        w = [torch.empty_like(ddp.flat) for _ in range(world)]
+        dist.all_gather(w, ddp.flat)
+        same = all(torch.equal(w[0], wi) for wi in w)
+        q.put((rank, err < 1e-6, same))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_native_train_step_allreduce_world2():
+    """The native step on 2 GPUs (BASELINE configs[3] mechanics): after yb_train_backward + the NCCL all-reduce of the flat
+    gradient buffer every rank holds the SUM of the two shards' gradients (each equal to a single-GPU step on that shard:
+    BatchNorm statistics stay per rank, as DDP without SyncBN), and yb_train_apply leaves identical weights on both ranks."""
+    _need(2)
+    assert _run(_train_worker, 2) == [(0, True, True), (1, True, True)]

@@ -43,3 +43,11 @@ tot = sum(r[1] for r in rows)
 print(f"# device time {tot:.2f} ms in {sum(r[2] for r in rows)} kernels")
 for k, ms, n in rows[:30]:
     print(f"{ms:9.3f} ms {100 * ms / tot:5.1f}% {n:5d}x  {k[:110]}")
+# YB_PROF_DUMP=substr[,substr]: every launch of the matching kernels in timeline order (duration, grid, block) - which layers
+# a kernel family spends its time on
+dump = [d for d in os.environ.get("YB_PROF_DUMP", "").split(",") if d]
+if dump:
+    evs = [e for e in prof.events() if e.device_type.name == "CUDA" and any(d in e.name for d in dump)]
+    evs.sort(key=lambda e: e.time_range.start)
+    for e in evs:
+        print(f"{e.time_range.start / 1e3:10.3f} {e.device_time / 1:8.1f} us  {e.name[:60]}")

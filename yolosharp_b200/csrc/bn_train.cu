@@ -134,6 +134,179 @@ __global__ void __launch_bounds__(256) bn_finish_kernel(int step, const float* _
   }
 }
 
+// ---- vectorised statistics pass with the fold fused in -----------------------------------------------------------------
+// C % 4 == 0: a thread owns 4 adjacent channels (16-byte loads) and walks its slab's rows 4 at a time, all loads of a batch
+// issued before the first add (the scalar kernel above keeps one 4-byte load per thread in flight and reaches a third of the
+// HBM rate on the 1.6 M-row layers).  Block = LX channel lanes x LY rows (LX * LY = 256).  Sums are taken in row order per
+// thread, folded over LY in lane order, written per slab; the block that arrives LAST on its channel column (a ticket from
+// `counter`) folds the slabs in slab order and finishes the statistics - same fixed summation order whichever block it is,
+// so the result is deterministic, and the 162 bn_finish launches of a YOLOv11s step disappear.
+struct BnStat {
+  const float *z, *dy;
+  long long M;
+  int C, pitch, dpitch, rpb, slabs, act;
+  const float *mean, *invstd, *gamma, *beta;
+  float *p0, *p1;
+  unsigned* counter;  // one per channel column, zero on entry, left zero
+  float eps, momentum;
+  float *o_mean, *o_invstd, *running_mean, *running_var, *dgamma, *dbeta;
+};
+
+constexpr int BN4_U_FWD = 8, BN4_U_BWD = 4;  // rows per batch: 8 x 16 B (forward, z only) / 4 x 2 x 16 B (backward, z and dy) in flight per thread
+
+template <int MODE>  // 3: forward shifted sums (S1, S2 about K = z[row 0]); 2: backward sums (sum g, sum g * xhat)
+__global__ void __launch_bounds__(256) bn_stats4_kernel(const BnStat a) {
+  const int LX = blockDim.x, LY = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
+  const int c = (blockIdx.x * LX + tx) * 4;
+  const bool on = c < a.C;
+  __shared__ float red[8][256];
+  __shared__ int s_last;
+  constexpr int BN4_U = MODE == 3 ? BN4_U_FWD : BN4_U_BWD;
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 K = make_float4(0.f, 0.f, 0.f, 0.f), IS = K, GA = K, BE = K;
+  if (on) {
+    if (MODE == 3) {
+      K = *reinterpret_cast<const float4*>(a.z + c);
+    } else {
+      // per-channel vectors may sit at any 4-byte offset of the caller's flat buffers: scalar loads
+      K = make_float4(a.mean[c], a.mean[c + 1], a.mean[c + 2], a.mean[c + 3]);
+      IS = make_float4(a.invstd[c], a.invstd[c + 1], a.invstd[c + 2], a.invstd[c + 3]);
+      GA = make_float4(a.gamma[c], a.gamma[c + 1], a.gamma[c + 2], a.gamma[c + 3]);
+      BE = make_float4(a.beta[c], a.beta[c + 1], a.beta[c + 2], a.beta[c + 3]);
+    }
+    const long long r0 = (long long)blockIdx.y * a.rpb, r1 = min(a.M, r0 + a.rpb);
+    const float kk[4] = {K.x, K.y, K.z, K.w}, ii[4] = {IS.x, IS.y, IS.z, IS.w};
+    const float gg[4] = {GA.x, GA.y, GA.z, GA.w}, bb[4] = {BE.x, BE.y, BE.z, BE.w};
+    auto acc = [&](const float4& v, const float4& d) {
+      const float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (MODE == 3) {
+          const float e = vv[j] - kk[j];
+          s0[j] += e;
+          s1[j] = fmaf(e, e, s1[j]);
+        } else {
+          const float xh = (vv[j] - kk[j]) * ii[j];
+          const float g = dd[j] * (a.act ? silu_grad(gg[j] * xh + bb[j]) : 1.f);
+          s0[j] += g;
+          s1[j] += g * xh;
+        }
+      }
+    };
+    // this thread's rows: r0 + ty, + LY, ...; full batches of BN4_U rows with every load issued before the first add
+    // (plain pointer steps and an int trip count: with 64-bit row indices or a guarded load per row the compiler keeps a
+    // single load in flight)
+    const long long span = r1 - r0 - ty;
+    const int nrows = span > 0 ? (int)((span + LY - 1) / LY) : 0;
+    const float* zp = a.z + (r0 + ty) * a.pitch + c;
+    const float* dp = MODE == 2 ? a.dy + (r0 + ty) * a.dpitch + c : nullptr;
+    const size_t zs = (size_t)LY * a.pitch, ds = MODE == 2 ? (size_t)LY * a.dpitch : 0;
+    int it = 0;
+#pragma unroll 1
+    for (; it + BN4_U <= nrows; it += BN4_U) {
+      float4 v[BN4_U], d[BN4_U];
+#pragma unroll
+      for (int u = 0; u < BN4_U; u++) {
+        v[u] = __ldg(reinterpret_cast<const float4*>(zp + u * zs));
+        if (MODE == 2) d[u] = __ldg(reinterpret_cast<const float4*>(dp + u * ds));
+        else d[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      zp += BN4_U * zs;
+      if (MODE == 2) dp += BN4_U * ds;
+#pragma unroll
+      for (int u = 0; u < BN4_U; u++) acc(v[u], d[u]);
+    }
+#pragma unroll 1
+    for (; it < nrows; it++) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(zp));
+      const float4 d = MODE == 2 ? __ldg(reinterpret_cast<const float4*>(dp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      zp += zs;
+      if (MODE == 2) dp += ds;
+      acc(v, d);
+    }
+  }
+  const int t = ty * LX + tx;
+#pragma unroll
+  for (int j = 0; j < 4; j++) { red[j][t] = s0[j]; red[4 + j][t] = s1[j]; }
+  __syncthreads();
+  // fold over the LY row lanes in lane order: thread (x, j) -> channel lane x, component j of (s0[0..3], s1[0..3])
+  if (t < LX * 8) {
+    const int j = t / LX, x = t - j * LX;
+    float f = 0.f;
+    for (int y = 0; y < LY; y++) f += red[j][y * LX + x];
+    const int ch = (blockIdx.x * LX + x) * 4 + (j & 3);
+    if (ch < a.C) (j < 4 ? a.p0 : a.p1)[(size_t)blockIdx.y * a.C + ch] = f;
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_last = atomicAdd(&a.counter[blockIdx.x], 1u) == (unsigned)(a.slabs - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // the last block of this channel column: fold the slabs (lane y takes slabs y, y + LY, ... in order; lanes added in order)
+  float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+  if (on)
+    for (int sl = ty; sl < a.slabs; sl += LY) {
+      const float4 u0 = __ldcg(reinterpret_cast<const float4*>(a.p0 + (size_t)sl * a.C + c));
+      const float4 u1 = __ldcg(reinterpret_cast<const float4*>(a.p1 + (size_t)sl * a.C + c));
+      q0.x += u0.x; q0.y += u0.y; q0.z += u0.z; q0.w += u0.w;
+      q1.x += u1.x; q1.y += u1.y; q1.z += u1.z; q1.w += u1.w;
+    }
+  __syncthreads();
+  red[0][t] = q0.x; red[1][t] = q0.y; red[2][t] = q0.z; red[3][t] = q0.w;
+  red[4][t] = q1.x; red[5][t] = q1.y; red[6][t] = q1.z; red[7][t] = q1.w;
+  __syncthreads();
+  if (t == 0) a.counter[blockIdx.x] = 0;
+  if (t >= LX * 4) return;
+  const int j = t / LX, x = t - j * LX;
+  const int ch = (blockIdx.x * LX + x) * 4 + j;
+  if (ch >= a.C) return;
+  float t0 = 0.f, t1 = 0.f;
+  for (int y = 0; y < LY; y++) { t0 += red[j][y * LX + x]; t1 += red[4 + j][y * LX + x]; }
+  if (MODE == 3) {
+    const float Kc = a.z[ch];
+    const float dm = t0 / (float)a.M;
+    const float mu = Kc + dm;
+    const float var = fmaxf(t1 / (float)a.M - dm * dm, 0.f);  // biased: used for normalisation
+    a.o_mean[ch] = mu;
+    a.o_invstd[ch] = 1.f / sqrtf(var + a.eps);
+    if (a.running_mean) {
+      const float unbiased = a.M > 1 ? var * ((float)a.M / (float)(a.M - 1)) : var;
+      a.running_mean[ch] = (1.f - a.momentum) * a.running_mean[ch] + a.momentum * mu;
+      a.running_var[ch] = (1.f - a.momentum) * a.running_var[ch] + a.momentum * unbiased;
+    }
+  } else {
+    a.dbeta[ch] = t0;
+    a.dgamma[ch] = t1;
+  }
+}
+
+// launch geometry of the vectorised pass: LX channel lanes (power of two <= 32), slabs sized for ~4 blocks per SM
+struct Bn4Plan { int LX, LY, colblocks, rpb, slabs; };
+static Bn4Plan bn4_plan(long long M, int C, int U) {
+  Bn4Plan p;
+  const int c4 = C / 4;
+  p.LX = 1;
+  while (p.LX < c4 && p.LX < 32) p.LX <<= 1;
+  p.LY = 256 / p.LX;
+  p.colblocks = (c4 + p.LX - 1) / p.LX;
+  const int want = std::min(BN_MAX_SLABS, std::max(1, 592 / p.colblocks));
+  const long long step = (long long)p.LY * U;
+  long long rpb = (M + want - 1) / want;
+  rpb = std::max(step, (rpb + step - 1) / step * step);
+  p.rpb = (int)rpb;
+  p.slabs = (int)((M + rpb - 1) / rpb);
+  return p;
+}
+// the elementwise float4 kernels load the per-channel vectors 16 bytes at a time (a caller's flat parameter buffer need not be
+// 16-byte aligned per tensor, e.g. after an nc = 1 bias)
+static bool aligned16(const void* a, const void* b, const void* c, const void* d) {
+  return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
+}
+static bool bn4_ok(long long M, int C, const void* z, int pitch, const void* dy, int dpitch) {
+  return C % 4 == 0 && pitch % 4 == 0 && dpitch % 4 == 0 && (uintptr_t)z % 16 == 0 && (uintptr_t)dy % 16 == 0 && M * C / 4 < (1ll << 31);
+}
+
 __global__ void bn_silu_apply_kernel(const float* __restrict__ z, long long M, int C, int pitch, int opitch,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, int act, float* __restrict__ y) {
@@ -207,20 +380,35 @@ int bn_silu_train_forward(const float* z, long long M, int C, int pitch, const f
     set_error("yb_bn_silu_train_forward: bad shape");
     return YB_ERR_SHAPE;
   }
-  const int rpb = bn_rows_per_block(M);
-  const int slabs = (int)((M + rpb - 1) / rpb);
   float* part = nullptr;
-  YB_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)2 * slabs * C * sizeof(float), s));
-  const dim3 grid((C + BN_TX - 1) / BN_TX, slabs), block(BN_TX, BN_TY);
-  const dim3 fb(32, 8);
-  const int fg = (C + 31) / 32;
-  // one pass over z: per-slab sums of (z - K) and (z - K)^2 about the shift K = z[row 0], folded in slab order
-  bn_partial_kernel<<<grid, block, 0, s>>>(3, act, z, nullptr, M, C, pitch, 0, nullptr, nullptr, nullptr, nullptr, part,
-                                          part + (size_t)slabs * C, rpb);
-  bn_finish_kernel<<<fg, fb, 0, s>>>(3, part, part + (size_t)slabs * C, slabs, C, M, eps, momentum, save_mean, save_invstd, running_mean,
-                                     running_var, const_cast<float*>(z) /* the shift row, read only */, nullptr);
+  if (bn4_ok(M, C, z, pitch, z, pitch)) {
+    // one vectorised pass over z, statistics finished by the last block of each channel column
+    const Bn4Plan pl = bn4_plan(M, C, BN4_U_FWD);
+    const size_t nf = (size_t)2 * pl.slabs * C;
+    YB_CUDA_CHECK(cudaMallocAsync((void**)&part, nf * sizeof(float) + pl.colblocks * sizeof(unsigned), s));
+    YB_CUDA_CHECK(cudaMemsetAsync(part + nf, 0, pl.colblocks * sizeof(unsigned), s));
+    BnStat a{};
+    a.z = z; a.M = M; a.C = C; a.pitch = pitch; a.rpb = pl.rpb; a.slabs = pl.slabs; a.act = act;
+    a.p0 = part; a.p1 = part + (size_t)pl.slabs * C; a.counter = reinterpret_cast<unsigned*>(part + nf);
+    a.eps = eps; a.momentum = momentum; a.o_mean = save_mean; a.o_invstd = save_invstd;
+    a.running_mean = running_mean; a.running_var = running_var;
+    bn_stats4_kernel<3><<<dim3(pl.colblocks, pl.slabs), dim3(pl.LX, pl.LY), 0, s>>>(a);
+  } else {
+    const int rpb = bn_rows_per_block(M);
+    const int slabs = (int)((M + rpb - 1) / rpb);
+    YB_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)2 * slabs * C * sizeof(float), s));
+    const dim3 grid((C + BN_TX - 1) / BN_TX, slabs), block(BN_TX, BN_TY);
+    const dim3 fb(32, 8);
+    const int fg = (C + 31) / 32;
+    // one pass over z: per-slab sums of (z - K) and (z - K)^2 about the shift K = z[row 0], folded in slab order
+    bn_partial_kernel<<<grid, block, 0, s>>>(3, act, z, nullptr, M, C, pitch, 0, nullptr, nullptr, nullptr, nullptr, part,
+                                            part + (size_t)slabs * C, rpb);
+    bn_finish_kernel<<<fg, fb, 0, s>>>(3, part, part + (size_t)slabs * C, slabs, C, M, eps, momentum, save_mean, save_invstd, running_mean,
+                                       running_var, const_cast<float*>(z) /* the shift row, read only */, nullptr);
+  }
   const long long total = M * C;
-  if (C % 4 == 0 && pitch % 4 == 0 && ypitch % 4 == 0 && total / 4 < (1ll << 31) && ((uintptr_t)z % 16 == 0) && ((uintptr_t)y % 16 == 0)) {
+  if (C % 4 == 0 && pitch % 4 == 0 && ypitch % 4 == 0 && total / 4 < (1ll << 31) && ((uintptr_t)z % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
+      aligned16(save_mean, save_invstd, gamma, beta)) {
     const int total4 = (int)(total / 4);
     bn_silu_apply4_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(z, total4, C / 4, pitch, ypitch, save_mean, save_invstd, gamma,
                                                                           beta, act, y);
@@ -239,15 +427,28 @@ int bn_silu_backward(const float* z, const float* dy, long long M, int C, int pi
     set_error("yb_bn_silu_backward: bad shape");
     return YB_ERR_SHAPE;
   }
-  const int rpb = bn_rows_per_block(M);
-  const int slabs = (int)((M + rpb - 1) / rpb);
   float* part = nullptr;
-  YB_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)2 * slabs * C * sizeof(float), s));
-  const dim3 grid((C + BN_TX - 1) / BN_TX, slabs), block(BN_TX, BN_TY);
-  bn_partial_kernel<<<grid, block, 0, s>>>(2, act, z, dy, M, C, pitch, dpitch, save_mean, save_invstd, gamma, beta, part,
-                                          part + (size_t)slabs * C, rpb);
-  bn_finish_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(2, part, part + (size_t)slabs * C, slabs, C, M, 0.f, 0.f, nullptr, nullptr, nullptr,
-                                                   nullptr, dgamma, dbeta);
+  if (bn4_ok(M, C, z, pitch, dy, dpitch)) {
+    const Bn4Plan pl = bn4_plan(M, C, BN4_U_BWD);
+    const size_t nf = (size_t)2 * pl.slabs * C;
+    YB_CUDA_CHECK(cudaMallocAsync((void**)&part, nf * sizeof(float) + pl.colblocks * sizeof(unsigned), s));
+    YB_CUDA_CHECK(cudaMemsetAsync(part + nf, 0, pl.colblocks * sizeof(unsigned), s));
+    BnStat a{};
+    a.z = z; a.dy = dy; a.M = M; a.C = C; a.pitch = pitch; a.dpitch = dpitch; a.rpb = pl.rpb; a.slabs = pl.slabs; a.act = act;
+    a.mean = save_mean; a.invstd = save_invstd; a.gamma = gamma; a.beta = beta;
+    a.p0 = part; a.p1 = part + (size_t)pl.slabs * C; a.counter = reinterpret_cast<unsigned*>(part + nf);
+    a.dgamma = dgamma; a.dbeta = dbeta;
+    bn_stats4_kernel<2><<<dim3(pl.colblocks, pl.slabs), dim3(pl.LX, pl.LY), 0, s>>>(a);
+  } else {
+    const int rpb = bn_rows_per_block(M);
+    const int slabs = (int)((M + rpb - 1) / rpb);
+    YB_CUDA_CHECK(cudaMallocAsync((void**)&part, (size_t)2 * slabs * C * sizeof(float), s));
+    const dim3 grid((C + BN_TX - 1) / BN_TX, slabs), block(BN_TX, BN_TY);
+    bn_partial_kernel<<<grid, block, 0, s>>>(2, act, z, dy, M, C, pitch, dpitch, save_mean, save_invstd, gamma, beta, part,
+                                            part + (size_t)slabs * C, rpb);
+    bn_finish_kernel<<<(C + 31) / 32, dim3(32, 8), 0, s>>>(2, part, part + (size_t)slabs * C, slabs, C, M, 0.f, 0.f, nullptr, nullptr, nullptr,
+                                                     nullptr, dgamma, dbeta);
+  }
   const long long total = M * C;
   if (C % 4 == 0 && pitch % 4 == 0 && dpitch % 4 == 0 && zpitch % 4 == 0 && total / 4 < (1ll << 31) && ((uintptr_t)z % 16 == 0) &&
       ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dz % 16 == 0)) {

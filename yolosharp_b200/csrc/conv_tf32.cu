@@ -240,6 +240,41 @@ __global__ void tf_pack_weights_kernel(const float* __restrict__ w, float* __res
   }
 }
 
+struct TfPackDesc { long long off, chunk0; int cout, cin, taps, pad_; };  // off: element offset in the flat buffers; chunk0: first block
+// Every dense conv weight of a model in ONE launch (the native training step packs once per step, after the optimizer, instead
+// of once per conv call: 158 launches of the kernel above in a YOLOv11s step).  wf / wb use the SAME element offsets as the
+// checkpoint-layout tensors inside their flat buffer, so a layer's packed operands sit at WF + off and WB + off.
+constexpr int TF_PACK_CHUNK = 4096;
+__global__ void __launch_bounds__(256) tf_pack_all_kernel(const float* __restrict__ P, float* __restrict__ WF, float* __restrict__ WB,
+                                                          const TfPackDesc* __restrict__ d, int nd) {
+  int lo = 0, hi = nd - 1;  // last layer whose first chunk <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (d[mid].chunk0 <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const TfPackDesc L = d[lo];
+  const long long n = (long long)L.cout * L.cin * L.taps;
+  const long long i0 = ((long long)blockIdx.x - L.chunk0) * TF_PACK_CHUNK;
+  const float* w = P + L.off;
+  float* wf = WF + L.off;
+  float* wb = WB + L.off;
+  for (long long i = i0 + threadIdx.x; i < min(n, i0 + TF_PACK_CHUNK); i += 256) {
+    const int t = (int)(i % L.taps);
+    const long long q = i / L.taps;
+    const int ci = (int)(q % L.cin), co = (int)(q / L.cin);
+    const float v = w[i];
+    wf[((size_t)t * L.cout + co) * L.cin + ci] = v;
+    wb[((size_t)t * L.cin + ci) * L.cout + co] = v;
+  }
+}
+long long tf_pack_chunks(int cout, int cin, int taps) { return ((long long)cout * cin * taps + TF_PACK_CHUNK - 1) / TF_PACK_CHUNK; }
+int tf_pack_all(const float* P, float* WF, float* WB, const TfPackDesc* dev_descs, int nd, long long total_chunks, cudaStream_t s) {
+  if (nd <= 0 || total_chunks <= 0) return YB_OK;
+  tf_pack_all_kernel<<<(unsigned)total_chunks, 256, 0, s>>>(P, WF, WB, dev_descs, nd);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return YB_OK;
+}
+
 static int tf_num_sms() {
   static int n = 0;
   if (!n) {
@@ -361,16 +396,18 @@ static bool tf_shape_ok(int Cin, int Cout, int k, int stride, int pad) {
 }
 
 int tf_conv_forward(const float* x, const float* w, const float* bias, int N, int H, int W, int Cin, int Cout, int k, int stride,
-                    int pad, float* z, float* ws, size_t ws_bytes, cudaStream_t s, int x_pitch) {
+                    int pad, float* z, float* ws, size_t ws_bytes, cudaStream_t s, int x_pitch, const float* prepacked) {
   if (x_pitch && (x_pitch < Cin || x_pitch % 4 || ((uintptr_t)x & 15))) { set_error("tf32 conv: input view must be 16-byte aligned with a pitch multiple of 4"); return YB_ERR_SHAPE; }
   if (!tf_shape_ok(Cin, Cout, k, stride, pad)) { set_error("tf32 conv: channels must be multiples of 8, k in {1,3}, stride in {1,2}, pad = k/2"); return YB_ERR_SHAPE; }
   const size_t wn = (size_t)Cout * Cin * k * k;
-  if (ws_bytes < wn * 4) { set_error("tf32 conv forward: workspace too small"); return YB_ERR_INVALID_ARG; }
-  tf_pack_weights_kernel<<<(unsigned)std::min<size_t>((wn + 255) / 256, 1024), 256, 0, s>>>(w, ws, nullptr, Cout, Cin, k * k);
+  if (!prepacked) {  // prepacked: [tap][Cout][Cin], e.g. from tf_pack_all
+    if (ws_bytes < wn * 4) { set_error("tf32 conv forward: workspace too small"); return YB_ERR_INVALID_ARG; }
+    tf_pack_weights_kernel<<<(unsigned)std::min<size_t>((wn + 255) / 256, 1024), 256, 0, s>>>(w, ws, nullptr, Cout, Cin, k * k);
+  }
   TfLaunch L;
   memset(&L, 0, sizeof(L));
   L.in = x; L.N = N; L.Hi = H; L.Wi = W; L.Kc = Cin; L.in_pitch = x_pitch;
-  L.wpk = ws; L.Nc = Cout; L.taps_total = k * k;
+  L.wpk = prepacked ? prepacked : ws; L.Nc = Cout; L.taps_total = k * k;
   L.Ho = (H + 2 * pad - k) / stride + 1; L.Wo = (W + 2 * pad - k) / stride + 1;
   L.out = z; L.o_pix = Cout; L.o_row = (long long)L.Wo * Cout; L.o_img = (long long)L.Ho * L.o_row; L.o_off = 0;
   L.bias = bias;
@@ -382,19 +419,21 @@ int tf_conv_forward(const float* x, const float* w, const float* bias, int N, in
 }
 
 int tf_conv_backward_data(const float* dz, const float* w, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
-                          float* dx, float* ws, size_t ws_bytes, cudaStream_t s) {
+                          float* dx, float* ws, size_t ws_bytes, cudaStream_t s, const float* prepacked) {
   if (!tf_shape_ok(Cin, Cout, k, stride, pad) || (stride == 2 && ((H | W) & 1))) {
     set_error("tf32 dgrad: channels must be multiples of 8, k in {1,3}, stride in {1,2} (even size for stride 2), pad = k/2");
     return YB_ERR_SHAPE;
   }
   const size_t wn = (size_t)Cout * Cin * k * k;
-  if (ws_bytes < wn * 4) { set_error("tf32 dgrad: workspace too small"); return YB_ERR_INVALID_ARG; }
-  tf_pack_weights_kernel<<<(unsigned)std::min<size_t>((wn + 255) / 256, 1024), 256, 0, s>>>(w, nullptr, ws, Cout, Cin, k * k);
+  if (!prepacked) {  // prepacked: [tap][Cin][Cout]
+    if (ws_bytes < wn * 4) { set_error("tf32 dgrad: workspace too small"); return YB_ERR_INVALID_ARG; }
+    tf_pack_weights_kernel<<<(unsigned)std::min<size_t>((wn + 255) / 256, 1024), 256, 0, s>>>(w, nullptr, ws, Cout, Cin, k * k);
+  }
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   TfLaunch L;
   memset(&L, 0, sizeof(L));
   L.in = dz; L.N = N; L.Hi = Ho; L.Wi = Wo; L.Kc = Cout;
-  L.wpk = ws; L.Nc = Cin; L.taps_total = k * k;
+  L.wpk = prepacked ? prepacked : ws; L.Nc = Cin; L.taps_total = k * k;
   L.out = dx; L.bias = nullptr;
   L.in_stride = 1;
   if (stride == 1) {
@@ -619,18 +658,32 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
 }
 
 // dw[co][ci][tap] = sum over splits (fixed order) of part[split][co][tap][ci]
-// (threads over the checkpoint layout; a variant with the reads coalesced over ci and scattered writes was slower: 1.13 vs 0.87 ms)
-__global__ void tf_wgrad_fold_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cout, int Cin, int taps, int splits,
-                                     int co_pad, int ci_pad) {
-  const long long n = (long long)Cout * Cin * taps;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(i % taps);
-    const long long q = i / taps;
-    const int ci = (int)(q % Cin), co = (int)(q / Cin);
+// One block per output channel: the partials are read along ci (coalesced), summed over the splits in split order, transposed
+// through shared memory ([ci][tap], stride `taps` is odd or 1: no bank conflicts) and written as the contiguous run
+// dw[co][:][:].  (Threads over the checkpoint layout read 4-byte words ci_pad apart: 0.86 ms over the 79 folds of a YOLOv11s
+// step; reads coalesced over ci with scattered writes: 1.13 ms.)
+__global__ void __launch_bounds__(256) tf_wgrad_fold_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cout, int Cin,
+                                                            int taps, int splits, int co_pad, int ci_pad) {
+  extern __shared__ float fold_sm[];  // [Cin][taps]
+  const int co = blockIdx.x;
+  const size_t ss = (size_t)co_pad * taps * ci_pad;
+  const float* base = part + (size_t)co * taps * ci_pad;
+  const int n = Cin * taps;
+  for (int e = threadIdx.x; e < n; e += 256) {
+    const int t = e / Cin, ci = e - t * Cin;
+    const float* p = base + (size_t)t * ci_pad + ci;
     float acc = 0.f;
-    for (int s = 0; s < splits; s++) acc += part[(((size_t)s * co_pad + co) * taps + t) * ci_pad + ci];
-    dw[i] = acc;
+    int sp = 0;
+    for (; sp + 4 <= splits; sp += 4) {
+      const float a0 = p[(size_t)sp * ss], a1 = p[(size_t)(sp + 1) * ss], a2 = p[(size_t)(sp + 2) * ss], a3 = p[(size_t)(sp + 3) * ss];
+      acc += a0; acc += a1; acc += a2; acc += a3;
+    }
+    for (; sp < splits; sp++) acc += p[(size_t)sp * ss];
+    fold_sm[ci * taps + t] = acc;
   }
+  __syncthreads();
+  float* out = dw + (size_t)co * n;
+  for (int e = threadIdx.x; e < n; e += 256) out[e] = fold_sm[e];
 }
 
 struct WgPlan { int nb, co_tiles, ci_tiles, splits, co_pad, ci_pad, pix_tiles, tiles_w, tiles_h, tpc, tap_groups; };
@@ -726,7 +779,14 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
   tf_wgrad_kernel<<<grid, TF_THREADS, smem, s>>>(a);
   YB_CUDA_CHECK(cudaGetLastError());
   const size_t n = (size_t)Cout * Cin * k * k;
-  tf_wgrad_fold_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 2048), 256, 0, s>>>(ws, dw, Cout, Cin, k * k, p.splits, p.co_pad, p.ci_pad);
+  static bool fold_attr = false;
+  if (!fold_attr) {
+    YB_CUDA_CHECK(cudaFuncSetAttribute(tf_wgrad_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    fold_attr = true;
+  }
+  if ((size_t)Cin * k * k * sizeof(float) > (size_t)160 * 1024) { set_error("tf32 wgrad: Cin * k * k too large for the fold"); return YB_ERR_SHAPE; }
+  tf_wgrad_fold_kernel<<<Cout, 256, (size_t)Cin * k * k * sizeof(float), s>>>(ws, dw, Cout, Cin, k * k, p.splits, p.co_pad, p.ci_pad);
+  (void)n;
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -920,7 +980,7 @@ int32_t yb_conv_forward_tc(const float* x, const float* w, const float* bias, in
   if (n <= 0 || height <= 0 || width <= 0 || cin <= 0 || cout <= 0) { set_error("yb_conv_forward_tc: bad shape"); return YB_ERR_SHAPE; }
   if (!tf_have_dev("yb_conv_forward_tc")) return YB_ERR_NO_DEVICE;
   return tf_conv_forward(x, w, bias, n, height, width, cin, cout, k, stride, pad, z, (float*)workspace, (size_t)workspace_bytes,
-                         (cudaStream_t)stream, 0);
+                         (cudaStream_t)stream, 0, nullptr);
 }
 
 int32_t yb_conv_backward_data_tc(const float* dz, const float* w, int32_t n, int32_t height, int32_t width, int32_t cin, int32_t cout,
@@ -930,7 +990,7 @@ int32_t yb_conv_backward_data_tc(const float* dz, const float* w, int32_t n, int
   if (n <= 0 || height <= 0 || width <= 0 || cin <= 0 || cout <= 0) { set_error("yb_conv_backward_data_tc: bad shape"); return YB_ERR_SHAPE; }
   if (!tf_have_dev("yb_conv_backward_data_tc")) return YB_ERR_NO_DEVICE;
   return tf_conv_backward_data(dz, w, n, height, width, cin, cout, k, stride, pad, dx, (float*)workspace, (size_t)workspace_bytes,
-                               (cudaStream_t)stream);
+                               (cudaStream_t)stream, nullptr);
 }
 
 int32_t yb_conv_backward_weight_tc(const float* x, const float* dz, int32_t n, int32_t height, int32_t width, int32_t cin,

@@ -30,9 +30,12 @@ namespace yb {
 
 // entry points of the other translation units this step is made of
 int tf_conv_forward(const float* x, const float* w, const float* bias, int N, int H, int W, int Cin, int Cout, int k, int stride,
-                    int pad, float* z, float* ws, size_t ws_bytes, cudaStream_t s, int x_pitch);
+                    int pad, float* z, float* ws, size_t ws_bytes, cudaStream_t s, int x_pitch, const float* prepacked);
 int tf_conv_backward_data(const float* dz, const float* w, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
-                          float* dx, float* ws, size_t ws_bytes, cudaStream_t s);
+                          float* dx, float* ws, size_t ws_bytes, cudaStream_t s, const float* prepacked);
+struct TfPackDesc { long long off, chunk0; int cout, cin, taps, pad_; };
+long long tf_pack_chunks(int cout, int cin, int taps);
+int tf_pack_all(const float* P, float* WF, float* WB, const TfPackDesc* dev_descs, int nd, long long total_chunks, cudaStream_t s);
 int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                             float* dw, float* ws, size_t ws_bytes, cudaStream_t s, int x_pitch);
 size_t tf_conv_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride);
@@ -71,6 +74,27 @@ __global__ void add_kernel(float* __restrict__ out, int opitch, const float* __r
   const long long r = i / C;
   const int c = (int)(i - r * C);
   out[r * opitch + c] = a[r * apitch + c] + b[r * bpitch + c];
+}
+// 4 channels per thread (C, pitches, channel offsets multiples of 4, 16-byte aligned bases; 32-bit index math): the scalar
+// kernels above pay a 64-bit division per element
+__global__ void slice_copy4_kernel(float* __restrict__ dst, int dpitch, const float* __restrict__ src, int spitch, int total4, int C4,
+                                   int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int r = i / C4, c = (i - r * C4) * 4;
+  float4 v = *reinterpret_cast<const float4*>(src + (size_t)r * spitch + c);
+  float4* d = reinterpret_cast<float4*>(dst + (size_t)r * dpitch + c);
+  if (accumulate) { const float4 o = *d; v.x = o.x + v.x; v.y = o.y + v.y; v.z = o.z + v.z; v.w = o.w + v.w; }
+  *d = v;
+}
+__global__ void add4_kernel(float* __restrict__ out, int opitch, const float* __restrict__ a, int apitch, const float* __restrict__ b,
+                            int bpitch, int total4, int C4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int r = i / C4, c = (i - r * C4) * 4;
+  const float4 u = *reinterpret_cast<const float4*>(a + (size_t)r * apitch + c);
+  const float4 v = *reinterpret_cast<const float4*>(b + (size_t)r * bpitch + c);
+  *reinterpret_cast<float4*>(out + (size_t)r * opitch + c) = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
 }
 // nearest 2x upsample (Yolo.cs:70-84 `Upsample(scale_factor: 2)`), NHWC
 __global__ void up2_forward_kernel(const float* __restrict__ x, int xpitch, float* __restrict__ y, int ypitch, int N, int H, int W, int C) {
@@ -263,6 +287,11 @@ struct Net {
   size_t arena_cap = 0, arena_off = 0;
   float* ws = nullptr;
   size_t ws_bytes = 0;
+  // tensor-core operand layouts of every dense conv weight, same offsets as P; repacked once per step (tf_pack_all)
+  float *WF = nullptr, *WB = nullptr;
+  TfPackDesc* pack_descs = nullptr;
+  int n_packs = 0;
+  long long pack_chunks = 0;
   int step_count = 0;
   int rc = 0;  // first error of the current step (modules return empty tensors after it)
 
@@ -279,15 +308,25 @@ struct Net {
     return t;
   }
   float* p(const std::string& k) { return P + params[pidx.at(k)].off; }
+  const float* wf(const std::string& k) { return WF ? WF + params[pidx.at(k)].off : nullptr; }
+  const float* wb(const std::string& k) { return WB ? WB + params[pidx.at(k)].off : nullptr; }
   float* g(const std::string& k) { return G + params[pidx.at(k)].off; }
   float* r(const std::string& k) { return R + stats[sidx.at(k)].off; }
   void check(int code) { if (code && !rc) rc = code; }
   void check_launch() { if (!rc && cudaGetLastError() != cudaSuccess) { rc = YB_ERR_CUDA; set_error("yb_train_step: kernel launch failed"); } }
 };
 
+static bool vec4_ok(long long numel, int C, const void* p0, int pitch0, const void* p1, int pitch1, const void* p2, int pitch2) {
+  return C % 4 == 0 && pitch0 % 4 == 0 && pitch1 % 4 == 0 && pitch2 % 4 == 0 && numel / 4 < (1ll << 31) &&
+         (((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2) & 15) == 0;
+}
 static void put(Net& n, const T4& dst, int c0, const T4& src, bool accumulate = false) {  // dst[..., c0 : c0 + src.C] (+)= src
   if (n.rc) return;
-  slice_copy_kernel<<<nb(src.numel()), 256, 0, n.s>>>(dst.p, dst.pitch, c0, src.p, src.pitch, 0, src.rows(), src.C, accumulate ? 1 : 0);
+  if (vec4_ok(src.numel(), src.C, dst.p + c0, dst.pitch, src.p, src.pitch, src.p, src.pitch))
+    slice_copy4_kernel<<<nb(src.numel() / 4), 256, 0, n.s>>>(dst.p + c0, dst.pitch, src.p, src.pitch, (int)(src.numel() / 4), src.C / 4,
+                                                            accumulate ? 1 : 0);
+  else
+    slice_copy_kernel<<<nb(src.numel()), 256, 0, n.s>>>(dst.p, dst.pitch, c0, src.p, src.pitch, 0, src.rows(), src.C, accumulate ? 1 : 0);
   n.check_launch();
 }
 static T4 dense_copy(Net& n, const T4& x) {  // contiguous copy of a view (kernels that take no pitch)
@@ -298,7 +337,10 @@ static T4 dense_copy(Net& n, const T4& x) {  // contiguous copy of a view (kerne
 }
 static void add_into(Net& n, const T4& out, const T4& a, const T4& b) {
   if (n.rc) return;
-  add_kernel<<<nb(a.numel()), 256, 0, n.s>>>(out.p, out.pitch, a.p, a.pitch, b.p, b.pitch, a.rows(), a.C);
+  if (vec4_ok(a.numel(), a.C, out.p, out.pitch, a.p, a.pitch, b.p, b.pitch))
+    add4_kernel<<<nb(a.numel() / 4), 256, 0, n.s>>>(out.p, out.pitch, a.p, a.pitch, b.p, b.pitch, (int)(a.numel() / 4), a.C / 4);
+  else
+    add_kernel<<<nb(a.numel()), 256, 0, n.s>>>(out.p, out.pitch, a.p, a.pitch, b.p, b.pitch, a.rows(), a.C);
   n.check_launch();
 }
 static T4 add(Net& n, const T4& a, const T4& b) {
@@ -347,9 +389,10 @@ struct Conv : Module {
       float* w8 = n.alloc((long long)cout * 8 * k * k);
       if (n.rc) return y;
       pad_weight8_kernel<<<nb((long long)cout * 8 * k * k), 256, 0, n.s>>>(w, w8, cout, k * k);
-      n.check(tf_conv_forward(x.p, w8, nullptr, x.N, x.H, x.W, 8, cout, k, s, k / 2, z.p, n.ws, n.ws_bytes, n.s, 0));
+      n.check(tf_conv_forward(x.p, w8, nullptr, x.N, x.H, x.W, 8, cout, k, s, k / 2, z.p, n.ws, n.ws_bytes, n.s, 0, nullptr));
     } else {
-      n.check(tf_conv_forward(x.p, w, nullptr, x.N, x.H, x.W, cin, cout, k, s, k / 2, z.p, n.ws, n.ws_bytes, n.s, x.dense() ? 0 : x.pitch));
+      n.check(tf_conv_forward(x.p, w, nullptr, x.N, x.H, x.W, cin, cout, k, s, k / 2, z.p, n.ws, n.ws_bytes, n.s, x.dense() ? 0 : x.pitch,
+                              n.wf(name + ".conv.weight")));
     }
     n.check(bn_silu_train_forward(z.p, z.rows(), cout, cout, n.p(name + ".bn.weight"), n.p(name + ".bn.bias"), 1e-3f, 0.03f, act,
                                   n.r(name + ".bn.running_mean"), n.r(name + ".bn.running_var"), y.p, y.pitch, mean, invstd, n.s));
@@ -379,7 +422,7 @@ struct Conv : Module {
       if (need_dx) {
         dx = n.make(x.N, x.H, x.W, x.C);
         if (n.rc) return dx;
-        n.check(tf_conv_backward_data(dz.p, w, x.N, x.H, x.W, cin, cout, k, s, k / 2, dx.p, n.ws, n.ws_bytes, n.s));
+        n.check(tf_conv_backward_data(dz.p, w, x.N, x.H, x.W, cin, cout, k, s, k / 2, dx.p, n.ws, n.ws_bytes, n.s, n.wb(name + ".conv.weight")));
       }
       n.check(tf_conv_backward_weight(x.p, dz.p, x.N, x.H, x.W, cin, cout, k, s, k / 2, gw, n.ws, n.ws_bytes, n.s, x.dense() ? 0 : x.pitch));
     }
@@ -399,14 +442,15 @@ struct Conv2dBias : Module {
     T4 y = n.make(in.N, in.H, in.W, cout);
     if (n.rc) return y;
     n.check(tf_conv_forward(in.p, n.p(name + ".weight"), n.p(name + ".bias"), in.N, in.H, in.W, cin, cout, 1, 1, 0, y.p, n.ws, n.ws_bytes, n.s,
-                            in.dense() ? 0 : in.pitch));
+                            in.dense() ? 0 : in.pitch, n.wf(name + ".weight")));
     return y;
   }
   T4 backward(Net& n, T4 dz_in) override {
     T4 dz = dense_copy(n, dz_in);
     T4 dx = n.make(x.N, x.H, x.W, x.C);
     if (n.rc) return dx;
-    n.check(tf_conv_backward_data(dz.p, n.p(name + ".weight"), x.N, x.H, x.W, cin, cout, 1, 1, 0, dx.p, n.ws, n.ws_bytes, n.s));
+    n.check(tf_conv_backward_data(dz.p, n.p(name + ".weight"), x.N, x.H, x.W, cin, cout, 1, 1, 0, dx.p, n.ws, n.ws_bytes, n.s,
+                                  n.wb(name + ".weight")));
     n.check(tf_conv_backward_weight(x.p, dz.p, x.N, x.H, x.W, cin, cout, 1, 1, 0, n.g(name + ".weight"), n.ws, n.ws_bytes, n.s,
                                     x.dense() ? 0 : x.pitch));
     const long long rows = dz.rows();
@@ -919,6 +963,7 @@ int run_backward(yb_trainer* t, const void* images, int in_dtype, int B, const f
   if (n.rc) return n.rc;
   images_to_nhwc8_kernel<<<nb((long long)B * H * W), 256, 0, s>>>(images, in_dtype == YB_U8 ? 1 : 0, x.p, B, H, W);
   n.check_launch();
+  n.check(tf_pack_all(n.P, n.WF, n.WB, n.pack_descs, n.n_packs, n.pack_chunks, s));  // the weights as this step sees them
   // ---- forward (Yolo.cs:92-134) ----
   t->outputs.clear();
   t->cat_split.clear();
@@ -1061,6 +1106,31 @@ int32_t yb_trainer_create(const yb_config* cfg, yb_trainer** out) {
     if (t->net.ws) cudaFree(t->net.ws);
     return YB_ERR_CUDA;
   }
+  {
+    // tensor-core operand copies of every dense conv weight (forward [tap][Cout][Cin], dgrad [tap][Cin][Cout]) at the
+    // offsets of the checkpoint-layout tensors; one pack launch per step
+    Net& n = t->net;
+    std::vector<TfPackDesc> d;
+    long long chunk = 0;
+    for (auto& e : n.params) {
+      if (e.shape.size() != 4 || e.shape[0] % 8 || e.shape[1] % 8 || e.shape[2] != e.shape[3] || (e.shape[2] != 1 && e.shape[2] != 3)) continue;
+      TfPackDesc q{};
+      q.off = e.off; q.chunk0 = chunk; q.cout = (int)e.shape[0]; q.cin = (int)e.shape[1]; q.taps = (int)(e.shape[2] * e.shape[3]);
+      chunk += tf_pack_chunks(q.cout, q.cin, q.taps);
+      d.push_back(q);
+    }
+    n.n_packs = (int)d.size();
+    n.pack_chunks = chunk;
+    const size_t wbytes = (size_t)n.n_params * sizeof(float);
+    if (cudaMalloc((void**)&n.WF, wbytes) != cudaSuccess || cudaMalloc((void**)&n.WB, wbytes) != cudaSuccess ||
+        cudaMalloc((void**)&n.pack_descs, std::max<size_t>(1, d.size()) * sizeof(TfPackDesc)) != cudaSuccess ||
+        cudaMemcpy(n.pack_descs, d.data(), d.size() * sizeof(TfPackDesc), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("yb_trainer_create: cudaMalloc of the packed weight buffers failed");
+      cudaGetLastError();
+      yb_trainer_destroy(t.release());
+      return YB_ERR_CUDA;
+    }
+  }
   *out = t.release();
   return YB_OK;
 }
@@ -1069,6 +1139,9 @@ void yb_trainer_destroy(yb_trainer* t) {
   if (!t) return;
   if (t->net.ws) cudaFree(t->net.ws);
   if (t->net.arena) cudaFree(t->net.arena);
+  if (t->net.WF) cudaFree(t->net.WF);
+  if (t->net.WB) cudaFree(t->net.WB);
+  if (t->net.pack_descs) cudaFree(t->net.pack_descs);
   delete t;
 }
 
