@@ -140,12 +140,14 @@ int detection_loss_launch(const float* boxes, const float* scores, int B, int nc
                           const float* targets_host, int n_targets, int topk, float hyp_box, float hyp_cls, float hyp_dfl,
                           float* loss_items, float* grad_boxes, float* grad_scores, unsigned char* fg_out, int* gt_idx_out,
                           float* tscore_out, cudaStream_t s);
+// counters: optional >= 64 zeroed words owned by ONE stream (the statistics kernels leave them zero); nullptr = allocate and
+// clear per call
 int bn_silu_train_forward(const float* z, long long M, int C, int pitch, const float* gamma, const float* beta, float eps,
                           float momentum, int act, float* running_mean, float* running_var, float* y, int ypitch,
-                          float* save_mean, float* save_invstd, cudaStream_t s);
+                          float* save_mean, float* save_invstd, cudaStream_t s, unsigned* counters = nullptr);
 int bn_silu_backward(const float* z, const float* dy, long long M, int C, int pitch, int dpitch, const float* gamma,
                      const float* beta, const float* save_mean, const float* save_invstd, int act, float* dz, int zpitch,
-                     float* dgamma, float* dbeta, cudaStream_t s);
+                     float* dgamma, float* dbeta, cudaStream_t s, unsigned* counters = nullptr);
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, int step, float lr, float b1, float b2, float eps,
                float wd, cudaStream_t s);
 int conv_backward_data(const float* dz, const float* w, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,

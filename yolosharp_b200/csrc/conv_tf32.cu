@@ -706,8 +706,14 @@ static WgPlan wg_plan(int N, int H, int W, int Cin, int Cout, int k, int stride,
   p.tpc = taps == 9 ? 3 : 1;
   p.tap_groups = taps / p.tpc;
   const int pairs = p.co_tiles * p.ci_tiles * p.tap_groups;
-  p.splits = std::max(1, std::min(p.pix_tiles, (2 * tf_num_sms() + pairs - 1) / pairs));
-  p.splits = std::min(p.splits, 64);
+  // pixel splits: one CTA per SM (189 KiB of shared memory), so the grid should fill ONE wave of SMs, or two when that fills
+  // them noticeably better - never a few CTAs over (ceil(2 * 148 / pairs) capped at 64 gave grids of 300 - 320 = a third
+  // wave of 4 - 24 CTAs on a third of the layers, and 64-CTA grids on the 1x1 layers with <= 128 channels)
+  const int sms = tf_num_sms();
+  const int s1 = std::max(1, sms / pairs), s2 = std::max(1, 2 * sms / pairs);
+  const double u1 = (double)std::min(pairs * s1, sms) / sms, u2 = (double)std::min(pairs * s2, 2 * sms) / (2.0 * sms);
+  p.splits = (pairs <= sms && u2 > u1 + 0.08) ? s2 : s1;
+  p.splits = std::max(1, std::min(p.splits, p.pix_tiles));
   return p;
 }
 
@@ -849,66 +855,88 @@ __global__ void __launch_bounds__(256) stem3_forward_kernel(const float* __restr
   }
 }
 
-// grid.x blocks walk the pixel tiles with stride gridDim.x; partial[block][27][C]
+// Row-segment version: a tile is up to 128 adjacent output pixels of one output row.  The three input rows it needs are staged
+// as [kh][column][4] (one 16-byte load per input pixel, coalesced), so the 3 x 3 window of output pixel p is 3 x three
+// adjacent float4 of shared memory; dz of the tile is staged as [pixel][C].  Thread = (channel lane, warp g): warp g takes
+// pixels g, g + 8, ... and keeps all 27 taps of its channel(s) in registers: per pixel 9 broadcast LDS.128 + 1 LDS feed
+// 27 FMAs (the first version staged im2col windows element by element - ~40 integer instructions per staged value - and
+// spent 5 LDS per 4 FMAs: 690 us for 1.4 GFMA).  The 8 warps are folded in warp order through shared memory, the blocks'
+// partials by stem3_wgrad_fold_kernel in block order: deterministic.
+// grid.x blocks walk the tiles with stride gridDim.x; partial[block][27][C], k = (kh * 3 + kw) * 3 + ci
+template <int CG>  // 32-channel groups per thread: ceil(C / 32)
 __global__ void __launch_bounds__(256) stem3_wgrad_partial_kernel(const float* __restrict__ x, int xc, const float* __restrict__ dz,
                                                                  float* __restrict__ partial, int N, int H, int W, int Ho, int Wo, int C) {
-  extern __shared__ float sm[];
-  float* xs = sm;                 // [ST_PIX][28] windows (27 used, row padded)
-  float* ds = sm + ST_PIX * 28;   // [ST_PIX][C]
-  const long long rows = (long long)N * Ho * Wo;
-  const long long tiles = (rows + ST_PIX - 1) / ST_PIX;
-  const int lane_c = threadIdx.x & 31, grp = threadIdx.x >> 5;  // 8 tap groups: taps k = grp, grp + 8, ... (<= 4 each)
-  const int cgroups = (C + 31) / 32;
-  float acc[4][4];                 // [tap slot][channel group] (C <= 128)
+  extern __shared__ __align__(16) float sm[];
+  float* xs = sm;                              // [3][2 * ST_PIX + 1][4]
+  float* ds = sm + 3 * (2 * ST_PIX + 1) * 4;   // [ST_PIX][C]; later the fold buffer [8][27][32]
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int segs = (Wo + ST_PIX - 1) / ST_PIX;
+  const long long tiles = (long long)N * Ho * segs;
+  float acc[CG][27];
 #pragma unroll
-  for (int a = 0; a < 4; a++)
+  for (int b2 = 0; b2 < CG; b2++)
 #pragma unroll
-    for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+    for (int k = 0; k < 27; k++) acc[b2][k] = 0.f;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const long long p0 = tile * ST_PIX;
+    const int seg = (int)(tile % segs);
+    const long long q = tile / segs;
+    const int ho = (int)(q % Ho), n = (int)(q / Ho);
+    const int wo0 = seg * ST_PIX, npx = min(ST_PIX, Wo - wo0);
+    const int ncol = 2 * npx + 1, wi0 = 2 * wo0 - 1;
     __syncthreads();
-    for (int i = threadIdx.x; i < ST_PIX * 27; i += 256) {
-      const int pl = i / 27, k = i - pl * 27;
-      const long long p = p0 + pl;
-      float v = 0.f;
-      if (p < rows) {
-        const int wo = (int)(p % Wo);
-        const long long q = p / Wo;
-        const int ho = (int)(q % Ho), n = (int)(q / Ho);
-        const int t = k / 3, ci = k - t * 3, kh = t / 3, kw = t - kh * 3;
-        const int hi = 2 * ho + kh - 1, wi = 2 * wo + kw - 1;
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[(((size_t)n * H + hi) * W + wi) * xc + ci];
+    for (int i = threadIdx.x; i < 3 * ncol; i += 256) {
+      const int kh = i / ncol, j = i - kh * ncol;
+      const int hi = 2 * ho + kh - 1, wi = wi0 + j;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+        const float* px = x + (((size_t)n * H + hi) * W + wi) * xc;
+        if ((xc & 3) == 0) v = __ldg(reinterpret_cast<const float4*>(px));
+        else { v.x = px[0]; v.y = px[1]; v.z = px[2]; }
       }
-      xs[pl * 28 + k] = v;
+      *reinterpret_cast<float4*>(xs + ((size_t)kh * (2 * ST_PIX + 1) + j) * 4) = v;
     }
-    for (int i = threadIdx.x; i < ST_PIX * C; i += 256) {
-      const int pl = i / C, c = i - pl * C;
-      ds[i] = (p0 + pl < rows) ? dz[(p0 + pl) * C + c] : 0.f;
-    }
+    const float* dzt = dz + (((size_t)n * Ho + ho) * Wo + wo0) * C;  // npx * C contiguous floats (C % 8 == 0: 16-byte aligned)
+    for (int i = threadIdx.x; i < npx * C / 4; i += 256)
+      *reinterpret_cast<float4*>(ds + (size_t)i * 4) = __ldg(reinterpret_cast<const float4*>(dzt) + i);
     __syncthreads();
-    for (int pl = 0; pl < ST_PIX; pl++) {
+    for (int pl = g; pl < npx; pl += 8) {
+      float4 w9[9];  // [kh][kw] -> (ci 0..2, pad)
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
-        if (b < cgroups) {
-          const int c = b * 32 + lane_c;
-          const float g = c < C ? ds[pl * C + c] : 0.f;
+      for (int kh = 0; kh < 3; kh++)
 #pragma unroll
-          for (int a = 0; a < 4; a++) {
-            const int k = grp + 8 * a;
-            if (k < 27) acc[a][b] = fmaf(g, xs[pl * 28 + k], acc[a][b]);
+        for (int kw = 0; kw < 3; kw++)
+          w9[kh * 3 + kw] = *reinterpret_cast<const float4*>(xs + ((size_t)kh * (2 * ST_PIX + 1) + 2 * pl + kw) * 4);
+#pragma unroll
+      for (int b2 = 0; b2 < CG; b2++) {
+        {
+          const int c = b2 * 32 + lane;
+          const float gv = c < C ? ds[pl * C + c] : 0.f;
+#pragma unroll
+          for (int t = 0; t < 9; t++) {
+            acc[b2][t * 3 + 0] = fmaf(gv, w9[t].x, acc[b2][t * 3 + 0]);
+            acc[b2][t * 3 + 1] = fmaf(gv, w9[t].y, acc[b2][t * 3 + 1]);
+            acc[b2][t * 3 + 2] = fmaf(gv, w9[t].z, acc[b2][t * 3 + 2]);
           }
         }
       }
     }
   }
+  // fold the 8 warps in warp order, one 32-channel group at a time
+  float* red = ds;  // [8][27][32]
 #pragma unroll
-  for (int a = 0; a < 4; a++) {
-    const int k = grp + 8 * a;
-    if (k >= 27) continue;
+  for (int b2 = 0; b2 < CG; b2++) {
+    {
+      __syncthreads();
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
-      const int c = b * 32 + lane_c;
-      if (b < cgroups && c < C) partial[((size_t)blockIdx.x * 27 + k) * C + c] = acc[a][b];
+      for (int k = 0; k < 27; k++) red[(g * 27 + k) * 32 + lane] = acc[b2][k];
+      __syncthreads();
+      for (int i = threadIdx.x; i < 27 * 32; i += 256) {
+        const int k = i >> 5, cl = i & 31;
+        float sum = 0.f;
+        for (int w8 = 0; w8 < 8; w8++) sum += red[(w8 * 27 + k) * 32 + cl];
+        const int c = b2 * 32 + cl;
+        if (c < C) partial[((size_t)blockIdx.x * 27 + k) * C + c] = sum;
+      }
     }
   }
 }
@@ -938,13 +966,21 @@ int stem3_backward_weight(const float* x, int xc, const float* dz, int N, int H,
   const int blocks = 148 * 4;
   if (ws_bytes < stem3_wgrad_workspace_bytes(C)) { set_error("stem wgrad: workspace too small"); return YB_ERR_INVALID_ARG; }
   const int Ho = H / 2, Wo = W / 2;
-  const size_t smem = (size_t)(ST_PIX * 28 + ST_PIX * C) * sizeof(float);
+  const size_t smem = (size_t)(3 * (2 * ST_PIX + 1) * 4 + std::max(ST_PIX * C, 8 * 27 * 32)) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    YB_CUDA_CHECK(cudaFuncSetAttribute(stem3_wgrad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    YB_CUDA_CHECK(cudaFuncSetAttribute(stem3_wgrad_partial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    YB_CUDA_CHECK(cudaFuncSetAttribute(stem3_wgrad_partial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    YB_CUDA_CHECK(cudaFuncSetAttribute(stem3_wgrad_partial_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    YB_CUDA_CHECK(cudaFuncSetAttribute(stem3_wgrad_partial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
-  stem3_wgrad_partial_kernel<<<blocks, 256, smem, s>>>(x, xc, dz, ws, N, H, W, Ho, Wo, C);
+  switch ((C + 31) / 32) {
+    case 1: stem3_wgrad_partial_kernel<1><<<blocks, 256, smem, s>>>(x, xc, dz, ws, N, H, W, Ho, Wo, C); break;
+    case 2: stem3_wgrad_partial_kernel<2><<<blocks, 256, smem, s>>>(x, xc, dz, ws, N, H, W, Ho, Wo, C); break;
+    case 3: stem3_wgrad_partial_kernel<3><<<blocks, 256, smem, s>>>(x, xc, dz, ws, N, H, W, Ho, Wo, C); break;
+    default: stem3_wgrad_partial_kernel<4><<<blocks, 256, smem, s>>>(x, xc, dz, ws, N, H, W, Ho, Wo, C); break;
+  }
   stem3_wgrad_fold_kernel<<<(27 * C + 127) / 128, 128, 0, s>>>(ws, blocks, C, dw);
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -373,25 +373,11 @@ __global__ void __launch_bounds__(128) loss_grad_kernel(LossGeom g, const float*
 
 }  // namespace
 
-int detection_loss_launch(const float* boxes, const float* scores, int B, int nc, int reg_max, int H, int W,
-                          const float* targets_host, int n_targets, int topk, float hyp_box, float hyp_cls, float hyp_dfl,
-                          float* loss_items, float* grad_boxes, float* grad_scores, unsigned char* fg_out, int* gt_idx_out,
-                          float* tscore_out, cudaStream_t s) {
-  if (B <= 0 || nc <= 0 || nc >= 4096 || reg_max < 2 || reg_max > 32 || H % 32 || W % 32 || H <= 0 || W <= 0 || topk < 1 ||
-      topk > TOPK_MAX || n_targets < 0) {
-    set_error("yb_detection_loss: unsupported shape (need H, W multiples of 32, 2 <= reg_max <= 32, 1 <= topk <= 16)");
-    return YB_ERR_SHAPE;
-  }
-  LossGeom g;
-  g.B = B; g.nc = nc; g.reg_max = reg_max; g.topk = topk;
-  int a0 = 0;
-  for (int l = 0; l < 3; l++) {
-    const int st = 8 << l;
-    g.lvl_w[l] = W / st; g.lvl_h[l] = H / st; g.lvl_a0[l] = a0; g.lvl_stride[l] = (float)st;
-    a0 += g.lvl_w[l] * g.lvl_h[l];
-  }
-  g.A = a0;
-  // preprocess (Loss.cs:363-389): rows [img, cls, x, y, w, h] (normalised xywh) -> (B, n_max, 5) [cls, xyxy pixels]
+// preprocess (Loss.cs:363-389) on the host: rows [img, cls, x, y, w, h] (normalised xywh) -> (B, n_max, 5) [cls, xyxy pixels],
+// zero rows as padding.  Split from the launch so that a training step can stage its targets BEFORE it queues the forward
+// pass (no host synchronisation in the middle of the step).
+int detection_loss_prepare(const float* targets_host, int n_targets, int B, int nc, int H, int W, std::vector<float>& gts, int* n_max_out) {
+  if (B <= 0 || n_targets < 0 || (n_targets > 0 && !targets_host)) { set_error("yb_detection_loss: bad targets"); return YB_ERR_INVALID_ARG; }
   std::vector<int> count(B, 0);
   for (int i = 0; i < n_targets; i++) {
     const int bi = (int)targets_host[(size_t)i * 6];
@@ -408,25 +394,47 @@ int detection_loss_launch(const float* boxes, const float* scores, int B, int nc
   }
   int n_max = 0;
   for (int b = 0; b < B; b++) n_max = std::max(n_max, count[b]);
-  g.n_max = std::max(n_max, 1);  // an all-padding row keeps the kernels uniform when there are no targets
-  std::vector<float> gts((size_t)B * g.n_max * 5, 0.f);
+  n_max = std::max(n_max, 1);  // an all-padding row keeps the kernels uniform when there are no targets
+  gts.assign((size_t)B * n_max * 5, 0.f);
   std::fill(count.begin(), count.end(), 0);
   for (int i = 0; i < n_targets; i++) {
     const float* t = targets_host + (size_t)i * 6;
     const int bi = (int)t[0];
-    float* o = gts.data() + ((size_t)bi * g.n_max + count[bi]++) * 5;
+    float* o = gts.data() + ((size_t)bi * n_max + count[bi]++) * 5;
     const float x = t[2] * (float)W, y = t[3] * (float)H, w = t[4] * (float)W, h = t[5] * (float)H;  // imgsz[[1,0,1,0]]
     o[0] = t[1];
     o[1] = x - w / 2; o[2] = y - h / 2; o[3] = x + w / 2; o[4] = y + h / 2;  // xywh2xyxy, Ops.cs:68-81
   }
+  *n_max_out = n_max;
+  return YB_OK;
+}
+
+// the device part: d_gts (B, n_max, 5) already on the device (stream-ordered before this call)
+int detection_loss_launch_dev(const float* boxes, const float* scores, int B, int nc, int reg_max, int H, int W, const float* d_gts,
+                              int n_max, int topk, float hyp_box, float hyp_cls, float hyp_dfl, float* loss_items, float* grad_boxes,
+                              float* grad_scores, unsigned char* fg_out, int* gt_idx_out, float* tscore_out, cudaStream_t s) {
+  if (B <= 0 || nc <= 0 || nc >= 4096 || reg_max < 2 || reg_max > 32 || H % 32 || W % 32 || H <= 0 || W <= 0 || topk < 1 ||
+      topk > TOPK_MAX || n_max < 1) {
+    set_error("yb_detection_loss: unsupported shape (need H, W multiples of 32, 2 <= reg_max <= 32, 1 <= topk <= 16)");
+    return YB_ERR_SHAPE;
+  }
+  LossGeom g;
+  g.B = B; g.nc = nc; g.reg_max = reg_max; g.topk = topk;
+  int a0 = 0;
+  for (int l = 0; l < 3; l++) {
+    const int st = 8 << l;
+    g.lvl_w[l] = W / st; g.lvl_h[l] = H / st; g.lvl_a0[l] = a0; g.lvl_stride[l] = (float)st;
+    a0 += g.lvl_w[l] * g.lvl_h[l];
+  }
+  g.A = a0;
+  g.n_max = n_max;
   const size_t nga = (size_t)B * g.n_max * g.A, na = (size_t)B * g.A;
-  // scratch: gts | pbox | ov | am | pos_am | pos_ov | tscore | tss | gt_idx | in_gts | mask_pos | fg
-  const size_t f_count = gts.size() + na * 4 + nga * 2 + (size_t)B * g.n_max * 2 + na + 1;
+  // scratch: pbox | ov | am | pos_am | pos_ov | tscore | tss | gt_idx | in_gts | mask_pos | fg
+  const size_t f_count = na * 4 + nga * 2 + (size_t)B * g.n_max * 2 + na + 1;
   char* scratch = nullptr;
   const size_t bytes = f_count * 4 + na * 4 + nga * 2 + na + 64;
   YB_CUDA_CHECK(cudaMallocAsync((void**)&scratch, bytes, s));
-  float* d_gts = reinterpret_cast<float*>(scratch);
-  float* pbox = d_gts + gts.size();
+  float* pbox = reinterpret_cast<float*>(scratch);
   float* ov = pbox + na * 4;
   float* am = ov + nga;
   float* pos_am = am + nga;
@@ -437,8 +445,6 @@ int detection_loss_launch(const float* boxes, const float* scores, int B, int nc
   unsigned char* in_gts = reinterpret_cast<unsigned char*>(gt_idx + na);
   unsigned char* mask_pos = in_gts + nga;
   unsigned char* fg = mask_pos + nga;
-  YB_CUDA_CHECK(cudaMemcpyAsync(d_gts, gts.data(), gts.size() * 4, cudaMemcpyHostToDevice, s));
-  YB_CUDA_CHECK(cudaStreamSynchronize(s));  // `gts` is a host temporary
   YB_CUDA_CHECK(cudaMemsetAsync(tss, 0, 4, s));
   YB_CUDA_CHECK(cudaMemsetAsync(loss_items, 0, 12, s));
   const dim3 ga((g.A + 255) / 256, B);
@@ -456,6 +462,23 @@ int detection_loss_launch(const float* boxes, const float* scores, int B, int nc
   if (tscore_out) YB_CUDA_CHECK(cudaMemcpyAsync(tscore_out, tscore, na * 4, cudaMemcpyDeviceToDevice, s));
   YB_CUDA_CHECK(cudaFreeAsync(scratch, s));
   return YB_OK;
+}
+
+int detection_loss_launch(const float* boxes, const float* scores, int B, int nc, int reg_max, int H, int W,
+                          const float* targets_host, int n_targets, int topk, float hyp_box, float hyp_cls, float hyp_dfl,
+                          float* loss_items, float* grad_boxes, float* grad_scores, unsigned char* fg_out, int* gt_idx_out,
+                          float* tscore_out, cudaStream_t s) {
+  std::vector<float> gts;
+  int n_max = 0;
+  if (int rc = detection_loss_prepare(targets_host, n_targets, B, nc, H, W, gts, &n_max)) return rc;
+  float* d_gts = nullptr;
+  YB_CUDA_CHECK(cudaMallocAsync((void**)&d_gts, gts.size() * 4, s));
+  YB_CUDA_CHECK(cudaMemcpyAsync(d_gts, gts.data(), gts.size() * 4, cudaMemcpyHostToDevice, s));
+  YB_CUDA_CHECK(cudaStreamSynchronize(s));  // `gts` is a host temporary
+  const int rc = detection_loss_launch_dev(boxes, scores, B, nc, reg_max, H, W, d_gts, n_max, topk, hyp_box, hyp_cls, hyp_dfl, loss_items,
+                                           grad_boxes, grad_scores, fg_out, gt_idx_out, tscore_out, s);
+  cudaFreeAsync(d_gts, s);
+  return rc;
 }
 
 }  // namespace yb

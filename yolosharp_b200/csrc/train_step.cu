@@ -36,6 +36,10 @@ int tf_conv_backward_data(const float* dz, const float* w, int N, int H, int W, 
 struct TfPackDesc { long long off, chunk0; int cout, cin, taps, pad_; };
 long long tf_pack_chunks(int cout, int cin, int taps);
 int tf_pack_all(const float* P, float* WF, float* WB, const TfPackDesc* dev_descs, int nd, long long total_chunks, cudaStream_t s);
+int detection_loss_prepare(const float* targets_host, int n_targets, int B, int nc, int H, int W, std::vector<float>& gts, int* n_max_out);
+int detection_loss_launch_dev(const float* boxes, const float* scores, int B, int nc, int reg_max, int H, int W, const float* d_gts,
+                              int n_max, int topk, float hyp_box, float hyp_cls, float hyp_dfl, float* loss_items, float* grad_boxes,
+                              float* grad_scores, unsigned char* fg_out, int* gt_idx_out, float* tscore_out, cudaStream_t s);
 int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W, int Cin, int Cout, int k, int stride, int pad,
                             float* dw, float* ws, size_t ws_bytes, cudaStream_t s, int x_pitch);
 size_t tf_conv_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride);
@@ -289,6 +293,7 @@ struct Net {
   size_t ws_bytes = 0;
   // tensor-core operand layouts of every dense conv weight, same offsets as P; repacked once per step (tf_pack_all)
   float *WF = nullptr, *WB = nullptr;
+  unsigned* bn_counters = nullptr;  // 64 zeroed tickets of the BatchNorm statistics kernels (they leave them zero; one stream)
   TfPackDesc* pack_descs = nullptr;
   int n_packs = 0;
   long long pack_chunks = 0;
@@ -395,7 +400,7 @@ struct Conv : Module {
                               n.wf(name + ".conv.weight")));
     }
     n.check(bn_silu_train_forward(z.p, z.rows(), cout, cout, n.p(name + ".bn.weight"), n.p(name + ".bn.bias"), 1e-3f, 0.03f, act,
-                                  n.r(name + ".bn.running_mean"), n.r(name + ".bn.running_var"), y.p, y.pitch, mean, invstd, n.s));
+                                  n.r(name + ".bn.running_mean"), n.r(name + ".bn.running_var"), y.p, y.pitch, mean, invstd, n.s, n.bn_counters));
     return y;
   }
   T4 backward(Net& n, T4 dy) override {
@@ -403,7 +408,7 @@ struct Conv : Module {
     T4 dx;
     if (n.rc) return dx;
     n.check(bn_silu_backward(z.p, dy.p, z.rows(), cout, cout, dy.pitch, n.p(name + ".bn.weight"), n.p(name + ".bn.bias"), mean, invstd, act,
-                             dz.p, cout, n.g(name + ".bn.weight"), n.g(name + ".bn.bias"), n.s));
+                             dz.p, cout, n.g(name + ".bn.weight"), n.g(name + ".bn.bias"), n.s, n.bn_counters));
     const float* w = n.p(name + ".conv.weight");
     float* gw = n.g(name + ".conv.weight");
     if (depthwise) {
@@ -758,6 +763,11 @@ struct yb_trainer {
   std::vector<T4> up_in;
   float *boxes = nullptr, *scores = nullptr, *gboxes = nullptr, *gscores = nullptr, *items_dev = nullptr;
   int last_batch = 0;
+  // targets of the step, staged before the forward pass is queued: host rows -> padded (B, n_max, 5) -> pinned -> device
+  std::vector<float> tg_host;
+  float* tg_pinned = nullptr;
+  size_t tg_cap = 0;
+  cudaEvent_t tg_copied = nullptr;
 };
 
 namespace {
@@ -961,6 +971,24 @@ int run_backward(yb_trainer* t, const void* images, int in_dtype, int B, const f
   const int H = n.H, W = n.W;
   T4 x = n.make(B, H, W, 8);
   if (n.rc) return n.rc;
+  // targets first: the host never waits on the stream between here and the end of the backward pass, so the launches of the
+  // whole step queue up behind the running kernels (the loss used to synchronise to hand over a host temporary: the
+  // backward pass then started from an empty queue)
+  int n_max = 0;
+  if (int rc = detection_loss_prepare(targets_host, n_targets, B, n.nc, H, W, t->tg_host, &n_max)) return rc;
+  if (!t->tg_copied && cudaEventCreateWithFlags(&t->tg_copied, cudaEventDisableTiming) != cudaSuccess) { set_error("yb_train_step: cudaEventCreate failed"); return YB_ERR_CUDA; }
+  if (t->tg_pinned && cudaEventSynchronize(t->tg_copied) != cudaSuccess) { set_error("yb_train_step: cudaEventSynchronize failed"); return YB_ERR_CUDA; }
+  if (t->tg_host.size() > t->tg_cap) {
+    if (t->tg_pinned) cudaFreeHost(t->tg_pinned);
+    t->tg_pinned = nullptr;
+    t->tg_cap = std::max<size_t>(t->tg_host.size() * 2, 4096);
+    if (cudaMallocHost((void**)&t->tg_pinned, t->tg_cap * sizeof(float)) != cudaSuccess) { t->tg_cap = 0; set_error("yb_train_step: cudaMallocHost failed"); return YB_ERR_CUDA; }
+  }
+  memcpy(t->tg_pinned, t->tg_host.data(), t->tg_host.size() * sizeof(float));
+  float* d_gts = n.alloc((long long)t->tg_host.size());
+  if (n.rc) return n.rc;
+  if (cudaMemcpyAsync(d_gts, t->tg_pinned, t->tg_host.size() * sizeof(float), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaEventRecord(t->tg_copied, s) != cudaSuccess) { set_error("yb_train_step: target copy failed"); return YB_ERR_CUDA; }
   images_to_nhwc8_kernel<<<nb((long long)B * H * W), 256, 0, s>>>(images, in_dtype == YB_U8 ? 1 : 0, x.p, B, H, W);
   n.check_launch();
   n.check(tf_pack_all(n.P, n.WF, n.WB, n.pack_descs, n.n_packs, n.pack_chunks, s));  // the weights as this step sees them
@@ -1008,8 +1036,8 @@ int run_backward(yb_trainer* t, const void* images, int in_dtype, int B, const f
   t->detect->forward(n, feats, t->boxes, t->scores, A);
   if (n.rc) return n.rc;
   // ---- loss (Loss.cs:328-485) and its gradient w.r.t. the head outputs ----
-  n.check(detection_loss_launch(t->boxes, t->scores, B, n.nc, 16, H, W, targets_host, n_targets, 10, 7.5f, 0.5f, 1.5f, t->items_dev,
-                                t->gboxes, t->gscores, fg, gt_idx, tsc, s));
+  n.check(detection_loss_launch_dev(t->boxes, t->scores, B, n.nc, 16, H, W, d_gts, n_max, 10, 7.5f, 0.5f, 1.5f, t->items_dev,
+                                    t->gboxes, t->gscores, fg, gt_idx, tsc, s));
   if (n.rc) return n.rc;
   // ---- backward through the graph ----
   if (cudaMemsetAsync(n.G, 0, (size_t)n.n_params * sizeof(float), s) != cudaSuccess) { set_error("yb_train_step: memset failed"); return YB_ERR_CUDA; }
@@ -1124,6 +1152,7 @@ int32_t yb_trainer_create(const yb_config* cfg, yb_trainer** out) {
     const size_t wbytes = (size_t)n.n_params * sizeof(float);
     if (cudaMalloc((void**)&n.WF, wbytes) != cudaSuccess || cudaMalloc((void**)&n.WB, wbytes) != cudaSuccess ||
         cudaMalloc((void**)&n.pack_descs, std::max<size_t>(1, d.size()) * sizeof(TfPackDesc)) != cudaSuccess ||
+        cudaMalloc((void**)&n.bn_counters, 64 * sizeof(unsigned)) != cudaSuccess || cudaMemset(n.bn_counters, 0, 64 * sizeof(unsigned)) != cudaSuccess ||
         cudaMemcpy(n.pack_descs, d.data(), d.size() * sizeof(TfPackDesc), cudaMemcpyHostToDevice) != cudaSuccess) {
       set_error("yb_trainer_create: cudaMalloc of the packed weight buffers failed");
       cudaGetLastError();
@@ -1142,6 +1171,9 @@ void yb_trainer_destroy(yb_trainer* t) {
   if (t->net.WF) cudaFree(t->net.WF);
   if (t->net.WB) cudaFree(t->net.WB);
   if (t->net.pack_descs) cudaFree(t->net.pack_descs);
+  if (t->net.bn_counters) cudaFree(t->net.bn_counters);
+  if (t->tg_pinned) cudaFreeHost(t->tg_pinned);
+  if (t->tg_copied) cudaEventDestroy(t->tg_copied);
   delete t;
 }
 
