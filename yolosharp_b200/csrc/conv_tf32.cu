@@ -486,6 +486,7 @@ struct WgArgs {
   int tpc, tap_groups;  // taps per CTA (3 = one kh row of a 3x3, 1 for 1x1) and groups of them
   int imgs, tiles_w, tiles_h, pix_tiles;
   int b_stages;
+  int merge_kw;     // halo mode with one 32-channel input block: the three kw taps of a row as ONE N = 96 MMA
   int halo;         // 3x3 stride 1: ONE PH x (PW+2) input tile per pixel tile serves the three taps of a kh row (row-shifted windows)
   uint32_t xblk;    // bytes reserved per 32-channel block of an x stage (1 KiB aligned)
   int co_pad, ci_pad;
@@ -593,12 +594,23 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
           mbar_wait(bfull + 8 * sb, pb);
           tc_fence_after();
           const uint32_t B0 = smemB + sb * b_stride;
-          for (int kw = 0; kw < 3; kw++) {
-            const uint32_t d_tmem = tmem_base + kw * ncols;
+          if (a.merge_kw) {
+            // one 32-channel input block: the three kw windows are the SAME box shifted by one pixel row (128 bytes), so they
+            // are three N blocks of one MMA with a block stride (LBO) of 128 bytes - N = 96 instead of three N = 32 MMAs
+            // (a TF32 M = 128 MMA costs ~100 cycles whatever its N: the Cin <= 32 layers at 160 x 160 were MMA-issue bound)
+            const uint32_t idesc3 = (idesc & ~(0x3fu << 17)) | ((uint32_t)(96 >> 3) << 17);
 #pragma unroll
-            for (int ks = 0; ks < WG_PH; ks++)  // output row ks: its 8 input pixels start at row ks * (PW + 2) + kw of the box
-              umma_tf32(d_tmem, tf_desc(A0 + ks * 1024, lbo16, sbo16, 1),
-                        tf_desc(B0 + (uint32_t)(ks * (WG_PW + 2) + kw) * 128, xlbo16, sbo16, 1), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < WG_PH; ks++)
+              umma_tf32(tmem_base, tf_desc(A0 + ks * 1024, lbo16, sbo16, 1),
+                        tf_desc(B0 + (uint32_t)(ks * (WG_PW + 2)) * 128, 128 >> 4, sbo16, 1), idesc3, (i > 0 || ks > 0) ? 1u : 0u);
+          } else {
+            for (int kw = 0; kw < 3; kw++) {
+              const uint32_t d_tmem = tmem_base + kw * ncols;
+#pragma unroll
+              for (int ks = 0; ks < WG_PH; ks++)  // output row ks: its 8 input pixels start at row ks * (PW + 2) + kw of the box
+                umma_tf32(d_tmem, tf_desc(A0 + ks * 1024, lbo16, sbo16, 1),
+                          tf_desc(B0 + (uint32_t)(ks * (WG_PW + 2) + kw) * 128, xlbo16, sbo16, 1), idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            }
           }
           umma_commit(bempty + 8 * sb);
           if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
@@ -750,6 +762,8 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
   // of conv_tc.cu does for the 16-byte-atom modes; tests/test_gpu_conv_tc.py's bit-exact case covers it.
   static const bool no_halo = getenv("YB_WGRAD_NO_HALO") != nullptr;
   a.halo = (k == 3 && stride == 1 && !no_halo) ? 1 : 0;
+  static const bool no_merge = getenv("YB_WGRAD_NO_MERGE") != nullptr;
+  a.merge_kw = (a.halo && p.nb == 1 && !no_merge) ? 1 : 0;
   a.xblk = a.halo ? (uint32_t)(((WG_PW + 2) * WG_PH * 128 + 1023) / 1024 * 1024) : (uint32_t)WG_BLK;
   const size_t b_stride = (size_t)p.nb * a.xblk;
   a.b_stages = (int)std::min<size_t>(16, ((size_t)190 * 1024 - (size_t)WG_A_STAGES * 4 * WG_BLK) / b_stride);
