@@ -254,8 +254,12 @@ int32_t yb_stem_conv_backward_weight_f32(const float* x, int32_t x_channels, con
  *   yb_trainer_bind     the caller owns the flat fp32 device buffers (parameters, gradients, Adam m / v, running stats):
  *                       a TorchSharp / PyTorch host wraps them as tensors, loads a checkpoint into them, reads gradients
  *                       and all-reduces the gradient buffer between yb_train_backward and yb_train_apply (DDP)
- *   yb_train_backward   images dev (B, 3, H, W) u8 (divided by 255 as Detector.cs:41) or f32; targets HOST float32
- *                       (n, 6) rows [image, class, x, y, w, h] normalised; loss_items HOST float[3] or NULL
+ *   yb_train_backward   images dev (B, 3, H, W) u8 (scaled by 1/255 as the training loader does, Data/YoloDataset.cs:140) or
+ *                       f32; targets HOST float32 (n, 6) rows [image, class, x, y, w, h] normalised, staged to the device
+ *                       before the forward pass is queued (the call does not synchronise until the end); loss_items HOST
+ *                       float[3] (the call then returns after the stream has finished) or NULL (fully asynchronous).
+ *                       A trainer is driven from ONE stream at a time (its activation arena, packed-weight buffers and
+ *                       BatchNorm ticket counters belong to the step in flight).
  *   yb_train_apply      one AdamW step (betas 0.9 / 0.999, eps 1e-8) with the two group learning rates
  *   yb_train_step       = yb_train_backward + yb_train_apply (single device)
  *   yb_get_grad / yb_get_tensor  copy one named gradient / parameter / running statistic to the host */
@@ -364,9 +368,29 @@ int32_t yb_nms_rotated(const float* boxes, const float* scores, int32_t n, float
  *   iou_thresholds_host  the reference's linspace(0.5, 0.95, 10) as float32 (HOST pointer)
  *   correct  dev uint8 (B, max_det, n_thresholds): 1 where detection d is a true positive at threshold i */
 int32_t yb_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, float eps, float* out, void* stream);
+
 int32_t yb_match_predictions(const float* dets, const int32_t* counts, int32_t batch, int32_t max_det, int32_t row_width,
                              const float* labels, int32_t n_labels, const float* iou_thresholds_host, int32_t n_thresholds,
                              uint8_t* correct, void* stream);
+
+/* Replaces `Metrics.ap_per_class(tp, conf, pred_cls, target_cls)` (Utils/Metrics.cs:308-384, with compute_ap :395-421,
+ * interp :424-468 and smooth :475-487), the reduction `Detector.Val` runs over ALL detections of a validation pass
+ * (csrc/metrics.cu).  Where the reference's three unstable `torch.argsort` calls meet equal keys its result is unspecified;
+ * this entry point uses the stable order (ties keep their input order).
+ *   tp  dev uint8 (n, n_thresholds) as yb_match_predictions writes it (rows of real detections only), conf dev float32 (n),
+ *   pred_cls dev int32 (n), target_cls dev int32 (m), classes in [0, max_classes), max_classes <= 4096
+ *   unique_classes dev int32 (max_classes): the classes that have labels, ascending (the reference's torch.unique)
+ *   counts_host  HOST int32[3]: number of unique classes nc, rows of prec_values (classes with labels AND predictions),
+ *                index of the best smoothed-F1 point
+ *   ap dev (max_classes, n_thresholds); p_curve / r_curve / f1_curve / prec_values dev (max_classes, 1000);
+ *   p, r, f1, tp_out, fp_out dev (max_classes): rows [0, nc) are written as the reference returns them.
+ * The call synchronises the stream (it returns counts).
+ * yb_linspace01  torch.linspace(0, 1, steps) as ATen computes it (the `x` axis the reference also returns), HOST output. */
+int32_t yb_ap_per_class(const uint8_t* tp, const float* conf, const int32_t* pred_cls, int32_t n, int32_t n_thresholds,
+                        const int32_t* target_cls, int32_t m, int32_t max_classes, int32_t* unique_classes, int32_t* counts_host,
+                        float* ap, float* p_curve, float* r_curve, float* f1_curve, float* prec_values, float* p, float* r, float* f1,
+                        float* tp_out, float* fp_out, void* stream);
+int32_t yb_linspace01(int32_t steps, float* out_host);
 
 /* ---- multi-GPU: exchange of the fixed-capacity detection payloads over NVLink peer memory (csrc/comm.cu) ----
  * Design target SURVEY.md section 8(e); the reference is single-device (Data/Config.cs:301), so this surface is

@@ -54,6 +54,9 @@ SIGNATURES = {
     "yb_nms_rotated": (c_i32, [c_vp, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp]),
     "yb_box_iou": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp]),
     "yb_match_predictions": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
+    "yb_linspace01": (c_i32, [c_i32, c_vp]),
+    "yb_ap_per_class": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                c_vp, c_vp, c_vp, c_vp]),
     "yb_masks": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "yb_detection_loss": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_f32, c_f32, c_f32,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

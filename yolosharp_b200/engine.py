@@ -304,6 +304,34 @@ def match_predictions(dets, counts, labels, iouv=None, stream=None):
     return correct
 
 
+def ap_per_class(tp, conf, pred_cls, target_cls, max_classes=80, stream=None):
+    """yb_ap_per_class (Utils/Metrics.cs:308-384): tp (n, T) uint8 / bool, conf (n,), pred_cls (n,), target_cls (m,) on the
+    device -> dict with the reference's outputs (tp, fp, p, r, f1, ap, unique_classes, p_curve, r_curve, f1_curve, x,
+    prec_values) plus `best`, the index of the smoothed-F1 maximum."""
+    dev = conf.device
+    assert conf.is_cuda
+    n, T = tp.shape[0], tp.shape[1]
+    tp8 = tp.to(torch.uint8).contiguous()
+    conf = conf.float().contiguous()
+    pc = pred_cls.to(torch.int32).contiguous()
+    tc = target_cls.to(device=dev, dtype=torch.int32).contiguous()
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    uniq = torch.empty(max_classes, dtype=torch.int32, device=dev)
+    counts = torch.zeros(3, dtype=torch.int32)
+    ap, pcv, rcv, f1c, pv = f(max_classes, T), f(max_classes, 1000), f(max_classes, 1000), f(max_classes, 1000), f(max_classes, 1000)
+    p, r, f1, tpo, fpo = (f(max_classes) for _ in range(5))
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t.numel() else None
+    L.check(L.lib().yb_ap_per_class(ptr(tp8), ptr(conf), ptr(pc), n, T, ptr(tc), tc.numel(), max_classes, ptr(uniq), C.c_void_p(counts.data_ptr()),
+                                    ptr(ap), ptr(pcv), ptr(rcv), ptr(f1c), ptr(pv), ptr(p), ptr(r), ptr(f1), ptr(tpo), ptr(fpo),
+                                    _stream_ptr(stream)))
+    nc, n_prec, best = (int(v) for v in counts)
+    x = torch.empty(1000, dtype=torch.float32)
+    L.check(L.lib().yb_linspace01(1000, C.c_void_p(x.data_ptr())))
+    prec_values = pv[:n_prec] if n_prec else torch.zeros((1, 1000), dtype=torch.float32, device=dev)
+    return {"tp": tpo[:nc], "fp": fpo[:nc], "p": p[:nc], "r": r[:nc], "f1": f1[:nc], "ap": ap[:nc], "unique_classes": uniq[:nc],
+            "p_curve": pcv[:nc], "r_curve": rcv[:nc], "f1_curve": f1c[:nc], "x": x, "prec_values": prec_values, "best": best}
+
+
 def detection_loss(boxes, scores, targets, height, width, reg_max=16, topk=10, hyp_box=7.5, hyp_cls=0.5, hyp_dfl=1.5,
                    want_grad=True, stream=None):
     """yb_detection_loss: v8DetectionLoss (Utils/Loss.cs:328-485) on the raw train-mode head outputs.
