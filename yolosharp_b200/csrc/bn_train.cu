@@ -156,6 +156,8 @@ constexpr int BN4_U_FWD = 8, BN4_U_BWD = 4;  // rows per batch: 8 x 16 B (forwar
 
 template <int MODE>  // 3: forward shifted sums (S1, S2 about K = z[row 0]); 2: backward sums (sum g, sum g * xhat)
 __global__ void __launch_bounds__(256) bn_stats4_kernel(const BnStat a) {
+  pdl_trigger();
+  pdl_wait();
   const int LX = blockDim.x, LY = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
   const int c = (blockIdx.x * LX + tx) * 4;
   const bool on = c < a.C;
@@ -364,6 +366,8 @@ __global__ void bn_silu_dz_kernel(const float* __restrict__ z, const float* __re
 __global__ void bn_silu_apply4_kernel(const float* __restrict__ z, int total4, int C4, int pitch, int opitch,
                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, int act, float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int r = i / C4, c = (i - r * C4) * 4;
@@ -381,6 +385,8 @@ __global__ void bn_silu_dz4_kernel(const float* __restrict__ z, const float* __r
                                    int opitch, float inv_m, const float* __restrict__ mean, const float* __restrict__ invstd,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dz) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int r = i / C4, c = (i - r * C4) * 4;
@@ -420,7 +426,7 @@ int bn_silu_train_forward(const float* z, long long M, int C, int pitch, const f
     a.p0 = part; a.p1 = part + (size_t)pl.slabs * C; a.counter = own ? reinterpret_cast<unsigned*>(part + nf) : counters;
     a.eps = eps; a.momentum = momentum; a.o_mean = save_mean; a.o_invstd = save_invstd;
     a.running_mean = running_mean; a.running_var = running_var;
-    bn_stats4_kernel<3><<<dim3(pl.colblocks, pl.slabs), dim3(pl.LX, pl.LY), 0, s>>>(a);
+    YB_CUDA_CHECK(launch_pdl(bn_stats4_kernel<3>, dim3(pl.colblocks, pl.slabs), dim3(pl.LX, pl.LY), 0, s, a));
   } else {
     const int rpb = bn_rows_per_block(M);
     const int slabs = (int)((M + rpb - 1) / rpb);
@@ -438,8 +444,8 @@ int bn_silu_train_forward(const float* z, long long M, int C, int pitch, const f
   if (C % 4 == 0 && pitch % 4 == 0 && ypitch % 4 == 0 && total / 4 < (1ll << 31) && ((uintptr_t)z % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
       aligned16(save_mean, save_invstd, gamma, beta)) {
     const int total4 = (int)(total / 4);
-    bn_silu_apply4_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(z, total4, C / 4, pitch, ypitch, save_mean, save_invstd, gamma,
-                                                                          beta, act, y);
+    YB_CUDA_CHECK(launch_pdl(bn_silu_apply4_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, s, z, total4, C / 4, pitch, ypitch,
+                             save_mean, save_invstd, gamma, beta, act, y));
   } else {
     bn_silu_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, M, C, pitch, ypitch, save_mean, save_invstd, gamma, beta, act, y);
   }
@@ -467,7 +473,7 @@ int bn_silu_backward(const float* z, const float* dy, long long M, int C, int pi
     a.mean = save_mean; a.invstd = save_invstd; a.gamma = gamma; a.beta = beta;
     a.p0 = part; a.p1 = part + (size_t)pl.slabs * C; a.counter = own ? reinterpret_cast<unsigned*>(part + nf) : counters;
     a.dgamma = dgamma; a.dbeta = dbeta;
-    bn_stats4_kernel<2><<<dim3(pl.colblocks, pl.slabs), dim3(pl.LX, pl.LY), 0, s>>>(a);
+    YB_CUDA_CHECK(launch_pdl(bn_stats4_kernel<2>, dim3(pl.colblocks, pl.slabs), dim3(pl.LX, pl.LY), 0, s, a));
   } else {
     const int rpb = bn_rows_per_block(M);
     const int slabs = (int)((M + rpb - 1) / rpb);
@@ -482,8 +488,8 @@ int bn_silu_backward(const float* z, const float* dy, long long M, int C, int pi
   if (C % 4 == 0 && pitch % 4 == 0 && dpitch % 4 == 0 && zpitch % 4 == 0 && total / 4 < (1ll << 31) && ((uintptr_t)z % 16 == 0) &&
       ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dz % 16 == 0)) {
     const int total4 = (int)(total / 4);
-    bn_silu_dz4_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, s>>>(z, dy, total4, C / 4, pitch, dpitch, zpitch, 1.f / (float)M, save_mean,
-                                                                       save_invstd, gamma, beta, act, dgamma, dbeta, dz);
+    YB_CUDA_CHECK(launch_pdl(bn_silu_dz4_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, s, z, dy, total4, C / 4, pitch, dpitch,
+                             zpitch, 1.f / (float)M, save_mean, save_invstd, gamma, beta, act, dgamma, dbeta, dz));
   } else {
     bn_silu_dz_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, dy, M, C, pitch, dpitch, zpitch, save_mean, save_invstd, gamma, beta,
                                                                   act, dgamma, dbeta, dz);

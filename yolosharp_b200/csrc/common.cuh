@@ -60,6 +60,34 @@ void set_error(const std::string& msg);
     }                                                                                        \
   } while (0)
 
+// ---- programmatic dependent launch for the kernels of the training step ----
+// A kernel launched through launch_pdl may be scheduled while its predecessor in the stream is still running: its CTAs
+// become resident as the predecessor's retire, run their prologue (parameter loads, barrier / TMEM setup, descriptor
+// prefetch) and block in pdl_wait() until the predecessor has completed and its writes are visible.  Every such kernel
+// calls pdl_trigger() first (lets ITS successor be scheduled once all of its own CTAs have started) and pdl_wait() before
+// its first global-memory access.  A dependent step of ~800 small kernels otherwise pays ~1.8 us of drain + launch + fill
+// per boundary (profiles/r2_train_profile_v11s_native.txt: 16.8 ms of kernels in an 18.2 ms step).
+// Both instructions are no-ops in a kernel launched the ordinary way, so a kernel may be launched either way.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();  // false when YB_NO_PDL is set (A/B measurements)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(static_cast<Args&&>(args))...);
+}
+#endif
+
 // ---- kernels_generic.cu : CUDA-core kernels, templated on storage type (float | __half) ----
 template <typename T>
 int launch_conv_generic(const ConvParams& p, cudaStream_t s);

@@ -102,6 +102,7 @@ struct TfArgs {
 };
 
 __global__ void __launch_bounds__(TF_THREADS, 2) tf_conv_kernel(const __grid_constant__ TfArgs a) {
+  pdl_trigger();  // the barrier / TMEM setup below overlaps the tail of the previous kernel (launch_pdl); pdl_wait() before any global access
   extern __shared__ __align__(1024) uint8_t tf_smem[];
   __shared__ __align__(8) uint64_t bars[2 * TF_MAX_STAGES + 4];
   __shared__ uint32_t tmem_slot;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(TF_THREADS, 2) tf_conv_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = tmem_slot;
   const int tiles_per_img = a.tiles_w * a.tiles_h;
   const int ksteps = a.ntaps * a.chunks;
@@ -384,8 +386,7 @@ static int tf_conv_launch(const TfLaunch& L, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = std::min(a.total_tiles, occ * tf_num_sms());
-  tf_conv_kernel<<<grid, TF_THREADS, smem, s>>>(a);
-  YB_CUDA_CHECK(cudaGetLastError());
+  YB_CUDA_CHECK(launch_pdl(tf_conv_kernel, dim3(grid), dim3(TF_THREADS), smem, s, a));
   return 0;
 }
 
@@ -494,6 +495,7 @@ struct WgArgs {
 };
 
 __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_constant__ WgArgs a) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t wg_smem[];
   __shared__ __align__(8) uint64_t bars[2 * WG_A_STAGES + 2 * 16 + 1];
   __shared__ uint32_t tmem_slot;
@@ -523,6 +525,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = tmem_slot;
 
   // CTA -> (output-channel tile, input-channel tile, pixel split)
@@ -676,6 +679,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
 // step; reads coalesced over ci with scattered writes: 1.13 ms.)
 __global__ void __launch_bounds__(256) tf_wgrad_fold_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cout, int Cin,
                                                             int taps, int splits, int co_pad, int ci_pad) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float fold_sm[];  // [Cin][taps]
   const int co = blockIdx.x;
   const size_t ss = (size_t)co_pad * taps * ci_pad;
@@ -796,8 +801,7 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
   }
   const size_t smem = (size_t)WG_A_STAGES * 4 * WG_BLK + (size_t)a.b_stages * b_stride + 1024;
   const int grid = p.co_tiles * p.ci_tiles * p.tap_groups * p.splits;
-  tf_wgrad_kernel<<<grid, TF_THREADS, smem, s>>>(a);
-  YB_CUDA_CHECK(cudaGetLastError());
+  YB_CUDA_CHECK(launch_pdl(tf_wgrad_kernel, dim3(grid), dim3(TF_THREADS), smem, s, a));
   const size_t n = (size_t)Cout * Cin * k * k;
   static bool fold_attr = false;
   if (!fold_attr) {
@@ -805,7 +809,8 @@ int tf_conv_backward_weight(const float* x, const float* dz, int N, int H, int W
     fold_attr = true;
   }
   if ((size_t)Cin * k * k * sizeof(float) > (size_t)160 * 1024) { set_error("tf32 wgrad: Cin * k * k too large for the fold"); return YB_ERR_SHAPE; }
-  tf_wgrad_fold_kernel<<<Cout, 256, (size_t)Cin * k * k * sizeof(float), s>>>(ws, dw, Cout, Cin, k * k, p.splits, p.co_pad, p.ci_pad);
+  YB_CUDA_CHECK(launch_pdl(tf_wgrad_fold_kernel, dim3(Cout), dim3(256), (size_t)Cin * k * k * sizeof(float), s, (const float*)ws, dw, Cout, Cin, k * k,
+                           p.splits, p.co_pad, p.ci_pad));
   (void)n;
   YB_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -28,6 +28,10 @@ extern int g_tc_dbg_countdown;
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+bool pdl_enabled() {
+  static const bool on = getenv("YB_NO_PDL") == nullptr;
+  return on;
+}
 
 struct VRef {  // view reference: buffer id + channel slice
   int buf = -1, coff = 0, C = 0;

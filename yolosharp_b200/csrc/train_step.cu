@@ -83,6 +83,8 @@ __global__ void add_kernel(float* __restrict__ out, int opitch, const float* __r
 // kernels above pay a 64-bit division per element
 __global__ void slice_copy4_kernel(float* __restrict__ dst, int dpitch, const float* __restrict__ src, int spitch, int total4, int C4,
                                    int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int r = i / C4, c = (i - r * C4) * 4;
@@ -93,6 +95,8 @@ __global__ void slice_copy4_kernel(float* __restrict__ dst, int dpitch, const fl
 }
 __global__ void add4_kernel(float* __restrict__ out, int opitch, const float* __restrict__ a, int apitch, const float* __restrict__ b,
                             int bpitch, int total4, int C4) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int r = i / C4, c = (i - r * C4) * 4;
@@ -328,8 +332,8 @@ static bool vec4_ok(long long numel, int C, const void* p0, int pitch0, const vo
 static void put(Net& n, const T4& dst, int c0, const T4& src, bool accumulate = false) {  // dst[..., c0 : c0 + src.C] (+)= src
   if (n.rc) return;
   if (vec4_ok(src.numel(), src.C, dst.p + c0, dst.pitch, src.p, src.pitch, src.p, src.pitch))
-    slice_copy4_kernel<<<nb(src.numel() / 4), 256, 0, n.s>>>(dst.p + c0, dst.pitch, src.p, src.pitch, (int)(src.numel() / 4), src.C / 4,
-                                                            accumulate ? 1 : 0);
+    n.check(launch_pdl(slice_copy4_kernel, dim3(nb(src.numel() / 4)), dim3(256), 0, n.s, dst.p + c0, dst.pitch, (const float*)src.p, src.pitch,
+                       (int)(src.numel() / 4), src.C / 4, accumulate ? 1 : 0) == cudaSuccess ? 0 : YB_ERR_CUDA);
   else
     slice_copy_kernel<<<nb(src.numel()), 256, 0, n.s>>>(dst.p, dst.pitch, c0, src.p, src.pitch, 0, src.rows(), src.C, accumulate ? 1 : 0);
   n.check_launch();
@@ -343,7 +347,8 @@ static T4 dense_copy(Net& n, const T4& x) {  // contiguous copy of a view (kerne
 static void add_into(Net& n, const T4& out, const T4& a, const T4& b) {
   if (n.rc) return;
   if (vec4_ok(a.numel(), a.C, out.p, out.pitch, a.p, a.pitch, b.p, b.pitch))
-    add4_kernel<<<nb(a.numel() / 4), 256, 0, n.s>>>(out.p, out.pitch, a.p, a.pitch, b.p, b.pitch, (int)(a.numel() / 4), a.C / 4);
+    n.check(launch_pdl(add4_kernel, dim3(nb(a.numel() / 4)), dim3(256), 0, n.s, out.p, out.pitch, (const float*)a.p, a.pitch, (const float*)b.p,
+                       b.pitch, (int)(a.numel() / 4), a.C / 4) == cudaSuccess ? 0 : YB_ERR_CUDA);
   else
     add_kernel<<<nb(a.numel()), 256, 0, n.s>>>(out.p, out.pitch, a.p, a.pitch, b.p, b.pitch, a.rows(), a.C);
   n.check_launch();
