@@ -156,8 +156,8 @@ constexpr int BN4_U_FWD = 8, BN4_U_BWD = 4;  // rows per batch: 8 x 16 B (forwar
 
 template <int MODE>  // 3: forward shifted sums (S1, S2 about K = z[row 0]); 2: backward sums (sum g, sum g * xhat)
 __global__ void __launch_bounds__(256) bn_stats4_kernel(const BnStat a) {
-  pdl_trigger();
   pdl_wait();
+  pdl_trigger();
   const int LX = blockDim.x, LY = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
   const int c = (blockIdx.x * LX + tx) * 4;
   const bool on = c < a.C;
@@ -366,8 +366,8 @@ __global__ void bn_silu_dz_kernel(const float* __restrict__ z, const float* __re
 __global__ void bn_silu_apply4_kernel(const float* __restrict__ z, int total4, int C4, int pitch, int opitch,
                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                       const float* __restrict__ gamma, const float* __restrict__ beta, int act, float* __restrict__ y) {
-  pdl_trigger();
   pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int r = i / C4, c = (i - r * C4) * 4;
@@ -385,8 +385,8 @@ __global__ void bn_silu_dz4_kernel(const float* __restrict__ z, const float* __r
                                    int opitch, float inv_m, const float* __restrict__ mean, const float* __restrict__ invstd,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dz) {
-  pdl_trigger();
   pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int r = i / C4, c = (i - r * C4) * 4;

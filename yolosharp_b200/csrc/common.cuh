@@ -64,9 +64,12 @@ void set_error(const std::string& msg);
 // A kernel launched through launch_pdl may be scheduled while its predecessor in the stream is still running: its CTAs
 // become resident as the predecessor's retire, run their prologue (parameter loads, barrier / TMEM setup, descriptor
 // prefetch) and block in pdl_wait() until the predecessor has completed and its writes are visible.  Every such kernel
-// calls pdl_trigger() first (lets ITS successor be scheduled once all of its own CTAs have started) and pdl_wait() before
-// its first global-memory access.  A dependent step of ~800 small kernels otherwise pays ~1.8 us of drain + launch + fill
-// per boundary (profiles/r2_train_profile_v11s_native.txt: 16.8 ms of kernels in an 18.2 ms step).
+// calls pdl_wait() before its first global-memory access and pdl_trigger() right AFTER it: the successor can be scheduled
+// once all CTAs of this kernel have passed their wait, so at most two kernels of the chain are ever in flight (this one
+// finishing, the next one in its prologue).  (Triggering before the wait lets a whole chain of small kernels become
+// resident at once; with that form a seven-kernel loss chain read a scalar before its producer's atomics - not understood,
+// so the conservative order is used everywhere.)  A dependent step of ~800 small kernels otherwise pays ~1.8 us of drain +
+// launch + fill per boundary (profiles/r2_train_profile_v11s_native.txt: 16.8 ms of kernels in an 18.2 ms step).
 // Both instructions are no-ops in a kernel launched the ordinary way, so a kernel may be launched either way.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -102,7 +102,7 @@ struct TfArgs {
 };
 
 __global__ void __launch_bounds__(TF_THREADS, 2) tf_conv_kernel(const __grid_constant__ TfArgs a) {
-  pdl_trigger();  // the barrier / TMEM setup below overlaps the tail of the previous kernel (launch_pdl); pdl_wait() before any global access
+  // the barrier / TMEM setup below overlaps the tail of the previous kernel (launch_pdl); pdl_wait() before any global access
   extern __shared__ __align__(1024) uint8_t tf_smem[];
   __shared__ __align__(8) uint64_t bars[2 * TF_MAX_STAGES + 4];
   __shared__ uint32_t tmem_slot;
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(TF_THREADS, 2) tf_conv_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_base = tmem_slot;
   const int tiles_per_img = a.tiles_w * a.tiles_h;
   const int ksteps = a.ntaps * a.chunks;
@@ -495,7 +496,6 @@ struct WgArgs {
 };
 
 __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_constant__ WgArgs a) {
-  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t wg_smem[];
   __shared__ __align__(8) uint64_t bars[2 * WG_A_STAGES + 2 * 16 + 1];
   __shared__ uint32_t tmem_slot;
@@ -526,6 +526,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_base = tmem_slot;
 
   // CTA -> (output-channel tile, input-channel tile, pixel split)
@@ -679,8 +680,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tf_wgrad_kernel(const __grid_co
 // step; reads coalesced over ci with scattered writes: 1.13 ms.)
 __global__ void __launch_bounds__(256) tf_wgrad_fold_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cout, int Cin,
                                                             int taps, int splits, int co_pad, int ci_pad) {
-  pdl_trigger();
   pdl_wait();
+  pdl_trigger();
   extern __shared__ float fold_sm[];  // [Cin][taps]
   const int co = blockIdx.x;
   const size_t ss = (size_t)co_pad * taps * ci_pad;

@@ -83,8 +83,8 @@ __global__ void add_kernel(float* __restrict__ out, int opitch, const float* __r
 // kernels above pay a 64-bit division per element
 __global__ void slice_copy4_kernel(float* __restrict__ dst, int dpitch, const float* __restrict__ src, int spitch, int total4, int C4,
                                    int accumulate) {
-  pdl_trigger();
   pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int r = i / C4, c = (i - r * C4) * 4;
@@ -95,8 +95,8 @@ __global__ void slice_copy4_kernel(float* __restrict__ dst, int dpitch, const fl
 }
 __global__ void add4_kernel(float* __restrict__ out, int opitch, const float* __restrict__ a, int apitch, const float* __restrict__ b,
                             int bpitch, int total4, int C4) {
-  pdl_trigger();
   pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int r = i / C4, c = (i - r * C4) * 4;
