@@ -17,4 +17,4 @@ print(json.dumps({"model": sys.argv[2], "batch": int(sys.argv[3]), "launches": l
                   "dram_bytes_per_step": tot["dram__bytes_read.sum"] + tot["dram__bytes_write.sum"],
                   "dram_read": tot["dram__bytes_read.sum"], "dram_write": tot["dram__bytes_write.sum"],
                   "kernel_seconds_serialised": tot["gpu__time_duration.sum"],
-                  "source": "ncu --metrics dram__bytes_{read,write}.sum over the conv_tc_kernel launches of one eager forward (tools/gpurun_scripts/run_final.sh)"}))
+                  "source": "ncu --metrics dram__bytes_{read,write}.sum over the conv_tc_kernel launches of one eager forward (tools/gpurun_scripts/run_traffic.sh)"}))
