@@ -152,10 +152,13 @@ struct BnStat {
   float *o_mean, *o_invstd, *running_mean, *running_var, *dgamma, *dbeta;
 };
 
-constexpr int BN4_U_FWD = 8, BN4_U_BWD = 4;  // rows per batch: 8 x 16 B (forward, z only) / 4 x 2 x 16 B (backward, z and dy) in flight per thread
+// rows per batch: 8 x 16 B (forward, z only) / 2 x 2 x 16 B (backward, z and dy) in flight per thread.  The backward pass
+// is instruction-bound (SiLU' = exp + two divisions per element: ncu issue-active 56 % at 32 % occupancy with an 80-register
+// batch of 4, profiles/r2_ncu_bn_kernels.txt): a batch of 2 fits 64 registers = 4 CTAs per SM
+constexpr int BN4_U_FWD = 8, BN4_U_BWD = 2;
 
 template <int MODE>  // 3: forward shifted sums (S1, S2 about K = z[row 0]); 2: backward sums (sum g, sum g * xhat)
-__global__ void __launch_bounds__(256) bn_stats4_kernel(const BnStat a) {
+__global__ void __launch_bounds__(256, 4) bn_stats4_kernel(const BnStat a) {
   pdl_wait();
   pdl_trigger();
   const int LX = blockDim.x, LY = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
@@ -327,11 +330,6 @@ static Bn4Plan bn4_plan(long long M, int C, int U) {
   p.slabs = (int)((M + rpb - 1) / rpb);
   return p;
 }
-// the elementwise float4 kernels load the per-channel vectors 16 bytes at a time (a caller's flat parameter buffer need not be
-// 16-byte aligned per tensor, e.g. after an nc = 1 bias)
-static bool aligned16(const void* a, const void* b, const void* c, const void* d) {
-  return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
-}
 static bool bn4_ok(long long M, int C, const void* z, int pitch, const void* dy, int dpitch) {
   return C % 4 == 0 && pitch % 4 == 0 && dpitch % 4 == 0 && (uintptr_t)z % 16 == 0 && (uintptr_t)dy % 16 == 0 && M * C / 4 < (1ll << 31);
 }
@@ -361,47 +359,99 @@ __global__ void bn_silu_dz_kernel(const float* __restrict__ z, const float* __re
   dz[r * opitch + c] = gamma[c] * invstd[c] * (g - dbeta[c] * inv_m - xh * dgamma[c] * inv_m);
 }
 
-// 4 channels per thread (C, pitches multiples of 4; 32-bit index math): the scalar kernels above spend a 64-bit division
-// per element
-__global__ void bn_silu_apply4_kernel(const float* __restrict__ z, int total4, int C4, int pitch, int opitch,
-                                      const float* __restrict__ mean, const float* __restrict__ invstd,
-                                      const float* __restrict__ gamma, const float* __restrict__ beta, int act, float* __restrict__ y) {
-  pdl_wait();
-  pdl_trigger();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total4) return;
-  const int r = i / C4, c = (i - r * C4) * 4;
-  const float4 v = *reinterpret_cast<const float4*>(z + (size_t)r * pitch + c);
-  const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
-  const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
-  float4 u;
-  u.x = ga.x * (v.x - mu.x) * is.x + be.x; u.y = ga.y * (v.y - mu.y) * is.y + be.y;
-  u.z = ga.z * (v.z - mu.z) * is.z + be.z; u.w = ga.w * (v.w - mu.w) * is.w + be.w;
-  if (act) { u.x = silu_f(u.x); u.y = silu_f(u.y); u.z = silu_f(u.z); u.w = silu_f(u.w); }
-  *reinterpret_cast<float4*>(y + (size_t)r * opitch + c) = u;
-}
+// Elementwise passes, 4 channels per thread: a thread owns one channel quad and walks rows r0 + ty, + LY, ... of its slab, so
+// the per-channel vectors (mean, invstd, gamma, beta [, dgamma, dbeta]) are loaded ONCE per thread instead of once per
+// element and there is no index division.  (One float4 per thread with the parameters re-loaded per element ran at 69 - 73 %
+// issue-active and 53 - 59 % of the DRAM rate on the 160 x 160 layers, profiles/r2_ncu_bn_kernels.txt.)
+struct BnRows {
+  const float *z, *dy;
+  float* out;
+  long long M;
+  int C, pitch, dpitch, opitch, rpb, act;
+  const float *mean, *invstd, *gamma, *beta, *dgamma, *dbeta;
+  float inv_m;
+};
 
-__global__ void bn_silu_dz4_kernel(const float* __restrict__ z, const float* __restrict__ dy, int total4, int C4, int pitch, int dpitch,
-                                   int opitch, float inv_m, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-                                   const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dz) {
+template <int BWD>  // 0: y = act(gamma * xhat + beta); 1: dz from dy (BatchNorm + SiLU backward)
+__global__ void __launch_bounds__(256, BWD ? 3 : 4) bn_rows4_kernel(const BnRows a) {
   pdl_wait();
   pdl_trigger();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total4) return;
-  const int r = i / C4, c = (i - r * C4) * 4;
-  const float4 v = *reinterpret_cast<const float4*>(z + (size_t)r * pitch + c);
-  const float4 d = *reinterpret_cast<const float4*>(dy + (size_t)r * dpitch + c);
-  const float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
-  float o[4];
+  const int LX = blockDim.x, LY = blockDim.y, ty = threadIdx.y;
+  const int c = (blockIdx.x * LX + threadIdx.x) * 4;
+  if (c >= a.C) return;
+  float mu[4], is[4], ga[4], be[4], dg[4], db[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    const float is = invstd[c + j], ga = gamma[c + j];
-    const float xh = (vv[j] - mean[c + j]) * is;
-    const float g = dd[j] * (act ? silu_grad(ga * xh + beta[c + j]) : 1.f);
-    o[j] = ga * is * (g - dbeta[c + j] * inv_m - xh * dgamma[c + j] * inv_m);
+    mu[j] = a.mean[c + j]; is[j] = a.invstd[c + j]; ga[j] = a.gamma[c + j]; be[j] = a.beta[c + j];
+    dg[j] = BWD ? a.dgamma[c + j] : 0.f;
+    db[j] = BWD ? a.dbeta[c + j] : 0.f;
   }
-  *reinterpret_cast<float4*>(dz + (size_t)r * opitch + c) = make_float4(o[0], o[1], o[2], o[3]);
+  const float inv_m = a.inv_m;
+  auto fwd = [&](const float4& v) {
+    float4 u;
+    u.x = ga[0] * (v.x - mu[0]) * is[0] + be[0]; u.y = ga[1] * (v.y - mu[1]) * is[1] + be[1];
+    u.z = ga[2] * (v.z - mu[2]) * is[2] + be[2]; u.w = ga[3] * (v.w - mu[3]) * is[3] + be[3];
+    if (a.act) { u.x = silu_f(u.x); u.y = silu_f(u.y); u.z = silu_f(u.z); u.w = silu_f(u.w); }
+    return u;
+  };
+  auto bwd = [&](const float4& v, const float4& d) {
+    const float vv[4] = {v.x, v.y, v.z, v.w}, dd[4] = {d.x, d.y, d.z, d.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float xh = (vv[j] - mu[j]) * is[j];
+      const float g = dd[j] * (a.act ? silu_grad(ga[j] * xh + be[j]) : 1.f);
+      o[j] = ga[j] * is[j] * (g - db[j] * inv_m - xh * dg[j] * inv_m);
+    }
+    return make_float4(o[0], o[1], o[2], o[3]);
+  };
+  const long long r0 = (long long)blockIdx.y * a.rpb, r1 = min(a.M, r0 + a.rpb);
+  const long long span = r1 - r0 - ty;
+  const int nrows = span > 0 ? (int)((span + LY - 1) / LY) : 0;
+  const float* zp = a.z + (r0 + ty) * a.pitch + c;
+  const float* dp = BWD ? a.dy + (r0 + ty) * a.dpitch + c : nullptr;
+  float* op = a.out + (r0 + ty) * a.opitch + c;
+  const size_t zs = (size_t)LY * a.pitch, ds = BWD ? (size_t)LY * a.dpitch : 0, os = (size_t)LY * a.opitch;
+  int it = 0;
+#pragma unroll 1
+  for (; it + 2 <= nrows; it += 2) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(zp)), v1 = __ldg(reinterpret_cast<const float4*>(zp + zs));
+    float4 o0, o1;
+    if (BWD) {
+      const float4 d0 = __ldg(reinterpret_cast<const float4*>(dp)), d1 = __ldg(reinterpret_cast<const float4*>(dp + ds));
+      o0 = bwd(v0, d0);
+      o1 = bwd(v1, d1);
+      dp += 2 * ds;
+    } else {
+      o0 = fwd(v0);
+      o1 = fwd(v1);
+    }
+    *reinterpret_cast<float4*>(op) = o0;
+    *reinterpret_cast<float4*>(op + os) = o1;
+    zp += 2 * zs;
+    op += 2 * os;
+  }
+  if (it < nrows) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(zp));
+    *reinterpret_cast<float4*>(op) = BWD ? bwd(v0, __ldg(reinterpret_cast<const float4*>(dp))) : fwd(v0);
+  }
+}
+
+struct BnRowsPlan { int LX, LY, colblocks, rpb, slabs; };
+static BnRowsPlan bn_rows_plan(long long M, int C) {
+  BnRowsPlan p;
+  const int c4 = C / 4;
+  p.LX = 1;
+  while (p.LX < c4 && p.LX < 32) p.LX <<= 1;
+  p.LY = 256 / p.LX;
+  p.colblocks = (c4 + p.LX - 1) / p.LX;
+  const long long want = std::max(1, 2368 / p.colblocks);  // ~16 CTAs per SM over the launch: 4 resident, 4 waves
+  const long long step = (long long)p.LY * 2;
+  long long rpb = (M + want - 1) / want;
+  rpb = std::max(step, (rpb + step - 1) / step * step);
+  p.rpb = (int)rpb;
+  p.slabs = (int)((M + rpb - 1) / rpb);
+  return p;
 }
 
 }  // namespace
@@ -441,11 +491,12 @@ int bn_silu_train_forward(const float* z, long long M, int C, int pitch, const f
                                        running_var, const_cast<float*>(z) /* the shift row, read only */, nullptr);
   }
   const long long total = M * C;
-  if (C % 4 == 0 && pitch % 4 == 0 && ypitch % 4 == 0 && total / 4 < (1ll << 31) && ((uintptr_t)z % 16 == 0) && ((uintptr_t)y % 16 == 0) &&
-      aligned16(save_mean, save_invstd, gamma, beta)) {
-    const int total4 = (int)(total / 4);
-    YB_CUDA_CHECK(launch_pdl(bn_silu_apply4_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, s, z, total4, C / 4, pitch, ypitch,
-                             save_mean, save_invstd, gamma, beta, act, y));
+  if (C % 4 == 0 && pitch % 4 == 0 && ypitch % 4 == 0 && ((uintptr_t)z % 16 == 0) && ((uintptr_t)y % 16 == 0)) {
+    const BnRowsPlan pl = bn_rows_plan(M, C);
+    BnRows a{};
+    a.z = z; a.out = y; a.M = M; a.C = C; a.pitch = pitch; a.opitch = ypitch; a.rpb = pl.rpb; a.act = act;
+    a.mean = save_mean; a.invstd = save_invstd; a.gamma = gamma; a.beta = beta;
+    YB_CUDA_CHECK(launch_pdl(bn_rows4_kernel<0>, dim3(pl.colblocks, pl.slabs), dim3(pl.LX, pl.LY), 0, s, a));
   } else {
     bn_silu_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, M, C, pitch, ypitch, save_mean, save_invstd, gamma, beta, act, y);
   }
@@ -485,11 +536,14 @@ int bn_silu_backward(const float* z, const float* dy, long long M, int C, int pi
                                                      nullptr, dgamma, dbeta);
   }
   const long long total = M * C;
-  if (C % 4 == 0 && pitch % 4 == 0 && dpitch % 4 == 0 && zpitch % 4 == 0 && total / 4 < (1ll << 31) && ((uintptr_t)z % 16 == 0) &&
-      ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dz % 16 == 0)) {
-    const int total4 = (int)(total / 4);
-    YB_CUDA_CHECK(launch_pdl(bn_silu_dz4_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, s, z, dy, total4, C / 4, pitch, dpitch,
-                             zpitch, 1.f / (float)M, save_mean, save_invstd, gamma, beta, act, dgamma, dbeta, dz));
+  if (C % 4 == 0 && pitch % 4 == 0 && dpitch % 4 == 0 && zpitch % 4 == 0 && ((uintptr_t)z % 16 == 0) && ((uintptr_t)dy % 16 == 0) &&
+      ((uintptr_t)dz % 16 == 0)) {
+    const BnRowsPlan pl = bn_rows_plan(M, C);
+    BnRows a{};
+    a.z = z; a.dy = dy; a.out = dz; a.M = M; a.C = C; a.pitch = pitch; a.dpitch = dpitch; a.opitch = zpitch; a.rpb = pl.rpb; a.act = act;
+    a.mean = save_mean; a.invstd = save_invstd; a.gamma = gamma; a.beta = beta; a.dgamma = dgamma; a.dbeta = dbeta;
+    a.inv_m = 1.f / (float)M;
+    YB_CUDA_CHECK(launch_pdl(bn_rows4_kernel<1>, dim3(pl.colblocks, pl.slabs), dim3(pl.LX, pl.LY), 0, s, a));
   } else {
     bn_silu_dz_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(z, dy, M, C, pitch, dpitch, zpitch, save_mean, save_invstd, gamma, beta,
                                                                   act, dgamma, dbeta, dz);
