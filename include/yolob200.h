@@ -392,6 +392,23 @@ int32_t yb_ap_per_class(const uint8_t* tp, const float* conf, const int32_t* pre
                         float* tp_out, float* fp_out, void* stream);
 int32_t yb_linspace01(int32_t steps, float* out_host);
 
+/* The instance-mask term of `v8SegmentationLoss` (Utils/Loss.cs:688-865: `calculate_segmentation_loss` :806-861 with
+ * `single_mask_loss` :787-795, overlap_mask = true), loss and gradients (csrc/segloss.cu).  The box / cls / dfl terms and the
+ * assignment are yb_detection_loss's (the criterion derives from v8DetectionLoss, :411-468); this entry point takes
+ *   fg (B, A) uint8, gt_idx (B, A) int32       as yb_detection_loss returns them
+ *   target_bboxes (B, A, 4)                     the assigned ground-truth boxes, xyxy in input pixels
+ *   masks (B, mask_h, mask_w) float32           instance index + 1 per pixel, 0 = background (the reference's overlap encoding)
+ *   proto (B, nm, mask_h, mask_w), mask_coefficient (B, nm, A)   the Segment head's train-mode outputs (nm <= 64)
+ *   img_h, img_w                                the input size (feats[0] shape * stride[0], :744)
+ * and writes loss_item (1) = loss[1] after the `hyp_box` gain (the value the criterion reports), grad_proto and
+ * grad_coefficient = d(loss[1] * batch) / d(proto, mask_coefficient) (the criterion returns loss * batch_size, :785).
+ * All pointers device.  Masks at another resolution than proto (the reference's interpolate branch, :739-743) are not
+ * supported. */
+int32_t yb_segmentation_loss(const uint8_t* fg, const int32_t* gt_idx, const float* target_bboxes, const float* masks,
+                             const float* proto, const float* mask_coefficient, int32_t batch, int32_t anchors, int32_t nm,
+                             int32_t mask_h, int32_t mask_w, float img_h, float img_w, float hyp_box, float* loss_item,
+                             float* grad_proto, float* grad_coefficient, void* stream);
+
 /* ---- multi-GPU: exchange of the fixed-capacity detection payloads over NVLink peer memory (csrc/comm.cu) ----
  * Design target SURVEY.md section 8(e); the reference is single-device (Data/Config.cs:301), so this surface is
  * net-new.  One yb_comm per process (= per GPU), all ranks on one node.  Every rank pushes its payload into a

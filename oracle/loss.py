@@ -252,3 +252,49 @@ class V8DetectionLoss:
         """Loss.cs:468-483: (loss * batch_size, loss.detach())."""
         _, loss = self.assigned_targets_and_loss(preds, batch)
         return loss * preds["boxes"].shape[0], loss.detach()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# v8SegmentationLoss: the instance-mask term (Loss.cs:688-865).  The box / cls / dfl terms are v8DetectionLoss's
+# (get_assigned_targets_and_loss, :411-468); what the segmentation criterion adds is calculate_segmentation_loss
+# (:806-861) with single_mask_loss (:787-795), driven by the assigner's fg_mask / target_gt_idx / target_bboxes.
+# ---------------------------------------------------------------------------------------------------------------------
+def single_mask_loss(gt_mask, pred, proto, xyxy, area):
+    """Loss.cs:787-795.  gt_mask (n, H, W), pred (n, nm), proto (nm, H, W), xyxy (n, 4) in mask pixels, area (n,)."""
+    from .ops import crop_mask  # the CUDA / n >= 50 branch of Ops.crop_mask (Ops.cs:437-447)
+    pred_mask = torch.einsum("in,nhw->ihw", pred, proto)
+    loss = F.binary_cross_entropy_with_logits(pred_mask, gt_mask, reduction="none")
+    return (crop_mask(loss, xyxy).mean(dim=(1, 2)) / area).sum()
+
+
+def calculate_segmentation_loss(fg_mask, masks, target_gt_idx, target_bboxes, proto, pred_masks, imgsz):
+    """Loss.cs:806-861, overlap_mask = true (the reference's default, :694): masks (B, H, W) holds instance index + 1.
+    imgsz = (H_img, W_img).  -> scalar: sum over images of single_mask_loss / number of foreground anchors."""
+    mask_h, mask_w = proto.shape[2], proto.shape[3]
+    loss = torch.zeros(1)
+    wh = torch.stack((imgsz[1], imgsz[0], imgsz[1], imgsz[0]))
+    tbn = target_bboxes / wh
+    marea = xyxy2xywh(tbn)[..., 2:].prod(2)
+    mxyxy = tbn * torch.tensor([mask_w, mask_h, mask_w, mask_h], dtype=tbn.dtype)
+    for i in range(fg_mask.shape[0]):
+        if bool(fg_mask[i].any()):
+            mask_idx = target_gt_idx[i][fg_mask[i]]
+            gt_mask = (masks[i] == (mask_idx + 1).view(-1, 1, 1)).float()
+            loss = loss + single_mask_loss(gt_mask, pred_masks[i][fg_mask[i]], proto[i], mxyxy[i][fg_mask[i]], marea[i][fg_mask[i]])
+        else:
+            loss = loss + (proto * 0).sum() + (pred_masks * 0).sum()
+    return loss.sum() / fg_mask.sum()
+
+
+def segmentation_mask_loss(fg_mask, target_gt_idx, target_bboxes, masks, proto, mask_coefficient, imgsz, hyp_box=7.5):
+    """loss[1] of v8SegmentationLoss.loss (Loss.cs:712-786): mask_coefficient (B, nm, A) as the head returns it, proto
+    (B, nm, H, W) at the resolution of `masks`.  -> (loss[1] * batch_size, loss[1]) as the criterion returns them."""
+    pred_masks = mask_coefficient.permute(0, 2, 1).contiguous()
+    B = proto.shape[0]
+    if float(fg_mask.sum()) > 0:
+        assert masks.shape[-2:] == proto.shape[-2:], "the interpolate branch (:739-743) is not restated"
+        item = calculate_segmentation_loss(fg_mask, masks.float(), target_gt_idx, target_bboxes, proto, pred_masks, imgsz)
+    else:
+        item = (proto * 0).sum() + (pred_masks * 0).sum()
+    item = item * hyp_box
+    return item * B, item.detach()

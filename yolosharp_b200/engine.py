@@ -332,6 +332,27 @@ def ap_per_class(tp, conf, pred_cls, target_cls, max_classes=80, stream=None):
             "p_curve": pcv[:nc], "r_curve": rcv[:nc], "f1_curve": f1c[:nc], "x": x, "prec_values": prec_values, "best": best}
 
 
+def segmentation_loss(fg, gt_idx, target_bboxes, masks, proto, mask_coefficient, height, width, hyp_box=7.5, stream=None):
+    """yb_segmentation_loss: the instance-mask term of v8SegmentationLoss (Utils/Loss.cs:688-865) and its gradients.
+    fg (B, A) uint8 / bool, gt_idx (B, A), target_bboxes (B, A, 4) px, masks (B, mh, mw) instance index + 1, proto
+    (B, nm, mh, mw), mask_coefficient (B, nm, A): CUDA tensors -> dict(item, grad_proto, grad_coefficient)."""
+    assert proto.is_cuda and proto.dtype == torch.float32 and proto.is_contiguous() and mask_coefficient.is_contiguous()
+    B, nm, mh, mw = proto.shape
+    A = mask_coefficient.shape[2]
+    dev = proto.device
+    fg8 = fg.to(device=dev, dtype=torch.uint8).contiguous()
+    gi = gt_idx.to(device=dev, dtype=torch.int32).contiguous()
+    tb = target_bboxes.to(device=dev, dtype=torch.float32).contiguous()
+    mk = masks.to(device=dev, dtype=torch.float32).contiguous()
+    assert fg8.shape == (B, A) and gi.shape == (B, A) and tb.shape == (B, A, 4) and mk.shape == (B, mh, mw)
+    item = torch.empty(1, dtype=torch.float32, device=dev)
+    gp, gc = torch.empty_like(proto), torch.empty_like(mask_coefficient)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    L.check(L.lib().yb_segmentation_loss(p(fg8), p(gi), p(tb), p(mk), p(proto), p(mask_coefficient), B, A, nm, mh, mw, float(height), float(width),
+                                         float(hyp_box), p(item), p(gp), p(gc), _stream_ptr(stream)))
+    return {"item": item, "grad_proto": gp, "grad_coefficient": gc}
+
+
 def detection_loss(boxes, scores, targets, height, width, reg_max=16, topk=10, hyp_box=7.5, hyp_cls=0.5, hyp_dfl=1.5,
                    want_grad=True, stream=None):
     """yb_detection_loss: v8DetectionLoss (Utils/Loss.cs:328-485) on the raw train-mode head outputs.
