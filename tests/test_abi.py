@@ -5,6 +5,7 @@ import os
 import re
 import struct
 import subprocess
+import sys
 import tempfile
 
 import pytest
@@ -26,6 +27,17 @@ def test_header_symbols_exported(built_lib):
         assert hasattr(lib, n), f"{n} declared in yolob200.h but not exported"
     from yolosharp_b200 import _lib
     assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+
+
+def test_integration_md_mentions_every_entry_point():
+    """INTEGRATION.md shows the reference-side binding of the boundary: every function of the header must appear in it, and
+    the generated P/Invoke listing (tools/gen_pinvoke.py) must cover the whole header."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in header_functions() if n not in text]
+    assert not missing, f"INTEGRATION.md lacks {missing}"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_pinvoke.py")], capture_output=True, text=True, check=True).stdout
+    declared = sorted(set(re.findall(r"\b(yb_[a-z0-9_]+)\(", out)))
+    assert declared == header_functions()
 
 
 def test_header_compiles_as_c(built_lib):
