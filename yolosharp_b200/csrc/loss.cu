@@ -445,22 +445,26 @@ int detection_loss_launch_dev(const float* boxes, const float* scores, int B, in
   unsigned char* in_gts = reinterpret_cast<unsigned char*>(gt_idx + na);
   unsigned char* mask_pos = in_gts + nga;
   unsigned char* fg = mask_pos + nga;
-  YB_CUDA_CHECK(cudaMemsetAsync(tss, 0, 4, s));
-  YB_CUDA_CHECK(cudaMemsetAsync(loss_items, 0, 12, s));
-  const dim3 ga((g.A + 255) / 256, B);
-  loss_decode_kernel<<<ga, 256, 0, s>>>(g, boxes, pbox);
-  tal_metric_kernel<<<dim3((g.A + 255) / 256, g.n_max, B), 256, 0, s>>>(g, scores, pbox, d_gts, ov, am, in_gts);
-  tal_topk_kernel<<<dim3(g.n_max, B), 256, 0, s>>>(g, am, in_gts, d_gts, mask_pos);
-  tal_resolve_kernel<<<ga, 256, 0, s>>>(g, ov, mask_pos, gt_idx, fg);
-  tal_norm_kernel<<<dim3(g.n_max, B), 256, 0, s>>>(g, ov, am, mask_pos, pos_am, pos_ov);
-  tal_score_kernel<<<ga, 256, 0, s>>>(g, ov, am, gt_idx, fg, pos_am, pos_ov, tscore, tss);
-  loss_grad_kernel<<<dim3((g.A + 127) / 128, B), 128, 0, s>>>(g, boxes, scores, pbox, d_gts, gt_idx, fg, tscore, tss, hyp_box,
-                                                              hyp_cls, hyp_dfl, loss_items, grad_boxes, grad_scores);
-  YB_CUDA_CHECK(cudaGetLastError());
-  if (fg_out) YB_CUDA_CHECK(cudaMemcpyAsync(fg_out, fg, na, cudaMemcpyDeviceToDevice, s));
-  if (gt_idx_out) YB_CUDA_CHECK(cudaMemcpyAsync(gt_idx_out, gt_idx, na * 4, cudaMemcpyDeviceToDevice, s));
-  if (tscore_out) YB_CUDA_CHECK(cudaMemcpyAsync(tscore_out, tscore, na * 4, cudaMemcpyDeviceToDevice, s));
-  YB_CUDA_CHECK(cudaFreeAsync(scratch, s));
+  // from here on every error path must release `scratch`: keep the first error and fall through to the free
+  cudaError_t ce = cudaMemsetAsync(tss, 0, 4, s);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(loss_items, 0, 12, s);
+  if (ce == cudaSuccess) {
+    const dim3 ga((g.A + 255) / 256, B);
+    loss_decode_kernel<<<ga, 256, 0, s>>>(g, boxes, pbox);
+    tal_metric_kernel<<<dim3((g.A + 255) / 256, g.n_max, B), 256, 0, s>>>(g, scores, pbox, d_gts, ov, am, in_gts);
+    tal_topk_kernel<<<dim3(g.n_max, B), 256, 0, s>>>(g, am, in_gts, d_gts, mask_pos);
+    tal_resolve_kernel<<<ga, 256, 0, s>>>(g, ov, mask_pos, gt_idx, fg);
+    tal_norm_kernel<<<dim3(g.n_max, B), 256, 0, s>>>(g, ov, am, mask_pos, pos_am, pos_ov);
+    tal_score_kernel<<<ga, 256, 0, s>>>(g, ov, am, gt_idx, fg, pos_am, pos_ov, tscore, tss);
+    loss_grad_kernel<<<dim3((g.A + 127) / 128, B), 128, 0, s>>>(g, boxes, scores, pbox, d_gts, gt_idx, fg, tscore, tss, hyp_box,
+                                                                hyp_cls, hyp_dfl, loss_items, grad_boxes, grad_scores);
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess && fg_out) ce = cudaMemcpyAsync(fg_out, fg, na, cudaMemcpyDeviceToDevice, s);
+  if (ce == cudaSuccess && gt_idx_out) ce = cudaMemcpyAsync(gt_idx_out, gt_idx, na * 4, cudaMemcpyDeviceToDevice, s);
+  if (ce == cudaSuccess && tscore_out) ce = cudaMemcpyAsync(tscore_out, tscore, na * 4, cudaMemcpyDeviceToDevice, s);
+  cudaFreeAsync(scratch, s);
+  if (ce != cudaSuccess) { set_error(std::string("yb_detection_loss: ") + cudaGetErrorString(ce)); return YB_ERR_CUDA; }
   return YB_OK;
 }
 
@@ -473,8 +477,13 @@ int detection_loss_launch(const float* boxes, const float* scores, int B, int nc
   if (int rc = detection_loss_prepare(targets_host, n_targets, B, nc, H, W, gts, &n_max)) return rc;
   float* d_gts = nullptr;
   YB_CUDA_CHECK(cudaMallocAsync((void**)&d_gts, gts.size() * 4, s));
-  YB_CUDA_CHECK(cudaMemcpyAsync(d_gts, gts.data(), gts.size() * 4, cudaMemcpyHostToDevice, s));
-  YB_CUDA_CHECK(cudaStreamSynchronize(s));  // `gts` is a host temporary
+  cudaError_t ce = cudaMemcpyAsync(d_gts, gts.data(), gts.size() * 4, cudaMemcpyHostToDevice, s);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);  // `gts` is a host temporary
+  if (ce != cudaSuccess) {
+    cudaFreeAsync(d_gts, s);
+    set_error(std::string("yb_detection_loss: ") + cudaGetErrorString(ce));
+    return YB_ERR_CUDA;
+  }
   const int rc = detection_loss_launch_dev(boxes, scores, B, nc, reg_max, H, W, d_gts, n_max, topk, hyp_box, hyp_cls, hyp_dfl, loss_items,
                                            grad_boxes, grad_scores, fg_out, gt_idx_out, tscore_out, s);
   cudaFreeAsync(d_gts, s);
