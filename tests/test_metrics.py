@@ -138,3 +138,15 @@ def test_ap_per_class_empty_inputs_gpu():
     # detections but no labels: no unique classes
     g = E.ap_per_class(torch.ones((4, 10), dtype=torch.bool).cuda(), torch.rand(4).cuda(), torch.zeros(4).cuda(), torch.zeros(0).cuda())
     assert g["ap"].shape == (0, 10) and g["unique_classes"].numel() == 0
+
+
+def test_oracle_reproduces_golden_ap():
+    """tests/golden/r2_val_seg.npz (make_golden_r2b.py): the committed ap_per_class vectors."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "r2_val_seg.npz"))
+    o = oval.ap_per_class(torch.from_numpy(g["ap_tp"]), torch.from_numpy(g["ap_conf"]), torch.from_numpy(g["ap_pred_cls"]),
+                          torch.from_numpy(g["ap_target_cls"]))
+    assert o["unique_classes"].tolist() == g["ap_unique"].tolist() and o["best"] == int(g["ap_best"])
+    for k, gk in (("ap", "ap_ap"), ("p", "ap_p"), ("r", "ap_r"), ("f1", "ap_f1"), ("tp", "ap_tpn"), ("fp", "ap_fpn"), ("p_curve", "ap_p_curve"),
+                  ("r_curve", "ap_r_curve"), ("prec_values", "ap_prec_values")):
+        torch.testing.assert_close(o[k].float(), torch.from_numpy(g[gk]).float(), rtol=1e-6, atol=1e-7)

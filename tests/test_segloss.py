@@ -66,3 +66,18 @@ def test_segmentation_loss_matches_oracle_gpu(kw):
         scale = float(ref.abs().max()) or 1.0
         err = float((got.cpu() - ref).abs().max()) / scale
         assert err < 2e-5, f"grad {name}: max scaled error {err:.3e}"
+
+
+def test_oracle_reproduces_golden_mask_loss():
+    """tests/golden/r2_val_seg.npz (make_golden_r2b.py): the committed segmentation-mask-loss vectors."""
+    import os
+
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "r2_val_seg.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    p, c = t("seg_proto").clone().requires_grad_(True), t("seg_coef").clone().requires_grad_(True)
+    scaled, item = oloss.segmentation_mask_loss(t("seg_fg"), t("seg_gt_idx"), t("seg_tbox"), t("seg_masks"), p, c, t("seg_imgsz"))
+    scaled.backward()
+    assert abs(float(item) - float(g["seg_item"])) < 1e-6 * max(1.0, abs(float(g["seg_item"])))
+    torch.testing.assert_close(p.grad, t("seg_grad_proto"), rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(c.grad, t("seg_grad_coef"), rtol=1e-5, atol=1e-8)
