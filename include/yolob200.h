@@ -368,6 +368,9 @@ int32_t yb_nms_rotated(const float* boxes, const float* scores, int32_t n, float
  *   iou_thresholds_host  the reference's linspace(0.5, 0.95, 10) as float32 (HOST pointer)
  *   correct  dev uint8 (B, max_det, n_thresholds): 1 where detection d is a true positive at threshold i */
 int32_t yb_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, float eps, float* out, void* stream);
+/* yb_mask_iou  replaces `Metrics.mask_iou(mask1, mask2)` (Utils/Metrics.cs:120-125, called by Segmenter.Val, Models/Segmenter.cs:142):
+ * mask1 (n1, pixels), mask2 (n2, pixels) float32 flattened masks -> out (n1, n2) float32. */
+int32_t yb_mask_iou(const float* mask1, int32_t n1, const float* mask2, int32_t n2, int32_t pixels, float eps, float* out, void* stream);
 
 int32_t yb_match_predictions(const float* dets, const int32_t* counts, int32_t batch, int32_t max_det, int32_t row_width,
                              const float* labels, int32_t n_labels, const float* iou_thresholds_host, int32_t n_thresholds,

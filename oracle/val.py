@@ -1,6 +1,7 @@
 """Oracle restatement of the validation matching (test infrastructure only).
 
 box_iou            Utils/Metrics.cs:16-34
+mask_iou           Utils/Metrics.cs:120-125
 match_predictions  Models/YoloBaseTaskModel.cs:377-446 (incl. GetUniqueMatches / GetUniqueByColumn: first occurrence per
                    unique value, rows returned in the order of the sorted unique values)
 ap_per_class       Utils/Metrics.cs:308-384, with compute_ap :395-421, interp :424-468, smooth :475-487.
@@ -16,6 +17,13 @@ def box_iou(box1, box2, eps=1e-7):
     b1, b2 = box2.float().unsqueeze(0).chunk(2, 2)
     inter = (torch.min(a2, b2) - torch.max(a1, b1)).clamp_(0).prod(2)
     return inter / ((a2 - a1).prod(2) + (b2 - b1).prod(2) - inter + eps)
+
+
+def mask_iou(mask1, mask2, eps=1e-7):
+    """Utils/Metrics.cs:120-125: mask1 (N, n), mask2 (M, n) -> (N, M)."""
+    inter = torch.matmul(mask1, mask2.T).clamp_(0)
+    union = (mask1.sum(1)[..., None] + mask2.sum(1)[None]) - inter
+    return inter / (union + eps)
 
 
 def _unique_by_column(matches, col):

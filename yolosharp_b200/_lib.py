@@ -55,6 +55,7 @@ SIGNATURES = {
     "yb_box_iou": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp]),
     "yb_match_predictions": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp]),
     "yb_linspace01": (c_i32, [c_i32, c_vp]),
+    "yb_mask_iou": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_f32, c_vp, c_vp]),
     "yb_segmentation_loss": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_f32, c_vp, c_vp,
                                      c_vp, c_vp]),
     "yb_ap_per_class": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,

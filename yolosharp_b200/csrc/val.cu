@@ -67,6 +67,40 @@ __global__ void __launch_bounds__(256) match_predictions_kernel(const float* __r
   }
 }
 
+
+// Metrics.mask_iou (Utils/Metrics.cs:120-125): iou[i][j] = inter / (sum(mask1[i]) + sum(mask2[j]) - inter + eps) with
+// inter = max(mask1[i] . mask2[j], 0) over the n = H * W pixels of the flattened masks.  One block per (i, j): the three sums
+// in one pass (warp shuffles, then the 8 warp partials in order).  Seg validation compares a few dozen masks per image
+// (Models/Segmenter.cs:142): a latency-sized problem, not a GEMM worth tensor cores.
+__global__ void __launch_bounds__(256) mask_iou_kernel(const float* __restrict__ m1, const float* __restrict__ m2, int n, float eps,
+                                                       float* __restrict__ out, int M) {
+  const int i = blockIdx.y, j = blockIdx.x;
+  const float* a = m1 + (size_t)i * n;
+  const float* b = m2 + (size_t)j * n;
+  float inter = 0.f, sa = 0.f, sb = 0.f;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const float x = a[k], y = b[k];
+    inter = fmaf(x, y, inter);
+    sa += x;
+    sb += y;
+  }
+  __shared__ float red[3][8];
+  for (int o = 16; o; o >>= 1) {
+    inter += __shfl_down_sync(0xffffffffu, inter, o);
+    sa += __shfl_down_sync(0xffffffffu, sa, o);
+    sb += __shfl_down_sync(0xffffffffu, sb, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { red[0][warp] = inter; red[1][warp] = sa; red[2][warp] = sb; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int w = 0; w < 8; w++) { t0 += red[0][w]; t1 += red[1][w]; t2 += red[2][w]; }
+    t0 = fmaxf(t0, 0.f);
+    out[(size_t)i * M + j] = __fdiv_rn(t0, __fadd_rn(__fsub_rn(__fadd_rn(t1, t2), t0), eps));
+  }
+}
+
 }  // namespace yb
 
 using namespace yb;
@@ -77,6 +111,15 @@ int32_t yb_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, f
   if (n < 0 || m < 0 || ((n > 0 && m > 0) && (!box1 || !box2 || !out))) { set_error("yb_box_iou: bad argument"); return YB_ERR_INVALID_ARG; }
   if (n == 0 || m == 0) return YB_OK;
   box_iou_kernel<<<(n * m + 255) / 256, 256, 0, (cudaStream_t)stream>>>(box1, n, box2, m, eps, out);
+  YB_CUDA_CHECK(cudaGetLastError());
+  return YB_OK;
+}
+
+int32_t yb_mask_iou(const float* mask1, int32_t n1, const float* mask2, int32_t n2, int32_t pixels, float eps, float* out, void* stream) {
+  if (n1 < 0 || n2 < 0 || pixels <= 0 || ((n1 > 0 && n2 > 0) && (!mask1 || !mask2 || !out))) { set_error("yb_mask_iou: bad argument"); return YB_ERR_INVALID_ARG; }
+  if (n1 == 0 || n2 == 0) return YB_OK;
+  if (n1 > 65535) { set_error("yb_mask_iou: at most 65535 rows in mask1"); return YB_ERR_INVALID_ARG; }
+  mask_iou_kernel<<<dim3(n2, n1), 256, 0, (cudaStream_t)stream>>>(mask1, mask2, pixels, eps, out, n2);
   YB_CUDA_CHECK(cudaGetLastError());
   return YB_OK;
 }

@@ -304,6 +304,16 @@ def match_predictions(dets, counts, labels, iouv=None, stream=None):
     return correct
 
 
+def mask_iou(mask1, mask2, eps=1e-7, stream=None):
+    """yb_mask_iou (Utils/Metrics.cs:120-125): mask1 (N, n), mask2 (M, n) float32 CUDA tensors -> (N, M) IoU."""
+    assert mask1.is_cuda and mask2.is_cuda and mask1.dim() == 2 and mask2.dim() == 2 and mask1.shape[1] == mask2.shape[1]
+    a, b = mask1.float().contiguous(), mask2.float().contiguous()
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    L.check(L.lib().yb_mask_iou(C.c_void_p(a.data_ptr()) if a.numel() else None, a.shape[0], C.c_void_p(b.data_ptr()) if b.numel() else None,
+                                b.shape[0], a.shape[1], float(eps), C.c_void_p(out.data_ptr()) if out.numel() else None, _stream_ptr(stream)))
+    return out
+
+
 def ap_per_class(tp, conf, pred_cls, target_cls, max_classes=80, stream=None):
     """yb_ap_per_class (Utils/Metrics.cs:308-384): tp (n, T) uint8 / bool, conf (n,), pred_cls (n,), target_cls (m,) on the
     device -> dict with the reference's outputs (tp, fp, p, r, f1, ap, unique_classes, p_curve, r_curve, f1_curve, x,
