@@ -98,9 +98,11 @@ int32_t yb_load_tensor(yb_engine* e, const char* name, int32_t dtype, int32_t nd
 
 /* Native checkpoint ingest (csrc/ckpt.cu; host code, no TorchSharp / PyTorch needed).
  * Replaces: `Lib.LoadModel` for the TorchSharp `.bin` format (Utils/Lib.cs:9-54), `SafetensorsLoader`
- * (ModelLoader/SafetensorsLoader.cs:7-109) and `SaveWeight` (Models/YoloBaseTaskModel.cs:470-490).  The format is chosen
- * by the file extension (`.safetensors`, anything else = `.bin`); Ultralytics `.pt` pickles return
- * YB_ERR_NOT_IMPLEMENTED.  dtype codes are torch ScalarType values (yb_dtype; also 1 i8, 2 i16, 3 i32, 4 i64, 7 f64).
+ * (ModelLoader/SafetensorsLoader.cs:7-109), `PickleLoader` for torch.save archives (ModelLoader/PickleLoader.cs:21-466: zip +
+ * pickle; tensors are named by their path through dicts / lists / object attributes, a pickled nn.Module yields its
+ * state_dict() names - an Ultralytics checkpoint gives "model.model.0.conv.weight", ...) and `SaveWeight`
+ * (Models/YoloBaseTaskModel.cs:470-490).  The format is chosen by the file extension (`.safetensors`, `.pt` / `.pth`,
+ * anything else = `.bin`).  dtype codes are torch ScalarType values (yb_dtype; also 1 i8, 2 i16, 3 i32, 4 i64, 7 f64, 11 bool).
  *   yb_load_checkpoint  = open + yb_load_tensor for every f16 / f32 / bf16 tensor (+ counts of loaded tensors and of
  *                         expected tensors the file lacks; unlike YoloBaseTaskModel.cs:32-35 nothing falls back to
  *                         random weights: yb_finalize_weights fails on the first missing tensor)

@@ -79,7 +79,11 @@ def test_checkpoint_errors(tmp_path):
         E.read_checkpoint(trunc)
     with pytest.raises(YbError) as ei:
         E.read_checkpoint(str(tmp_path / "model.pt"))
-    assert "cannot read" in str(ei.value) or "pickle" in str(ei.value)
+    assert "cannot read" in str(ei.value)
+    notzip = str(tmp_path / "x.pt")
+    open(notzip, "wb").write(b"\x80\x02}q\x00." * 8)  # a bare pickle, not a torch.save archive
+    with pytest.raises(YbError):
+        E.read_checkpoint(notzip)
 
 
 def test_engine_load_checkpoint_dry_run(tmp_path):
@@ -117,3 +121,89 @@ def test_train_state_dict_roundtrip(tmp_path):
             assert int(back[k]) == 3
         elif v.numel():
             assert torch.equal(back[k].float(), v.float()), k
+
+
+# ---- torch.save archives (.pt): zip + pickle, read natively (replaces ModelLoader/PickleLoader.cs) ----
+def _same(got, want):
+    assert list(got) == list(want), (list(got)[:5], list(want)[:5])
+    for k, v in want.items():
+        assert got[k].dtype == v.dtype and tuple(got[k].shape) == tuple(v.shape) and torch.equal(got[k], v), k
+
+
+@pytest.mark.parametrize("proto", [2, 4])
+def test_pt_state_dict(tmp_path, proto):
+    from tests.util import oracle_model
+    sd = oracle_model("v8", "detect", "n").state_dict()  # OrderedDict with _metadata, fp32 + int64 num_batches_tracked
+    sd["extra.half"] = torch.randn(4, 3).half()
+    sd["extra.bf16"] = torch.randn(2, 5).bfloat16()
+    sd["extra.bool"] = torch.tensor([True, False, True])
+    sd["extra.u8"] = torch.arange(7, dtype=torch.uint8)
+    sd["extra.f64"] = torch.randn(3, dtype=torch.float64)
+    sd["extra.i32"] = torch.arange(5, dtype=torch.int32).view(5, 1)
+    sd["extra.scalar"] = torch.tensor(3.5)
+    sd["extra.empty"] = torch.zeros(0, 4)
+    p = str(tmp_path / "sd.pt")
+    torch.save(sd, p, pickle_protocol=proto)
+    _same(E.read_checkpoint(p), sd)
+
+
+def test_pt_nested_checkpoint_and_shared_storage(tmp_path):
+    """An Ultralytics-style dict {'epoch', 'model': state_dict, ...}: names are dotted paths (ExtractTensors, PickleLoader.cs:49-88);
+    views that share one storage keep their storage offsets."""
+    base = torch.arange(24, dtype=torch.float32)
+    ck = {"epoch": 7, "best_fitness": 0.25, "names": {0: "person", 1: "car"}, "date": "2024", "model": {"a.weight": base[4:16].view(3, 4),
+                                                                                                 "a.bias": base[16:20]},
+          "lst": [torch.ones(2), None, torch.zeros(1, 3)], "train_args": {"imgsz": 640, "rect": False}}
+    p = str(tmp_path / "ck.pth")
+    torch.save(ck, p)
+    got = E.read_checkpoint(p)
+    want = {"model.a.weight": ck["model"]["a.weight"], "model.a.bias": ck["model"]["a.bias"], "lst.0": ck["lst"][0], "lst.2": ck["lst"][2]}
+    _same(got, want)
+
+
+def test_pt_pickled_module_gives_state_dict_names(tmp_path):
+    """torch.save(module): the object tree of nn.Module instances (BUILD states with _parameters / _buffers / _modules) yields
+    the names module.state_dict() has; non-persistent extras (num_batches_tracked is a buffer, so it is included)."""
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, bias=False), torch.nn.BatchNorm2d(8), torch.nn.SiLU(),
+                            torch.nn.Sequential(torch.nn.Conv2d(8, 4, 1), torch.nn.Identity()))
+    p = str(tmp_path / "m.pt")
+    torch.save({"model": m, "epoch": 1}, p)
+    got = E.read_checkpoint(p)
+    want = {"model." + k: v for k, v in m.state_dict().items()}
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert torch.equal(got[k], v), k
+
+
+def test_pt_rejects_non_contiguous(tmp_path):
+    p = str(tmp_path / "t.pt")
+    torch.save({"w": torch.arange(12.).view(3, 4).t()}, p)
+    with pytest.raises(YbError) as ei:
+        E.read_checkpoint(p)
+    assert "contiguous" in str(ei.value)
+
+
+def test_engine_load_checkpoint_from_pt(tmp_path):
+    import yolosharp_b200 as y
+    from yolosharp_b200 import _lib as L
+    p = str(tmp_path / "n.pt")
+    torch.save(golden_sd(), p)
+    e = y.Engine("v8", "n", "detect", 80, "f16", 0, 1, 64, 64, flags=L.YB_FLAG_DRY_RUN)
+    loaded, missing = e.load_checkpoint(p)
+    assert missing == 0 and loaded >= len(e.expected_tensors())
+    e.close()
+
+
+def test_pt_whole_yolo_model_object(tmp_path):
+    """The way Ultralytics checkpoints are written: {'model': <model object in half precision>, ...}: every state_dict() entry
+    of a YOLOv11n object tree comes back under 'model.', bit for bit."""
+    from tests.util import oracle_model
+    m = oracle_model("v11", "detect", "n").half()
+    p = str(tmp_path / "full.pt")
+    torch.save({"model": m, "ema": None, "epoch": -1, "train_args": {"imgsz": 640}}, p)
+    got = E.read_checkpoint(p)
+    want = {"model." + k: v for k, v in m.state_dict().items()}
+    assert set(got) == set(want) and len(got) == 501
+    for k, v in want.items():
+        assert got[k].dtype == v.dtype and torch.equal(got[k], v), k

@@ -10,11 +10,26 @@
 //                                                                 {name: {dtype, shape, data_offsets}}, payload
 //   * `SaveWeight(path)`               Models/YoloBaseTaskModel.cs:470-490   `.bin` writer (keys containing "one2one"
 //                                                                 are skipped there; the caller chooses the tensors here)
-// The Ultralytics `.pt` pickle (ModelLoader/PickleLoader.cs) is NOT read: it needs a zip + pickle-opcode interpreter
-// and the reference itself only uses it in its offline converter (Tools.TransModelFromPickle).
+//   * `PickleLoader.Load(path)`        ModelLoader/PickleLoader.cs:21-466   torch.save archives (`.pt` / `.pth`): a ZIP with
+//                                                                 stored entries `<prefix>/data.pkl` (pickle protocol 2 - 4) and
+//                                                                 `<prefix>/data/<key>` (raw storages).  A pickle-opcode
+//                                                                 interpreter rebuilds the object tree (dicts, lists, tuples,
+//                                                                 objects with their BUILD state, `_rebuild_tensor_v2`,
+//                                                                 `_rebuild_parameter`, persistent storage ids) and every
+//                                                                 tensor is named by its path, as the reference's
+//                                                                 ExtractTensors does (:49-88: dict keys, list indices and
+//                                                                 attribute names joined by '.'); the `_parameters` /
+//                                                                 `_buffers` / `_modules` levels of pickled nn.Module objects
+//                                                                 are not spelled out, so a pickled module yields its
+//                                                                 state_dict() names.  (The reference's own
+//                                                                 ReadTensorsInfoFromFile ends in `ExtractTensors(null)`, :46,
+//                                                                 i.e. returns no tensors at this commit; it is only used by
+//                                                                 the offline converter Tools.TransModelFromPickle.)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -31,7 +46,7 @@ struct CkptTensor {
 
 static int item_size(int dt) {
   switch (dt) {
-    case 0: case 1: return 1;
+    case 0: case 1: case 11: return 1;
     case 2: case 5: case 15: return 2;
     case 3: case 6: return 4;
     case 4: case 7: return 8;
@@ -245,6 +260,326 @@ static bool ends_with(const std::string& s, const char* sfx) {
   return s.size() >= n && s.compare(s.size() - n, n, sfx) == 0;
 }
 
+// ---- torch.save archives: ZIP (stored entries) + pickle -------------------------------------------------------------------
+struct ZipEntry { std::string name; uint64_t data_off = 0, size = 0; int method = 0; };
+
+static uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+static uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+static bool zip_entries(const std::vector<uint8_t>& b, std::vector<ZipEntry>& out, std::string& err) {
+  const size_t n = b.size();
+  if (n < 22) { err = "too small for a zip archive"; return false; }
+  size_t eocd = std::string::npos;
+  for (size_t i = n - 22;; i--) {  // end-of-central-directory record, searched from the back (the comment is at most 64 KiB)
+    if (rd32(&b[i]) == 0x06054b50u) { eocd = i; break; }
+    if (i == 0 || n - i > 22 + 65535 + 1) break;
+  }
+  if (eocd == std::string::npos) { err = "no end-of-central-directory record"; return false; }
+  uint64_t count = rd16(&b[eocd + 10]), cd_size = rd32(&b[eocd + 12]), cd_off = rd32(&b[eocd + 16]);
+  if (eocd >= 20 && rd32(&b[eocd - 20]) == 0x07064b50u) {  // zip64 locator -> zip64 end-of-central-directory record
+    const uint64_t z = rd64(&b[eocd - 20 + 8]);
+    if (z + 56 <= n && rd32(&b[z]) == 0x06064b50u) { count = rd64(&b[z + 32]); cd_size = rd64(&b[z + 40]); cd_off = rd64(&b[z + 48]); }
+  }
+  if (cd_off + cd_size > n) { err = "central directory out of range"; return false; }
+  size_t p = (size_t)cd_off;
+  for (uint64_t i = 0; i < count; i++) {
+    if (p + 46 > n || rd32(&b[p]) != 0x02014b50u) { err = "bad central directory entry"; return false; }
+    ZipEntry e;
+    e.method = rd16(&b[p + 10]);
+    uint64_t csize = rd32(&b[p + 20]), usize = rd32(&b[p + 24]), lho = rd32(&b[p + 42]);
+    const size_t nl = rd16(&b[p + 28]), xl = rd16(&b[p + 30]), cl = rd16(&b[p + 32]);
+    if (p + 46 + nl + xl + cl > n) { err = "truncated central directory"; return false; }
+    e.name.assign(reinterpret_cast<const char*>(&b[p + 46]), nl);
+    for (size_t x = p + 46 + nl; x + 4 <= p + 46 + nl + xl;) {  // zip64 extended information
+      const uint16_t id = rd16(&b[x]), sz = rd16(&b[x + 2]);
+      if (id == 0x0001) {
+        size_t q = x + 4;
+        if (usize == 0xffffffffu && q + 8 <= x + 4 + sz) { usize = rd64(&b[q]); q += 8; }
+        if (csize == 0xffffffffu && q + 8 <= x + 4 + sz) { csize = rd64(&b[q]); q += 8; }
+        if (lho == 0xffffffffu && q + 8 <= x + 4 + sz) { lho = rd64(&b[q]); q += 8; }
+      }
+      x += 4 + (size_t)sz;
+    }
+    if (lho + 30 > n || rd32(&b[lho]) != 0x04034b50u) { err = "bad local header of " + e.name; return false; }
+    e.data_off = lho + 30 + rd16(&b[lho + 26]) + rd16(&b[lho + 28]);
+    e.size = usize;
+    if (e.method == 0 && e.data_off + e.size > n) { err = "entry " + e.name + " out of range"; return false; }
+    (void)csize;
+    out.push_back(std::move(e));
+    p += 46 + nl + xl + cl;
+  }
+  return true;
+}
+
+// value model of the unpickler
+struct PVal;
+typedef std::shared_ptr<PVal> PV;
+struct PVal {
+  enum Kind { NONE, BOOL, INT, FLOAT, STR, GLOBAL, TUPLE, LIST, DICT, OBJECT, STORAGE, TENSOR, MARK } kind = NONE;
+  long long i = 0;
+  double f = 0;
+  std::string s;                                  // STR / GLOBAL name / OBJECT class / STORAGE key
+  std::vector<PV> items;                          // TUPLE / LIST; OBJECT: constructor args
+  std::vector<std::pair<PV, PV>> dict;            // DICT in insertion order; OBJECT: attributes (string keys)
+  int dtype = 6;                                  // STORAGE / TENSOR
+  PV storage;                                     // TENSOR
+  long long offset = 0;                           // TENSOR: storage offset in elements
+  std::vector<int64_t> shape, stride;             // TENSOR
+};
+static PV mk(PVal::Kind k) { PV v = std::make_shared<PVal>(); v->kind = k; return v; }
+
+static int storage_dtype(const std::string& n) {
+  struct { const char* k; int d; } T[] = {{"HalfStorage", 5}, {"BFloat16Storage", 15}, {"DoubleStorage", 7}, {"FloatStorage", 6}, {"LongStorage", 4},
+                                          {"IntStorage", 3}, {"ShortStorage", 2}, {"CharStorage", 1}, {"ByteStorage", 0}, {"BoolStorage", 11}};
+  for (auto& t : T) if (n.find(t.k) != std::string::npos) return t.d;
+  return -1;
+}
+
+static bool unpickle(const uint8_t* d, size_t n, PV& result, std::string& err) {
+  std::vector<PV> st;
+  std::map<long long, PV> memo;
+  auto need = [&](size_t pos, size_t k) { return pos + k <= n; };
+  auto pop = [&]() { PV v = st.empty() ? mk(PVal::NONE) : st.back(); if (!st.empty()) st.pop_back(); return v; };
+  auto pop_to_mark = [&]() {
+    std::vector<PV> items;
+    while (!st.empty() && st.back()->kind != PVal::MARK) { items.insert(items.begin(), st.back()); st.pop_back(); }
+    if (!st.empty()) st.pop_back();
+    return items;
+  };
+  auto set_item = [&](const PV& target, const PV& k, const PV& v) {
+    if (target->kind != PVal::DICT && target->kind != PVal::OBJECT) return;
+    if (target->kind == PVal::OBJECT && target->s.find("OrderedDict") == std::string::npos && target->s.find("dict") == std::string::npos) return;
+    target->dict.push_back({k, v});
+  };
+  size_t p = 0;
+  while (p < n) {
+    const uint8_t op = d[p++];
+    switch (op) {
+      case 0x80: p += 1; break;                                   // PROTO
+      case 0x95: p += 8; break;                                   // FRAME
+      case '.': result = st.empty() ? mk(PVal::NONE) : st.back(); return true;
+      case '(': st.push_back(mk(PVal::MARK)); break;
+      case '0': pop(); break;                                     // POP
+      case '1': pop_to_mark(); break;                             // POP_MARK
+      case '2': if (!st.empty()) st.push_back(st.back()); break;  // DUP
+      case 'N': st.push_back(mk(PVal::NONE)); break;
+      case 0x88: case 0x89: { PV v = mk(PVal::BOOL); v->i = op == 0x88; st.push_back(v); break; }
+      case 'K': { if (!need(p, 1)) goto trunc; PV v = mk(PVal::INT); v->i = d[p]; p += 1; st.push_back(v); break; }
+      case 'M': { if (!need(p, 2)) goto trunc; PV v = mk(PVal::INT); v->i = rd16(d + p); p += 2; st.push_back(v); break; }
+      case 'J': { if (!need(p, 4)) goto trunc; PV v = mk(PVal::INT); v->i = (int32_t)rd32(d + p); p += 4; st.push_back(v); break; }
+      case 0x8a: {                                                // LONG1: little-endian two's complement
+        if (!need(p, 1)) goto trunc;
+        const size_t k = d[p++];
+        if (!need(p, k) || k > 8) { err = "LONG1 wider than 8 bytes"; return false; }
+        long long x = 0;
+        for (size_t i = 0; i < k; i++) x |= (long long)d[p + i] << (8 * i);
+        if (k && k < 8 && (d[p + k - 1] & 0x80)) x |= -1ll << (8 * k);
+        p += k;
+        PV v = mk(PVal::INT); v->i = x; st.push_back(v);
+        break;
+      }
+      case 'G': {                                                 // BINFLOAT: big-endian double
+        if (!need(p, 8)) goto trunc;
+        uint64_t u = 0;
+        for (int i = 0; i < 8; i++) u = (u << 8) | d[p + i];
+        p += 8;
+        PV v = mk(PVal::FLOAT); memcpy(&v->f, &u, 8); st.push_back(v);
+        break;
+      }
+      case 'X': case 'T': case 'B': {                             // BINUNICODE / BINSTRING / BINBYTES (4-byte length)
+        if (!need(p, 4)) goto trunc;
+        const size_t k = rd32(d + p); p += 4;
+        if (!need(p, k)) goto trunc;
+        PV v = mk(PVal::STR); v->s.assign(reinterpret_cast<const char*>(d + p), k); p += k; st.push_back(v);
+        break;
+      }
+      case 0x8c: case 'U': case 'C': {                            // SHORT_BINUNICODE / SHORT_BINSTRING / SHORT_BINBYTES
+        if (!need(p, 1)) goto trunc;
+        const size_t k = d[p++];
+        if (!need(p, k)) goto trunc;
+        PV v = mk(PVal::STR); v->s.assign(reinterpret_cast<const char*>(d + p), k); p += k; st.push_back(v);
+        break;
+      }
+      case 0x8d: case 0x8e: {                                     // BINUNICODE8 / BINBYTES8
+        if (!need(p, 8)) goto trunc;
+        const uint64_t k = rd64(d + p); p += 8;
+        if (k > n || !need(p, (size_t)k)) goto trunc;
+        PV v = mk(PVal::STR); v->s.assign(reinterpret_cast<const char*>(d + p), (size_t)k); p += (size_t)k; st.push_back(v);
+        break;
+      }
+      case 'c': {                                                 // GLOBAL: "module\nname\n"
+        std::string a, b2;
+        while (p < n && d[p] != '\n') a.push_back((char)d[p++]);
+        p++;
+        while (p < n && d[p] != '\n') b2.push_back((char)d[p++]);
+        p++;
+        PV v = mk(PVal::GLOBAL); v->s = a + "." + b2; st.push_back(v);
+        break;
+      }
+      case 0x93: { PV nm = pop(), md = pop(); PV v = mk(PVal::GLOBAL); v->s = md->s + "." + nm->s; st.push_back(v); break; }  // STACK_GLOBAL
+      case 'q': { if (!need(p, 1)) goto trunc; if (!st.empty()) memo[d[p]] = st.back(); p += 1; break; }
+      case 'r': { if (!need(p, 4)) goto trunc; if (!st.empty()) memo[rd32(d + p)] = st.back(); p += 4; break; }
+      case 0x94: { if (!st.empty()) { const long long k = (long long)memo.size(); memo[k] = st.back(); } break; }                // MEMOIZE
+      case 'h': { if (!need(p, 1)) goto trunc; auto it = memo.find(d[p]); st.push_back(it == memo.end() ? mk(PVal::NONE) : it->second); p += 1; break; }
+      case 'j': { if (!need(p, 4)) goto trunc; auto it = memo.find(rd32(d + p)); st.push_back(it == memo.end() ? mk(PVal::NONE) : it->second); p += 4; break; }
+      case ')': st.push_back(mk(PVal::TUPLE)); break;
+      case ']': st.push_back(mk(PVal::LIST)); break;
+      case '}': st.push_back(mk(PVal::DICT)); break;
+      case 0x8f: st.push_back(mk(PVal::LIST)); break;            // EMPTY_SET (kept as a list)
+      case 't': { PV v = mk(PVal::TUPLE); v->items = pop_to_mark(); st.push_back(v); break; }
+      case 'l': { PV v = mk(PVal::LIST); v->items = pop_to_mark(); st.push_back(v); break; }
+      case 'd': {
+        std::vector<PV> it = pop_to_mark();
+        PV v = mk(PVal::DICT);
+        for (size_t i = 0; i + 1 < it.size(); i += 2) v->dict.push_back({it[i], it[i + 1]});
+        st.push_back(v);
+        break;
+      }
+      case 0x85: { PV a = pop(); PV v = mk(PVal::TUPLE); v->items = {a}; st.push_back(v); break; }
+      case 0x86: { PV b2 = pop(), a = pop(); PV v = mk(PVal::TUPLE); v->items = {a, b2}; st.push_back(v); break; }
+      case 0x87: { PV c2 = pop(), b2 = pop(), a = pop(); PV v = mk(PVal::TUPLE); v->items = {a, b2, c2}; st.push_back(v); break; }
+      case 'a': { PV x = pop(); if (!st.empty() && st.back()->kind == PVal::LIST) st.back()->items.push_back(x); break; }
+      case 'e': case 0x90: {                                      // APPENDS / ADDITEMS
+        std::vector<PV> it = pop_to_mark();
+        if (!st.empty() && st.back()->kind == PVal::LIST) for (auto& x : it) st.back()->items.push_back(x);
+        break;
+      }
+      case 's': { PV v = pop(), k = pop(); if (!st.empty()) set_item(st.back(), k, v); break; }
+      case 'u': {
+        std::vector<PV> it = pop_to_mark();
+        if (!st.empty()) for (size_t i = 0; i + 1 < it.size(); i += 2) set_item(st.back(), it[i], it[i + 1]);
+        break;
+      }
+      case 'Q': {                                                 // BINPERSID: ('storage', storage_type, key, location, numel)
+        PV pid = pop();
+        PV v = mk(PVal::NONE);
+        if (pid->kind == PVal::TUPLE && pid->items.size() >= 5 && pid->items[0]->kind == PVal::STR && pid->items[0]->s == "storage") {
+          const int dt = storage_dtype(pid->items[1]->s);
+          if (dt < 0) { err = "unsupported storage type " + pid->items[1]->s; return false; }
+          v = mk(PVal::STORAGE);
+          v->dtype = dt;
+          v->s = pid->items[2]->kind == PVal::INT ? std::to_string(pid->items[2]->i) : pid->items[2]->s;
+          v->i = pid->items[4]->i;
+        }
+        st.push_back(v);
+        break;
+      }
+      case 'R': case 0x81: case 0x92: {                           // REDUCE / NEWOBJ / NEWOBJ_EX
+        PV kwargs = op == 0x92 ? pop() : nullptr;
+        PV args = pop(), fn = pop();
+        (void)kwargs;
+        PV v = mk(PVal::OBJECT);
+        v->s = fn->kind == PVal::GLOBAL ? fn->s : std::string();
+        if (args->kind == PVal::TUPLE) v->items = args->items;
+        if (op == 'R' && v->s.find("_rebuild_tensor") != std::string::npos && v->items.size() >= 4 && v->items[0]->kind == PVal::STORAGE) {
+          PV t = mk(PVal::TENSOR);
+          t->storage = v->items[0];
+          t->dtype = t->storage->dtype;
+          t->offset = v->items[1]->i;
+          for (auto& x : v->items[2]->items) t->shape.push_back(x->i);
+          for (auto& x : v->items[3]->items) t->stride.push_back(x->i);
+          v = t;
+        } else if (op == 'R' && v->s.find("_rebuild_parameter") != std::string::npos && !v->items.empty() && v->items[0]->kind == PVal::TENSOR) {
+          v = v->items[0];  // Parameter(data, requires_grad, backward_hooks): the tensor itself
+        }
+        st.push_back(v);
+        break;
+      }
+      case 'b': {                                                 // BUILD: obj.__setstate__(state) / obj.__dict__.update(state)
+        PV state = pop();
+        if (!st.empty() && st.back()->kind == PVal::OBJECT) {
+          PV obj = st.back();
+          const bool is_dict = obj->s.find("OrderedDict") != std::string::npos;  // a state_dict's `_metadata`: not an entry
+          PV sd = state;
+          if (state->kind == PVal::TUPLE && state->items.size() == 2 && state->items[0]->kind == PVal::DICT) sd = state->items[0];
+          if (!is_dict && sd->kind == PVal::DICT) for (auto& kv : sd->dict) obj->dict.push_back(kv);
+        }
+        break;
+      }
+      default:
+        err = "unsupported pickle opcode 0x" + std::string(1, "0123456789abcdef"[op >> 4]) + std::string(1, "0123456789abcdef"[op & 15]);
+        return false;
+    }
+  }
+trunc:
+  err = "truncated pickle stream";
+  return false;
+}
+
+static int pt_collect(yb_ckpt* c, const PV& v, const std::string& prefix, const std::map<std::string, const ZipEntry*>& data, const char* path,
+                      int depth) {
+  if (!v || depth > 64) return YB_OK;
+  auto join = [&](const std::string& k) { return prefix.empty() ? k : prefix + "." + k; };
+  auto key_str = [](const PV& k) { return k->kind == PVal::INT ? std::to_string(k->i) : (k->kind == PVal::STR ? k->s : std::string()); };
+  switch (v->kind) {
+    case PVal::TENSOR: {
+      if (prefix.empty()) return YB_OK;
+      CkptTensor t;
+      t.name = prefix;
+      t.dtype = v->dtype;
+      t.shape = v->shape;
+      const int isz = item_size(t.dtype);
+      uint64_t numel = 1;
+      for (auto dsz : t.shape) numel *= (uint64_t)dsz;
+      int64_t expect = 1;  // contiguous row-major strides (dimensions of extent 1 may carry any stride)
+      for (int k = (int)t.shape.size() - 1; k >= 0; k--) {
+        if (t.shape[k] != 1 && numel && v->stride[k] != expect) { set_error(std::string(path) + ": " + t.name + " is not contiguous"); return YB_ERR_NOT_IMPLEMENTED; }
+        expect *= t.shape[k];
+      }
+      auto it = data.find(v->storage->s);
+      if (it == data.end()) { set_error(std::string(path) + ": storage '" + v->storage->s + "' of " + t.name + " is not in the archive"); return YB_ERR_INVALID_ARG; }
+      if (it->second->method != 0) { set_error(std::string(path) + ": compressed zip entries are not supported (torch.save stores)"); return YB_ERR_NOT_IMPLEMENTED; }
+      t.nbytes = (size_t)numel * isz;
+      const uint64_t off = (uint64_t)v->offset * isz;
+      if (off + t.nbytes > it->second->size) { set_error(std::string(path) + ": " + t.name + " exceeds its storage"); return YB_ERR_INVALID_ARG; }
+      t.offset = (size_t)(it->second->data_off + off);
+      c->tensors.push_back(std::move(t));
+      return YB_OK;
+    }
+    case PVal::TUPLE: case PVal::LIST:
+      for (size_t i = 0; i < v->items.size(); i++)
+        if (int rc = pt_collect(c, v->items[i], join(std::to_string(i)), data, path, depth + 1)) return rc;
+      return YB_OK;
+    case PVal::DICT:
+      for (auto& kv : v->dict) {
+        const std::string k = key_str(kv.first);
+        if (k.empty()) continue;
+        if (int rc = pt_collect(c, kv.second, join(k), data, path, depth + 1)) return rc;
+      }
+      return YB_OK;
+    case PVal::OBJECT:
+      for (auto& kv : v->dict) {
+        const std::string k = key_str(kv.first);
+        if (k.empty()) continue;
+        // nn.Module internals: parameters, buffers and sub-modules are named as state_dict() names them
+        const bool transparent = k == "_parameters" || k == "_buffers" || k == "_modules";
+        if (int rc = pt_collect(c, kv.second, transparent ? prefix : join(k), data, path, depth + 1)) return rc;
+      }
+      return YB_OK;
+    default:
+      return YB_OK;
+  }
+}
+
+static int parse_pt(yb_ckpt* c, const char* path) {
+  std::vector<ZipEntry> entries;
+  std::string err;
+  if (!zip_entries(c->blob, entries, err)) { set_error(std::string(path) + ": " + err); return YB_ERR_INVALID_ARG; }
+  const ZipEntry* pkl = nullptr;
+  for (auto& e : entries) if (e.name == "data.pkl" || ends_with(e.name, "/data.pkl")) { pkl = &e; break; }
+  if (!pkl) { set_error(std::string(path) + ": no data.pkl in the archive"); return YB_ERR_INVALID_ARG; }  // reference: ArgumentException (:34)
+  if (pkl->method != 0) { set_error(std::string(path) + ": data.pkl is compressed"); return YB_ERR_NOT_IMPLEMENTED; }
+  if (pkl->size < 2 || c->blob[pkl->data_off] != 0x80) { set_error(std::string(path) + ": not a valid pickle"); return YB_ERR_INVALID_ARG; }  // (:45)
+  const std::string prefix = pkl->name.substr(0, pkl->name.size() - 8);  // "archive/" or ""
+  std::map<std::string, const ZipEntry*> data;
+  for (auto& e : entries)
+    if (e.name.compare(0, prefix.size() + 5, prefix + "data/") == 0) data[e.name.substr(prefix.size() + 5)] = &e;
+  PV root;
+  if (!unpickle(c->blob.data() + pkl->data_off, (size_t)pkl->size, root, err)) { set_error(std::string(path) + ": " + err); return YB_ERR_INVALID_ARG; }
+  return pt_collect(c, root, "", data, path, 0);
+}
+
 static void put_leb(FILE* f, uint64_t v) {
   do {
     uint8_t b = v & 0x7F;
@@ -270,7 +605,7 @@ int32_t yb_ckpt_open(const char* path, yb_ckpt** out) {
   const std::string p(path);
   int rc;
   if (ends_with(p, ".safetensors")) rc = parse_safetensors(c, path);
-  else if (ends_with(p, ".pt") || ends_with(p, ".pth")) { set_error("yb_ckpt_open: Ultralytics .pt pickles are not read natively - convert to .bin / .safetensors"); rc = YB_ERR_NOT_IMPLEMENTED; }
+  else if (ends_with(p, ".pt") || ends_with(p, ".pth")) rc = parse_pt(c, path);
   else rc = parse_bin(c, path);
   if (rc) { delete c; return rc; }
   *out = c;

@@ -655,12 +655,13 @@ def detection_payload_bytes(batch, max_det, row_width):
 
 
 _TORCH_OF_CODE = {0: torch.uint8, 1: torch.int8, 2: torch.int16, 3: torch.int32, 4: torch.int64, 5: torch.float16, 6: torch.float32,
-                  7: torch.float64, 15: torch.bfloat16}
+                  7: torch.float64, 11: torch.bool, 15: torch.bfloat16}
 _CODE_OF_TORCH = {v: k for k, v in _TORCH_OF_CODE.items()}
 
 
 def read_checkpoint(path):
-    """yb_ckpt_*: native reader of TorchSharp .bin / .safetensors files -> ordered dict name -> torch tensor (file dtype)."""
+    """yb_ckpt_*: native reader of TorchSharp .bin, .safetensors and torch.save (.pt / .pth) files -> ordered dict name -> torch
+    tensor (file dtype)."""
     lib = L.lib()
     h = C.c_void_p()
     L.check(lib.yb_ckpt_open(str(path).encode(), C.byref(h)))
