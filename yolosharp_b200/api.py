@@ -67,7 +67,8 @@ class _YoloModule:
     def __init__(self, nc=80, reg_max=16, yoloSize="n", end2end=False, device=0, dtype=torch.float16, max_batch=1,
                  flags=0):
         if end2end:
-            raise NotImplementedError("end2end heads are outside the accelerated path (SURVEY.md §8(f))")
+            raise NotImplementedError("end2end heads are not wired into this façade: run the forward and call engine.topk_postprocess "
+                                      "(yb_topk_postprocess, Head.cs:117-127) on the decoded prediction tensor")
         if reg_max != 16:
             raise ValueError("reg_max must be 16")
         self.nc, self.yoloSize, self.dtype, self.max_batch, self.flags = nc, yoloSize, dtype, max_batch, flags
@@ -84,7 +85,8 @@ class _YoloModule:
 
     def train(self, mode=True):
         if mode:
-            raise NotImplementedError("training (config 4) is not part of this build's hot path yet")
+            raise NotImplementedError("this façade is the inference engine; the training step is yolosharp_b200.train_native.NativeTrainer "
+                                      "(yb_train_step) or train.TrainStepV8 / train_v11.TrainStepV11")
         return self
 
     def load_state_dict(self, state_dict, strict=False):
@@ -300,7 +302,8 @@ class YoloTask:
         self.yolo.LoadModel(path, skipNcNotEqualLayers)
 
     def Train(self):
-        raise NotImplementedError("Train() is outside this build's hot path (SURVEY.md §8 row a18 = next)")
+        raise NotImplementedError("Train() needs the reference's dataset pipeline (out of scope, DESIGN.md §8); the step it would run per "
+                                  "batch is train_native.NativeTrainer.step and the epoch loop is train.fit")
 
     def ImagePredict(self, image, predictThreshold=None, iouThreshold=None) -> List[YoloResult]:
         if isinstance(image, str):
