@@ -207,3 +207,38 @@ def test_pt_whole_yolo_model_object(tmp_path):
     assert set(got) == set(want) and len(got) == 501
     for k, v in want.items():
         assert got[k].dtype == v.dtype and torch.equal(got[k], v), k
+
+
+@pytest.mark.parametrize("kind", ["bin", "pt", "pt_module"])
+def test_checkpoint_readers_survive_corruption(tmp_path, kind):
+    """Truncated or bit-flipped files must come back as an error (or as a successfully parsed file), never as a crash: the
+    readers bounds-check every length they take from the file."""
+    import random
+    sd = {"a.weight": torch.randn(4, 3, 3, 3), "a.bias": torch.randn(4).half(), "n": torch.tensor([5])}
+    if kind == "bin":
+        p = str(tmp_path / "x.bin")
+        E.write_checkpoint_bin(p, sd)
+    elif kind == "pt":
+        p = str(tmp_path / "x.pt")
+        torch.save({"model": sd, "epoch": 3}, p)
+    else:
+        p = str(tmp_path / "x.pt")
+        torch.save({"model": torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8))}, p, pickle_protocol=4)
+    raw = open(p, "rb").read()
+    rng = random.Random(0)
+    q = str(tmp_path / ("f" + os.path.splitext(p)[1]))
+    outcomes = {"ok": 0, "err": 0}
+    for it in range(200):
+        b = bytearray(raw)
+        if it % 2:
+            b = b[: rng.randrange(0, len(b))]
+        else:
+            for _ in range(rng.randrange(1, 8)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+        open(q, "wb").write(bytes(b))
+        try:
+            E.read_checkpoint(q)
+            outcomes["ok"] += 1
+        except (YbError, KeyError):  # KeyError: a corrupted dtype code the Python table does not know
+            outcomes["err"] += 1
+    assert outcomes["err"] >= 90  # every truncation is an error

@@ -676,7 +676,7 @@ def read_checkpoint(path):
                 t = torch.frombuffer(bytearray(C.string_at(data.value, nb.value)), dtype=td).reshape(shape)
             else:
                 t = torch.empty(shape, dtype=td)
-            out[name.value.decode()] = t
+            out[name.value.decode("utf-8", errors="replace")] = t
     finally:
         lib.yb_ckpt_close(h)
     return out
