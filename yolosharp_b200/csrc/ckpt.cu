@@ -25,6 +25,7 @@
 //                                                                 ReadTensorsInfoFromFile ends in `ExtractTensors(null)`, :46,
 //                                                                 i.e. returns no tensors at this commit; it is only used by
 //                                                                 the offline converter Tools.TransModelFromPickle.)
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -281,7 +282,7 @@ static bool zip_entries(const std::vector<uint8_t>& b, std::vector<ZipEntry>& ou
     const uint64_t z = rd64(&b[eocd - 20 + 8]);
     if (z + 56 <= n && rd32(&b[z]) == 0x06064b50u) { count = rd64(&b[z + 32]); cd_size = rd64(&b[z + 40]); cd_off = rd64(&b[z + 48]); }
   }
-  if (cd_off + cd_size > n) { err = "central directory out of range"; return false; }
+  if (cd_off > n || cd_size > n || cd_off + cd_size > n) { err = "central directory out of range"; return false; }
   size_t p = (size_t)cd_off;
   for (uint64_t i = 0; i < count; i++) {
     if (p + 46 > n || rd32(&b[p]) != 0x02014b50u) { err = "bad central directory entry"; return false; }
@@ -295,16 +296,17 @@ static bool zip_entries(const std::vector<uint8_t>& b, std::vector<ZipEntry>& ou
       const uint16_t id = rd16(&b[x]), sz = rd16(&b[x + 2]);
       if (id == 0x0001) {
         size_t q = x + 4;
-        if (usize == 0xffffffffu && q + 8 <= x + 4 + sz) { usize = rd64(&b[q]); q += 8; }
-        if (csize == 0xffffffffu && q + 8 <= x + 4 + sz) { csize = rd64(&b[q]); q += 8; }
-        if (lho == 0xffffffffu && q + 8 <= x + 4 + sz) { lho = rd64(&b[q]); q += 8; }
+        const size_t lim = std::min(x + 4 + (size_t)sz, p + 46 + nl + xl);
+        if (usize == 0xffffffffu && q + 8 <= lim) { usize = rd64(&b[q]); q += 8; }
+        if (csize == 0xffffffffu && q + 8 <= lim) { csize = rd64(&b[q]); q += 8; }
+        if (lho == 0xffffffffu && q + 8 <= lim) { lho = rd64(&b[q]); q += 8; }
       }
       x += 4 + (size_t)sz;
     }
-    if (lho + 30 > n || rd32(&b[lho]) != 0x04034b50u) { err = "bad local header of " + e.name; return false; }
+    if (lho > n || lho + 30 > n || rd32(&b[lho]) != 0x04034b50u) { err = "bad local header of " + e.name; return false; }
     e.data_off = lho + 30 + rd16(&b[lho + 26]) + rd16(&b[lho + 28]);
     e.size = usize;
-    if (e.method == 0 && e.data_off + e.size > n) { err = "entry " + e.name + " out of range"; return false; }
+    if (e.method == 0 && (e.data_off > n || e.size > n || e.data_off + e.size > n)) { err = "entry " + e.name + " out of range"; return false; }
     (void)csize;
     out.push_back(std::move(e));
     p += 46 + nl + xl + cl;
@@ -509,7 +511,11 @@ trunc:
 
 static int pt_collect(yb_ckpt* c, const PV& v, const std::string& prefix, const std::map<std::string, const ZipEntry*>& data, const char* path,
                       int depth) {
+  // a corrupted memo reference can make the object graph cyclic or heavily shared: bound the depth and the total work
+  static thread_local long long budget = 0;
+  if (depth == 0) budget = 4000000;
   if (!v || depth > 64) return YB_OK;
+  if (--budget < 0) { set_error(std::string(path) + ": object graph too large (cyclic pickle?)"); return YB_ERR_INVALID_ARG; }
   auto join = [&](const std::string& k) { return prefix.empty() ? k : prefix + "." + k; };
   auto key_str = [](const PV& k) { return k->kind == PVal::INT ? std::to_string(k->i) : (k->kind == PVal::STR ? k->s : std::string()); };
   switch (v->kind) {
@@ -520,8 +526,16 @@ static int pt_collect(yb_ckpt* c, const PV& v, const std::string& prefix, const 
       t.dtype = v->dtype;
       t.shape = v->shape;
       const int isz = item_size(t.dtype);
+      if (!isz || !v->storage || v->stride.size() != t.shape.size() || t.shape.size() > 16 || v->offset < 0) {
+        set_error(std::string(path) + ": malformed tensor record for " + t.name);
+        return YB_ERR_INVALID_ARG;
+      }
       uint64_t numel = 1;
-      for (auto dsz : t.shape) numel *= (uint64_t)dsz;
+      for (auto dsz : t.shape) {
+        if (dsz < 0 || (dsz > 0 && numel > (uint64_t)1 << 40)) { set_error(std::string(path) + ": bad shape of " + t.name); return YB_ERR_INVALID_ARG; }
+        numel *= (uint64_t)dsz;
+      }
+      if (numel > (uint64_t)1 << 40 || (uint64_t)v->offset > (uint64_t)1 << 40) { set_error(std::string(path) + ": bad extent of " + t.name); return YB_ERR_INVALID_ARG; }
       int64_t expect = 1;  // contiguous row-major strides (dimensions of extent 1 may carry any stride)
       for (int k = (int)t.shape.size() - 1; k >= 0; k--) {
         if (t.shape[k] != 1 && numel && v->stride[k] != expect) { set_error(std::string(path) + ": " + t.name + " is not contiguous"); return YB_ERR_NOT_IMPLEMENTED; }
