@@ -103,7 +103,9 @@ int32_t yb_load_tensor(yb_engine* e, const char* name, int32_t dtype, int32_t nd
  * state_dict() names - an Ultralytics checkpoint gives "model.model.0.conv.weight", ...) and `SaveWeight`
  * (Models/YoloBaseTaskModel.cs:470-490).  The format is chosen by the file extension (`.safetensors`, `.pt` / `.pth`,
  * anything else = `.bin`).  dtype codes are torch ScalarType values (yb_dtype; also 1 i8, 2 i16, 3 i32, 4 i64, 7 f64, 11 bool).
- *   yb_load_checkpoint  = open + yb_load_tensor for every f16 / f32 / bf16 tensor (+ counts of loaded tensors and of
+ *   yb_load_checkpoint  = open + yb_load_tensor for every f16 / f32 / bf16 tensor; when no name of the file is an expected
+ *                         name but the names are after dropping a leading "model." (an Ultralytics {'model': object}
+ *                         checkpoint), that level is dropped (+ counts of loaded tensors and of
  *                         expected tensors the file lacks; unlike YoloBaseTaskModel.cs:32-35 nothing falls back to
  *                         random weights: yb_finalize_weights fails on the first missing tensor)
  *   yb_ckpt_*           iterate a file without an engine; pointers stay valid until yb_ckpt_close */

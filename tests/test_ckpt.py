@@ -242,3 +242,17 @@ def test_checkpoint_readers_survive_corruption(tmp_path, kind):
         except (YbError, KeyError):  # KeyError: a corrupted dtype code the Python table does not know
             outcomes["err"] += 1
     assert outcomes["err"] >= 90  # every truncation is an error
+
+
+def test_engine_load_checkpoint_from_ultralytics_style_pt(tmp_path):
+    """{'model': <model object>} checkpoints name their tensors "model.<state_dict key>": yb_load_checkpoint drops that level
+    when nothing matches as it stands."""
+    import yolosharp_b200 as y
+    from tests.util import oracle_model
+    from yolosharp_b200 import _lib as L
+    p = str(tmp_path / "u.pt")
+    torch.save({"model": oracle_model("v8", "detect", "n").half(), "epoch": -1}, p)
+    e = y.Engine("v8", "n", "detect", 80, "f16", 0, 1, 64, 64, flags=L.YB_FLAG_DRY_RUN)
+    loaded, missing = e.load_checkpoint(p)
+    assert missing == 0 and loaded >= len(e.expected_tensors())
+    e.close()

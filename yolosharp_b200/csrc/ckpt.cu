@@ -650,11 +650,24 @@ int32_t yb_load_checkpoint(yb_engine* e, const char* path, int32_t* n_loaded, in
   if (rc) return rc;
   int loaded = 0;
   std::vector<std::string> have;
+  // an Ultralytics checkpoint pickles {'model': <model object>}: its tensors arrive as "model.<state_dict key>".  When no
+  // tensor of the file carries an expected name as it stands but the names do after dropping that first "model." level,
+  // drop it (the reference goes the other way round with PickleLoader.Load(fileName, addString), PickleLoader.cs:438-465)
+  std::vector<std::string> expected;
+  for (int i = 0, n = yb_num_expected_tensors(e); i < n; i++) expected.push_back(yb_expected_tensor_name(e, i));
+  auto is_expected = [&](const std::string& k) { return std::find(expected.begin(), expected.end(), k) != expected.end(); };
+  int direct = 0, stripped = 0;
+  for (const CkptTensor& t : c->tensors) {
+    if (is_expected(t.name)) direct++;
+    else if (t.name.compare(0, 6, "model.") == 0 && is_expected(t.name.substr(6))) stripped++;
+  }
+  const bool strip = direct == 0 && stripped > 0;
   for (const CkptTensor& t : c->tensors) {
     if (t.dtype != YB_F16 && t.dtype != YB_F32 && t.dtype != YB_BF16) continue;  // num_batches_tracked (int64) etc.
-    rc = yb_load_tensor(e, t.name.c_str(), t.dtype, (int32_t)t.shape.size(), t.shape.data(), t.nbytes ? c->blob.data() + t.offset : nullptr);
+    const std::string name = strip && t.name.compare(0, 6, "model.") == 0 ? t.name.substr(6) : t.name;
+    rc = yb_load_tensor(e, name.c_str(), t.dtype, (int32_t)t.shape.size(), t.shape.data(), t.nbytes ? c->blob.data() + t.offset : nullptr);
     if (rc) break;
-    have.push_back(t.name);
+    have.push_back(name);
     loaded++;
   }
   int missing = 0;
