@@ -97,3 +97,21 @@ def test_native_train_step_u8_images_and_second_step():
     f = NativeTrainer(m.state_dict(), "v8", "n", 80, device="cuda", max_batch=2, height=64, width=96, lr=1e-3)
     j1 = f.step(u8.float().mul(1 / 255.0), _targets(2))
     torch.testing.assert_close(j1, i1, rtol=1e-6, atol=1e-7)
+
+
+def test_load_state_dict_skip_nc_not_equal_layers_cpu():
+    """LoadModel(path, skipNcNotEqualLayers: true) (YoloBaseTaskModel.cs:82-92) on the trainer's flat buffers: an 80-class
+    checkpoint into a 3-class trainer leaves every model.22.cv3 tensor untouched and loads the rest."""
+    from yolosharp_b200.train_native import NativeTrainer, nc_skip_list
+    sd80 = oracle_model("v8", "detect", "n").state_dict()
+    assert nc_skip_list(sd80, 80) == []
+    skip = nc_skip_list(sd80, 3)
+    assert len(skip) == 42 and all(k.startswith("model.22.cv3.") for k in skip) and skip[-1] == "model.22.cv3.2.2.bias"
+    t = NativeTrainer(None, "v8", "n", 3, device="cpu")  # dry run: layout only; give it host buffers
+    t.flat = torch.full((sum(c for _, c, _ in t.params.values()),), 7.0)
+    t.running = torch.zeros(sum(c for _, c, _ in t.stats.values()))
+    with pytest.raises(ValueError):
+        t.load_state_dict(sd80)
+    assert t.load_state_dict(sd80, skipNcNotEqualLayers=True) == skip
+    assert float(t.p("model.22.cv3.1.2.weight").min()) == 7.0 and torch.equal(t.p("model.0.conv.weight"), sd80["model.0.conv.weight"])
+    assert torch.equal(t.p("model.22.cv2.0.0.conv.weight"), sd80["model.22.cv2.0.0.conv.weight"])

@@ -12,6 +12,21 @@ import torch
 from . import _lib as L
 
 
+def nc_skip_list(state_dict, nc):
+    """The `skipList` of `LoadModel(path, skipNcNotEqualLayers: true)` for a Detect head (Models/YoloBaseTaskModel.cs:82-92):
+    the head is the last `model.<i>` of the checkpoint; the class count of the checkpoint is the row count of the LAST key matching
+    `model\\.<i>\\.cv3.+bias`; when it differs from `nc`, every key matching `model\\.<i>\\.cv3` is skipped."""
+    import re
+    idx = [int(m.group(1)) for m in (re.match(r"model\.(\d+)\.", k) for k in state_dict) if m]
+    if not idx:
+        return []
+    pat = rf"model\.{max(idx)}\.cv3"
+    bias_keys = [k for k in state_dict if re.search(pat + r".+bias", k)]
+    if not bias_keys or int(state_dict[bias_keys[-1]].shape[0]) == nc:
+        return []
+    return [k for k in state_dict if re.search(pat, k)]
+
+
 class NativeTrainer:
     def __init__(self, state_dict, arch="v8", size="n", nc=80, device="cuda", max_batch=16, height=640, width=640, lr=None,
                  weight_decay=5e-4):
@@ -45,15 +60,24 @@ class NativeTrainer:
             out[name.value.decode()] = (off.value, cnt.value, tuple(shp[j] for j in range(nd.value)))
         return out
 
-    def load_state_dict(self, sd):
-        missing = [k for k in list(self.params) + list(self.stats) if k not in sd]
+    def load_state_dict(self, sd, skipNcNotEqualLayers=False):
+        """`yolo.load_state_dict(state_dict, skip: skipList, strict: false)` as `LoadModel` calls it
+        (Models/YoloBaseTaskModel.cs:27-114).  skipNcNotEqualLayers: when the checkpoint's class count (rows of the last cv3
+        bias of the Detect head) differs from this trainer's, every `model.<head>.cv3...` tensor is left as it is in the
+        buffers (:82-92: the reference keeps the freshly constructed head there) - load a randomly initialised state_dict of
+        the target class count first, then the checkpoint with this flag.  -> list of skipped keys."""
+        skip = nc_skip_list(sd, self.nc) if skipNcNotEqualLayers else []
+        missing = [k for k in list(self.params) + list(self.stats) if k not in sd and k not in skip]
         if missing:
             raise KeyError(f"state_dict lacks {len(missing)} tensors of the model, e.g. {missing[:3]}")
         for table, buf in ((self.params, self.flat), (self.stats, self.running)):
             for k, (o, c, shp) in table.items():
+                if k in skip:
+                    continue
                 if tuple(sd[k].shape) != shp:
                     raise ValueError(f"{k}: shape {tuple(sd[k].shape)} != {shp}")
                 buf[o:o + c].copy_(sd[k].detach().reshape(-1).to(device=self.device, dtype=torch.float32))
+        return skip
 
     def p(self, k):
         table, buf = (self.params, self.flat) if k in self.params else (self.stats, self.running)
