@@ -242,6 +242,29 @@ def test_fit_loop_learning_rates():
     assert abs(st2.calls[30][1] - d) < 1e-15 and st2.calls[31] == st2.calls[30] == st2.calls[-1]   # ni = 100 is the last update
 
 
+def test_early_stopping_and_epoch_tail():
+    """Utils/EarlyStopping.cs and the tail of the reference's epoch (YoloBaseTaskModel.cs:184-207): fitness = -sum(val loss),
+    best.bin when it improves, stop after `patience` epochs without improvement, no last.bin for the stopping epoch."""
+    from yolosharp_b200.train import EarlyStopping, fit
+    es = EarlyStopping(patience=2)
+    # negative fitness: the first epoch becomes the best although best_fitness starts at 0 (the `== 0` clause)
+    assert [es.ShouldStop(f, e) for e, f in enumerate([-5.0, -4.0, -4.5, -4.2, -4.1], start=1)] == [False, False, False, True, True]
+    assert es.best_epoch == 2 and es.best_fitness == -4.0
+    es0 = EarlyStopping(patience=0)
+    assert es0.ShouldStop(-1.0, 1) is True  # delta 0 >= patience 0: the reference's literal behaviour for patience = 0
+
+    class FakeStep:
+        lr = 1e-3
+
+        def step(self, images, targets, lrs=None):
+            return torch.tensor([1.0, 1.0, 1.0])
+    val = {1: [3.0, 1.0, 1.0], 2: [2.0, 1.0, 1.0], 3: [2.5, 1.0, 1.0], 4: [2.6, 1.0, 1.0], 5: [1.0, 1.0, 1.0]}
+    best, ends = [], []
+    hist = fit(FakeStep(), [(None, torch.zeros(1, 6))] * 3, epochs=5, validate=lambda e: val[e], patience=2, on_best=best.append,
+               on_epoch_end=ends.append)
+    assert best == [1, 2] and ends == [1, 2, 3] and len(hist) == 4  # epoch 4: two epochs without improvement -> stop before last.bin
+
+
 @pytest.mark.gpu
 def test_train_step_v11_kernels_gpu():
     """The same comparison with the library's kernels (csrc/train_v11.cu: depthwise conv + attention forward / backward,

@@ -430,7 +430,24 @@ class TrainStepV8:
         return items
 
 
-def fit(step, batches, epochs, lrf=0.01, warmup_epochs=3, warmup_bias_lr=0.1, cos_lr=False, on_iteration=None, group=None):
+class EarlyStopping:
+    """Utils/EarlyStopping.cs:3-40, restated.  `fitness` is whatever Train() feeds it: -sum(validation loss items)
+    (YoloBaseTaskModel.cs:186), i.e. negative - the first epoch always becomes the best one because best_fitness starts at 0
+    and `best_fitness == 0` counts as "no best yet" (:21)."""
+
+    def __init__(self, patience=50):
+        self.best_fitness, self.best_epoch, self.patience, self.possible_stop = 0.0, 0, float(patience), False
+
+    def ShouldStop(self, fitness, epoch):
+        if fitness > self.best_fitness or self.best_fitness == 0:
+            self.best_epoch, self.best_fitness = epoch, fitness
+        delta = epoch - self.best_epoch
+        self.possible_stop = delta >= (self.patience - 1)
+        return delta >= self.patience
+
+
+def fit(step, batches, epochs, lrf=0.01, warmup_epochs=3, warmup_bias_lr=0.1, cos_lr=False, on_iteration=None, group=None,
+        validate=None, patience=50, on_best=None, on_epoch_end=None):
     """The reference's epoch loop around the training step, restated index for index
     (YoloBaseTaskModel.cs:167-170 Train, :291-356 TrainEpoch):
       * epochs run 1 .. Epochs; inside an epoch `i` counts the EXECUTED batches only (the `continue` of a target-less
@@ -444,13 +461,18 @@ def fit(step, batches, epochs, lrf=0.01, warmup_epochs=3, warmup_bias_lr=0.1, co
     skip it alone - a batch is skipped only when EVERY rank of `group` has no targets (one all-reduce of a flag per
     iteration); a rank with an empty shard calls step() with zero targets (the loss kernels handle n_targets = 0).
     `batches` is a re-iterable of (images (B,3,H,W) float32 on the device, targets (n,6)) - data loading and
-    augmentation are outside this library.  Returns the per-epoch mean of the loss items."""
+    augmentation are outside this library.  Returns the per-epoch mean of the loss items.
+    The tail of the reference's epoch (YoloBaseTaskModel.cs:184-207) is available through callbacks: `validate(epoch)` ->
+    validation loss items; fitness = -sum(items) (:186); `on_best(epoch)` when it beats the best so far (best.bin, :188-194,
+    best_fitness starts at float.MinValue, :118); EarlyStopping(patience).ShouldStop(fitness, epoch) ends the run BEFORE
+    `on_epoch_end(epoch)` (last.bin, :205) of that epoch, as the reference's `break` does (:198-203)."""
     lam = lr_lambda_onecycle if cos_lr else lr_lambda_linear
     nb = len(batches)
     nw = max(warmup_epochs * nb, 100)
     dp = group is not False and torch.distributed.is_available() and torch.distributed.is_initialized() and \
         torch.distributed.get_world_size(group) > 1
     history = []
+    stopper, best_fitness = EarlyStopping(patience), float("-inf")
     lrs = (step.lr * lam(0, lrf, epochs),) * 2  # LambdaLR construction: InitialLR * lambda(0)
     for epoch in range(1, epochs + 1):
         total, count, i = None, 0, 0
@@ -461,7 +483,8 @@ def fit(step, batches, epochs, lrf=0.01, warmup_epochs=3, warmup_bias_lr=0.1, co
                 lrs = w
             has = len(targets) >= 1
             if dp:
-                flag = torch.tensor([1.0 if has else 0.0], device=step.P.grad.device if hasattr(step, "P") else "cpu")
+                flag = torch.tensor([1.0 if has else 0.0],
+                                    device=step.P.grad.device if hasattr(step, "P") else getattr(step, "device", "cpu"))
                 torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX, group=group)
                 has = bool(flag.item() > 0)
             if not has:
@@ -474,4 +497,14 @@ def fit(step, batches, epochs, lrf=0.01, warmup_epochs=3, warmup_bias_lr=0.1, co
             i += 1
         lrs = (step.lr * lam(epoch, lrf, epochs),) * 2  # lr_scheduler.step() after the epoch
         history.append(total / max(count, 1) if total is not None else None)
+        if validate is not None:
+            fitness = -float(sum(float(v) for v in validate(epoch)))
+            if fitness > best_fitness:
+                best_fitness = fitness
+                if on_best is not None:
+                    on_best(epoch)
+            if stopper.ShouldStop(fitness, epoch):
+                break
+        if on_epoch_end is not None:
+            on_epoch_end(epoch)
     return history
