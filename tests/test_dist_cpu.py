@@ -212,6 +212,48 @@ def test_fit_with_an_empty_shard_world2():
     assert sorted(res) == [(0, True), (1, True)]
 
 
+class _FakeStep:
+    lr = 1e-3
+
+    def step(self, images, targets, lrs=None):
+        return torch.tensor([1.0, 1.0, 1.0])
+
+
+def _fit_early_stop_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from yolosharp_b200.train import fit
+        # alone, rank 0 (best epoch 2) would stop in epoch 4 and rank 1 (best epoch 3) in epoch 5; summed over the ranks the
+        # best epoch is 3 and patience 2 ends the run in epoch 5 on BOTH
+        val = {0: {1: 5.0, 2: 4.0, 3: 4.5, 4: 4.6, 5: 4.7, 6: 1.0}, 1: {1: 5.0, 2: 4.6, 3: 4.0, 4: 4.3, 5: 4.4, 6: 1.0}}[rank]
+        best, ends = [], []
+        hist = fit(_FakeStep(), [(None, torch.zeros(1, 6))] * 2, epochs=6, validate=lambda e: [val[e]], patience=2, on_best=best.append,
+                   on_epoch_end=ends.append)
+        q.put((rank, best, ends, len(hist)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fit_early_stopping_is_collective_world2():
+    """Each rank validates its own shard; the fitness is summed over the ranks before EarlyStopping sees it, so every rank
+    leaves the epoch loop in the same epoch (a rank that stopped alone would leave the others hanging in the next all-reduce)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fit_early_stop_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    # summed losses: 10.0, 8.6, 8.5, 8.9, 9.1 -> best at 1, 2, 3; epochs 4 and 5 do not improve: stop in epoch 5, no last.bin for it
+    assert res[0][1:] == res[1][1:]
+    assert res[0][1] == [1, 2, 3] and res[0][2] == [1, 2, 3, 4] and res[0][3] == 5
+
+
 def _gather_packed_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

@@ -499,6 +499,11 @@ def fit(step, batches, epochs, lrf=0.01, warmup_epochs=3, warmup_bias_lr=0.1, co
         history.append(total / max(count, 1) if total is not None else None)
         if validate is not None:
             fitness = -float(sum(float(v) for v in validate(epoch)))
+            if dp:  # every rank validated its own shard: the decision to stop (and what counts as best) must be collective
+                f = torch.tensor([fitness], dtype=torch.float64,
+                                 device=step.P.grad.device if hasattr(step, "P") else getattr(step, "device", "cpu"))
+                torch.distributed.all_reduce(f, group=group)
+                fitness = float(f.item())
             if fitness > best_fitness:
                 best_fitness = fitness
                 if on_best is not None:
