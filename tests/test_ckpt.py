@@ -256,3 +256,28 @@ def test_engine_load_checkpoint_from_ultralytics_style_pt(tmp_path):
     loaded, missing = e.load_checkpoint(p)
     assert missing == 0 and loaded >= len(e.expected_tensors())
     e.close()
+
+
+def test_convert_checkpoint_tool(tmp_path):
+    """tools/convert_checkpoint.py: an Ultralytics-style .pt becomes a .bin that loads into the engine (dry run)."""
+    import subprocess
+    import sys
+
+    import yolosharp_b200 as y
+    from tests.util import oracle_model
+    from yolosharp_b200 import _lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src, dst = str(tmp_path / "u.pt"), str(tmp_path / "u.bin")
+    m = oracle_model("v8", "detect", "n")
+    torch.save({"model": m, "epoch": 3}, src)
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "convert_checkpoint.py"), src, dst, "--strip", "model.", "--half"])
+    got = E.read_checkpoint(dst)
+    want = m.state_dict()
+    assert list(got) == list(want)
+    for k, v in want.items():
+        ref = v.half() if v.dtype == torch.float32 else v
+        assert got[k].dtype == ref.dtype and torch.equal(got[k], ref), k
+    e = y.Engine("v8", "n", "detect", 80, "f16", 0, 1, 64, 64, flags=L.YB_FLAG_DRY_RUN)
+    loaded, missing = e.load_checkpoint(dst)
+    assert missing == 0
+    e.close()
